@@ -1,0 +1,77 @@
+"""Pins oracle/svjg_oracle.py to outputs of the unmodified reference
+(tests/golden/, produced by tests/golden/make_golden.py)."""
+import hashlib
+import json
+
+import pytest
+
+from conftest import alt_len_from_gfa_text, read_golden
+from oracle import svjg_oracle as O
+
+
+def test_kat40_expected_genotype_rows():
+    rows = read_golden("kat40.tsv").splitlines()
+    assert len(rows) == 40
+    for row in rows:
+        _vid, svtype, n0, n1, sample = row.split("\t")
+        gt, dp, ad, pl = O.genotype_counts(int(n0), int(n1), svtype)
+        assert f"{gt}:{dp}:{ad}:{','.join(pl)}" == sample, row
+
+
+def test_likelihood_random_vectors():
+    n = 0
+    for row in read_golden("lik_random.tsv.gz").splitlines():
+        t, a, b, ms, e, geno, dp, numbers, prob = row.split("\t")
+        gt, dp2, ad, pl = O.genotype_counts(int(a), int(b), t, int(ms), float(e))
+        assert (gt, dp2, ad, ",".join(pl)) == (geno, dp, numbers, prob), row
+        n += 1
+    assert n == 30000
+
+
+@pytest.mark.parametrize("case_idx", range(32))
+def test_quirk_cases(quirks, case_idx):
+    if case_idx >= len(quirks["cases"]):
+        pytest.skip("no such case")
+    case = quirks["cases"][case_idx]
+    edges = json.loads(quirks["edges"])
+    alt = alt_len_from_gfa_text(quirks["gfa"])
+    lines = case["gaf"].splitlines(True)
+    if case["rc"] == 0:
+        got = O.dumps_informative(O.filter_alignments(lines, edges, alt))
+        assert got == case["json"], case["name"]
+    else:
+        with pytest.raises(O.OracleInputError):
+            O.filter_alignments(lines, edges, alt)
+
+
+def test_quirk_case_count(quirks):
+    assert 25 <= len(quirks["cases"]) <= 32
+
+
+def test_c1_filter_and_genotype_byte_equal():
+    edges = json.loads(read_golden("c1_svs_edges.json"))
+    alt = alt_len_from_gfa_text(read_golden("c1.gfa.gz"))
+    assert len(edges) == 118 and len(alt) == 11
+    lines = read_golden("c1.gaf.gz").splitlines(True)
+    d = O.filter_alignments(lines, edges, alt)
+    assert O.dumps_informative(d) == read_golden("c1_informative_aln.json.gz")
+    vcf_lines = read_golden("c1.vcf").splitlines(True)
+    text, n = O.genotype_vcf(O.hit_counts(d), vcf_lines)
+    assert text == read_golden("c1_genotype.vcf")
+    assert f"Genotyped svs: {n}\n" == read_golden("c1_stdout.txt")
+    text2, _ = O.genotype_vcf(O.hit_counts(d), vcf_lines, 40, 0.001)
+    assert text2 == read_golden("c1_genotype_ms40_e1e-3.vcf")
+
+
+@pytest.mark.parametrize("tag", ["s2", "s3", "s4"])
+def test_scaled_configs_byte_equal(tag):
+    edges = json.loads(read_golden(f"{tag}_svs_edges.json.gz"))
+    alt = alt_len_from_gfa_text(read_golden(f"{tag}.gfa.gz"))
+    lines = read_golden(f"{tag}.gaf.gz").splitlines(True)
+    d = O.filter_alignments(lines, edges, alt)
+    js = O.dumps_informative(d)
+    assert hashlib.sha256(js.encode()).hexdigest() == read_golden(f"{tag}_informative_aln.sha256").strip()
+    assert {k: list(v) for k, v in O.hit_counts(d).items()} == json.loads(read_golden(f"{tag}_counts.json.gz"))
+    text, n = O.genotype_vcf(O.hit_counts(d), read_golden(f"{tag}.vcf.gz").splitlines(True))
+    assert text == read_golden(f"{tag}_genotype.vcf.gz")
+    assert f"Genotyped svs: {n}\n" == read_golden(f"{tag}_stdout.txt")
