@@ -1,0 +1,148 @@
+/* svjg.h — C ABI of libsvjg.so: the B200-native post-mapping hot path of
+ * SVJedi-graph (informative-alignment filter + per-SV allele counts + genotype
+ * likelihoods).
+ *
+ * The reference has no in-process plugin API: its boundary is two CLI stages
+ * glued by files (svjedi-graph.py:113-128).  Each entry point below cites the
+ * reference code it replaces (paths relative to the reference checkout).
+ * Plain pointers and sizes only; no torch types.  Pointers named d_* are CUDA
+ * device pointers owned by the caller; everything else is host memory.
+ *
+ * Every function returns 0 (SVJG_OK) or a non-zero SVJG_E_* code; a drop-in
+ * front-end turns any non-zero code into process exit status 1, which is what
+ * the reference's uncaught Python exceptions produce (svjedi-graph.py:117,127).
+ * svjg_last_error() gives a human-readable message for the calling thread.
+ */
+#ifndef SVJG_H
+#define SVJG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVJG_OK 0
+#define SVJG_E_CUDA 1          /* CUDA runtime failure                                */
+#define SVJG_E_ARG 2           /* bad argument (NULL, misaligned, too large)          */
+#define SVJG_E_IO 3            /* file could not be read / written                    */
+#define SVJG_E_JSON 4          /* <prefix>_svs_edges.json is not the expected JSON    */
+#define SVJG_E_INPUT 5         /* input on which the reference raises (exit status 1) */
+#define SVJG_E_HITS_OVERFLOW 6 /* hit buffers too small: re-run with >= n_hits slots  */
+#define SVJG_E_NOMEM 7
+
+/* reason codes stored in svjg_filter_stats.status when a GAF line would make the
+ * reference raise */
+#define SVJG_BAD_COLUMNS 1   /* blank line / fewer than 12 columns  (filter-alignments.py:185-187) */
+#define SVJG_BAD_INT 2       /* non-integer numeric column          (:189-191)                     */
+#define SVJG_BAD_ALEN 3      /* Alen == 0 and no id:f: tag          (:196)                         */
+#define SVJG_BAD_PATH 4      /* empty path, or token with nothing in front of it (:206, :366)      */
+#define SVJG_BAD_ALTNODE 5   /* alt node of a hit record missing from the GFA (:346)               */
+#define SVJG_BAD_NODENAME 6  /* reference-node name without start-end (:342, :349)                 */
+#define SVJG_BAD_ENTRY 7     /* sv id without ':' or allele not 0/1 in svs_edges (:160, :166)      */
+#define SVJG_BAD_SHORTLINE 8 /* a line shorter than 16 bytes (cannot hold 12 columns)              */
+#define SVJG_BAD_RANGE 9     /* integer beyond 18 digits (unsupported; the reference has bigints)  */
+
+typedef struct svjg_tables svjg_tables;
+
+const char *svjg_version(void);
+const char *svjg_last_error(void);
+
+/* ---- graph tables --------------------------------------------------------
+ * Replaces filter-alignments.py:95-98 (json.load of <prefix>_svs_edges.json into
+ * d_link_sv) and :103-113 (alt-node length scan of the GFA).  Builds, on the
+ * host, a hash of link key -> [(sv index, allele)] and a hash of alt-node name
+ * -> sequence length; sv indices are ranks in the byte-sorted list of distinct
+ * sv ids (the order json.dumps(sort_keys=True) prints them, :175). */
+int svjg_tables_load(const char *svs_edges_json_path, const char *gfa_path, svjg_tables **out);
+int svjg_tables_from_memory(const char *edges_json, size_t edges_len, const char *gfa, size_t gfa_len,
+                            svjg_tables **out);
+void svjg_tables_free(svjg_tables *t);
+uint32_t svjg_tables_num_sv(const svjg_tables *t);
+uint32_t svjg_tables_num_links(const svjg_tables *t);     /* distinct link keys        */
+uint32_t svjg_tables_num_alt_nodes(const svjg_tables *t);
+uint64_t svjg_tables_device_bytes(const svjg_tables *t);  /* size of the device image  */
+/* sv id string of index i (not NUL terminated); NULL when i is out of range */
+const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len);
+/* index of an sv id, or UINT32_MAX — what `in_sv in dict` needs (predict-genotype.py:216) */
+uint32_t svjg_tables_find_sv(const svjg_tables *t, const char *sv_id, uint32_t len);
+/* copies the device image to `device` (cudaMalloc inside; freed by svjg_tables_free) */
+int svjg_tables_to_device(svjg_tables *t, int device);
+
+/* ---- filter + count (kernels 1-3) ------------------------------------------
+ * Replaces the whole per-line loop filter-alignments.py:123-166: line split and
+ * integer parse (read_gaf_line :184-198), path tokenising (extract_nodes
+ * :351-373), strands and links (get_aln_links :200-219), forward / reverse key
+ * probes (:141-148), the breakpoint-overlap test (check_bkpt_overlap :258-273,
+ * get_node_len :343-349) and the append (:160-166), which becomes
+ *   d_counts[2*sv + allele] += 1          (what predict-genotype.py:219-226 counts)
+ *   hit (2*sv + allele, line offset, line length)   appended at an atomic cursor.
+ * The text the reference stores per hit (:166) is gaf[off : off+len] cut at the
+ * first "cg:Z:" — svjg_emit_informative_json() does that cut when it prints.
+ *
+ * d_gaf must be 16-byte aligned; n_bytes < 2^32 (shard larger files by lines).
+ * d_counts (2*num_sv u32) and d_stats are ACCUMULATED, so several shards can be
+ * filtered into one set of counters: clear them first with svjg_filter_reset().
+ * Asynchronous on `stream` (a cudaStream_t); nothing is read back. */
+typedef struct svjg_filter_stats {
+    uint64_t n_hits;     /* hits produced; > hit_cap means the tail was dropped  */
+    uint64_t n_records;  /* GAF lines seen                                       */
+    uint64_t n_multi;    /* lines whose path has >= 2 nodes (:133)               */
+    uint64_t n_checks;   /* overlap tests evaluated (-O given => reference raises if > 0, :269) */
+    uint64_t status;     /* 0, or the first SVJG_BAD_* reason                    */
+    uint64_t err_offset; /* byte offset of the lowest offending line             */
+    uint64_t n_generic;  /* records that took the general (quirk-exact) path     */
+    uint64_t reserved;
+} svjg_filter_stats;
+
+int svjg_filter_reset(uint32_t *d_counts, uint32_t num_sv, svjg_filter_stats *d_stats, void *stream);
+int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset,
+                       int64_t d_over, uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off,
+                       uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream);
+
+/* Same, from HOST memory: stages the bytes to the device in pinned chunks cut at
+ * line ends, overlapping copies with the kernel; returns counts, stats and the
+ * hits (offsets are absolute in `gaf`) in host arrays.  `hit_*` may be NULL to
+ * skip the hit list (counts only).  Synchronous.  Returns SVJG_E_INPUT with
+ * stats->status set where the reference would raise. */
+int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                     uint32_t *hit_sv2, uint64_t *hit_off, uint32_t *hit_len, uint64_t hit_cap,
+                     svjg_filter_stats *stats);
+
+/* ---- genotype (kernel 4) ----------------------------------------------------
+ * Replaces likelihood() / allele_normalization() / encode_genotype()
+ * (predict-genotype.py:281-346) and the gate at :216 for n SVs of a VCF.
+ *   sv_index[i]  index into d_counts pairs, or UINT32_MAX if the key is not in the tables
+ *   svtype[i]    0 DEL, 1 INS, 2 INV, 3 BND, 255 other;  bit 7 set = |length| < 50 (:216)
+ *   log10_1me, log10_e, log10_half : math.log10(1-e), math.log10(e), math.log10(1/2)
+ *                as computed by the caller's libm (the reference uses CPython's)
+ *   lut          log10(C(n,k)) at [n*(n+1)/2 + k] for 0 <= k <= n <= lut_nmax, bit-equal
+ *                to CPython's math.log10(math.comb(n,k)) (:313); SVs whose rounded
+ *                counts exceed lut_nmax get flag SVJG_GT_NEED_K and are re-run with
+ *                k_override[i] (NaN = not given; pointer may be NULL)
+ * Outputs per SV: pl[3] = int(-10*(lik+comb)) exact (:319-323); gt 0,1,2 = 0/0,0/1,1/1,
+ * 3 = ./. ; ad2[2] = normalised counts in HALF units (:327-338); flags below. */
+#define SVJG_GT_GENOTYPED 1 /* passed the gate at predict-genotype.py:216 */
+#define SVJG_GT_HALVED_0 2  /* c1 was normalised (prints as float)        */
+#define SVJG_GT_HALVED_1 4  /* c2 was normalised                          */
+#define SVJG_GT_NEED_K 8    /* log10 C(n,k) not available: pl invalid     */
+
+int svjg_genotype_device(const uint32_t *d_counts, const uint32_t *d_sv_index, const uint8_t *d_svtype,
+                         uint32_t n, int64_t min_support, double log10_1me, double log10_e,
+                         double log10_half, const double *d_lut, uint32_t lut_nmax,
+                         const double *d_k_override, int64_t *d_pl, uint8_t *d_gt, uint32_t *d_ad2,
+                         uint8_t *d_flags, void *stream);
+
+/* ---- output (host) ------------------------------------------------------------
+ * Replaces filter-alignments.py:174-175: writes json.dumps(dict, sort_keys=True,
+ * indent=4) of {sv id: [[ref lines], [alt lines]]} byte-for-byte, from the hit
+ * list (any order) and the GAF bytes the offsets refer to. */
+int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes,
+                               const uint32_t *hit_sv2, const uint64_t *hit_off, const uint32_t *hit_len,
+                               uint64_t n_hits, const char *out_path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVJG_H */

@@ -1,0 +1,385 @@
+// C-ABI glue: error strings, device upload of the tables, the host-buffer entry
+// point (pinned/pageable GAF bytes -> chunked H2D overlapped with the filter
+// kernel -> counts, stats and hits back on the host) and the
+// informative_aln.json writer (filter-alignments.py:174-175).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "svjg_internal.h"
+
+namespace svjg {
+
+static thread_local std::string g_err;
+
+int set_error(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(int cuda_err, const char *what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(cudaError_t(cuda_err)) + " in " + what;
+    return SVJG_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------
+// workspace of svjg_filter_host
+// ---------------------------------------------------------------------------
+struct HostWs {
+    static constexpr uint64_t CHUNK = 256ull << 20;
+    uint8_t *d_buf[2] = {nullptr, nullptr};
+    uint64_t buf_cap = 0;
+    uint32_t *d_counts = nullptr;
+    svjg_filter_stats *d_stats = nullptr;
+    uint32_t *d_hit[3] = {nullptr, nullptr, nullptr};
+    uint64_t hit_cap = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    unsigned long long *h_cursor = nullptr;   // pinned: hit cursor after each chunk
+    uint64_t cursor_cap = 0;
+    uint32_t *h_hit[2] = {nullptr, nullptr};  // pinned staging of hit_off / hit_len
+    uint64_t h_hit_cap = 0;
+};
+
+void free_host_ws(svjg_tables *t) {
+    HostWs *w = t->ws;
+    if (!w) return;
+    for (int i = 0; i < 2; ++i) {
+        if (w->d_buf[i]) cudaFree(w->d_buf[i]);
+        if (w->copied[i]) cudaEventDestroy(w->copied[i]);
+        if (w->freed[i]) cudaEventDestroy(w->freed[i]);
+        if (w->h_hit[i]) cudaFreeHost(w->h_hit[i]);
+    }
+    for (int i = 0; i < 3; ++i)
+        if (w->d_hit[i]) cudaFree(w->d_hit[i]);
+    if (w->d_counts) cudaFree(w->d_counts);
+    if (w->d_stats) cudaFree(w->d_stats);
+    if (w->h_cursor) cudaFreeHost(w->h_cursor);
+    if (w->s_copy) cudaStreamDestroy(w->s_copy);
+    if (w->s_comp) cudaStreamDestroy(w->s_comp);
+    delete w;
+    t->ws = nullptr;
+}
+
+}  // namespace svjg
+
+using namespace svjg;
+
+extern "C" const char *svjg_version(void) { return "svjg-b200 0.1.0 (sm_100a)"; }
+extern "C" const char *svjg_last_error(void) { return g_err.c_str(); }
+
+extern "C" int svjg_tables_to_device(svjg_tables *t, int device) {
+    if (!t) return set_error(SVJG_E_ARG, "svjg_tables_to_device: NULL tables");
+    if (t->device == device) return SVJG_OK;
+    if (t->device >= 0) return set_error(SVJG_E_ARG, "tables already live on another device");
+    SVJG_CUDA(cudaSetDevice(device));
+    auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    SVJG_CUDA(up(&t->d_links, t->links.data(), t->links.size() * sizeof(LinkSlot)));
+    SVJG_CUDA(up(&t->d_alts, t->alts.data(), t->alts.size() * sizeof(AltSlot)));
+    SVJG_CUDA(up(&t->d_blob, t->blob.data(), t->blob.size()));
+    SVJG_CUDA(up(&t->d_entries, t->entries.data(), t->entries.size() * sizeof(uint32_t)));
+    t->dev.links = static_cast<const LinkSlot *>(t->d_links);
+    t->dev.alts = static_cast<const AltSlot *>(t->d_alts);
+    t->dev.blob = static_cast<const uint8_t *>(t->d_blob);
+    t->dev.entries = static_cast<const uint32_t *>(t->d_entries);
+    t->dev.link_mask = uint32_t(t->links.size() - 1);
+    t->dev.alt_mask = uint32_t(t->alts.size() - 1);
+    t->dev.num_sv = uint32_t(t->sv_ids.size());
+    t->device = device;
+    return SVJG_OK;
+}
+
+extern "C" void svjg_tables_free(svjg_tables *t) {
+    if (!t) return;
+    if (t->device >= 0) {
+        cudaSetDevice(t->device);
+        free_host_ws(t);
+        cudaFree(t->d_links);
+        cudaFree(t->d_alts);
+        cudaFree(t->d_blob);
+        cudaFree(t->d_entries);
+    }
+    delete t;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer filter
+// ---------------------------------------------------------------------------
+extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                                uint32_t *hit_sv2, uint64_t *hit_off, uint32_t *hit_len, uint64_t hit_cap,
+                                svjg_filter_stats *stats) {
+    if (!t || t->device < 0) return set_error(SVJG_E_ARG, "svjg_filter_host: tables are not on a device");
+    if (!counts || !stats || (n_bytes && !gaf)) return set_error(SVJG_E_ARG, "svjg_filter_host: NULL argument");
+    if (hit_cap && (!hit_sv2 || !hit_off || !hit_len)) return set_error(SVJG_E_ARG, "svjg_filter_host: NULL hit buffer");
+    SVJG_CUDA(cudaSetDevice(t->device));
+    const uint32_t num_sv = uint32_t(t->sv_ids.size());
+
+    // chunk plan: cut at line ends, each chunk < 4 GiB
+    std::vector<uint64_t> cut{0};
+    while (cut.back() < n_bytes) {
+        uint64_t b = cut.back(), e = std::min(n_bytes, b + HostWs::CHUNK);
+        if (e < n_bytes) {
+            const void *nl = memrchr(gaf + b, '\n', size_t(e - b));
+            if (nl) {
+                e = uint64_t(static_cast<const uint8_t *>(nl) - gaf) + 1;
+            } else {
+                const void *fw = memchr(gaf + e, '\n', size_t(n_bytes - e));
+                e = fw ? uint64_t(static_cast<const uint8_t *>(fw) - gaf) + 1 : n_bytes;
+            }
+        }
+        if (e - b >= 0xFFFF0000ull) return set_error(SVJG_E_ARG, "a single GAF line exceeds 4 GiB");
+        cut.push_back(e);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    uint64_t max_chunk = 0;
+    for (size_t k = 0; k < n_chunks; ++k) max_chunk = std::max(max_chunk, cut[k + 1] - cut[k]);
+
+    if (!t->ws) {
+        t->ws = new HostWs();
+        HostWs *w = t->ws;
+        SVJG_CUDA(cudaStreamCreateWithFlags(&w->s_copy, cudaStreamNonBlocking));
+        SVJG_CUDA(cudaStreamCreateWithFlags(&w->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SVJG_CUDA(cudaEventCreateWithFlags(&w->copied[i], cudaEventDisableTiming));
+            SVJG_CUDA(cudaEventCreateWithFlags(&w->freed[i], cudaEventDisableTiming));
+        }
+        SVJG_CUDA(cudaMalloc(&w->d_counts, std::max<size_t>(16, size_t(num_sv) * 8)));
+        SVJG_CUDA(cudaMalloc(&w->d_stats, sizeof(svjg_filter_stats)));
+    }
+    HostWs *w = t->ws;
+    if (w->buf_cap < max_chunk) {
+        for (int i = 0; i < 2; ++i) {
+            if (w->d_buf[i]) SVJG_CUDA(cudaFree(w->d_buf[i]));
+            w->d_buf[i] = nullptr;
+        }
+        w->buf_cap = 0;
+        uint64_t cap = (max_chunk + 255) & ~255ull;
+        for (int i = 0; i < (n_chunks > 1 ? 2 : 1); ++i) SVJG_CUDA(cudaMalloc(&w->d_buf[i], cap));
+        w->buf_cap = cap;
+    } else if (n_chunks > 1 && !w->d_buf[1]) {
+        SVJG_CUDA(cudaMalloc(&w->d_buf[1], w->buf_cap));
+    }
+    if (w->hit_cap < hit_cap) {
+        for (int i = 0; i < 3; ++i) {
+            if (w->d_hit[i]) SVJG_CUDA(cudaFree(w->d_hit[i]));
+            w->d_hit[i] = nullptr;
+        }
+        w->hit_cap = 0;
+        for (int i = 0; i < 3; ++i) SVJG_CUDA(cudaMalloc(&w->d_hit[i], hit_cap * 4));
+        w->hit_cap = hit_cap;
+    }
+    if (w->cursor_cap < n_chunks + 1) {
+        if (w->h_cursor) SVJG_CUDA(cudaFreeHost(w->h_cursor));
+        w->h_cursor = nullptr;
+        SVJG_CUDA(cudaMallocHost(&w->h_cursor, (n_chunks + 1) * sizeof(unsigned long long)));
+        w->cursor_cap = n_chunks + 1;
+    }
+
+    int rc = svjg_filter_reset(w->d_counts, num_sv, w->d_stats, w->s_comp);
+    if (rc) return rc;
+    for (size_t k = 0; k < n_chunks; ++k) {
+        int b = int(k & 1);
+        uint64_t len = cut[k + 1] - cut[k];
+        if (k >= 2) SVJG_CUDA(cudaStreamWaitEvent(w->s_copy, w->freed[b], 0));
+        SVJG_CUDA(cudaMemcpyAsync(w->d_buf[b], gaf + cut[k], len, cudaMemcpyHostToDevice, w->s_copy));
+        SVJG_CUDA(cudaEventRecord(w->copied[b], w->s_copy));
+        SVJG_CUDA(cudaStreamWaitEvent(w->s_comp, w->copied[b], 0));
+        rc = svjg_filter_device(t, w->d_buf[b], len, cut[k], d_over, w->d_counts, w->d_hit[0], w->d_hit[1], w->d_hit[2],
+                                hit_cap, w->d_stats, w->s_comp);
+        if (rc) return rc;
+        SVJG_CUDA(cudaEventRecord(w->freed[b], w->s_comp));
+        // the hit cursor after this chunk tells which hits carry which chunk base
+        SVJG_CUDA(cudaMemcpyAsync(w->h_cursor + k + 1, &w->d_stats->n_hits, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, w->s_comp));
+    }
+    SVJG_CUDA(cudaMemcpyAsync(stats, w->d_stats, sizeof(svjg_filter_stats), cudaMemcpyDeviceToHost, w->s_comp));
+    SVJG_CUDA(cudaMemcpyAsync(counts, w->d_counts, size_t(num_sv) * 8, cudaMemcpyDeviceToHost, w->s_comp));
+    SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
+    if (n_bytes == 0) memset(stats, 0, sizeof *stats), stats->err_offset = ~0ull;
+    if (stats->status) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "GAF line at byte %llu: the reference raises here (reason %llu)",
+                 (unsigned long long)stats->err_offset, (unsigned long long)stats->status);
+        return set_error(SVJG_E_INPUT, msg);
+    }
+    if (hit_cap == 0) return SVJG_OK;
+    if (stats->n_hits > hit_cap) return set_error(SVJG_E_HITS_OVERFLOW, "hit buffers too small");
+    const uint64_t nh = stats->n_hits;
+    if (nh) {
+        if (w->h_hit_cap < nh) {
+            for (int i = 0; i < 2; ++i) {
+                if (w->h_hit[i]) SVJG_CUDA(cudaFreeHost(w->h_hit[i]));
+                w->h_hit[i] = nullptr;
+            }
+            w->h_hit_cap = 0;
+            for (int i = 0; i < 2; ++i) SVJG_CUDA(cudaMallocHost(&w->h_hit[i], hit_cap * 4));
+            w->h_hit_cap = hit_cap;
+        }
+        SVJG_CUDA(cudaMemcpyAsync(hit_sv2, w->d_hit[0], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
+        SVJG_CUDA(cudaMemcpyAsync(w->h_hit[0], w->d_hit[1], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
+        SVJG_CUDA(cudaMemcpyAsync(hit_len, w->d_hit[2], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
+        SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
+        w->h_cursor[0] = 0;
+        for (size_t k = 0; k < n_chunks; ++k) {
+            uint64_t lo = w->h_cursor[k], hi = std::min<uint64_t>(w->h_cursor[k + 1], nh);
+            for (uint64_t i = lo; i < hi; ++i) hit_off[i] = cut[k] + w->h_hit[0][i];
+        }
+    }
+    return SVJG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// informative_aln.json   (json.dumps(d, sort_keys=True, indent=4))
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Out {
+    FILE *f;
+    std::vector<char> buf;
+    bool ok = true;
+    explicit Out(FILE *fp) : f(fp) { buf.reserve(1 << 22); }
+    void flush() {
+        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) ok = false;
+        buf.clear();
+    }
+    void put(const char *s, size_t n) {
+        if (buf.size() + n > (1u << 22)) flush();
+        buf.insert(buf.end(), s, s + n);
+    }
+    void put(const char *s) { put(s, strlen(s)); }
+};
+
+// JSON string with ensure_ascii=True; returns false on invalid UTF-8 (Python
+// would have failed to decode the file)
+bool put_json_string(Out &o, const uint8_t *s, size_t n) {
+    static const char hex[] = "0123456789abcdef";
+    char tmp[16];
+    o.put("\"", 1);
+    size_t run = 0;
+    for (size_t i = 0; i < n;) {
+        uint8_t c = s[i];
+        if (c >= 0x20 && c < 0x80 && c != '"' && c != '\\') {
+            ++run;
+            ++i;
+            continue;
+        }
+        if (run) o.put(reinterpret_cast<const char *>(s + i - run), run), run = 0;
+        if (c < 0x80) {
+            switch (c) {
+                case '"': o.put("\\\"", 2); break;
+                case '\\': o.put("\\\\", 2); break;
+                case '\n': o.put("\\n", 2); break;
+                case '\r': o.put("\\r", 2); break;
+                case '\t': o.put("\\t", 2); break;
+                case '\b': o.put("\\b", 2); break;
+                case '\f': o.put("\\f", 2); break;
+                default:
+                    tmp[0] = '\\'; tmp[1] = 'u'; tmp[2] = '0'; tmp[3] = '0';
+                    tmp[4] = hex[c >> 4]; tmp[5] = hex[c & 15];
+                    o.put(tmp, 6);
+            }
+            ++i;
+            continue;
+        }
+        uint32_t cp;
+        int extra;
+        if ((c & 0xE0) == 0xC0) cp = c & 0x1F, extra = 1;
+        else if ((c & 0xF0) == 0xE0) cp = c & 0x0F, extra = 2;
+        else if ((c & 0xF8) == 0xF0) cp = c & 0x07, extra = 3;
+        else return false;
+        if (i + size_t(extra) >= n) return false;
+        for (int k = 1; k <= extra; ++k) {
+            if ((s[i + k] & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (s[i + k] & 0x3F);
+        }
+        if ((extra == 1 && cp < 0x80) || (extra == 2 && cp < 0x800) || (extra == 3 && cp < 0x10000) || cp > 0x10FFFF ||
+            (cp >= 0xD800 && cp < 0xE000))
+            return false;
+        auto u4 = [&](uint32_t v) {
+            tmp[0] = '\\'; tmp[1] = 'u';
+            tmp[2] = hex[(v >> 12) & 15]; tmp[3] = hex[(v >> 8) & 15]; tmp[4] = hex[(v >> 4) & 15]; tmp[5] = hex[v & 15];
+            o.put(tmp, 6);
+        };
+        if (cp >= 0x10000) {
+            cp -= 0x10000;
+            u4(0xD800 + (cp >> 10));
+            u4(0xDC00 + (cp & 0x3FF));
+        } else {
+            u4(cp);
+        }
+        i += size_t(extra) + 1;
+    }
+    if (run) o.put(reinterpret_cast<const char *>(s + n - run), run);
+    o.put("\"", 1);
+    return true;
+}
+
+}  // namespace
+
+extern "C" int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes,
+                                          const uint32_t *hit_sv2, const uint64_t *hit_off, const uint32_t *hit_len,
+                                          uint64_t n_hits, const char *out_path) {
+    if (!t || !out_path || (n_hits && (!gaf || !hit_sv2 || !hit_off || !hit_len)))
+        return set_error(SVJG_E_ARG, "svjg_emit_informative_json: NULL argument");
+    const uint64_t n2 = uint64_t(t->sv_ids.size()) * 2;
+    // counting sort by (sv, allele); inside a list the reference appends in file order
+    std::vector<uint64_t> start(n2 + 1, 0);
+    for (uint64_t i = 0; i < n_hits; ++i) {
+        if (hit_sv2[i] >= n2) return set_error(SVJG_E_ARG, "hit with an sv index outside the tables");
+        if (hit_off[i] + hit_len[i] > n_bytes) return set_error(SVJG_E_ARG, "hit outside the GAF buffer");
+        ++start[hit_sv2[i] + 1];
+    }
+    for (uint64_t k = 0; k < n2; ++k) start[k + 1] += start[k];
+    std::vector<uint64_t> order(n_hits);
+    {
+        std::vector<uint64_t> cur(start.begin(), start.end() - 1);
+        for (uint64_t i = 0; i < n_hits; ++i) order[cur[hit_sv2[i]]++] = i;
+    }
+    for (uint64_t k = 0; k < n2; ++k)
+        std::sort(order.begin() + start[k], order.begin() + start[k + 1],
+                  [&](uint64_t x, uint64_t y) { return hit_off[x] < hit_off[y]; });
+
+    FILE *f = fopen(out_path, "wb");
+    if (!f) return set_error(SVJG_E_IO, std::string("cannot write ") + out_path);
+    Out o(f);
+    bool any = false, utf8_ok = true;
+    for (uint64_t sv = 0; sv < n2 / 2 && utf8_ok; ++sv) {
+        if (start[2 * sv] == start[2 * sv + 2]) continue;   // a key exists only once something was appended (:163)
+        o.put(any ? ",\n    " : "{\n    ");
+        any = true;
+        const std::string &id = t->sv_ids[sv];
+        utf8_ok &= put_json_string(o, reinterpret_cast<const uint8_t *>(id.data()), id.size());
+        o.put(": [\n        ");
+        for (int al = 0; al < 2 && utf8_ok; ++al) {
+            uint64_t b = start[2 * sv + al], e = start[2 * sv + al + 1];
+            if (b == e) {
+                o.put("[]");
+            } else {
+                o.put("[\n            ");
+                for (uint64_t k = b; k < e && utf8_ok; ++k) {
+                    uint64_t i = order[k];
+                    const uint8_t *line = gaf + hit_off[i];
+                    size_t len = hit_len[i];
+                    const void *cgz = memmem(line, len, "cg:Z:", 5);      // line.split("cg:Z:")[0]  (:166)
+                    if (cgz) len = size_t(static_cast<const uint8_t *>(cgz) - line);
+                    if (k != b) o.put(",\n            ");
+                    utf8_ok &= put_json_string(o, line, len);
+                }
+                o.put("\n        ]");
+            }
+            if (al == 0) o.put(",\n        ");
+        }
+        o.put("\n    ]");
+    }
+    o.put(any ? "\n}" : "{}");
+    o.flush();
+    bool ok = o.ok && fclose(f) == 0;
+    if (!utf8_ok) return set_error(SVJG_E_INPUT, "GAF text is not valid UTF-8 (the reference cannot read it)");
+    if (!ok) return set_error(SVJG_E_IO, std::string("write failed: ") + out_path);
+    return SVJG_OK;
+}

@@ -1,0 +1,38 @@
+// Internal declarations shared by the translation units of libsvjg.so.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/svjg.h"
+#include "svjg_common.h"
+
+namespace svjg {
+struct HostWs;
+}
+
+struct svjg_tables {
+    std::vector<std::string> sv_ids;          // byte-sorted distinct sv ids
+    std::vector<svjg::LinkSlot> links;
+    std::vector<svjg::AltSlot> alts;
+    std::vector<uint8_t> blob;
+    std::vector<uint32_t> entries;
+    uint32_t n_keys = 0, n_link_slots = 0, n_alt = 0;
+    // device image
+    int device = -1;
+    void *d_links = nullptr, *d_alts = nullptr, *d_blob = nullptr, *d_entries = nullptr;
+    svjg::DevTables dev{};
+    // lazily created workspace of svjg_filter_host
+    svjg::HostWs *ws = nullptr;
+};
+
+namespace svjg {
+int set_error(int code, const std::string &msg);
+int cuda_fail(int cuda_err, const char *what);   // records the message, returns SVJG_E_CUDA
+void free_host_ws(svjg_tables *t);
+}  // namespace svjg
+
+#define SVJG_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return svjg::cuda_fail(int(_e), #call);        \
+    } while (0)

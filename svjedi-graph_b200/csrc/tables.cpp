@@ -1,0 +1,592 @@
+// Host side of the graph tables: parses <prefix>_svs_edges.json and the GFA and
+// builds the device image (link-key hash -> SV entries, alt-node hash -> length).
+// Reference behaviour restated: filter-alignments.py:95-98 (json.load into
+// d_link_sv) and :103-113 (alt_node_len).  Written from scratch; no reference
+// code is reused.
+#include "svjg_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <unordered_map>
+
+namespace svjg {
+
+// ---------------------------------------------------------------------------
+// a small strict JSON reader (only what svs_edges.json needs, but any valid
+// JSON value is skipped correctly)
+// ---------------------------------------------------------------------------
+struct JsonIn {
+    const char *p, *end;
+    std::string err;
+    bool fail(const char *m) {
+        if (err.empty()) err = m;
+        return false;
+    }
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) ++p;
+    }
+    bool lit(const char *s) {
+        size_t n = strlen(s);
+        if (size_t(end - p) >= n && memcmp(p, s, n) == 0) {
+            p += n;
+            return true;
+        }
+        return false;
+    }
+    static void put_utf8(std::string &out, uint32_t cp) {
+        if (cp < 0x80) out.push_back(char(cp));
+        else if (cp < 0x800) {
+            out.push_back(char(0xC0 | (cp >> 6)));
+            out.push_back(char(0x80 | (cp & 0x3F)));
+        } else if (cp < 0x10000) {
+            out.push_back(char(0xE0 | (cp >> 12)));
+            out.push_back(char(0x80 | ((cp >> 6) & 0x3F)));
+            out.push_back(char(0x80 | (cp & 0x3F)));
+        } else {
+            out.push_back(char(0xF0 | (cp >> 18)));
+            out.push_back(char(0x80 | ((cp >> 12) & 0x3F)));
+            out.push_back(char(0x80 | ((cp >> 6) & 0x3F)));
+            out.push_back(char(0x80 | (cp & 0x3F)));
+        }
+    }
+    bool hex4(uint32_t &v) {
+        if (end - p < 4) return fail("truncated \\u escape");
+        v = 0;
+        for (int i = 0; i < 4; ++i) {
+            char c = *p++;
+            v <<= 4;
+            if (c >= '0' && c <= '9') v |= uint32_t(c - '0');
+            else if (c >= 'a' && c <= 'f') v |= uint32_t(c - 'a' + 10);
+            else if (c >= 'A' && c <= 'F') v |= uint32_t(c - 'A' + 10);
+            else return fail("bad \\u escape");
+        }
+        return true;
+    }
+    bool string(std::string &out) {
+        out.clear();
+        if (p >= end || *p != '"') return fail("expected string");
+        ++p;
+        while (p < end) {
+            unsigned char c = (unsigned char)*p++;
+            if (c == '"') return true;
+            if (c != '\\') {
+                out.push_back(char(c));
+                continue;
+            }
+            if (p >= end) break;
+            char e = *p++;
+            switch (e) {
+                case '"': out.push_back('"'); break;
+                case '\\': out.push_back('\\'); break;
+                case '/': out.push_back('/'); break;
+                case 'b': out.push_back('\b'); break;
+                case 'f': out.push_back('\f'); break;
+                case 'n': out.push_back('\n'); break;
+                case 'r': out.push_back('\r'); break;
+                case 't': out.push_back('\t'); break;
+                case 'u': {
+                    uint32_t cp;
+                    if (!hex4(cp)) return false;
+                    if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+                        const char *save = p;
+                        p += 2;
+                        uint32_t lo;
+                        if (!hex4(lo)) return false;
+                        if (lo >= 0xDC00 && lo < 0xE000) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                        else p = save;
+                    }
+                    put_utf8(out, cp);
+                    break;
+                }
+                default: return fail("bad escape");
+            }
+        }
+        return fail("unterminated string");
+    }
+    // scalar kinds for the allele slot
+    enum Kind { K_INT, K_FLOAT, K_TRUE, K_FALSE, K_NULL, K_STRING, K_ARRAY, K_OBJECT };
+    bool skip_value(Kind &kind, long long *ival = nullptr, std::string *sval = nullptr) {
+        ws();
+        if (p >= end) return fail("unexpected end");
+        char c = *p;
+        if (c == '"') {
+            std::string tmp;
+            kind = K_STRING;
+            return string(sval ? *sval : tmp);
+        }
+        if (c == '{') {
+            kind = K_OBJECT;
+            ++p;
+            ws();
+            if (p < end && *p == '}') {
+                ++p;
+                return true;
+            }
+            for (;;) {
+                ws();
+                std::string k;
+                if (!string(k)) return false;
+                ws();
+                if (p >= end || *p != ':') return fail("expected ':'");
+                ++p;
+                Kind kk;
+                if (!skip_value(kk)) return false;
+                ws();
+                if (p < end && *p == ',') {
+                    ++p;
+                    continue;
+                }
+                if (p < end && *p == '}') {
+                    ++p;
+                    return true;
+                }
+                return fail("expected ',' or '}'");
+            }
+        }
+        if (c == '[') {
+            kind = K_ARRAY;
+            ++p;
+            ws();
+            if (p < end && *p == ']') {
+                ++p;
+                return true;
+            }
+            for (;;) {
+                Kind kk;
+                if (!skip_value(kk)) return false;
+                ws();
+                if (p < end && *p == ',') {
+                    ++p;
+                    continue;
+                }
+                if (p < end && *p == ']') {
+                    ++p;
+                    return true;
+                }
+                return fail("expected ',' or ']'");
+            }
+        }
+        if (lit("true")) {
+            kind = K_TRUE;
+            return true;
+        }
+        if (lit("false")) {
+            kind = K_FALSE;
+            return true;
+        }
+        if (lit("null")) {
+            kind = K_NULL;
+            return true;
+        }
+        if (lit("NaN") || lit("Infinity") || lit("-Infinity")) {
+            kind = K_FLOAT;
+            return true;
+        }
+        // number
+        const char *s = p;
+        bool is_float = false;
+        if (p < end && *p == '-') ++p;
+        if (p >= end || *p < '0' || *p > '9') return fail("bad value");
+        while (p < end && *p >= '0' && *p <= '9') ++p;
+        if (p < end && *p == '.') {
+            is_float = true;
+            ++p;
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        }
+        if (p < end && (*p == 'e' || *p == 'E')) {
+            is_float = true;
+            ++p;
+            if (p < end && (*p == '+' || *p == '-')) ++p;
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        }
+        kind = is_float ? K_FLOAT : K_INT;
+        if (!is_float && ival) {
+            // clamp: anything outside [-2, 1] is an out-of-range list index anyway
+            long long v = 0;
+            bool neg = (*s == '-');
+            const char *d = s + (neg ? 1 : 0);
+            int nd = 0;
+            for (; d < p; ++d, ++nd) v = nd < 18 ? v * 10 + (*d - '0') : 1000;
+            *ival = neg ? -v : v;
+        }
+        return true;
+    }
+};
+
+struct RawKey {
+    std::string key;
+    bool poison_key = false;
+    std::vector<std::pair<std::string, int>> ents;  // allele -1 = poison entry
+};
+
+static bool parse_edges(const char *text, size_t len, std::vector<RawKey> &keys, std::string &err) {
+    JsonIn in{text, text + len, {}};
+    // json.load() accepts a UTF-8 BOM-less document; skip leading whitespace
+    in.ws();
+    if (in.p >= in.end || *in.p != '{') {
+        err = "svs_edges: top level is not a JSON object";
+        return false;
+    }
+    ++in.p;
+    std::unordered_map<std::string, size_t> seen;  // duplicate keys: the last one wins (dict)
+    in.ws();
+    if (in.p < in.end && *in.p == '}') {
+        ++in.p;
+    } else {
+        for (;;) {
+            in.ws();
+            RawKey rk;
+            if (!in.string(rk.key)) break;
+            in.ws();
+            if (in.p >= in.end || *in.p != ':') {
+                in.fail("expected ':'");
+                break;
+            }
+            ++in.p;
+            in.ws();
+            if (in.p < in.end && *in.p == '[') {
+                ++in.p;
+                in.ws();
+                if (in.p < in.end && *in.p == ']') {
+                    ++in.p;
+                } else {
+                    for (;;) {
+                        in.ws();
+                        // one entry: [ "sv id", allele ]
+                        if (in.p < in.end && *in.p == '[') {
+                            ++in.p;
+                            int n_el = 0;
+                            std::string sv;
+                            bool sv_is_str = false;
+                            int allele = -1;
+                            in.ws();
+                            if (in.p < in.end && *in.p == ']') {
+                                ++in.p;
+                            } else {
+                                for (;;) {
+                                    JsonIn::Kind kind;
+                                    long long iv = 0;
+                                    std::string sval;
+                                    if (!in.skip_value(kind, &iv, &sval)) break;
+                                    if (n_el == 0 && kind == JsonIn::K_STRING) {
+                                        sv_is_str = true;
+                                        sv.swap(sval);
+                                    }
+                                    if (n_el == 1) {
+                                        // list index semantics of Python: 0,1,-1,-2 and bools are valid
+                                        if (kind == JsonIn::K_INT) {
+                                            if (iv == 0 || iv == -2) allele = 0;
+                                            else if (iv == 1 || iv == -1) allele = 1;
+                                        } else if (kind == JsonIn::K_TRUE) allele = 1;
+                                        else if (kind == JsonIn::K_FALSE) allele = 0;
+                                    }
+                                    ++n_el;
+                                    in.ws();
+                                    if (in.p < in.end && *in.p == ',') {
+                                        ++in.p;
+                                        continue;
+                                    }
+                                    if (in.p < in.end && *in.p == ']') {
+                                        ++in.p;
+                                        break;
+                                    }
+                                    in.fail("expected ',' or ']'");
+                                    break;
+                                }
+                            }
+                            if (!in.err.empty()) break;
+                            if (n_el != 2) rk.poison_key = true;  // tuple unpack raises as soon as the key is found
+                            else if (!sv_is_str || sv.find(':') == std::string::npos) rk.ents.push_back({std::string(), -1});
+                            else rk.ents.push_back({sv, allele});
+                        } else {
+                            JsonIn::Kind kind;
+                            if (!in.skip_value(kind)) break;
+                            // a 2-character string would unpack; everything else raises
+                            rk.poison_key = true;
+                        }
+                        in.ws();
+                        if (in.p < in.end && *in.p == ',') {
+                            ++in.p;
+                            continue;
+                        }
+                        if (in.p < in.end && *in.p == ']') {
+                            ++in.p;
+                            break;
+                        }
+                        in.fail("expected ',' or ']'");
+                        break;
+                    }
+                }
+            } else {
+                JsonIn::Kind kind;
+                if (!in.skip_value(kind)) break;
+                rk.poison_key = true;
+            }
+            if (!in.err.empty()) break;
+            auto it = seen.find(rk.key);
+            if (it == seen.end()) {
+                seen.emplace(rk.key, keys.size());
+                keys.push_back(std::move(rk));
+            } else {
+                keys[it->second] = std::move(rk);
+            }
+            in.ws();
+            if (in.p < in.end && *in.p == ',') {
+                ++in.p;
+                continue;
+            }
+            if (in.p < in.end && *in.p == '}') {
+                ++in.p;
+                break;
+            }
+            in.fail("expected ',' or '}'");
+            break;
+        }
+    }
+    if (!in.err.empty()) {
+        err = "svs_edges: " + in.err;
+        return false;
+    }
+    in.ws();
+    if (in.p != in.end) {
+        err = "svs_edges: trailing data after the JSON object";
+        return false;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// GFA: alt-node lengths   (filter-alignments.py:103-113)
+// ---------------------------------------------------------------------------
+static inline bool py_space(unsigned char c) {
+    return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
+}
+
+static bool scan_gfa(const char *text, size_t len, std::vector<std::pair<std::string, int64_t>> &alts,
+                     std::string &err) {
+    std::unordered_map<std::string, size_t> seen;
+    const char *p = text, *end = text + len;
+    while (p < end) {
+        const char *nl = (const char *)memchr(p, '\n', size_t(end - p));
+        const char *le = nl ? nl : end;            // line without '\n'
+        const char *next = nl ? nl + 1 : end;
+        if (*p == 'S') {
+            // cols of the raw line (with its newline, as the reference splits before stripping)
+            const char *t1 = (const char *)memchr(p, '\t', size_t(next - p));
+            if (!t1) {
+                err = "GFA: S line without a name column";
+                return false;
+            }
+            const char *name_b = t1 + 1;
+            const char *t2 = (const char *)memchr(name_b, '\t', size_t(next - name_b));
+            const char *name_e = t2 ? t2 : next;
+            // last ':' piece
+            const char *q = name_e;
+            while (q > name_b && q[-1] != ':') --q;
+            bool alt = memchr(q, '.', size_t(name_e - q)) != nullptr;
+            if (alt) {
+                // line.rstrip().split("\t")[2]
+                const char *re = le;
+                while (re > p && py_space((unsigned char)re[-1])) --re;
+                if (!t2 || t2 >= re) {   // fewer than 3 columns once stripped -> IndexError in the reference
+                    err = "GFA: alt-node S line without a sequence column";
+                    return false;
+                }
+                const char *seq_b = t2 + 1;
+                const char *seq_e = (const char *)memchr(seq_b, '\t', size_t(re - seq_b));
+                if (!seq_e) seq_e = re;
+                int64_t n = 0;   // len() of a str counts code points
+                for (const char *c = seq_b; c < seq_e; ++c) n += ((unsigned char)*c & 0xC0) != 0x80;
+                std::string name(name_b, size_t(name_e - name_b));
+                auto it = seen.find(name);
+                if (it == seen.end()) {
+                    seen.emplace(name, alts.size());
+                    alts.push_back({std::move(name), n});
+                } else {
+                    alts[it->second].second = n;
+                }
+            }
+        }
+        p = next;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------
+static uint64_t hash_bytes(const char *s, size_t n) {
+    TokHash h = tok_init();
+    for (size_t i = 0; i < n; ++i) tok_step(h, (unsigned char)s[i]);
+    return tok_value(h);
+}
+
+static uint32_t pow2_at_least(uint64_t n) {
+    uint64_t c = 2;
+    while (c < n) c <<= 1;
+    return uint32_t(c);
+}
+
+static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pair<std::string, int64_t>> &alts,
+                  std::string &err) {
+    // distinct sv ids, byte-sorted == the order json.dumps(sort_keys=True) prints them
+    for (auto &k : keys)
+        for (auto &e : k.ents)
+            if (e.second >= 0) t->sv_ids.push_back(e.first);
+    std::sort(t->sv_ids.begin(), t->sv_ids.end());
+    t->sv_ids.erase(std::unique(t->sv_ids.begin(), t->sv_ids.end()), t->sv_ids.end());
+    if (t->sv_ids.size() >= 0x7FFFFFFFull) {
+        err = "too many distinct sv ids";
+        return false;
+    }
+    t->n_keys = uint32_t(keys.size());
+
+    struct Parse {
+        uint32_t key, split;   // nL = key[0:split), sL = key[split+1], nR = key[split+3 : len-2)
+    };
+    std::vector<Parse> parses;
+    std::vector<uint32_t> ent_begin(keys.size() + 1, 0);
+    for (size_t ki = 0; ki < keys.size(); ++ki) {
+        const std::string &k = keys[ki].key;
+        ent_begin[ki] = uint32_t(t->entries.size());
+        for (auto &e : keys[ki].ents) {
+            if (e.second < 0) {
+                t->entries.push_back(ENTRY_POISON);
+            } else {
+                auto it = std::lower_bound(t->sv_ids.begin(), t->sv_ids.end(), e.first);
+                t->entries.push_back(uint32_t(it - t->sv_ids.begin()) * 2 + uint32_t(e.second));
+            }
+        }
+        size_t n = k.size();
+        if (n < 7 || k[n - 2] != '@' || (k[n - 1] != '+' && k[n - 1] != '-')) continue;
+        // every "@+@" / "@-@" with a non-empty name on both sides is a possible reading of the key
+        for (size_t s = 1; s + 3 < n - 2; ++s) {
+            if (k[s] == '@' && k[s + 2] == '@' && (k[s + 1] == '+' || k[s + 1] == '-')) parses.push_back({uint32_t(ki), uint32_t(s)});
+        }
+    }
+    ent_begin[keys.size()] = uint32_t(t->entries.size());
+    if (t->entries.empty()) t->entries.push_back(ENTRY_POISON);  // never empty on the device
+
+    uint32_t cap = pow2_at_least(parses.size() * 2 + 2);
+    t->links.assign(cap, LinkSlot{});
+    for (auto &ps : parses) {
+        const std::string &k = keys[ps.key].key;
+        size_t n = k.size();
+        size_t len_l = ps.split, off_r = ps.split + 3, len_r = n - 2 - off_r;
+        if (len_l > 0xFFFF || len_r > 0xFFFF) {
+            err = "node name longer than 65535 bytes in svs_edges key";
+            return false;
+        }
+        uint32_t sl = k[ps.split + 1] == '+', sr = k[n - 1] == '+';
+        uint64_t h = link_hash(hash_bytes(k.data(), len_l), sl, hash_bytes(k.data() + off_r, len_r), sr);
+        uint32_t cnt = ent_begin[ps.key + 1] - ent_begin[ps.key];
+        if (cnt >= (1u << 28)) {
+            err = "too many entries under one link key";
+            return false;
+        }
+        LinkSlot s{};
+        s.hash = h;
+        s.name_off = uint32_t(t->blob.size());
+        s.len_l = uint16_t(len_l);
+        s.len_r = uint16_t(len_r);
+        s.ent_begin = ent_begin[ps.key];
+        s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | (sl << 2) | (sr << 1) | 1u;
+        s.ent0 = cnt ? t->entries[ent_begin[ps.key]] : ENTRY_POISON;
+        t->blob.insert(t->blob.end(), k.begin(), k.begin() + len_l);
+        t->blob.insert(t->blob.end(), k.begin() + off_r, k.begin() + off_r + len_r);
+        if (t->blob.size() >= 0xFFFF0000ull) {
+            err = "link table name blob exceeds 4 GiB";
+            return false;
+        }
+        uint32_t i = uint32_t(h) & (cap - 1);
+        while (t->links[i].meta & 1u) i = (i + 1) & (cap - 1);
+        t->links[i] = s;
+    }
+    t->n_link_slots = uint32_t(parses.size());
+
+    t->n_alt = uint32_t(alts.size());
+    uint32_t acap = pow2_at_least(alts.size() * 2 + 2);
+    t->alts.assign(acap, AltSlot{});
+    for (auto &a : alts) {
+        AltSlot s{};
+        s.hash = alt_hash(hash_bytes(a.first.data(), a.first.size()));
+        s.name_off = uint32_t(t->blob.size());
+        s.name_len = uint32_t(a.first.size());
+        s.seq_len = a.second;
+        s.used = 1;
+        t->blob.insert(t->blob.end(), a.first.begin(), a.first.end());
+        if (t->blob.size() >= 0xFFFF0000ull) {
+            err = "alt-node name blob exceeds 4 GiB";
+            return false;
+        }
+        uint32_t i = uint32_t(s.hash) & (acap - 1);
+        while (t->alts[i].used) i = (i + 1) & (acap - 1);
+        t->alts[i] = s;
+    }
+    // pad the blob so 4-byte reads at the tail stay in bounds
+    t->blob.insert(t->blob.end(), 16, 0);
+    return true;
+}
+
+static bool read_file(const char *path, std::string &out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+
+}  // namespace svjg
+
+using namespace svjg;
+
+extern "C" int svjg_tables_from_memory(const char *edges_json, size_t edges_len, const char *gfa, size_t gfa_len,
+                                       svjg_tables **out) {
+    if (!edges_json || !out || (!gfa && gfa_len)) return set_error(SVJG_E_ARG, "svjg_tables_from_memory: NULL argument");
+    std::vector<RawKey> keys;
+    std::vector<std::pair<std::string, int64_t>> alts;
+    std::string err;
+    if (!parse_edges(edges_json, edges_len, keys, err)) return set_error(SVJG_E_JSON, err);
+    if (!scan_gfa(gfa, gfa_len, alts, err)) return set_error(SVJG_E_INPUT, err);
+    svjg_tables *t = new svjg_tables();
+    if (!build(t, keys, alts, err)) {
+        delete t;
+        return set_error(SVJG_E_ARG, err);
+    }
+    *out = t;
+    return SVJG_OK;
+}
+
+extern "C" int svjg_tables_load(const char *svs_edges_json_path, const char *gfa_path, svjg_tables **out) {
+    if (!svs_edges_json_path || !gfa_path || !out) return set_error(SVJG_E_ARG, "svjg_tables_load: NULL argument");
+    std::string edges, gfa;
+    if (!read_file(svs_edges_json_path, edges)) return set_error(SVJG_E_IO, std::string("cannot read ") + svs_edges_json_path);
+    if (!read_file(gfa_path, gfa)) return set_error(SVJG_E_IO, std::string("cannot read ") + gfa_path);
+    return svjg_tables_from_memory(edges.data(), edges.size(), gfa.data(), gfa.size(), out);
+}
+
+extern "C" uint32_t svjg_tables_num_sv(const svjg_tables *t) { return t ? uint32_t(t->sv_ids.size()) : 0; }
+extern "C" uint32_t svjg_tables_num_links(const svjg_tables *t) { return t ? t->n_keys : 0; }
+extern "C" uint32_t svjg_tables_num_alt_nodes(const svjg_tables *t) { return t ? t->n_alt : 0; }
+extern "C" uint64_t svjg_tables_device_bytes(const svjg_tables *t) {
+    if (!t) return 0;
+    return t->links.size() * sizeof(LinkSlot) + t->alts.size() * sizeof(AltSlot) + t->blob.size() +
+           t->entries.size() * sizeof(uint32_t);
+}
+extern "C" const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len) {
+    if (!t || i >= t->sv_ids.size()) return nullptr;
+    if (len) *len = uint32_t(t->sv_ids[i].size());
+    return t->sv_ids[i].data();
+}
+extern "C" uint32_t svjg_tables_find_sv(const svjg_tables *t, const char *sv_id, uint32_t len) {
+    if (!t || !sv_id) return UINT32_MAX;
+    std::string key(sv_id, len);
+    auto it = std::lower_bound(t->sv_ids.begin(), t->sv_ids.end(), key);
+    if (it == t->sv_ids.end() || *it != key) return UINT32_MAX;
+    return uint32_t(it - t->sv_ids.begin());
+}

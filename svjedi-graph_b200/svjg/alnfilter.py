@@ -1,0 +1,228 @@
+"""Host mirror of filter-alignments.py (reference :27-175): graph tables, the
+filter over a GAF, and the informative_aln.json writer — all through libsvjg.so.
+PyTorch is used only to own device / pinned buffers and streams."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+D_OVER = 100    # filter-alignments.py:56
+
+
+class InputError(Exception):
+    """The reference raises on this input (exit status 1)."""
+
+
+class Tables:
+    """link key -> SV entries and alt-node lengths (filter-alignments.py:95-113)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        self.num_sv = int(capi.lib.svjg_tables_num_sv(self._h))
+        self.num_links = int(capi.lib.svjg_tables_num_links(self._h))
+        self.num_alt_nodes = int(capi.lib.svjg_tables_num_alt_nodes(self._h))
+        self.device = None
+        self._ids = None
+
+    @classmethod
+    def load(cls, svs_edges_path, gfa_path):
+        h = C.c_void_p()
+        capi.check(capi.lib.svjg_tables_load(os.fsencode(svs_edges_path), os.fsencode(gfa_path), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_memory(cls, edges_json, gfa_text):
+        ej = edges_json.encode() if isinstance(edges_json, str) else bytes(edges_json)
+        gt = gfa_text.encode() if isinstance(gfa_text, str) else bytes(gfa_text)
+        h = C.c_void_p()
+        capi.check(capi.lib.svjg_tables_from_memory(ej, len(ej), gt, len(gt), C.byref(h)))
+        return cls(h.value)
+
+    def to_device(self, device=0):
+        capi.check(capi.lib.svjg_tables_to_device(self._h, int(device)))
+        self.device = int(device)
+        return self
+
+    @property
+    def device_bytes(self):
+        return int(capi.lib.svjg_tables_device_bytes(self._h))
+
+    def sv_id(self, i):
+        n = C.c_uint32()
+        p = capi.lib.svjg_tables_sv_id(self._h, i, C.byref(n))
+        if not p:
+            raise IndexError(i)
+        return C.string_at(p, n.value).decode("utf-8")
+
+    @property
+    def sv_ids(self):
+        if self._ids is None:
+            self._ids = [self.sv_id(i) for i in range(self.num_sv)]
+        return self._ids
+
+    def find_sv(self, key):
+        b = key.encode("utf-8")
+        i = capi.lib.svjg_tables_find_sv(self._h, b, len(b))
+        return None if i == capi.NO_SV else int(i)
+
+    def close(self):
+        if self._h:
+            capi.lib.svjg_tables_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FilterResult:
+    def __init__(self, counts, stats, hit_sv2=None, hit_off=None, hit_len=None):
+        self.counts = counts          # np.uint32 [num_sv, 2]  (REF, ALT hit multiplicities)
+        self.stats = stats
+        self.hit_sv2, self.hit_off, self.hit_len = hit_sv2, hit_off, hit_len
+
+    @property
+    def n_hits(self):
+        return self.stats["n_hits"]
+
+
+def _as_u8(buf):
+    """numpy uint8 view (no copy) of bytes / bytearray / memoryview / ndarray / pinned torch tensor."""
+    if isinstance(buf, np.ndarray):
+        a = buf
+    elif hasattr(buf, "numpy") and hasattr(buf, "is_pinned"):
+        a = buf.numpy()
+    else:
+        a = np.frombuffer(buf, dtype=np.uint8)
+    if a.dtype != np.uint8 or not a.flags.c_contiguous:
+        raise TypeError("GAF buffer must be contiguous bytes")
+    return a
+
+
+def _raise_input(stats):
+    reason = capi.BAD_REASONS.get(stats["status"], "malformed input")
+    raise InputError(f"GAF line at byte {stats['err_offset']}: {reason} (the reference raises here)")
+
+
+def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None):
+    """The per-line loop of filter-alignments.py:123-166 over GAF bytes in HOST
+    memory (pinned memory copies fastest).  Returns counts, stats and, if
+    ``want_hits``, the hit list with absolute byte offsets."""
+    if tables.device is None:
+        raise RuntimeError("tables.to_device() first")
+    a = _as_u8(gaf)
+    n = int(a.size)
+    counts = np.zeros((tables.num_sv, 2), dtype=np.uint32)
+    stats = capi.FilterStats()
+    if hit_cap is None:
+        hit_cap = max(1024, n // 64) if want_hits else 0
+    while True:
+        if hit_cap:
+            sv2 = np.empty(hit_cap, dtype=np.uint32)
+            off = np.empty(hit_cap, dtype=np.uint64)
+            ln = np.empty(hit_cap, dtype=np.uint32)
+            ptrs = (sv2.ctypes.data, off.ctypes.data, ln.ctypes.data)
+        else:
+            sv2 = off = ln = None
+            ptrs = (None, None, None)
+        rc = capi.lib.svjg_filter_host(tables._h, a.ctypes.data if n else None, n, int(d_over),
+                                       counts.ctypes.data, *ptrs, hit_cap, C.byref(stats))
+        st = stats.as_dict()
+        if rc == capi.E_HITS_OVERFLOW:
+            hit_cap = int(st["n_hits"]) + 16
+            continue
+        if rc == capi.E_INPUT:
+            _raise_input(st)
+        capi.check(rc)
+        break
+    nh = st["n_hits"] if hit_cap else 0
+    if hit_cap:
+        return FilterResult(counts, st, sv2[:nh], off[:nh], ln[:nh])
+    return FilterResult(counts, st)
+
+
+class DeviceFilter:
+    """Device-resident variant: GAF shard already in HBM (torch uint8 tensor).
+    Buffers are torch tensors; launches go to torch's current stream."""
+
+    def __init__(self, tables, hit_cap=1 << 20, device=None):
+        import torch
+        self.torch = torch
+        self.tables = tables
+        self.dev = torch.device("cuda", tables.device if device is None else device)
+        self.counts = torch.zeros((max(1, tables.num_sv), 2), dtype=torch.int32, device=self.dev)
+        self.stats = torch.zeros(8, dtype=torch.int64, device=self.dev)
+        self._alloc_hits(hit_cap)
+
+    def _alloc_hits(self, cap):
+        t = self.torch
+        self.hit_cap = int(cap)
+        self.hit_sv2 = t.empty(max(1, cap), dtype=t.int32, device=self.dev)
+        self.hit_off = t.empty(max(1, cap), dtype=t.int32, device=self.dev)
+        self.hit_len = t.empty(max(1, cap), dtype=t.int32, device=self.dev)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def reset(self):
+        capi.check(capi.lib.svjg_filter_reset(self.counts.data_ptr(), self.tables.num_sv, self.stats.data_ptr(),
+                                              self._stream()))
+
+    def run(self, d_gaf, n_bytes=None, base_offset=0, d_over=D_OVER):
+        """Asynchronous: accumulates into self.counts / self.stats / hit arrays."""
+        n = int(d_gaf.numel() if n_bytes is None else n_bytes)
+        capi.check(capi.lib.svjg_filter_device(self.tables._h, d_gaf.data_ptr(), n, int(base_offset), int(d_over),
+                                               self.counts.data_ptr(), self.hit_sv2.data_ptr(), self.hit_off.data_ptr(),
+                                               self.hit_len.data_ptr(), self.hit_cap, self.stats.data_ptr(),
+                                               self._stream()))
+
+    def read_stats(self):
+        v = self.stats.cpu().numpy().astype(np.uint64)
+        names = [n for n, _ in capi.FilterStats._fields_]
+        return {k: int(x) for k, x in zip(names, v)}
+
+    def result(self):
+        """Synchronises and copies everything back (hits as absolute offsets
+        within the shard passed to run())."""
+        st = self.read_stats()
+        if st["status"]:
+            _raise_input(st)
+        nh = min(st["n_hits"], self.hit_cap)
+        counts = self.counts.cpu().numpy().view(np.uint32)[: self.tables.num_sv]
+        return FilterResult(counts, st, self.hit_sv2[:nh].cpu().numpy().view(np.uint32),
+                            self.hit_off[:nh].cpu().numpy().view(np.uint32).astype(np.uint64),
+                            self.hit_len[:nh].cpu().numpy().view(np.uint32))
+
+
+def write_informative_json(tables, gaf, result, out_path):
+    """filter-alignments.py:174-175, byte for byte."""
+    a = _as_u8(gaf)
+    nh = int(result.hit_sv2.size)
+    sv2 = np.ascontiguousarray(result.hit_sv2, dtype=np.uint32)
+    off = np.ascontiguousarray(result.hit_off, dtype=np.uint64)
+    ln = np.ascontiguousarray(result.hit_len, dtype=np.uint32)
+    capi.check(capi.lib.svjg_emit_informative_json(
+        tables._h, a.ctypes.data if a.size else None, int(a.size), sv2.ctypes.data if nh else None,
+        off.ctypes.data if nh else None, ln.ctypes.data if nh else None, nh, os.fsencode(out_path)))
+
+
+def read_file_pinned(path):
+    """Whole file into page-locked host memory (torch pinned uint8 tensor)."""
+    import torch
+    n = os.path.getsize(path)
+    t = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    with open(path, "rb", buffering=0) as fh:
+        view = memoryview(t.numpy())[:n]
+        got = 0
+        while got < n:
+            k = fh.readinto(view[got:])
+            if not k:
+                break
+            got += k
+    return t[:n]

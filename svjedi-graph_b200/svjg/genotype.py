@@ -1,0 +1,212 @@
+"""Host mirror of predict-genotype.py (reference :29-72, :89-346): VCF keys on
+the host, likelihood / GT / PL on the device (kernel 4), VCF text out."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+
+MIN_SUPPORT = 3     # predict-genotype.py:46
+ERR = 0.00005       # predict-genotype.py:61
+LUT_NMAX = 256
+
+SVTYPE_CODE = {"DEL": 0, "INS": 1, "INV": 2, "BND": 3}
+GT_TEXT = ("0/0", "0/1", "1/1", "./.")
+
+_FORMAT_LINES = (
+    '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n'
+    '##FORMAT=<ID=DP,Number=1,Type=Float,Description="Total number of informative read alignments across all alleles (after normalization for unbalanced SVs)">\n'
+    '##FORMAT=<ID=AD,Number=2,Type=Float,Description="Number of informative read alignments supporting each allele (after normalization by breakpoint number for unbalanced SVs)">\n'
+    '##FORMAT=<ID=PL,Number=3,Type=Integer,Description="Phred-scaled likelihood for each genotype">\n'
+    "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE\n"
+)
+
+
+class VcfError(Exception):
+    """The reference raises on this VCF line (exit status 1)."""
+
+
+_lut_cache = {}
+
+
+def log10comb_lut(nmax=LUT_NMAX):
+    """log10(C(n,k)) for 0<=k<=n<=nmax at [n(n+1)/2 + k], from CPython's own
+    math.log10(math.comb()) so it is bit-equal to predict-genotype.py:313."""
+    lut = _lut_cache.get(nmax)
+    if lut is None:
+        lut = np.empty((nmax + 1) * (nmax + 2) // 2, dtype=np.float64)
+        i = 0
+        for n in range(nmax + 1):
+            for k in range(n + 1):
+                lut[i] = math.log10(math.comb(n, k))
+                i += 1
+        _lut_cache[nmax] = lut
+    return lut
+
+
+def _info(info, label):
+    # predict-genotype.py:77-87
+    fields = info.split(";")
+    tag = label + "="
+    try:
+        if fields[0].startswith(tag):
+            return info.split(tag)[1].split(";")[0]
+        rest = info.split(";" + tag)[1]
+    except IndexError:
+        raise VcfError(f"INFO has no {label}=") from None
+    return rest if fields[-1].startswith(tag) else rest.split(";")[0]
+
+
+def parse_vcf(lines):
+    """Splits a VCF into output header text and body records.
+    Each record: (head_text, svtype_code|0x80 if short, key or None).
+    Mirrors predict-genotype.py:100-211 and the column cut at :250-256."""
+    header, recs = [], []
+    seen_ins = {}
+    for line in lines:
+        if line.startswith("##FORMAT"):
+            continue
+        if line.startswith("##"):
+            header.append((len(recs), line))
+            continue
+        if line.startswith("#C"):
+            header.append((len(recs), _FORMAT_LINES))
+            continue
+        cols = line.rstrip("\n").split("\t")
+        if len(cols) < 8:
+            raise VcfError("VCF line with fewer than 8 columns")
+        chrom, pos, alt, info = cols[0], cols[1], cols[4], cols[7]
+        svtype = ""
+        if "SVTYPE" in info:
+            parts = info.split("SVTYPE=")
+            if len(parts) < 2:
+                raise VcfError("SVTYPE without a value")
+            svtype = parts[1] if info.split(";")[-1].startswith("SVTYPE=") else parts[1].split(";")[0]
+        key, length = None, 0
+        if svtype not in ("BND", "INS"):
+            end = _info(info, "END")
+            if svtype in ("DEL", "INV"):
+                try:
+                    length = int(end) - int(pos)
+                except ValueError:
+                    raise VcfError("non-integer POS/END") from None
+                key = f"{chrom}:{svtype}-{pos}-{end}"
+        elif svtype == "INS":
+            k = seen_ins.get(pos, 0) + 1          # running count per POS string, any chromosome (:151-155)
+            seen_ins[pos] = k
+            key, length = f"{chrom}:INS-{pos}-{k}", len(alt)
+        else:
+            length = 50
+            key = "wrong_format"
+            for br in "[]":
+                if br in alt:
+                    pieces = [p for p in alt.split(br) if p]
+                    if len(pieces) < 2:
+                        raise VcfError("malformed BND ALT")
+                    key = (f"{chrom}:BND-{pos}{br}{pieces[1]}{br}" if ":" in pieces[1]
+                           else f"{chrom}:BND-{br}{pieces[0]}{br}{pos}")
+                    break
+        code = SVTYPE_CODE.get(svtype, 255)
+        if code != 255 and abs(length) < 50:
+            code |= 0x80
+        n_tabs = line.count("\t")
+        head = line.rstrip("\n") if n_tabs + 1 <= 8 else "\t".join(line.split("\t")[:8])
+        recs.append((head, code, key))
+    return header, recs
+
+
+def _num(twice, halved):
+    if not halved:
+        return str(twice >> 1)
+    return f"{twice >> 1}.5" if twice & 1 else f"{twice >> 1}.0"
+
+
+def genotype_device(d_counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR, device=None):
+    """Runs kernel 4 for len(sv_index) SVs; returns numpy (gt, flags, ad2, pl).
+    ``d_counts``: torch int32 [num_sv, 2] on the device (the filter's counters)."""
+    import torch
+    dev = d_counts.device if device is None else device
+    n = int(len(sv_index))
+    if not 0 < e < 1:
+        raise VcfError("error rate must be in (0, 1)")      # math.log10 raises in the reference
+    la, lb, lh = math.log10(1 - e), math.log10(e), math.log10(1 / 2)
+    lut = torch.from_numpy(log10comb_lut()).to(dev)
+    d_idx = torch.from_numpy(np.ascontiguousarray(sv_index, dtype=np.uint32).view(np.int32)).to(dev)
+    d_ty = torch.from_numpy(np.ascontiguousarray(svtype, dtype=np.uint8)).to(dev)
+    d_pl = torch.empty((max(n, 1), 3), dtype=torch.int64, device=dev)
+    d_gt = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    d_ad = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
+    d_fl = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def launch(k_override):
+        capi.check(capi.lib.svjg_genotype_device(
+            d_counts.data_ptr(), d_idx.data_ptr(), d_ty.data_ptr(), n, int(min_support), la, lb, lh,
+            lut.data_ptr(), LUT_NMAX, k_override.data_ptr() if k_override is not None else None,
+            d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), stream))
+
+    launch(None)
+    flags = d_fl.cpu().numpy()[:n]
+    need = np.nonzero(flags & capi.GT_NEED_K)[0]
+    if need.size:
+        # counts beyond the table: log10 C(n,k) from CPython for exactly those SVs
+        ad = d_ad.cpu().numpy().view(np.uint32)[:n]
+        kov = np.full(n, np.nan)
+        memo = {}
+        for i in need:
+            t1, t2 = int(ad[i, 0]), int(ad[i, 1])
+            r1 = (t1 >> 1) + ((t1 >> 1) & 1 if t1 & 1 else 0)
+            r2 = (t2 >> 1) + ((t2 >> 1) & 1 if t2 & 1 else 0)
+            v = memo.get((r1, r2))
+            if v is None:
+                v = memo[(r1, r2)] = math.log10(math.comb(r1 + r2, r1))
+            kov[i] = v
+        launch(torch.from_numpy(kov).to(dev))
+        flags = d_fl.cpu().numpy()[:n]
+        if (flags & capi.GT_NEED_K).any():
+            raise RuntimeError("genotype kernel could not represent a likelihood exactly")
+    return (d_gt.cpu().numpy()[:n], flags, d_ad.cpu().numpy().view(np.uint32)[:n], d_pl.cpu().numpy()[:n])
+
+
+def format_vcf(header, recs, gt, flags, ad2, pl):
+    """predict-genotype.py:248-271."""
+    out = []
+    hi = 0
+    genotyped = 0
+    for i, (head, _code, _key) in enumerate(recs):
+        while hi < len(header) and header[hi][0] <= i:
+            out.append(header[hi][1])
+            hi += 1
+        f = int(flags[i])
+        if f & capi.GT_GENOTYPED:
+            genotyped += 1
+            t1, t2 = int(ad2[i, 0]), int(ad2[i, 1])
+            h0, h1 = bool(f & capi.GT_HALVED_0), bool(f & capi.GT_HALVED_1)
+            sample = (f"{GT_TEXT[gt[i]]}:{_num(t1 + t2, h0 or h1)}:{_num(t1, h0)},{_num(t2, h1)}:"
+                      f"{pl[i, 0]},{pl[i, 1]},{pl[i, 2]}")
+        else:
+            sample = "./.:0:0,0:.,.,."
+        out.append(f"{head}\tGT:DP:AD:PL\t{sample}\n")
+    while hi < len(header):
+        out.append(header[hi][1])
+        hi += 1
+    return "".join(out), genotyped
+
+
+def genotype_vcf(tables, d_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR):
+    """decision_vcf (predict-genotype.py:89-279) with the counters already on
+    the device.  Returns (vcf text, number of genotyped SVs)."""
+    header, recs = parse_vcf(vcf_lines)
+    idx = np.fromiter((capi.NO_SV if r[2] is None else (lambda j: capi.NO_SV if j is None else j)(tables.find_sv(r[2]))
+                       for r in recs), dtype=np.uint32, count=len(recs))
+    ty = np.fromiter((r[1] for r in recs), dtype=np.uint8, count=len(recs))
+    if len(recs):
+        gt, flags, ad2, pl = genotype_device(d_counts, idx, ty, min_support, e)
+    else:
+        gt = flags = np.zeros(0, np.uint8)
+        ad2 = np.zeros((0, 2), np.uint32)
+        pl = np.zeros((0, 3), np.int64)
+    return format_vcf(header, recs, gt, flags, ad2, pl)

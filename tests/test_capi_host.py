@@ -1,0 +1,90 @@
+"""CPU-only checks of libsvjg.so: it loads, exports every symbol include/svjg.h
+declares, builds the host tables like the reference's loaders, and writes
+informative_aln.json byte-for-byte (hits supplied by the oracle here; the GPU
+tests supply them from the kernel)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, alt_len_from_gfa_text, read_golden
+from oracle import svjg_oracle as O
+from svjg import alnfilter, capi
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "svjg.h")).read()
+    declared = set(re.findall(r"\b(svjg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(capi.lib, name), f"{name} declared in svjg.h but not exported"
+    assert declared == set(capi.EXPORTS)
+    assert b"sm_100a" in capi.lib.svjg_version()
+
+
+@pytest.mark.parametrize("tag", ["c1", "s2", "s3", "s4"])
+def test_tables_match_reference_loaders(tag):
+    edges_text = read_golden("c1_svs_edges.json" if tag == "c1" else f"{tag}_svs_edges.json.gz")
+    gfa_text = read_golden(f"{tag}.gfa.gz")
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text)
+    d = json.loads(edges_text)
+    want_ids = sorted({sv for ents in d.values() for sv, _ in ents})
+    assert t.num_links == len(d)
+    assert t.sv_ids == want_ids
+    assert t.num_alt_nodes == len(alt_len_from_gfa_text(gfa_text))
+    assert t.find_sv(want_ids[-1]) == len(want_ids) - 1
+    assert t.find_sv("nope:DEL-1-2") is None
+
+
+def test_tables_reject_bad_json():
+    with pytest.raises(capi.SvjgError):
+        alnfilter.Tables.from_memory("[1, 2]", "")
+    with pytest.raises(capi.SvjgError):
+        alnfilter.Tables.from_memory('{"a@+@b@+": [["x:DEL-1-2", 0]', "")
+
+
+def _oracle_hits(lines, edges, alt, ids):
+    idx = {s: i for i, s in enumerate(ids)}
+    sv2, off, ln = [], [], []
+    pos = 0
+    for line in lines:
+        nbytes = len(line.encode())
+        for sv, allele in O.record_hits(line, edges, alt):
+            sv2.append(idx[sv] * 2 + (allele if allele >= 0 else allele + 2))
+            off.append(pos)
+            ln.append(nbytes)
+        pos += nbytes
+    return (np.array(sv2, np.uint32), np.array(off, np.uint64), np.array(ln, np.uint32))
+
+
+def test_json_emitter_byte_equal_c1(tmp_path):
+    edges_text = read_golden("c1_svs_edges.json")
+    gfa_text = read_golden("c1.gfa.gz")
+    gaf = read_golden("c1.gaf.gz")
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text)
+    sv2, off, ln = _oracle_hits(gaf.splitlines(True), json.loads(edges_text), alt_len_from_gfa_text(gfa_text), t.sv_ids)
+    # shuffled: the emitter must restore file order inside each list
+    perm = np.random.default_rng(1).permutation(len(sv2))
+    res = alnfilter.FilterResult(None, {"n_hits": len(sv2)}, sv2[perm], off[perm], ln[perm])
+    out = tmp_path / "c1_informative_aln.json"
+    alnfilter.write_informative_json(t, gaf.encode(), res, str(out))
+    assert out.read_text() == read_golden("c1_informative_aln.json.gz")
+
+
+def test_json_emitter_quirks_and_empty(tmp_path, quirks):
+    edges = json.loads(quirks["edges"])
+    alt = alt_len_from_gfa_text(quirks["gfa"])
+    t = alnfilter.Tables.from_memory(quirks["edges"], quirks["gfa"])
+    n = 0
+    for case in quirks["cases"]:
+        if case["rc"] != 0:
+            continue
+        sv2, off, ln = _oracle_hits(case["gaf"].splitlines(True), edges, alt, t.sv_ids)
+        res = alnfilter.FilterResult(None, {"n_hits": len(sv2)}, sv2, off, ln)
+        out = tmp_path / "q.json"
+        alnfilter.write_informative_json(t, case["gaf"].encode(), res, str(out))
+        assert out.read_text() == case["json"], case["name"]
+        n += 1
+    assert n >= 15

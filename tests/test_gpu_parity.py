@@ -1,0 +1,179 @@
+"""Parity of the CUDA path (through the C ABI) against the golden outputs of the
+unmodified reference and against the oracle.  Needs a GPU: -m gpu."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from conftest import alt_len_from_gfa_text, read_golden
+from oracle import svjg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from svjg import alnfilter, capi, genotype
+    return alnfilter, capi, genotype, torch
+
+
+def _tables(alnfilter, tag):
+    edges = read_golden("c1_svs_edges.json" if tag == "c1" else f"{tag}_svs_edges.json.gz")
+    return alnfilter.Tables.from_memory(edges, read_golden(f"{tag}.gfa.gz")).to_device(0), edges
+
+
+def _counts_dict(t, counts):
+    return {t.sv_ids[i]: [int(counts[i, 0]), int(counts[i, 1])] for i in range(t.num_sv) if counts[i].any()}
+
+
+@pytest.mark.parametrize("tag", ["c1", "s2", "s3", "s4"])
+def test_filter_and_genotype_match_reference(gpu, tag, tmp_path):
+    alnfilter, capi, genotype, torch = gpu
+    t, edges = _tables(alnfilter, tag)
+    gaf = read_golden(f"{tag}.gaf.gz").encode()
+    res = alnfilter.filter_host(t, gaf)
+    assert res.stats["n_records"] == gaf.count(b"\n")
+    # JSON, byte for byte
+    out = tmp_path / "x_informative_aln.json"
+    alnfilter.write_informative_json(t, gaf, res, str(out))
+    js = out.read_text()
+    if tag == "c1":
+        assert js == read_golden("c1_informative_aln.json.gz")
+        want_counts = {k: [len(v[0]), len(v[1])] for k, v in json.loads(js).items()}
+    else:
+        assert hashlib.sha256(js.encode()).hexdigest() == read_golden(f"{tag}_informative_aln.sha256").strip()
+        want_counts = json.loads(read_golden(f"{tag}_counts.json.gz"))
+    assert _counts_dict(t, res.counts) == want_counts
+    # genotype VCF, byte for byte
+    vcf_lines = read_golden("c1.vcf" if tag == "c1" else f"{tag}.vcf.gz").splitlines(True)
+    d_counts = torch.from_numpy(res.counts.view(np.int32)).cuda()
+    text, n = genotype.genotype_vcf(t, d_counts, vcf_lines)
+    assert text == read_golden("c1_genotype.vcf" if tag == "c1" else f"{tag}_genotype.vcf.gz")
+    assert f"Genotyped svs: {n}\n" == read_golden(f"{tag}_stdout.txt")
+    if tag == "c1":
+        text2, _ = genotype.genotype_vcf(t, d_counts, vcf_lines, 40, 0.001)
+        assert text2 == read_golden("c1_genotype_ms40_e1e-3.vcf")
+
+
+def test_device_resident_path_equals_host_path(gpu):
+    alnfilter, capi, genotype, torch = gpu
+    t, _ = _tables(alnfilter, "s3")
+    gaf = read_golden("s3.gaf.gz").encode()
+    host = alnfilter.filter_host(t, gaf)
+    d = torch.frombuffer(bytearray(gaf), dtype=torch.uint8).cuda()
+    f = alnfilter.DeviceFilter(t, hit_cap=host.n_hits + 8)
+    f.reset()
+    f.run(d)
+    r = f.result()
+    assert (r.counts == host.counts).all()
+    assert r.stats["n_hits"] == host.n_hits and r.stats["n_records"] == host.stats["n_records"]
+    a = sorted(zip(r.hit_sv2.tolist(), r.hit_off.tolist(), r.hit_len.tolist()))
+    b = sorted(zip(host.hit_sv2.tolist(), host.hit_off.tolist(), host.hit_len.tolist()))
+    assert a == b
+    # accumulate semantics: a second pass doubles the counters
+    f.run(d)
+    assert (f.counts.cpu().numpy().view(np.uint32) == 2 * host.counts).all()
+
+
+def test_quirk_cases(gpu, quirks, tmp_path):
+    alnfilter, capi, genotype, torch = gpu
+    t = alnfilter.Tables.from_memory(quirks["edges"], quirks["gfa"]).to_device(0)
+    for case in quirks["cases"]:
+        gaf = case["gaf"].encode()
+        if case["rc"] == 0:
+            res = alnfilter.filter_host(t, gaf)
+            out = tmp_path / "q.json"
+            alnfilter.write_informative_json(t, gaf, res, str(out))
+            assert out.read_text() == case["json"], case["name"]
+        else:
+            with pytest.raises(alnfilter.InputError):
+                alnfilter.filter_host(t, gaf)
+                pytest.fail(case["name"])
+
+
+def test_empty_and_tiny_inputs(gpu, tmp_path):
+    alnfilter, capi, genotype, torch = gpu
+    t, _ = _tables(alnfilter, "c1")
+    res = alnfilter.filter_host(t, b"")
+    assert res.n_hits == 0 and not res.counts.any()
+    out = tmp_path / "e.json"
+    alnfilter.write_informative_json(t, b"", res, str(out))
+    assert out.read_text() == "{}"
+    one = read_golden("c1.gaf.gz").splitlines(True)[0].encode()
+    assert alnfilter.filter_host(t, one).stats["n_records"] == 1
+    assert alnfilter.filter_host(t, one.rstrip(b"\n")).stats["n_records"] == 1
+
+
+def test_tile_boundaries_and_long_lines(gpu):
+    """Lines straddling 32 KiB tiles, lines longer than the look-ahead window
+    (parsed from global memory) and read names padded so that line starts fall
+    on every offset relative to the 16-byte scan chunks."""
+    alnfilter, capi, genotype, torch = gpu
+    t, edges = _tables(alnfilter, "c1")
+    edges = json.loads(edges)
+    alt = alt_len_from_gfa_text(read_golden("c1.gfa.gz"))
+    base = read_golden("c1.gaf.gz").splitlines(True)[:400]
+    lines = []
+    for i, l in enumerate(base):
+        cols = l.split("\t")
+        cols[0] = cols[0] + "x" * (i % 37)
+        l = "\t".join(cols)
+        if i % 97 == 5:
+            l = l.rstrip("\n") + "\tcg:Z:" + "5M1I" * 3000 + "\n"       # 12 KB > look-ahead
+        if i % 131 == 7:
+            l = l.rstrip("\n") + "\tzz:Z:" + "A" * 70000 + "\n"          # longer than a whole window
+        lines.append(l)
+    gaf = "".join(lines)
+    res = alnfilter.filter_host(t, gaf.encode())
+    want = O.hit_counts(O.filter_alignments(lines, edges, alt))
+    assert _counts_dict(t, res.counts) == {k: list(v) for k, v in want.items()}
+    assert res.stats["n_records"] == len(lines)
+
+
+def test_genotype_kat40_and_random_vectors(gpu):
+    alnfilter, capi, genotype, torch = gpu
+    rows = [r.split("\t") for r in read_golden("kat40.tsv").splitlines()]
+    cases = [(r[1], int(r[2]), int(r[3]), 3, 0.00005, r[4]) for r in rows]
+    for row in read_golden("lik_random.tsv.gz").splitlines():
+        ty, a, b, ms, e, geno, dp, numbers, prob = row.split("\t")
+        cases.append((ty, int(a), int(b), int(ms), float(e), f"{geno}:{dp}:{numbers}:{prob}"))
+    groups = {}
+    for c in cases:
+        groups.setdefault((c[3], c[4]), []).append(c)
+    checked = 0
+    for (ms, e), cs in groups.items():
+        counts = torch.tensor([[c[1], c[2]] for c in cs], dtype=torch.int64).to(torch.int32).cuda()
+        idx = np.arange(len(cs), dtype=np.uint32)
+        ty = np.array([genotype.SVTYPE_CODE[c[0]] for c in cs], dtype=np.uint8)
+        gt, flags, ad2, pl = genotype.genotype_device(counts, idx, ty, ms, e)
+        for i, c in enumerate(cs):
+            if c[1] == 0 and c[2] == 0:
+                # a key with no hit never reaches likelihood() in the pipeline (gate :216)
+                assert not flags[i] & capi.GT_GENOTYPED
+                continue
+            f = int(flags[i])
+            h0, h1 = bool(f & capi.GT_HALVED_0), bool(f & capi.GT_HALVED_1)
+            t1, t2 = int(ad2[i, 0]), int(ad2[i, 1])
+            got = (f"{genotype.GT_TEXT[gt[i]]}:{genotype._num(t1 + t2, h0 or h1)}:"
+                   f"{genotype._num(t1, h0)},{genotype._num(t2, h1)}:{pl[i, 0]},{pl[i, 1]},{pl[i, 2]}")
+            assert got == c[5], c
+            checked += 1
+    assert checked > 27000
+
+
+def test_genotype_oracle_sweep(gpu):
+    """Dense sweep of small counts (every rounding / tie / min-support corner)
+    against the oracle, all four SV types."""
+    alnfilter, capi, genotype, torch = gpu
+    pairs = [(a, b) for a in range(0, 41) for b in range(0, 41) if a or b]
+    counts = torch.tensor(pairs, dtype=torch.int32).cuda()
+    idx = np.arange(len(pairs), dtype=np.uint32)
+    for name, code in genotype.SVTYPE_CODE.items():
+        for ms in (0, 3, 7):
+            gt, flags, ad2, pl = genotype.genotype_device(counts, idx, np.full(len(pairs), code, np.uint8), ms)
+            for i, (a, b) in enumerate(pairs):
+                g, dp, ad, p = O.genotype_counts(a, b, name, ms)
+                assert genotype.GT_TEXT[gt[i]] == g and [str(x) for x in pl[i]] == p, (name, ms, a, b)
