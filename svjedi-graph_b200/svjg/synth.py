@@ -253,13 +253,16 @@ def _hex_names(rng, n):
 
 
 def simulate_gaf(g, n_records, seed, mean_len=31000, sigma=0.45, edge_frac=0.05,
-                 bnd_frac=None, cg_frac=0.0, idf=False, bare_single=True):
+                 bnd_frac=None, cg_frac=0.0, idf=False, bare_single=True, haps=None, stream=0):
     """Returns the GAF text (str).  Reads are laid on haplotypes; BND junction
     reads are made explicitly from the SV's alt link.  ``edge_frac`` of the
     multi-node records are clipped so that one side overlaps the breakpoint by
-    98..101 bases (the filter's threshold is 100)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    haps = _build_haps(g, rng)
+    98..101 bases (the filter's threshold is 100).  The haplotypes depend on
+    ``seed`` only; ``stream`` selects an independent stream of reads on them
+    (used by :func:`simulate_gaf_parallel` and for per-rank shards)."""
+    if haps is None:
+        haps = _build_haps(g, np.random.Generator(np.random.PCG64(seed)))
+    rng = np.random.Generator(np.random.PCG64([seed, 7919 + stream]))
     chroms = list(g.chrom_len)
     bnd_links = [(c, sv, lk) for (c, sv), lks in g.sv_alt_links.items() if sv.startswith("BND-") for lk in lks]
     if bnd_frac is None:
@@ -351,6 +354,34 @@ def simulate_gaf(g, n_records, seed, mean_len=31000, sigma=0.45, edge_frac=0.05,
     return "".join(lines)
 
 
+_PAR = {}
+
+
+def _par_worker(args):
+    k, n, kw = args
+    return simulate_gaf(_PAR["g"], n, _PAR["seed"], haps=_PAR["haps"], stream=_PAR["stream0"] + k, **kw)
+
+
+def simulate_gaf_parallel(g, n_records, seed, procs=None, chunk=200_000, stream0=0, **kw):
+    """Same distribution as :func:`simulate_gaf`, generated in ``chunk``-record
+    pieces on a fork pool; deterministic in (seed, chunk, stream0), independent
+    of ``procs``."""
+    import multiprocessing as mp
+    import os
+    haps = _build_haps(g, np.random.Generator(np.random.PCG64(seed)))
+    sizes = [chunk] * (n_records // chunk) + ([n_records % chunk] if n_records % chunk else [])
+    procs = procs or min(len(sizes), max(1, (os.cpu_count() or 2) - 1), 32)
+    _PAR.update(g=g, seed=seed, haps=haps, stream0=stream0 * 100_000)
+    jobs = [(k, n, kw) for k, n in enumerate(sizes)]
+    if procs <= 1 or len(sizes) == 1:
+        parts = [_par_worker(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_par_worker, jobs, chunksize=1)
+    _PAR.clear()
+    return "".join(parts)
+
+
 def _ref_len(name):
     s, e = name.rsplit(":", 1)[1].split("-")
     return int(e) - int(s) + 1
@@ -368,7 +399,7 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, scale=1.0, seed=None, **gaf_kw):
+def make_workload(name, scale=1.0, seed=None, stream0=0, **gaf_kw):
     """(Graph, vcf_text, gaf_text) for a named config shrunk by ``scale`` in both
     SV count and record count (genome scaled alike so densities stay put)."""
     kind, n_sv, n_rec, gscale, mean_len = WORKLOADS[name]
@@ -379,5 +410,8 @@ def make_workload(name, scale=1.0, seed=None, **gaf_kw):
     ins_max = 5000 if name != "C5" else 600
     rows = catalogue(kind, n_sv, chrom_len, seed, ins_max=ins_max)
     g = graphgen.build_graph(chrom_len, rows)
-    gaf = simulate_gaf(g, n_rec, seed + 7, mean_len=mean_len, **gaf_kw)
+    if n_rec > 400_000:
+        gaf = simulate_gaf_parallel(g, n_rec, seed + 7, mean_len=mean_len, stream0=stream0, **gaf_kw)
+    else:
+        gaf = simulate_gaf(g, n_rec, seed + 7, mean_len=mean_len, stream=stream0, **gaf_kw)
     return g, vcf_text(rows), gaf
