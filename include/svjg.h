@@ -67,6 +67,16 @@ uint64_t svjg_tables_device_bytes(const svjg_tables *t);  /* size of the device 
 const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len);
 /* index of an sv id, or UINT32_MAX — what `in_sv in dict` needs (predict-genotype.py:216) */
 uint32_t svjg_tables_find_sv(const svjg_tables *t, const char *sv_id, uint32_t len);
+/* Filter behaviour switches (OR-ed in; EXACT_CHECKS is set automatically when svs_edges
+ * holds an entry the reference would raise on):
+ *   SVJG_FLAG_EXACT_CHECKS  probe the link table even for links whose breakpoint-overlap
+ *                           test fails, so stats.n_checks counts every evaluation the
+ *                           reference makes (needed to mirror the -O crash, :269)
+ *   SVJG_FLAG_FORCE_GENERAL send every multi-node line through the general routine
+ *                           (test hook: fast path and general routine must agree) */
+#define SVJG_FLAG_EXACT_CHECKS 1u
+#define SVJG_FLAG_FORCE_GENERAL 2u
+int svjg_tables_set_flags(svjg_tables *t, uint32_t flags);
 /* copies the device image to `device` (cudaMalloc inside; freed by svjg_tables_free) */
 int svjg_tables_to_device(svjg_tables *t, int device);
 

@@ -8,13 +8,24 @@
 //
 // Layout: a persistent grid walks 32 KiB tiles of the byte buffer.  A tile plus
 // 8 KiB of look-ahead (and the 16 bytes in front of it) is staged into shared
-// memory by one TMA bulk copy (cp.async.bulk + mbarrier).  The CTA finds every
-// newline with 16-byte SWAR loads and an ordered block scan, then one thread
-// parses one line straight out of shared memory.  A line belongs to the tile
-// its first byte is in; a line running past the window is parsed from global
-// memory by the same routine.
+// memory by one TMA bulk copy (cp.async.bulk + mbarrier).  Per tile:
+//   A  the CTA finds every newline with 16-byte SWAR loads and an ordered block
+//      scan (line starts in shared memory);
+//   B  one thread per line splits the 12 columns, validates the integers and
+//      counts the path tokens — uniform work, warps stay converged; lines with
+//      >= 2 path nodes are compacted into a shared-memory queue;
+//   C  one thread per queued line resolves its links.  The fast path streams the
+//      path twice (lengths/total, then prefix sums + hash probes) and needs no
+//      per-token storage; it hands the line to the general routine whenever a
+//      token could be a substring of an earlier one (the first-occurrence rule
+//      of :206 and list.index() of :269-271 only differ from "own position"
+//      in that case), or any name is not of the plain chrom:start-end form.
+// A line belongs to the tile its first byte is in; a line running past the
+// window is handled by the general routine reading global memory.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+
+#include <algorithm>
 
 #include "svjg_internal.h"
 
@@ -32,7 +43,16 @@ constexpr int NWARPS = THREADS / 32;
 constexpr int CHUNKS = WIN / 16;
 constexpr int ROUNDS = (CHUNKS + THREADS - 1) / THREADS;   // 11
 constexpr int NL_CAP = CHUNKS;                 // more newlines than this => some line < 16 bytes
-constexpr int SMEM_BYTES = WIN + NL_CAP * 2 + 6 /*pad to 4*/ + ROUNDS * NWARPS * 4 + 16;
+constexpr int QCAP = 1024;                     // multi-node lines queued per tile (overflow: handled in place)
+constexpr int OFF_NL = WIN;
+constexpr int OFF_WTOT = OFF_NL + ((NL_CAP * 2 + 15) & ~15);
+constexpr int OFF_Q = OFF_WTOT + ((ROUNDS * NWARPS * 4 + 15) & ~15);
+constexpr int SMEM_BYTES = OFF_Q + QCAP * 8;
+static_assert(WIN <= 65536, "line starts are stored as 16-bit window offsets");
+
+constexpr uint32_t FLAG_EXACT_CHECKS = SVJG_FLAG_EXACT_CHECKS;   // probe links whose overlap test fails too
+constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through the general routine
+constexpr uint32_t COMMA_PATH = 0xFFFFFFFFu;
 
 struct FilterArgs {
     const uint8_t *gaf;
@@ -45,6 +65,7 @@ struct FilterArgs {
     uint64_t hit_cap;
     unsigned long long *stats;   // svjg_filter_stats as 8 x u64
     uint32_t n_tiles;
+    uint32_t flags;
 };
 
 struct Local {
@@ -66,6 +87,7 @@ struct GmemSrc {
 __device__ __forceinline__ bool py_space(uint32_t c) {
     return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
 }
+__device__ __forceinline__ bool is_delim(uint32_t c) { return (c | 2u) == '>'; }   // '<' = 0x3C, '>' = 0x3E
 
 __device__ __noinline__ void report(const FilterArgs &a, uint32_t code, uint64_t line_off) {
     atomicCAS(a.stats + 4, 0ull, (unsigned long long)code);
@@ -75,7 +97,7 @@ __device__ __noinline__ void report(const FilterArgs &a, uint32_t code, uint64_t
 // Python int(): optional surrounding whitespace, optional sign, decimal digits.
 // (Underscore separators and non-ASCII digits are not accepted: documented.)
 template <class Src>
-__device__ int parse_int(const Src &src, typename Src::pos_t b, typename Src::pos_t e, int64_t &out) {
+__device__ __noinline__ int parse_int(const Src &src, typename Src::pos_t b, typename Src::pos_t e, int64_t &out) {
     while (b < e && py_space(src[b])) ++b;
     while (e > b && py_space(src[e - 1])) --e;
     bool neg = false;
@@ -120,14 +142,102 @@ struct Rec {
         uint32_t l;
     };
 
+    // ------------------------------------------------------------------ phase B
+    // read_gaf_line (:184-198) on line.rstrip() (:126): 12 tab-separated columns,
+    // 9 of them int().  Returns the number of path tokens for a '<'/'>' path,
+    // COMMA_PATH for any other non-empty path.  Sets err where the reference raises.
+    __device__ uint32_t parse_fields(P s, P e) {
+        loc.n_rec++;
+        while (e > s && py_space(src[e - 1])) --e;
+        P pos = s;
+        int col = 0;
+        int64_t alen = 1;
+        uint32_t ntok = 0;
+        for (;;) {
+            P f = pos;
+            int r = 0;
+            if (col == 5) {
+                // path column: find its end and count tokens on the way (extract_nodes :366-367)
+                bool prev_delim = true;
+                for (; f < e; ++f) {
+                    uint32_t c = src[f];
+                    if (c == '\t') break;
+                    bool d = is_delim(c);
+                    ntok += (prev_delim && !d);
+                    prev_delim = d;
+                }
+                ps = pos;
+                pe = f;
+            } else {
+                // numeric columns: plain digit strings are checked on the fly
+                uint32_t nd = 0;
+                bool plain = true;
+                int64_t v = 0;
+                for (; f < e; ++f) {
+                    uint32_t c = src[f];
+                    if (c == '\t') break;
+                    uint32_t d = c - '0';
+                    plain &= (d <= 9);
+                    v = v * 10 + int64_t(d);
+                    ++nd;
+                }
+                bool numeric = (col >= 1 && col <= 3) || (col >= 6 && col <= 11);
+                if (numeric) {
+                    if (!plain || nd == 0 || nd > 18) r = parse_int(src, pos, f, v);
+                    if (col == 6) tlen = v;
+                    else if (col == 7) ts = v;
+                    else if (col == 8) te = v;
+                    else if (col == 10) alen = v;
+                }
+            }
+            if (r && !err) err = r;
+            ++col;
+            if (f >= e || col == 12) break;
+            pos = f + 1;
+        }
+        if (col < 12) err = SVJG_BAD_COLUMNS;
+        if (err) return 0;
+        if (alen == 0) {                                        // Am / Alen (:196) unless "id:f:" in line (:193)
+            bool found = false;
+            for (P j = s; j + 5 <= e && !found; ++j)
+                found = src[j] == 'i' && src[j + 1] == 'd' && src[j + 2] == ':' && src[j + 3] == 'f' && src[j + 4] == ':';
+            if (!found) {
+                err = SVJG_BAD_ALEN;
+                return 0;
+            }
+        }
+        if (ps == pe) {                                         // p[0] on an empty string (:366)
+            err = SVJG_BAD_PATH;
+            return 0;
+        }
+        angle = is_delim(src[ps]);
+        return angle ? ntok : COMMA_PATH;
+    }
+
+    // phase C re-reads Tlen, Ts, Te (columns 7-9) instead of carrying 24 bytes per queued line
+    __device__ void reparse_coords(P e) {
+        while (e > pe && py_space(src[e - 1])) --e;
+        P pos = pe + 1;
+        int64_t *dst[3] = {&tlen, &ts, &te};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            P f = pos;
+            while (f < e && src[f] != '\t') ++f;
+            parse_int(src, pos, f, *dst[k]);
+            pos = f + 1;
+        }
+        angle = true;
+    }
+
+    // --------------------------------------------------------- shared pieces
     // tokens of the path column: '<'/'>' separated, or (path not starting with
     // one of those) ','-separated pieces minus their last character
     __device__ bool next_tok(P &cur, Tok &t) const {
         if (angle) {
-            while (cur < pe && (src[cur] | 2u) == '>') ++cur;   // '<' = 0x3C, '>' = 0x3E
+            while (cur < pe && is_delim(src[cur])) ++cur;
             if (cur >= pe) return false;
             t.b = cur;
-            while (cur < pe && (src[cur] | 2u) != '>') ++cur;
+            while (cur < pe && !is_delim(src[cur])) ++cur;
             t.l = uint32_t(cur - t.b);
             return true;
         }
@@ -157,28 +267,6 @@ struct Rec {
         TokHash h = tok_init();
         for (uint32_t i = 0; i < t.l; ++i) tok_step(h, src[t.b + i]);
         return tok_value(h);
-    }
-
-    // strand of a token: the byte in front of the FIRST occurrence of its text
-    // anywhere in the path (filter-alignments.py:206).  1 = '+'.
-    __device__ int strand(const Tok &t) {
-        if (t.l == 0) {
-            err = SVJG_BAD_PATH;
-            return 0;
-        }
-        uint32_t c0 = src[t.b];
-        P j = ps;
-        for (; j < t.b; ++j) {
-            if (src[j] != c0) continue;
-            uint32_t i = 1;
-            while (i < t.l && src[j + i] == src[t.b + i]) ++i;
-            if (i == t.l) break;
-        }
-        if (j == ps) {
-            err = SVJG_BAD_PATH;
-            return 0;
-        }
-        return src[j - 1] == '>';
     }
 
     __device__ bool names_match(uint32_t off, const Tok &t) const {
@@ -211,26 +299,211 @@ struct Rec {
         }
     }
 
-    // filter-alignments.py:343-349
+    // alt_node_len[name] (:346); false when the name is not in the GFA
+    __device__ bool alt_lookup(uint64_t tokh, const Tok &t, int64_t &len) const {
+        uint64_t h = alt_hash(tokh);
+        uint32_t i = uint32_t(h) & a.tb.alt_mask;
+        for (;;) {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.alts + i);
+            uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+            if (!hi.z) return false;
+            uint64_t sh = (uint64_t(lo.y) << 32) | lo.x;
+            if (sh == h && lo.w == t.l && names_match(lo.z, t)) {
+                len = int64_t((uint64_t(hi.y) << 32) | hi.x);
+                return true;
+            }
+            i = (i + 1) & a.tb.alt_mask;
+        }
+    }
+
+    __device__ void emit(uint32_t sv2) {
+        // warp-aggregated: one counter atomic per distinct SV allele among the
+        // lanes that are here together, one cursor atomic for all of them
+        cg::coalesced_group active = cg::coalesced_threads();
+        cg::coalesced_group same = cg::labeled_partition(active, sv2);
+        if (same.thread_rank() == 0) atomicAdd(a.counts + sv2, same.size());
+        unsigned long long base = 0;
+        if (active.thread_rank() == 0) base = atomicAdd(a.stats + 0, (unsigned long long)active.size());
+        base = active.shfl(base, 0) + active.thread_rank();
+        if (base < a.hit_cap) {
+            a.hit_sv2[base] = sv2;
+            a.hit_off[base] = line_off;
+            a.hit_len[base] = line_len;
+        }
+    }
+
+    // forward and reverse key of one link (:141-148) and their entries (:150-166).
+    // ok_known: the overlap verdict is already there (fast path); otherwise it is
+    // computed once, on the first key that has entries, by the general overlap().
+    __device__ void link(const Tok &A, uint64_t hA, int sA, const Tok &B, uint64_t hB, int sB, bool ok_known, bool ok) {
+#pragma unroll 1
+        for (int dir = 0; dir < 2; ++dir) {
+            LinkSlot s;
+            bool hit = dir == 0 ? probe(hA, sA, A, hB, sB, B, s) : probe(hB, !sB, B, hA, !sA, A, s);
+            if (!hit) continue;
+            if (s.meta & 8u) {
+                err = SVJG_BAD_ENTRY;
+                return;
+            }
+            uint32_t cnt = s.meta >> 4;
+            if (cnt == 0) continue;
+            loc.n_checks += cnt;
+            if (!ok_known) {
+                ok = overlap(A, B);
+                if (err) return;
+                ok_known = true;
+            }
+            if (!ok) continue;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                uint32_t sv2 = k == 0 ? s.ent0 : __ldg(a.tb.entries + s.ent_begin + k);
+                if (sv2 == ENTRY_POISON) {
+                    err = SVJG_BAD_ENTRY;
+                    return;
+                }
+                emit(sv2);
+            }
+        }
+    }
+
+    // ------------------------------------------------------- phase C, fast path
+    // One token of a '<'/'>' path, streamed: hash, node length and the two
+    // "could be a substring of an earlier token" signals.
+    struct Scan {
+        Tok t;
+        uint64_t hash, sig;
+        int64_t len;
+        uint32_t start_val;
+        int plus;          // 1 when the delimiter in front is '>'
+        bool alt, plain;   // plain: exactly one ':', then digits-digits (<= 9 each) or digits.<anything>
+    };
+
+    __device__ bool scan_tok(P &cur, Scan &o) const {
+        while (cur < pe && is_delim(src[cur])) ++cur;
+        if (cur >= pe) return false;
+        o.plus = src[cur - 1] == '>';
+        o.t.b = cur;
+        TokHash h = tok_init();
+        uint64_t sig = 0;
+        uint32_t v0 = 0, v1 = 0, nd0 = 0, nd1 = 0, dash = 0, colons = 0, prev = 0;
+        bool dot = false, junk = false;
+        for (; cur < pe; ++cur) {
+            uint32_t c = src[cur];
+            if (is_delim(c)) break;
+            tok_step(h, c);
+            if (cur != o.t.b) sig |= 1ull << ((c ^ (prev << 3) ^ (prev >> 2)) & 63);   // adjacent byte pair
+            prev = c;
+            uint32_t d = c - '0';
+            if (d <= 9) {
+                if (dot) {
+                } else if (dash == 0) {
+                    v0 = v0 * 10 + d;
+                    ++nd0;
+                } else {
+                    v1 = v1 * 10 + d;
+                    ++nd1;
+                }
+            } else if (c == ':') {
+                ++colons;
+                v0 = v1 = nd0 = nd1 = dash = 0;
+                dot = junk = false;
+            } else if (c == '-' && !dot) {
+                ++dash;
+            } else if (c == '.' && dash == 0) {
+                dot = true;
+            } else if (!dot) {
+                junk = true;
+            }
+        }
+        o.t.l = uint32_t(cur - o.t.b);
+        o.hash = tok_value(h);
+        o.sig = sig;
+        o.alt = dot;
+        o.start_val = v0;
+        o.plain = colons == 1 && !junk && nd0 >= 1 && nd0 <= 9 && (dot || (dash == 1 && nd1 >= 1 && nd1 <= 9));
+        o.len = int64_t(v1) - int64_t(v0) + 1;
+        return true;
+    }
+
+    // false -> the general routine must take the line
+    __device__ bool fast() {
+        // pass 1: total path length; bail out on anything that is not plain
+        int64_t total = 0;
+        uint64_t seen = 0;
+        uint32_t lo[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, hi[2] = {0, 0};
+        uint32_t n = 0;
+        P cur = ps;
+        Scan t;
+        while (scan_tok(cur, t)) {
+            if (!t.plain) return false;
+            if (t.alt && !alt_lookup(t.hash, t.t, t.len)) return false;
+            if (t.len <= 0) return false;
+            // t can only sit inside an earlier token x if every adjacent byte pair of t
+            // occurs in x, and (single ':' in both) x has the same start digits and kind
+            int k = t.alt;
+            if (n && (t.sig & ~seen) == 0 && t.start_val >= lo[k] && t.start_val <= hi[k]) return false;
+            seen |= t.sig;
+            lo[k] = min(lo[k], t.start_val);
+            hi[k] = max(hi[k], t.start_val);
+            total += t.len;
+            ++n;
+        }
+        // pass 2: every token is its own first occurrence, so strand = own delimiter
+        // (:206), index = own position (:269-271) and the overlap sums are a prefix
+        // sum and its complement (:269-273)
+        const int64_t tail = tlen - te - 1;
+        const bool all = a.flags & FLAG_EXACT_CHECKS;
+        cur = ps;
+        Scan A, B;
+        scan_tok(cur, A);
+        if (A.alt) alt_lookup(A.hash, A.t, A.len);
+        int64_t pre = A.len;
+        for (uint32_t i = 1; i < n; ++i) {
+            scan_tok(cur, B);
+            if (B.alt) alt_lookup(B.hash, B.t, B.len);
+            bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);
+            if (ok || all) {
+                link(A.t, A.hash, A.plus, B.t, B.hash, B.plus, true, ok);
+                if (err) return true;
+            }
+            pre += B.len;
+            A = B;
+        }
+        return true;
+    }
+
+    // ---------------------------------------------------- general (exact) routine
+    // strand of a token: the byte in front of the FIRST occurrence of its text
+    // anywhere in the path (:206).  1 = '+'.
+    __device__ int strand(const Tok &t) {
+        if (t.l == 0) {
+            err = SVJG_BAD_PATH;
+            return 0;
+        }
+        uint32_t c0 = src[t.b];
+        P j = ps;
+        for (; j < t.b; ++j) {
+            if (src[j] != c0) continue;
+            uint32_t i = 1;
+            while (i < t.l && src[j + i] == src[t.b + i]) ++i;
+            if (i == t.l) break;
+        }
+        if (j == ps) {
+            err = SVJG_BAD_PATH;
+            return 0;
+        }
+        return src[j - 1] == '>';
+    }
+
+    // get_node_len (:343-349)
     __device__ int64_t node_len(const Tok &t) {
         P end = t.b + t.l, q = end;
         while (q > t.b && src[q - 1] != ':') --q;
         bool dot = false;
         for (P i = q; i < end; ++i) dot |= (src[i] == '.');
         if (dot) {
-            uint64_t h = alt_hash(tok_hash(t));
-            uint32_t i = uint32_t(h) & a.tb.alt_mask;
-            for (;;) {
-                const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.alts + i);
-                uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-                if (!hi.z) {
-                    err = SVJG_BAD_ALTNODE;
-                    return 0;
-                }
-                uint64_t sh = (uint64_t(lo.y) << 32) | lo.x;
-                if (sh == h && lo.w == t.l && names_match(lo.z, t)) return int64_t((uint64_t(hi.y) << 32) | hi.x);
-                i = (i + 1) & a.tb.alt_mask;
-            }
+            int64_t len = 0;
+            if (!alt_lookup(tok_hash(t), t, len)) err = SVJG_BAD_ALTNODE;
+            return len;
         }
         P d1 = q;
         while (d1 < end && src[d1] != '-') ++d1;
@@ -272,97 +545,8 @@ struct Rec {
         return (left - ts >= a.d_over) && (right - (tlen - te - 1) >= a.d_over);
     }
 
-    __device__ void emit(uint32_t sv2) {
-        // warp-aggregated: one counter atomic per distinct SV allele among the
-        // lanes that are here together, one cursor atomic for all of them
-        cg::coalesced_group active = cg::coalesced_threads();
-        cg::coalesced_group same = cg::labeled_partition(active, sv2);
-        if (same.thread_rank() == 0) atomicAdd(a.counts + sv2, same.size());
-        unsigned long long base = 0;
-        if (active.thread_rank() == 0) base = atomicAdd(a.stats + 0, (unsigned long long)active.size());
-        base = active.shfl(base, 0) + active.thread_rank();
-        if (base < a.hit_cap) {
-            a.hit_sv2[base] = sv2;
-            a.hit_off[base] = line_off;
-            a.hit_len[base] = line_len;
-        }
-    }
-
-    __device__ void link(const Tok &A, uint64_t hA, int sA, const Tok &B, uint64_t hB, int sB) {
-        bool have_ok = false, ok = false;
-#pragma unroll 1
-        for (int dir = 0; dir < 2; ++dir) {
-            LinkSlot s;
-            bool hit = dir == 0 ? probe(hA, sA, A, hB, sB, B, s) : probe(hB, !sB, B, hA, !sA, A, s);
-            if (!hit) continue;
-            if (s.meta & 8u) {
-                err = SVJG_BAD_ENTRY;
-                return;
-            }
-            uint32_t cnt = s.meta >> 4;
-            if (cnt == 0) continue;
-            loc.n_checks += cnt;
-            if (!have_ok) {
-                ok = overlap(A, B);
-                if (err) return;
-                have_ok = true;
-            }
-            if (!ok) continue;
-            for (uint32_t k = 0; k < cnt; ++k) {
-                uint32_t sv2 = k == 0 ? s.ent0 : __ldg(a.tb.entries + s.ent_begin + k);
-                if (sv2 == ENTRY_POISON) {
-                    err = SVJG_BAD_ENTRY;
-                    return;
-                }
-                emit(sv2);
-            }
-        }
-    }
-
-    // one GAF line [s, e) without its newline
-    __device__ void run(P s, P e) {
-        loc.n_rec++;
-        while (e > s && py_space(src[e - 1])) --e;            // line.rstrip()  (:126)
-        // --- read_gaf_line (:184-198): 12 tab-separated columns, 9 of them int()
-        P pos = s;
-        int col = 0;
-        int64_t alen = 1;
-        for (;;) {
-            P f = pos;
-            while (f < e && src[f] != '\t') ++f;
-            int64_t v = 0;
-            int r = 0;
-            switch (col) {
-                case 1: case 2: case 3: case 9: case 11: r = parse_int(src, pos, f, v); break;
-                case 5: ps = pos; pe = f; break;
-                case 6: r = parse_int(src, pos, f, tlen); break;
-                case 7: r = parse_int(src, pos, f, ts); break;
-                case 8: r = parse_int(src, pos, f, te); break;
-                case 10: r = parse_int(src, pos, f, alen); break;
-                default: break;
-            }
-            if (r && !err) err = r;
-            ++col;
-            if (f >= e || col == 12) break;
-            pos = f + 1;
-        }
-        if (col < 12) err = SVJG_BAD_COLUMNS;
-        if (err) return;
-        if (alen == 0) {                                        // Am / Alen (:196) unless "id:f:" in line (:193)
-            bool found = false;
-            for (P j = s; j + 5 <= e && !found; ++j)
-                found = src[j] == 'i' && src[j + 1] == 'd' && src[j + 2] == ':' && src[j + 3] == 'f' && src[j + 4] == ':';
-            if (!found) {
-                err = SVJG_BAD_ALEN;
-                return;
-            }
-        }
-        // --- extract_nodes (:351-373)
-        if (ps == pe) {
-            err = SVJG_BAD_PATH;
-            return;
-        }
-        angle = (src[ps] | 2u) == '>';
+    // extract_nodes / get_aln_links / lookups for any path (:130-166)
+    __device__ __noinline__ void general() {
         uint32_t n = 0;
         {
             P cur = ps;
@@ -370,9 +554,8 @@ struct Rec {
             while (next_tok(cur, t)) ++n;
         }
         if (n < 2) return;                                       // :133
-        loc.n_multi++;
+        if (!angle) loc.n_multi++;
         loc.n_generic++;
-        // --- links (:200-219) and lookups (:139-166)
         P cur = ps;
         Tok A, B;
         next_tok(cur, A);
@@ -384,12 +567,18 @@ struct Rec {
             uint64_t hB = tok_hash(B);
             int sB = strand(B);
             if (err) return;
-            link(A, hA, sA, B, hB, sB);
+            link(A, hA, sA, B, hB, sB, false, false);
             if (err) return;
             A = B;
             hA = hB;
             sA = sB;
         }
+    }
+
+    // links of a line already split by parse_fields() / reparse_coords()
+    __device__ void resolve() {
+        if (angle && !(a.flags & FLAG_FORCE_GENERAL) && fast()) return;
+        if (!err) general();
     }
 };
 
@@ -429,13 +618,14 @@ __device__ __forceinline__ uint32_t nl_bytes(uint32_t w) {
 // bits 7,15,23,31 -> bits 0..3
 __device__ __forceinline__ uint32_t pack4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
 
-__global__ void __launch_bounds__(THREADS) filter_kernel(const FilterArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *win = smem;
-    uint16_t *nl = reinterpret_cast<uint16_t *>(smem + WIN);
-    uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + WIN + ((NL_CAP * 2 + 7) & ~7));
+    uint16_t *nl = reinterpret_cast<uint16_t *>(smem + OFF_NL);
+    uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + OFF_WTOT);
+    ushort4 *queue = reinterpret_cast<ushort4 *>(smem + OFF_Q);   // (start, path start, path end, line end)
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_total, s_qn;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_init(&mbar, 1);
@@ -454,10 +644,13 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const FilterArgs a) {
         const uint32_t bulk = nbytes & ~15u;
         const uint32_t valid_end = dst0 + nbytes;
 
-        if (tid == 0 && bulk) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&mbar, bulk);
-            bulk_g2s(win + dst0, a.gaf + g0, bulk, &mbar);
+        if (tid == 0) {
+            s_qn = 0;
+            if (bulk) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&mbar, bulk);
+                bulk_g2s(win + dst0, a.gaf + g0, bulk, &mbar);
+            }
         }
         for (uint32_t i = bulk + tid; i < nbytes; i += THREADS) win[dst0 + i] = __ldg(a.gaf + g0 + i);
         if (dst0 && tid < HEAD) win[tid] = tid == HEAD - 1 ? '\n' : 0;   // "newline" in front of byte 0 of the file
@@ -468,7 +661,7 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const FilterArgs a) {
         }
         __syncthreads();
 
-        // ---- kernel 1: newline scan, ordered compaction of line starts
+        // ---- phase A: newline scan, ordered compaction of line starts
         uint32_t masks[ROUNDS];
         uint32_t excl[ROUNDS];
 #pragma unroll
@@ -533,30 +726,87 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const FilterArgs a) {
         }
         __syncthreads();
 
-        // ---- kernels 2+3: one thread per line
         if (m_total <= NL_CAP) {
-            for (uint32_t k = tid; k < m_total; k += THREADS) {
-                uint32_t start = uint32_t(nl[k]) + 1;
-                if (start < HEAD || start >= HEAD + TILE || start >= valid_end) continue;
-                uint32_t off = uint32_t(tile_start) + (start - HEAD);
-                if (k + 1 < m_total) {
-                    uint32_t end = nl[k + 1];
-                    Rec<SmemSrc> rec(a, SmemSrc{win}, off, end - start + 1, loc);
-                    rec.run(start, end);
-                    if (rec.err) report(a, rec.err, off);
-                } else if (at_eof) {
-                    Rec<SmemSrc> rec(a, SmemSrc{win}, off, valid_end - start, loc);
-                    rec.run(start, valid_end);
-                    if (rec.err) report(a, rec.err, off);
-                } else {
-                    // the line runs past the staged window: same routine on global memory
-                    uint64_t e = tile_start + TILE + LOOKAHEAD;
-                    while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
-                    uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
-                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-                    rec.run(uint64_t(off), e);
-                    if (rec.err) report(a, rec.err, off);
+            // ---- phase B: one thread per line, columns + integers + token count
+            for (uint32_t k0 = 0; k0 < m_total; k0 += THREADS) {
+                uint32_t k = k0 + tid;
+                bool queued = false;
+                uint32_t start = 0, end = 0, rps = 0, rpe = 0;
+                if (k < m_total) {
+                    start = uint32_t(nl[k]) + 1;
+                    bool owned = start >= HEAD && start < HEAD + TILE && start < valid_end;
+                    if (owned) {
+                        uint32_t off = uint32_t(tile_start) + (start - HEAD);
+                        bool in_win = (k + 1 < m_total) || at_eof;
+                        if (in_win) {
+                            end = (k + 1 < m_total) ? nl[k + 1] : valid_end;
+                            uint32_t len = end - start + ((k + 1 < m_total) ? 1u : 0u);
+                            Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
+                            uint32_t ntok = rec.parse_fields(start, end);
+                            if (rec.err) {
+                                report(a, rec.err, off);
+                            } else if (ntok == COMMA_PATH) {
+                                rec.general();
+                                if (rec.err) report(a, rec.err, off);
+                            } else if (ntok >= 2) {
+                                loc.n_multi++;
+                                queued = true;
+                                rps = rec.ps;
+                                rpe = rec.pe;
+                            }
+                        } else {
+                            // the line runs past the staged window: general routine on global memory
+                            uint64_t e = tile_start + TILE + LOOKAHEAD;
+                            while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
+                            uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
+                            Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+                            uint32_t ntok = rec.parse_fields(uint64_t(off), e);
+                            if (!rec.err && ntok >= 2) {
+                                if (ntok != COMMA_PATH) loc.n_multi++;
+                                rec.general();
+                            }
+                            if (rec.err) report(a, rec.err, off);
+                        }
+                    }
                 }
+                // compaction of the multi-node lines (one shared atomic per warp)
+                uint32_t bal = __ballot_sync(0xFFFFFFFFu, queued);
+                if (bal) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (queued) {
+                        uint32_t q = base + __popc(bal & ((1u << lane) - 1));
+                        if (q < QCAP) {
+                            queue[q] = make_ushort4(uint16_t(start), uint16_t(rps), uint16_t(rpe), uint16_t(end));
+                        } else {
+                            // queue full: resolve in place
+                            uint32_t off = uint32_t(tile_start) + (start - HEAD);
+                            uint32_t len = end - start + ((end < valid_end && win[end] == '\n') ? 1u : 0u);
+                            Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
+                            rec.ps = rps;
+                            rec.pe = rpe;
+                            rec.reparse_coords(end);
+                            rec.resolve();
+                            if (rec.err) report(a, rec.err, off);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase C: one thread per multi-node line
+            const uint32_t qn = min(s_qn, uint32_t(QCAP));
+            for (uint32_t q = tid; q < qn; q += THREADS) {
+                ushort4 e4 = queue[q];
+                uint32_t start = e4.x, end = e4.w;
+                uint32_t off = uint32_t(tile_start) + (start - HEAD);
+                uint32_t len = end - start + ((end < valid_end && win[end] == '\n') ? 1u : 0u);
+                Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
+                rec.ps = e4.y;
+                rec.pe = e4.z;
+                rec.reparse_coords(end);
+                rec.resolve();
+                if (rec.err) report(a, rec.err, off);
             }
         }
         __syncthreads();
@@ -633,6 +883,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.hit_cap = hit_cap;
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
+    a.flags = t->filter_flags;
     int grid = int(std::min<uint32_t>(a.n_tiles, uint32_t(g_grid_cap)));
     filter_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
     SVJG_CUDA(cudaGetLastError());

@@ -17,6 +17,7 @@ struct svjg_tables {
     std::vector<uint8_t> blob;
     std::vector<uint32_t> entries;
     uint32_t n_keys = 0, n_link_slots = 0, n_alt = 0;
+    uint32_t filter_flags = 0;                // SVJG_FLAG_* passed to the filter kernel
     // device image
     int device = -1;
     void *d_links = nullptr, *d_alts = nullptr, *d_blob = nullptr, *d_entries = nullptr;

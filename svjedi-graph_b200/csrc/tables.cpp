@@ -442,6 +442,12 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         return false;
     }
     t->n_keys = uint32_t(keys.size());
+    // entries on which the reference raises make skipping any probe unsafe
+    for (auto &k : keys) {
+        if (k.poison_key) t->filter_flags |= SVJG_FLAG_EXACT_CHECKS;
+        for (auto &e : k.ents)
+            if (e.second < 0) t->filter_flags |= SVJG_FLAG_EXACT_CHECKS;
+    }
 
     struct Parse {
         uint32_t key, split;   // nL = key[0:split), sL = key[split+1], nR = key[split+3 : len-2)
@@ -568,6 +574,12 @@ extern "C" int svjg_tables_load(const char *svs_edges_json_path, const char *gfa
     if (!read_file(svs_edges_json_path, edges)) return set_error(SVJG_E_IO, std::string("cannot read ") + svs_edges_json_path);
     if (!read_file(gfa_path, gfa)) return set_error(SVJG_E_IO, std::string("cannot read ") + gfa_path);
     return svjg_tables_from_memory(edges.data(), edges.size(), gfa.data(), gfa.size(), out);
+}
+
+extern "C" int svjg_tables_set_flags(svjg_tables *t, uint32_t flags) {
+    if (!t) return set_error(SVJG_E_ARG, "svjg_tables_set_flags: NULL tables");
+    t->filter_flags |= flags & (SVJG_FLAG_EXACT_CHECKS | SVJG_FLAG_FORCE_GENERAL);
+    return SVJG_OK;
 }
 
 extern "C" uint32_t svjg_tables_num_sv(const svjg_tables *t) { return t ? uint32_t(t->sv_ids.size()) : 0; }

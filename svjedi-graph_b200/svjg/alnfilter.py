@@ -47,6 +47,10 @@ class Tables:
         self.device = int(device)
         return self
 
+    def set_flags(self, flags):
+        capi.check(capi.lib.svjg_tables_set_flags(self._h, int(flags)))
+        return self
+
     @property
     def device_bytes(self):
         return int(capi.lib.svjg_tables_device_bytes(self._h))

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsvjg.so")
 OK, E_CUDA, E_ARG, E_IO, E_JSON, E_INPUT, E_HITS_OVERFLOW, E_NOMEM = range(8)
 GT_GENOTYPED, GT_HALVED_0, GT_HALVED_1, GT_NEED_K = 1, 2, 4, 8
 NO_SV = 0xFFFFFFFF
+FLAG_EXACT_CHECKS, FLAG_FORCE_GENERAL = 1, 2
 
 BAD_REASONS = {
     1: "blank line or fewer than 12 columns",
@@ -59,6 +60,7 @@ def _load():
         "svjg_tables_sv_id": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "svjg_tables_find_sv": (C.c_uint32, [vp, C.c_char_p, C.c_uint32]),
         "svjg_tables_to_device": (C.c_int, [vp, C.c_int]),
+        "svjg_tables_set_flags": (C.c_int, [vp, C.c_uint32]),
         "svjg_filter_reset": (C.c_int, [u32p, C.c_uint32, vp, vp]),
         "svjg_filter_device": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint64, C.c_int64, u32p, u32p, u32p, u32p,
                                          C.c_uint64, vp, vp]),

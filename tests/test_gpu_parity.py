@@ -177,3 +177,26 @@ def test_genotype_oracle_sweep(gpu):
             for i, (a, b) in enumerate(pairs):
                 g, dp, ad, p = O.genotype_counts(a, b, name, ms)
                 assert genotype.GT_TEXT[gt[i]] == g and [str(x) for x in pl[i]] == p, (name, ms, a, b)
+
+
+@pytest.mark.parametrize("tag", ["c1", "s2", "s3", "s4"])
+def test_fast_path_equals_general_routine(gpu, tag):
+    """The storage-free fast path and the quirk-exact general routine must give
+    identical hits; the fast path must actually be taken for most lines."""
+    alnfilter, capi, genotype, torch = gpu
+    gaf = read_golden(f"{tag}.gaf.gz").encode()
+    t_fast, _ = _tables(alnfilter, tag)
+    t_gen, _ = _tables(alnfilter, tag)
+    t_gen.set_flags(capi.FLAG_FORCE_GENERAL)
+    a = alnfilter.filter_host(t_fast, gaf)
+    b = alnfilter.filter_host(t_gen, gaf)
+    assert (a.counts == b.counts).all()
+    assert sorted(zip(a.hit_sv2.tolist(), a.hit_off.tolist())) == sorted(zip(b.hit_sv2.tolist(), b.hit_off.tolist()))
+    assert b.stats["n_generic"] == b.stats["n_multi"] > 0
+    assert a.stats["n_generic"] < 0.35 * a.stats["n_multi"], a.stats
+    # exact-check mode probes more links but changes no result
+    t_all, _ = _tables(alnfilter, tag)
+    t_all.set_flags(capi.FLAG_EXACT_CHECKS)
+    c = alnfilter.filter_host(t_all, gaf)
+    assert (c.counts == a.counts).all() and c.stats["n_checks"] >= a.stats["n_checks"]
+    assert c.stats["n_checks"] == b.stats["n_checks"]
