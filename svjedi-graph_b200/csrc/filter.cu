@@ -7,25 +7,31 @@
 // reverse_link :221-225, check_bkpt_overlap :258-273, get_node_len :343-349.
 //
 // Layout: a persistent grid walks 32 KiB tiles of the byte buffer.  A tile plus
-// 8 KiB of look-ahead (and the 16 bytes in front of it) is staged into shared
-// memory by one TMA bulk copy (cp.async.bulk + mbarrier).  Per tile:
-//   A  the CTA finds every newline with 16-byte SWAR loads and an ordered block
-//      scan (line starts in shared memory);
-//   B  one thread per line splits the 12 columns, validates the integers and
-//      counts the path tokens — uniform work, warps stay converged; lines with
-//      >= 2 path nodes are compacted into a shared-memory queue;
-//   C  one thread per queued line resolves its links.  The fast path streams the
-//      path twice (lengths/total, then prefix sums + hash probes) and needs no
-//      per-token storage; it hands the line to the general routine whenever a
-//      token could be a substring of an earlier one (the first-occurrence rule
-//      of :206 and list.index() of :269-271 only differ from "own position"
-//      in that case), or any name is not of the plain chrom:start-end form.
-// A line belongs to the tile its first byte is in; a line running past the
-// window is handled by the general routine reading global memory.
+// 8 KiB of look-ahead (and the 32 bytes in front of it) is staged into shared
+// memory by one TMA bulk copy (cp.async.bulk + mbarrier).  Work is then spread
+// at the granularity that keeps lanes busy in each phase:
+//   A  byte-parallel: every thread classifies 16-byte chunks with SWAR compares,
+//      writes a newline bitmap and appends the line starts it sees to a list;
+//   B  line-parallel: one thread per line finds the 12 columns with word-wide
+//      tab compares, validates the integer columns, classifies the path column
+//      and, for paths with >= 2 nodes, appends one record per node to a token list;
+//   C  token-parallel: one thread per path node hashes the name (4 bytes a step),
+//      parses chrom:start-end / looks the alt node up, and stores the record;
+//   D  line-parallel over multi-node lines: Tlen/Ts/Te, prefix sums of the node
+//      lengths, the breakpoint-overlap verdict of every link; token-parallel
+//      check that no node name can occur inside an earlier one;
+//   E  link-parallel: forward and reverse key probes of the link hash, counter
+//      atomics and hit tuples.
+// Anything that is not of the plain shape (odd integers, odd node names, a name
+// that could be a substring of an earlier one, lines longer than the window, ...)
+// is handed to the exact per-line routines parse_fields() / general(), which
+// follow the reference's string semantics literally.
+// A line belongs to the tile its first byte is in.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "svjg_internal.h"
 
@@ -35,24 +41,61 @@ using namespace svjg;
 namespace {
 
 constexpr int TILE = 32768;
-constexpr int LOOKAHEAD = 8192;
-constexpr int HEAD = 16;
-constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 40976 = 16 * 2561
+constexpr int LOOKAHEAD = 4096;
+constexpr int HEAD = 32;
+constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 36896 = 32 * 1153
 constexpr int THREADS = 256;
 constexpr int NWARPS = THREADS / 32;
-constexpr int CHUNKS = WIN / 16;
-constexpr int ROUNDS = (CHUNKS + THREADS - 1) / THREADS;   // 11
-constexpr int NL_CAP = CHUNKS;                 // more newlines than this => some line < 16 bytes
-constexpr int QCAP = 1024;                     // multi-node lines queued per tile (overflow: handled in place)
-constexpr int OFF_NL = WIN;
-constexpr int OFF_WTOT = OFF_NL + ((NL_CAP * 2 + 15) & ~15);
-constexpr int OFF_Q = OFF_WTOT + ((ROUNDS * NWARPS * 4 + 15) & ~15);
-constexpr int SMEM_BYTES = OFF_Q + QCAP * 8;
-static_assert(WIN <= 65536, "line starts are stored as 16-bit window offsets");
+constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunks = words of newline bitmap
+constexpr int HEAD_SPAN = 96;                  // bytes searched for the tabs of columns 1-5 on the fast route
+constexpr int TAIL_SPAN = 96;                  // bytes searched for the tabs of columns 7-12
+constexpr int LINE_SPAN = 160;                 // spare bytes behind the window for those fixed-span reads
+constexpr int LCAP = 2048;                     // line starts per tile (more => some line < 16 bytes)
+constexpr int MCAP = 512;                      // multi-node lines per tile on the token-parallel route
+constexpr int TCAP = 1536;                     // path nodes per tile on the token-parallel route
+constexpr int HCAP = 1024;                     // hits staged per tile before the flush
+static_assert(WIN % 32 == 0 && WIN + LINE_SPAN <= 65536, "window offsets are 16 bit, bitmap words are 32 bit");
+
+// shared memory map (bytes)
+constexpr int OFF_WIN = 0;
+constexpr int OFF_NLB = OFF_WIN + WIN + LINE_SPAN + 16;     // spare bytes: fixed-span reads may run past the window
+constexpr int OFF_LST = OFF_NLB + (NPAIRS + 3) * 4;
+constexpr int OFF_ML = (OFF_LST + LCAP * 2 + 15) & ~15;     // MLine[MCAP]
+constexpr int OFF_TH = (OFF_ML + MCAP * 16 + 15) & ~15;     // token hash   u64[TCAP]
+constexpr int OFF_TPRE = OFF_TH + TCAP * 8;                 // inclusive prefix of node lengths i64[TCAP]
+constexpr int OFF_TLEN = OFF_TPRE + TCAP * 8;               // node length  i32[TCAP]
+constexpr int OFF_TS = OFF_TLEN + TCAP * 4;                 // start value  u32[TCAP]
+constexpr int OFF_TB = OFF_TS + TCAP * 4;                   // token begin  u16[TCAP]
+constexpr int OFF_TL = OFF_TB + TCAP * 2;                   // token length u16[TCAP]
+constexpr int OFF_TLINE = OFF_TL + TCAP * 2;                // MLine index  u16[TCAP]
+constexpr int OFF_TF = OFF_TLINE + TCAP * 2;                // flags        u8[TCAP]
+constexpr int OFF_HSV = (OFF_TF + TCAP + 15) & ~15;         // staged hits: 2*sv + allele  u32[HCAP]
+constexpr int OFF_HML = OFF_HSV + HCAP * 4;                 //              MLine index    u16[HCAP]
+constexpr int SMEM_BYTES = (OFF_HML + HCAP * 2 + 15) & ~15;
 
 constexpr uint32_t FLAG_EXACT_CHECKS = SVJG_FLAG_EXACT_CHECKS;   // probe links whose overlap test fails too
-constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through the general routine
+constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through general()
 constexpr uint32_t COMMA_PATH = 0xFFFFFFFFu;
+
+// token flags
+constexpr uint32_t TF_PLUS = 1;     // delimiter in front is '>'
+constexpr uint32_t TF_ALT = 2;      // chrom:pos.k (length from the GFA)
+constexpr uint32_t TF_PLAIN = 4;    // exactly one ':', digits-digits or digits.<anything>, length > 0
+constexpr uint32_t TF_OK = 8;       // overlap verdict of the link (previous node, this node)
+// line flags
+constexpr uint32_t LF_GENERAL = 1;  // must go through general()
+constexpr uint32_t LF_HAS_NL = 2;   // the line ends in a newline (it counts in the hit's length)
+constexpr uint32_t LF_SKIP = 4;     // reported as an error: no links
+
+struct MLine {
+    uint16_t s, e;        // window offsets of the line's first byte and of its end (newline or end of data)
+    uint16_t p6;          // tab that ends the path column
+    uint16_t tok0, ntok;  // tokens [tok0, tok0 + ntok); ntok == 0 marks a slot that was given up
+    uint16_t flags;
+    uint16_t ps;          // first byte of the path column
+    uint16_t pad;
+};
+static_assert(sizeof(MLine) == 16, "MLine is 16 bytes");
 
 struct FilterArgs {
     const uint8_t *gaf;
@@ -89,6 +132,62 @@ __device__ __forceinline__ bool py_space(uint32_t c) {
 }
 __device__ __forceinline__ bool is_delim(uint32_t c) { return (c | 2u) == '>'; }   // '<' = 0x3C, '>' = 0x3E
 
+// ---- SWAR byte classes: the answer is bit 7 of each byte, exact for all 256 byte values.
+// (w & 0x7F..) ^ C is zero in its low 7 bits iff the byte's low 7 bits equal C; adding 0x7F carries
+// into bit 7 unless they are zero; a byte with bit 7 set never matches (C < 0x80).  3 instructions.
+#define SVJG_M7 0x7F7F7F7Fu
+#define SVJG_H8 0x80808080u
+__device__ __forceinline__ uint32_t lop_and_xor(uint32_t w, uint32_t m, uint32_t c) {      // (w & m) ^ c
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(r) : "r"(w), "r"(m), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop_nor_and(uint32_t t, uint32_t w, uint32_t h) {      // ~t & ~w & h
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(r) : "r"(t), "r"(w), "r"(h));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop_or_and(uint32_t t, uint32_t w, uint32_t h) {       // (t | w) & h
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xA8;" : "=r"(r) : "r"(t), "r"(w), "r"(h));
+    return r;
+}
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c4) {                    // c4: four copies of a byte < 0x80
+    return lop_nor_and(lop_and_xor(w, SVJG_M7, c4) + SVJG_M7, w, SVJG_H8);
+}
+__device__ __forceinline__ uint32_t digit_bytes(uint32_t w) {                              // '0'..'9'
+    return lop_nor_and(lop_and_xor(w, SVJG_M7, 0x30303030u) + 0x76767676u, w, SVJG_H8);
+}
+__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t w) {
+    return lop_or_and(lop_and_xor(w, SVJG_M7, 0x30303030u) + 0x76767676u, w, SVJG_H8);
+}
+__device__ __forceinline__ uint32_t delim_bytes(uint32_t w) {                              // '<' 0x3C or '>' 0x3E
+    return lop_nor_and(lop_and_xor(w, 0x7D7D7D7Du, 0x3C3C3C3Cu) + SVJG_M7, w, SVJG_H8);
+}
+// flags of bytes [lo, hi) of a word (byte indices; any ints)
+__device__ __forceinline__ uint32_t byte_range(int lo, int hi) {
+    uint32_t m = 0xFFFFFFFFu;
+    if (lo > 0) m = lo >= 4 ? 0u : (m << (8 * lo));
+    if (hi < 4) m = hi <= 0 ? 0u : (m & (0xFFFFFFFFu >> (8 * (4 - hi))));
+    return m;
+}
+// 16 class flags of a 16-byte chunk, bit i = byte i.  dp4a gathers the four bit-7 flags of a
+// word: sum(0x80 * weight) = bits << 7.
+template <class F>
+__device__ __forceinline__ uint32_t mask16(const uint4 &v, F cls) {
+    uint32_t lo = __dp4a(cls(v.x), 0x08040201u, 0u);
+    lo = __dp4a(cls(v.y), 0x80402010u, lo);
+    uint32_t hi = __dp4a(cls(v.z), 0x08040201u, 0u);
+    hi = __dp4a(cls(v.w), 0x80402010u, hi);
+    return (lo >> 7) | (hi << 1);
+}
+struct IsNewline {
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return eq_bytes(w, 0x0A0A0A0Au); }
+};
+struct IsTab {
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return eq_bytes(w, 0x09090909u); }
+};
+
 __device__ __noinline__ void report(const FilterArgs &a, uint32_t code, uint64_t line_off) {
     atomicCAS(a.stats + 4, 0ull, (unsigned long long)code);
     atomicMin(a.stats + 5, (unsigned long long)(a.base + line_off));
@@ -122,6 +221,10 @@ __device__ __noinline__ int parse_int(const Src &src, typename Src::pos_t b, typ
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Rec: one GAF line.  parse_fields()/general() are the exact, string-level
+// routines; link()/probe()/emit() are shared with the token-parallel route.
+// ---------------------------------------------------------------------------
 template <class Src>
 struct Rec {
     typedef typename Src::pos_t P;
@@ -142,12 +245,10 @@ struct Rec {
         uint32_t l;
     };
 
-    // ------------------------------------------------------------------ phase B
     // read_gaf_line (:184-198) on line.rstrip() (:126): 12 tab-separated columns,
     // 9 of them int().  Returns the number of path tokens for a '<'/'>' path,
     // COMMA_PATH for any other non-empty path.  Sets err where the reference raises.
-    __device__ uint32_t parse_fields(P s, P e) {
-        loc.n_rec++;
+    __device__ __noinline__ uint32_t parse_fields(P s, P e) {
         while (e > s && py_space(src[e - 1])) --e;
         P pos = s;
         int col = 0;
@@ -169,7 +270,6 @@ struct Rec {
                 ps = pos;
                 pe = f;
             } else {
-                // numeric columns: plain digit strings are checked on the fly
                 uint32_t nd = 0;
                 bool plain = true;
                 int64_t v = 0;
@@ -183,7 +283,17 @@ struct Rec {
                 }
                 bool numeric = (col >= 1 && col <= 3) || (col >= 6 && col <= 11);
                 if (numeric) {
-                    if (!plain || nd == 0 || nd > 18) r = parse_int(src, pos, f, v);
+                    const bool used = col >= 6 && col <= 8;         // Tlen, Ts, Te: the only values that matter
+                    if (!plain || nd == 0 || (nd > 18 && used)) {
+                        r = parse_int(src, pos, f, v);
+                        // Python's int() has no size limit; only the used columns are held to 18 digits
+                        if (r == SVJG_BAD_RANGE && !used) r = 0, v = 1;
+                    } else if (nd > 18) {
+                        v = 1;                                       // digits only: int() accepts; non-zero unless all '0'
+                        bool all0 = true;
+                        for (P j = pos; j < f; ++j) all0 &= src[j] == '0';
+                        if (all0) v = 0;
+                    }
                     if (col == 6) tlen = v;
                     else if (col == 7) ts = v;
                     else if (col == 8) te = v;
@@ -214,7 +324,7 @@ struct Rec {
         return angle ? ntok : COMMA_PATH;
     }
 
-    // phase C re-reads Tlen, Ts, Te (columns 7-9) instead of carrying 24 bytes per queued line
+    // Tlen, Ts, Te (columns 7-9) of a line whose columns were validated already
     __device__ void reparse_coords(P e) {
         while (e > pe && py_space(src[e - 1])) --e;
         P pos = pe + 1;
@@ -229,7 +339,6 @@ struct Rec {
         angle = true;
     }
 
-    // --------------------------------------------------------- shared pieces
     // tokens of the path column: '<'/'>' separated, or (path not starting with
     // one of those) ','-separated pieces minus their last character
     __device__ bool next_tok(P &cur, Tok &t) const {
@@ -265,15 +374,42 @@ struct Rec {
 
     __device__ uint64_t tok_hash(const Tok &t) const {
         TokHash h = tok_init();
-        for (uint32_t i = 0; i < t.l; ++i) tok_step(h, src[t.b + i]);
-        return tok_value(h);
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < t.l; ++i) {
+            w |= src[t.b + i] << (8 * (i & 3));
+            if ((i & 3) == 3) {
+                tok_step(h, w);
+                w = 0;
+            }
+        }
+        if (t.l & 3) tok_step(h, w);
+        return tok_value(h, t.l);
     }
 
+    // name bytes against the table's copy (4-byte aligned, zero padded).  In shared memory the
+    // compare is word-wide and never exits early, so all table loads are in flight together.
     __device__ bool names_match(uint32_t off, const Tok &t) const {
-        const uint8_t *q = a.tb.blob + off;
-        for (uint32_t i = 0; i < t.l; ++i)
-            if (__ldg(q + i) != src[t.b + i]) return false;
-        return true;
+        if constexpr (std::is_same<Src, SmemSrc>::value) {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(a.tb.blob + off);
+            const uint32_t sh = (uint32_t(t.b) & 3u) * 8u;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(src.p + (uint32_t(t.b) & ~3u));
+            const uint32_t nw = (t.l + 3u) >> 2;
+            uint32_t cur = wp[0], diff = 0;
+#pragma unroll 4
+            for (uint32_t k = 0; k < nw; ++k) {
+                uint32_t nxt = wp[k + 1];
+                uint32_t w = __funnelshift_r(cur, nxt, sh);
+                cur = nxt;
+                if (k == nw - 1 && (t.l & 3u)) w &= (1u << (8u * (t.l & 3u))) - 1u;
+                diff |= w ^ __ldg(q + k);
+            }
+            return diff == 0;
+        } else {
+            const uint8_t *q = a.tb.blob + off;
+            for (uint32_t i = 0; i < t.l; ++i)
+                if (__ldg(q + i) != src[t.b + i]) return false;
+            return true;
+        }
     }
 
     __device__ bool probe(uint64_t hl, uint32_t sl, const Tok &tl_, uint64_t hr, uint32_t sr, const Tok &tr_,
@@ -287,7 +423,7 @@ struct Rec {
             if (!(meta & 1u)) return false;
             uint64_t sh = (uint64_t(lo.y) << 32) | lo.x;
             if (sh == h && ((meta >> 2) & 1u) == sl && ((meta >> 1) & 1u) == sr && (lo.w & 0xFFFFu) == tl_.l &&
-                (lo.w >> 16) == tr_.l && names_match(lo.z, tl_) && names_match(lo.z + tl_.l, tr_)) {
+                (lo.w >> 16) == tr_.l && names_match(lo.z, tl_) && names_match(lo.z + ((tl_.l + 3u) & ~3u), tr_)) {
                 out.hash = sh;
                 out.name_off = lo.z;
                 out.ent_begin = hi.x;
@@ -316,15 +452,33 @@ struct Rec {
         }
     }
 
+    // Hits of the token-parallel route are staged in shared memory (flushed once per tile with one
+    // cursor atomic for the whole block); everything else appends to the global arrays directly.
+    uint32_t *stage_sv = nullptr;
+    uint16_t *stage_ml = nullptr;
+    uint32_t *stage_n = nullptr;
+    uint32_t stage_line = 0;
+
     __device__ void emit(uint32_t sv2) {
+        cg::coalesced_group active = cg::coalesced_threads();
+        if (stage_sv) {
+            uint32_t base = 0;
+            if (active.thread_rank() == 0) base = atomicAdd(stage_n, active.size());
+            base = active.shfl(base, 0) + active.thread_rank();
+            if (base < HCAP) {
+                stage_sv[base] = sv2;
+                stage_ml[base] = uint16_t(stage_line);
+                return;
+            }
+        }
         // warp-aggregated: one counter atomic per distinct SV allele among the
         // lanes that are here together, one cursor atomic for all of them
-        cg::coalesced_group active = cg::coalesced_threads();
-        cg::coalesced_group same = cg::labeled_partition(active, sv2);
+        cg::coalesced_group now = cg::coalesced_threads();
+        cg::coalesced_group same = cg::labeled_partition(now, sv2);
         if (same.thread_rank() == 0) atomicAdd(a.counts + sv2, same.size());
         unsigned long long base = 0;
-        if (active.thread_rank() == 0) base = atomicAdd(a.stats + 0, (unsigned long long)active.size());
-        base = active.shfl(base, 0) + active.thread_rank();
+        if (now.thread_rank() == 0) base = atomicAdd(a.stats + 0, (unsigned long long)now.size());
+        base = now.shfl(base, 0) + now.thread_rank();
         if (base < a.hit_cap) {
             a.hit_sv2[base] = sv2;
             a.hit_off[base] = line_off;
@@ -333,8 +487,8 @@ struct Rec {
     }
 
     // forward and reverse key of one link (:141-148) and their entries (:150-166).
-    // ok_known: the overlap verdict is already there (fast path); otherwise it is
-    // computed once, on the first key that has entries, by the general overlap().
+    // ok_known: the overlap verdict is already there; otherwise it is computed
+    // once, on the first key that has entries, by the general overlap().
     __device__ void link(const Tok &A, uint64_t hA, int sA, const Tok &B, uint64_t hB, int sB, bool ok_known, bool ok) {
 #pragma unroll 1
         for (int dir = 0; dir < 2; ++dir) {
@@ -363,112 +517,6 @@ struct Rec {
                 emit(sv2);
             }
         }
-    }
-
-    // ------------------------------------------------------- phase C, fast path
-    // One token of a '<'/'>' path, streamed: hash, node length and the two
-    // "could be a substring of an earlier token" signals.
-    struct Scan {
-        Tok t;
-        uint64_t hash, sig;
-        int64_t len;
-        uint32_t start_val;
-        int plus;          // 1 when the delimiter in front is '>'
-        bool alt, plain;   // plain: exactly one ':', then digits-digits (<= 9 each) or digits.<anything>
-    };
-
-    __device__ bool scan_tok(P &cur, Scan &o) const {
-        while (cur < pe && is_delim(src[cur])) ++cur;
-        if (cur >= pe) return false;
-        o.plus = src[cur - 1] == '>';
-        o.t.b = cur;
-        TokHash h = tok_init();
-        uint64_t sig = 0;
-        uint32_t v0 = 0, v1 = 0, nd0 = 0, nd1 = 0, dash = 0, colons = 0, prev = 0;
-        bool dot = false, junk = false;
-        for (; cur < pe; ++cur) {
-            uint32_t c = src[cur];
-            if (is_delim(c)) break;
-            tok_step(h, c);
-            if (cur != o.t.b) sig |= 1ull << ((c ^ (prev << 3) ^ (prev >> 2)) & 63);   // adjacent byte pair
-            prev = c;
-            uint32_t d = c - '0';
-            if (d <= 9) {
-                if (dot) {
-                } else if (dash == 0) {
-                    v0 = v0 * 10 + d;
-                    ++nd0;
-                } else {
-                    v1 = v1 * 10 + d;
-                    ++nd1;
-                }
-            } else if (c == ':') {
-                ++colons;
-                v0 = v1 = nd0 = nd1 = dash = 0;
-                dot = junk = false;
-            } else if (c == '-' && !dot) {
-                ++dash;
-            } else if (c == '.' && dash == 0) {
-                dot = true;
-            } else if (!dot) {
-                junk = true;
-            }
-        }
-        o.t.l = uint32_t(cur - o.t.b);
-        o.hash = tok_value(h);
-        o.sig = sig;
-        o.alt = dot;
-        o.start_val = v0;
-        o.plain = colons == 1 && !junk && nd0 >= 1 && nd0 <= 9 && (dot || (dash == 1 && nd1 >= 1 && nd1 <= 9));
-        o.len = int64_t(v1) - int64_t(v0) + 1;
-        return true;
-    }
-
-    // false -> the general routine must take the line
-    __device__ bool fast() {
-        // pass 1: total path length; bail out on anything that is not plain
-        int64_t total = 0;
-        uint64_t seen = 0;
-        uint32_t lo[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, hi[2] = {0, 0};
-        uint32_t n = 0;
-        P cur = ps;
-        Scan t;
-        while (scan_tok(cur, t)) {
-            if (!t.plain) return false;
-            if (t.alt && !alt_lookup(t.hash, t.t, t.len)) return false;
-            if (t.len <= 0) return false;
-            // t can only sit inside an earlier token x if every adjacent byte pair of t
-            // occurs in x, and (single ':' in both) x has the same start digits and kind
-            int k = t.alt;
-            if (n && (t.sig & ~seen) == 0 && t.start_val >= lo[k] && t.start_val <= hi[k]) return false;
-            seen |= t.sig;
-            lo[k] = min(lo[k], t.start_val);
-            hi[k] = max(hi[k], t.start_val);
-            total += t.len;
-            ++n;
-        }
-        // pass 2: every token is its own first occurrence, so strand = own delimiter
-        // (:206), index = own position (:269-271) and the overlap sums are a prefix
-        // sum and its complement (:269-273)
-        const int64_t tail = tlen - te - 1;
-        const bool all = a.flags & FLAG_EXACT_CHECKS;
-        cur = ps;
-        Scan A, B;
-        scan_tok(cur, A);
-        if (A.alt) alt_lookup(A.hash, A.t, A.len);
-        int64_t pre = A.len;
-        for (uint32_t i = 1; i < n; ++i) {
-            scan_tok(cur, B);
-            if (B.alt) alt_lookup(B.hash, B.t, B.len);
-            bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);
-            if (ok || all) {
-                link(A.t, A.hash, A.plus, B.t, B.hash, B.plus, true, ok);
-                if (err) return true;
-            }
-            pre += B.len;
-            A = B;
-        }
-        return true;
     }
 
     // ---------------------------------------------------- general (exact) routine
@@ -574,12 +622,6 @@ struct Rec {
             sA = sB;
         }
     }
-
-    // links of a line already split by parse_fields() / reparse_coords()
-    __device__ void resolve() {
-        if (angle && !(a.flags & FLAG_FORCE_GENERAL) && fast()) return;
-        if (!err) general();
-    }
 };
 
 // ---- TMA bulk copy + mbarrier helpers ---------------------------------------
@@ -609,29 +651,114 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-// 0x80 in every byte of w that equals '\n' (exact, no borrow artefacts)
-__device__ __forceinline__ uint32_t nl_bytes(uint32_t w) {
-    uint32_t x = w ^ 0x0A0A0A0Au;
-    uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    return ~(t | x | 0x7F7F7F7Fu);
+// the exact per-line route for a line that is inside the window
+__device__ __noinline__ void slow_line(const FilterArgs &a, const uint8_t *win, uint32_t s, uint32_t e, uint32_t off,
+                                       uint32_t len, Local &loc) {
+    Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
+    uint32_t ntok = rec.parse_fields(s, e);
+    if (!rec.err && ntok >= 2) {
+        if (ntok != COMMA_PATH) loc.n_multi++;
+        rec.general();
+    }
+    if (rec.err) report(a, rec.err, off);
 }
-// bits 7,15,23,31 -> bits 0..3
-__device__ __forceinline__ uint32_t pack4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+// a line that runs past the staged window: exact route on global memory
+__device__ __noinline__ void long_line(const FilterArgs &a, uint64_t from, uint32_t off, Local &loc) {
+    uint64_t e = from;
+    while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
+    uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
+    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+    uint32_t ntok = rec.parse_fields(uint64_t(off), e);
+    if (!rec.err && ntok >= 2) {
+        if (ntok != COMMA_PATH) loc.n_multi++;
+        rec.general();
+    }
+    if (rec.err) report(a, rec.err, off);
+}
+
+// general() for a line whose columns are known to be valid (path [ps, pe), coordinates after pe)
+__device__ __noinline__ void general_line(const FilterArgs &a, const uint8_t *win, uint32_t ps, uint32_t pe, uint32_t e,
+                                          uint32_t off, uint32_t len, Local &loc) {
+    Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
+    rec.ps = ps;
+    rec.pe = pe;
+    rec.reparse_coords(e);
+    rec.general();
+    if (rec.err) report(a, rec.err, off);
+}
+
+__device__ __forceinline__ uint32_t lds32(const uint8_t *win, uint32_t a) { return *reinterpret_cast<const uint32_t *>(win + a); }
+
+// number of non-digit bytes in window bytes [lo, hi), hi > lo
+__device__ __forceinline__ uint32_t count_nondigits(const uint8_t *win, uint32_t lo, uint32_t hi) {
+    const uint32_t a0 = lo & ~3u, a1 = (hi - 1u) & ~3u;
+    const uint32_t lom = 0xFFFFFFFFu << (8u * (lo & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((hi - 1u) & 3u)));
+    uint32_t f = nondigit_bytes(lds32(win, a0)) & lom;
+    if (a0 == a1) return __popc(f & him);
+    uint32_t n = __popc(f);
+    for (uint32_t a = a0 + 4; a < a1; a += 4) n += __popc(nondigit_bytes(lds32(win, a)));
+    return n + __popc(nondigit_bytes(lds32(win, a1)) & him);
+}
+
+// any ',' in window bytes [lo, hi), hi > lo
+__device__ __forceinline__ bool has_comma(const uint8_t *win, uint32_t lo, uint32_t hi) {
+    const uint32_t a0 = lo & ~3u, a1 = (hi - 1u) & ~3u;
+    const uint32_t lom = 0xFFFFFFFFu << (8u * (lo & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((hi - 1u) & 3u)));
+    uint32_t f = eq_bytes(lds32(win, a0), 0x2C2C2C2Cu) & lom;
+    if (a0 == a1) return (f & him) != 0;
+    for (uint32_t a = a0 + 4; a < a1; a += 4) f |= eq_bytes(lds32(win, a), 0x2C2C2C2Cu);
+    return (f | (eq_bytes(lds32(win, a1), 0x2C2C2C2Cu) & him)) != 0;
+}
+
+// Writes this tile's staged hits: one cursor atomic for the block, coalesced tuple stores and
+// warp-aggregated counter atomics (one per distinct SV allele among the 32 hits a warp holds).
+__device__ __forceinline__ void flush_hits(const FilterArgs &a, const uint32_t *h_sv, const uint16_t *h_ml, const MLine *ml,
+                                           uint32_t n, uint64_t tile_start, unsigned long long base) {
+    for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+        const uint32_t sv2 = h_sv[i];
+        const MLine L = ml[h_ml[i]];
+        const unsigned peers = __match_any_sync(__activemask(), sv2);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(a.counts + sv2, uint32_t(__popc(peers)));
+        const unsigned long long k = base + i;
+        if (k < a.hit_cap) {
+            a.hit_sv2[k] = sv2;
+            a.hit_off[k] = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
+            a.hit_len[k] = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *win = smem;
-    uint16_t *nl = reinterpret_cast<uint16_t *>(smem + OFF_NL);
-    uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + OFF_WTOT);
-    ushort4 *queue = reinterpret_cast<ushort4 *>(smem + OFF_Q);   // (start, path start, path end, line end)
+    uint8_t *win = smem + OFF_WIN;
+    uint32_t *nlb = reinterpret_cast<uint32_t *>(smem + OFF_NLB);
+    uint16_t *lstart = reinterpret_cast<uint16_t *>(smem + OFF_LST);
+    MLine *ml = reinterpret_cast<MLine *>(smem + OFF_ML);
+    uint64_t *t_hash = reinterpret_cast<uint64_t *>(smem + OFF_TH);
+    int64_t *t_pre = reinterpret_cast<int64_t *>(smem + OFF_TPRE);
+    int32_t *t_len = reinterpret_cast<int32_t *>(smem + OFF_TLEN);
+    uint32_t *t_sval = reinterpret_cast<uint32_t *>(smem + OFF_TS);
+    uint16_t *t_b = reinterpret_cast<uint16_t *>(smem + OFF_TB);
+    uint16_t *t_l = reinterpret_cast<uint16_t *>(smem + OFF_TL);
+    uint16_t *t_line = reinterpret_cast<uint16_t *>(smem + OFF_TLINE);
+    uint8_t *t_flags = smem + OFF_TF;
+    uint32_t *h_sv = reinterpret_cast<uint32_t *>(smem + OFF_HSV);
+    uint16_t *h_ml = reinterpret_cast<uint16_t *>(smem + OFF_HML);
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_total, s_qn;
+    __shared__ uint32_t s_nlines, s_nml, s_ntok, s_nhits;
+    __shared__ unsigned long long s_hbase;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) mbar_init(&mbar, 1);
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        s_nhits = 0;
+    }
     __syncthreads();
     uint32_t phase = 0;
     Local loc;
+    const bool all_links = a.flags & FLAG_EXACT_CHECKS;
+    uint64_t prev_tile_start = 0;
 
     for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const uint64_t tile_start = uint64_t(tile) * TILE;
@@ -644,172 +771,434 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
         const uint32_t bulk = nbytes & ~15u;
         const uint32_t valid_end = dst0 + nbytes;
 
+        // the previous tile's hits go out while this tile's bytes come in
+        const uint32_t n_staged = min(s_nhits, uint32_t(HCAP));
         if (tid == 0) {
-            s_qn = 0;
             if (bulk) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&mbar, bulk);
                 bulk_g2s(win + dst0, a.gaf + g0, bulk, &mbar);
             }
+            if (n_staged) s_hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
         }
+        __syncthreads();
+        if (n_staged) flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, s_hbase);
+        prev_tile_start = tile_start;
         for (uint32_t i = bulk + tid; i < nbytes; i += THREADS) win[dst0 + i] = __ldg(a.gaf + g0 + i);
         if (dst0 && tid < HEAD) win[tid] = tid == HEAD - 1 ? '\n' : 0;   // "newline" in front of byte 0 of the file
-        for (uint32_t i = valid_end + tid; i < WIN; i += THREADS) win[i] = 0;
+        for (uint32_t i = valid_end + tid; i < WIN + LINE_SPAN + 16; i += THREADS) win[i] = 0;
+        if (tid < 3) nlb[NPAIRS + tid] = 0;
+        __syncthreads();                       // every thread is done with the previous tile's ml[] / staged hits
+        if (tid == 0) {
+            s_nlines = 0;
+            s_nml = 0;
+            s_ntok = 0;
+            s_nhits = 0;
+        }
         if (bulk) {
             mbar_wait(&mbar, phase);
             phase ^= 1;
         }
         __syncthreads();
 
-        // ---- phase A: newline scan, ordered compaction of line starts
-        uint32_t masks[ROUNDS];
-        uint32_t excl[ROUNDS];
-#pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) {
-            int c = r * THREADS + tid;
-            uint32_t m = 0;
-            if (c < CHUNKS) {
-                uint4 v = *reinterpret_cast<const uint4 *>(win + c * 16);
-                m = pack4(nl_bytes(v.x)) | (pack4(nl_bytes(v.y)) << 4) | (pack4(nl_bytes(v.z)) << 8) |
-                    (pack4(nl_bytes(v.w)) << 12);
-            }
-            masks[r] = m;
-            uint32_t cnt = __popc(m), inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            excl[r] = inc - cnt;
-            if (lane == 31) wtot[r * NWARPS + warp] = inc;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            constexpr int PER = (ROUNDS * NWARPS + 31) / 32;
-            uint32_t v[PER], sum = 0;
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                int idx = lane * PER + k;
-                v[k] = idx < ROUNDS * NWARPS ? wtot[idx] : 0;
-                sum += v[k];
-            }
-            uint32_t inc = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            uint32_t run = inc - sum;
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                int idx = lane * PER + k;
-                if (idx < ROUNDS * NWARPS) wtot[idx] = run;
-                run += v[k];
-            }
-            if (lane == 31) s_total = inc;
-        }
-        __syncthreads();
-        const uint32_t m_total = s_total;
-        if (m_total > NL_CAP) {
-            if (tid == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
-        } else {
-#pragma unroll
-            for (int r = 0; r < ROUNDS; ++r) {
-                uint32_t m = masks[r], o = wtot[r * NWARPS + warp] + excl[r];
-                uint32_t basepos = uint32_t(r * THREADS + tid) * 16;
-                while (m) {
-                    int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    nl[o++] = uint16_t(basepos + b);
-                }
-            }
-        }
-        __syncthreads();
-
-        if (m_total <= NL_CAP) {
-            // ---- phase B: one thread per line, columns + integers + token count
-            for (uint32_t k0 = 0; k0 < m_total; k0 += THREADS) {
-                uint32_t k = k0 + tid;
-                bool queued = false;
-                uint32_t start = 0, end = 0, rps = 0, rpe = 0;
-                if (k < m_total) {
-                    start = uint32_t(nl[k]) + 1;
-                    bool owned = start >= HEAD && start < HEAD + TILE && start < valid_end;
-                    if (owned) {
-                        uint32_t off = uint32_t(tile_start) + (start - HEAD);
-                        bool in_win = (k + 1 < m_total) || at_eof;
-                        if (in_win) {
-                            end = (k + 1 < m_total) ? nl[k + 1] : valid_end;
-                            uint32_t len = end - start + ((k + 1 < m_total) ? 1u : 0u);
-                            Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
-                            uint32_t ntok = rec.parse_fields(start, end);
-                            if (rec.err) {
-                                report(a, rec.err, off);
-                            } else if (ntok == COMMA_PATH) {
-                                rec.general();
-                                if (rec.err) report(a, rec.err, off);
-                            } else if (ntok >= 2) {
-                                loc.n_multi++;
-                                queued = true;
-                                rps = rec.ps;
-                                rpe = rec.pe;
-                            }
-                        } else {
-                            // the line runs past the staged window: general routine on global memory
-                            uint64_t e = tile_start + TILE + LOOKAHEAD;
-                            while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
-                            uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
-                            Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-                            uint32_t ntok = rec.parse_fields(uint64_t(off), e);
-                            if (!rec.err && ntok >= 2) {
-                                if (ntok != COMMA_PATH) loc.n_multi++;
-                                rec.general();
-                            }
-                            if (rec.err) report(a, rec.err, off);
-                        }
+        // ---- phase A: newline bitmap + unordered list of the line starts this tile owns.
+        // A lane takes two adjacent 16-byte chunks = one 32-bit word of the bitmap.
+        {
+            const uint32_t own_lo = HEAD - 1;                                        // newline positions p with
+            const uint32_t own_hi = min(uint32_t(HEAD + TILE), valid_end) - 1;       // HEAD <= p+1 < own end
+            for (int c0 = warp * 32; c0 < NPAIRS; c0 += NWARPS * 32) {
+                const int c = c0 + lane;
+                uint32_t m = 0;
+                if (c < NPAIRS) {
+                    const uint4 v0 = *reinterpret_cast<const uint4 *>(win + c * 32);
+                    const uint4 v1 = *reinterpret_cast<const uint4 *>(win + c * 32 + 16);
+                    m = mask16(v0, IsNewline()) | (mask16(v1, IsNewline()) << 16);
+                    nlb[c] = m;
+                    const uint32_t p0 = uint32_t(c) * 32u;
+                    if (p0 < own_lo || p0 + 32u > own_hi) {                           // edge words only
+                        const int lo = int(own_lo) - int(p0), hi = int(own_hi) - int(p0);   // keep bits [lo, hi)
+                        if (lo > 0) m = lo >= 32 ? 0u : (m & (0xFFFFFFFFu << lo));
+                        if (hi < 32) m = hi <= 0 ? 0u : (m & ((1u << hi) - 1u));
                     }
                 }
-                // compaction of the multi-node lines (one shared atomic per warp)
-                uint32_t bal = __ballot_sync(0xFFFFFFFFu, queued);
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m != 0);
                 if (bal) {
                     uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&s_qn, __popc(bal));
+                    if (lane == 0) base = atomicAdd(&s_nlines, __popc(bal));
                     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (queued) {
-                        uint32_t q = base + __popc(bal & ((1u << lane) - 1));
-                        if (q < QCAP) {
-                            queue[q] = make_ushort4(uint16_t(start), uint16_t(rps), uint16_t(rpe), uint16_t(end));
-                        } else {
-                            // queue full: resolve in place
-                            uint32_t off = uint32_t(tile_start) + (start - HEAD);
-                            uint32_t len = end - start + ((end < valid_end && win[end] == '\n') ? 1u : 0u);
-                            Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
-                            rec.ps = rps;
-                            rec.pe = rpe;
-                            rec.reparse_coords(end);
-                            rec.resolve();
-                            if (rec.err) report(a, rec.err, off);
+                    if (m) {
+                        uint32_t q = base + __popc(bal & ((1u << lane) - 1u));
+                        if (q < LCAP) lstart[q] = uint16_t(c * 32 + __ffs(m));       // start = newline position + 1
+                        m &= m - 1;
+                        while (m) {                                                   // a second newline in 32 bytes (rare)
+                            q = atomicAdd(&s_nlines, 1u);
+                            if (q < LCAP) lstart[q] = uint16_t(c * 32 + __ffs(m));
+                            m &= m - 1;
                         }
                     }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_lines = s_nlines;
+
+        if (n_lines > LCAP) {
+            // more than LCAP lines in 32 KiB: some line is shorter than 16 bytes and cannot hold 12 columns
+            if (tid == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
+        } else {
+            // ---- phase B: one thread per line
+            for (uint32_t k = tid; k < n_lines; k += THREADS) {
+                const uint32_t s = lstart[k];
+                const uint32_t off = uint32_t(tile_start) + (s - HEAD);
+                loc.n_rec++;
+                // end of the line: next newline at or after s
+                uint32_t wi = s >> 5;
+                uint32_t bits = nlb[wi] & (0xFFFFFFFFu << (s & 31u));
+                while (!bits && wi < NPAIRS - 1) bits = nlb[++wi];
+                uint32_t e;
+                const bool has_nl = bits != 0;
+                if (has_nl) {
+                    e = wi * 32 + (__ffs(bits) - 1);
+                } else if (at_eof) {
+                    e = valid_end;
+                } else {
+                    long_line(a, tile_start + TILE + LOOKAHEAD, off, loc);
+                    continue;
+                }
+                const uint32_t len = e - s + (has_nl ? 1u : 0u);
+
+                // columns 1-5: tab bitmap of the first HEAD_SPAN bytes (fixed trip count: lanes stay together)
+                bool plain = e > s && !py_space(win[e - 1]);
+                uint32_t p1, p2, p3, p4, p5;
+                {
+                    const uint32_t base = s & ~15u;
+                    uint32_t tm[HEAD_SPAN / 32];
+#pragma unroll
+                    for (int j = 0; j < HEAD_SPAN / 32; ++j) {
+                        const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
+                        const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
+                        tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
+                    }
+                    tm[0] &= 0xFFFFFFFFu << (s - base);
+                    const uint32_t rel_e = e - base;
+#pragma unroll
+                    for (int j = 0; j < HEAD_SPAN / 32; ++j)
+                        if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
+                    // the first 5 tab positions (relative to base), one byte each, newest in the low byte
+                    uint32_t r0 = 0, r1 = 0, nt = 0;
+#pragma unroll
+                    for (int j = 0; j < HEAD_SPAN / 32; ++j) {
+                        uint32_t m = tm[j];
+                        while (m && nt < 5) {
+                            const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                            m &= m - 1;
+                            r1 = __funnelshift_l(r0, r1, 8);
+                            r0 = (r0 << 8) | pos;
+                            ++nt;
+                        }
+                    }
+                    plain &= nt == 5;
+                    p1 = base + (r1 & 255u), p2 = base + (r0 >> 24), p3 = base + ((r0 >> 16) & 255u);
+                    p4 = base + ((r0 >> 8) & 255u), p5 = base + (r0 & 255u);
+                }
+                // column 6, the path [ps, pe): walk to its tab; count token starts (a non-delimiter byte
+                // right after a delimiter) and look for ',' on the way
+                const uint32_t ps = p5 + 1;
+                uint32_t pe = e, ntok = 0, comma = 0;
+                if (plain) {
+                    uint32_t carry = 0;   // delimiter flag of the byte in front of the word, at bit 7
+                    uint32_t keep = 0xFFFFFFFFu << (8u * (ps & 3u));
+                    for (uint32_t w0 = ps & ~3u; w0 < e; w0 += 4) {
+                        const uint32_t w = lds32(win, w0);
+                        const uint32_t tb = eq_bytes(w, 0x09090909u) & keep;
+                        const uint32_t d = delim_bytes(w);
+                        if (tb) {
+                            const uint32_t j = uint32_t(__ffs(tb) - 1) >> 3;          // byte of the tab in this word
+                            pe = w0 + j;
+                            keep &= j ? (0xFFFFFFFFu >> (8u * (4u - j))) : 0u;
+                        }
+                        ntok += __popc(((d << 8) | carry) & ~d & SVJG_H8 & keep);
+                        comma |= eq_bytes(w, 0x2C2C2C2Cu) & keep;
+                        if (tb) break;
+                        carry = d >> 24;
+                        keep = 0xFFFFFFFFu;
+                    }
+                    plain = pe < e && pe > ps;
+                }
+                // columns 7-12: tab bitmap of the TAIL_SPAN bytes around the end of the path
+                uint32_t p6 = pe, p12 = 0;
+                if (plain) {
+                    const uint32_t base = p6 & ~15u;
+                    uint32_t tm[TAIL_SPAN / 32];
+#pragma unroll
+                    for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                        const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
+                        const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
+                        tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
+                    }
+                    tm[0] &= 0xFFFFFFFEu << (p6 - base);                               // tabs after p6
+                    const uint32_t rel_e = e - base;
+#pragma unroll
+                    for (int j = 0; j < TAIL_SPAN / 32; ++j)
+                        if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
+                    uint32_t r0 = 0, r1 = 0, nt = 0;
+#pragma unroll
+                    for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                        uint32_t m = tm[j];
+                        while (m && nt < 6) {
+                            const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                            m &= m - 1;
+                            r1 = __funnelshift_l(r0, r1, 8);
+                            r0 = (r0 << 8) | pos;
+                            ++nt;
+                        }
+                    }
+                    if (nt == 5 && rel_e <= TAIL_SPAN) {                               // no tab after column 12
+                        r1 = __funnelshift_l(r0, r1, 8);
+                        r0 = (r0 << 8) | rel_e;
+                        ++nt;
+                    }
+                    plain = nt == 6;
+                    const uint32_t p7 = base + ((r1 >> 8) & 255u), p8 = base + (r1 & 255u), p9 = base + (r0 >> 24),
+                                   p10 = base + ((r0 >> 16) & 255u), p11 = base + ((r0 >> 8) & 255u);
+                    p12 = base + (r0 & 255u);
+                    if (plain) {
+                        // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
+                        const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) & (p8 - p7 > 1u) &
+                                          (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) & (p12 - p11 > 1u);
+                        plain = w_ok && win[p10 + 1] != '0';
+                        if (plain) plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
+                    }
+                }
+                if (!plain) {
+                    slow_line(a, win, s, e, off, len, loc);
+                    continue;
+                }
+                if (!is_delim(win[ps])) {
+                    // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
+                    if (comma) slow_line(a, win, s, e, off, len, loc);
+                    continue;
+                }
+                const uint32_t a0 = ps & ~3u, a1 = (pe - 1u) & ~3u;
+                const uint32_t lom = 0xFFFFFFFFu << (8u * (ps & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((pe - 1u) & 3u)));
+                if (ntok < 2) continue;                                              // :133
+                loc.n_multi++;
+                uint32_t li = MCAP, t0 = TCAP;
+                if (!(a.flags & FLAG_FORCE_GENERAL) && ntok <= TCAP) {
+                    li = atomicAdd(&s_nml, 1u);
+                    t0 = atomicAdd(&s_ntok, ntok);
+                }
+                if (li >= MCAP || t0 + ntok > TCAP) {
+                    // no room on the token-parallel route (or the test hook): exact route, in place.
+                    // Slots already reserved are marked as holes for the later phases.
+                    if (li < MCAP) {
+                        MLine H{};
+                        ml[li] = H;
+                    }
+                    for (uint32_t t = t0; t < min(t0 + ntok, uint32_t(TCAP)); ++t) t_line[t] = 0xFFFFu;
+                    general_line(a, win, ps, pe, e, off, len, loc);
+                    continue;
+                }
+                MLine L;
+                L.s = uint16_t(s);
+                L.e = uint16_t(e);
+                L.p6 = uint16_t(p6);
+                L.tok0 = uint16_t(t0);
+                L.ntok = uint16_t(ntok);
+                L.flags = has_nl ? LF_HAS_NL : 0;
+                L.ps = uint16_t(ps);
+                L.pad = 0;
+                ml[li] = L;
+                // token records: maximal runs of non-delimiter bytes, from the start / end flags
+                {
+                    uint32_t t = t0, cur = 0xFFFFFFFFu, carry = 0;
+                    for (uint32_t w0 = a0; w0 <= a1; w0 += 4) {
+                        const uint32_t d = delim_bytes(lds32(win, w0));
+                        const uint32_t pd = (d << 8) | carry;                       // "previous byte is a delimiter"
+                        uint32_t st = pd & ~d & SVJG_H8, en = d & ~pd & SVJG_H8;
+                        if (w0 == a0) st &= lom, en &= lom;
+                        if (w0 == a1) st &= him, en &= him;
+                        carry = d >> 24;
+                        uint32_t ev = st | en;
+                        while (ev) {
+                            const uint32_t bit = uint32_t(__ffs(ev) - 1);
+                            ev &= ev - 1;
+                            const uint32_t pos = w0 + (bit >> 3);
+                            if ((st >> bit) & 1u) {
+                                cur = pos;
+                                t_b[t] = uint16_t(pos);
+                                t_line[t] = uint16_t(li);
+                            } else if (cur != 0xFFFFFFFFu) {
+                                t_l[t++] = uint16_t(pos - cur);
+                                cur = 0xFFFFFFFFu;
+                            }
+                        }
+                    }
+                    if (cur != 0xFFFFFFFFu) t_l[t++] = uint16_t(pe - cur);
                 }
             }
             __syncthreads();
-            // ---- phase C: one thread per multi-node line
-            const uint32_t qn = min(s_qn, uint32_t(QCAP));
-            for (uint32_t q = tid; q < qn; q += THREADS) {
-                ushort4 e4 = queue[q];
-                uint32_t start = e4.x, end = e4.w;
-                uint32_t off = uint32_t(tile_start) + (start - HEAD);
-                uint32_t len = end - start + ((end < valid_end && win[end] == '\n') ? 1u : 0u);
+            const uint32_t n_ml = min(s_nml, uint32_t(MCAP));
+            const uint32_t n_tok = min(s_ntok, uint32_t(TCAP));
+            // a line that found no room took the exact route and left holes: ml[].ntok == 0 marks an
+            // unused line slot, t_line[] == 0xFFFF an unused token slot
+
+            // ---- phase C: one thread per path node
+            for (uint32_t t = tid; t < n_tok; t += THREADS) {
+                if (t_line[t] == 0xFFFFu) continue;
+                const uint32_t b = t_b[t], l = t_l[t];
+                // name hash, 4 bytes a step, and the colons on the way
+                const uint32_t al = b & ~3u, sh = (b & 3u) * 8u;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(win + al);
+                uint32_t curw = wp[0];
+                TokHash h = tok_init();
+                uint32_t ncolon = 0, cpos = 0;
+                for (uint32_t i = 0; i < l; i += 4) {
+                    uint32_t nxt = wp[(i >> 2) + 1];
+                    uint32_t w = __funnelshift_r(curw, nxt, sh);
+                    curw = nxt;
+                    uint32_t rem = l - i;
+                    if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+                    tok_step(h, w);
+                    uint32_t f = eq_bytes(w, 0x3A3A3A3Au);
+                    if (f) {
+                        ncolon += __popc(f);
+                        cpos = i + ((31 - __clz(f)) >> 3);
+                    }
+                }
+                const uint64_t hv = tok_value(h, l);
+                // chrom:start-end  or  chrom:pos.<anything>
+                uint32_t fl = win[b - 1] == '>' ? TF_PLUS : 0;
+                uint32_t sval = 0;
+                int64_t nlen = 0;
+                if (ncolon == 1) {
+                    uint32_t q = b + cpos + 1, end = b + l;
+                    uint32_t v0 = 0, nd0 = 0;
+                    for (; q < end; ++q) {
+                        uint32_t d = uint32_t(win[q]) - '0';
+                        if (d > 9) break;
+                        v0 = v0 * 10 + d;
+                        ++nd0;
+                    }
+                    if (nd0 >= 1 && nd0 <= 9 && q < end) {
+                        uint32_t c = win[q];
+                        if (c == '.') {
+                            Rec<SmemSrc> rec(a, SmemSrc{win}, 0, 0, loc);
+                            Rec<SmemSrc>::Tok tk{b, l};
+                            if (rec.alt_lookup(hv, tk, nlen) && nlen > 0 && nlen <= 0x7FFFFFFF) fl |= TF_ALT | TF_PLAIN;
+                        } else if (c == '-') {
+                            uint32_t v1 = 0, nd1 = 0;
+                            for (++q; q < end; ++q) {
+                                uint32_t d = uint32_t(win[q]) - '0';
+                                if (d > 9) break;
+                                v1 = v1 * 10 + d;
+                                ++nd1;
+                            }
+                            nlen = int64_t(v1) - int64_t(v0) + 1;
+                            if (q == end && nd1 >= 1 && nd1 <= 9 && nlen > 0) fl |= TF_PLAIN;
+                        }
+                    }
+                    sval = v0;
+                }
+                t_hash[t] = hv;
+                t_len[t] = int32_t(nlen);
+                t_sval[t] = sval;
+                t_flags[t] = uint8_t(fl);
+            }
+            __syncthreads();
+
+            // ---- phase D: per multi-node line, coordinates + prefix sums + overlap verdicts;
+            //      per node, "could this name occur inside an earlier one" (first-occurrence rules :206, :269-271)
+            for (uint32_t k = tid; k < n_ml; k += THREADS) {
+                MLine L = ml[k];
+                if (L.ntok == 0) continue;
+                // Tlen, Ts, Te: digit-only columns 7-9 (validated in phase B)
+                int64_t v[3];
+                uint32_t q = uint32_t(L.p6) + 1, too_long = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    int64_t x = 0;
+                    uint32_t nd = 0;
+                    for (;; ++q) {
+                        uint32_t d = uint32_t(win[q]) - '0';
+                        if (d > 9) break;
+                        nd += (x != 0 || d != 0);
+                        x = x * 10 + int64_t(d);
+                    }
+                    too_long |= nd > 18;
+                    v[j] = x;
+                    ++q;
+                }
+                if (too_long) {
+                    // the reference has bigints; this implementation stops at 18 digits and says so
+                    report(a, SVJG_BAD_RANGE, uint32_t(tile_start) + (uint32_t(L.s) - HEAD));
+                    ml[k].flags = uint16_t(L.flags | LF_SKIP);
+                    continue;
+                }
+                const int64_t tlen = v[0], ts = v[1], te = v[2];
+                uint32_t bad = 0;
+                int64_t total = 0;
+                for (uint32_t t = L.tok0; t < uint32_t(L.tok0) + L.ntok; ++t) {
+                    bad |= !(t_flags[t] & TF_PLAIN);
+                    total += t_len[t];
+                    t_pre[t] = total;
+                }
+                const int64_t tail = tlen - te - 1;
+                for (uint32_t t = uint32_t(L.tok0) + 1; t < uint32_t(L.tok0) + L.ntok; ++t) {
+                    int64_t pre = t_pre[t - 1];
+                    bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);   // :269-273
+                    if (ok) t_flags[t] |= TF_OK;
+                }
+                if (bad) ml[k].flags = uint16_t(L.flags | LF_GENERAL);
+            }
+            __syncthreads();
+            for (uint32_t t = tid; t < n_tok; t += THREADS) {
+                const uint32_t li = t_line[t];
+                if (li == 0xFFFFu) continue;
+                const uint32_t t0 = ml[li].tok0;
+                const uint32_t sv = t_sval[t], kind = t_flags[t] & TF_ALT;
+                bool clash = false;
+                for (uint32_t j = t0; j < t; ++j) clash |= (t_sval[j] == sv) && ((t_flags[j] & TF_ALT) == kind);
+                if (clash) ml[li].flags |= LF_GENERAL;   // benign race: every writer sets the same bit
+            }
+            __syncthreads();
+
+            // ---- phase E: one thread per link (node t with its predecessor), both keys
+            for (uint32_t t = tid; t < n_tok; t += THREADS) {
+                const uint32_t li = t_line[t];
+                if (li == 0xFFFFu) continue;
+                const MLine L = ml[li];
+                if (t == L.tok0 || (L.flags & (LF_GENERAL | LF_SKIP))) continue;
+                const uint32_t fb = t_flags[t];
+                const bool ok = fb & TF_OK;
+                if (!ok && !all_links) continue;
+                const uint32_t off = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
+                const uint32_t len = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
                 Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
-                rec.ps = e4.y;
-                rec.pe = e4.z;
-                rec.reparse_coords(end);
-                rec.resolve();
+                rec.stage_sv = h_sv;
+                rec.stage_ml = h_ml;
+                rec.stage_n = &s_nhits;
+                rec.stage_line = li;
+                Rec<SmemSrc>::Tok A{t_b[t - 1], t_l[t - 1]}, B{t_b[t], t_l[t]};
+                rec.link(A, t_hash[t - 1], t_flags[t - 1] & TF_PLUS, B, t_hash[t], fb & TF_PLUS, true, ok);
                 if (rec.err) report(a, rec.err, off);
+            }
+            for (uint32_t k = tid; k < n_ml; k += THREADS) {
+                const MLine L = ml[k];
+                if (!(L.flags & LF_GENERAL) || (L.flags & LF_SKIP)) continue;
+                const uint32_t off = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
+                const uint32_t len = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
+                general_line(a, win, L.ps, L.p6, L.e, off, len, loc);
             }
         }
         __syncthreads();
+    }
+    // hits of the last tile
+    {
+        const uint32_t n_staged = min(s_nhits, uint32_t(HCAP));
+        if (tid == 0 && n_staged) s_hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
+        __syncthreads();
+        if (n_staged) flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, s_hbase);
     }
 
     // ---- per-CTA statistics

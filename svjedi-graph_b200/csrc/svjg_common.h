@@ -11,16 +11,21 @@
 
 namespace svjg {
 
-// ---- token hash: two independent 32-bit multiplicative streams over the bytes
+// ---- token hash: two independent 32-bit multiplicative streams over the name
+// taken as little-endian 4-byte words (the last one zero padded), closed with
+// the length
 struct TokHash {
     uint32_t a, b;
 };
 SVJG_HD TokHash tok_init() { return TokHash{0x811C9DC5u, 0x2F0B4A67u}; }
-SVJG_HD void tok_step(TokHash &h, uint32_t c) {
-    h.a = (h.a ^ c) * 0x01000193u;
-    h.b = (h.b ^ c) * 0x5BD1E995u + 0x7F4A7C15u;
+SVJG_HD void tok_step(TokHash &h, uint32_t w) {
+    uint32_t x = h.a ^ w;
+    h.a = ((x << 13) | (x >> 19)) * 0x9E3779B1u;
+    h.b = (h.b ^ w) * 0x85EBCA77u + 0x7F4A7C15u;
 }
-SVJG_HD uint64_t tok_value(const TokHash &h) { return (uint64_t(h.a) << 32) | h.b; }
+SVJG_HD uint64_t tok_value(const TokHash &h, uint32_t len) {
+    return (uint64_t(h.a ^ (len * 0x27D4EB2Fu)) << 32) | h.b;
+}
 
 SVJG_HD uint64_t mix64(uint64_t x) {
     x ^= x >> 30;
@@ -45,7 +50,7 @@ SVJG_HD uint64_t alt_hash(uint64_t tok) { return mix64(tok ^ 0xA0761D6478BD642Fu
 // DRAM/L2 sector for everything but the name check.
 struct LinkSlot {          // open addressing, linear probing, capacity = power of two
     uint64_t hash;         // link_hash of the key
-    uint32_t name_off;     // into blob: left node name then right node name
+    uint32_t name_off;     // into blob (multiple of 4): left name, zero padded to 4 bytes, then right name, padded
     uint16_t len_l, len_r;
     uint32_t ent_begin;    // entries[ent_begin .. ent_begin + count)
     uint32_t meta;         // count << 4 | poison_key << 3 | sL << 2 | sR << 1 | used

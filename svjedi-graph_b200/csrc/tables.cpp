@@ -419,8 +419,12 @@ static bool scan_gfa(const char *text, size_t len, std::vector<std::pair<std::st
 // ---------------------------------------------------------------------------
 static uint64_t hash_bytes(const char *s, size_t n) {
     TokHash h = tok_init();
-    for (size_t i = 0; i < n; ++i) tok_step(h, (unsigned char)s[i]);
-    return tok_value(h);
+    for (size_t i = 0; i < n; i += 4) {
+        uint32_t w = 0;
+        for (size_t k = 0; k < 4 && i + k < n; ++k) w |= uint32_t((unsigned char)s[i + k]) << (8 * k);
+        tok_step(h, w);
+    }
+    return tok_value(h, uint32_t(n));
 }
 
 static uint32_t pow2_at_least(uint64_t n) {
@@ -500,8 +504,11 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         s.ent_begin = ent_begin[ps.key];
         s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | (sl << 2) | (sr << 1) | 1u;
         s.ent0 = cnt ? t->entries[ent_begin[ps.key]] : ENTRY_POISON;
+        // every name starts on a 4-byte boundary and is zero padded: the kernel compares words
         t->blob.insert(t->blob.end(), k.begin(), k.begin() + len_l);
+        t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
         t->blob.insert(t->blob.end(), k.begin() + off_r, k.begin() + off_r + len_r);
+        t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
         if (t->blob.size() >= 0xFFFF0000ull) {
             err = "link table name blob exceeds 4 GiB";
             return false;
@@ -523,6 +530,7 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         s.seq_len = a.second;
         s.used = 1;
         t->blob.insert(t->blob.end(), a.first.begin(), a.first.end());
+        t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
         if (t->blob.size() >= 0xFFFF0000ull) {
             err = "alt-node name blob exceeds 4 GiB";
             return false;
