@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--scale", type=float, default=None, help="shrink SV and record counts (default: full; C5: per-GPU shard)")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--kernel-only", action="store_true", help="developer mode: print the kernel times and stop")
     ap.add_argument("--cpu-sample", type=int, default=150_000, help="records the CPU baseline is timed on")
     return ap.parse_args()
 
@@ -346,6 +347,13 @@ def main():
     else:
         job_rec = n_rec
     st = filt.read_stats()
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"kernel_ms": {"filter": filt_ms, "allreduce": comm_ms, "genotype": geno_ms},
+                              "GBps": n_bytes / filt_ms / 1e6, "stats": st, "stop_after": os.environ.get("SVJG_STOP_AFTER")}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the C ABI with host buffers (copies inside the timed region)
     Ke = args.e2e_steps or max(3, min(K, 20))

@@ -6,22 +6,25 @@
 // read_gaf_line :184-198, extract_nodes :351-373, get_aln_links :200-219,
 // reverse_link :221-225, check_bkpt_overlap :258-273, get_node_len :343-349.
 //
-// Layout: a persistent grid walks 32 KiB tiles of the byte buffer.  A tile plus
-// 8 KiB of look-ahead (and the 32 bytes in front of it) is staged into shared
-// memory by one TMA bulk copy (cp.async.bulk + mbarrier).  Work is then spread
-// at the granularity that keeps lanes busy in each phase:
-//   A  byte-parallel: every thread classifies 16-byte chunks with SWAR compares,
-//      writes a newline bitmap and appends the line starts it sees to a list;
-//   B  line-parallel: one thread per line finds the 12 columns with word-wide
-//      tab compares, validates the integer columns, classifies the path column
-//      and, for paths with >= 2 nodes, appends one record per node to a token list;
-//   C  token-parallel: one thread per path node hashes the name (4 bytes a step),
+// Layout: every WARP is an independent worker with its own slice of shared memory
+// (no block-wide barrier anywhere).  A warp walks 4 KiB tiles of the byte buffer;
+// a tile plus 2 KiB of look-ahead (and the 32 bytes in front of it) is staged into
+// the warp's window by one TMA bulk copy (cp.async.bulk + mbarrier).  Per tile the
+// 32 lanes are re-assigned at the granularity that keeps them busy:
+//   A  byte-parallel: every lane classifies 32 bytes with SWAR compares; ballots
+//      turn the newline flags into the ordered list of line boundaries;
+//   B  line-parallel: one lane per line finds the 12 columns (tab bitmaps of fixed
+//      spans, so lanes stay converged), validates the integer columns, walks the
+//      path column and, for paths with >= 2 nodes, appends one record per node
+//      to the token list (slots handed out by a warp scan);
+//   C  token-parallel: one lane per path node hashes the name (4 bytes a step),
 //      parses chrom:start-end / looks the alt node up, and stores the record;
-//   D  line-parallel over multi-node lines: Tlen/Ts/Te, prefix sums of the node
+//   D  line-parallel over multi-node lines: Tlen/Ts/Te, running sums of the node
 //      lengths, the breakpoint-overlap verdict of every link; token-parallel
 //      check that no node name can occur inside an earlier one;
-//   E  link-parallel: forward and reverse key probes of the link hash, counter
-//      atomics and hit tuples.
+//   E  link-parallel: forward and reverse key probes of the link hash; hits are
+//      staged in shared memory and written out (one cursor atomic per warp and
+//      tile, warp-aggregated counter atomics) while the next tile's bytes fly in.
 // Anything that is not of the plain shape (odd integers, odd node names, a name
 // that could be a substring of an earlier one, lines longer than the window, ...)
 // is handed to the exact per-line routines parse_fields() / general(), which
@@ -31,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "svjg_internal.h"
@@ -40,30 +44,28 @@ using namespace svjg;
 
 namespace {
 
-constexpr int TILE = 32768;
-constexpr int LOOKAHEAD = 4096;
-constexpr int HEAD = 32;
-constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 36896 = 32 * 1153
-constexpr int THREADS = 256;
-constexpr int NWARPS = THREADS / 32;
-constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunks = words of newline bitmap
+constexpr int TILE = 4096;                     // bytes a warp owns per step
+constexpr int LOOKAHEAD = 2048;                // staged behind the tile so that lines starting in it are whole
+constexpr int HEAD = 32;                       // staged in front of it (the newline that starts the first line)
+constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 6176 = 32 * 193
+constexpr int WARPS = 4;                       // per block; warps never synchronise with each other
+constexpr int THREADS = WARPS * 32;
+constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunks
 constexpr int HEAD_SPAN = 96;                  // bytes searched for the tabs of columns 1-5 on the fast route
 constexpr int TAIL_SPAN = 96;                  // bytes searched for the tabs of columns 7-12
-constexpr int LINE_SPAN = 160;                 // spare bytes behind the window for those fixed-span reads
-constexpr int LCAP = 2048;                     // line starts per tile (more => some line < 16 bytes)
-constexpr int MCAP = 512;                      // multi-node lines per tile on the token-parallel route
-constexpr int TCAP = 1536;                     // path nodes per tile on the token-parallel route
-constexpr int HCAP = 1024;                     // hits staged per tile before the flush
-static_assert(WIN % 32 == 0 && WIN + LINE_SPAN <= 65536, "window offsets are 16 bit, bitmap words are 32 bit");
+constexpr int SPARE = 176;                     // readable bytes behind the window for those fixed-span reads
+constexpr int NLCAP = 400;                     // newlines per window (more => some line is shorter than 16 bytes)
+constexpr int MCAP = 64;                       // multi-node lines per tile on the token-parallel route
+constexpr int TCAP = 192;                      // path nodes per tile on the token-parallel route
+constexpr int HCAP = 128;                      // hits staged per tile before the flush
+static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit");
 
-// shared memory map (bytes)
+// shared memory map of ONE warp (bytes)
 constexpr int OFF_WIN = 0;
-constexpr int OFF_NLB = OFF_WIN + WIN + LINE_SPAN + 16;     // spare bytes: fixed-span reads may run past the window
-constexpr int OFF_LST = OFF_NLB + (NPAIRS + 3) * 4;
-constexpr int OFF_ML = (OFF_LST + LCAP * 2 + 15) & ~15;     // MLine[MCAP]
+constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline positions, ascending  u16[NLCAP]
+constexpr int OFF_ML = (OFF_NL + NLCAP * 2 + 15) & ~15;     // MLine[MCAP]
 constexpr int OFF_TH = (OFF_ML + MCAP * 16 + 15) & ~15;     // token hash   u64[TCAP]
-constexpr int OFF_TPRE = OFF_TH + TCAP * 8;                 // inclusive prefix of node lengths i64[TCAP]
-constexpr int OFF_TLEN = OFF_TPRE + TCAP * 8;               // node length  i32[TCAP]
+constexpr int OFF_TLEN = OFF_TH + TCAP * 8;                 // node length  i32[TCAP]
 constexpr int OFF_TS = OFF_TLEN + TCAP * 4;                 // start value  u32[TCAP]
 constexpr int OFF_TB = OFF_TS + TCAP * 4;                   // token begin  u16[TCAP]
 constexpr int OFF_TL = OFF_TB + TCAP * 2;                   // token length u16[TCAP]
@@ -71,7 +73,8 @@ constexpr int OFF_TLINE = OFF_TL + TCAP * 2;                // MLine index  u16[
 constexpr int OFF_TF = OFF_TLINE + TCAP * 2;                // flags        u8[TCAP]
 constexpr int OFF_HSV = (OFF_TF + TCAP + 15) & ~15;         // staged hits: 2*sv + allele  u32[HCAP]
 constexpr int OFF_HML = OFF_HSV + HCAP * 4;                 //              MLine index    u16[HCAP]
-constexpr int SMEM_BYTES = (OFF_HML + HCAP * 2 + 15) & ~15;
+constexpr int WARP_SMEM = (OFF_HML + HCAP * 2 + 127) & ~127;
+constexpr int SMEM_BYTES = WARP_SMEM * WARPS;
 
 constexpr uint32_t FLAG_EXACT_CHECKS = SVJG_FLAG_EXACT_CHECKS;   // probe links whose overlap test fails too
 constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through general()
@@ -711,32 +714,49 @@ __device__ __forceinline__ bool has_comma(const uint8_t *win, uint32_t lo, uint3
     return (f | (eq_bytes(lds32(win, a1), 0x2C2C2C2Cu) & him)) != 0;
 }
 
-// Writes this tile's staged hits: one cursor atomic for the block, coalesced tuple stores and
-// warp-aggregated counter atomics (one per distinct SV allele among the 32 hits a warp holds).
+// Writes a warp's staged hits: coalesced tuple stores and warp-aggregated counter atomics
+// (one per distinct SV allele among the 32 hits the warp holds at a time).
 __device__ __forceinline__ void flush_hits(const FilterArgs &a, const uint32_t *h_sv, const uint16_t *h_ml, const MLine *ml,
-                                           uint32_t n, uint64_t tile_start, unsigned long long base) {
-    for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
-        const uint32_t sv2 = h_sv[i];
-        const MLine L = ml[h_ml[i]];
-        const unsigned peers = __match_any_sync(__activemask(), sv2);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(a.counts + sv2, uint32_t(__popc(peers)));
-        const unsigned long long k = base + i;
-        if (k < a.hit_cap) {
-            a.hit_sv2[k] = sv2;
-            a.hit_off[k] = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
-            a.hit_len[k] = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
+                                           uint32_t n, uint64_t tile_start, unsigned long long base, int lane) {
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool act = i < n;
+        const uint32_t sv2 = act ? h_sv[i] : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, sv2);
+        if (act) {
+            if (lane == __ffs(peers) - 1) atomicAdd(a.counts + sv2, uint32_t(__popc(peers)));
+            const MLine L = ml[h_ml[i]];
+            const unsigned long long k = base + i;
+            if (k < a.hit_cap) {
+                a.hit_sv2[k] = sv2;
+                a.hit_off[k] = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
+                a.hit_len[k] = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 4) filter_kernel(const FilterArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    __shared__ __align__(8) uint64_t mbars[WARPS];
+    __shared__ uint32_t s_hits[WARPS];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint8_t *smem = smem_all + warp * WARP_SMEM;
     uint8_t *win = smem + OFF_WIN;
-    uint32_t *nlb = reinterpret_cast<uint32_t *>(smem + OFF_NLB);
-    uint16_t *lstart = reinterpret_cast<uint16_t *>(smem + OFF_LST);
+    uint16_t *nl = reinterpret_cast<uint16_t *>(smem + OFF_NL);
     MLine *ml = reinterpret_cast<MLine *>(smem + OFF_ML);
     uint64_t *t_hash = reinterpret_cast<uint64_t *>(smem + OFF_TH);
-    int64_t *t_pre = reinterpret_cast<int64_t *>(smem + OFF_TPRE);
     int32_t *t_len = reinterpret_cast<int32_t *>(smem + OFF_TLEN);
     uint32_t *t_sval = reinterpret_cast<uint32_t *>(smem + OFF_TS);
     uint16_t *t_b = reinterpret_cast<uint16_t *>(smem + OFF_TB);
@@ -745,22 +765,22 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
     uint8_t *t_flags = smem + OFF_TF;
     uint32_t *h_sv = reinterpret_cast<uint32_t *>(smem + OFF_HSV);
     uint16_t *h_ml = reinterpret_cast<uint16_t *>(smem + OFF_HML);
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t s_nlines, s_nml, s_ntok, s_nhits;
-    __shared__ unsigned long long s_hbase;
+    uint64_t *mbar = &mbars[warp];
+    uint32_t *s_nhits = &s_hits[warp];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&mbar, 1);
-        s_nhits = 0;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        *s_nhits = 0;
     }
-    __syncthreads();
+    __syncwarp();
     uint32_t phase = 0;
     Local loc;
     const bool all_links = a.flags & FLAG_EXACT_CHECKS;
+    const uint32_t stop_after = (a.flags >> 8) & 7u;     // profiling hook (SVJG_STOP_AFTER): 1 = A, 2 = B, 3 = C, 4 = D
     uint64_t prev_tile_start = 0;
+    const uint32_t n_workers = gridDim.x * WARPS;
 
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < a.n_tiles; tile += n_workers) {
         const uint64_t tile_start = uint64_t(tile) * TILE;
         const uint64_t g0 = tile_start ? tile_start - HEAD : 0;
         const uint32_t dst0 = tile_start ? 0 : HEAD;
@@ -772,245 +792,254 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
         const uint32_t valid_end = dst0 + nbytes;
 
         // the previous tile's hits go out while this tile's bytes come in
-        const uint32_t n_staged = min(s_nhits, uint32_t(HCAP));
-        if (tid == 0) {
+        const uint32_t n_staged = min(*s_nhits, uint32_t(HCAP));
+        unsigned long long hbase = 0;
+        if (lane == 0) {
             if (bulk) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&mbar, bulk);
-                bulk_g2s(win + dst0, a.gaf + g0, bulk, &mbar);
+                mbar_expect_tx(mbar, bulk);
+                bulk_g2s(win + dst0, a.gaf + g0, bulk, mbar);
             }
-            if (n_staged) s_hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
+            if (n_staged) hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
         }
-        __syncthreads();
-        if (n_staged) flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, s_hbase);
+        if (n_staged) {
+            hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
+            flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, hbase, lane);
+        }
         prev_tile_start = tile_start;
-        for (uint32_t i = bulk + tid; i < nbytes; i += THREADS) win[dst0 + i] = __ldg(a.gaf + g0 + i);
-        if (dst0 && tid < HEAD) win[tid] = tid == HEAD - 1 ? '\n' : 0;   // "newline" in front of byte 0 of the file
-        for (uint32_t i = valid_end + tid; i < WIN + LINE_SPAN + 16; i += THREADS) win[i] = 0;
-        if (tid < 3) nlb[NPAIRS + tid] = 0;
-        __syncthreads();                       // every thread is done with the previous tile's ml[] / staged hits
-        if (tid == 0) {
-            s_nlines = 0;
-            s_nml = 0;
-            s_ntok = 0;
-            s_nhits = 0;
-        }
+        __syncwarp();
+        if (lane == 0) *s_nhits = 0;
+        for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
+        if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;               // "newline" in front of byte 0 of the file
+        for (uint32_t i = valid_end + lane; i < WIN + SPARE; i += 32) win[i] = 0;
         if (bulk) {
-            mbar_wait(&mbar, phase);
+            mbar_wait(mbar, phase);
             phase ^= 1;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- phase A: newline bitmap + unordered list of the line starts this tile owns.
-        // A lane takes two adjacent 16-byte chunks = one 32-bit word of the bitmap.
-        {
-            const uint32_t own_lo = HEAD - 1;                                        // newline positions p with
-            const uint32_t own_hi = min(uint32_t(HEAD + TILE), valid_end) - 1;       // HEAD <= p+1 < own end
-            for (int c0 = warp * 32; c0 < NPAIRS; c0 += NWARPS * 32) {
-                const int c = c0 + lane;
-                uint32_t m = 0;
-                if (c < NPAIRS) {
-                    const uint4 v0 = *reinterpret_cast<const uint4 *>(win + c * 32);
-                    const uint4 v1 = *reinterpret_cast<const uint4 *>(win + c * 32 + 16);
-                    m = mask16(v0, IsNewline()) | (mask16(v1, IsNewline()) << 16);
-                    nlb[c] = m;
-                    const uint32_t p0 = uint32_t(c) * 32u;
-                    if (p0 < own_lo || p0 + 32u > own_hi) {                           // edge words only
-                        const int lo = int(own_lo) - int(p0), hi = int(own_hi) - int(p0);   // keep bits [lo, hi)
-                        if (lo > 0) m = lo >= 32 ? 0u : (m & (0xFFFFFFFFu << lo));
-                        if (hi < 32) m = hi <= 0 ? 0u : (m & ((1u << hi) - 1u));
-                    }
-                }
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m != 0);
-                if (bal) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&s_nlines, __popc(bal));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (m) {
-                        uint32_t q = base + __popc(bal & ((1u << lane) - 1u));
-                        if (q < LCAP) lstart[q] = uint16_t(c * 32 + __ffs(m));       // start = newline position + 1
-                        m &= m - 1;
-                        while (m) {                                                   // a second newline in 32 bytes (rare)
-                            q = atomicAdd(&s_nlines, 1u);
-                            if (q < LCAP) lstart[q] = uint16_t(c * 32 + __ffs(m));
-                            m &= m - 1;
-                        }
-                    }
-                }
+        // ---- phase A: ordered list of the newline positions from HEAD-1 on.  A lane takes two
+        // adjacent 16-byte chunks; the scan stops behind the tile once the last owned line has its end.
+        const uint32_t own_end = min(uint32_t(HEAD + TILE), valid_end);   // lines starting before own_end are ours
+        uint32_t n_nl = 0, n_own = 0;
+        for (int c0 = 0; c0 < NPAIRS; c0 += 32) {
+            if (uint32_t(c0) * 32u >= own_end && n_nl > n_own) break;
+            const int c = c0 + lane;
+            const uint32_t p0 = uint32_t(c) * 32u;
+            uint32_t m = 0;
+            if (c < NPAIRS) {
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(win + p0);
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(win + p0 + 16);
+                m = mask16(v0, IsNewline()) | (mask16(v1, IsNewline()) << 16);
+                if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
             }
+            const uint32_t cnt = __popc(m);
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+            if (!bal) continue;
+            uint32_t q, total;
+            if (__ballot_sync(0xFFFFFFFFu, cnt > 1) == 0) {
+                q = __popc(bal & lt_mask);
+                total = __popc(bal);
+            } else {                                                      // two newlines within 32 bytes (rare)
+                const uint32_t incl = warp_incl_scan(cnt, lane);
+                q = incl - cnt;
+                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            // newline at p starts an owned line iff p + 1 < own_end
+            const int hi = int(own_end) - 1 - int(p0);
+            const uint32_t mo = hi >= 32 ? m : (hi <= 0 ? 0u : (m & ((1u << hi) - 1u)));
+            n_own += __reduce_add_sync(0xFFFFFFFFu, uint32_t(__popc(mo)));
+            uint32_t idx = n_nl + q;
+            while (m) {
+                if (idx < NLCAP) nl[idx] = uint16_t(p0 + uint32_t(__ffs(m) - 1));
+                ++idx;
+                m &= m - 1;
+            }
+            n_nl += total;
         }
-        __syncthreads();
-        const uint32_t n_lines = s_nlines;
+        __syncwarp();
 
-        if (n_lines > LCAP) {
-            // more than LCAP lines in 32 KiB: some line is shorter than 16 bytes and cannot hold 12 columns
-            if (tid == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
+        uint32_t n_ml = 0, n_tok = 0;
+        if (stop_after == 1) continue;
+        if (n_nl > NLCAP) {
+            // that many lines in 6 KiB: some line is shorter than 16 bytes and cannot hold 12 columns
+            if (lane == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
         } else {
-            // ---- phase B: one thread per line
-            for (uint32_t k = tid; k < n_lines; k += THREADS) {
-                const uint32_t s = lstart[k];
-                const uint32_t off = uint32_t(tile_start) + (s - HEAD);
-                loc.n_rec++;
-                // end of the line: next newline at or after s
-                uint32_t wi = s >> 5;
-                uint32_t bits = nlb[wi] & (0xFFFFFFFFu << (s & 31u));
-                while (!bits && wi < NPAIRS - 1) bits = nlb[++wi];
-                uint32_t e;
-                const bool has_nl = bits != 0;
-                if (has_nl) {
-                    e = wi * 32 + (__ffs(bits) - 1);
-                } else if (at_eof) {
-                    e = valid_end;
+            // ---- phase B: one lane per line
+            bool route_full = false;
+            for (uint32_t k0 = 0; k0 < n_own; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                uint32_t want = 0;                 // path nodes of a line that asks for the token-parallel route
+                uint32_t s = 0, e = 0, ps = 0, pe = 0, off = 0, len = 0;
+                bool has_nl = false;
+                if (k < n_own) {
+                    s = uint32_t(nl[k]) + 1u;
+                    off = uint32_t(tile_start) + (s - HEAD);
+                    loc.n_rec++;
+                    bool in_win = true;
+                    if (k + 1 < n_nl) {
+                        e = nl[k + 1];
+                        has_nl = true;
+                    } else if (at_eof) {
+                        e = valid_end;
+                    } else {
+                        in_win = false;
+                        long_line(a, tile_start + TILE + LOOKAHEAD, off, loc);
+                    }
+                    if (in_win) {
+                        len = e - s + (has_nl ? 1u : 0u);
+                        // columns 1-5: tab bitmap of the first HEAD_SPAN bytes (fixed trip count: lanes stay together)
+                        bool plain = e > s && !py_space(win[e - 1]);
+                        uint32_t p1, p2, p3, p4, p5;
+                        {
+                            const uint32_t base = s & ~15u;
+                            uint32_t tm[HEAD_SPAN / 32];
+#pragma unroll
+                            for (int j = 0; j < HEAD_SPAN / 32; ++j) {
+                                const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
+                                const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
+                                tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
+                            }
+                            tm[0] &= 0xFFFFFFFFu << (s - base);
+                            const uint32_t rel_e = e - base;
+#pragma unroll
+                            for (int j = 0; j < HEAD_SPAN / 32; ++j)
+                                if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
+                            // the first 5 tab positions (relative to base), one byte each, newest in the low byte
+                            uint32_t r0 = 0, r1 = 0, nt = 0;
+#pragma unroll
+                            for (int j = 0; j < HEAD_SPAN / 32; ++j) {
+                                uint32_t m = tm[j];
+                                while (m && nt < 5) {
+                                    const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                                    m &= m - 1;
+                                    r1 = __funnelshift_l(r0, r1, 8);
+                                    r0 = (r0 << 8) | pos;
+                                    ++nt;
+                                }
+                            }
+                            plain &= nt == 5;
+                            p1 = base + (r1 & 255u), p2 = base + (r0 >> 24), p3 = base + ((r0 >> 16) & 255u);
+                            p4 = base + ((r0 >> 8) & 255u), p5 = base + (r0 & 255u);
+                        }
+                        // column 6, the path [ps, pe): walk to its tab; count token starts (a non-delimiter byte
+                        // right after a delimiter) and look for ',' on the way
+                        ps = p5 + 1;
+                        pe = e;
+                        uint32_t ntok = 0, comma = 0;
+                        if (plain) {
+                            uint32_t carry = 0;   // delimiter flag of the byte in front of the word, at bit 7
+                            uint32_t keep = 0xFFFFFFFFu << (8u * (ps & 3u));
+                            for (uint32_t w0 = ps & ~3u; w0 < e; w0 += 4) {
+                                const uint32_t w = lds32(win, w0);
+                                const uint32_t tb = eq_bytes(w, 0x09090909u) & keep;
+                                const uint32_t d = delim_bytes(w);
+                                if (tb) {
+                                    const uint32_t j = uint32_t(__ffs(tb) - 1) >> 3;          // byte of the tab in this word
+                                    pe = w0 + j;
+                                    keep &= j ? (0xFFFFFFFFu >> (8u * (4u - j))) : 0u;
+                                }
+                                ntok += __popc(((d << 8) | carry) & ~d & SVJG_H8 & keep);
+                                comma |= eq_bytes(w, 0x2C2C2C2Cu) & keep;
+                                if (tb) break;
+                                carry = d >> 24;
+                                keep = 0xFFFFFFFFu;
+                            }
+                            plain = pe < e && pe > ps;
+                        }
+                        // columns 7-12: tab bitmap of the TAIL_SPAN bytes around the end of the path
+                        if (plain) {
+                            const uint32_t p6 = pe;
+                            const uint32_t base = p6 & ~15u;
+                            uint32_t tm[TAIL_SPAN / 32];
+#pragma unroll
+                            for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                                const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
+                                const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
+                                tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
+                            }
+                            tm[0] &= 0xFFFFFFFEu << (p6 - base);                               // tabs after p6
+                            const uint32_t rel_e = e - base;
+#pragma unroll
+                            for (int j = 0; j < TAIL_SPAN / 32; ++j)
+                                if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
+                            uint32_t r0 = 0, r1 = 0, nt = 0;
+#pragma unroll
+                            for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                                uint32_t m = tm[j];
+                                while (m && nt < 6) {
+                                    const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                                    m &= m - 1;
+                                    r1 = __funnelshift_l(r0, r1, 8);
+                                    r0 = (r0 << 8) | pos;
+                                    ++nt;
+                                }
+                            }
+                            if (nt == 5 && rel_e <= TAIL_SPAN) {                               // no tab after column 12
+                                r1 = __funnelshift_l(r0, r1, 8);
+                                r0 = (r0 << 8) | rel_e;
+                                ++nt;
+                            }
+                            plain = nt == 6;
+                            const uint32_t p7 = base + ((r1 >> 8) & 255u), p8 = base + (r1 & 255u), p9 = base + (r0 >> 24),
+                                           p10 = base + ((r0 >> 16) & 255u), p11 = base + ((r0 >> 8) & 255u),
+                                           p12 = base + (r0 & 255u);
+                            if (plain) {
+                                // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
+                                const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) &
+                                                  (p8 - p7 > 1u) & (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) &
+                                                  (p12 - p11 > 1u);
+                                plain = w_ok && win[p10 + 1] != '0';
+                                if (plain)
+                                    plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
+                            }
+                        }
+                        if (!plain) {
+                            slow_line(a, win, s, e, off, len, loc);
+                        } else if (!is_delim(win[ps])) {
+                            // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
+                            if (comma) slow_line(a, win, s, e, off, len, loc);
+                        } else if (ntok >= 2) {                                                // :133
+                            loc.n_multi++;
+                            if ((a.flags & FLAG_FORCE_GENERAL) || ntok > TCAP) general_line(a, win, ps, pe, e, off, len, loc);
+                            else want = ntok;
+                        }
+                    }
+                }
+                __syncwarp();
+                // slots on the token-parallel route for the lanes that want them (in lane order, no holes)
+                const uint32_t wb = __ballot_sync(0xFFFFFFFFu, want != 0);
+                if (!wb) continue;
+                const uint32_t incl = warp_incl_scan(want, lane);
+                const uint32_t t0 = n_tok + incl - want;
+                const uint32_t li = n_ml + __popc(wb & lt_mask);
+                const bool fits = want && !route_full && t0 + want <= TCAP && li < MCAP;
+                const uint32_t nofit = __ballot_sync(0xFFFFFFFFu, want && !fits);
+                if (nofit) {                       // everything from the first lane without room takes the exact route
+                    const int first = __ffs(nofit) - 1;
+                    n_tok = __shfl_sync(0xFFFFFFFFu, t0, first);
+                    n_ml = __shfl_sync(0xFFFFFFFFu, li, first);
+                    route_full = true;
                 } else {
-                    long_line(a, tile_start + TILE + LOOKAHEAD, off, loc);
-                    continue;
+                    n_tok += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    n_ml += __popc(wb);
                 }
-                const uint32_t len = e - s + (has_nl ? 1u : 0u);
-
-                // columns 1-5: tab bitmap of the first HEAD_SPAN bytes (fixed trip count: lanes stay together)
-                bool plain = e > s && !py_space(win[e - 1]);
-                uint32_t p1, p2, p3, p4, p5;
-                {
-                    const uint32_t base = s & ~15u;
-                    uint32_t tm[HEAD_SPAN / 32];
-#pragma unroll
-                    for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                        const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
-                        const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
-                        tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                    }
-                    tm[0] &= 0xFFFFFFFFu << (s - base);
-                    const uint32_t rel_e = e - base;
-#pragma unroll
-                    for (int j = 0; j < HEAD_SPAN / 32; ++j)
-                        if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
-                    // the first 5 tab positions (relative to base), one byte each, newest in the low byte
-                    uint32_t r0 = 0, r1 = 0, nt = 0;
-#pragma unroll
-                    for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                        uint32_t m = tm[j];
-                        while (m && nt < 5) {
-                            const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                            m &= m - 1;
-                            r1 = __funnelshift_l(r0, r1, 8);
-                            r0 = (r0 << 8) | pos;
-                            ++nt;
-                        }
-                    }
-                    plain &= nt == 5;
-                    p1 = base + (r1 & 255u), p2 = base + (r0 >> 24), p3 = base + ((r0 >> 16) & 255u);
-                    p4 = base + ((r0 >> 8) & 255u), p5 = base + (r0 & 255u);
-                }
-                // column 6, the path [ps, pe): walk to its tab; count token starts (a non-delimiter byte
-                // right after a delimiter) and look for ',' on the way
-                const uint32_t ps = p5 + 1;
-                uint32_t pe = e, ntok = 0, comma = 0;
-                if (plain) {
-                    uint32_t carry = 0;   // delimiter flag of the byte in front of the word, at bit 7
-                    uint32_t keep = 0xFFFFFFFFu << (8u * (ps & 3u));
-                    for (uint32_t w0 = ps & ~3u; w0 < e; w0 += 4) {
-                        const uint32_t w = lds32(win, w0);
-                        const uint32_t tb = eq_bytes(w, 0x09090909u) & keep;
-                        const uint32_t d = delim_bytes(w);
-                        if (tb) {
-                            const uint32_t j = uint32_t(__ffs(tb) - 1) >> 3;          // byte of the tab in this word
-                            pe = w0 + j;
-                            keep &= j ? (0xFFFFFFFFu >> (8u * (4u - j))) : 0u;
-                        }
-                        ntok += __popc(((d << 8) | carry) & ~d & SVJG_H8 & keep);
-                        comma |= eq_bytes(w, 0x2C2C2C2Cu) & keep;
-                        if (tb) break;
-                        carry = d >> 24;
-                        keep = 0xFFFFFFFFu;
-                    }
-                    plain = pe < e && pe > ps;
-                }
-                // columns 7-12: tab bitmap of the TAIL_SPAN bytes around the end of the path
-                uint32_t p6 = pe, p12 = 0;
-                if (plain) {
-                    const uint32_t base = p6 & ~15u;
-                    uint32_t tm[TAIL_SPAN / 32];
-#pragma unroll
-                    for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                        const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
-                        const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
-                        tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                    }
-                    tm[0] &= 0xFFFFFFFEu << (p6 - base);                               // tabs after p6
-                    const uint32_t rel_e = e - base;
-#pragma unroll
-                    for (int j = 0; j < TAIL_SPAN / 32; ++j)
-                        if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
-                    uint32_t r0 = 0, r1 = 0, nt = 0;
-#pragma unroll
-                    for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                        uint32_t m = tm[j];
-                        while (m && nt < 6) {
-                            const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                            m &= m - 1;
-                            r1 = __funnelshift_l(r0, r1, 8);
-                            r0 = (r0 << 8) | pos;
-                            ++nt;
-                        }
-                    }
-                    if (nt == 5 && rel_e <= TAIL_SPAN) {                               // no tab after column 12
-                        r1 = __funnelshift_l(r0, r1, 8);
-                        r0 = (r0 << 8) | rel_e;
-                        ++nt;
-                    }
-                    plain = nt == 6;
-                    const uint32_t p7 = base + ((r1 >> 8) & 255u), p8 = base + (r1 & 255u), p9 = base + (r0 >> 24),
-                                   p10 = base + ((r0 >> 16) & 255u), p11 = base + ((r0 >> 8) & 255u);
-                    p12 = base + (r0 & 255u);
-                    if (plain) {
-                        // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
-                        const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) & (p8 - p7 > 1u) &
-                                          (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) & (p12 - p11 > 1u);
-                        plain = w_ok && win[p10 + 1] != '0';
-                        if (plain) plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
-                    }
-                }
-                if (!plain) {
-                    slow_line(a, win, s, e, off, len, loc);
-                    continue;
-                }
-                if (!is_delim(win[ps])) {
-                    // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
-                    if (comma) slow_line(a, win, s, e, off, len, loc);
-                    continue;
-                }
-                const uint32_t a0 = ps & ~3u, a1 = (pe - 1u) & ~3u;
-                const uint32_t lom = 0xFFFFFFFFu << (8u * (ps & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((pe - 1u) & 3u)));
-                if (ntok < 2) continue;                                              // :133
-                loc.n_multi++;
-                uint32_t li = MCAP, t0 = TCAP;
-                if (!(a.flags & FLAG_FORCE_GENERAL) && ntok <= TCAP) {
-                    li = atomicAdd(&s_nml, 1u);
-                    t0 = atomicAdd(&s_ntok, ntok);
-                }
-                if (li >= MCAP || t0 + ntok > TCAP) {
-                    // no room on the token-parallel route (or the test hook): exact route, in place.
-                    // Slots already reserved are marked as holes for the later phases.
-                    if (li < MCAP) {
-                        MLine H{};
-                        ml[li] = H;
-                    }
-                    for (uint32_t t = t0; t < min(t0 + ntok, uint32_t(TCAP)); ++t) t_line[t] = 0xFFFFu;
+                if (want && !fits) {
                     general_line(a, win, ps, pe, e, off, len, loc);
-                    continue;
-                }
-                MLine L;
-                L.s = uint16_t(s);
-                L.e = uint16_t(e);
-                L.p6 = uint16_t(p6);
-                L.tok0 = uint16_t(t0);
-                L.ntok = uint16_t(ntok);
-                L.flags = has_nl ? LF_HAS_NL : 0;
-                L.ps = uint16_t(ps);
-                L.pad = 0;
-                ml[li] = L;
-                // token records: maximal runs of non-delimiter bytes, from the start / end flags
-                {
+                } else if (want) {
+                    MLine L;
+                    L.s = uint16_t(s);
+                    L.e = uint16_t(e);
+                    L.p6 = uint16_t(pe);
+                    L.tok0 = uint16_t(t0);
+                    L.ntok = uint16_t(want);
+                    L.flags = has_nl ? LF_HAS_NL : 0;
+                    L.ps = uint16_t(ps);
+                    L.pad = 0;
+                    ml[li] = L;
+                    // token records: maximal runs of non-delimiter bytes, from the start / end flags
+                    const uint32_t a0 = ps & ~3u, a1 = (pe - 1u) & ~3u;
+                    const uint32_t lom = 0xFFFFFFFFu << (8u * (ps & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((pe - 1u) & 3u)));
                     uint32_t t = t0, cur = 0xFFFFFFFFu, carry = 0;
                     for (uint32_t w0 = a0; w0 <= a1; w0 += 4) {
                         const uint32_t d = delim_bytes(lds32(win, w0));
@@ -1037,15 +1066,11 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
                     if (cur != 0xFFFFFFFFu) t_l[t++] = uint16_t(pe - cur);
                 }
             }
-            __syncthreads();
-            const uint32_t n_ml = min(s_nml, uint32_t(MCAP));
-            const uint32_t n_tok = min(s_ntok, uint32_t(TCAP));
-            // a line that found no room took the exact route and left holes: ml[].ntok == 0 marks an
-            // unused line slot, t_line[] == 0xFFFF an unused token slot
+            __syncwarp();
+            if (stop_after == 2) continue;
 
-            // ---- phase C: one thread per path node
-            for (uint32_t t = tid; t < n_tok; t += THREADS) {
-                if (t_line[t] == 0xFFFFu) continue;
+            // ---- phase C: one lane per path node
+            for (uint32_t t = lane; t < n_tok; t += 32) {
                 const uint32_t b = t_b[t], l = t_l[t];
                 // name hash, 4 bytes a step, and the colons on the way
                 const uint32_t al = b & ~3u, sh = (b & 3u) * 8u;
@@ -1105,13 +1130,13 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
                 t_sval[t] = sval;
                 t_flags[t] = uint8_t(fl);
             }
-            __syncthreads();
+            __syncwarp();
+            if (stop_after == 3) continue;
 
-            // ---- phase D: per multi-node line, coordinates + prefix sums + overlap verdicts;
+            // ---- phase D: per multi-node line, coordinates + running sums + overlap verdicts;
             //      per node, "could this name occur inside an earlier one" (first-occurrence rules :206, :269-271)
-            for (uint32_t k = tid; k < n_ml; k += THREADS) {
-                MLine L = ml[k];
-                if (L.ntok == 0) continue;
+            for (uint32_t k = lane; k < n_ml; k += 32) {
+                const MLine L = ml[k];
                 // Tlen, Ts, Te: digit-only columns 7-9 (validated in phase B)
                 int64_t v[3];
                 uint32_t q = uint32_t(L.p6) + 1, too_long = 0;
@@ -1135,38 +1160,36 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
                     ml[k].flags = uint16_t(L.flags | LF_SKIP);
                     continue;
                 }
-                const int64_t tlen = v[0], ts = v[1], te = v[2];
+                const int64_t ts = v[1], tail = v[0] - v[2] - 1;
                 uint32_t bad = 0;
                 int64_t total = 0;
                 for (uint32_t t = L.tok0; t < uint32_t(L.tok0) + L.ntok; ++t) {
                     bad |= !(t_flags[t] & TF_PLAIN);
                     total += t_len[t];
-                    t_pre[t] = total;
                 }
-                const int64_t tail = tlen - te - 1;
+                int64_t pre = t_len[L.tok0];
                 for (uint32_t t = uint32_t(L.tok0) + 1; t < uint32_t(L.tok0) + L.ntok; ++t) {
-                    int64_t pre = t_pre[t - 1];
-                    bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);   // :269-273
+                    const bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);   // :269-273
                     if (ok) t_flags[t] |= TF_OK;
+                    pre += t_len[t];
                 }
                 if (bad) ml[k].flags = uint16_t(L.flags | LF_GENERAL);
             }
-            __syncthreads();
-            for (uint32_t t = tid; t < n_tok; t += THREADS) {
+            __syncwarp();
+            for (uint32_t t = lane; t < n_tok; t += 32) {
                 const uint32_t li = t_line[t];
-                if (li == 0xFFFFu) continue;
                 const uint32_t t0 = ml[li].tok0;
                 const uint32_t sv = t_sval[t], kind = t_flags[t] & TF_ALT;
                 bool clash = false;
                 for (uint32_t j = t0; j < t; ++j) clash |= (t_sval[j] == sv) && ((t_flags[j] & TF_ALT) == kind);
                 if (clash) ml[li].flags |= LF_GENERAL;   // benign race: every writer sets the same bit
             }
-            __syncthreads();
+            __syncwarp();
+            if (stop_after == 4) continue;
 
-            // ---- phase E: one thread per link (node t with its predecessor), both keys
-            for (uint32_t t = tid; t < n_tok; t += THREADS) {
+            // ---- phase E: one lane per link (node t with its predecessor), both keys
+            for (uint32_t t = lane; t < n_tok; t += 32) {
                 const uint32_t li = t_line[t];
-                if (li == 0xFFFFu) continue;
                 const MLine L = ml[li];
                 if (t == L.tok0 || (L.flags & (LF_GENERAL | LF_SKIP))) continue;
                 const uint32_t fb = t_flags[t];
@@ -1177,13 +1200,13 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
                 Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
                 rec.stage_sv = h_sv;
                 rec.stage_ml = h_ml;
-                rec.stage_n = &s_nhits;
+                rec.stage_n = s_nhits;
                 rec.stage_line = li;
                 Rec<SmemSrc>::Tok A{t_b[t - 1], t_l[t - 1]}, B{t_b[t], t_l[t]};
                 rec.link(A, t_hash[t - 1], t_flags[t - 1] & TF_PLUS, B, t_hash[t], fb & TF_PLUS, true, ok);
                 if (rec.err) report(a, rec.err, off);
             }
-            for (uint32_t k = tid; k < n_ml; k += THREADS) {
+            for (uint32_t k = lane; k < n_ml; k += 32) {
                 const MLine L = ml[k];
                 if (!(L.flags & LF_GENERAL) || (L.flags & LF_SKIP)) continue;
                 const uint32_t off = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
@@ -1191,17 +1214,20 @@ __global__ void __launch_bounds__(THREADS, 2) filter_kernel(const FilterArgs a) 
                 general_line(a, win, L.ps, L.p6, L.e, off, len, loc);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     // hits of the last tile
     {
-        const uint32_t n_staged = min(s_nhits, uint32_t(HCAP));
-        if (tid == 0 && n_staged) s_hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
-        __syncthreads();
-        if (n_staged) flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, s_hbase);
+        const uint32_t n_staged = min(*s_nhits, uint32_t(HCAP));
+        if (n_staged) {
+            unsigned long long hbase = 0;
+            if (lane == 0) hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
+            hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
+            flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, hbase, lane);
+        }
     }
 
-    // ---- per-CTA statistics
+    // ---- per-warp statistics
     uint64_t v1 = loc.n_rec, v2 = loc.n_multi, v3 = loc.n_checks, v6 = loc.n_generic;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -1273,7 +1299,9 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
     a.flags = t->filter_flags;
-    int grid = int(std::min<uint32_t>(a.n_tiles, uint32_t(g_grid_cap)));
+    static const char *stop_env = getenv("SVJG_STOP_AFTER");   // profiling hook: run the phases up to A/B/C/D only
+    if (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'D') a.flags |= uint32_t(stop_env[0] - 'A' + 1) << 8;
+    int grid = int(std::min<uint32_t>((a.n_tiles + WARPS - 1) / WARPS, uint32_t(g_grid_cap)));
     filter_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
     SVJG_CUDA(cudaGetLastError());
     return SVJG_OK;
