@@ -1,41 +1,40 @@
-// Kernels 1-3 of the hot path, fused: GAF ingest (newline scan + field split),
-// alignment -> allele resolution through the device link hash, and the per-SV
-// counter / hit-tuple reduction.  One pass over the GAF bytes.
+// Kernels 1-3 of the hot path: GAF ingest (newline scan + field split), alignment
+// -> allele resolution through the device link hash, and the per-SV counter /
+// hit-tuple reduction.
 //
 // Reference semantics restated (filter-alignments.py): per-line loop :123-166,
 // read_gaf_line :184-198, extract_nodes :351-373, get_aln_links :200-219,
 // reverse_link :221-225, check_bkpt_overlap :258-273, get_node_len :343-349.
 //
-// Layout: every WARP is an independent worker with its own slice of shared memory
-// (no block-wide barrier anywhere).  A warp walks 4 KiB tiles of the byte buffer;
-// a tile plus 2 KiB of look-ahead (and the 32 bytes in front of it) is staged into
-// the warp's window by one TMA bulk copy (cp.async.bulk + mbarrier).  Per tile the
-// 32 lanes are re-assigned at the granularity that keeps them busy:
-//   A  byte-parallel: every lane classifies 32 bytes with SWAR compares; ballots
-//      turn the newline flags into the ordered list of line boundaries;
-//   B  line-parallel: one lane per line finds the 12 columns (tab bitmaps of fixed
-//      spans, so lanes stay converged), validates the integer columns, walks the
-//      path column and, for paths with >= 2 nodes, appends one record per node
-//      to the token list (slots handed out by a warp scan);
-//   C  token-parallel: one lane per path node hashes the name (4 bytes a step),
-//      parses chrom:start-end / looks the alt node up, and stores the record;
-//   D  line-parallel over multi-node lines: Tlen/Ts/Te, running sums of the node
-//      lengths, the breakpoint-overlap verdict of every link; token-parallel
-//      check that no node name can occur inside an earlier one;
-//   E  link-parallel: forward and reverse key probes of the link hash; hits are
-//      staged in shared memory and written out (one cursor atomic per warp and
-//      tile, warp-aggregated counter atomics) while the next tile's bytes fly in.
-// Anything that is not of the plain shape (odd integers, odd node names, a name
-// that could be a substring of an earlier one, lines longer than the window, ...)
-// is handed to the exact per-line routines parse_fields() / general(), which
-// follow the reference's string semantics literally.
+// The work is a chain of kernels, each parallel over the unit that keeps all lanes
+// busy and each at full occupancy; compacted lists in device scratch memory link them:
+//   scan_parse  every WARP is an independent worker with its own shared-memory window
+//               (no block barrier).  It walks 4 KiB tiles of the byte buffer; a tile
+//               plus 1 KiB of look-ahead is staged by one TMA bulk copy.
+//               A  byte-parallel: every lane classifies 32 bytes with SWAR compares;
+//                  ballots turn the newline flags into the ordered list of line ends;
+//               B  line-parallel: one lane per line finds the 12 columns (tab bitmaps
+//                  of fixed spans, so lanes stay converged), validates the integer
+//                  columns and walks the path column.  Lines with >= 2 path nodes go
+//                  to the multi-node list with one token record per node; lines that
+//                  are not of the plain shape go to the "exact" list.
+//   token       one thread per path node: name hash (4 bytes a step), chrom:start-end
+//               parse or alt-node lookup.
+//   line        one thread per multi-node line: Tlen/Ts/Te, sums of the node lengths,
+//               the breakpoint-overlap verdict of every link.
+//   clash       one thread per node: could this name occur inside an earlier one of
+//               the same path (first-occurrence rules of :206 and :269-271)?
+//   link        one thread per link: forward and reverse key probes of the link hash,
+//               warp-aggregated counter atomics and hit tuples.
+//   exact       one thread per irregular line: parse_fields() / general(), which follow
+//               the reference's string semantics literally (odd integers, odd node
+//               names, names that could be substrings of earlier ones, long lines ...).
 // A line belongs to the tile its first byte is in.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdlib>
-#include <type_traits>
 
 #include "svjg_internal.h"
 
@@ -45,36 +44,25 @@ using namespace svjg;
 namespace {
 
 constexpr int TILE = 4096;                     // bytes a warp owns per step
-constexpr int LOOKAHEAD = 2048;                // staged behind the tile so that lines starting in it are whole
+constexpr int LOOKAHEAD = 1024;                // staged behind the tile so that lines starting in it are whole
 constexpr int HEAD = 32;                       // staged in front of it (the newline that starts the first line)
-constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 6176 = 32 * 193
+constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 5152 = 32 * 161
 constexpr int WARPS = 4;                       // per block; warps never synchronise with each other
 constexpr int THREADS = WARPS * 32;
 constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunks
 constexpr int HEAD_SPAN = 96;                  // bytes searched for the tabs of columns 1-5 on the fast route
 constexpr int TAIL_SPAN = 96;                  // bytes searched for the tabs of columns 7-12
 constexpr int SPARE = 176;                     // readable bytes behind the window for those fixed-span reads
-constexpr int NLCAP = 400;                     // newlines per window (more => some line is shorter than 16 bytes)
-constexpr int MCAP = 64;                       // multi-node lines per tile on the token-parallel route
-constexpr int TCAP = 192;                      // path nodes per tile on the token-parallel route
-constexpr int HCAP = 128;                      // hits staged per tile before the flush
+constexpr int NLCAP = 336;                     // newlines per window (more => some line is shorter than 16 bytes)
 static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit");
 
-// shared memory map of ONE warp (bytes)
+// shared memory map of ONE warp of scan_parse (bytes)
 constexpr int OFF_WIN = 0;
 constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline positions, ascending  u16[NLCAP]
-constexpr int OFF_ML = (OFF_NL + NLCAP * 2 + 15) & ~15;     // MLine[MCAP]
-constexpr int OFF_TH = (OFF_ML + MCAP * 16 + 15) & ~15;     // token hash   u64[TCAP]
-constexpr int OFF_TLEN = OFF_TH + TCAP * 8;                 // node length  i32[TCAP]
-constexpr int OFF_TS = OFF_TLEN + TCAP * 4;                 // start value  u32[TCAP]
-constexpr int OFF_TB = OFF_TS + TCAP * 4;                   // token begin  u16[TCAP]
-constexpr int OFF_TL = OFF_TB + TCAP * 2;                   // token length u16[TCAP]
-constexpr int OFF_TLINE = OFF_TL + TCAP * 2;                // MLine index  u16[TCAP]
-constexpr int OFF_TF = OFF_TLINE + TCAP * 2;                // flags        u8[TCAP]
-constexpr int OFF_HSV = (OFF_TF + TCAP + 15) & ~15;         // staged hits: 2*sv + allele  u32[HCAP]
-constexpr int OFF_HML = OFF_HSV + HCAP * 4;                 //              MLine index    u16[HCAP]
-constexpr int WARP_SMEM = (OFF_HML + HCAP * 2 + 127) & ~127;
+constexpr int WARP_SMEM = (OFF_NL + NLCAP * 2 + 127) & ~127;
 constexpr int SMEM_BYTES = WARP_SMEM * WARPS;
+
+constexpr int FLAT_THREADS = 256;              // block size of the flat (grid-stride) kernels
 
 constexpr uint32_t FLAG_EXACT_CHECKS = SVJG_FLAG_EXACT_CHECKS;   // probe links whose overlap test fails too
 constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through general()
@@ -89,16 +77,30 @@ constexpr uint32_t TF_OK = 8;       // overlap verdict of the link (previous nod
 constexpr uint32_t LF_GENERAL = 1;  // must go through general()
 constexpr uint32_t LF_HAS_NL = 2;   // the line ends in a newline (it counts in the hit's length)
 constexpr uint32_t LF_SKIP = 4;     // reported as an error: no links
+constexpr uint32_t NO_LINE = 0xFFFFFFFFu;
 
-struct MLine {
-    uint16_t s, e;        // window offsets of the line's first byte and of its end (newline or end of data)
-    uint16_t p6;          // tab that ends the path column
-    uint16_t tok0, ntok;  // tokens [tok0, tok0 + ntok); ntok == 0 marks a slot that was given up
-    uint16_t flags;
-    uint16_t ps;          // first byte of the path column
-    uint16_t pad;
+// a multi-node line on the token-parallel route (byte offsets into the shard)
+struct GLine {
+    uint32_t s, e;        // first byte of the line, its end (newline or end of data)
+    uint32_t ps, pe;      // path column [ps, pe); pe is the tab that ends it
+    uint32_t tok0, ntok;  // tokens [tok0, tok0 + ntok); ntok == 0 marks a slot that was given up
+    uint32_t flags;
+    uint32_t pad;
 };
-static_assert(sizeof(MLine) == 16, "MLine is 16 bytes");
+static_assert(sizeof(GLine) == 32, "GLine is one sector");
+
+// device scratch of one svjg_filter_device() call
+struct Scratch {
+    uint32_t *cnt;        // [0] multi-node lines, [1] tokens, [2] exact-route lines
+    GLine *ml;
+    uint32_t *tk_b, *tk_line, *tk_sval;
+    uint16_t *tk_l;
+    uint64_t *tk_hash;
+    int32_t *tk_len;
+    uint8_t *tk_flags;
+    uint32_t *exact;      // line start offsets
+    uint32_t cap_ml, cap_tok, cap_exact;
+};
 
 struct FilterArgs {
     const uint8_t *gaf;
@@ -112,6 +114,7 @@ struct FilterArgs {
     unsigned long long *stats;   // svjg_filter_stats as 8 x u64
     uint32_t n_tiles;
     uint32_t flags;
+    Scratch sc;
 };
 
 struct Local {
@@ -119,11 +122,6 @@ struct Local {
     uint64_t n_checks = 0;
 };
 
-struct SmemSrc {
-    typedef uint32_t pos_t;
-    const uint8_t *p;
-    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { return p[i]; }
-};
 struct GmemSrc {
     typedef uint64_t pos_t;
     const uint8_t *p;
@@ -134,6 +132,14 @@ __device__ __forceinline__ bool py_space(uint32_t c) {
     return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
 }
 __device__ __forceinline__ bool is_delim(uint32_t c) { return (c | 2u) == '>'; }   // '<' = 0x3C, '>' = 0x3E
+
+// aligned 4-byte word of the shard at byte offset al (al % 4 == 0); bytes past the end read as zero
+__device__ __forceinline__ uint32_t gaf_word(const FilterArgs &a, uint64_t al) {
+    if (al + 4 <= a.n) return __ldg(reinterpret_cast<const uint32_t *>(a.gaf + al));
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < 4 && al + k < a.n; ++k) w |= uint32_t(__ldg(a.gaf + al + k)) << (8 * k);
+    return w;
+}
 
 // ---- SWAR byte classes: the answer is bit 7 of each byte, exact for all 256 byte values.
 // (w & 0x7F..) ^ C is zero in its low 7 bits iff the byte's low 7 bits equal C; adding 0x7F carries
@@ -158,21 +164,11 @@ __device__ __forceinline__ uint32_t lop_or_and(uint32_t t, uint32_t w, uint32_t 
 __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c4) {                    // c4: four copies of a byte < 0x80
     return lop_nor_and(lop_and_xor(w, SVJG_M7, c4) + SVJG_M7, w, SVJG_H8);
 }
-__device__ __forceinline__ uint32_t digit_bytes(uint32_t w) {                              // '0'..'9'
-    return lop_nor_and(lop_and_xor(w, SVJG_M7, 0x30303030u) + 0x76767676u, w, SVJG_H8);
-}
-__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t w) {
+__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t w) {                           // not '0'..'9'
     return lop_or_and(lop_and_xor(w, SVJG_M7, 0x30303030u) + 0x76767676u, w, SVJG_H8);
 }
 __device__ __forceinline__ uint32_t delim_bytes(uint32_t w) {                              // '<' 0x3C or '>' 0x3E
     return lop_nor_and(lop_and_xor(w, 0x7D7D7D7Du, 0x3C3C3C3Cu) + SVJG_M7, w, SVJG_H8);
-}
-// flags of bytes [lo, hi) of a word (byte indices; any ints)
-__device__ __forceinline__ uint32_t byte_range(int lo, int hi) {
-    uint32_t m = 0xFFFFFFFFu;
-    if (lo > 0) m = lo >= 4 ? 0u : (m << (8 * lo));
-    if (hi < 4) m = hi <= 0 ? 0u : (m & (0xFFFFFFFFu >> (8 * (4 - hi))));
-    return m;
 }
 // 16 class flags of a 16-byte chunk, bit i = byte i.  dp4a gathers the four bit-7 flags of a
 // word: sum(0x80 * weight) = bits << 7.
@@ -194,6 +190,23 @@ struct IsTab {
 __device__ __noinline__ void report(const FilterArgs &a, uint32_t code, uint64_t line_off) {
     atomicCAS(a.stats + 4, 0ull, (unsigned long long)code);
     atomicMin(a.stats + 5, (unsigned long long)(a.base + line_off));
+}
+
+__device__ __forceinline__ void add_stats(const FilterArgs &a, const Local &loc) {
+    uint64_t v1 = loc.n_rec, v2 = loc.n_multi, v3 = loc.n_checks, v6 = loc.n_generic;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, d);
+        v2 += __shfl_xor_sync(0xFFFFFFFFu, v2, d);
+        v3 += __shfl_xor_sync(0xFFFFFFFFu, v3, d);
+        v6 += __shfl_xor_sync(0xFFFFFFFFu, v6, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (v1) atomicAdd(a.stats + 1, (unsigned long long)v1);
+        if (v2) atomicAdd(a.stats + 2, (unsigned long long)v2);
+        if (v3) atomicAdd(a.stats + 3, (unsigned long long)v3);
+        if (v6) atomicAdd(a.stats + 6, (unsigned long long)v6);
+    }
 }
 
 // Python int(): optional surrounding whitespace, optional sign, decimal digits.
@@ -389,30 +402,23 @@ struct Rec {
         return tok_value(h, t.l);
     }
 
-    // name bytes against the table's copy (4-byte aligned, zero padded).  In shared memory the
-    // compare is word-wide and never exits early, so all table loads are in flight together.
+    // name bytes against the table's copy (4-byte aligned, zero padded): word-wide and without an
+    // early exit, so all loads are in flight together
     __device__ bool names_match(uint32_t off, const Tok &t) const {
-        if constexpr (std::is_same<Src, SmemSrc>::value) {
-            const uint32_t *q = reinterpret_cast<const uint32_t *>(a.tb.blob + off);
-            const uint32_t sh = (uint32_t(t.b) & 3u) * 8u;
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(src.p + (uint32_t(t.b) & ~3u));
-            const uint32_t nw = (t.l + 3u) >> 2;
-            uint32_t cur = wp[0], diff = 0;
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(a.tb.blob + off);
+        const uint32_t nw = (t.l + 3u) >> 2;
+        const uint64_t al = uint64_t(t.b) & ~3ull;
+        const uint32_t sh = (uint32_t(t.b) & 3u) * 8u;
+        uint32_t cur = gaf_word(a, al), diff = 0;
 #pragma unroll 4
-            for (uint32_t k = 0; k < nw; ++k) {
-                uint32_t nxt = wp[k + 1];
-                uint32_t w = __funnelshift_r(cur, nxt, sh);
-                cur = nxt;
-                if (k == nw - 1 && (t.l & 3u)) w &= (1u << (8u * (t.l & 3u))) - 1u;
-                diff |= w ^ __ldg(q + k);
-            }
-            return diff == 0;
-        } else {
-            const uint8_t *q = a.tb.blob + off;
-            for (uint32_t i = 0; i < t.l; ++i)
-                if (__ldg(q + i) != src[t.b + i]) return false;
-            return true;
+        for (uint32_t k = 0; k < nw; ++k) {
+            const uint32_t nxt = gaf_word(a, al + 4ull * (k + 1));
+            uint32_t w = __funnelshift_r(cur, nxt, sh);
+            cur = nxt;
+            if (k == nw - 1 && (t.l & 3u)) w &= (1u << (8u * (t.l & 3u))) - 1u;
+            diff |= w ^ __ldg(q + k);
         }
+        return diff == 0;
     }
 
     __device__ bool probe(uint64_t hl, uint32_t sl, const Tok &tl_, uint64_t hr, uint32_t sr, const Tok &tr_,
@@ -455,22 +461,21 @@ struct Rec {
         }
     }
 
-    // Hits of the token-parallel route are staged in shared memory (flushed once per tile with one
-    // cursor atomic for the whole block); everything else appends to the global arrays directly.
-    uint32_t *stage_sv = nullptr;
-    uint16_t *stage_ml = nullptr;
-    uint32_t *stage_n = nullptr;
-    uint32_t stage_line = 0;
+    // link_kernel stages its hits in shared memory and writes them out with one cursor atomic per
+    // block and round; everything else appends to the global arrays directly.
+    uint32_t *stage_sv = nullptr, *stage_off = nullptr, *stage_len = nullptr, *stage_n = nullptr;
+    uint32_t stage_cap = 0;
 
     __device__ void emit(uint32_t sv2) {
-        cg::coalesced_group active = cg::coalesced_threads();
         if (stage_sv) {
+            cg::coalesced_group active = cg::coalesced_threads();
             uint32_t base = 0;
             if (active.thread_rank() == 0) base = atomicAdd(stage_n, active.size());
             base = active.shfl(base, 0) + active.thread_rank();
-            if (base < HCAP) {
+            if (base < stage_cap) {
                 stage_sv[base] = sv2;
-                stage_ml[base] = uint16_t(stage_line);
+                stage_off[base] = line_off;
+                stage_len[base] = line_len;
                 return;
             }
         }
@@ -654,43 +659,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-// the exact per-line route for a line that is inside the window
-__device__ __noinline__ void slow_line(const FilterArgs &a, const uint8_t *win, uint32_t s, uint32_t e, uint32_t off,
-                                       uint32_t len, Local &loc) {
-    Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
-    uint32_t ntok = rec.parse_fields(s, e);
-    if (!rec.err && ntok >= 2) {
-        if (ntok != COMMA_PATH) loc.n_multi++;
-        rec.general();
-    }
-    if (rec.err) report(a, rec.err, off);
-}
-
-// a line that runs past the staged window: exact route on global memory
-__device__ __noinline__ void long_line(const FilterArgs &a, uint64_t from, uint32_t off, Local &loc) {
-    uint64_t e = from;
-    while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
-    uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
-    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-    uint32_t ntok = rec.parse_fields(uint64_t(off), e);
-    if (!rec.err && ntok >= 2) {
-        if (ntok != COMMA_PATH) loc.n_multi++;
-        rec.general();
-    }
-    if (rec.err) report(a, rec.err, off);
-}
-
-// general() for a line whose columns are known to be valid (path [ps, pe), coordinates after pe)
-__device__ __noinline__ void general_line(const FilterArgs &a, const uint8_t *win, uint32_t ps, uint32_t pe, uint32_t e,
-                                          uint32_t off, uint32_t len, Local &loc) {
-    Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
-    rec.ps = ps;
-    rec.pe = pe;
-    rec.reparse_coords(e);
-    rec.general();
-    if (rec.err) report(a, rec.err, off);
-}
-
 __device__ __forceinline__ uint32_t lds32(const uint8_t *win, uint32_t a) { return *reinterpret_cast<const uint32_t *>(win + a); }
 
 // number of non-digit bytes in window bytes [lo, hi), hi > lo
@@ -704,38 +672,6 @@ __device__ __forceinline__ uint32_t count_nondigits(const uint8_t *win, uint32_t
     return n + __popc(nondigit_bytes(lds32(win, a1)) & him);
 }
 
-// any ',' in window bytes [lo, hi), hi > lo
-__device__ __forceinline__ bool has_comma(const uint8_t *win, uint32_t lo, uint32_t hi) {
-    const uint32_t a0 = lo & ~3u, a1 = (hi - 1u) & ~3u;
-    const uint32_t lom = 0xFFFFFFFFu << (8u * (lo & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((hi - 1u) & 3u)));
-    uint32_t f = eq_bytes(lds32(win, a0), 0x2C2C2C2Cu) & lom;
-    if (a0 == a1) return (f & him) != 0;
-    for (uint32_t a = a0 + 4; a < a1; a += 4) f |= eq_bytes(lds32(win, a), 0x2C2C2C2Cu);
-    return (f | (eq_bytes(lds32(win, a1), 0x2C2C2C2Cu) & him)) != 0;
-}
-
-// Writes a warp's staged hits: coalesced tuple stores and warp-aggregated counter atomics
-// (one per distinct SV allele among the 32 hits the warp holds at a time).
-__device__ __forceinline__ void flush_hits(const FilterArgs &a, const uint32_t *h_sv, const uint16_t *h_ml, const MLine *ml,
-                                           uint32_t n, uint64_t tile_start, unsigned long long base, int lane) {
-    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool act = i < n;
-        const uint32_t sv2 = act ? h_sv[i] : 0xFFFFFFFFu;
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, sv2);
-        if (act) {
-            if (lane == __ffs(peers) - 1) atomicAdd(a.counts + sv2, uint32_t(__popc(peers)));
-            const MLine L = ml[h_ml[i]];
-            const unsigned long long k = base + i;
-            if (k < a.hit_cap) {
-                a.hit_sv2[k] = sv2;
-                a.hit_off[k] = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
-                a.hit_len[k] = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -745,39 +681,24 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(THREADS, 4) filter_kernel(const FilterArgs a) {
+// ===========================================================================
+// scan_parse: newline scan, column split, validation, path walk
+// ===========================================================================
+__global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     __shared__ __align__(8) uint64_t mbars[WARPS];
-    __shared__ uint32_t s_hits[WARPS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint8_t *smem = smem_all + warp * WARP_SMEM;
-    uint8_t *win = smem + OFF_WIN;
-    uint16_t *nl = reinterpret_cast<uint16_t *>(smem + OFF_NL);
-    MLine *ml = reinterpret_cast<MLine *>(smem + OFF_ML);
-    uint64_t *t_hash = reinterpret_cast<uint64_t *>(smem + OFF_TH);
-    int32_t *t_len = reinterpret_cast<int32_t *>(smem + OFF_TLEN);
-    uint32_t *t_sval = reinterpret_cast<uint32_t *>(smem + OFF_TS);
-    uint16_t *t_b = reinterpret_cast<uint16_t *>(smem + OFF_TB);
-    uint16_t *t_l = reinterpret_cast<uint16_t *>(smem + OFF_TL);
-    uint16_t *t_line = reinterpret_cast<uint16_t *>(smem + OFF_TLINE);
-    uint8_t *t_flags = smem + OFF_TF;
-    uint32_t *h_sv = reinterpret_cast<uint32_t *>(smem + OFF_HSV);
-    uint16_t *h_ml = reinterpret_cast<uint16_t *>(smem + OFF_HML);
+    uint8_t *win = smem_all + warp * WARP_SMEM + OFF_WIN;
+    uint16_t *nl = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_NL);
     uint64_t *mbar = &mbars[warp];
-    uint32_t *s_nhits = &s_hits[warp];
 
-    if (lane == 0) {
-        mbar_init(mbar, 1);
-        *s_nhits = 0;
-    }
+    if (lane == 0) mbar_init(mbar, 1);
     __syncwarp();
     uint32_t phase = 0;
     Local loc;
-    const bool all_links = a.flags & FLAG_EXACT_CHECKS;
-    const uint32_t stop_after = (a.flags >> 8) & 7u;     // profiling hook (SVJG_STOP_AFTER): 1 = A, 2 = B, 3 = C, 4 = D
-    uint64_t prev_tile_start = 0;
+    const bool stop_after_scan = ((a.flags >> 8) & 7u) == 1u;     // profiling hook (SVJG_STOP_AFTER=A)
     const uint32_t n_workers = gridDim.x * WARPS;
 
     for (uint32_t tile = blockIdx.x * WARPS + warp; tile < a.n_tiles; tile += n_workers) {
@@ -790,25 +711,13 @@ __global__ void __launch_bounds__(THREADS, 4) filter_kernel(const FilterArgs a) 
         const uint32_t nbytes = uint32_t(g1 - g0);
         const uint32_t bulk = nbytes & ~15u;
         const uint32_t valid_end = dst0 + nbytes;
+        const uint32_t wbase = uint32_t(tile_start) - HEAD;            // shard offset = wbase + window offset
 
-        // the previous tile's hits go out while this tile's bytes come in
-        const uint32_t n_staged = min(*s_nhits, uint32_t(HCAP));
-        unsigned long long hbase = 0;
-        if (lane == 0) {
-            if (bulk) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(mbar, bulk);
-                bulk_g2s(win + dst0, a.gaf + g0, bulk, mbar);
-            }
-            if (n_staged) hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
+        if (lane == 0 && bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(mbar, bulk);
+            bulk_g2s(win + dst0, a.gaf + g0, bulk, mbar);
         }
-        if (n_staged) {
-            hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
-            flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, hbase, lane);
-        }
-        prev_tile_start = tile_start;
-        __syncwarp();
-        if (lane == 0) *s_nhits = 0;
         for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
         if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;               // "newline" in front of byte 0 of the file
         for (uint32_t i = valid_end + lane; i < WIN + SPARE; i += 32) win[i] = 0;
@@ -858,185 +767,183 @@ __global__ void __launch_bounds__(THREADS, 4) filter_kernel(const FilterArgs a) 
             n_nl += total;
         }
         __syncwarp();
+        if (stop_after_scan) continue;
 
-        uint32_t n_ml = 0, n_tok = 0;
-        if (stop_after == 1) continue;
         if (n_nl > NLCAP) {
-            // that many lines in 6 KiB: some line is shorter than 16 bytes and cannot hold 12 columns
+            // that many lines in 5 KiB: some line is shorter than 16 bytes and cannot hold 12 columns
             if (lane == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
-        } else {
-            // ---- phase B: one lane per line
-            bool route_full = false;
-            for (uint32_t k0 = 0; k0 < n_own; k0 += 32) {
-                const uint32_t k = k0 + lane;
-                uint32_t want = 0;                 // path nodes of a line that asks for the token-parallel route
-                uint32_t s = 0, e = 0, ps = 0, pe = 0, off = 0, len = 0;
-                bool has_nl = false;
-                if (k < n_own) {
-                    s = uint32_t(nl[k]) + 1u;
-                    off = uint32_t(tile_start) + (s - HEAD);
-                    loc.n_rec++;
-                    bool in_win = true;
-                    if (k + 1 < n_nl) {
-                        e = nl[k + 1];
-                        has_nl = true;
-                    } else if (at_eof) {
-                        e = valid_end;
-                    } else {
-                        in_win = false;
-                        long_line(a, tile_start + TILE + LOOKAHEAD, off, loc);
-                    }
-                    if (in_win) {
-                        len = e - s + (has_nl ? 1u : 0u);
-                        // columns 1-5: tab bitmap of the first HEAD_SPAN bytes (fixed trip count: lanes stay together)
-                        bool plain = e > s && !py_space(win[e - 1]);
-                        uint32_t p1, p2, p3, p4, p5;
-                        {
-                            const uint32_t base = s & ~15u;
-                            uint32_t tm[HEAD_SPAN / 32];
+            __syncwarp();
+            continue;
+        }
+        // ---- phase B: one lane per line
+        for (uint32_t k0 = 0; k0 < n_own; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint32_t want = 0;                 // path nodes of a plain line with >= 2 of them
+            bool exact = false;                // the line must take the exact route
+            uint32_t s = 0, e = 0, ps = 0, pe = 0;
+            bool has_nl = false;
+            if (k < n_own) {
+                s = uint32_t(nl[k]) + 1u;
+                loc.n_rec++;
+                if (k + 1 < n_nl) {
+                    e = nl[k + 1];
+                    has_nl = true;
+                } else if (at_eof) {
+                    e = valid_end;
+                } else {
+                    exact = true;              // runs past the window
+                }
+                if (!exact) {
+                    // columns 1-5: tab bitmap of the first HEAD_SPAN bytes (fixed trip count: lanes stay together)
+                    bool plain = e > s && !py_space(win[e - 1]);
+                    uint32_t p1, p2, p3, p4, p5;
+                    {
+                        const uint32_t base = s & ~15u;
+                        uint32_t tm[HEAD_SPAN / 32];
 #pragma unroll
-                            for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                                const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
-                                const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
-                                tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                            }
-                            tm[0] &= 0xFFFFFFFFu << (s - base);
-                            const uint32_t rel_e = e - base;
-#pragma unroll
-                            for (int j = 0; j < HEAD_SPAN / 32; ++j)
-                                if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
-                            // the first 5 tab positions (relative to base), one byte each, newest in the low byte
-                            uint32_t r0 = 0, r1 = 0, nt = 0;
-#pragma unroll
-                            for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                                uint32_t m = tm[j];
-                                while (m && nt < 5) {
-                                    const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                                    m &= m - 1;
-                                    r1 = __funnelshift_l(r0, r1, 8);
-                                    r0 = (r0 << 8) | pos;
-                                    ++nt;
-                                }
-                            }
-                            plain &= nt == 5;
-                            p1 = base + (r1 & 255u), p2 = base + (r0 >> 24), p3 = base + ((r0 >> 16) & 255u);
-                            p4 = base + ((r0 >> 8) & 255u), p5 = base + (r0 & 255u);
+                        for (int j = 0; j < HEAD_SPAN / 32; ++j) {
+                            const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
+                            const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
+                            tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
                         }
-                        // column 6, the path [ps, pe): walk to its tab; count token starts (a non-delimiter byte
-                        // right after a delimiter) and look for ',' on the way
-                        ps = p5 + 1;
-                        pe = e;
-                        uint32_t ntok = 0, comma = 0;
-                        if (plain) {
-                            uint32_t carry = 0;   // delimiter flag of the byte in front of the word, at bit 7
-                            uint32_t keep = 0xFFFFFFFFu << (8u * (ps & 3u));
-                            for (uint32_t w0 = ps & ~3u; w0 < e; w0 += 4) {
-                                const uint32_t w = lds32(win, w0);
-                                const uint32_t tb = eq_bytes(w, 0x09090909u) & keep;
-                                const uint32_t d = delim_bytes(w);
-                                if (tb) {
-                                    const uint32_t j = uint32_t(__ffs(tb) - 1) >> 3;          // byte of the tab in this word
-                                    pe = w0 + j;
-                                    keep &= j ? (0xFFFFFFFFu >> (8u * (4u - j))) : 0u;
-                                }
-                                ntok += __popc(((d << 8) | carry) & ~d & SVJG_H8 & keep);
-                                comma |= eq_bytes(w, 0x2C2C2C2Cu) & keep;
-                                if (tb) break;
-                                carry = d >> 24;
-                                keep = 0xFFFFFFFFu;
-                            }
-                            plain = pe < e && pe > ps;
-                        }
-                        // columns 7-12: tab bitmap of the TAIL_SPAN bytes around the end of the path
-                        if (plain) {
-                            const uint32_t p6 = pe;
-                            const uint32_t base = p6 & ~15u;
-                            uint32_t tm[TAIL_SPAN / 32];
+                        tm[0] &= 0xFFFFFFFFu << (s - base);
+                        const uint32_t rel_e = e - base;
 #pragma unroll
-                            for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                                const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
-                                const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
-                                tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                            }
-                            tm[0] &= 0xFFFFFFFEu << (p6 - base);                               // tabs after p6
-                            const uint32_t rel_e = e - base;
+                        for (int j = 0; j < HEAD_SPAN / 32; ++j)
+                            if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
+                        // the first 5 tab positions (relative to base), one byte each, newest in the low byte
+                        uint32_t r0 = 0, r1 = 0, nt = 0;
 #pragma unroll
-                            for (int j = 0; j < TAIL_SPAN / 32; ++j)
-                                if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
-                            uint32_t r0 = 0, r1 = 0, nt = 0;
-#pragma unroll
-                            for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                                uint32_t m = tm[j];
-                                while (m && nt < 6) {
-                                    const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                                    m &= m - 1;
-                                    r1 = __funnelshift_l(r0, r1, 8);
-                                    r0 = (r0 << 8) | pos;
-                                    ++nt;
-                                }
-                            }
-                            if (nt == 5 && rel_e <= TAIL_SPAN) {                               // no tab after column 12
+                        for (int j = 0; j < HEAD_SPAN / 32; ++j) {
+                            uint32_t m = tm[j];
+                            while (m && nt < 5) {
+                                const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                                m &= m - 1;
                                 r1 = __funnelshift_l(r0, r1, 8);
-                                r0 = (r0 << 8) | rel_e;
+                                r0 = (r0 << 8) | pos;
                                 ++nt;
                             }
-                            plain = nt == 6;
-                            const uint32_t p7 = base + ((r1 >> 8) & 255u), p8 = base + (r1 & 255u), p9 = base + (r0 >> 24),
-                                           p10 = base + ((r0 >> 16) & 255u), p11 = base + ((r0 >> 8) & 255u),
-                                           p12 = base + (r0 & 255u);
-                            if (plain) {
-                                // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
-                                const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) &
-                                                  (p8 - p7 > 1u) & (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) &
-                                                  (p12 - p11 > 1u);
-                                plain = w_ok && win[p10 + 1] != '0';
-                                if (plain)
-                                    plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
+                        }
+                        plain &= nt == 5;
+                        p1 = base + (r1 & 255u), p2 = base + (r0 >> 24), p3 = base + ((r0 >> 16) & 255u);
+                        p4 = base + ((r0 >> 8) & 255u), p5 = base + (r0 & 255u);
+                    }
+                    // column 6, the path [ps, pe): walk to its tab; count token starts (a non-delimiter byte
+                    // right after a delimiter) and look for ',' on the way
+                    ps = p5 + 1;
+                    pe = e;
+                    uint32_t ntok = 0, comma = 0;
+                    if (plain) {
+                        uint32_t carry = 0;   // delimiter flag of the byte in front of the word, at bit 7
+                        uint32_t keep = 0xFFFFFFFFu << (8u * (ps & 3u));
+                        for (uint32_t w0 = ps & ~3u; w0 < e; w0 += 4) {
+                            const uint32_t w = lds32(win, w0);
+                            const uint32_t tb = eq_bytes(w, 0x09090909u) & keep;
+                            const uint32_t d = delim_bytes(w);
+                            if (tb) {
+                                const uint32_t j = uint32_t(__ffs(tb) - 1) >> 3;          // byte of the tab in this word
+                                pe = w0 + j;
+                                keep &= j ? (0xFFFFFFFFu >> (8u * (4u - j))) : 0u;
+                            }
+                            ntok += __popc(((d << 8) | carry) & ~d & SVJG_H8 & keep);
+                            comma |= eq_bytes(w, 0x2C2C2C2Cu) & keep;
+                            if (tb) break;
+                            carry = d >> 24;
+                            keep = 0xFFFFFFFFu;
+                        }
+                        plain = pe < e && pe > ps;
+                    }
+                    // columns 7-12: tab bitmap of the TAIL_SPAN bytes around the end of the path
+                    if (plain) {
+                        const uint32_t p6 = pe;
+                        const uint32_t base = p6 & ~15u;
+                        uint32_t tm[TAIL_SPAN / 32];
+#pragma unroll
+                        for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                            const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
+                            const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
+                            tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
+                        }
+                        tm[0] &= 0xFFFFFFFEu << (p6 - base);                               // tabs after p6
+                        const uint32_t rel_e = e - base;
+#pragma unroll
+                        for (int j = 0; j < TAIL_SPAN / 32; ++j)
+                            if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
+                        uint32_t r0 = 0, r1 = 0, nt = 0;
+#pragma unroll
+                        for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                            uint32_t m = tm[j];
+                            while (m && nt < 6) {
+                                const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                                m &= m - 1;
+                                r1 = __funnelshift_l(r0, r1, 8);
+                                r0 = (r0 << 8) | pos;
+                                ++nt;
                             }
                         }
-                        if (!plain) {
-                            slow_line(a, win, s, e, off, len, loc);
-                        } else if (!is_delim(win[ps])) {
-                            // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
-                            if (comma) slow_line(a, win, s, e, off, len, loc);
-                        } else if (ntok >= 2) {                                                // :133
-                            loc.n_multi++;
-                            if ((a.flags & FLAG_FORCE_GENERAL) || ntok > TCAP) general_line(a, win, ps, pe, e, off, len, loc);
-                            else want = ntok;
+                        if (nt == 5 && rel_e <= TAIL_SPAN) {                               // no tab after column 12
+                            r1 = __funnelshift_l(r0, r1, 8);
+                            r0 = (r0 << 8) | rel_e;
+                            ++nt;
+                        }
+                        plain = nt == 6;
+                        const uint32_t p7 = base + ((r1 >> 8) & 255u), p8 = base + (r1 & 255u), p9 = base + (r0 >> 24),
+                                       p10 = base + ((r0 >> 16) & 255u), p11 = base + ((r0 >> 8) & 255u),
+                                       p12 = base + (r0 & 255u);
+                        if (plain) {
+                            // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
+                            const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) &
+                                              (p8 - p7 > 1u) & (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) &
+                                              (p12 - p11 > 1u);
+                            plain = w_ok && win[p10 + 1] != '0';
+                            if (plain)
+                                plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
                         }
                     }
+                    if (!plain) {
+                        exact = true;
+                    } else if (!is_delim(win[ps])) {
+                        // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
+                        exact = comma != 0;
+                    } else if (ntok >= 2) {                                                // :133
+                        if (a.flags & FLAG_FORCE_GENERAL) exact = true;
+                        else want = ntok;
+                    }
                 }
-                __syncwarp();
-                // slots on the token-parallel route for the lanes that want them (in lane order, no holes)
-                const uint32_t wb = __ballot_sync(0xFFFFFFFFu, want != 0);
-                if (!wb) continue;
+            }
+            __syncwarp();
+            // slots in the multi-node list / token list for the lanes that want them: one warp scan and
+            // one pair of cursor atomics per pass
+            const uint32_t wb = __ballot_sync(0xFFFFFFFFu, want != 0);
+            if (wb) {
                 const uint32_t incl = warp_incl_scan(want, lane);
-                const uint32_t t0 = n_tok + incl - want;
-                const uint32_t li = n_ml + __popc(wb & lt_mask);
-                const bool fits = want && !route_full && t0 + want <= TCAP && li < MCAP;
-                const uint32_t nofit = __ballot_sync(0xFFFFFFFFu, want && !fits);
-                if (nofit) {                       // everything from the first lane without room takes the exact route
-                    const int first = __ffs(nofit) - 1;
-                    n_tok = __shfl_sync(0xFFFFFFFFu, t0, first);
-                    n_ml = __shfl_sync(0xFFFFFFFFu, li, first);
-                    route_full = true;
-                } else {
-                    n_tok += __shfl_sync(0xFFFFFFFFu, incl, 31);
-                    n_ml += __popc(wb);
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), n_new = __popc(wb);
+                uint32_t tb = 0, lb = 0;
+                if (lane == 0) {
+                    tb = atomicAdd(a.sc.cnt + 1, total);
+                    lb = atomicAdd(a.sc.cnt + 0, n_new);
                 }
-                if (want && !fits) {
-                    general_line(a, win, ps, pe, e, off, len, loc);
+                tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
+                lb = __shfl_sync(0xFFFFFFFFu, lb, 0);
+                const uint32_t t0 = tb + incl - want, li = lb + __popc(wb & lt_mask);
+                const bool room = uint64_t(tb) + total <= a.sc.cap_tok && uint64_t(lb) + n_new <= a.sc.cap_ml;
+                if (want && !room) {
+                    // scratch exhausted: mark what was reserved as holes and take the exact route
+                    if (li < a.sc.cap_ml) a.sc.ml[li].ntok = 0;
+                    for (uint32_t t = t0; t < t0 + want && t < a.sc.cap_tok; ++t) a.sc.tk_line[t] = NO_LINE;
+                    exact = true;
                 } else if (want) {
-                    MLine L;
-                    L.s = uint16_t(s);
-                    L.e = uint16_t(e);
-                    L.p6 = uint16_t(pe);
-                    L.tok0 = uint16_t(t0);
-                    L.ntok = uint16_t(want);
+                    loc.n_multi++;
+                    GLine L;
+                    L.s = wbase + s;
+                    L.e = wbase + e;
+                    L.ps = wbase + ps;
+                    L.pe = wbase + pe;
+                    L.tok0 = t0;
+                    L.ntok = want;
                     L.flags = has_nl ? LF_HAS_NL : 0;
-                    L.ps = uint16_t(ps);
                     L.pad = 0;
-                    ml[li] = L;
+                    a.sc.ml[li] = L;
                     // token records: maximal runs of non-delimiter bytes, from the start / end flags
                     const uint32_t a0 = ps & ~3u, a1 = (pe - 1u) & ~3u;
                     const uint32_t lom = 0xFFFFFFFFu << (8u * (ps & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((pe - 1u) & 3u)));
@@ -1055,193 +962,264 @@ __global__ void __launch_bounds__(THREADS, 4) filter_kernel(const FilterArgs a) 
                             const uint32_t pos = w0 + (bit >> 3);
                             if ((st >> bit) & 1u) {
                                 cur = pos;
-                                t_b[t] = uint16_t(pos);
-                                t_line[t] = uint16_t(li);
+                                a.sc.tk_b[t] = wbase + pos;
+                                a.sc.tk_line[t] = li;
                             } else if (cur != 0xFFFFFFFFu) {
-                                t_l[t++] = uint16_t(pos - cur);
+                                a.sc.tk_l[t++] = uint16_t(pos - cur);
                                 cur = 0xFFFFFFFFu;
                             }
                         }
                     }
-                    if (cur != 0xFFFFFFFFu) t_l[t++] = uint16_t(pe - cur);
+                    if (cur != 0xFFFFFFFFu) a.sc.tk_l[t++] = uint16_t(pe - cur);
                 }
             }
-            __syncwarp();
-            if (stop_after == 2) continue;
-
-            // ---- phase C: one lane per path node
-            for (uint32_t t = lane; t < n_tok; t += 32) {
-                const uint32_t b = t_b[t], l = t_l[t];
-                // name hash, 4 bytes a step, and the colons on the way
-                const uint32_t al = b & ~3u, sh = (b & 3u) * 8u;
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(win + al);
-                uint32_t curw = wp[0];
-                TokHash h = tok_init();
-                uint32_t ncolon = 0, cpos = 0;
-                for (uint32_t i = 0; i < l; i += 4) {
-                    uint32_t nxt = wp[(i >> 2) + 1];
-                    uint32_t w = __funnelshift_r(curw, nxt, sh);
-                    curw = nxt;
-                    uint32_t rem = l - i;
-                    if (rem < 4) w &= (1u << (8 * rem)) - 1u;
-                    tok_step(h, w);
-                    uint32_t f = eq_bytes(w, 0x3A3A3A3Au);
-                    if (f) {
-                        ncolon += __popc(f);
-                        cpos = i + ((31 - __clz(f)) >> 3);
-                    }
+            const uint32_t xb = __ballot_sync(0xFFFFFFFFu, exact);
+            if (xb) {
+                uint32_t xbase = 0;
+                if (lane == 0) xbase = atomicAdd(a.sc.cnt + 2, uint32_t(__popc(xb)));
+                xbase = __shfl_sync(0xFFFFFFFFu, xbase, 0);
+                if (exact) {
+                    const uint32_t idx = xbase + __popc(xb & lt_mask);
+                    if (idx < a.sc.cap_exact) a.sc.exact[idx] = wbase + s;
+                    else report(a, SVJG_BAD_SHORTLINE, wbase + s);   // only possible with lines shorter than 16 bytes
                 }
-                const uint64_t hv = tok_value(h, l);
-                // chrom:start-end  or  chrom:pos.<anything>
-                uint32_t fl = win[b - 1] == '>' ? TF_PLUS : 0;
-                uint32_t sval = 0;
-                int64_t nlen = 0;
-                if (ncolon == 1) {
-                    uint32_t q = b + cpos + 1, end = b + l;
-                    uint32_t v0 = 0, nd0 = 0;
-                    for (; q < end; ++q) {
-                        uint32_t d = uint32_t(win[q]) - '0';
-                        if (d > 9) break;
-                        v0 = v0 * 10 + d;
-                        ++nd0;
-                    }
-                    if (nd0 >= 1 && nd0 <= 9 && q < end) {
-                        uint32_t c = win[q];
-                        if (c == '.') {
-                            Rec<SmemSrc> rec(a, SmemSrc{win}, 0, 0, loc);
-                            Rec<SmemSrc>::Tok tk{b, l};
-                            if (rec.alt_lookup(hv, tk, nlen) && nlen > 0 && nlen <= 0x7FFFFFFF) fl |= TF_ALT | TF_PLAIN;
-                        } else if (c == '-') {
-                            uint32_t v1 = 0, nd1 = 0;
-                            for (++q; q < end; ++q) {
-                                uint32_t d = uint32_t(win[q]) - '0';
-                                if (d > 9) break;
-                                v1 = v1 * 10 + d;
-                                ++nd1;
-                            }
-                            nlen = int64_t(v1) - int64_t(v0) + 1;
-                            if (q == end && nd1 >= 1 && nd1 <= 9 && nlen > 0) fl |= TF_PLAIN;
-                        }
-                    }
-                    sval = v0;
-                }
-                t_hash[t] = hv;
-                t_len[t] = int32_t(nlen);
-                t_sval[t] = sval;
-                t_flags[t] = uint8_t(fl);
-            }
-            __syncwarp();
-            if (stop_after == 3) continue;
-
-            // ---- phase D: per multi-node line, coordinates + running sums + overlap verdicts;
-            //      per node, "could this name occur inside an earlier one" (first-occurrence rules :206, :269-271)
-            for (uint32_t k = lane; k < n_ml; k += 32) {
-                const MLine L = ml[k];
-                // Tlen, Ts, Te: digit-only columns 7-9 (validated in phase B)
-                int64_t v[3];
-                uint32_t q = uint32_t(L.p6) + 1, too_long = 0;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    int64_t x = 0;
-                    uint32_t nd = 0;
-                    for (;; ++q) {
-                        uint32_t d = uint32_t(win[q]) - '0';
-                        if (d > 9) break;
-                        nd += (x != 0 || d != 0);
-                        x = x * 10 + int64_t(d);
-                    }
-                    too_long |= nd > 18;
-                    v[j] = x;
-                    ++q;
-                }
-                if (too_long) {
-                    // the reference has bigints; this implementation stops at 18 digits and says so
-                    report(a, SVJG_BAD_RANGE, uint32_t(tile_start) + (uint32_t(L.s) - HEAD));
-                    ml[k].flags = uint16_t(L.flags | LF_SKIP);
-                    continue;
-                }
-                const int64_t ts = v[1], tail = v[0] - v[2] - 1;
-                uint32_t bad = 0;
-                int64_t total = 0;
-                for (uint32_t t = L.tok0; t < uint32_t(L.tok0) + L.ntok; ++t) {
-                    bad |= !(t_flags[t] & TF_PLAIN);
-                    total += t_len[t];
-                }
-                int64_t pre = t_len[L.tok0];
-                for (uint32_t t = uint32_t(L.tok0) + 1; t < uint32_t(L.tok0) + L.ntok; ++t) {
-                    const bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);   // :269-273
-                    if (ok) t_flags[t] |= TF_OK;
-                    pre += t_len[t];
-                }
-                if (bad) ml[k].flags = uint16_t(L.flags | LF_GENERAL);
-            }
-            __syncwarp();
-            for (uint32_t t = lane; t < n_tok; t += 32) {
-                const uint32_t li = t_line[t];
-                const uint32_t t0 = ml[li].tok0;
-                const uint32_t sv = t_sval[t], kind = t_flags[t] & TF_ALT;
-                bool clash = false;
-                for (uint32_t j = t0; j < t; ++j) clash |= (t_sval[j] == sv) && ((t_flags[j] & TF_ALT) == kind);
-                if (clash) ml[li].flags |= LF_GENERAL;   // benign race: every writer sets the same bit
-            }
-            __syncwarp();
-            if (stop_after == 4) continue;
-
-            // ---- phase E: one lane per link (node t with its predecessor), both keys
-            for (uint32_t t = lane; t < n_tok; t += 32) {
-                const uint32_t li = t_line[t];
-                const MLine L = ml[li];
-                if (t == L.tok0 || (L.flags & (LF_GENERAL | LF_SKIP))) continue;
-                const uint32_t fb = t_flags[t];
-                const bool ok = fb & TF_OK;
-                if (!ok && !all_links) continue;
-                const uint32_t off = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
-                const uint32_t len = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
-                Rec<SmemSrc> rec(a, SmemSrc{win}, off, len, loc);
-                rec.stage_sv = h_sv;
-                rec.stage_ml = h_ml;
-                rec.stage_n = s_nhits;
-                rec.stage_line = li;
-                Rec<SmemSrc>::Tok A{t_b[t - 1], t_l[t - 1]}, B{t_b[t], t_l[t]};
-                rec.link(A, t_hash[t - 1], t_flags[t - 1] & TF_PLUS, B, t_hash[t], fb & TF_PLUS, true, ok);
-                if (rec.err) report(a, rec.err, off);
-            }
-            for (uint32_t k = lane; k < n_ml; k += 32) {
-                const MLine L = ml[k];
-                if (!(L.flags & LF_GENERAL) || (L.flags & LF_SKIP)) continue;
-                const uint32_t off = uint32_t(tile_start) + (uint32_t(L.s) - HEAD);
-                const uint32_t len = uint32_t(L.e) - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
-                general_line(a, win, L.ps, L.p6, L.e, off, len, loc);
             }
         }
         __syncwarp();
     }
-    // hits of the last tile
-    {
-        const uint32_t n_staged = min(*s_nhits, uint32_t(HCAP));
-        if (n_staged) {
-            unsigned long long hbase = 0;
-            if (lane == 0) hbase = atomicAdd(a.stats + 0, (unsigned long long)n_staged);
-            hbase = __shfl_sync(0xFFFFFFFFu, hbase, 0);
-            flush_hits(a, h_sv, h_ml, ml, n_staged, prev_tile_start, hbase, lane);
-        }
-    }
+    add_stats(a, loc);
+}
 
-    // ---- per-warp statistics
-    uint64_t v1 = loc.n_rec, v2 = loc.n_multi, v3 = loc.n_checks, v6 = loc.n_generic;
+// ===========================================================================
+// token: one thread per path node
+// ===========================================================================
+__global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_constant__ FilterArgs a) {
+    const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
+    Local loc;
+    for (uint32_t t = blockIdx.x * FLAT_THREADS + threadIdx.x; t < n_tok; t += gridDim.x * FLAT_THREADS) {
+        if (a.sc.tk_line[t] == NO_LINE) continue;
+        const uint32_t b = a.sc.tk_b[t], l = a.sc.tk_l[t];
+        // name hash, 4 bytes a step, and the colons on the way
+        const uint64_t al = uint64_t(b) & ~3ull;
+        const uint32_t sh = (b & 3u) * 8u;
+        uint32_t curw = gaf_word(a, al);
+        TokHash h = tok_init();
+        uint32_t ncolon = 0, cpos = 0;
+        for (uint32_t i = 0; i < l; i += 4) {
+            const uint32_t nxt = gaf_word(a, al + i + 4);
+            uint32_t w = __funnelshift_r(curw, nxt, sh);
+            curw = nxt;
+            const uint32_t rem = l - i;
+            if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+            tok_step(h, w);
+            const uint32_t f = eq_bytes(w, 0x3A3A3A3Au);
+            if (f) {
+                ncolon += __popc(f);
+                cpos = i + ((31 - __clz(f)) >> 3);
+            }
+        }
+        const uint64_t hv = tok_value(h, l);
+        // chrom:start-end  or  chrom:pos.<anything>
+        uint32_t fl = __ldg(a.gaf + b - 1) == '>' ? TF_PLUS : 0;
+        uint32_t sval = 0;
+        int64_t nlen = 0;
+        if (ncolon == 1) {
+            uint32_t q = b + cpos + 1;
+            const uint32_t end = b + l;
+            uint32_t v0 = 0, nd0 = 0;
+            for (; q < end; ++q) {
+                const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
+                if (d > 9) break;
+                v0 = v0 * 10 + d;
+                ++nd0;
+            }
+            if (nd0 >= 1 && nd0 <= 9 && q < end) {
+                const uint32_t c = __ldg(a.gaf + q);
+                if (c == '.') {
+                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, 0, 0, loc);
+                    Rec<GmemSrc>::Tok tk{b, l};
+                    if (rec.alt_lookup(hv, tk, nlen) && nlen > 0 && nlen <= 0x7FFFFFFF) fl |= TF_ALT | TF_PLAIN;
+                } else if (c == '-') {
+                    uint32_t v1 = 0, nd1 = 0;
+                    for (++q; q < end; ++q) {
+                        const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
+                        if (d > 9) break;
+                        v1 = v1 * 10 + d;
+                        ++nd1;
+                    }
+                    nlen = int64_t(v1) - int64_t(v0) + 1;
+                    if (q == end && nd1 >= 1 && nd1 <= 9 && nlen > 0) fl |= TF_PLAIN;
+                }
+            }
+            sval = v0;
+        }
+        a.sc.tk_hash[t] = hv;
+        a.sc.tk_len[t] = int32_t(nlen);
+        a.sc.tk_sval[t] = sval;
+        a.sc.tk_flags[t] = uint8_t(fl);
+    }
+}
+
+// ===========================================================================
+// line: one thread per multi-node line — coordinates, sums, overlap verdicts
+// ===========================================================================
+__global__ void __launch_bounds__(FLAT_THREADS) line_kernel(const __grid_constant__ FilterArgs a) {
+    const uint32_t n_ml = min(a.sc.cnt[0], a.sc.cap_ml);
+    for (uint32_t k = blockIdx.x * FLAT_THREADS + threadIdx.x; k < n_ml; k += gridDim.x * FLAT_THREADS) {
+        const GLine L = a.sc.ml[k];
+        if (L.ntok == 0) continue;
+        // Tlen, Ts, Te: digit-only columns 7-9 (validated by scan_parse)
+        int64_t v[3];
+        uint32_t q = L.pe + 1, too_long = 0;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        v1 += __shfl_xor_sync(0xFFFFFFFFu, v1, d);
-        v2 += __shfl_xor_sync(0xFFFFFFFFu, v2, d);
-        v3 += __shfl_xor_sync(0xFFFFFFFFu, v3, d);
-        v6 += __shfl_xor_sync(0xFFFFFFFFu, v6, d);
+        for (int j = 0; j < 3; ++j) {
+            int64_t x = 0;
+            uint32_t nd = 0;
+            for (;; ++q) {
+                const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
+                if (d > 9) break;
+                nd += (x != 0 || d != 0);
+                x = x * 10 + int64_t(d);
+            }
+            too_long |= nd > 18;
+            v[j] = x;
+            ++q;
+        }
+        if (too_long) {
+            // the reference has bigints; this implementation stops at 18 digits and says so
+            report(a, SVJG_BAD_RANGE, L.s);
+            a.sc.ml[k].flags = L.flags | LF_SKIP;
+            continue;
+        }
+        const int64_t ts = v[1], tail = v[0] - v[2] - 1;
+        uint32_t bad = 0;
+        int64_t total = 0;
+        for (uint32_t t = L.tok0; t < L.tok0 + L.ntok; ++t) {
+            bad |= !(a.sc.tk_flags[t] & TF_PLAIN);
+            total += a.sc.tk_len[t];
+        }
+        int64_t pre = a.sc.tk_len[L.tok0];
+        for (uint32_t t = L.tok0 + 1; t < L.tok0 + L.ntok; ++t) {
+            const bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);   // :269-273
+            if (ok) a.sc.tk_flags[t] |= TF_OK;
+            pre += a.sc.tk_len[t];
+        }
+        if (bad) a.sc.ml[k].flags = L.flags | LF_GENERAL;
     }
-    if (lane == 0) {
-        if (v1) atomicAdd(a.stats + 1, (unsigned long long)v1);
-        if (v2) atomicAdd(a.stats + 2, (unsigned long long)v2);
-        if (v3) atomicAdd(a.stats + 3, (unsigned long long)v3);
-        if (v6) atomicAdd(a.stats + 6, (unsigned long long)v6);
+}
+
+// ===========================================================================
+// clash: one thread per node — same start value and kind as an earlier node of the path means the
+// name could occur inside that one; then the first-occurrence rules (:206, :269-271) need general()
+// ===========================================================================
+__global__ void __launch_bounds__(FLAT_THREADS) clash_kernel(const __grid_constant__ FilterArgs a) {
+    const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
+    for (uint32_t t = blockIdx.x * FLAT_THREADS + threadIdx.x; t < n_tok; t += gridDim.x * FLAT_THREADS) {
+        const uint32_t li = a.sc.tk_line[t];
+        if (li == NO_LINE) continue;
+        const uint32_t t0 = a.sc.ml[li].tok0;
+        const uint32_t sv = a.sc.tk_sval[t], kind = a.sc.tk_flags[t] & TF_ALT;
+        bool clash = false;
+        for (uint32_t j = t0; j < t; ++j) clash |= (a.sc.tk_sval[j] == sv) && ((a.sc.tk_flags[j] & TF_ALT) == kind);
+        if (clash) atomicOr(&a.sc.ml[li].flags, LF_GENERAL);
     }
+}
+
+// ===========================================================================
+// link: one thread per link (node t with its predecessor), both keys; the first node's thread
+// runs general() for a line that needs it
+// ===========================================================================
+constexpr int LINK_STAGE = 1024;   // hits a block stages per round of FLAT_THREADS links
+
+__global__ void __launch_bounds__(FLAT_THREADS, 3) link_kernel(const __grid_constant__ FilterArgs a) {
+    __shared__ uint32_t h_sv[LINK_STAGE], h_off[LINK_STAGE], h_len[LINK_STAGE];
+    __shared__ uint32_t h_n;
+    __shared__ unsigned long long h_base;
+    const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
+    const bool all_links = a.flags & FLAG_EXACT_CHECKS;
+    Local loc;
+    if (threadIdx.x == 0) h_n = 0;
+    __syncthreads();
+    for (uint32_t t0 = blockIdx.x * FLAT_THREADS; t0 < n_tok; t0 += gridDim.x * FLAT_THREADS) {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t li = t < n_tok ? a.sc.tk_line[t] : NO_LINE;
+        if (li != NO_LINE) {
+            const GLine L = a.sc.ml[li];
+            const uint32_t len = L.e - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
+            if (L.flags & LF_SKIP) {
+            } else if (L.flags & LF_GENERAL) {
+                if (t == L.tok0) {
+                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
+                    rec.ps = L.ps;
+                    rec.pe = L.pe;
+                    rec.reparse_coords(L.e);
+                    rec.general();
+                    if (rec.err) report(a, rec.err, L.s);
+                }
+            } else if (t != L.tok0) {
+                const uint32_t fb = a.sc.tk_flags[t];
+                const bool ok = fb & TF_OK;
+                if (ok || all_links) {
+                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
+                    rec.stage_sv = h_sv;
+                    rec.stage_off = h_off;
+                    rec.stage_len = h_len;
+                    rec.stage_n = &h_n;
+                    rec.stage_cap = LINK_STAGE;
+                    Rec<GmemSrc>::Tok A{a.sc.tk_b[t - 1], a.sc.tk_l[t - 1]}, B{a.sc.tk_b[t], a.sc.tk_l[t]};
+                    rec.link(A, a.sc.tk_hash[t - 1], a.sc.tk_flags[t - 1] & TF_PLUS, B, a.sc.tk_hash[t], fb & TF_PLUS, true, ok);
+                    if (rec.err) report(a, rec.err, L.s);
+                }
+            }
+        }
+        // flush the staged hits: one cursor atomic for the block, coalesced tuple stores,
+        // warp-aggregated counter atomics
+        __syncthreads();
+        const uint32_t n = min(h_n, uint32_t(LINK_STAGE));
+        if (threadIdx.x == 0 && n) h_base = atomicAdd(a.stats + 0, (unsigned long long)n);
+        __syncthreads();
+        for (uint32_t i0 = 0; i0 < n; i0 += FLAT_THREADS) {
+            const uint32_t i = i0 + threadIdx.x;
+            const bool act = i < n;
+            const uint32_t sv2 = act ? h_sv[i] : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, sv2);
+            if (act) {
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(a.counts + sv2, uint32_t(__popc(peers)));
+                const unsigned long long k = h_base + i;
+                if (k < a.hit_cap) {
+                    a.hit_sv2[k] = sv2;
+                    a.hit_off[k] = h_off[i];
+                    a.hit_len[k] = h_len[i];
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) h_n = 0;
+        __syncthreads();
+    }
+    add_stats(a, loc);
+}
+
+// ===========================================================================
+// exact: one thread per irregular line — the reference's string semantics, literally
+// ===========================================================================
+__global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_constant__ FilterArgs a) {
+    const uint32_t n = min(a.sc.cnt[2], a.sc.cap_exact);
+    Local loc;
+    for (uint32_t i = blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += gridDim.x * FLAT_THREADS) {
+        const uint32_t off = a.sc.exact[i];
+        uint64_t e = off;
+        while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
+        const uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
+        Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+        const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
+        if (!rec.err && ntok >= 2) {
+            if (ntok != COMMA_PATH) loc.n_multi++;
+            rec.general();
+        }
+        if (rec.err) report(a, rec.err, off);
+    }
+    add_stats(a, loc);
 }
 
 __global__ void reset_kernel(uint32_t *counts, uint64_t n, unsigned long long *stats) {
@@ -1251,7 +1229,8 @@ __global__ void reset_kernel(uint32_t *counts, uint64_t n, unsigned long long *s
     if (i < 8) stats[i] = (i == 5) ? ~0ull : 0ull;
 }
 
-int g_grid_cap = 0;   // blocks resident at once (SM count x occupancy), per process
+int g_scan_grid_cap = 0;   // blocks of scan_parse resident at once (SM count x occupancy), per process
+int g_sms = 0;
 
 }  // namespace
 
@@ -1274,15 +1253,21 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     if (reinterpret_cast<uintptr_t>(d_gaf) & 15) return set_error(SVJG_E_ARG, "svjg_filter_device: d_gaf must be 16-byte aligned");
     if (n_bytes >= 0xFFFF0000ull) return set_error(SVJG_E_ARG, "svjg_filter_device: shard must be smaller than 4 GiB");
     if (n_bytes == 0) return SVJG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
     static bool configured = false;
     if (!configured) {
-        SVJG_CUDA(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        int dev = 0, sms = 0, occ = 0;
+        SVJG_CUDA(cudaFuncSetAttribute(scan_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        int dev = 0, occ = 0;
         SVJG_CUDA(cudaGetDevice(&dev));
-        SVJG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        SVJG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_kernel, THREADS, SMEM_BYTES));
-        if (occ < 1) return set_error(SVJG_E_CUDA, "filter kernel does not fit on an SM");
-        g_grid_cap = sms * occ;
+        SVJG_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+        SVJG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_parse_kernel, THREADS, SMEM_BYTES));
+        if (occ < 1) return set_error(SVJG_E_CUDA, "scan_parse kernel does not fit on an SM");
+        g_scan_grid_cap = g_sms * occ;
+        // scratch comes from the device's default memory pool: keep freed blocks cached in the pool
+        cudaMemPool_t pool;
+        SVJG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = ~0ull;
+        SVJG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         configured = true;
     }
     FilterArgs a;
@@ -1299,10 +1284,50 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
     a.flags = t->filter_flags;
-    static const char *stop_env = getenv("SVJG_STOP_AFTER");   // profiling hook: run the phases up to A/B/C/D only
-    if (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'D') a.flags |= uint32_t(stop_env[0] - 'A' + 1) << 8;
-    int grid = int(std::min<uint32_t>((a.n_tiles + WARPS - 1) / WARPS, uint32_t(g_grid_cap)));
-    filter_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
-    SVJG_CUDA(cudaGetLastError());
+    static const char *stop_env = getenv("SVJG_STOP_AFTER");   // profiling hook: run the chain up to A/B/C/D only
+    const int stop = (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'D') ? stop_env[0] - 'A' + 1 : 0;
+    if (stop == 1) a.flags |= 1u << 8;
+
+    // scratch: one stream-ordered allocation, carved into the lists
+    Scratch &sc = a.sc;
+    sc.cap_tok = uint32_t(n_bytes / 20 + 4096);       // a path node with its delimiter is rarely under 20 bytes
+    sc.cap_ml = uint32_t(n_bytes / 64 + 1024);
+    sc.cap_exact = uint32_t(n_bytes / 16 + 64);       // a line shorter than 16 bytes cannot hold 12 columns
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_cnt = 0, o_ml = up(64), o_hash = o_ml + up(size_t(sc.cap_ml) * sizeof(GLine)),
+                 o_b = o_hash + up(size_t(sc.cap_tok) * 8), o_line = o_b + up(size_t(sc.cap_tok) * 4),
+                 o_sval = o_line + up(size_t(sc.cap_tok) * 4), o_len = o_sval + up(size_t(sc.cap_tok) * 4),
+                 o_l = o_len + up(size_t(sc.cap_tok) * 4), o_fl = o_l + up(size_t(sc.cap_tok) * 2),
+                 o_ex = o_fl + up(size_t(sc.cap_tok)), total = o_ex + up(size_t(sc.cap_exact) * 4);
+    uint8_t *ws = nullptr;
+    SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
+    sc.cnt = reinterpret_cast<uint32_t *>(ws + o_cnt);
+    sc.ml = reinterpret_cast<GLine *>(ws + o_ml);
+    sc.tk_hash = reinterpret_cast<uint64_t *>(ws + o_hash);
+    sc.tk_b = reinterpret_cast<uint32_t *>(ws + o_b);
+    sc.tk_line = reinterpret_cast<uint32_t *>(ws + o_line);
+    sc.tk_sval = reinterpret_cast<uint32_t *>(ws + o_sval);
+    sc.tk_len = reinterpret_cast<int32_t *>(ws + o_len);
+    sc.tk_l = reinterpret_cast<uint16_t *>(ws + o_l);
+    sc.tk_flags = ws + o_fl;
+    sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
+    SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
+
+    const int scan_grid = int(std::min<uint32_t>((a.n_tiles + WARPS - 1) / WARPS, uint32_t(g_scan_grid_cap)));
+    const int flat_grid = g_sms * 8;
+    scan_parse_kernel<<<scan_grid, THREADS, SMEM_BYTES, st>>>(a);
+    if (stop == 0 || stop >= 3) token_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
+    if (stop == 0 || stop >= 4) {
+        line_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
+        clash_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
+    }
+    if (stop == 0) {
+        link_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
+        exact_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
+    }
+    cudaError_t le = cudaGetLastError();
+    cudaError_t fe = cudaFreeAsync(ws, st);
+    SVJG_CUDA(le);
+    SVJG_CUDA(fe);
     return SVJG_OK;
 }
