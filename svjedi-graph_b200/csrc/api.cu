@@ -80,15 +80,15 @@ extern "C" int svjg_tables_to_device(svjg_tables *t, int device) {
         return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
     };
     SVJG_CUDA(up(&t->d_links, t->links.data(), t->links.size() * sizeof(LinkSlot)));
-    SVJG_CUDA(up(&t->d_alts, t->alts.data(), t->alts.size() * sizeof(AltSlot)));
+    SVJG_CUDA(up(&t->d_nodes, t->nodes.data(), t->nodes.size() * sizeof(NodeSlot)));
     SVJG_CUDA(up(&t->d_blob, t->blob.data(), t->blob.size()));
     SVJG_CUDA(up(&t->d_entries, t->entries.data(), t->entries.size() * sizeof(uint32_t)));
     t->dev.links = static_cast<const LinkSlot *>(t->d_links);
-    t->dev.alts = static_cast<const AltSlot *>(t->d_alts);
+    t->dev.nodes = static_cast<const NodeSlot *>(t->d_nodes);
     t->dev.blob = static_cast<const uint8_t *>(t->d_blob);
     t->dev.entries = static_cast<const uint32_t *>(t->d_entries);
     t->dev.link_mask = uint32_t(t->links.size() - 1);
-    t->dev.alt_mask = uint32_t(t->alts.size() - 1);
+    t->dev.node_mask = uint32_t(t->nodes.size() - 1);
     t->dev.num_sv = uint32_t(t->sv_ids.size());
     t->device = device;
     return SVJG_OK;
@@ -100,7 +100,7 @@ extern "C" void svjg_tables_free(svjg_tables *t) {
         cudaSetDevice(t->device);
         free_host_ws(t);
         cudaFree(t->d_links);
-        cudaFree(t->d_alts);
+        cudaFree(t->d_nodes);
         cudaFree(t->d_blob);
         cudaFree(t->d_entries);
     }

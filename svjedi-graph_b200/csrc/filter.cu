@@ -91,14 +91,14 @@ static_assert(sizeof(GLine) == 32, "GLine is one sector");
 
 // device scratch of one svjg_filter_device() call
 struct Scratch {
-    uint32_t *cnt;        // [0] multi-node lines, [1] tokens, [2] exact-route lines
+    uint32_t *cnt;        // [0] multi-node lines, [1] tokens, [2] exact-route lines, [3] lines for general()
     GLine *ml;
-    uint32_t *tk_b, *tk_line, *tk_sval;
+    uint32_t *tk_b, *tk_line, *tk_sval, *tk_node;
     uint16_t *tk_l;
-    uint64_t *tk_hash;
     int32_t *tk_len;
     uint8_t *tk_flags;
     uint32_t *exact;      // line start offsets
+    uint32_t *general;    // multi-node lines (index into ml) that need general(); at most cap_ml
     uint32_t cap_ml, cap_tok, cap_exact;
 };
 
@@ -421,43 +421,49 @@ struct Rec {
         return diff == 0;
     }
 
-    __device__ bool probe(uint64_t hl, uint32_t sl, const Tok &tl_, uint64_t hr, uint32_t sr, const Tok &tr_,
-                          LinkSlot &out) const {
-        uint64_t h = link_hash(hl, sl, hr, sr);
-        uint32_t i = uint32_t(h) & a.tb.link_mask;
+    // node table: name -> (id, alt sequence length); false when the name is in no link key and is
+    // no alt node of the GFA
+    __device__ bool node_find(uint64_t tokh, const Tok &t, uint32_t &id, int64_t &seq_len) const {
+        const uint64_t h = node_hash(tokh);
+        uint32_t i = uint32_t(h) & a.tb.node_mask;
         for (;;) {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.links + i);
-            uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-            uint32_t meta = hi.y;
-            if (!(meta & 1u)) return false;
-            uint64_t sh = (uint64_t(lo.y) << 32) | lo.x;
-            if (sh == h && ((meta >> 2) & 1u) == sl && ((meta >> 1) & 1u) == sr && (lo.w & 0xFFFFu) == tl_.l &&
-                (lo.w >> 16) == tr_.l && names_match(lo.z, tl_) && names_match(lo.z + ((tl_.l + 3u) & ~3u), tr_)) {
-                out.hash = sh;
-                out.name_off = lo.z;
-                out.ent_begin = hi.x;
-                out.meta = meta;
-                out.ent0 = hi.z;
+            const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.nodes + i);
+            const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+            if (!hi.z) return false;
+            const uint64_t sh = (uint64_t(lo.y) << 32) | lo.x;
+            if (sh == h && lo.w == t.l && names_match(lo.z, t)) {
+                id = hi.z - 1u;
+                seq_len = int64_t((uint64_t(hi.y) << 32) | hi.x);
+                return true;
+            }
+            i = (i + 1) & a.tb.node_mask;
+        }
+    }
+    __device__ uint32_t node_id(uint64_t tokh, const Tok &t) const {
+        uint32_t id;
+        int64_t sl;
+        return node_find(tokh, t, id, sl) ? id : NO_NODE;
+    }
+    // alt_node_len[name] (:346); false when the GFA has no such alt node
+    __device__ bool alt_lookup(uint64_t tokh, const Tok &t, int64_t &len) const {
+        uint32_t id;
+        return node_find(tokh, t, id, len) && len >= 0;
+    }
+
+    // link table: exact integer key -> entries
+    __device__ bool probe(uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr, LinkSlot &out) const {
+        const uint64_t key = link_key(idl, sl, idr, sr);
+        uint32_t i = uint32_t(link_hash(key)) & a.tb.link_mask;
+        for (;;) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
+            if (!(v.w & 1u)) return false;
+            if (((uint64_t(v.y) << 32) | v.x) == key) {
+                out.key = key;
+                out.val = v.z;
+                out.meta = v.w;
                 return true;
             }
             i = (i + 1) & a.tb.link_mask;
-        }
-    }
-
-    // alt_node_len[name] (:346); false when the name is not in the GFA
-    __device__ bool alt_lookup(uint64_t tokh, const Tok &t, int64_t &len) const {
-        uint64_t h = alt_hash(tokh);
-        uint32_t i = uint32_t(h) & a.tb.alt_mask;
-        for (;;) {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.alts + i);
-            uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-            if (!hi.z) return false;
-            uint64_t sh = (uint64_t(lo.y) << 32) | lo.x;
-            if (sh == h && lo.w == t.l && names_match(lo.z, t)) {
-                len = int64_t((uint64_t(hi.y) << 32) | hi.x);
-                return true;
-            }
-            i = (i + 1) & a.tb.alt_mask;
         }
     }
 
@@ -494,15 +500,21 @@ struct Rec {
         }
     }
 
-    // forward and reverse key of one link (:141-148) and their entries (:150-166).
+    // forward and reverse key of one link (:141-148) and their entries (:150-166).  idA / idB are
+    // the node ids (NO_NODE: the name is in no key, so no key can match).
     // ok_known: the overlap verdict is already there; otherwise it is computed
     // once, on the first key that has entries, by the general overlap().
-    __device__ void link(const Tok &A, uint64_t hA, int sA, const Tok &B, uint64_t hB, int sB, bool ok_known, bool ok) {
-#pragma unroll 1
+    __device__ void link(const Tok &A, uint32_t idA, int sA, const Tok &B, uint32_t idB, int sB, bool ok_known, bool ok) {
+        if (idA == NO_NODE || idB == NO_NODE) return;
+        // both slots are fetched before either is looked at: one round trip
+        LinkSlot sl[2];
+        bool hit[2];
+        hit[0] = probe(idA, sA, idB, sB, sl[0]);
+        hit[1] = probe(idB, !sB, idA, !sA, sl[1]);
+#pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
-            LinkSlot s;
-            bool hit = dir == 0 ? probe(hA, sA, A, hB, sB, B, s) : probe(hB, !sB, B, hA, !sA, A, s);
-            if (!hit) continue;
+            if (!hit[dir]) continue;
+            const LinkSlot &s = sl[dir];
             if (s.meta & 8u) {
                 err = SVJG_BAD_ENTRY;
                 return;
@@ -517,7 +529,7 @@ struct Rec {
             }
             if (!ok) continue;
             for (uint32_t k = 0; k < cnt; ++k) {
-                uint32_t sv2 = k == 0 ? s.ent0 : __ldg(a.tb.entries + s.ent_begin + k);
+                uint32_t sv2 = cnt == 1 ? s.val : __ldg(a.tb.entries + s.val + k);
                 if (sv2 == ENTRY_POISON) {
                     err = SVJG_BAD_ENTRY;
                     return;
@@ -615,18 +627,18 @@ struct Rec {
         P cur = ps;
         Tok A, B;
         next_tok(cur, A);
-        uint64_t hA = tok_hash(A);
+        uint32_t idA = node_id(tok_hash(A), A);
         int sA = strand(A);
         if (err) return;
         for (uint32_t i = 1; i < n; ++i) {
             next_tok(cur, B);
-            uint64_t hB = tok_hash(B);
+            uint32_t idB = node_id(tok_hash(B), B);
             int sB = strand(B);
             if (err) return;
-            link(A, hA, sA, B, hB, sB, false, false);
+            link(A, idA, sA, B, idB, sB, false, false);
             if (err) return;
             A = B;
-            hA = hB;
+            idA = idB;
             sA = sB;
         }
     }
@@ -1019,6 +1031,14 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
             }
         }
         const uint64_t hv = tok_value(h, l);
+        // the name's node id (and alt sequence length): the one byte-exact name check of the chain
+        uint32_t nid = NO_NODE;
+        int64_t seq_len = -1;
+        {
+            Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, 0, 0, loc);
+            Rec<GmemSrc>::Tok tk{b, l};
+            if (!rec.node_find(hv, tk, nid, seq_len)) nid = NO_NODE, seq_len = -1;
+        }
         // chrom:start-end  or  chrom:pos.<anything>
         uint32_t fl = __ldg(a.gaf + b - 1) == '>' ? TF_PLUS : 0;
         uint32_t sval = 0;
@@ -1036,9 +1056,10 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
             if (nd0 >= 1 && nd0 <= 9 && q < end) {
                 const uint32_t c = __ldg(a.gaf + q);
                 if (c == '.') {
-                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, 0, 0, loc);
-                    Rec<GmemSrc>::Tok tk{b, l};
-                    if (rec.alt_lookup(hv, tk, nlen) && nlen > 0 && nlen <= 0x7FFFFFFF) fl |= TF_ALT | TF_PLAIN;
+                    if (seq_len > 0 && seq_len <= 0x7FFFFFFF) {
+                        nlen = seq_len;
+                        fl |= TF_ALT | TF_PLAIN;
+                    }
                 } else if (c == '-') {
                     uint32_t v1 = 0, nd1 = 0;
                     for (++q; q < end; ++q) {
@@ -1053,7 +1074,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
             }
             sval = v0;
         }
-        a.sc.tk_hash[t] = hv;
+        a.sc.tk_node[t] = nid;
         a.sc.tk_len[t] = int32_t(nlen);
         a.sc.tk_sval[t] = sval;
         a.sc.tk_flags[t] = uint8_t(fl);
@@ -1131,7 +1152,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) clash_kernel(const __grid_consta
 // ===========================================================================
 constexpr int LINK_STAGE = 1024;   // hits a block stages per round of FLAT_THREADS links
 
-__global__ void __launch_bounds__(FLAT_THREADS, 3) link_kernel(const __grid_constant__ FilterArgs a) {
+__global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_constant__ FilterArgs a) {
     __shared__ uint32_t h_sv[LINK_STAGE], h_off[LINK_STAGE], h_len[LINK_STAGE];
     __shared__ uint32_t h_n;
     __shared__ unsigned long long h_base;
@@ -1148,14 +1169,8 @@ __global__ void __launch_bounds__(FLAT_THREADS, 3) link_kernel(const __grid_cons
             const uint32_t len = L.e - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
             if (L.flags & LF_SKIP) {
             } else if (L.flags & LF_GENERAL) {
-                if (t == L.tok0) {
-                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
-                    rec.ps = L.ps;
-                    rec.pe = L.pe;
-                    rec.reparse_coords(L.e);
-                    rec.general();
-                    if (rec.err) report(a, rec.err, L.s);
-                }
+                // the exact kernel runs general() on it; the first node's thread hands the line over
+                if (t == L.tok0) a.sc.general[atomicAdd(a.sc.cnt + 3, 1u)] = li;
             } else if (t != L.tok0) {
                 const uint32_t fb = a.sc.tk_flags[t];
                 const bool ok = fb & TF_OK;
@@ -1167,7 +1182,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 3) link_kernel(const __grid_cons
                     rec.stage_n = &h_n;
                     rec.stage_cap = LINK_STAGE;
                     Rec<GmemSrc>::Tok A{a.sc.tk_b[t - 1], a.sc.tk_l[t - 1]}, B{a.sc.tk_b[t], a.sc.tk_l[t]};
-                    rec.link(A, a.sc.tk_hash[t - 1], a.sc.tk_flags[t - 1] & TF_PLUS, B, a.sc.tk_hash[t], fb & TF_PLUS, true, ok);
+                    rec.link(A, a.sc.tk_node[t - 1], a.sc.tk_flags[t - 1] & TF_PLUS, B, a.sc.tk_node[t], fb & TF_PLUS, true, ok);
                     if (rec.err) report(a, rec.err, L.s);
                 }
             }
@@ -1218,6 +1233,18 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
             rec.general();
         }
         if (rec.err) report(a, rec.err, off);
+    }
+    // multi-node lines whose columns are fine but whose node names need the literal string rules
+    const uint32_t n_gen = min(a.sc.cnt[3], a.sc.cap_ml);
+    for (uint32_t i = blockIdx.x * FLAT_THREADS + threadIdx.x; i < n_gen; i += gridDim.x * FLAT_THREADS) {
+        const GLine L = a.sc.ml[a.sc.general[i]];
+        const uint32_t len = L.e - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
+        Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
+        rec.ps = L.ps;
+        rec.pe = L.pe;
+        rec.reparse_coords(L.e);
+        rec.general();
+        if (rec.err) report(a, rec.err, L.s);
     }
     add_stats(a, loc);
 }
@@ -1294,16 +1321,17 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     sc.cap_ml = uint32_t(n_bytes / 64 + 1024);
     sc.cap_exact = uint32_t(n_bytes / 16 + 64);       // a line shorter than 16 bytes cannot hold 12 columns
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o_cnt = 0, o_ml = up(64), o_hash = o_ml + up(size_t(sc.cap_ml) * sizeof(GLine)),
-                 o_b = o_hash + up(size_t(sc.cap_tok) * 8), o_line = o_b + up(size_t(sc.cap_tok) * 4),
+    const size_t o_cnt = 0, o_ml = up(64), o_node = o_ml + up(size_t(sc.cap_ml) * sizeof(GLine)),
+                 o_b = o_node + up(size_t(sc.cap_tok) * 4), o_line = o_b + up(size_t(sc.cap_tok) * 4),
                  o_sval = o_line + up(size_t(sc.cap_tok) * 4), o_len = o_sval + up(size_t(sc.cap_tok) * 4),
                  o_l = o_len + up(size_t(sc.cap_tok) * 4), o_fl = o_l + up(size_t(sc.cap_tok) * 2),
-                 o_ex = o_fl + up(size_t(sc.cap_tok)), total = o_ex + up(size_t(sc.cap_exact) * 4);
+                 o_ex = o_fl + up(size_t(sc.cap_tok)), o_gen = o_ex + up(size_t(sc.cap_exact) * 4),
+                 total = o_gen + up(size_t(sc.cap_ml) * 4);
     uint8_t *ws = nullptr;
     SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     sc.cnt = reinterpret_cast<uint32_t *>(ws + o_cnt);
     sc.ml = reinterpret_cast<GLine *>(ws + o_ml);
-    sc.tk_hash = reinterpret_cast<uint64_t *>(ws + o_hash);
+    sc.tk_node = reinterpret_cast<uint32_t *>(ws + o_node);
     sc.tk_b = reinterpret_cast<uint32_t *>(ws + o_b);
     sc.tk_line = reinterpret_cast<uint32_t *>(ws + o_line);
     sc.tk_sval = reinterpret_cast<uint32_t *>(ws + o_sval);
@@ -1311,6 +1339,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     sc.tk_l = reinterpret_cast<uint16_t *>(ws + o_l);
     sc.tk_flags = ws + o_fl;
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
+    sc.general = reinterpret_cast<uint32_t *>(ws + o_gen);
     SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
 
     const int scan_grid = int(std::min<uint32_t>((a.n_tiles + WARPS - 1) / WARPS, uint32_t(g_scan_grid_cap)));

@@ -37,47 +37,44 @@ SVJG_HD uint64_t mix64(uint64_t x) {
 }
 SVJG_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 
-// link (nL, sL, nR, sR): strands are 1 for '+', 0 for '-'
-SVJG_HD uint64_t link_hash(uint64_t tokL, uint32_t sL, uint64_t tokR, uint32_t sR) {
-    uint64_t x = tokL * 0x9E3779B97F4A7C15ull + rotl64(tokR, 23) * 0xC2B2AE3D27D4EB4Full +
-                 uint64_t(sL * 2 + sR + 1) * 0x165667B19E3779F9ull;
-    return mix64(x);
-}
-SVJG_HD uint64_t alt_hash(uint64_t tok) { return mix64(tok ^ 0xA0761D6478BD642Full); }
-
 // ---- device tables ---------------------------------------------------------
-// One 32-byte sector per slot: a probe that lands on the right slot needs one
-// DRAM/L2 sector for everything but the name check.
-struct LinkSlot {          // open addressing, linear probing, capacity = power of two
-    uint64_t hash;         // link_hash of the key
-    uint32_t name_off;     // into blob (multiple of 4): left name, zero padded to 4 bytes, then right name, padded
-    uint16_t len_l, len_r;
-    uint32_t ent_begin;    // entries[ent_begin .. ent_begin + count)
-    uint32_t meta;         // count << 4 | poison_key << 3 | sL << 2 | sR << 1 | used
-    uint32_t ent0;         // copy of entries[ent_begin] (most keys have one entry)
-    uint32_t pad;
-};
-static_assert(sizeof(LinkSlot) == 32, "LinkSlot must be one sector");
+// Node names are interned: a path node is looked up once (hash probe + byte compare of the name),
+// after that a link is the exact integer key (node id, strand, node id, strand).
+SVJG_HD uint64_t node_hash(uint64_t tok) { return mix64(tok ^ 0xA0761D6478BD642Full); }
+constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
 
-struct AltSlot {
-    uint64_t hash;         // alt_hash of the node name
-    uint32_t name_off;
+// link (nL, sL, nR, sR): strands are 1 for '+', 0 for '-'; ids < 2^31
+SVJG_HD uint64_t link_key(uint32_t idL, uint32_t sL, uint32_t idR, uint32_t sR) {
+    return (uint64_t(idL) << 33) | (uint64_t(sL) << 32) | (uint64_t(idR) << 1) | uint64_t(sR);
+}
+SVJG_HD uint64_t link_hash(uint64_t key) { return mix64(key + 0x9E3779B97F4A7C15ull); }
+
+struct LinkSlot {          // open addressing, linear probing, capacity = power of two; two slots per sector
+    uint64_t key;          // link_key()
+    uint32_t val;          // count == 1: the entry itself; otherwise entries[val .. val + count)
+    uint32_t meta;         // count << 4 | poison_key << 3 | used
+};
+static_assert(sizeof(LinkSlot) == 16, "LinkSlot is half a sector");
+
+struct NodeSlot {
+    uint64_t hash;         // node_hash of the name's token hash
+    uint32_t name_off;     // into blob (multiple of 4), zero padded to 4 bytes
     uint32_t name_len;
-    int64_t seq_len;
-    uint32_t used;
+    int64_t seq_len;       // alt node: length of its GFA sequence (filter-alignments.py:103-113); -1 if the GFA has none
+    uint32_t id1;          // node id + 1; 0 = empty slot
     uint32_t pad;
 };
-static_assert(sizeof(AltSlot) == 32, "AltSlot must be one sector");
+static_assert(sizeof(NodeSlot) == 32, "NodeSlot must be one sector");
 
 constexpr uint32_t ENTRY_POISON = 0xFFFFFFFFu;  // entry on which the reference raises
 
 struct DevTables {
     const LinkSlot *links;
-    const AltSlot *alts;
+    const NodeSlot *nodes;
     const uint8_t *blob;
     const uint32_t *entries;   // 2*sv_index + allele, or ENTRY_POISON
     uint32_t link_mask;        // capacity - 1
-    uint32_t alt_mask;         // capacity - 1 (0 capacity is never used: min 2 slots)
+    uint32_t node_mask;        // capacity - 1 (0 capacity is never used: min 2 slots)
     uint32_t num_sv;
     uint32_t pad;
 };

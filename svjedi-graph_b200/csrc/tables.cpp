@@ -479,6 +479,19 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
     ent_begin[keys.size()] = uint32_t(t->entries.size());
     if (t->entries.empty()) t->entries.push_back(ENTRY_POISON);  // never empty on the device
 
+    // node names: every name a link key can be read with, plus the GFA's alt nodes
+    std::unordered_map<std::string, uint32_t> node_id;
+    std::vector<std::pair<std::string, int64_t>> nodes;      // name, alt sequence length or -1
+    auto intern = [&](const std::string &name) -> uint32_t {
+        auto it = node_id.find(name);
+        if (it != node_id.end()) return it->second;
+        uint32_t id = uint32_t(nodes.size());
+        node_id.emplace(name, id);
+        nodes.push_back({name, -1});
+        return id;
+    };
+    for (auto &a : alts) nodes[intern(a.first)].second = a.second;
+
     uint32_t cap = pow2_at_least(parses.size() * 2 + 2);
     t->links.assign(cap, LinkSlot{});
     for (auto &ps : parses) {
@@ -490,54 +503,48 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
             return false;
         }
         uint32_t sl = k[ps.split + 1] == '+', sr = k[n - 1] == '+';
-        uint64_t h = link_hash(hash_bytes(k.data(), len_l), sl, hash_bytes(k.data() + off_r, len_r), sr);
+        uint32_t idl = intern(k.substr(0, len_l)), idr = intern(k.substr(off_r, len_r));
+        if (nodes.size() >= 0x7FFFFFFFull) {
+            err = "too many distinct node names";
+            return false;
+        }
         uint32_t cnt = ent_begin[ps.key + 1] - ent_begin[ps.key];
         if (cnt >= (1u << 28)) {
             err = "too many entries under one link key";
             return false;
         }
         LinkSlot s{};
-        s.hash = h;
-        s.name_off = uint32_t(t->blob.size());
-        s.len_l = uint16_t(len_l);
-        s.len_r = uint16_t(len_r);
-        s.ent_begin = ent_begin[ps.key];
-        s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | (sl << 2) | (sr << 1) | 1u;
-        s.ent0 = cnt ? t->entries[ent_begin[ps.key]] : ENTRY_POISON;
-        // every name starts on a 4-byte boundary and is zero padded: the kernel compares words
-        t->blob.insert(t->blob.end(), k.begin(), k.begin() + len_l);
-        t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
-        t->blob.insert(t->blob.end(), k.begin() + off_r, k.begin() + off_r + len_r);
-        t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
-        if (t->blob.size() >= 0xFFFF0000ull) {
-            err = "link table name blob exceeds 4 GiB";
-            return false;
-        }
-        uint32_t i = uint32_t(h) & (cap - 1);
+        s.key = link_key(idl, sl, idr, sr);
+        s.val = cnt == 1 ? t->entries[ent_begin[ps.key]] : ent_begin[ps.key];
+        s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | 1u;
+        uint32_t i = uint32_t(link_hash(s.key)) & (cap - 1);
         while (t->links[i].meta & 1u) i = (i + 1) & (cap - 1);
         t->links[i] = s;
     }
     t->n_link_slots = uint32_t(parses.size());
 
     t->n_alt = uint32_t(alts.size());
-    uint32_t acap = pow2_at_least(alts.size() * 2 + 2);
-    t->alts.assign(acap, AltSlot{});
-    for (auto &a : alts) {
-        AltSlot s{};
-        s.hash = alt_hash(hash_bytes(a.first.data(), a.first.size()));
+    t->n_nodes = uint32_t(nodes.size());
+    uint32_t ncap = pow2_at_least(nodes.size() * 2 + 2);
+    t->nodes.assign(ncap, NodeSlot{});
+    for (size_t id = 0; id < nodes.size(); ++id) {
+        const std::string &name = nodes[id].first;
+        NodeSlot s{};
+        s.hash = node_hash(hash_bytes(name.data(), name.size()));
         s.name_off = uint32_t(t->blob.size());
-        s.name_len = uint32_t(a.first.size());
-        s.seq_len = a.second;
-        s.used = 1;
-        t->blob.insert(t->blob.end(), a.first.begin(), a.first.end());
+        s.name_len = uint32_t(name.size());
+        s.seq_len = nodes[id].second;
+        s.id1 = uint32_t(id) + 1;
+        // every name starts on a 4-byte boundary and is zero padded: the kernel compares words
+        t->blob.insert(t->blob.end(), name.begin(), name.end());
         t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
         if (t->blob.size() >= 0xFFFF0000ull) {
-            err = "alt-node name blob exceeds 4 GiB";
+            err = "node name blob exceeds 4 GiB";
             return false;
         }
-        uint32_t i = uint32_t(s.hash) & (acap - 1);
-        while (t->alts[i].used) i = (i + 1) & (acap - 1);
-        t->alts[i] = s;
+        uint32_t i = uint32_t(s.hash) & (ncap - 1);
+        while (t->nodes[i].id1) i = (i + 1) & (ncap - 1);
+        t->nodes[i] = s;
     }
     // pad the blob so 4-byte reads at the tail stay in bounds
     t->blob.insert(t->blob.end(), 16, 0);
@@ -595,7 +602,7 @@ extern "C" uint32_t svjg_tables_num_links(const svjg_tables *t) { return t ? t->
 extern "C" uint32_t svjg_tables_num_alt_nodes(const svjg_tables *t) { return t ? t->n_alt : 0; }
 extern "C" uint64_t svjg_tables_device_bytes(const svjg_tables *t) {
     if (!t) return 0;
-    return t->links.size() * sizeof(LinkSlot) + t->alts.size() * sizeof(AltSlot) + t->blob.size() +
+    return t->links.size() * sizeof(LinkSlot) + t->nodes.size() * sizeof(NodeSlot) + t->blob.size() +
            t->entries.size() * sizeof(uint32_t);
 }
 extern "C" const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len) {
