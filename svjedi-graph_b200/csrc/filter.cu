@@ -59,7 +59,10 @@ static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit"
 // shared memory map of ONE warp of scan_parse (bytes)
 constexpr int OFF_WIN = 0;
 constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline positions, ascending  u16[NLCAP]
-constexpr int WARP_SMEM = (OFF_NL + NLCAP * 2 + 127) & ~127;
+constexpr int BMWORDS = NPAIRS + 7;                         // bitmap words: reads may run a few words past the window
+constexpr int OFF_TABB = (OFF_NL + NLCAP * 2 + 15) & ~15;   // tab bitmap        u32[BMWORDS]
+constexpr int OFF_DLB = OFF_TABB + BMWORDS * 4;             // delimiter bitmap  u32[BMWORDS]
+constexpr int WARP_SMEM = (OFF_DLB + BMWORDS * 4 + 127) & ~127;
 constexpr int SMEM_BYTES = WARP_SMEM * WARPS;
 
 constexpr int FLAT_THREADS = 256;              // block size of the flat (grid-stride) kernels
@@ -185,6 +188,9 @@ struct IsNewline {
 };
 struct IsTab {
     __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return eq_bytes(w, 0x09090909u); }
+};
+struct IsDelim {
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return delim_bytes(w); }
 };
 
 __device__ __noinline__ void report(const FilterArgs &a, uint32_t code, uint64_t line_off) {
@@ -684,6 +690,16 @@ __device__ __forceinline__ uint32_t count_nondigits(const uint8_t *win, uint32_t
     return n + __popc(nondigit_bytes(lds32(win, a1)) & him);
 }
 
+// any ',' in window bytes [lo, hi), hi > lo
+__device__ __forceinline__ bool has_comma(const uint8_t *win, uint32_t lo, uint32_t hi) {
+    const uint32_t a0 = lo & ~3u, a1 = (hi - 1u) & ~3u;
+    const uint32_t lom = 0xFFFFFFFFu << (8u * (lo & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((hi - 1u) & 3u)));
+    uint32_t f = eq_bytes(lds32(win, a0), 0x2C2C2C2Cu) & lom;
+    if (a0 == a1) return (f & him) != 0;
+    for (uint32_t a = a0 + 4; a < a1; a += 4) f |= eq_bytes(lds32(win, a), 0x2C2C2C2Cu);
+    return (f | (eq_bytes(lds32(win, a1), 0x2C2C2C2Cu) & him)) != 0;
+}
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -693,10 +709,18 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
+// 32 bits of a byte-indexed bitmap starting at bit `pos`
+__device__ __forceinline__ uint32_t bm_bits(const uint32_t *bm, uint32_t pos) {
+    const uint32_t w = pos >> 5;
+    return __funnelshift_r(bm[w], bm[w + 1], pos & 31u);
+}
+// the low n bits (n may exceed 32 or be <= 0)
+__device__ __forceinline__ uint32_t low_bits(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+
 // ===========================================================================
 // scan_parse: newline scan, column split, validation, path walk
 // ===========================================================================
-__global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
+__global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     __shared__ __align__(8) uint64_t mbars[WARPS];
 
@@ -704,9 +728,12 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint8_t *win = smem_all + warp * WARP_SMEM + OFF_WIN;
     uint16_t *nl = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_NL);
+    uint32_t *tabb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_TABB);   // bit i: window byte i is a tab
+    uint32_t *dlb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_DLB);     // bit i: ... is '<' or '>'
     uint64_t *mbar = &mbars[warp];
 
     if (lane == 0) mbar_init(mbar, 1);
+    for (int i = NPAIRS + lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0;
     __syncwarp();
     uint32_t phase = 0;
     Local loc;
@@ -739,8 +766,9 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
         }
         __syncwarp();
 
-        // ---- phase A: ordered list of the newline positions from HEAD-1 on.  A lane takes two
-        // adjacent 16-byte chunks; the scan stops behind the tile once the last owned line has its end.
+        // ---- phase A: byte classes.  A lane takes two adjacent 16-byte chunks = one word of each bitmap.
+        // Newlines become the ordered list of line ends from HEAD-1 on; tabs and path delimiters stay
+        // bitmaps.  The scan stops behind the tile once the last owned line has its end.
         const uint32_t own_end = min(uint32_t(HEAD + TILE), valid_end);   // lines starting before own_end are ours
         uint32_t n_nl = 0, n_own = 0;
         for (int c0 = 0; c0 < NPAIRS; c0 += 32) {
@@ -752,6 +780,8 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(win + p0);
                 const uint4 v1 = *reinterpret_cast<const uint4 *>(win + p0 + 16);
                 m = mask16(v0, IsNewline()) | (mask16(v1, IsNewline()) << 16);
+                tabb[c] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
+                dlb[c] = mask16(v0, IsDelim()) | (mask16(v1, IsDelim()) << 16);
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
             }
             const uint32_t cnt = __popc(m);
@@ -767,8 +797,7 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
                 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
             // newline at p starts an owned line iff p + 1 < own_end
-            const int hi = int(own_end) - 1 - int(p0);
-            const uint32_t mo = hi >= 32 ? m : (hi <= 0 ? 0u : (m & ((1u << hi) - 1u)));
+            const uint32_t mo = m & low_bits(int(own_end) - 1 - int(p0));
             n_own += __reduce_add_sync(0xFFFFFFFFu, uint32_t(__popc(mo)));
             uint32_t idx = n_nl + q;
             while (m) {
@@ -787,7 +816,7 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
             __syncwarp();
             continue;
         }
-        // ---- phase B: one lane per line
+        // ---- phase B: one lane per line, mostly bit work on the class bitmaps
         for (uint32_t k0 = 0; k0 < n_own; k0 += 32) {
             const uint32_t k = k0 + lane;
             uint32_t want = 0;                 // path nodes of a plain line with >= 2 of them
@@ -806,85 +835,15 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
                     exact = true;              // runs past the window
                 }
                 if (!exact) {
-                    // columns 1-5: tab bitmap of the first HEAD_SPAN bytes (fixed trip count: lanes stay together)
                     bool plain = e > s && !py_space(win[e - 1]);
-                    uint32_t p1, p2, p3, p4, p5;
+                    // columns 1-6: the first six tabs among the first HEAD_SPAN bytes (positions relative to s,
+                    // one byte each, newest in the low byte)
+                    uint32_t r0 = 0, r1 = 0, nt = 0;
                     {
-                        const uint32_t base = s & ~15u;
-                        uint32_t tm[HEAD_SPAN / 32];
+                        const int nbits = int(e - s);
 #pragma unroll
                         for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                            const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
-                            const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
-                            tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                        }
-                        tm[0] &= 0xFFFFFFFFu << (s - base);
-                        const uint32_t rel_e = e - base;
-#pragma unroll
-                        for (int j = 0; j < HEAD_SPAN / 32; ++j)
-                            if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
-                        // the first 5 tab positions (relative to base), one byte each, newest in the low byte
-                        uint32_t r0 = 0, r1 = 0, nt = 0;
-#pragma unroll
-                        for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                            uint32_t m = tm[j];
-                            while (m && nt < 5) {
-                                const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                                m &= m - 1;
-                                r1 = __funnelshift_l(r0, r1, 8);
-                                r0 = (r0 << 8) | pos;
-                                ++nt;
-                            }
-                        }
-                        plain &= nt == 5;
-                        p1 = base + (r1 & 255u), p2 = base + (r0 >> 24), p3 = base + ((r0 >> 16) & 255u);
-                        p4 = base + ((r0 >> 8) & 255u), p5 = base + (r0 & 255u);
-                    }
-                    // column 6, the path [ps, pe): walk to its tab; count token starts (a non-delimiter byte
-                    // right after a delimiter) and look for ',' on the way
-                    ps = p5 + 1;
-                    pe = e;
-                    uint32_t ntok = 0, comma = 0;
-                    if (plain) {
-                        uint32_t carry = 0;   // delimiter flag of the byte in front of the word, at bit 7
-                        uint32_t keep = 0xFFFFFFFFu << (8u * (ps & 3u));
-                        for (uint32_t w0 = ps & ~3u; w0 < e; w0 += 4) {
-                            const uint32_t w = lds32(win, w0);
-                            const uint32_t tb = eq_bytes(w, 0x09090909u) & keep;
-                            const uint32_t d = delim_bytes(w);
-                            if (tb) {
-                                const uint32_t j = uint32_t(__ffs(tb) - 1) >> 3;          // byte of the tab in this word
-                                pe = w0 + j;
-                                keep &= j ? (0xFFFFFFFFu >> (8u * (4u - j))) : 0u;
-                            }
-                            ntok += __popc(((d << 8) | carry) & ~d & SVJG_H8 & keep);
-                            comma |= eq_bytes(w, 0x2C2C2C2Cu) & keep;
-                            if (tb) break;
-                            carry = d >> 24;
-                            keep = 0xFFFFFFFFu;
-                        }
-                        plain = pe < e && pe > ps;
-                    }
-                    // columns 7-12: tab bitmap of the TAIL_SPAN bytes around the end of the path
-                    if (plain) {
-                        const uint32_t p6 = pe;
-                        const uint32_t base = p6 & ~15u;
-                        uint32_t tm[TAIL_SPAN / 32];
-#pragma unroll
-                        for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                            const uint4 v0 = *reinterpret_cast<const uint4 *>(win + base + 32 * j);
-                            const uint4 v1 = *reinterpret_cast<const uint4 *>(win + base + 32 * j + 16);
-                            tm[j] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                        }
-                        tm[0] &= 0xFFFFFFFEu << (p6 - base);                               // tabs after p6
-                        const uint32_t rel_e = e - base;
-#pragma unroll
-                        for (int j = 0; j < TAIL_SPAN / 32; ++j)
-                            if (rel_e < 32u * (j + 1)) tm[j] = rel_e <= 32u * j ? 0u : (tm[j] & ((1u << (rel_e - 32u * j)) - 1u));
-                        uint32_t r0 = 0, r1 = 0, nt = 0;
-#pragma unroll
-                        for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                            uint32_t m = tm[j];
+                            uint32_t m = bm_bits(tabb, s + 32u * j) & low_bits(nbits - 32 * j);
                             while (m && nt < 6) {
                                 const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
                                 m &= m - 1;
@@ -893,33 +852,79 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
                                 ++nt;
                             }
                         }
-                        if (nt == 5 && rel_e <= TAIL_SPAN) {                               // no tab after column 12
-                            r1 = __funnelshift_l(r0, r1, 8);
-                            r0 = (r0 << 8) | rel_e;
-                            ++nt;
+                    }
+                    // a long path pushes its tab out of the span: five tabs found, look for the sixth
+                    uint32_t p6 = e;
+                    if (nt == 6) {
+                        p6 = s + (r0 & 255u);
+                    } else if (nt == 5) {
+                        r1 = __funnelshift_l(r0, r1, 8);
+                        r0 <<= 8;
+                        for (uint32_t q = s + HEAD_SPAN; q < e; q += 32) {
+                            const uint32_t m = bm_bits(tabb, q) & low_bits(int(e - q));
+                            if (m) {
+                                p6 = q + uint32_t(__ffs(m) - 1);
+                                break;
+                            }
                         }
-                        plain = nt == 6;
-                        const uint32_t p7 = base + ((r1 >> 8) & 255u), p8 = base + (r1 & 255u), p9 = base + (r0 >> 24),
-                                       p10 = base + ((r0 >> 16) & 255u), p11 = base + ((r0 >> 8) & 255u),
-                                       p12 = base + (r0 & 255u);
-                        if (plain) {
-                            // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
-                            const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) &
-                                              (p8 - p7 > 1u) & (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) &
-                                              (p12 - p11 > 1u);
-                            plain = w_ok && win[p10 + 1] != '0';
-                            if (plain)
-                                plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
+                    }
+                    plain &= nt >= 5 && p6 < e;
+                    const uint32_t p1 = s + ((r1 >> 8) & 255u), p2 = s + (r1 & 255u), p3 = s + (r0 >> 24),
+                                   p4 = s + ((r0 >> 16) & 255u), p5 = s + ((r0 >> 8) & 255u);
+                    ps = p5 + 1;
+                    pe = p6;
+                    plain &= pe > ps;
+                    // columns 7-12: the next six tabs (or five and the end of the line) within TAIL_SPAN bytes
+                    uint32_t p7 = 0, p8 = 0, p9 = 0, p10 = 0, p11 = 0, p12 = 0;
+                    if (plain) {
+                        const uint32_t t0 = p6 + 1;
+                        const int nbits = int(e - t0);
+                        uint32_t q0 = 0, q1 = 0, n2 = 0;
+#pragma unroll
+                        for (int j = 0; j < TAIL_SPAN / 32; ++j) {
+                            uint32_t m = bm_bits(tabb, t0 + 32u * j) & low_bits(nbits - 32 * j);
+                            while (m && n2 < 6) {
+                                const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
+                                m &= m - 1;
+                                q1 = __funnelshift_l(q0, q1, 8);
+                                q0 = (q0 << 8) | pos;
+                                ++n2;
+                            }
                         }
+                        if (n2 == 5 && nbits <= TAIL_SPAN) {                               // no tab after column 12
+                            q1 = __funnelshift_l(q0, q1, 8);
+                            q0 = (q0 << 8) | uint32_t(nbits);
+                            ++n2;
+                        }
+                        plain = n2 == 6;
+                        p7 = t0 + ((q1 >> 8) & 255u), p8 = t0 + (q1 & 255u), p9 = t0 + (q0 >> 24);
+                        p10 = t0 + ((q0 >> 16) & 255u), p11 = t0 + ((q0 >> 8) & 255u), p12 = t0 + (q0 & 255u);
+                    }
+                    if (plain) {
+                        // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
+                        const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) &
+                                          (p8 - p7 > 1u) & (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) &
+                                          (p12 - p11 > 1u);
+                        plain = w_ok && win[p10 + 1] != '0';
+                        if (plain) plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
                     }
                     if (!plain) {
                         exact = true;
                     } else if (!is_delim(win[ps])) {
                         // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
-                        exact = comma != 0;
-                    } else if (ntok >= 2) {                                                // :133
-                        if (a.flags & FLAG_FORCE_GENERAL) exact = true;
-                        else want = ntok;
+                        exact = has_comma(win, ps, pe);
+                    } else {
+                        // token starts: a non-delimiter byte right after a delimiter
+                        uint32_t ntok = 0, carry = 0;
+                        for (uint32_t q = ps; q < pe; q += 32) {
+                            const uint32_t d = bm_bits(dlb, q);
+                            ntok += __popc(((d << 1) | carry) & ~d & low_bits(int(pe - q)));
+                            carry = d >> 31;
+                        }
+                        if (ntok >= 2) {                                                   // :133
+                            if (a.flags & FLAG_FORCE_GENERAL) exact = true;
+                            else want = ntok;
+                        }
                     }
                 }
             }
@@ -956,22 +961,19 @@ __global__ void __launch_bounds__(THREADS, 8) scan_parse_kernel(const __grid_con
                     L.flags = has_nl ? LF_HAS_NL : 0;
                     L.pad = 0;
                     a.sc.ml[li] = L;
-                    // token records: maximal runs of non-delimiter bytes, from the start / end flags
-                    const uint32_t a0 = ps & ~3u, a1 = (pe - 1u) & ~3u;
-                    const uint32_t lom = 0xFFFFFFFFu << (8u * (ps & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((pe - 1u) & 3u)));
+                    // token records: maximal runs of non-delimiter bytes, from the start / end bits
                     uint32_t t = t0, cur = 0xFFFFFFFFu, carry = 0;
-                    for (uint32_t w0 = a0; w0 <= a1; w0 += 4) {
-                        const uint32_t d = delim_bytes(lds32(win, w0));
-                        const uint32_t pd = (d << 8) | carry;                       // "previous byte is a delimiter"
-                        uint32_t st = pd & ~d & SVJG_H8, en = d & ~pd & SVJG_H8;
-                        if (w0 == a0) st &= lom, en &= lom;
-                        if (w0 == a1) st &= him, en &= him;
-                        carry = d >> 24;
+                    for (uint32_t q = ps; q < pe; q += 32) {
+                        const uint32_t d = bm_bits(dlb, q);
+                        const uint32_t pd = (d << 1) | carry;                       // "previous byte is a delimiter"
+                        const uint32_t keep = low_bits(int(pe - q));
+                        const uint32_t st = pd & ~d & keep, en = d & ~pd & keep;
+                        carry = d >> 31;
                         uint32_t ev = st | en;
                         while (ev) {
                             const uint32_t bit = uint32_t(__ffs(ev) - 1);
                             ev &= ev - 1;
-                            const uint32_t pos = w0 + (bit >> 3);
+                            const uint32_t pos = q + bit;
                             if ((st >> bit) & 1u) {
                                 cur = pos;
                                 a.sc.tk_b[t] = wbase + pos;
