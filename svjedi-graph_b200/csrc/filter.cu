@@ -89,8 +89,9 @@ struct GLine {
     uint32_t tok0, ntok;  // tokens [tok0, tok0 + ntok); ntok == 0 marks a slot that was given up
     uint32_t flags;
     uint32_t pad;
+    int64_t ts, tail;     // Ts and Tlen - Te - 1 (check_bkpt_overlap :260-261)
 };
-static_assert(sizeof(GLine) == 32, "GLine is one sector");
+static_assert(sizeof(GLine) == 48, "GLine is 48 bytes");
 
 // device scratch of one svjg_filter_device() call
 struct Scratch {
@@ -822,6 +823,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
             uint32_t want = 0;                 // path nodes of a plain line with >= 2 of them
             bool exact = false;                // the line must take the exact route
             uint32_t s = 0, e = 0, ps = 0, pe = 0;
+            int64_t c_ts = 0, c_tail = 0;
             bool has_nl = false;
             if (k < n_own) {
                 s = uint32_t(nl[k]) + 1u;
@@ -922,7 +924,27 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                             carry = d >> 31;
                         }
                         if (ntok >= 2) {                                                   // :133
-                            if (a.flags & FLAG_FORCE_GENERAL) exact = true;
+                            // Tlen, Ts, Te: digit-only columns 7-9; the reference has bigints, this route stops
+                            // at 18 digits and leaves longer ones to the exact route (which reports them)
+                            int64_t v[3];
+                            uint32_t q = p6 + 1, too_long = 0;
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                int64_t x = 0;
+                                uint32_t nd = 0;
+                                for (;; ++q) {
+                                    const uint32_t d = uint32_t(win[q]) - '0';
+                                    if (d > 9) break;
+                                    nd += (x != 0 || d != 0);
+                                    x = x * 10 + int64_t(d);
+                                }
+                                too_long |= nd > 18;
+                                v[j] = x;
+                                ++q;
+                            }
+                            c_ts = v[1];
+                            c_tail = v[0] - v[2] - 1;
+                            if ((a.flags & FLAG_FORCE_GENERAL) || too_long) exact = true;
                             else want = ntok;
                         }
                     }
@@ -960,6 +982,8 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                     L.ntok = want;
                     L.flags = has_nl ? LF_HAS_NL : 0;
                     L.pad = 0;
+                    L.ts = c_ts;
+                    L.tail = c_tail;
                     a.sc.ml[li] = L;
                     // token records: maximal runs of non-delimiter bytes, from the start / end bits
                     uint32_t t = t0, cur = 0xFFFFFFFFu, carry = 0;
@@ -1013,30 +1037,72 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
     for (uint32_t t = blockIdx.x * FLAT_THREADS + threadIdx.x; t < n_tok; t += gridDim.x * FLAT_THREADS) {
         if (a.sc.tk_line[t] == NO_LINE) continue;
         const uint32_t b = a.sc.tk_b[t], l = a.sc.tk_l[t];
-        // name hash, 4 bytes a step, and the colons on the way
+        // name hash (4 bytes a step), the colons on the way, and the name's node id (with the alt
+        // sequence length): the one byte-exact name check of the chain
         const uint64_t al = uint64_t(b) & ~3ull;
         const uint32_t sh = (b & 3u) * 8u;
-        uint32_t curw = gaf_word(a, al);
         TokHash h = tok_init();
         uint32_t ncolon = 0, cpos = 0;
-        for (uint32_t i = 0; i < l; i += 4) {
-            const uint32_t nxt = gaf_word(a, al + i + 4);
-            uint32_t w = __funnelshift_r(curw, nxt, sh);
-            curw = nxt;
-            const uint32_t rem = l - i;
-            if (rem < 4) w &= (1u << (8 * rem)) - 1u;
-            tok_step(h, w);
-            const uint32_t f = eq_bytes(w, 0x3A3A3A3Au);
-            if (f) {
-                ncolon += __popc(f);
-                cpos = i + ((31 - __clz(f)) >> 3);
-            }
-        }
-        const uint64_t hv = tok_value(h, l);
-        // the name's node id (and alt sequence length): the one byte-exact name check of the chain
         uint32_t nid = NO_NODE;
         int64_t seq_len = -1;
-        {
+        uint64_t hv;
+        if (l <= 32 && al + 40 <= a.n) {
+            // the usual case: the whole name in registers, every load in flight at once
+            const uint32_t nw = (l + 3u) >> 2;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a.gaf + al);
+            uint32_t raw[9], w[8];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) raw[k] = uint32_t(k) <= nw ? __ldg(wp + k) : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                w[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+                if (uint32_t(k) == nw - 1 && (l & 3u)) w[k] &= (1u << (8u * (l & 3u))) - 1u;
+                if (uint32_t(k) < nw) {
+                    tok_step(h, w[k]);
+                    const uint32_t f = eq_bytes(w[k], 0x3A3A3A3Au);
+                    if (f) {
+                        ncolon += __popc(f);
+                        cpos = 4u * k + ((31 - __clz(f)) >> 3);
+                    }
+                }
+            }
+            hv = tok_value(h, l);
+            const uint64_t nh = node_hash(hv);
+            uint32_t i = uint32_t(nh) & a.tb.node_mask;
+            for (;;) {
+                const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.nodes + i);
+                const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+                if (!hi.z) break;
+                if (((uint64_t(lo.y) << 32) | lo.x) == nh && lo.w == l) {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(a.tb.blob + lo.z);
+                    uint32_t diff = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (uint32_t(k) < nw) diff |= w[k] ^ __ldg(q + k);
+                    if (diff == 0) {
+                        nid = hi.z - 1u;
+                        seq_len = int64_t((uint64_t(hi.y) << 32) | hi.x);
+                        break;
+                    }
+                }
+                i = (i + 1) & a.tb.node_mask;
+            }
+        } else {
+            uint32_t curw = gaf_word(a, al);
+            for (uint32_t i = 0; i < l; i += 4) {
+                const uint32_t nxt = gaf_word(a, al + i + 4);
+                uint32_t w = __funnelshift_r(curw, nxt, sh);
+                curw = nxt;
+                const uint32_t rem = l - i;
+                if (rem < 4) w &= (1u << (8 * rem)) - 1u;
+                tok_step(h, w);
+                const uint32_t f = eq_bytes(w, 0x3A3A3A3Au);
+                if (f) {
+                    ncolon += __popc(f);
+                    cpos = i + ((31 - __clz(f)) >> 3);
+                }
+            }
+            hv = tok_value(h, l);
             Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, 0, 0, loc);
             Rec<GmemSrc>::Tok tk{b, l};
             if (!rec.node_find(hv, tk, nid, seq_len)) nid = NO_NODE, seq_len = -1;
@@ -1080,54 +1146,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
         a.sc.tk_len[t] = int32_t(nlen);
         a.sc.tk_sval[t] = sval;
         a.sc.tk_flags[t] = uint8_t(fl);
-    }
-}
-
-// ===========================================================================
-// line: one thread per multi-node line — coordinates, sums, overlap verdicts
-// ===========================================================================
-__global__ void __launch_bounds__(FLAT_THREADS) line_kernel(const __grid_constant__ FilterArgs a) {
-    const uint32_t n_ml = min(a.sc.cnt[0], a.sc.cap_ml);
-    for (uint32_t k = blockIdx.x * FLAT_THREADS + threadIdx.x; k < n_ml; k += gridDim.x * FLAT_THREADS) {
-        const GLine L = a.sc.ml[k];
-        if (L.ntok == 0) continue;
-        // Tlen, Ts, Te: digit-only columns 7-9 (validated by scan_parse)
-        int64_t v[3];
-        uint32_t q = L.pe + 1, too_long = 0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            int64_t x = 0;
-            uint32_t nd = 0;
-            for (;; ++q) {
-                const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
-                if (d > 9) break;
-                nd += (x != 0 || d != 0);
-                x = x * 10 + int64_t(d);
-            }
-            too_long |= nd > 18;
-            v[j] = x;
-            ++q;
-        }
-        if (too_long) {
-            // the reference has bigints; this implementation stops at 18 digits and says so
-            report(a, SVJG_BAD_RANGE, L.s);
-            a.sc.ml[k].flags = L.flags | LF_SKIP;
-            continue;
-        }
-        const int64_t ts = v[1], tail = v[0] - v[2] - 1;
-        uint32_t bad = 0;
-        int64_t total = 0;
-        for (uint32_t t = L.tok0; t < L.tok0 + L.ntok; ++t) {
-            bad |= !(a.sc.tk_flags[t] & TF_PLAIN);
-            total += a.sc.tk_len[t];
-        }
-        int64_t pre = a.sc.tk_len[L.tok0];
-        for (uint32_t t = L.tok0 + 1; t < L.tok0 + L.ntok; ++t) {
-            const bool ok = (pre - ts >= a.d_over) && (total - pre - tail >= a.d_over);   // :269-273
-            if (ok) a.sc.tk_flags[t] |= TF_OK;
-            pre += a.sc.tk_len[t];
-        }
-        if (bad) a.sc.ml[k].flags = L.flags | LF_GENERAL;
+        if (!(fl & TF_PLAIN)) atomicOr(&a.sc.ml[a.sc.tk_line[t]].flags, LF_GENERAL);   // odd name: general() decides
     }
 }
 
@@ -1174,8 +1193,15 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
                 // the exact kernel runs general() on it; the first node's thread hands the line over
                 if (t == L.tok0) a.sc.general[atomicAdd(a.sc.cnt + 3, 1u)] = li;
             } else if (t != L.tok0) {
+                // node lengths left of the link and in total; check_bkpt_overlap (:269-273)
+                int64_t pre = 0, total = 0;
+                for (uint32_t j = L.tok0; j < L.tok0 + L.ntok; ++j) {
+                    const int64_t nlen = a.sc.tk_len[j];
+                    total += nlen;
+                    if (j < t) pre += nlen;
+                }
+                const bool ok = (pre - L.ts >= a.d_over) && (total - pre - L.tail >= a.d_over);
                 const uint32_t fb = a.sc.tk_flags[t];
-                const bool ok = fb & TF_OK;
                 if (ok || all_links) {
                     Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
                     rec.stage_sv = h_sv;
@@ -1348,10 +1374,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     const int flat_grid = g_sms * 8;
     scan_parse_kernel<<<scan_grid, THREADS, SMEM_BYTES, st>>>(a);
     if (stop == 0 || stop >= 3) token_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
-    if (stop == 0 || stop >= 4) {
-        line_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
-        clash_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
-    }
+    if (stop == 0 || stop >= 4) clash_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
     if (stop == 0) {
         link_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
         exact_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
