@@ -75,7 +75,6 @@ constexpr uint32_t COMMA_PATH = 0xFFFFFFFFu;
 constexpr uint32_t TF_PLUS = 1;     // delimiter in front is '>'
 constexpr uint32_t TF_ALT = 2;      // chrom:pos.k (length from the GFA)
 constexpr uint32_t TF_PLAIN = 4;    // exactly one ':', digits-digits or digits.<anything>, length > 0
-constexpr uint32_t TF_OK = 8;       // overlap verdict of the link (previous node, this node)
 // line flags
 constexpr uint32_t LF_GENERAL = 1;  // must go through general()
 constexpr uint32_t LF_HAS_NL = 2;   // the line ends in a newline (it counts in the hit's length)
@@ -716,7 +715,7 @@ __device__ __forceinline__ uint32_t bm_bits(const uint32_t *bm, uint32_t pos) {
     return __funnelshift_r(bm[w], bm[w + 1], pos & 31u);
 }
 // the low n bits (n may exceed 32 or be <= 0)
-__device__ __forceinline__ uint32_t low_bits(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+__device__ __forceinline__ uint32_t low_bits(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, uint32_t(max(n, 0))); }
 
 // ===========================================================================
 // scan_parse: newline scan, column split, validation, path walk
@@ -823,7 +822,6 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
             uint32_t want = 0;                 // path nodes of a plain line with >= 2 of them
             bool exact = false;                // the line must take the exact route
             uint32_t s = 0, e = 0, ps = 0, pe = 0;
-            int64_t c_ts = 0, c_tail = 0;
             bool has_nl = false;
             if (k < n_own) {
                 s = uint32_t(nl[k]) + 1u;
@@ -924,27 +922,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                             carry = d >> 31;
                         }
                         if (ntok >= 2) {                                                   // :133
-                            // Tlen, Ts, Te: digit-only columns 7-9; the reference has bigints, this route stops
-                            // at 18 digits and leaves longer ones to the exact route (which reports them)
-                            int64_t v[3];
-                            uint32_t q = p6 + 1, too_long = 0;
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                int64_t x = 0;
-                                uint32_t nd = 0;
-                                for (;; ++q) {
-                                    const uint32_t d = uint32_t(win[q]) - '0';
-                                    if (d > 9) break;
-                                    nd += (x != 0 || d != 0);
-                                    x = x * 10 + int64_t(d);
-                                }
-                                too_long |= nd > 18;
-                                v[j] = x;
-                                ++q;
-                            }
-                            c_ts = v[1];
-                            c_tail = v[0] - v[2] - 1;
-                            if ((a.flags & FLAG_FORCE_GENERAL) || too_long) exact = true;
+                            if (a.flags & FLAG_FORCE_GENERAL) exact = true;
                             else want = ntok;
                         }
                     }
@@ -982,8 +960,8 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                     L.ntok = want;
                     L.flags = has_nl ? LF_HAS_NL : 0;
                     L.pad = 0;
-                    L.ts = c_ts;
-                    L.tail = c_tail;
+                    L.ts = 0;
+                    L.tail = 0;
                     a.sc.ml[li] = L;
                     // token records: maximal runs of non-delimiter bytes, from the start / end bits
                     uint32_t t = t0, cur = 0xFFFFFFFFu, carry = 0;
@@ -1035,8 +1013,16 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
     const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
     Local loc;
     for (uint32_t t = blockIdx.x * FLAT_THREADS + threadIdx.x; t < n_tok; t += gridDim.x * FLAT_THREADS) {
-        if (a.sc.tk_line[t] == NO_LINE) continue;
+        const uint32_t li = a.sc.tk_line[t];
+        if (li == NO_LINE) continue;
         const uint32_t b = a.sc.tk_b[t], l = a.sc.tk_l[t];
+        // the first node's thread will read columns 7-9 at the end: start fetching them now
+        const bool first = t == a.sc.ml[li].tok0;
+        const uint32_t coords = first ? a.sc.ml[li].pe + 1 : 0;
+        if (first) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gaf + coords));
+            if (uint64_t(coords) + 32 < a.n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gaf + coords + 32));
+        }
         // name hash (4 bytes a step), the colons on the way, and the name's node id (with the alt
         // sequence length): the one byte-exact name check of the chain
         const uint64_t al = uint64_t(b) & ~3ull;
@@ -1146,7 +1132,33 @@ __global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_consta
         a.sc.tk_len[t] = int32_t(nlen);
         a.sc.tk_sval[t] = sval;
         a.sc.tk_flags[t] = uint8_t(fl);
-        if (!(fl & TF_PLAIN)) atomicOr(&a.sc.ml[a.sc.tk_line[t]].flags, LF_GENERAL);   // odd name: general() decides
+        if (!(fl & TF_PLAIN)) atomicOr(&a.sc.ml[li].flags, LF_GENERAL);   // odd name: general() decides
+        if (first) {
+            // the first node's thread also reads Tlen, Ts, Te: digit-only columns 7-9 (validated by
+            // scan_parse).  The reference has bigints; this route stops at 18 digits and says so.
+            int64_t v[3];
+            uint32_t q = coords, too_long = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                int64_t x = 0;
+                uint32_t nd = 0;
+                for (;; ++q) {
+                    const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
+                    if (d > 9) break;
+                    nd += (x != 0 || d != 0);
+                    x = x * 10 + int64_t(d);
+                }
+                too_long |= nd > 18;
+                v[j] = x;
+                ++q;
+            }
+            a.sc.ml[li].ts = v[1];
+            a.sc.ml[li].tail = v[0] - v[2] - 1;
+            if (too_long) {
+                report(a, SVJG_BAD_RANGE, a.sc.ml[li].s);
+                atomicOr(&a.sc.ml[li].flags, LF_SKIP);
+            }
+        }
     }
 }
 
