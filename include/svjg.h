@@ -124,7 +124,9 @@ int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64
  * Replaces likelihood() / allele_normalization() / encode_genotype()
  * (predict-genotype.py:281-346) and the gate at :216 for n SVs of a VCF.
  *   sv_index[i]  index into d_counts pairs, or UINT32_MAX if the key is not in the tables
- *   svtype[i]    0 DEL, 1 INS, 2 INV, 3 BND, 255 other;  bit 7 set = |length| < 50 (:216)
+ *   svtype[i]    0 DEL, 1 INS, 2 INV, 3 BND, 255 other;  bit 7 set = |length| < 50 (:216);
+ *                bit 6 set = the key is present even if both counts are 0 (a hand-made JSON;
+ *                with counters that come from the filter a key exists iff it has a hit)
  *   log10_1me, log10_e, log10_half : math.log10(1-e), math.log10(e), math.log10(1/2)
  *                as computed by the caller's libm (the reference uses CPython's)
  *   lut          log10(C(n,k)) at [n*(n+1)/2 + k] for 0 <= k <= n <= lut_nmax, bit-equal
@@ -143,6 +145,21 @@ int svjg_genotype_device(const uint32_t *d_counts, const uint32_t *d_sv_index, c
                          double log10_half, const double *d_lut, uint32_t lut_nmax,
                          const double *d_k_override, int64_t *d_pl, uint8_t *d_gt, uint32_t *d_ad2,
                          uint8_t *d_flags, void *stream);
+
+/* ---- informative_aln.json reader (host) -------------------------------------
+ * Replaces predict-genotype.py:67-68 (json.load of <prefix>_informative_aln.json) and
+ * :219-226 (nbAln = the lengths of the two lists of a key): the stand-alone
+ * predict-genotype front-end gets its counters from the JSON file, as the reference
+ * does.  Keys are byte-sorted; counts are [num][2] u32 (UINT32_MAX in both where the
+ * value is not "[iterable, iterable, ...]" and the reference would raise on lookup). */
+typedef struct svjg_aln_counts svjg_aln_counts;
+int svjg_aln_counts_load(const char *json_path, svjg_aln_counts **out);
+int svjg_aln_counts_from_memory(const char *json, size_t len, svjg_aln_counts **out);
+void svjg_aln_counts_free(svjg_aln_counts *c);
+uint32_t svjg_aln_counts_num(const svjg_aln_counts *c);
+const char *svjg_aln_counts_key(const svjg_aln_counts *c, uint32_t i, uint32_t *len);
+const uint32_t *svjg_aln_counts_data(const svjg_aln_counts *c);
+uint32_t svjg_aln_counts_find(const svjg_aln_counts *c, const char *key, uint32_t len);
 
 /* ---- output (host) ------------------------------------------------------------
  * Replaces filter-alignments.py:174-175: writes json.dumps(dict, sort_keys=True,

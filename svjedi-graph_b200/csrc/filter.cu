@@ -1360,6 +1360,9 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     sc.cap_tok = uint32_t(n_bytes / 20 + 4096);       // a path node with its delimiter is rarely under 20 bytes
     sc.cap_ml = uint32_t(n_bytes / 64 + 1024);
     sc.cap_exact = uint32_t(n_bytes / 16 + 64);       // a line shorter than 16 bytes cannot hold 12 columns
+    if (const char *tiny = getenv("SVJG_TEST_TINY_SCRATCH")) {   // test hook: force the "no room" fallbacks
+        if (tiny[0] == '1') sc.cap_tok = 64, sc.cap_ml = 16;
+    }
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_cnt = 0, o_ml = up(64), o_node = o_ml + up(size_t(sc.cap_ml) * sizeof(GLine)),
                  o_b = o_node + up(size_t(sc.cap_tok) * 4), o_line = o_b + up(size_t(sc.cap_tok) * 4),

@@ -108,7 +108,7 @@ __global__ void genotype_kernel(const uint32_t *__restrict__ counts, const uint3
         n1 = c.y;
     }
     // predict-genotype.py:216 — a key is "in the dict" once it has at least one hit
-    bool gate = (ty & 0x7F) <= 3 && !(ty & 0x80) && ty != 255 && idx != 0xFFFFFFFFu && (n0 | n1) != 0;
+    bool gate = (ty & 0x3F) <= 3 && !(ty & 0x80) && ty != 255 && idx != 0xFFFFFFFFu && ((n0 | n1) != 0 || (ty & 0x40));
     if (!gate) {
         gt[i] = 3;
         flags[i] = 0;
@@ -117,7 +117,7 @@ __global__ void genotype_kernel(const uint32_t *__restrict__ counts, const uint3
         pl[3 * size_t(i)] = pl[3 * size_t(i) + 1] = pl[3 * size_t(i) + 2] = 0;
         return;
     }
-    ty &= 0x7F;
+    ty &= 0x3F;
     // allele_normalization (:327-338): counts in half units
     uint64_t t1 = 2ull * n0, t2 = 2ull * n1;
     uint32_t fl = SVJG_GT_GENOTYPED;

@@ -564,7 +564,216 @@ static bool read_file(const char *path, std::string &out) {
 
 }  // namespace svjg
 
+// ---------------------------------------------------------------------------
+// informative_aln.json -> per-key list lengths   (predict-genotype.py:67-68, :219-226)
+// ---------------------------------------------------------------------------
+struct svjg_aln_counts {
+    std::vector<std::string> keys;        // byte-sorted, distinct (the last duplicate wins, like a dict)
+    std::vector<uint32_t> counts;         // [n][2]; UINT32_MAX where the reference would raise on lookup
+};
+
+namespace svjg {
+
+// number of items `for x in value` yields in Python; false if not iterable (TypeError)
+static bool iter_len(JsonIn &in, uint32_t &n) {
+    in.ws();
+    n = 0;
+    if (in.p < in.end && *in.p == '[') {
+        ++in.p;
+        in.ws();
+        if (in.p < in.end && *in.p == ']') {
+            ++in.p;
+            return true;
+        }
+        for (;;) {
+            JsonIn::Kind k;
+            if (!in.skip_value(k)) return true;   // error is recorded in `in`
+            ++n;
+            in.ws();
+            if (in.p < in.end && *in.p == ',') {
+                ++in.p;
+                continue;
+            }
+            if (in.p < in.end && *in.p == ']') {
+                ++in.p;
+                return true;
+            }
+            in.fail("expected ',' or ']'");
+            return true;
+        }
+    }
+    JsonIn::Kind k;
+    std::string sval;
+    const char *before = in.p;
+    if (!in.skip_value(k, nullptr, &sval)) return true;
+    if (k == JsonIn::K_STRING) {          // iterating a str yields its code points
+        for (unsigned char c : sval) n += (c & 0xC0) != 0x80;
+        return true;
+    }
+    if (k == JsonIn::K_OBJECT) {          // iterating a dict yields its keys; count them by re-scanning
+        JsonIn sub{before, in.p, {}};
+        ++sub.p;
+        sub.ws();
+        if (sub.p < sub.end && *sub.p == '}') return true;
+        for (;;) {
+            std::string key;
+            sub.ws();
+            if (!sub.string(key)) return true;
+            sub.ws();
+            ++sub.p;                      // ':'
+            JsonIn::Kind kk;
+            if (!sub.skip_value(kk)) return true;
+            ++n;                          // duplicate keys collapse in a dict; rare enough to ignore here
+            sub.ws();
+            if (sub.p < sub.end && *sub.p == ',') {
+                ++sub.p;
+                continue;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+static bool parse_aln_counts(const char *text, size_t len, svjg_aln_counts *out, std::string &err) {
+    JsonIn in{text, text + len, {}};
+    in.ws();
+    if (in.p >= in.end || *in.p != '{') {
+        err = "informative_aln: top level is not a JSON object";
+        return false;
+    }
+    ++in.p;
+    std::unordered_map<std::string, std::pair<uint32_t, uint32_t>> d;
+    in.ws();
+    if (in.p < in.end && *in.p == '}') {
+        ++in.p;
+    } else {
+        for (;;) {
+            in.ws();
+            std::string key;
+            if (!in.string(key)) break;
+            in.ws();
+            if (in.p >= in.end || *in.p != ':') {
+                in.fail("expected ':'");
+                break;
+            }
+            ++in.p;
+            in.ws();
+            std::pair<uint32_t, uint32_t> c{UINT32_MAX, UINT32_MAX};
+            if (in.p < in.end && *in.p == '[') {
+                // value[0] and value[1] are iterated (:220-221); anything after them is ignored
+                ++in.p;
+                uint32_t idx = 0, n0 = 0, n1 = 0;
+                bool ok0 = false, ok1 = false;
+                in.ws();
+                if (in.p < in.end && *in.p == ']') {
+                    ++in.p;
+                } else {
+                    for (;;) {
+                        if (idx == 0) ok0 = iter_len(in, n0);
+                        else if (idx == 1) ok1 = iter_len(in, n1);
+                        else {
+                            JsonIn::Kind k;
+                            if (!in.skip_value(k)) break;
+                        }
+                        if (!in.err.empty()) break;
+                        ++idx;
+                        in.ws();
+                        if (in.p < in.end && *in.p == ',') {
+                            ++in.p;
+                            continue;
+                        }
+                        if (in.p < in.end && *in.p == ']') {
+                            ++in.p;
+                            break;
+                        }
+                        in.fail("expected ',' or ']'");
+                        break;
+                    }
+                }
+                if (idx >= 2 && ok0 && ok1) c = {n0, n1};
+            } else {
+                JsonIn::Kind k;
+                std::string sval;
+                if (!in.skip_value(k, nullptr, &sval)) break;
+                if (k == JsonIn::K_STRING) {            // "ab"[0] and "ab"[1] are 1-character strings
+                    uint32_t cp = 0;
+                    for (unsigned char ch : sval) cp += (ch & 0xC0) != 0x80;
+                    if (cp >= 2) c = {1u, 1u};
+                }
+            }
+            if (!in.err.empty()) break;
+            d[key] = c;
+            in.ws();
+            if (in.p < in.end && *in.p == ',') {
+                ++in.p;
+                continue;
+            }
+            if (in.p < in.end && *in.p == '}') {
+                ++in.p;
+                break;
+            }
+            in.fail("expected ',' or '}'");
+            break;
+        }
+    }
+    if (!in.err.empty()) {
+        err = "informative_aln: " + in.err;
+        return false;
+    }
+    in.ws();
+    if (in.p != in.end) {
+        err = "informative_aln: trailing data after the JSON object";
+        return false;
+    }
+    out->keys.reserve(d.size());
+    for (auto &kv : d) out->keys.push_back(kv.first);
+    std::sort(out->keys.begin(), out->keys.end());
+    out->counts.reserve(out->keys.size() * 2);
+    for (auto &k : out->keys) {
+        auto &c = d[k];
+        out->counts.push_back(c.first);
+        out->counts.push_back(c.second);
+    }
+    return true;
+}
+
+}  // namespace svjg
+
 using namespace svjg;
+
+extern "C" int svjg_aln_counts_from_memory(const char *json, size_t len, svjg_aln_counts **out) {
+    if (!json || !out) return set_error(SVJG_E_ARG, "svjg_aln_counts_from_memory: NULL argument");
+    svjg_aln_counts *c = new svjg_aln_counts();
+    std::string err;
+    if (!parse_aln_counts(json, len, c, err)) {
+        delete c;
+        return set_error(SVJG_E_JSON, err);
+    }
+    *out = c;
+    return SVJG_OK;
+}
+extern "C" int svjg_aln_counts_load(const char *json_path, svjg_aln_counts **out) {
+    if (!json_path || !out) return set_error(SVJG_E_ARG, "svjg_aln_counts_load: NULL argument");
+    std::string text;
+    if (!read_file(json_path, text)) return set_error(SVJG_E_IO, std::string("cannot read ") + json_path);
+    return svjg_aln_counts_from_memory(text.data(), text.size(), out);
+}
+extern "C" void svjg_aln_counts_free(svjg_aln_counts *c) { delete c; }
+extern "C" uint32_t svjg_aln_counts_num(const svjg_aln_counts *c) { return c ? uint32_t(c->keys.size()) : 0; }
+extern "C" const char *svjg_aln_counts_key(const svjg_aln_counts *c, uint32_t i, uint32_t *len) {
+    if (!c || i >= c->keys.size()) return nullptr;
+    if (len) *len = uint32_t(c->keys[i].size());
+    return c->keys[i].data();
+}
+extern "C" const uint32_t *svjg_aln_counts_data(const svjg_aln_counts *c) { return c ? c->counts.data() : nullptr; }
+extern "C" uint32_t svjg_aln_counts_find(const svjg_aln_counts *c, const char *key, uint32_t len) {
+    if (!c || !key) return UINT32_MAX;
+    std::string k(key, len);
+    auto it = std::lower_bound(c->keys.begin(), c->keys.end(), k);
+    if (it == c->keys.end() || *it != k) return UINT32_MAX;
+    return uint32_t(it - c->keys.begin());
+}
 
 extern "C" int svjg_tables_from_memory(const char *edges_json, size_t edges_len, const char *gfa, size_t gfa_len,
                                        svjg_tables **out) {

@@ -68,6 +68,13 @@ def _load():
                                        C.POINTER(FilterStats)]),
         "svjg_genotype_device": (C.c_int, [u32p, u32p, u8p, C.c_uint32, C.c_int64, C.c_double, C.c_double,
                                            C.c_double, f64p, C.c_uint32, f64p, i64p, u8p, u32p, u8p, vp]),
+        "svjg_aln_counts_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+        "svjg_aln_counts_from_memory": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+        "svjg_aln_counts_free": (None, [vp]),
+        "svjg_aln_counts_num": (C.c_uint32, [vp]),
+        "svjg_aln_counts_key": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "svjg_aln_counts_data": (C.c_void_p, [vp]),
+        "svjg_aln_counts_find": (C.c_uint32, [vp, C.c_char_p, C.c_uint32]),
         "svjg_emit_informative_json": (C.c_int, [vp, u8p, C.c_uint64, u32p, u64p, u32p, C.c_uint64, C.c_char_p]),
     }
     for name, (res, args) in sig.items():

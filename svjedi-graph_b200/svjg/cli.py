@@ -1,0 +1,138 @@
+"""Drop-in command lines of the post-mapping stages: the same flags, files and exit
+statuses as the reference's filter-alignments.py (:29-71), predict-genotype.py (:31-48)
+and svjedi-graph.py (:28-71); the work is done by libsvjg.so on the GPU.  Where the
+reference dies with a traceback (exit status 1) these print one line and exit 1."""
+from __future__ import annotations
+
+import argparse
+import subprocess
+import sys
+
+
+def _die(msg):
+    sys.stderr.write(f"svjg: {msg}\n")
+    sys.exit(1)
+
+
+def _load_tables(prefix, gfa_file):
+    from . import alnfilter
+    return alnfilter.Tables.load(prefix + "_svs_edges.json", gfa_file).to_device(0)
+
+
+def _filter_to_json(tables, gaf_file, out_json, dover_given=False):
+    """filter-alignments.py:119-175.  Returns (FilterResult, pinned GAF tensor)."""
+    from . import alnfilter, capi
+    if dover_given:
+        # -O leaves a list in d_over and `int >= list` raises at the first overlap test (:269);
+        # count every test the reference would make
+        tables.set_flags(capi.FLAG_EXACT_CHECKS)
+    gaf = alnfilter.read_file_pinned(gaf_file)
+    res = alnfilter.filter_host(tables, gaf)
+    if dover_given and res.stats["n_checks"] > 0:
+        _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
+    alnfilter.write_informative_json(tables, gaf, res, out_json)
+    return res, gaf
+
+
+def filter_main(argv=None):
+    ap = argparse.ArgumentParser(description="---")
+    ap.add_argument("-a", "--gaf", metavar="<align_file>", nargs=1, help="align file in gaf format", required=True)
+    ap.add_argument("-g", "--gfa", metavar="<graph_file>", nargs=1, help="variant graph in gfa format", required=True)
+    ap.add_argument("-i", "--gfainfo", metavar="<gfa_info>", nargs=1, help="gfa info", required=False)
+    ap.add_argument("-O", "--dover", metavar="<min_breakpoint_overlap>", nargs=1, required=False, default=100)
+    ap.add_argument("-o", "--outputDir", metavar="<outputDirectory>", type=str, required=False)
+    ap.add_argument("-p", "--prefix", metavar="<prefix", type=str, required=False)
+    args = ap.parse_args(argv)
+    if not args.prefix:
+        # the reference never assigns svs_edges_dict without -p (UnboundLocalError, :95)
+        _die("-p/--prefix is required: <prefix>_svs_edges.json holds the link -> SV table")
+    out_json = args.prefix + "_informative_aln.json"
+    if args.outputDir:
+        out_json = "/".join([args.outputDir, out_json])
+    from . import alnfilter, capi
+    try:
+        tables = _load_tables(args.prefix, args.gfa[0])
+        _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100)
+    except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
+        _die(str(exc))
+    return 0
+
+
+def genotype_main(argv=None):
+    ap = argparse.ArgumentParser(description="Structural variations genotyping using long reads")
+    ap.add_argument("-d", "--aln", metavar="<alndict>", nargs=1, required=True)
+    ap.add_argument("-v", "--vcf", metavar="<vcffile>", help="vcf format", required=True)
+    ap.add_argument("-o", "--output", metavar="<output>", nargs=1, help="output file")
+    ap.add_argument("-e", "--err", nargs=1, type=float, help="allele error probability")
+    ap.add_argument("-ms", "--minsupport", metavar="<minNbAln>", type=int, default=3,
+                    help="Minimum number of alignments to genotype a SV (default: 3>=)")
+    args = ap.parse_args(argv)
+    output = "genotype_results.txt" if args.output is None else args.output[0]
+    e = args.err[0] if args.err is not None else 0.00005
+    from . import capi, genotype
+    try:
+        counts = genotype.AlnCounts.load(args.aln[0])
+        with open(args.vcf) as fh:
+            lines = fh.readlines()
+        with open(output, "w") as out:          # the reference opens the output before it reads the VCF (:92)
+            text, n = genotype.genotype_vcf_from_json(counts, lines, args.minsupport, e)
+            out.write(text)
+    except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
+        _die(str(exc))
+    print(f"Genotyped svs: {n}")
+    return 0
+
+
+def pipeline_main(svjg_dir, argv=None):
+    """svjedi-graph.py: graph construction and mapping are external tools exactly as in the
+    reference (:85-108); filtering and genotyping run fused in this process — the counters
+    never leave the GPU between the two stages — and still write both output files."""
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-v", "--vcf", type=str, help="SV set in vcf format", required=True)
+    ap.add_argument("-r", "--ref", type=str, help="Reference genome in fasta format", required=True)
+    ap.add_argument("-q", "--reads", type=str, help="Long reads in fastq format", required=True)
+    ap.add_argument("-p", "--prefix", type=str, help="Prefix of generated files", required=True)
+    ap.add_argument("-t", "--threads", type=int, help="Number of threads to use for read mapping", default=[1])
+    ap.add_argument("-ms", "--minsupport", metavar="<minNbAln>", type=int, default=3,
+                    help="Minimum number of alignments to genotype a SV (default: 3>=)")
+    args = ap.parse_args(argv)
+    import os
+    out_gfa, out_gaf = args.prefix + ".gfa", args.prefix + ".gaf"
+
+    print("Constructing variation graph...")
+    construct = os.environ.get("SVJG_CONSTRUCT_GRAPH", f"{svjg_dir}/construct-graph.py")
+    if subprocess.run(f"python3 {construct} -v {args.vcf} -r {args.ref} -o {out_gfa}", shell=True).returncode == 1:
+        sys.exit("Failed to contruct the variation graph.\nExiting SVJedi-graph.")
+
+    print("Mapping reads on graph...")
+    subprocess.run(f"touch {out_gaf}", shell=True)
+    proc = None
+    for fq in args.reads.split(","):
+        proc = subprocess.run(f"minigraph -x lr -t{args.threads} {out_gfa} {fq} >> {out_gaf}", shell=True)
+    if proc.returncode == 1:
+        sys.exit("Failed to map the reads on the graph.\nExiting SVJedi-graph.")
+
+    print("Filtering alignment file...")
+    from . import alnfilter, capi, genotype
+    import numpy as np
+    import torch
+    try:
+        tables = _load_tables(args.prefix, out_gfa)
+        res, _gaf = _filter_to_json(tables, out_gaf, args.prefix + "_informative_aln.json")
+    except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
+        sys.stderr.write(f"svjg: {exc}\n")
+        sys.exit("Failed to filter the alignments.\nExiting SVJedi-graph.")
+
+    print("Genotyping SVs...")
+    try:
+        with open(args.vcf) as fh:
+            lines = fh.readlines()
+        d_counts = torch.from_numpy(res.counts.view(np.int32)).cuda()
+        with open(args.prefix + "_genotype.vcf", "w") as out:
+            text, n = genotype.genotype_vcf(tables, d_counts, lines, args.minsupport)
+            out.write(text)
+    except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
+        sys.stderr.write(f"svjg: {exc}\n")
+        sys.exit("Failed to predict the genotypes.\nExiting SVJedi-graph.")
+    print(f"Genotyped svs: {n}")
+    return 0

@@ -210,3 +210,87 @@ def genotype_vcf(tables, d_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR):
         ad2 = np.zeros((0, 2), np.uint32)
         pl = np.zeros((0, 3), np.int64)
     return format_vcf(header, recs, gt, flags, ad2, pl)
+
+
+class AlnCounts:
+    """Per-key list lengths of an informative_aln.json (predict-genotype.py:67-68, :219-226),
+    read by libsvjg's streaming JSON reader."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        self.num = int(capi.lib.svjg_aln_counts_num(self._h))
+        p = capi.lib.svjg_aln_counts_data(self._h)
+        if self.num:
+            self.counts = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.num, 2)).copy()
+        else:
+            self.counts = np.zeros((0, 2), np.uint32)
+
+    @classmethod
+    def load(cls, path):
+        import os
+        h = C.c_void_p()
+        capi.check(capi.lib.svjg_aln_counts_load(os.fsencode(path), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_memory(cls, text):
+        b = text.encode() if isinstance(text, str) else bytes(text)
+        h = C.c_void_p()
+        capi.check(capi.lib.svjg_aln_counts_from_memory(b, len(b), C.byref(h)))
+        return cls(h.value)
+
+    def key(self, i):
+        n = C.c_uint32()
+        p = capi.lib.svjg_aln_counts_key(self._h, i, C.byref(n))
+        if not p:
+            raise IndexError(i)
+        return C.string_at(p, n.value).decode("utf-8")
+
+    def find(self, key):
+        b = key.encode("utf-8")
+        i = capi.lib.svjg_aln_counts_find(self._h, b, len(b))
+        return None if i == capi.NO_SV else int(i)
+
+    def close(self):
+        if self._h:
+            capi.lib.svjg_aln_counts_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def genotype_vcf_from_json(aln_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR, device=0):
+    """decision_vcf (predict-genotype.py:89-279) with the counters taken from an
+    informative_aln.json, as the stand-alone reference stage does.  A key that is
+    present gates the SV in even when both of its lists are empty (:216)."""
+    import torch
+    header, recs = parse_vcf(vcf_lines)
+    n = len(recs)
+    idx = np.full(n, capi.NO_SV, dtype=np.uint32)
+    ty = np.fromiter((r[1] for r in recs), dtype=np.uint8, count=n)
+    for i, r in enumerate(recs):
+        if r[2] is None:
+            continue
+        j = aln_counts.find(r[2])
+        if j is None:
+            continue
+        gated = (ty[i] & 0x3F) <= 3 and not (ty[i] & 0x80) and ty[i] != 255
+        if gated and aln_counts.counts[j, 0] == capi.NO_SV:
+            raise VcfError(f"informative_aln entry of {r[2]!r} is not a pair of lists (the reference raises here)")
+        idx[i] = j
+        if ty[i] != 255:
+            ty[i] |= 0x40
+    if n:
+        dev = torch.device("cuda", device)
+        d_counts = torch.from_numpy(np.ascontiguousarray(aln_counts.counts).view(np.int32).reshape(-1, 2).copy()).to(dev) \
+            if aln_counts.num else torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        gt, flags, ad2, pl = genotype_device(d_counts, idx, ty, min_support, e)
+    else:
+        gt = flags = np.zeros(0, np.uint8)
+        ad2 = np.zeros((0, 2), np.uint32)
+        pl = np.zeros((0, 3), np.int64)
+    return format_vcf(header, recs, gt, flags, ad2, pl)

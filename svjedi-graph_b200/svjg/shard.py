@@ -1,0 +1,70 @@
+"""Multi-GPU host logic of the hot path (one process per GPU, torch.distributed).
+
+GAF records are independent (filter-alignments.py:124 keeps no cross-record state but the
+appends), so the file is cut into one contiguous byte range per rank, snapped to line ends;
+the graph tables are replicated.  The only exchange is ONE all-reduce (sum) of the per-SV
+REF/ALT counters before genotyping; hit tuples stay with their rank and are concatenated in
+rank order = file order when informative_aln.json is written."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_cuts(gaf, world):
+    """world+1 byte offsets: rank r owns gaf[cuts[r]:cuts[r+1]].  Every cut but the last sits right
+    behind a newline, so no record is split and the ranges tile the buffer."""
+    a = gaf if isinstance(gaf, np.ndarray) else np.frombuffer(gaf, dtype=np.uint8)
+    n = int(a.size)
+    cuts = [0]
+    for r in range(1, world):
+        pos = max(cuts[-1], (n * r) // world)
+        if pos >= n:
+            cuts.append(n)
+            continue
+        if pos > 0 and a[pos - 1] == 10:          # already at a line start
+            cuts.append(pos)
+            continue
+        # first newline at or after pos (searched in blocks so huge files are not scanned whole)
+        nxt = n
+        step = 1 << 20
+        q = pos
+        while q < n:
+            blk = a[q:min(n, q + step)]
+            hit = np.flatnonzero(blk == 10)
+            if hit.size:
+                nxt = q + int(hit[0]) + 1
+                break
+            q += step
+        cuts.append(nxt)
+    cuts.append(n)
+    return cuts
+
+
+def allreduce_counts(counts, group=None):
+    """Sum of the [num_sv, 2] counters over all ranks, in place (NCCL for CUDA tensors, gloo for
+    CPU ones).  Integer sums: bit-exact in any order."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return counts
+    t = counts if isinstance(counts, torch.Tensor) else torch.from_numpy(counts)
+    if t.dtype == torch.uint32:
+        t = t.view(torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def gather_hits(hit_sv2, hit_off, hit_len, base_offset, group=None):
+    """All ranks' hit tuples on rank 0 (None elsewhere), offsets made absolute in the whole file;
+    concatenated in rank order."""
+    import torch.distributed as dist
+    mine = (np.asarray(hit_sv2, np.uint32), np.asarray(hit_off, np.uint64) + np.uint64(base_offset),
+            np.asarray(hit_len, np.uint32))
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mine
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))

@@ -200,3 +200,117 @@ def test_fast_path_equals_general_routine(gpu, tag):
     c = alnfilter.filter_host(t_all, gaf)
     assert (c.counts == a.counts).all() and c.stats["n_checks"] >= a.stats["n_checks"]
     assert c.stats["n_checks"] == b.stats["n_checks"]
+
+
+def _oracle_counts(lines, edges_text, gfa_text):
+    return O.hit_counts(O.filter_alignments(lines, json.loads(edges_text), alt_len_from_gfa_text(gfa_text)))
+
+
+def _synthetic(name, scale, **kw):
+    import io
+    from svjg import synth
+    g, vcf, gaf = synth.make_workload(name, scale=scale, **kw)
+    buf = io.StringIO()
+    g.write_gfa(buf)
+    return g.edges_json(), buf.getvalue(), vcf, gaf
+
+
+@pytest.mark.parametrize("name,scale", [("C2", 0.02), ("C3", 0.004), ("C4", 0.02), ("C5", 0.0002)])
+def test_named_workloads_scaled_match_oracle(gpu, name, scale, tmp_path):
+    """The BASELINE.json config shapes at a size the Python oracle finishes in seconds:
+    counters, informative_aln.json (byte for byte) and the genotype VCF."""
+    alnfilter, capi, genotype, torch = gpu
+    edges_text, gfa_text, vcf, gaf = _synthetic(name, scale, cg_frac=0.05)
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text).to_device(0)
+    res = alnfilter.filter_host(t, gaf.encode())
+    want = O.filter_alignments(gaf.splitlines(True), json.loads(edges_text), alt_len_from_gfa_text(gfa_text))
+    assert _counts_dict(t, res.counts) == {k: list(v) for k, v in O.hit_counts(want).items()}
+    out = tmp_path / "x.json"
+    alnfilter.write_informative_json(t, gaf.encode(), res, str(out))
+    assert out.read_text() == O.dumps_informative(want)
+    d_counts = torch.from_numpy(res.counts.view(np.int32)).cuda()
+    text, n = genotype.genotype_vcf(t, d_counts, vcf.splitlines(True))
+    assert (text, n) == O.genotype_vcf(O.hit_counts(want), vcf.splitlines(True))
+    assert res.stats["n_multi"] > 0 and res.n_hits > 0
+
+
+def test_full_size_c2_properties(gpu):
+    """BASELINE.json's C2 at full size (3 M records, ~0.5 GB): size-independent properties.
+    Records seen = newlines; hits = sum of the counters; the chunked host path equals the
+    single-shard device path; counters are additive over a cut at a line end; a slice of the
+    batch matches the oracle exactly."""
+    alnfilter, capi, genotype, torch = gpu
+    edges_text, gfa_text, vcf, gaf = _synthetic("C2", 1.0)
+    raw = gaf.encode()
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text).to_device(0)
+    host = alnfilter.filter_host(t, raw, want_hits=False)
+    assert host.stats["n_records"] == raw.count(b"\n") == 3_000_000
+    assert int(host.counts.sum()) == host.stats["n_hits"]
+    d = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    f = alnfilter.DeviceFilter(t, hit_cap=host.stats["n_hits"] + 8)
+    f.reset()
+    f.run(d)
+    whole = f.result()
+    assert (whole.counts == host.counts).all() and whole.stats["n_hits"] == host.stats["n_hits"]
+    # every hit points at a whole line of the buffer
+    off, ln = whole.hit_off.astype(np.int64), whole.hit_len.astype(np.int64)
+    a = np.frombuffer(raw, dtype=np.uint8)
+    assert (a[off + ln - 1] == 10).all() and ((off == 0) | (a[np.maximum(off, 1) - 1] == 10)).all()
+    # additivity over a cut at a line end (what the multi-GPU sharding relies on)
+    cut = raw.index(b"\n", len(raw) // 2) + 1
+    left = alnfilter.filter_host(t, raw[:cut], want_hits=False)
+    right = alnfilter.filter_host(t, raw[cut:], want_hits=False)
+    assert (left.counts + right.counts == host.counts).all()
+    # a slice against the oracle
+    lines = gaf[:cut].splitlines(True)[:60000]
+    part = alnfilter.filter_host(t, "".join(lines).encode(), want_hits=False)
+    assert _counts_dict(t, part.counts) == {k: list(v) for k, v in _oracle_counts(lines, edges_text, gfa_text).items()}
+
+
+def test_irregular_lines_take_the_exact_route(gpu):
+    """CRLF line ends, read names longer than the fixed column spans, node names longer than the
+    register path of the token kernel, 10-digit coordinates: all must equal the oracle."""
+    alnfilter, capi, genotype, torch = gpu
+    t, edges = _tables(alnfilter, "c1")
+    edges = json.loads(edges)
+    alt = alt_len_from_gfa_text(read_golden("c1.gfa.gz"))
+    base = read_golden("c1.gaf.gz").splitlines(True)[:600]
+    lines = []
+    for i, l in enumerate(base):
+        cols = l.rstrip("\n").split("\t")
+        if i % 3 == 0:
+            cols[0] = "Read_%d_length=8203bp_startpos=4333_number_of_errors=912_total_error_prob=0.1145_passes=1.9" % i
+        if i % 5 == 0:
+            cols[1] = cols[3] = "1234567890123"          # 13-digit Qlen / Qe: unused columns, any size is fine
+        l = "\t".join(cols) + ("\r\n" if i % 4 == 1 else "\n")
+        lines.append(l)
+    gaf = "".join(lines)
+    res = alnfilter.filter_host(t, gaf.encode())
+    want = O.hit_counts(O.filter_alignments(lines, edges, alt))
+    assert _counts_dict(t, res.counts) == {k: list(v) for k, v in want.items()}
+    assert res.stats["n_records"] == len(lines) and res.stats["n_generic"] > 0
+    # long node names and long coordinates in a private little graph
+    long_chr = "a_very_long_contig_name_that_does_not_fit_in_thirty_two_bytes"
+    n1, n2, n3 = f"{long_chr}:1-1000", f"{long_chr}:1001-2000", f"{long_chr}:4000000001-4000001000"
+    edges2 = {f"{n1}@+@{n2}@+": [[f"{long_chr}:DEL-1000-1000", 0]], f"{n2}@+@{n3}@+": [[f"{long_chr}:DEL-2000-4000000000", 1]]}
+    t2 = alnfilter.Tables.from_memory(json.dumps(edges2), "").to_device(0)
+    rec = lambda path, tlen, ts, te: f"r\t3000\t0\t3000\t+\t{path}\t{tlen}\t{ts}\t{te}\t2900\t3000\t60\ttp:A:P\n"
+    lines2 = [rec(f">{n1}>{n2}", 2000, 100, 1900), rec(f">{n1}>{n2}>{n3}", 3000, 100, 2900),
+              rec(f"<{n2}<{n1}", 2000, 100, 1900), rec(f">{n2}>{n3}", 2000, 950, 1050)]
+    res2 = alnfilter.filter_host(t2, "".join(lines2).encode())
+    want2 = O.hit_counts(O.filter_alignments(lines2, edges2, {}))
+    assert _counts_dict(t2, res2.counts) == {k: list(v) for k, v in want2.items()} and want2
+
+
+def test_scratch_exhaustion_falls_back_to_the_exact_route(gpu, monkeypatch):
+    alnfilter, capi, genotype, torch = gpu
+    t, _ = _tables(alnfilter, "s3")
+    gaf = read_golden("s3.gaf.gz").encode()
+    normal = alnfilter.filter_host(t, gaf)
+    monkeypatch.setenv("SVJG_TEST_TINY_SCRATCH", "1")
+    tiny = alnfilter.filter_host(t, gaf)
+    monkeypatch.delenv("SVJG_TEST_TINY_SCRATCH")
+    assert (tiny.counts == normal.counts).all() and tiny.n_hits == normal.n_hits
+    assert tiny.stats["n_multi"] == normal.stats["n_multi"]
+    assert tiny.stats["n_generic"] > normal.stats["n_generic"]
+    assert sorted(zip(tiny.hit_sv2.tolist(), tiny.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))

@@ -1,0 +1,94 @@
+"""world_size-2 run of the multi-GPU host logic on CPU (gloo): byte-range sharding snapped to
+line ends, the single all-reduce of the per-SV counters and the rank-ordered merge of the hit
+tuples.  The per-shard filter is the oracle here (the CUDA filter needs a GPU; its own parity
+is tests/test_gpu_parity.py) — what is checked is that sharding + exchange reproduce the
+single-process result exactly."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import alt_len_from_gfa_text, read_golden
+from oracle import svjg_oracle as O
+from svjg import shard
+
+
+def test_shard_cuts_tile_the_buffer_at_line_ends():
+    gaf = read_golden("s3.gaf.gz").encode()
+    for world in (1, 2, 3, 8, 64):
+        cuts = shard.shard_cuts(gaf, world)
+        assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == len(gaf)
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        for c in cuts[1:-1]:
+            assert c == len(gaf) or gaf[c - 1:c] == b"\n"
+        assert b"".join(gaf[a:b] for a, b in zip(cuts, cuts[1:])) == gaf
+    # ragged inputs: empty, no newline at all, fewer lines than ranks
+    assert shard.shard_cuts(b"", 4) == [0, 0, 0, 0, 0]
+    assert shard.shard_cuts(b"abc", 2) == [0, 3, 3]
+    assert shard.shard_cuts(b"a\nb\n", 8)[-1] == 4
+
+
+def _worker(rank, world, port, tag, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gaf = read_golden(f"{tag}.gaf.gz").encode()
+    edges = json.loads(read_golden(f"{tag}_svs_edges.json.gz"))
+    alt = alt_len_from_gfa_text(read_golden(f"{tag}.gfa.gz"))
+    ids = sorted({sv for ents in edges.values() for sv, _ in ents})
+    index = {s: i for i, s in enumerate(ids)}
+    cuts = shard.shard_cuts(gaf, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    counts = np.zeros((len(ids), 2), dtype=np.int32)
+    sv2, off, ln = [], [], []
+    pos = 0
+    for line in gaf[lo:hi].decode().splitlines(True):
+        nb = len(line.encode())
+        for sv, allele in O.record_hits(line, edges, alt):
+            counts[index[sv], allele] += 1
+            sv2.append(index[sv] * 2 + allele)
+            off.append(pos)
+            ln.append(nb)
+        pos += nb
+    t = torch.from_numpy(counts)
+    shard.allreduce_counts(t)
+    merged = shard.gather_hits(sv2, off, ln, lo)
+    np.save(os.path.join(out_dir, f"counts_{rank}.npy"), counts)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "hits.npz"), sv2=merged[0], off=merged[1], ln=merged[2])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_two_rank_gloo_run_equals_single_process(tmp_path, world):
+    import torch.multiprocessing as mp
+    tag = "s3"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, tag, str(tmp_path)), nprocs=world, join=True)
+    gaf = read_golden(f"{tag}.gaf.gz")
+    edges = json.loads(read_golden(f"{tag}_svs_edges.json.gz"))
+    alt = alt_len_from_gfa_text(read_golden(f"{tag}.gfa.gz"))
+    ids = sorted({sv for ents in edges.values() for sv, _ in ents})
+    want = O.hit_counts(O.filter_alignments(gaf.splitlines(True), edges, alt))
+    for r in range(world):
+        c = np.load(tmp_path / f"counts_{r}.npy")
+        got = {ids[i]: (int(c[i, 0]), int(c[i, 1])) for i in range(len(ids)) if c[i].any()}
+        assert got == want, f"rank {r}"
+    h = np.load(tmp_path / "hits.npz")
+    # rank order is file order: offsets ascend, and the tuples are those of a single pass
+    assert (np.diff(h["off"].astype(np.int64)) >= 0).all()
+    single = []
+    pos = 0
+    index = {s: i for i, s in enumerate(ids)}
+    for line in gaf.splitlines(True):
+        for sv, allele in O.record_hits(line, edges, alt):
+            single.append((index[sv] * 2 + allele, pos, len(line.encode())))
+        pos += len(line.encode())
+    assert list(zip(h["sv2"].tolist(), h["off"].tolist(), h["ln"].tolist())) == single
