@@ -28,6 +28,9 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 METRIC = "gaf_alignments_filtered_assigned_per_sec"
+# dram__bytes_read.sum + dram__bytes_write.sum of the filter chain per launch, from the ncu --set full
+# capture committed under profiles/ (None where no capture exists for the workload)
+FILTER_TRAFFIC = {"C2": 811_000_000}
 UNIT = "alignments/s"
 
 
@@ -347,6 +350,25 @@ def main():
     else:
         job_rec = n_rec
     st = filt.read_stats()
+
+    # the dominant kernel on its own (profiling hook of the library: stop the chain after scan_parse)
+    def timed_filter(n_iter):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(n_iter):
+            capi.check(lib.svjg_filter_reset(filt.counts.data_ptr(), tables.num_sv, filt.stats.data_ptr(), sp))
+            a0.record(stream)
+            capi.check(lib.svjg_filter_device(tables._h, d_gaf.data_ptr(), n_bytes, 0, 100, filt.counts.data_ptr(),
+                                              filt.hit_sv2.data_ptr(), filt.hit_off.data_ptr(), filt.hit_len.data_ptr(),
+                                              filt.hit_cap, filt.stats.data_ptr(), sp))
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            tot += a0.elapsed_time(a1)
+        return tot / n_iter
+    os.environ["SVJG_STOP_AFTER"] = "B"
+    timed_filter(2)
+    scan_ms = timed_filter(max(3, min(K, 10)))
+    os.environ.pop("SVJG_STOP_AFTER")
     if args.kernel_only:
         if rank == 0:
             print(json.dumps({"kernel_ms": {"filter": filt_ms, "allreduce": comm_ms, "genotype": geno_ms},
@@ -405,10 +427,13 @@ def main():
             "tables_device_bytes": tables.device_bytes, "gen_seconds": round(gen_s, 1),
         },
         "svs_genotyped_per_sec": n_sv / (geno_ms * 1e-3) if geno_ms > 0 else None,
-        "kernel_ms": {"filter": filt_ms, "allreduce": comm_ms, "genotype": geno_ms},
+        "kernel_ms": {"filter": filt_ms, "filter_scan_parse_only": scan_ms, "allreduce": comm_ms, "genotype": geno_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "filter_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                     "traffic": FILTER_TRAFFIC.get(args.workload), "kernel": "filter chain: scan_parse+token+clash+link+exact", "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": peak_src,
+                     "dominant_kernel": {"name": "scan_parse_kernel", "ms": scan_ms, "share_of_chain": scan_ms / filt_ms,
+                                         "achieved": n_bytes / (scan_ms * 1e-3) / 1e9, "frac": n_bytes / (scan_ms * 1e-3) / 1e9 / peak,
+                                         "algorithmic_bytes_per_launch": n_bytes},
                      "genotype_kernel": {"achieved": geno_bytes / (geno_ms * 1e-3) / 1e9 if geno_ms > 0 else None,
                                          "bytes_per_launch": geno_bytes}},
         "cpu_baseline": {"value": n_rec / (tf * n_rec / sample_n + tg), "unit": UNIT, "cores": 1, "kind": "port",
@@ -417,7 +442,7 @@ def main():
                                    "single thread like the reference"},
         "e2e": {"value": job_rec * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke},
-        "gpu_launches": 3 * K,
+        "gpu_launches": 8 * K,   # reset + scan_parse + token + clash + link + exact + genotype (+1 memset node)
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -1351,7 +1351,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
     a.flags = t->filter_flags;
-    static const char *stop_env = getenv("SVJG_STOP_AFTER");   // profiling hook: run the chain up to A/B/C/D only
+    const char *stop_env = getenv("SVJG_STOP_AFTER");          // profiling hook: run the chain up to A/B/C/D only
     const int stop = (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'D') ? stop_env[0] - 'A' + 1 : 0;
     if (stop == 1) a.flags |= 1u << 8;
 
