@@ -83,6 +83,9 @@ extern "C" int svjg_tables_to_device(svjg_tables *t, int device) {
     SVJG_CUDA(up(&t->d_nodes, t->nodes.data(), t->nodes.size() * sizeof(NodeSlot)));
     SVJG_CUDA(up(&t->d_blob, t->blob.data(), t->blob.size()));
     SVJG_CUDA(up(&t->d_entries, t->entries.data(), t->entries.size() * sizeof(uint32_t)));
+    SVJG_CUDA(up(&t->d_pnodes, t->pnodes.data(), t->pnodes.size() * sizeof(PNodeSlot)));
+    t->dev.pnodes = static_cast<const PNodeSlot *>(t->d_pnodes);
+    t->dev.pnode_mask = uint32_t(t->pnodes.size() - 1);
     t->dev.links = static_cast<const LinkSlot *>(t->d_links);
     t->dev.nodes = static_cast<const NodeSlot *>(t->d_nodes);
     t->dev.blob = static_cast<const uint8_t *>(t->d_blob);
@@ -103,6 +106,7 @@ extern "C" void svjg_tables_free(svjg_tables *t) {
         cudaFree(t->d_nodes);
         cudaFree(t->d_blob);
         cudaFree(t->d_entries);
+        cudaFree(t->d_pnodes);
     }
     delete t;
 }

@@ -6,8 +6,8 @@
 // read_gaf_line :184-198, extract_nodes :351-373, get_aln_links :200-219,
 // reverse_link :221-225, check_bkpt_overlap :258-273, get_node_len :343-349.
 //
-// The work is a chain of kernels, each parallel over the unit that keeps all lanes
-// busy and each at full occupancy; compacted lists in device scratch memory link them:
+// The work is a chain of three kernels; a compacted list of link records in device scratch
+// memory connects the first two:
 //   scan_parse  every WARP is an independent worker with its own shared-memory window
 //               (no block barrier).  It walks 4 KiB tiles of the byte buffer; a tile
 //               plus 1 KiB of look-ahead is staged by one TMA bulk copy.
@@ -15,20 +15,22 @@
 //                  ballots turn the newline flags into the ordered list of line ends;
 //               B  line-parallel: one lane per line finds the 12 columns (tab bitmaps
 //                  of fixed spans, so lanes stay converged), validates the integer
-//                  columns and walks the path column.  Lines with >= 2 path nodes go
-//                  to the multi-node list with one token record per node; lines that
-//                  are not of the plain shape go to the "exact" list.
-//   token       one thread per path node: name hash (4 bytes a step), chrom:start-end
-//               parse or alt-node lookup.
-//   line        one thread per multi-node line: Tlen/Ts/Te, sums of the node lengths,
-//               the breakpoint-overlap verdict of every link.
-//   clash       one thread per node: could this name occur inside an earlier one of
-//               the same path (first-occurrence rules of :206 and :269-271)?
-//   link        one thread per link: forward and reverse key probes of the link hash,
-//               warp-aggregated counter atomics and hit tuples.
+//                  columns, walks the path column and reads Tlen/Ts/Te of the lines
+//                  with >= 2 path nodes;
+//               C  node-parallel: one lane per path node of those lines, still from shared
+//                  memory: chrom:start-end / chrom:pos.k -> exact 24-byte key -> one probe of
+//                  the plain-node table (node id, alt length);
+//               D  same lanes: node-length prefix sums, the breakpoint-overlap verdict of
+//                  every link (:269-273), the first-occurrence hazard (:206), and one 16-byte
+//                  link record (integer link key, line offset, line length) per link that
+//                  can have hits.
+//               Lines that are not of the plain shape go to the "exact" list.
+//   link        one thread per link record: forward and reverse key probes of the link
+//               hash, warp-aggregated counter atomics and hit tuples.
 //   exact       one thread per irregular line: parse_fields() / general(), which follow
 //               the reference's string semantics literally (odd integers, odd node
 //               names, names that could be substrings of earlier ones, long lines ...).
+// The GAF bytes are read from DRAM once (scan_parse); only the exact route reads them again.
 // A line belongs to the tile its first byte is in.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -54,6 +56,7 @@ constexpr int HEAD_SPAN = 96;                  // bytes searched for the tabs of
 constexpr int TAIL_SPAN = 96;                  // bytes searched for the tabs of columns 7-12
 constexpr int SPARE = 176;                     // readable bytes behind the window for those fixed-span reads
 constexpr int NLCAP = 336;                     // newlines per window (more => some line is shorter than 16 bytes)
+constexpr int TOKCAP = 32;                     // path nodes resolved per round of phases C/D (one lane each)
 static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit");
 
 // shared memory map of ONE warp of scan_parse (bytes)
@@ -62,7 +65,10 @@ constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline positions
 constexpr int BMWORDS = NPAIRS + 7;                         // bitmap words: reads may run a few words past the window
 constexpr int OFF_TABB = (OFF_NL + NLCAP * 2 + 15) & ~15;   // tab bitmap        u32[BMWORDS]
 constexpr int OFF_DLB = OFF_TABB + BMWORDS * 4;             // delimiter bitmap  u32[BMWORDS]
-constexpr int WARP_SMEM = (OFF_DLB + BMWORDS * 4 + 127) & ~127;
+constexpr int OFF_TKP = OFF_DLB + BMWORDS * 4;              // node list of a round: window position u16[TOKCAP],
+constexpr int OFF_TKL = OFF_TKP + TOKCAP * 2;               //   length u8[TOKCAP] (255 = longer),
+constexpr int OFF_TKO = OFF_TKL + TOKCAP;                   //   lane of its line u8[TOKCAP]
+constexpr int WARP_SMEM = (OFF_TKO + TOKCAP + 127) & ~127;
 constexpr int SMEM_BYTES = WARP_SMEM * WARPS;
 
 constexpr int FLAT_THREADS = 256;              // block size of the flat (grid-stride) kernels
@@ -71,38 +77,23 @@ constexpr uint32_t FLAG_EXACT_CHECKS = SVJG_FLAG_EXACT_CHECKS;   // probe links 
 constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through general()
 constexpr uint32_t COMMA_PATH = 0xFFFFFFFFu;
 
-// token flags
-constexpr uint32_t TF_PLUS = 1;     // delimiter in front is '>'
-constexpr uint32_t TF_ALT = 2;      // chrom:pos.k (length from the GFA)
-constexpr uint32_t TF_PLAIN = 4;    // exactly one ':', digits-digits or digits.<anything>, length > 0
-// line flags
-constexpr uint32_t LF_GENERAL = 1;  // must go through general()
-constexpr uint32_t LF_HAS_NL = 2;   // the line ends in a newline (it counts in the hit's length)
-constexpr uint32_t LF_SKIP = 4;     // reported as an error: no links
-constexpr uint32_t NO_LINE = 0xFFFFFFFFu;
+constexpr uint64_t LINK_HOLE = ~0ull;           // link record that was reserved but not filled
+constexpr uint32_t LINK_OK = 0x80000000u;       // in LinkRec::len: the breakpoint-overlap test passed
 
-// a multi-node line on the token-parallel route (byte offsets into the shard)
-struct GLine {
-    uint32_t s, e;        // first byte of the line, its end (newline or end of data)
-    uint32_t ps, pe;      // path column [ps, pe); pe is the tab that ends it
-    uint32_t tok0, ntok;  // tokens [tok0, tok0 + ntok); ntok == 0 marks a slot that was given up
-    uint32_t flags;
-    uint32_t pad;
-    int64_t ts, tail;     // Ts and Tlen - Te - 1 (check_bkpt_overlap :260-261)
+// a link of a multi-node line that passed phases C/D
+struct LinkRec {
+    uint64_t key;         // link_key(idL, sL, idR, sR)
+    uint32_t off;         // first byte of the line (offset into the shard)
+    uint32_t len;         // bytes of the line incl. its newline | LINK_OK
 };
-static_assert(sizeof(GLine) == 48, "GLine is 48 bytes");
+static_assert(sizeof(LinkRec) == 16, "LinkRec is 16 bytes");
 
 // device scratch of one svjg_filter_device() call
 struct Scratch {
-    uint32_t *cnt;        // [0] multi-node lines, [1] tokens, [2] exact-route lines, [3] lines for general()
-    GLine *ml;
-    uint32_t *tk_b, *tk_line, *tk_sval, *tk_node;
-    uint16_t *tk_l;
-    int32_t *tk_len;
-    uint8_t *tk_flags;
+    uint32_t *cnt;        // [0] link records, [2] exact-route lines
+    LinkRec *links;
     uint32_t *exact;      // line start offsets
-    uint32_t *general;    // multi-node lines (index into ml) that need general(); at most cap_ml
-    uint32_t cap_ml, cap_tok, cap_exact;
+    uint32_t cap_links, cap_exact;
 };
 
 struct FilterArgs {
@@ -344,21 +335,6 @@ struct Rec {
         }
         angle = is_delim(src[ps]);
         return angle ? ntok : COMMA_PATH;
-    }
-
-    // Tlen, Ts, Te (columns 7-9) of a line whose columns were validated already
-    __device__ void reparse_coords(P e) {
-        while (e > pe && py_space(src[e - 1])) --e;
-        P pos = pe + 1;
-        int64_t *dst[3] = {&tlen, &ts, &te};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            P f = pos;
-            while (f < e && src[f] != '\t') ++f;
-            parse_int(src, pos, f, *dst[k]);
-            pos = f + 1;
-        }
-        angle = true;
     }
 
     // tokens of the path column: '<'/'>' separated, or (path not starting with
@@ -717,8 +693,40 @@ __device__ __forceinline__ uint32_t bm_bits(const uint32_t *bm, uint32_t pos) {
 // the low n bits (n may exceed 32 or be <= 0)
 __device__ __forceinline__ uint32_t low_bits(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, uint32_t(max(n, 0))); }
 
+// value of the decimal digits in window bytes [lo, hi) (validated: digits only, hi > lo); false
+// when there are more than 18 significant digits
+__device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
+    int64_t x = 0;
+    uint32_t nd = 0;
+    for (uint32_t q = lo; q < hi; ++q) {
+        const uint32_t d = uint32_t(win[q]) - '0';
+        nd += (x != 0 || d != 0);
+        x = x * 10 + int64_t(d);
+    }
+    out = x;
+    return nd <= 18;
+}
+
+// plain-node table: exact key -> (node id, alt sequence length)
+__device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uint64_t c1, uint32_t ka, uint32_t kb,
+                                           uint32_t &id, uint32_t &alt_len) {
+    uint32_t i = pnode_hash(c0, c1, ka, kb) & tb.pnode_mask;
+    for (;;) {
+        const uint4 *sp = reinterpret_cast<const uint4 *>(tb.pnodes + i);
+        const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+        if (!hi.z) return false;
+        if (lo.x == uint32_t(c0) && lo.y == uint32_t(c0 >> 32) && lo.z == uint32_t(c1) && lo.w == uint32_t(c1 >> 32) &&
+            hi.x == ka && hi.y == kb) {
+            id = hi.z - 1u;
+            alt_len = hi.w;
+            return true;
+        }
+        i = (i + 1) & tb.pnode_mask;
+    }
+}
+
 // ===========================================================================
-// scan_parse: newline scan, column split, validation, path walk
+// scan_parse: newline scan, column split, validation, path walk, node and link resolution
 // ===========================================================================
 __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_all[];
@@ -730,6 +738,8 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
     uint16_t *nl = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_NL);
     uint32_t *tabb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_TABB);   // bit i: window byte i is a tab
     uint32_t *dlb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_DLB);     // bit i: ... is '<' or '>'
+    uint16_t *tkp = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_TKP);
+    uint8_t *tkl = smem_all + warp * WARP_SMEM + OFF_TKL, *tko = smem_all + warp * WARP_SMEM + OFF_TKO;
     uint64_t *mbar = &mbars[warp];
 
     if (lane == 0) mbar_init(mbar, 1);
@@ -822,6 +832,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
             uint32_t want = 0;                 // path nodes of a plain line with >= 2 of them
             bool exact = false;                // the line must take the exact route
             uint32_t s = 0, e = 0, ps = 0, pe = 0;
+            uint32_t c6 = 0, c7 = 0, c8 = 0, c9 = 0;   // tabs that end columns 6-9
             bool has_nl = false;
             if (k < n_own) {
                 s = uint32_t(nl[k]) + 1u;
@@ -898,6 +909,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                         }
                         plain = n2 == 6;
                         p7 = t0 + ((q1 >> 8) & 255u), p8 = t0 + (q1 & 255u), p9 = t0 + (q0 >> 24);
+                        c6 = p6, c7 = p7, c8 = p8, c9 = p9;
                         p10 = t0 + ((q0 >> 16) & 255u), p11 = t0 + ((q0 >> 8) & 255u), p12 = t0 + (q0 & 255u);
                     }
                     if (plain) {
@@ -929,42 +941,33 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 }
             }
             __syncwarp();
-            // slots in the multi-node list / token list for the lanes that want them: one warp scan and
-            // one pair of cursor atomics per pass
-            const uint32_t wb = __ballot_sync(0xFFFFFFFFu, want != 0);
-            if (wb) {
-                const uint32_t incl = warp_incl_scan(want, lane);
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31), n_new = __popc(wb);
-                uint32_t tb = 0, lb = 0;
-                if (lane == 0) {
-                    tb = atomicAdd(a.sc.cnt + 1, total);
-                    lb = atomicAdd(a.sc.cnt + 0, n_new);
+            // Tlen, Ts, Te of the lines that go on (digit-only columns 7-9).  The reference has bigints;
+            // this route stops at 18 digits and says so.
+            int64_t ts = 0, tail = 0;
+            if (want > TOKCAP) {
+                exact = true;                  // more nodes than a round holds: the exact route
+                want = 0;
+            } else if (want) {
+                int64_t tlen = 0, te = 0;
+                const bool fits = dec_field(win, c6 + 1, c7, tlen) & dec_field(win, c7 + 1, c8, ts) & dec_field(win, c8 + 1, c9, te);
+                tail = tlen - te - 1;
+                if (!fits) {
+                    report(a, SVJG_BAD_RANGE, wbase + s);
+                    want = 0;
                 }
-                tb = __shfl_sync(0xFFFFFFFFu, tb, 0);
-                lb = __shfl_sync(0xFFFFFFFFu, lb, 0);
-                const uint32_t t0 = tb + incl - want, li = lb + __popc(wb & lt_mask);
-                const bool room = uint64_t(tb) + total <= a.sc.cap_tok && uint64_t(lb) + n_new <= a.sc.cap_ml;
-                if (want && !room) {
-                    // scratch exhausted: mark what was reserved as holes and take the exact route
-                    if (li < a.sc.cap_ml) a.sc.ml[li].ntok = 0;
-                    for (uint32_t t = t0; t < t0 + want && t < a.sc.cap_tok; ++t) a.sc.tk_line[t] = NO_LINE;
-                    exact = true;
-                } else if (want) {
-                    loc.n_multi++;
-                    GLine L;
-                    L.s = wbase + s;
-                    L.e = wbase + e;
-                    L.ps = wbase + ps;
-                    L.pe = wbase + pe;
-                    L.tok0 = t0;
-                    L.ntok = want;
-                    L.flags = has_nl ? LF_HAS_NL : 0;
-                    L.pad = 0;
-                    L.ts = 0;
-                    L.tail = 0;
-                    a.sc.ml[li] = L;
-                    // token records: maximal runs of non-delimiter bytes, from the start / end bits
-                    uint32_t t = t0, cur = 0xFFFFFFFFu, carry = 0;
+            }
+            // ---- phases C and D: rounds of at most TOKCAP path nodes, whole lines only, one lane per node
+            uint32_t pend = want;
+            for (;;) {
+                if (__ballot_sync(0xFFFFFFFFu, pend != 0) == 0) break;
+                const uint32_t incl = warp_incl_scan(pend, lane);
+                const bool take = pend != 0 && incl <= TOKCAP;                  // a prefix of the pending lines
+                const uint32_t takeb = __ballot_sync(0xFFFFFFFFu, take);
+                const uint32_t ntk = __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(takeb));
+                const uint32_t first = incl - pend;                             // list slot of this line's first node
+                if (take) {
+                    // node list: maximal runs of non-delimiter bytes, from the start / end bits
+                    uint32_t t = first, cur = 0xFFFFFFFFu, carry = 0;
                     for (uint32_t q = ps; q < pe; q += 32) {
                         const uint32_t d = bm_bits(dlb, q);
                         const uint32_t pd = (d << 1) | carry;                       // "previous byte is a delimiter"
@@ -978,16 +981,129 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                             const uint32_t pos = q + bit;
                             if ((st >> bit) & 1u) {
                                 cur = pos;
-                                a.sc.tk_b[t] = wbase + pos;
-                                a.sc.tk_line[t] = li;
+                                tkp[t] = uint16_t(pos);
+                                tko[t] = uint8_t(lane);
                             } else if (cur != 0xFFFFFFFFu) {
-                                a.sc.tk_l[t++] = uint16_t(pos - cur);
+                                tkl[t++] = uint8_t(min(pos - cur, 255u));
                                 cur = 0xFFFFFFFFu;
                             }
                         }
                     }
-                    if (cur != 0xFFFFFFFFu) a.sc.tk_l[t++] = uint16_t(pe - cur);
+                    if (cur != 0xFFFFFFFFu) tkl[t++] = uint8_t(min(pe - cur, 255u));
                 }
+                __syncwarp();
+                // C: this lane's node -- strand, exact key, table probe, length
+                const bool is_tok = uint32_t(lane) < ntk;
+                uint32_t own = 0, nid = NO_NODE, nlen = 0, akey = 0, plus = 0;
+                bool plain = false;
+                if (is_tok) {
+                    const uint32_t tpos = tkp[lane], tlen = tkl[lane];
+                    own = tko[lane];
+                    plus = win[tpos - 1] == '>';
+                    uint64_t c0 = 0, c1 = 0;
+                    uint32_t c = 0;
+                    bool colon = false, clean = true;
+                    for (; c < tlen && c <= 16; ++c) {                              // chrom: at most 16 bytes, no NUL
+                        const uint32_t ch = win[tpos + c];
+                        if (ch == ':') {
+                            colon = true;
+                            break;
+                        }
+                        if (c == 16) break;
+                        clean &= ch != 0;
+                        if (c < 8) c0 |= uint64_t(ch) << (8 * c);
+                        else c1 |= uint64_t(ch) << (8 * (c - 8));
+                    }
+                    if (colon && clean) {
+                        uint32_t q = tpos + c + 1;
+                        const uint32_t end = tpos + tlen;
+                        const uint32_t q0 = q;
+                        uint32_t v0 = 0;
+                        for (; q < end; ++q) {
+                            const uint32_t d = uint32_t(win[q]) - '0';
+                            if (d > 9) break;
+                            v0 = v0 * 10 + d;
+                        }
+                        const uint32_t nd0 = q - q0;
+                        const uint32_t sep = q < end ? win[q] : 0u;
+                        if (nd0 >= 1 && nd0 <= 9 && !(nd0 > 1 && win[q0] == '0') && (sep == '-' || sep == '.')) {
+                            const uint32_t q1 = ++q;
+                            uint32_t v1 = 0;
+                            for (; q < end; ++q) {
+                                const uint32_t d = uint32_t(win[q]) - '0';
+                                if (d > 9) break;
+                                v1 = v1 * 10 + d;
+                            }
+                            const uint32_t nd1 = q - q1;
+                            if (q == end && nd1 >= 1 && nd1 <= 9 && !(nd1 > 1 && win[q1] == '0')) {
+                                const uint32_t kind = sep == '.' ? PN_ALT : 0u;
+                                uint32_t id = NO_NODE, alt_len = PN_NO_LEN;
+                                const bool found = pnode_find(a.tb, c0, c1, v0, v1 | kind, id, alt_len);
+                                akey = v0 | kind;
+                                if (!kind) {
+                                    if (v1 >= v0) {                                 // get_node_len :343-349
+                                        plain = true;
+                                        nlen = v1 - v0 + 1u;
+                                        nid = found ? id : NO_NODE;
+                                    }
+                                } else if (found && alt_len != PN_NO_LEN) {         // alt_node_len[name] :346
+                                    plain = true;
+                                    nlen = alt_len;
+                                    nid = id;
+                                }
+                            }
+                        }
+                    }
+                }
+                // D: per line -- sums of the node lengths left of every node, names that repeat a start
+                // value (the first-occurrence rules :206 and :269-271 would bite: exact route), verdicts
+                const uint32_t lfirst = __shfl_sync(0xFFFFFFFFu, first, own);
+                const uint32_t lcnt = __shfl_sync(0xFFFFFFFFu, pend, own);
+                const uint32_t idx = is_tok ? uint32_t(lane) - lfirst : 0u;
+                const uint32_t maxidx = __reduce_max_sync(0xFFFFFFFFu, idx);
+                uint64_t pre = 0;
+                bool clash = false;
+                for (uint32_t d = 1; d <= maxidx; ++d) {
+                    const uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, akey, d);
+                    const uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, nlen, d);
+                    if (d <= idx) {
+                        clash |= pa == akey;
+                        pre += pl;
+                    }
+                }
+                const uint32_t bad = __reduce_or_sync(0xFFFFFFFFu, (is_tok && (!plain || clash)) ? (1u << own) : 0u);
+                const uint64_t total = __shfl_sync(0xFFFFFFFFu, pre + nlen, is_tok ? lfirst + lcnt - 1u : 0u);
+                const uint32_t idl = __shfl_up_sync(0xFFFFFFFFu, nid, 1), sl = __shfl_up_sync(0xFFFFFFFFu, plus, 1);
+                const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, own), ltail = __shfl_sync(0xFFFFFFFFu, tail, own);
+                const uint32_t loff = __shfl_sync(0xFFFFFFFFu, s, own);
+                const uint32_t llen = __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), own);
+                const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
+                const bool emit = is_tok && idx >= 1 && !((bad >> own) & 1u) && idl != NO_NODE && nid != NO_NODE &&
+                                  (ok || (a.flags & FLAG_EXACT_CHECKS));
+                uint32_t redo = bad;                                                // lines of this round for the exact route
+                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, emit);
+                if (eb) {
+                    const uint32_t n_new = __popc(eb);
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(a.sc.cnt + 0, n_new);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    const uint32_t slot = base + __popc(eb & lt_mask);
+                    const bool room = uint64_t(base) + n_new <= a.sc.cap_links;
+                    if (!room) redo = takeb;                                        // scratch exhausted: exact route for all
+                    if (emit && slot < a.sc.cap_links) {
+                        LinkRec r;
+                        r.key = room ? link_key(idl, sl, nid, plus) : LINK_HOLE;
+                        r.off = wbase + loff;
+                        r.len = llen | (ok ? LINK_OK : 0u);
+                        *reinterpret_cast<uint4 *>(a.sc.links + slot) = *reinterpret_cast<const uint4 *>(&r);
+                    }
+                }
+                if (take) {
+                    if ((redo >> lane) & 1u) exact = true;
+                    else loc.n_multi++;
+                    pend = 0;
+                }
+                __syncwarp();
             }
             const uint32_t xb = __ballot_sync(0xFFFFFFFFu, exact);
             if (xb) {
@@ -1007,181 +1123,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
 }
 
 // ===========================================================================
-// token: one thread per path node
-// ===========================================================================
-__global__ void __launch_bounds__(FLAT_THREADS) token_kernel(const __grid_constant__ FilterArgs a) {
-    const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
-    Local loc;
-    for (uint32_t t = blockIdx.x * FLAT_THREADS + threadIdx.x; t < n_tok; t += gridDim.x * FLAT_THREADS) {
-        const uint32_t li = a.sc.tk_line[t];
-        if (li == NO_LINE) continue;
-        const uint32_t b = a.sc.tk_b[t], l = a.sc.tk_l[t];
-        // the first node's thread will read columns 7-9 at the end: start fetching them now
-        const bool first = t == a.sc.ml[li].tok0;
-        const uint32_t coords = first ? a.sc.ml[li].pe + 1 : 0;
-        if (first) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gaf + coords));
-            if (uint64_t(coords) + 32 < a.n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gaf + coords + 32));
-        }
-        // name hash (4 bytes a step), the colons on the way, and the name's node id (with the alt
-        // sequence length): the one byte-exact name check of the chain
-        const uint64_t al = uint64_t(b) & ~3ull;
-        const uint32_t sh = (b & 3u) * 8u;
-        TokHash h = tok_init();
-        uint32_t ncolon = 0, cpos = 0;
-        uint32_t nid = NO_NODE;
-        int64_t seq_len = -1;
-        uint64_t hv;
-        if (l <= 32 && al + 40 <= a.n) {
-            // the usual case: the whole name in registers, every load in flight at once
-            const uint32_t nw = (l + 3u) >> 2;
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a.gaf + al);
-            uint32_t raw[9], w[8];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) raw[k] = uint32_t(k) <= nw ? __ldg(wp + k) : 0u;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                w[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
-                if (uint32_t(k) == nw - 1 && (l & 3u)) w[k] &= (1u << (8u * (l & 3u))) - 1u;
-                if (uint32_t(k) < nw) {
-                    tok_step(h, w[k]);
-                    const uint32_t f = eq_bytes(w[k], 0x3A3A3A3Au);
-                    if (f) {
-                        ncolon += __popc(f);
-                        cpos = 4u * k + ((31 - __clz(f)) >> 3);
-                    }
-                }
-            }
-            hv = tok_value(h, l);
-            const uint64_t nh = node_hash(hv);
-            uint32_t i = uint32_t(nh) & a.tb.node_mask;
-            for (;;) {
-                const uint4 *sp = reinterpret_cast<const uint4 *>(a.tb.nodes + i);
-                const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-                if (!hi.z) break;
-                if (((uint64_t(lo.y) << 32) | lo.x) == nh && lo.w == l) {
-                    const uint32_t *q = reinterpret_cast<const uint32_t *>(a.tb.blob + lo.z);
-                    uint32_t diff = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (uint32_t(k) < nw) diff |= w[k] ^ __ldg(q + k);
-                    if (diff == 0) {
-                        nid = hi.z - 1u;
-                        seq_len = int64_t((uint64_t(hi.y) << 32) | hi.x);
-                        break;
-                    }
-                }
-                i = (i + 1) & a.tb.node_mask;
-            }
-        } else {
-            uint32_t curw = gaf_word(a, al);
-            for (uint32_t i = 0; i < l; i += 4) {
-                const uint32_t nxt = gaf_word(a, al + i + 4);
-                uint32_t w = __funnelshift_r(curw, nxt, sh);
-                curw = nxt;
-                const uint32_t rem = l - i;
-                if (rem < 4) w &= (1u << (8 * rem)) - 1u;
-                tok_step(h, w);
-                const uint32_t f = eq_bytes(w, 0x3A3A3A3Au);
-                if (f) {
-                    ncolon += __popc(f);
-                    cpos = i + ((31 - __clz(f)) >> 3);
-                }
-            }
-            hv = tok_value(h, l);
-            Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, 0, 0, loc);
-            Rec<GmemSrc>::Tok tk{b, l};
-            if (!rec.node_find(hv, tk, nid, seq_len)) nid = NO_NODE, seq_len = -1;
-        }
-        // chrom:start-end  or  chrom:pos.<anything>
-        uint32_t fl = __ldg(a.gaf + b - 1) == '>' ? TF_PLUS : 0;
-        uint32_t sval = 0;
-        int64_t nlen = 0;
-        if (ncolon == 1) {
-            uint32_t q = b + cpos + 1;
-            const uint32_t end = b + l;
-            uint32_t v0 = 0, nd0 = 0;
-            for (; q < end; ++q) {
-                const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
-                if (d > 9) break;
-                v0 = v0 * 10 + d;
-                ++nd0;
-            }
-            if (nd0 >= 1 && nd0 <= 9 && q < end) {
-                const uint32_t c = __ldg(a.gaf + q);
-                if (c == '.') {
-                    if (seq_len > 0 && seq_len <= 0x7FFFFFFF) {
-                        nlen = seq_len;
-                        fl |= TF_ALT | TF_PLAIN;
-                    }
-                } else if (c == '-') {
-                    uint32_t v1 = 0, nd1 = 0;
-                    for (++q; q < end; ++q) {
-                        const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
-                        if (d > 9) break;
-                        v1 = v1 * 10 + d;
-                        ++nd1;
-                    }
-                    nlen = int64_t(v1) - int64_t(v0) + 1;
-                    if (q == end && nd1 >= 1 && nd1 <= 9 && nlen > 0) fl |= TF_PLAIN;
-                }
-            }
-            sval = v0;
-        }
-        a.sc.tk_node[t] = nid;
-        a.sc.tk_len[t] = int32_t(nlen);
-        a.sc.tk_sval[t] = sval;
-        a.sc.tk_flags[t] = uint8_t(fl);
-        if (!(fl & TF_PLAIN)) atomicOr(&a.sc.ml[li].flags, LF_GENERAL);   // odd name: general() decides
-        if (first) {
-            // the first node's thread also reads Tlen, Ts, Te: digit-only columns 7-9 (validated by
-            // scan_parse).  The reference has bigints; this route stops at 18 digits and says so.
-            int64_t v[3];
-            uint32_t q = coords, too_long = 0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                int64_t x = 0;
-                uint32_t nd = 0;
-                for (;; ++q) {
-                    const uint32_t d = uint32_t(__ldg(a.gaf + q)) - '0';
-                    if (d > 9) break;
-                    nd += (x != 0 || d != 0);
-                    x = x * 10 + int64_t(d);
-                }
-                too_long |= nd > 18;
-                v[j] = x;
-                ++q;
-            }
-            a.sc.ml[li].ts = v[1];
-            a.sc.ml[li].tail = v[0] - v[2] - 1;
-            if (too_long) {
-                report(a, SVJG_BAD_RANGE, a.sc.ml[li].s);
-                atomicOr(&a.sc.ml[li].flags, LF_SKIP);
-            }
-        }
-    }
-}
-
-// ===========================================================================
-// clash: one thread per node — same start value and kind as an earlier node of the path means the
-// name could occur inside that one; then the first-occurrence rules (:206, :269-271) need general()
-// ===========================================================================
-__global__ void __launch_bounds__(FLAT_THREADS) clash_kernel(const __grid_constant__ FilterArgs a) {
-    const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
-    for (uint32_t t = blockIdx.x * FLAT_THREADS + threadIdx.x; t < n_tok; t += gridDim.x * FLAT_THREADS) {
-        const uint32_t li = a.sc.tk_line[t];
-        if (li == NO_LINE) continue;
-        const uint32_t t0 = a.sc.ml[li].tok0;
-        const uint32_t sv = a.sc.tk_sval[t], kind = a.sc.tk_flags[t] & TF_ALT;
-        bool clash = false;
-        for (uint32_t j = t0; j < t; ++j) clash |= (a.sc.tk_sval[j] == sv) && ((a.sc.tk_flags[j] & TF_ALT) == kind);
-        if (clash) atomicOr(&a.sc.ml[li].flags, LF_GENERAL);
-    }
-}
-
-// ===========================================================================
-// link: one thread per link (node t with its predecessor), both keys; the first node's thread
-// runs general() for a line that needs it
+// link: one thread per link record, both keys
 // ===========================================================================
 constexpr int LINK_STAGE = 1024;   // hits a block stages per round of FLAT_THREADS links
 
@@ -1189,42 +1131,26 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
     __shared__ uint32_t h_sv[LINK_STAGE], h_off[LINK_STAGE], h_len[LINK_STAGE];
     __shared__ uint32_t h_n;
     __shared__ unsigned long long h_base;
-    const uint32_t n_tok = min(a.sc.cnt[1], a.sc.cap_tok);
-    const bool all_links = a.flags & FLAG_EXACT_CHECKS;
+    const uint32_t n_links = min(a.sc.cnt[0], a.sc.cap_links);
     Local loc;
     if (threadIdx.x == 0) h_n = 0;
     __syncthreads();
-    for (uint32_t t0 = blockIdx.x * FLAT_THREADS; t0 < n_tok; t0 += gridDim.x * FLAT_THREADS) {
+    for (uint32_t t0 = blockIdx.x * FLAT_THREADS; t0 < n_links; t0 += gridDim.x * FLAT_THREADS) {
         const uint32_t t = t0 + threadIdx.x;
-        const uint32_t li = t < n_tok ? a.sc.tk_line[t] : NO_LINE;
-        if (li != NO_LINE) {
-            const GLine L = a.sc.ml[li];
-            const uint32_t len = L.e - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
-            if (L.flags & LF_SKIP) {
-            } else if (L.flags & LF_GENERAL) {
-                // the exact kernel runs general() on it; the first node's thread hands the line over
-                if (t == L.tok0) a.sc.general[atomicAdd(a.sc.cnt + 3, 1u)] = li;
-            } else if (t != L.tok0) {
-                // node lengths left of the link and in total; check_bkpt_overlap (:269-273)
-                int64_t pre = 0, total = 0;
-                for (uint32_t j = L.tok0; j < L.tok0 + L.ntok; ++j) {
-                    const int64_t nlen = a.sc.tk_len[j];
-                    total += nlen;
-                    if (j < t) pre += nlen;
-                }
-                const bool ok = (pre - L.ts >= a.d_over) && (total - pre - L.tail >= a.d_over);
-                const uint32_t fb = a.sc.tk_flags[t];
-                if (ok || all_links) {
-                    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
-                    rec.stage_sv = h_sv;
-                    rec.stage_off = h_off;
-                    rec.stage_len = h_len;
-                    rec.stage_n = &h_n;
-                    rec.stage_cap = LINK_STAGE;
-                    Rec<GmemSrc>::Tok A{a.sc.tk_b[t - 1], a.sc.tk_l[t - 1]}, B{a.sc.tk_b[t], a.sc.tk_l[t]};
-                    rec.link(A, a.sc.tk_node[t - 1], a.sc.tk_flags[t - 1] & TF_PLUS, B, a.sc.tk_node[t], fb & TF_PLUS, true, ok);
-                    if (rec.err) report(a, rec.err, L.s);
-                }
+        if (t < n_links) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(a.sc.links) + t);
+            const uint64_t key = (uint64_t(r.y) << 32) | r.x;
+            if (key != LINK_HOLE) {
+                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, r.z, r.w & ~LINK_OK, loc);
+                rec.stage_sv = h_sv;
+                rec.stage_off = h_off;
+                rec.stage_len = h_len;
+                rec.stage_n = &h_n;
+                rec.stage_cap = LINK_STAGE;
+                const Rec<GmemSrc>::Tok none{0, 0};
+                rec.link(none, uint32_t(key >> 33), int((key >> 32) & 1u), none, uint32_t(key) >> 1, int(key & 1u), true,
+                         (r.w & LINK_OK) != 0);
+                if (rec.err) report(a, rec.err, r.z);
             }
         }
         // flush the staged hits: one cursor atomic for the block, coalesced tuple stores,
@@ -1273,18 +1199,6 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
             rec.general();
         }
         if (rec.err) report(a, rec.err, off);
-    }
-    // multi-node lines whose columns are fine but whose node names need the literal string rules
-    const uint32_t n_gen = min(a.sc.cnt[3], a.sc.cap_ml);
-    for (uint32_t i = blockIdx.x * FLAT_THREADS + threadIdx.x; i < n_gen; i += gridDim.x * FLAT_THREADS) {
-        const GLine L = a.sc.ml[a.sc.general[i]];
-        const uint32_t len = L.e - L.s + ((L.flags & LF_HAS_NL) ? 1u : 0u);
-        Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, L.s, len, loc);
-        rec.ps = L.ps;
-        rec.pe = L.pe;
-        rec.reparse_coords(L.e);
-        rec.general();
-        if (rec.err) report(a, rec.err, L.s);
     }
     add_stats(a, loc);
 }
@@ -1352,44 +1266,29 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
     a.flags = t->filter_flags;
     const char *stop_env = getenv("SVJG_STOP_AFTER");          // profiling hook: run the chain up to A/B/C/D only
-    const int stop = (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'D') ? stop_env[0] - 'A' + 1 : 0;
+    const int stop = (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'B') ? stop_env[0] - 'A' + 1 : 0;
     if (stop == 1) a.flags |= 1u << 8;
 
     // scratch: one stream-ordered allocation, carved into the lists
     Scratch &sc = a.sc;
-    sc.cap_tok = uint32_t(n_bytes / 20 + 4096);       // a path node with its delimiter is rarely under 20 bytes
-    sc.cap_ml = uint32_t(n_bytes / 64 + 1024);
+    sc.cap_links = uint32_t(n_bytes / 20 + 4096);     // a path node with its delimiter is rarely under 20 bytes
     sc.cap_exact = uint32_t(n_bytes / 16 + 64);       // a line shorter than 16 bytes cannot hold 12 columns
     if (const char *tiny = getenv("SVJG_TEST_TINY_SCRATCH")) {   // test hook: force the "no room" fallbacks
-        if (tiny[0] == '1') sc.cap_tok = 64, sc.cap_ml = 16;
+        if (tiny[0] == '1') sc.cap_links = 64;
     }
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o_cnt = 0, o_ml = up(64), o_node = o_ml + up(size_t(sc.cap_ml) * sizeof(GLine)),
-                 o_b = o_node + up(size_t(sc.cap_tok) * 4), o_line = o_b + up(size_t(sc.cap_tok) * 4),
-                 o_sval = o_line + up(size_t(sc.cap_tok) * 4), o_len = o_sval + up(size_t(sc.cap_tok) * 4),
-                 o_l = o_len + up(size_t(sc.cap_tok) * 4), o_fl = o_l + up(size_t(sc.cap_tok) * 2),
-                 o_ex = o_fl + up(size_t(sc.cap_tok)), o_gen = o_ex + up(size_t(sc.cap_exact) * 4),
-                 total = o_gen + up(size_t(sc.cap_ml) * 4);
+    const size_t o_cnt = 0, o_links = up(64), o_ex = o_links + up(size_t(sc.cap_links) * sizeof(LinkRec)),
+                 total = o_ex + up(size_t(sc.cap_exact) * 4);
     uint8_t *ws = nullptr;
     SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     sc.cnt = reinterpret_cast<uint32_t *>(ws + o_cnt);
-    sc.ml = reinterpret_cast<GLine *>(ws + o_ml);
-    sc.tk_node = reinterpret_cast<uint32_t *>(ws + o_node);
-    sc.tk_b = reinterpret_cast<uint32_t *>(ws + o_b);
-    sc.tk_line = reinterpret_cast<uint32_t *>(ws + o_line);
-    sc.tk_sval = reinterpret_cast<uint32_t *>(ws + o_sval);
-    sc.tk_len = reinterpret_cast<int32_t *>(ws + o_len);
-    sc.tk_l = reinterpret_cast<uint16_t *>(ws + o_l);
-    sc.tk_flags = ws + o_fl;
+    sc.links = reinterpret_cast<LinkRec *>(ws + o_links);
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
-    sc.general = reinterpret_cast<uint32_t *>(ws + o_gen);
     SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
 
     const int scan_grid = int(std::min<uint32_t>((a.n_tiles + WARPS - 1) / WARPS, uint32_t(g_scan_grid_cap)));
     const int flat_grid = g_sms * 8;
     scan_parse_kernel<<<scan_grid, THREADS, SMEM_BYTES, st>>>(a);
-    if (stop == 0 || stop >= 3) token_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
-    if (stop == 0 || stop >= 4) clash_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
     if (stop == 0) {
         link_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
         exact_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);

@@ -66,6 +66,33 @@ struct NodeSlot {
 };
 static_assert(sizeof(NodeSlot) == 32, "NodeSlot must be one sector");
 
+// Plain node names -- chrom:start-end (reference node) or chrom:pos.k (alt node), chrom of at most
+// 16 bytes without NUL, numbers of 1-9 digits without leading zeros -- have an exact 24-byte key, so
+// scan_parse resolves them from shared memory with one probe and no name bytes are compared.  Any
+// other name is reachable only through the name-hash table above (the exact route).
+constexpr uint32_t PN_ALT = 0x80000000u;       // in PNodeSlot::b: chrom:pos.k
+constexpr uint32_t PN_NO_LEN = 0xFFFFFFFFu;    // alt node without a usable GFA sequence length
+struct PNodeSlot {
+    uint64_t c0, c1;       // chrom bytes, little endian, zero padded
+    uint32_t a;            // start / pos
+    uint32_t b;            // end, or k | PN_ALT
+    uint32_t id1;          // node id + 1 (same ids as NodeSlot); 0 = empty slot
+    uint32_t alt_len;      // alt node: GFA sequence length (1 .. 2^31-1) or PN_NO_LEN
+};
+static_assert(sizeof(PNodeSlot) == 32, "PNodeSlot must be one sector");
+SVJG_HD uint32_t pnode_hash(uint64_t c0, uint64_t c1, uint32_t a, uint32_t b) {
+    uint32_t h = uint32_t(c0) * 0x9E3779B1u;
+    h = (h ^ uint32_t(c0 >> 32)) * 0x85EBCA77u;
+    h = (h ^ uint32_t(c1)) * 0xC2B2AE3Du;
+    h = (h ^ uint32_t(c1 >> 32)) * 0x27D4EB2Fu;
+    h = (h ^ a) * 0x165667B1u;
+    h = (h ^ b ^ (h >> 15)) * 0x2C1B3C6Du;
+    h ^= h >> 13;
+    h *= 0x297A2D39u;
+    h ^= h >> 16;
+    return h;
+}
+
 constexpr uint32_t ENTRY_POISON = 0xFFFFFFFFu;  // entry on which the reference raises
 
 struct DevTables {
@@ -73,10 +100,11 @@ struct DevTables {
     const NodeSlot *nodes;
     const uint8_t *blob;
     const uint32_t *entries;   // 2*sv_index + allele, or ENTRY_POISON
+    const PNodeSlot *pnodes;
     uint32_t link_mask;        // capacity - 1
     uint32_t node_mask;        // capacity - 1 (0 capacity is never used: min 2 slots)
+    uint32_t pnode_mask;
     uint32_t num_sv;
-    uint32_t pad;
 };
 
 }  // namespace svjg

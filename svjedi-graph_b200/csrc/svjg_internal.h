@@ -14,13 +14,14 @@ struct svjg_tables {
     std::vector<std::string> sv_ids;          // byte-sorted distinct sv ids
     std::vector<svjg::LinkSlot> links;
     std::vector<svjg::NodeSlot> nodes;
+    std::vector<svjg::PNodeSlot> pnodes;
     std::vector<uint8_t> blob;
     std::vector<uint32_t> entries;
     uint32_t n_keys = 0, n_link_slots = 0, n_alt = 0, n_nodes = 0;
     uint32_t filter_flags = 0;                // SVJG_FLAG_* passed to the filter kernel
     // device image
     int device = -1;
-    void *d_links = nullptr, *d_nodes = nullptr, *d_blob = nullptr, *d_entries = nullptr;
+    void *d_links = nullptr, *d_nodes = nullptr, *d_blob = nullptr, *d_entries = nullptr, *d_pnodes = nullptr;
     svjg::DevTables dev{};
     // lazily created workspace of svjg_filter_host
     svjg::HostWs *ws = nullptr;

@@ -427,6 +427,37 @@ static uint64_t hash_bytes(const char *s, size_t n) {
     return tok_value(h, uint32_t(n));
 }
 
+// exact key of a plain node name (see PNodeSlot); false for any other name
+static bool plain_key(const std::string &name, PNodeSlot &k) {
+    const size_t n = name.size();
+    const size_t c = name.find(':');
+    if (c == std::string::npos || c > 16 || name.find(':', c + 1) != std::string::npos) return false;
+    uint8_t chrom[16] = {0};
+    for (size_t i = 0; i < c; ++i) {
+        if (name[i] == '\0') return false;
+        chrom[i] = uint8_t(name[i]);
+    }
+    auto number = [&](size_t b, size_t e, uint32_t &v) {     // 1-9 digits, no leading zero
+        if (e <= b || e - b > 9 || (e - b > 1 && name[b] == '0')) return false;
+        v = 0;
+        for (size_t i = b; i < e; ++i) {
+            if (name[i] < '0' || name[i] > '9') return false;
+            v = v * 10 + uint32_t(name[i] - '0');
+        }
+        return true;
+    };
+    size_t q = c + 1;
+    while (q < n && name[q] >= '0' && name[q] <= '9') ++q;
+    if (q >= n || (name[q] != '-' && name[q] != '.')) return false;
+    uint32_t a, b;
+    if (!number(c + 1, q, a) || !number(q + 1, n, b)) return false;
+    memcpy(&k.c0, chrom, 8);
+    memcpy(&k.c1, chrom + 8, 8);
+    k.a = a;
+    k.b = b | (name[q] == '.' ? PN_ALT : 0u);
+    return true;
+}
+
 static uint32_t pow2_at_least(uint64_t n) {
     uint64_t c = 2;
     while (c < n) c <<= 1;
@@ -545,6 +576,25 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         uint32_t i = uint32_t(s.hash) & (ncap - 1);
         while (t->nodes[i].id1) i = (i + 1) & (ncap - 1);
         t->nodes[i] = s;
+    }
+    // plain names once more under their exact key (same ids)
+    {
+        std::vector<PNodeSlot> plain;
+        for (size_t id = 0; id < nodes.size(); ++id) {
+            PNodeSlot s{};
+            if (!plain_key(nodes[id].first, s)) continue;
+            s.id1 = uint32_t(id) + 1;
+            const int64_t sl = nodes[id].second;
+            s.alt_len = (sl > 0 && sl <= 0x7FFFFFFF) ? uint32_t(sl) : PN_NO_LEN;
+            plain.push_back(s);
+        }
+        uint32_t pcap = pow2_at_least(plain.size() * 2 + 2);
+        t->pnodes.assign(pcap, PNodeSlot{});
+        for (auto &s : plain) {
+            uint32_t i = pnode_hash(s.c0, s.c1, s.a, s.b) & (pcap - 1);
+            while (t->pnodes[i].id1) i = (i + 1) & (pcap - 1);
+            t->pnodes[i] = s;
+        }
     }
     // pad the blob so 4-byte reads at the tail stay in bounds
     t->blob.insert(t->blob.end(), 16, 0);
@@ -812,7 +862,7 @@ extern "C" uint32_t svjg_tables_num_alt_nodes(const svjg_tables *t) { return t ?
 extern "C" uint64_t svjg_tables_device_bytes(const svjg_tables *t) {
     if (!t) return 0;
     return t->links.size() * sizeof(LinkSlot) + t->nodes.size() * sizeof(NodeSlot) + t->blob.size() +
-           t->entries.size() * sizeof(uint32_t);
+           t->entries.size() * sizeof(uint32_t) + t->pnodes.size() * sizeof(PNodeSlot);
 }
 extern "C" const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len) {
     if (!t || i >= t->sv_ids.size()) return nullptr;
