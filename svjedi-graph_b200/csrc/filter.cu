@@ -55,15 +55,17 @@ constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunk
 constexpr int HEAD_SPAN = 96;                  // bytes searched for the tabs of columns 1-5 on the fast route
 constexpr int TAIL_SPAN = 96;                  // bytes searched for the tabs of columns 7-12
 constexpr int SPARE = 176;                     // readable bytes behind the window for those fixed-span reads
-constexpr int NLCAP = 336;                     // newlines per window (more => some line is shorter than 16 bytes)
+constexpr int NLCAP = 256;                     // newlines per window (more => some line is shorter than 21 bytes)
 constexpr int TOKCAP = 32;                     // path nodes resolved per round of phases C/D (one lane each)
 static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit");
 
 // shared memory map of ONE warp of scan_parse (bytes)
 constexpr int OFF_WIN = 0;
-constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline positions, ascending  u16[NLCAP]
 constexpr int BMWORDS = NPAIRS + 7;                         // bitmap words: reads may run a few words past the window
-constexpr int OFF_TABB = (OFF_NL + NLCAP * 2 + 15) & ~15;   // tab bitmap        u32[BMWORDS]
+constexpr int NLW = (NPAIRS + 31) / 32;                     // newline bitmap words a lane turns into list entries
+constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline bitmap u32[BMWORDS] during phase A, then the
+constexpr int NL_BYTES = BMWORDS * 4 > NLCAP * 2 ? BMWORDS * 4 : NLCAP * 2;   // newline positions, ascending, u16[NLCAP]
+constexpr int OFF_TABB = (OFF_NL + NL_BYTES + 15) & ~15;    // tab bitmap        u32[BMWORDS]
 constexpr int OFF_DLB = OFF_TABB + BMWORDS * 4;             // delimiter bitmap  u32[BMWORDS]
 constexpr int OFF_TKP = OFF_DLB + BMWORDS * 4;              // node list of a round: window position u16[TOKCAP],
 constexpr int OFF_TKL = OFF_TKP + TOKCAP * 2;               //   length u8[TOKCAP] (255 = longer),
@@ -108,6 +110,7 @@ struct FilterArgs {
     unsigned long long *stats;   // svjg_filter_stats as 8 x u64
     uint32_t n_tiles;
     uint32_t flags;
+    uint32_t one;                // 1 (see IsNewline)
     Scratch sc;
 };
 
@@ -174,14 +177,26 @@ __device__ __forceinline__ uint32_t mask16(const uint4 &v, F cls) {
     hi = __dp4a(cls(v.w), 0x80402010u, hi);
     return (lo >> 7) | (hi << 1);
 }
+// The same classes for the byte-parallel phase.  `one` is 1 at run time but opaque to the compiler: the
+// carry add becomes an IMAD on the FMA pipe, next to the LOP3s on the ALU pipe (each pipe takes one
+// warp instruction every other cycle, so the mix issues faster than ALU work alone).
 struct IsNewline {
-    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return eq_bytes(w, 0x0A0A0A0Au); }
+    uint32_t one;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
+        return lop_nor_and(lop_and_xor(w, SVJG_M7, 0x0A0A0A0Au) * one + SVJG_M7, w, SVJG_H8);
+    }
 };
 struct IsTab {
-    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return eq_bytes(w, 0x09090909u); }
+    uint32_t one;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
+        return lop_nor_and(lop_and_xor(w, SVJG_M7, 0x09090909u) * one + SVJG_M7, w, SVJG_H8);
+    }
 };
 struct IsDelim {
-    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return delim_bytes(w); }
+    uint32_t one;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
+        return lop_nor_and(lop_and_xor(w, 0x7D7D7D7Du, 0x3C3C3C3Cu) * one + SVJG_M7, w, SVJG_H8);
+    }
 };
 
 __device__ __noinline__ void report(const FilterArgs &a, uint32_t code, uint64_t line_off) {
@@ -693,9 +708,32 @@ __device__ __forceinline__ uint32_t bm_bits(const uint32_t *bm, uint32_t pos) {
 // the low n bits (n may exceed 32 or be <= 0)
 __device__ __forceinline__ uint32_t low_bits(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, uint32_t(max(n, 0))); }
 
+// four ASCII digits, the first one in the low byte -> their value (a zero byte counts as '0')
+__device__ __forceinline__ uint32_t dec4(uint32_t w) {
+    uint32_t t = w & 0x0F0F0F0Fu;
+    t = t * 10u + (t >> 8);                     // bytes 0 and 2: two-digit values
+    t &= 0x00FF00FFu;
+    return (t * 100u + (t >> 16)) & 0xFFFFu;
+}
+// word with its lowest min(n, 4) bytes cleared (n <= 0: unchanged)
+__device__ __forceinline__ uint32_t clear_low_bytes(uint32_t w, int n) {
+    return w & __funnelshift_lc(0u, 0xFFFFFFFFu, uint32_t(max(n, 0)) * 8u);
+}
 // value of the decimal digits in window bytes [lo, hi) (validated: digits only, hi > lo); false
-// when there are more than 18 significant digits
+// when there are more than 18 significant digits.  Up to 12 digits without a loop: the 12 bytes
+// that end at hi as three words, the bytes in front of lo masked away.
 __device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
+    const uint32_t n = hi - lo;
+    if (n <= 12) {
+        const uint32_t base = hi - 12u, al = base & ~3u, sh = (base & 3u) * 8u;
+        const uint32_t r0 = lds32(win, al), r1 = lds32(win, al + 4), r2 = lds32(win, al + 8), r3 = lds32(win, al + 12);
+        const int m = 12 - int(n);              // bytes of the 12 that are not ours
+        const uint32_t g0 = dec4(clear_low_bytes(__funnelshift_r(r0, r1, sh), m));
+        const uint32_t g1 = dec4(clear_low_bytes(__funnelshift_r(r1, r2, sh), m - 4));
+        const uint32_t g2 = dec4(clear_low_bytes(__funnelshift_r(r2, r3, sh), m - 8));
+        out = int64_t(uint64_t(g0) * 100000000ull + uint64_t(g1 * 10000u + g2));
+        return true;
+    }
     int64_t x = 0;
     uint32_t nd = 0;
     for (uint32_t q = lo; q < hi; ++q) {
@@ -738,16 +776,19 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
     uint16_t *nl = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_NL);
     uint32_t *tabb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_TABB);   // bit i: window byte i is a tab
     uint32_t *dlb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_DLB);     // bit i: ... is '<' or '>'
+    uint32_t *nlb = reinterpret_cast<uint32_t *>(nl);                                        // bit i: ... is a newline (phase A only)
     uint16_t *tkp = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_TKP);
     uint8_t *tkl = smem_all + warp * WARP_SMEM + OFF_TKL, *tko = smem_all + warp * WARP_SMEM + OFF_TKO;
     uint64_t *mbar = &mbars[warp];
 
     if (lane == 0) mbar_init(mbar, 1);
     for (int i = NPAIRS + lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0;
+    for (int i = WIN + lane; i < WIN + SPARE; i += 32) win[i] = 0;   // never written by the copies
     __syncwarp();
     uint32_t phase = 0;
     Local loc;
     const bool stop_after_scan = ((a.flags >> 8) & 7u) == 1u;     // profiling hook (SVJG_STOP_AFTER=A)
+    const uint32_t one = a.one;
     const uint32_t n_workers = gridDim.x * WARPS;
 
     for (uint32_t tile = blockIdx.x * WARPS + warp; tile < a.n_tiles; tile += n_workers) {
@@ -769,59 +810,71 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
         }
         for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
         if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;               // "newline" in front of byte 0 of the file
-        for (uint32_t i = valid_end + lane; i < WIN + SPARE; i += 32) win[i] = 0;
+        for (uint32_t i = valid_end + lane; i < WIN; i += 32) win[i] = 0;
         if (bulk) {
             mbar_wait(mbar, phase);
             phase ^= 1;
         }
         __syncwarp();
 
-        // ---- phase A: byte classes.  A lane takes two adjacent 16-byte chunks = one word of each bitmap.
-        // Newlines become the ordered list of line ends from HEAD-1 on; tabs and path delimiters stay
-        // bitmaps.  The scan stops behind the tile once the last owned line has its end.
+        // ---- phase A: byte classes.  A lane takes two adjacent 16-byte chunks = one word of each of the
+        // three bitmaps (newlines, tabs, path delimiters).  The scan stops behind the tile once the last
+        // owned line has its end.
         const uint32_t own_end = min(uint32_t(HEAD + TILE), valid_end);   // lines starting before own_end are ours
-        uint32_t n_nl = 0, n_own = 0;
+        uint32_t n_words = 0;
         for (int c0 = 0; c0 < NPAIRS; c0 += 32) {
-            if (uint32_t(c0) * 32u >= own_end && n_nl > n_own) break;
             const int c = c0 + lane;
             const uint32_t p0 = uint32_t(c) * 32u;
             uint32_t m = 0;
             if (c < NPAIRS) {
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(win + p0);
                 const uint4 v1 = *reinterpret_cast<const uint4 *>(win + p0 + 16);
-                m = mask16(v0, IsNewline()) | (mask16(v1, IsNewline()) << 16);
-                tabb[c] = mask16(v0, IsTab()) | (mask16(v1, IsTab()) << 16);
-                dlb[c] = mask16(v0, IsDelim()) | (mask16(v1, IsDelim()) << 16);
+                m = mask16(v0, IsNewline{one}) | (mask16(v1, IsNewline{one}) << 16);
+                tabb[c] = mask16(v0, IsTab{one}) | (mask16(v1, IsTab{one}) << 16);
+                dlb[c] = mask16(v0, IsDelim{one}) | (mask16(v1, IsDelim{one}) << 16);
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
+                nlb[c] = m;
             }
-            const uint32_t cnt = __popc(m);
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, cnt != 0);
-            if (!bal) continue;
-            uint32_t q, total;
-            if (__ballot_sync(0xFFFFFFFFu, cnt > 1) == 0) {
-                q = __popc(bal & lt_mask);
-                total = __popc(bal);
-            } else {                                                      // two newlines within 32 bytes (rare)
-                const uint32_t incl = warp_incl_scan(cnt, lane);
-                q = incl - cnt;
-                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            n_words = min(uint32_t(c0) + 32u, uint32_t(NPAIRS));
+            // behind the tile: a newline at or after own_end - 1 ends the last owned line
+            const bool ends_it = (m & ~low_bits(int(own_end) - 1 - int(p0))) != 0;
+            if ((uint32_t(c0) + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, ends_it)) break;
+        }
+        __syncwarp();
+        // newline bitmap -> ordered list of line ends from HEAD-1 on: every lane takes a run of words
+        // (held in registers: the list overwrites the bitmap), one warp scan places its newlines
+        uint32_t n_nl, n_own;
+        {
+            const uint32_t per = (n_words + 31u) >> 5, j0 = uint32_t(lane) * per;
+            uint32_t mw[NLW];
+            uint32_t cnt = 0, own = 0;
+#pragma unroll
+            for (int i = 0; i < NLW; ++i) {
+                const uint32_t j = j0 + uint32_t(i);
+                mw[i] = (uint32_t(i) < per && j < n_words) ? nlb[j] : 0u;
+                cnt += __popc(mw[i]);
+                own += __popc(mw[i] & low_bits(int(own_end) - 1 - int(j * 32u)));   // newline at p starts an owned line iff p + 1 < own_end
             }
-            // newline at p starts an owned line iff p + 1 < own_end
-            const uint32_t mo = m & low_bits(int(own_end) - 1 - int(p0));
-            n_own += __reduce_add_sync(0xFFFFFFFFu, uint32_t(__popc(mo)));
-            uint32_t idx = n_nl + q;
-            while (m) {
-                if (idx < NLCAP) nl[idx] = uint16_t(p0 + uint32_t(__ffs(m) - 1));
-                ++idx;
-                m &= m - 1;
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            n_nl = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            n_own = __reduce_add_sync(0xFFFFFFFFu, own);
+            uint32_t idx = incl - cnt;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NLW; ++i) {
+                uint32_t m = mw[i];
+                while (m) {
+                    if (idx < NLCAP) nl[idx] = uint16_t((j0 + uint32_t(i)) * 32u + uint32_t(__ffs(m) - 1));
+                    ++idx;
+                    m &= m - 1;
+                }
             }
-            n_nl += total;
         }
         __syncwarp();
         if (stop_after_scan) continue;
 
         if (n_nl > NLCAP) {
-            // that many lines in 5 KiB: some line is shorter than 16 bytes and cannot hold 12 columns
+            // that many lines in 5 KiB: some line is shorter than 21 bytes and cannot hold 12 columns
             if (lane == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
             __syncwarp();
             continue;
@@ -1265,6 +1318,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
     a.flags = t->filter_flags;
+    a.one = 1;
     const char *stop_env = getenv("SVJG_STOP_AFTER");          // profiling hook: run the chain up to A/B/C/D only
     const int stop = (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'B') ? stop_env[0] - 'A' + 1 : 0;
     if (stop == 1) a.flags |= 1u << 8;
