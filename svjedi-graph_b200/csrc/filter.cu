@@ -67,7 +67,8 @@ constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline bitmap u3
 constexpr int NL_BYTES = BMWORDS * 4 > NLCAP * 2 ? BMWORDS * 4 : NLCAP * 2;   // newline positions, ascending, u16[NLCAP]
 constexpr int OFF_TABB = (OFF_NL + NL_BYTES + 15) & ~15;    // tab bitmap        u32[BMWORDS]
 constexpr int OFF_DLB = OFF_TABB + BMWORDS * 4;             // delimiter bitmap  u32[BMWORDS]
-constexpr int OFF_TKP = OFF_DLB + BMWORDS * 4;              // node list of a round: window position u16[TOKCAP],
+constexpr int OFF_XDB = OFF_DLB + BMWORDS * 4;              // non-digit bitmap  u32[BMWORDS]
+constexpr int OFF_TKP = OFF_XDB + BMWORDS * 4;              // node list of a round: window position u16[TOKCAP],
 constexpr int OFF_TKL = OFF_TKP + TOKCAP * 2;               //   length u8[TOKCAP] (255 = longer),
 constexpr int OFF_TKO = OFF_TKL + TOKCAP;                   //   lane of its line u8[TOKCAP]
 constexpr int WARP_SMEM = (OFF_TKO + TOKCAP + 127) & ~127;
@@ -190,6 +191,12 @@ struct IsTab {
     uint32_t one;
     __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
         return lop_nor_and(lop_and_xor(w, SVJG_M7, 0x09090909u) * one + SVJG_M7, w, SVJG_H8);
+    }
+};
+struct IsNonDigit {
+    uint32_t one;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
+        return lop_or_and(lop_and_xor(w, SVJG_M7, 0x30303030u) * one + 0x76767676u, w, SVJG_H8);
     }
 };
 struct IsDelim {
@@ -707,6 +714,21 @@ __device__ __forceinline__ uint32_t bm_bits(const uint32_t *bm, uint32_t pos) {
 }
 // the low n bits (n may exceed 32 or be <= 0)
 __device__ __forceinline__ uint32_t low_bits(int n) { return __funnelshift_lc(0xFFFFFFFFu, 0u, uint32_t(max(n, 0))); }
+// first set bit of the bitmap at or behind `pos` and in front of `end`; `end` (or more) if there is none
+__device__ __forceinline__ uint32_t next_tab(const uint32_t *bm, uint32_t pos, uint32_t end) {
+    for (uint32_t q = pos; q < end; q += 32) {
+        const uint32_t m = bm_bits(bm, q) & low_bits(int(end - q));
+        if (m) return q + uint32_t(__ffs(m) - 1);
+    }
+    return end;
+}
+// 64 bits of a byte-indexed bitmap starting at bit `pos`; the low n bits of 64
+__device__ __forceinline__ uint64_t bm64(const uint32_t *bm, uint32_t pos) {
+    const uint32_t w = pos >> 5, sh = pos & 31u;
+    const uint32_t b0 = bm[w], b1 = bm[w + 1], b2 = bm[w + 2];
+    return (uint64_t(__funnelshift_r(b1, b2, sh)) << 32) | __funnelshift_r(b0, b1, sh);
+}
+__device__ __forceinline__ uint64_t low_bits64(int n) { return (uint64_t(low_bits(n - 32)) << 32) | low_bits(n); }
 
 // four ASCII digits, the first one in the low byte -> their value (a zero byte counts as '0')
 __device__ __forceinline__ uint32_t dec4(uint32_t w) {
@@ -776,13 +798,14 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
     uint16_t *nl = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_NL);
     uint32_t *tabb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_TABB);   // bit i: window byte i is a tab
     uint32_t *dlb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_DLB);     // bit i: ... is '<' or '>'
+    uint32_t *xdb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_XDB);     // bit i: ... is not '0'..'9'
     uint32_t *nlb = reinterpret_cast<uint32_t *>(nl);                                        // bit i: ... is a newline (phase A only)
     uint16_t *tkp = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_TKP);
     uint8_t *tkl = smem_all + warp * WARP_SMEM + OFF_TKL, *tko = smem_all + warp * WARP_SMEM + OFF_TKO;
     uint64_t *mbar = &mbars[warp];
 
     if (lane == 0) mbar_init(mbar, 1);
-    for (int i = NPAIRS + lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0;
+    for (int i = NPAIRS + lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0, xdb[i] = 0;
     for (int i = WIN + lane; i < WIN + SPARE; i += 32) win[i] = 0;   // never written by the copies
     __syncwarp();
     uint32_t phase = 0;
@@ -832,6 +855,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 m = mask16(v0, IsNewline{one}) | (mask16(v1, IsNewline{one}) << 16);
                 tabb[c] = mask16(v0, IsTab{one}) | (mask16(v1, IsTab{one}) << 16);
                 dlb[c] = mask16(v0, IsDelim{one}) | (mask16(v1, IsDelim{one}) << 16);
+                xdb[c] = mask16(v0, IsNonDigit{one}) | (mask16(v1, IsNonDigit{one}) << 16);
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
                 nlb[c] = m;
             }
@@ -899,80 +923,46 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                     exact = true;              // runs past the window
                 }
                 if (!exact) {
+                    // Shape of a plain line, read off the tab bitmap and the non-digit bitmap:
+                    //   name TAB digits TAB digits TAB digits TAB strand TAB path TAB (digits TAB) x 5 digits [TAB tags]
+                    // A run of digits and single tabs must follow the first tab up to the strand, and the
+                    // sixth tab up to the tags (or the end of the line).  Anything else: the exact route.
                     bool plain = e > s && !py_space(win[e - 1]);
-                    // columns 1-6: the first six tabs among the first HEAD_SPAN bytes (positions relative to s,
-                    // one byte each, newest in the low byte)
-                    uint32_t r0 = 0, r1 = 0, nt = 0;
-                    {
-                        const int nbits = int(e - s);
-#pragma unroll
-                        for (int j = 0; j < HEAD_SPAN / 32; ++j) {
-                            uint32_t m = bm_bits(tabb, s + 32u * j) & low_bits(nbits - 32 * j);
-                            while (m && nt < 6) {
-                                const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                                m &= m - 1;
-                                r1 = __funnelshift_l(r0, r1, 8);
-                                r0 = (r0 << 8) | pos;
-                                ++nt;
-                            }
-                        }
-                    }
-                    // a long path pushes its tab out of the span: five tabs found, look for the sixth
-                    uint32_t p6 = e;
-                    if (nt == 6) {
-                        p6 = s + (r0 & 255u);
-                    } else if (nt == 5) {
-                        r1 = __funnelshift_l(r0, r1, 8);
-                        r0 <<= 8;
-                        for (uint32_t q = s + HEAD_SPAN; q < e; q += 32) {
-                            const uint32_t m = bm_bits(tabb, q) & low_bits(int(e - q));
-                            if (m) {
-                                p6 = q + uint32_t(__ffs(m) - 1);
-                                break;
-                            }
-                        }
-                    }
-                    plain &= nt >= 5 && p6 < e;
-                    const uint32_t p1 = s + ((r1 >> 8) & 255u), p2 = s + (r1 & 255u), p3 = s + (r0 >> 24),
-                                   p4 = s + ((r0 >> 16) & 255u), p5 = s + ((r0 >> 8) & 255u);
-                    ps = p5 + 1;
-                    pe = p6;
-                    plain &= pe > ps;
-                    // columns 7-12: the next six tabs (or five and the end of the line) within TAIL_SPAN bytes
-                    uint32_t p7 = 0, p8 = 0, p9 = 0, p10 = 0, p11 = 0, p12 = 0;
-                    if (plain) {
-                        const uint32_t t0 = p6 + 1;
-                        const int nbits = int(e - t0);
-                        uint32_t q0 = 0, q1 = 0, n2 = 0;
-#pragma unroll
-                        for (int j = 0; j < TAIL_SPAN / 32; ++j) {
-                            uint32_t m = bm_bits(tabb, t0 + 32u * j) & low_bits(nbits - 32 * j);
-                            while (m && n2 < 6) {
-                                const uint32_t pos = 32u * j + uint32_t(__ffs(m) - 1);
-                                m &= m - 1;
-                                q1 = __funnelshift_l(q0, q1, 8);
-                                q0 = (q0 << 8) | pos;
-                                ++n2;
-                            }
-                        }
-                        if (n2 == 5 && nbits <= TAIL_SPAN) {                               // no tab after column 12
-                            q1 = __funnelshift_l(q0, q1, 8);
-                            q0 = (q0 << 8) | uint32_t(nbits);
-                            ++n2;
-                        }
-                        plain = n2 == 6;
-                        p7 = t0 + ((q1 >> 8) & 255u), p8 = t0 + (q1 & 255u), p9 = t0 + (q0 >> 24);
-                        c6 = p6, c7 = p7, c8 = p8, c9 = p9;
-                        p10 = t0 + ((q0 >> 16) & 255u), p11 = t0 + ((q0 >> 8) & 255u), p12 = t0 + (q0 & 255u);
-                    }
-                    if (plain) {
-                        // no empty integer column, Alen not zero, digits only in columns 2-4 and 7-12
-                        const bool w_ok = (p2 - p1 > 1u) & (p3 - p2 > 1u) & (p4 - p3 > 1u) & (p7 - p6 > 1u) &
-                                          (p8 - p7 > 1u) & (p9 - p8 > 1u) & (p10 - p9 > 1u) & (p11 - p10 > 1u) &
-                                          (p12 - p11 > 1u);
-                        plain = w_ok && win[p10 + 1] != '0';
-                        if (plain) plain = count_nondigits(win, p1 + 1, p4) == 2u && count_nondigits(win, p6 + 1, p12) == 5u;
-                    }
+                    const uint32_t t1 = next_tab(tabb, s, e);
+                    plain &= t1 < e;
+                    const uint32_t n2 = t1 + 1u;                                          // first byte of column 2
+                    const uint32_t tw = bm_bits(tabb, n2);
+                    const uint32_t xa = bm_bits(xdb, n2) & ~tw;                           // neither digit nor tab (the newline is one)
+                    plain &= xa != 0;
+                    const uint32_t l2 = uint32_t(__ffs(xa)) - 1u;                         // length of the run: columns 2-4 and their tabs
+                    const uint32_t ta = tw & low_bits(int(l2));
+                    // tabs 2, 3 and 4 and nothing else, the last one right in front of the strand, no empty column
+                    plain &= __popc(ta) == 3 && (ta >> ((l2 - 1u) & 31u)) == 1u && (ta & ((ta >> 1) | 1u)) == 0;
+                    const uint32_t n5 = n2 + l2;                                          // strand
+                    ps = next_tab(tabb, n5, e) + 1u;
+                    pe = next_tab(tabb, ps, e);
+                    plain &= pe < e && pe > ps;
+                    const uint32_t n7 = pe + 1u;                                          // first byte of column 7
+                    uint64_t tt = bm64(tabb, n7);
+                    const uint64_t xt = bm64(xdb, n7) & ~tt;
+                    plain &= xt != 0;
+                    const uint32_t l7 = uint32_t(__ffsll((long long)xt)) - 1u;            // length of the run: columns 7-12 and their tabs
+                    tt &= low_bits64(int(l7));
+                    const uint32_t ntab = uint32_t(__popcll(tt));
+                    const bool last_is_tab = l7 != 0 && ((tt >> ((l7 - 1u) & 63u)) & 1ull) != 0;
+                    // six tabs, the sixth right in front of the tags -- or five and the line ends behind column 12
+                    plain &= (ntab == 6 && last_is_tab) || (ntab == 5 && !last_is_tab && n7 + l7 == e);
+                    plain &= (tt & ((tt >> 1) | 1ull)) == 0;                              // no empty column
+                    // tabs 7-10: the coordinates are columns 7-9, Alen (column 11, behind tab 10) must not start with '0'
+                    c6 = pe;
+                    c7 = n7 + uint32_t(__ffsll((long long)tt)) - 1u;
+                    tt &= tt - 1;
+                    c8 = n7 + uint32_t(__ffsll((long long)tt)) - 1u;
+                    tt &= tt - 1;
+                    c9 = n7 + uint32_t(__ffsll((long long)tt)) - 1u;
+                    tt &= tt - 1;
+                    const uint32_t p10 = n7 + uint32_t(__ffsll((long long)tt)) - 1u;
+                    plain = plain && win[p10 + 1] != '0';
                     if (!plain) {
                         exact = true;
                     } else if (!is_delim(win[ps])) {
