@@ -45,23 +45,23 @@ using namespace svjg;
 
 namespace {
 
-constexpr int TILE = 4096;                     // bytes a warp owns per step
+constexpr int TILE_MAX = 5024;                 // most bytes a warp owns per step; the launch picks the tile so that a
+constexpr int TILE_MIN = 1024;                 // tile holds about TILE_LINES lines = one line per lane (probe_kernel)
+constexpr int TILE_LINES = 30;
 constexpr int LOOKAHEAD = 1024;                // staged behind the tile so that lines starting in it are whole
 constexpr int HEAD = 32;                       // staged in front of it (the newline that starts the first line)
-constexpr int WIN = HEAD + TILE + LOOKAHEAD;   // 5152 = 32 * 161
+constexpr int WIN = HEAD + TILE_MAX + LOOKAHEAD;   // 6080 = 32 * 190
 constexpr int WARPS = 4;                       // per block; warps never synchronise with each other
 constexpr int THREADS = WARPS * 32;
 constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunks
-constexpr int HEAD_SPAN = 96;                  // bytes searched for the tabs of columns 1-5 on the fast route
-constexpr int TAIL_SPAN = 96;                  // bytes searched for the tabs of columns 7-12
-constexpr int SPARE = 176;                     // readable bytes behind the window for those fixed-span reads
-constexpr int NLCAP = 256;                     // newlines per window (more => some line is shorter than 21 bytes)
+constexpr int SPARE = 32;                      // readable (zero) bytes behind the window
+constexpr int NLCAP = 320;                     // newlines per window (more => some line is shorter than 20 bytes)
 constexpr int TOKCAP = 32;                     // path nodes resolved per round of phases C/D (one lane each)
 static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit");
 
 // shared memory map of ONE warp of scan_parse (bytes)
 constexpr int OFF_WIN = 0;
-constexpr int BMWORDS = NPAIRS + 7;                         // bitmap words: reads may run a few words past the window
+constexpr int BMWORDS = NPAIRS + 3;                         // bitmap words: reads may run a few words past the window
 constexpr int NLW = (NPAIRS + 31) / 32;                     // newline bitmap words a lane turns into list entries
 constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline bitmap u32[BMWORDS] during phase A, then the
 constexpr int NL_BYTES = BMWORDS * 4 > NLCAP * 2 ? BMWORDS * 4 : NLCAP * 2;   // newline positions, ascending, u16[NLCAP]
@@ -109,7 +109,6 @@ struct FilterArgs {
     uint32_t *hit_sv2, *hit_off, *hit_len;
     uint64_t hit_cap;
     unsigned long long *stats;   // svjg_filter_stats as 8 x u64
-    uint32_t n_tiles;
     uint32_t flags;
     uint32_t one;                // 1 (see IsNewline)
     Scratch sc;
@@ -677,17 +676,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 __device__ __forceinline__ uint32_t lds32(const uint8_t *win, uint32_t a) { return *reinterpret_cast<const uint32_t *>(win + a); }
 
-// number of non-digit bytes in window bytes [lo, hi), hi > lo
-__device__ __forceinline__ uint32_t count_nondigits(const uint8_t *win, uint32_t lo, uint32_t hi) {
-    const uint32_t a0 = lo & ~3u, a1 = (hi - 1u) & ~3u;
-    const uint32_t lom = 0xFFFFFFFFu << (8u * (lo & 3u)), him = 0xFFFFFFFFu >> (8u * (3u - ((hi - 1u) & 3u)));
-    uint32_t f = nondigit_bytes(lds32(win, a0)) & lom;
-    if (a0 == a1) return __popc(f & him);
-    uint32_t n = __popc(f);
-    for (uint32_t a = a0 + 4; a < a1; a += 4) n += __popc(nondigit_bytes(lds32(win, a)));
-    return n + __popc(nondigit_bytes(lds32(win, a1)) & him);
-}
-
 // any ',' in window bytes [lo, hi), hi > lo
 __device__ __forceinline__ bool has_comma(const uint8_t *win, uint32_t lo, uint32_t hi) {
     const uint32_t a0 = lo & ~3u, a1 = (hi - 1u) & ~3u;
@@ -805,7 +793,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
     uint64_t *mbar = &mbars[warp];
 
     if (lane == 0) mbar_init(mbar, 1);
-    for (int i = NPAIRS + lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0, xdb[i] = 0;
+    for (int i = lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0, xdb[i] = 0;
     for (int i = WIN + lane; i < WIN + SPARE; i += 32) win[i] = 0;   // never written by the copies
     __syncwarp();
     uint32_t phase = 0;
@@ -814,11 +802,15 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
     const uint32_t one = a.one;
     const uint32_t n_workers = gridDim.x * WARPS;
 
-    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < a.n_tiles; tile += n_workers) {
-        const uint64_t tile_start = uint64_t(tile) * TILE;
+    const uint32_t tile_bytes = a.sc.cnt[4];                       // chosen by probe_kernel: a multiple of 32
+    const uint32_t n_tiles = uint32_t((a.n + tile_bytes - 1) / tile_bytes);
+    const uint32_t win_bytes = HEAD + tile_bytes + LOOKAHEAD, n_pairs = win_bytes / 32u;
+
+    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < n_tiles; tile += n_workers) {
+        const uint64_t tile_start = uint64_t(tile) * tile_bytes;
         const uint64_t g0 = tile_start ? tile_start - HEAD : 0;
         const uint32_t dst0 = tile_start ? 0 : HEAD;
-        uint64_t g1 = tile_start + TILE + LOOKAHEAD;
+        uint64_t g1 = tile_start + tile_bytes + LOOKAHEAD;
         if (g1 > a.n) g1 = a.n;
         const bool at_eof = (g1 == a.n);
         const uint32_t nbytes = uint32_t(g1 - g0);
@@ -833,7 +825,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
         }
         for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
         if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;               // "newline" in front of byte 0 of the file
-        for (uint32_t i = valid_end + lane; i < WIN; i += 32) win[i] = 0;
+        for (uint32_t i = valid_end + lane; i < win_bytes; i += 32) win[i] = 0;
         if (bulk) {
             mbar_wait(mbar, phase);
             phase ^= 1;
@@ -843,13 +835,13 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
         // ---- phase A: byte classes.  A lane takes two adjacent 16-byte chunks = one word of each of the
         // three bitmaps (newlines, tabs, path delimiters).  The scan stops behind the tile once the last
         // owned line has its end.
-        const uint32_t own_end = min(uint32_t(HEAD + TILE), valid_end);   // lines starting before own_end are ours
+        const uint32_t own_end = min(HEAD + tile_bytes, valid_end);   // lines starting before own_end are ours
         uint32_t n_words = 0;
-        for (int c0 = 0; c0 < NPAIRS; c0 += 32) {
-            const int c = c0 + lane;
-            const uint32_t p0 = uint32_t(c) * 32u;
+        for (uint32_t c0 = 0; c0 < n_pairs; c0 += 32) {
+            const uint32_t c = c0 + uint32_t(lane);
+            const uint32_t p0 = c * 32u;
             uint32_t m = 0;
-            if (c < NPAIRS) {
+            if (c < n_pairs) {
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(win + p0);
                 const uint4 v1 = *reinterpret_cast<const uint4 *>(win + p0 + 16);
                 m = mask16(v0, IsNewline{one}) | (mask16(v1, IsNewline{one}) << 16);
@@ -859,10 +851,10 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
                 nlb[c] = m;
             }
-            n_words = min(uint32_t(c0) + 32u, uint32_t(NPAIRS));
+            n_words = min(c0 + 32u, n_pairs);
             // behind the tile: a newline at or after own_end - 1 ends the last owned line
             const bool ends_it = (m & ~low_bits(int(own_end) - 1 - int(p0))) != 0;
-            if ((uint32_t(c0) + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, ends_it)) break;
+            if ((c0 + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, ends_it)) break;
         }
         __syncwarp();
         // newline bitmap -> ordered list of line ends from HEAD-1 on: every lane takes a run of words
@@ -898,7 +890,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
         if (stop_after_scan) continue;
 
         if (n_nl > NLCAP) {
-            // that many lines in 5 KiB: some line is shorter than 21 bytes and cannot hold 12 columns
+            // that many lines in 5 KiB: some line is shorter than 20 bytes and cannot hold 12 columns
             if (lane == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
             __syncwarp();
             continue;
@@ -1246,6 +1238,39 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
     add_stats(a, loc);
 }
 
+// ===========================================================================
+// probe: average line length of the head of the shard -> bytes per tile, so that a tile holds about
+// one line per lane of the warp that parses it
+// ===========================================================================
+constexpr int PROBE_THREADS = 1024, PROBE_BYTES = 256 << 10;
+
+__global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const __grid_constant__ FilterArgs a) {
+    __shared__ uint32_t total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    const uint64_t span = a.n < uint64_t(PROBE_BYTES) ? a.n : uint64_t(PROBE_BYTES);
+    const uint32_t n16 = uint32_t(span / 16);
+    const uint4 *p = reinterpret_cast<const uint4 *>(a.gaf);
+    uint32_t cnt = 0;
+    for (uint32_t i = threadIdx.x; i < n16; i += PROBE_THREADS) {
+        const uint4 v = __ldg(p + i);
+        cnt += __popc(eq_bytes(v.x, 0x0A0A0A0Au)) + __popc(eq_bytes(v.y, 0x0A0A0A0Au)) + __popc(eq_bytes(v.z, 0x0A0A0A0Au)) +
+               __popc(eq_bytes(v.w, 0x0A0A0A0Au));
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tile = TILE_MAX;
+        if (total) {
+            const uint64_t want = uint64_t(n16) * 16ull * TILE_LINES / total;
+            tile = uint32_t(want < uint64_t(TILE_MAX) ? want : uint64_t(TILE_MAX)) & ~31u;
+        }
+        if (const uint32_t forced = (a.flags >> 16)) tile = forced & ~31u;    // test hook (SVJG_TILE_BYTES)
+        a.sc.cnt[4] = max(uint32_t(TILE_MIN), min(tile, uint32_t(TILE_MAX) & ~31u));
+    }
+}
+
 __global__ void reset_kernel(uint32_t *counts, uint64_t n, unsigned long long *stats) {
     uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
     uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -1306,7 +1331,6 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.hit_len = d_hit_len;
     a.hit_cap = hit_cap;
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
-    a.n_tiles = uint32_t((n_bytes + TILE - 1) / TILE);
     a.flags = t->filter_flags;
     a.one = 1;
     const char *stop_env = getenv("SVJG_STOP_AFTER");          // profiling hook: run the chain up to A/B/C/D only
@@ -1330,7 +1354,10 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
     SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
 
-    const int scan_grid = int(std::min<uint32_t>((a.n_tiles + WARPS - 1) / WARPS, uint32_t(g_scan_grid_cap)));
+    if (const char *tb = getenv("SVJG_TILE_BYTES")) a.flags |= uint32_t(std::min(65535, std::max(0, atoi(tb)))) << 16;
+    const uint32_t max_tiles = uint32_t((n_bytes + TILE_MIN - 1) / TILE_MIN);
+    const int scan_grid = int(std::min<uint32_t>((max_tiles + WARPS - 1) / WARPS, uint32_t(g_scan_grid_cap)));
+    probe_kernel<<<1, PROBE_THREADS, 0, st>>>(a);
     const int flat_grid = g_sms * 8;
     scan_parse_kernel<<<scan_grid, THREADS, SMEM_BYTES, st>>>(a);
     if (stop == 0) {
