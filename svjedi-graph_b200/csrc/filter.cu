@@ -68,9 +68,7 @@ constexpr int NL_BYTES = BMWORDS * 4 > NLCAP * 2 ? BMWORDS * 4 : NLCAP * 2;   //
 constexpr int OFF_TABB = (OFF_NL + NL_BYTES + 15) & ~15;    // tab bitmap        u32[BMWORDS]
 constexpr int OFF_DLB = OFF_TABB + BMWORDS * 4;             // delimiter bitmap  u32[BMWORDS]
 constexpr int OFF_XDB = OFF_DLB + BMWORDS * 4;              // non-digit bitmap  u32[BMWORDS]
-constexpr int OFF_TKP = OFF_XDB + BMWORDS * 4;              // node list of a round: window position u16[TOKCAP],
-constexpr int OFF_TKL = OFF_TKP + TOKCAP * 2;               //   length u8[TOKCAP] (255 = longer),
-constexpr int OFF_TKO = OFF_TKL + TOKCAP;                   //   lane of its line u8[TOKCAP]
+constexpr int OFF_TKO = OFF_XDB + BMWORDS * 4;              // lanes of the lines of a round, in order  u8[TOKCAP]
 constexpr int WARP_SMEM = (OFF_TKO + TOKCAP + 127) & ~127;
 constexpr int SMEM_BYTES = WARP_SMEM * WARPS;
 
@@ -788,8 +786,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
     uint32_t *dlb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_DLB);     // bit i: ... is '<' or '>'
     uint32_t *xdb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_XDB);     // bit i: ... is not '0'..'9'
     uint32_t *nlb = reinterpret_cast<uint32_t *>(nl);                                        // bit i: ... is a newline (phase A only)
-    uint16_t *tkp = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_TKP);
-    uint8_t *tkl = smem_all + warp * WARP_SMEM + OFF_TKL, *tko = smem_all + warp * WARP_SMEM + OFF_TKO;
+    uint8_t *tko = smem_all + warp * WARP_SMEM + OFF_TKO;
     uint64_t *mbar = &mbars[warp];
 
     if (lane == 0) mbar_init(mbar, 1);
@@ -869,22 +866,23 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 const uint32_t j = j0 + uint32_t(i);
                 mw[i] = (uint32_t(i) < per && j < n_words) ? nlb[j] : 0u;
                 cnt += __popc(mw[i]);
-                own += __popc(mw[i] & low_bits(int(own_end) - 1 - int(j * 32u)));   // newline at p starts an owned line iff p + 1 < own_end
             }
             const uint32_t incl = warp_incl_scan(cnt, lane);
             n_nl = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            n_own = __reduce_add_sync(0xFFFFFFFFu, own);
             uint32_t idx = incl - cnt;
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < NLW; ++i) {
                 uint32_t m = mw[i];
                 while (m) {
-                    if (idx < NLCAP) nl[idx] = uint16_t((j0 + uint32_t(i)) * 32u + uint32_t(__ffs(m) - 1));
+                    const uint32_t pos = (j0 + uint32_t(i)) * 32u + uint32_t(__ffs(m) - 1);
+                    if (idx < NLCAP) nl[idx] = uint16_t(pos);
+                    own += pos + 1u < own_end;                                 // the newline at pos starts an owned line
                     ++idx;
                     m &= m - 1;
                 }
             }
+            n_own = __reduce_add_sync(0xFFFFFFFFu, own);
         }
         __syncwarp();
         if (stop_after_scan) continue;
@@ -1000,40 +998,45 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 const uint32_t takeb = __ballot_sync(0xFFFFFFFFu, take);
                 const uint32_t ntk = __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(takeb));
                 const uint32_t first = incl - pend;                             // list slot of this line's first node
-                if (take) {
-                    // node list: maximal runs of non-delimiter bytes, from the start / end bits
-                    uint32_t t = first, cur = 0xFFFFFFFFu, carry = 0;
-                    for (uint32_t q = ps; q < pe; q += 32) {
-                        const uint32_t d = bm_bits(dlb, q);
-                        const uint32_t pd = (d << 1) | carry;                       // "previous byte is a delimiter"
-                        const uint32_t keep = low_bits(int(pe - q));
-                        const uint32_t st = pd & ~d & keep, en = d & ~pd & keep;
-                        carry = d >> 31;
-                        uint32_t ev = st | en;
-                        while (ev) {
-                            const uint32_t bit = uint32_t(__ffs(ev) - 1);
-                            ev &= ev - 1;
-                            const uint32_t pos = q + bit;
-                            if ((st >> bit) & 1u) {
-                                cur = pos;
-                                tkp[t] = uint16_t(pos);
-                                tko[t] = uint8_t(lane);
-                            } else if (cur != 0xFFFFFFFFu) {
-                                tkl[t++] = uint8_t(min(pos - cur, 255u));
-                                cur = 0xFFFFFFFFu;
-                            }
-                        }
-                    }
-                    if (cur != 0xFFFFFFFFu) tkl[t++] = uint8_t(min(pe - cur, 255u));
-                }
+                // no list of nodes is written: a node lane finds its line from the bit mask of the lines'
+                // first slots, and its own start and end in the delimiter bitmap
+                const uint32_t startmask = __reduce_or_sync(0xFFFFFFFFu, take ? (1u << first) : 0u);
+                if (take) tko[__popc(takeb & lt_mask)] = uint8_t(lane);             // ordinal among the taken lines -> lane
                 __syncwarp();
-                // C: this lane's node -- strand, exact key, table probe, length
                 const bool is_tok = uint32_t(lane) < ntk;
-                uint32_t own = 0, nid = NO_NODE, nlen = 0, akey = 0, plus = 0;
+                uint32_t own = 0, idx = 0, nid = NO_NODE, nlen = 0, akey = 0, plus = 0;
+                if (is_tok) {
+                    const uint32_t below = startmask & (0xFFFFFFFFu >> (31 - lane));
+                    own = tko[__popc(below) - 1];
+                    idx = uint32_t(lane) - uint32_t(31 - __clz(below));             // number of this node in its line
+                }
+                const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), own);
+                // C: this lane's node -- strand, exact key, table probe, length
                 bool plain = false;
                 if (is_tok) {
-                    const uint32_t tpos = tkp[lane], tlen = tkl[lane];
-                    own = tko[lane];
+                    const uint32_t lps = lpath & 0xFFFFu, lpe = lpath >> 16;
+                    // node starts: a non-delimiter byte right behind a delimiter; take the idx-th
+                    uint32_t q = lps, rem = idx, carry = 0, st;
+                    for (;;) {
+                        const uint32_t d = bm_bits(dlb, q);
+                        st = ((d << 1) | carry) & ~d & low_bits(int(lpe - q));
+                        const uint32_t c = __popc(st);
+                        if (rem < c) break;
+                        rem -= c;
+                        carry = d >> 31;
+                        q += 32;
+                    }
+                    for (; rem; --rem) st &= st - 1;
+                    const uint32_t tpos = q + uint32_t(__ffs(st) - 1);
+                    // its end: the next delimiter or the end of the path (a plain name has at most 36 bytes)
+                    const uint32_t d0 = bm_bits(dlb, tpos) & low_bits(int(lpe - tpos));
+                    uint32_t tlen;
+                    if (d0) {
+                        tlen = uint32_t(__ffs(d0) - 1);
+                    } else {
+                        const uint32_t d1 = bm_bits(dlb, tpos + 32u) & low_bits(int(lpe - tpos) - 32);
+                        tlen = d1 ? 32u + uint32_t(__ffs(d1) - 1) : min(lpe - tpos, 64u);
+                    }
                     plus = win[tpos - 1] == '>';
                     uint64_t c0 = 0, c1 = 0;
                     uint32_t c = 0;
@@ -1092,9 +1095,8 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 }
                 // D: per line -- sums of the node lengths left of every node, names that repeat a start
                 // value (the first-occurrence rules :206 and :269-271 would bite: exact route), verdicts
-                const uint32_t lfirst = __shfl_sync(0xFFFFFFFFu, first, own);
+                const uint32_t lfirst = uint32_t(lane) - idx;
                 const uint32_t lcnt = __shfl_sync(0xFFFFFFFFu, pend, own);
-                const uint32_t idx = is_tok ? uint32_t(lane) - lfirst : 0u;
                 const uint32_t maxidx = __reduce_max_sync(0xFFFFFFFFu, idx);
                 uint64_t pre = 0;
                 bool clash = false;
