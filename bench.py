@@ -283,14 +283,14 @@ def main():
     pl_all = torch.empty((world, max(1, (n_sv + world - 1) // world), 3), dtype=torch.int64, device=dev) if world > 1 else None
 
     # size the hit buffers from one untimed pass
-    filt = alnfilter.DeviceFilter(tables, hit_cap=max(1024, n_rec * 4), device=local)
+    filt = alnfilter.DeviceFilter(tables, hit_cap=1024, device=local)
     filt.reset()
-    filt.run(d_gaf)
+    filt.run(d_gaf)                                   # the cursor counts every hit, stored or not
     st = filt.read_stats()
     if st["status"]:
         raise SystemExit(f"synthetic GAF rejected: {st}")
     n_hits = st["n_hits"]
-    assert n_hits <= filt.hit_cap
+    filt = alnfilter.DeviceFilter(tables, hit_cap=n_hits + 1024, device=local)
     stream = torch.cuda.current_stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
     lib = capi.lib

@@ -693,6 +693,15 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
+__device__ __forceinline__ uint64_t warp_incl_scan64(uint64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
 // 32 bits of a byte-indexed bitmap starting at bit `pos`
 __device__ __forceinline__ uint32_t bm_bits(const uint32_t *bm, uint32_t pos) {
     const uint32_t w = pos >> 5;
@@ -769,6 +778,97 @@ __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uin
         }
         i = (i + 1) & tb.pnode_mask;
     }
+}
+
+// ---- phase C: the idx-th node of the path [lps, lpe) -- strand, exact key, table probe, length
+struct Node {
+    uint32_t nid = NO_NODE;   // node id; NO_NODE: the name is in no link key
+    uint32_t nlen = 0;        // get_node_len (:343-349)
+    uint32_t akey = 0;        // start value and kind: equal ones in a path mean the first-occurrence rules may bite
+    uint32_t plus = 0;        // the delimiter in front is '>'
+    bool plain = false;       // chrom:start-end or chrom:pos.k of the exact-key form, with a length
+};
+__device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t *dlb, const DevTables &tb, uint32_t lps,
+                                             uint32_t lpe, uint32_t idx) {
+    Node n;
+    // node starts: a non-delimiter byte right behind a delimiter; take the idx-th
+    uint32_t q = lps, rem = idx, carry = 0, st;
+    for (;;) {
+        const uint32_t d = bm_bits(dlb, q);
+        st = ((d << 1) | carry) & ~d & low_bits(int(lpe - q));
+        const uint32_t c = __popc(st);
+        if (rem < c) break;
+        rem -= c;
+        carry = d >> 31;
+        q += 32;
+    }
+    for (; rem; --rem) st &= st - 1;
+    const uint32_t tpos = q + uint32_t(__ffs(st) - 1);
+    // its end: the next delimiter or the end of the path (a plain name has at most 36 bytes)
+    const uint32_t d0 = bm_bits(dlb, tpos) & low_bits(int(lpe - tpos));
+    uint32_t tlen;
+    if (d0) {
+        tlen = uint32_t(__ffs(d0) - 1);
+    } else {
+        const uint32_t d1 = bm_bits(dlb, tpos + 32u) & low_bits(int(lpe - tpos) - 32);
+        tlen = d1 ? 32u + uint32_t(__ffs(d1) - 1) : min(lpe - tpos, 64u);
+    }
+    n.plus = win[tpos - 1] == '>';
+    uint64_t c0 = 0, c1 = 0;
+    uint32_t c = 0;
+    bool colon = false, clean = true;
+    for (; c < tlen && c <= 16; ++c) {                              // chrom: at most 16 bytes, no NUL
+        const uint32_t ch = win[tpos + c];
+        if (ch == ':') {
+            colon = true;
+            break;
+        }
+        if (c == 16) break;
+        clean &= ch != 0;
+        if (c < 8) c0 |= uint64_t(ch) << (8 * c);
+        else c1 |= uint64_t(ch) << (8 * (c - 8));
+    }
+    if (colon && clean) {
+        uint32_t q = tpos + c + 1;
+        const uint32_t end = tpos + tlen;
+        const uint32_t q0 = q;
+        uint32_t v0 = 0;
+        for (; q < end; ++q) {
+            const uint32_t d = uint32_t(win[q]) - '0';
+            if (d > 9) break;
+            v0 = v0 * 10 + d;
+        }
+        const uint32_t nd0 = q - q0;
+        const uint32_t sep = q < end ? win[q] : 0u;
+        if (nd0 >= 1 && nd0 <= 9 && !(nd0 > 1 && win[q0] == '0') && (sep == '-' || sep == '.')) {
+            const uint32_t q1 = ++q;
+            uint32_t v1 = 0;
+            for (; q < end; ++q) {
+                const uint32_t d = uint32_t(win[q]) - '0';
+                if (d > 9) break;
+                v1 = v1 * 10 + d;
+            }
+            const uint32_t nd1 = q - q1;
+            if (q == end && nd1 >= 1 && nd1 <= 9 && !(nd1 > 1 && win[q1] == '0')) {
+                const uint32_t kind = sep == '.' ? PN_ALT : 0u;
+                uint32_t id = NO_NODE, alt_len = PN_NO_LEN;
+                const bool found = pnode_find(tb, c0, c1, v0, v1 | kind, id, alt_len);
+                n.akey = v0 | kind;
+                if (!kind) {
+                    if (v1 >= v0) {                                 // get_node_len :343-349
+                        n.plain = true;
+                        n.nlen = v1 - v0 + 1u;
+                        n.nid = found ? id : NO_NODE;
+                    }
+                } else if (found && alt_len != PN_NO_LEN) {         // alt_node_len[name] :346
+                    n.plain = true;
+                    n.nlen = alt_len;
+                    n.nid = id;
+                }
+            }
+        }
+    }
+    return n;
 }
 
 // ===========================================================================
@@ -977,8 +1077,12 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
             // Tlen, Ts, Te of the lines that go on (digit-only columns 7-9).  The reference has bigints;
             // this route stops at 18 digits and says so.
             int64_t ts = 0, tail = 0;
+#ifdef SVJG_NO_LONG
             if (want > TOKCAP) {
-                exact = true;                  // more nodes than a round holds: the exact route
+#else
+            if (want > 2 * TOKCAP) {
+#endif
+                exact = true;                  // more nodes than two per lane: the exact route
                 want = 0;
             } else if (want) {
                 int64_t tlen = 0, te = 0;
@@ -990,7 +1094,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 }
             }
             // ---- phases C and D: rounds of at most TOKCAP path nodes, whole lines only, one lane per node
-            uint32_t pend = want;
+            uint32_t pend = want > TOKCAP ? 0u : want;
             for (;;) {
                 if (__ballot_sync(0xFFFFFFFFu, pend != 0) == 0) break;
                 const uint32_t incl = warp_incl_scan(pend, lane);
@@ -1004,95 +1108,18 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 if (take) tko[__popc(takeb & lt_mask)] = uint8_t(lane);             // ordinal among the taken lines -> lane
                 __syncwarp();
                 const bool is_tok = uint32_t(lane) < ntk;
-                uint32_t own = 0, idx = 0, nid = NO_NODE, nlen = 0, akey = 0, plus = 0;
+                uint32_t own = 0, idx = 0;
                 if (is_tok) {
                     const uint32_t below = startmask & (0xFFFFFFFFu >> (31 - lane));
                     own = tko[__popc(below) - 1];
                     idx = uint32_t(lane) - uint32_t(31 - __clz(below));             // number of this node in its line
                 }
                 const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), own);
-                // C: this lane's node -- strand, exact key, table probe, length
-                bool plain = false;
-                if (is_tok) {
-                    const uint32_t lps = lpath & 0xFFFFu, lpe = lpath >> 16;
-                    // node starts: a non-delimiter byte right behind a delimiter; take the idx-th
-                    uint32_t q = lps, rem = idx, carry = 0, st;
-                    for (;;) {
-                        const uint32_t d = bm_bits(dlb, q);
-                        st = ((d << 1) | carry) & ~d & low_bits(int(lpe - q));
-                        const uint32_t c = __popc(st);
-                        if (rem < c) break;
-                        rem -= c;
-                        carry = d >> 31;
-                        q += 32;
-                    }
-                    for (; rem; --rem) st &= st - 1;
-                    const uint32_t tpos = q + uint32_t(__ffs(st) - 1);
-                    // its end: the next delimiter or the end of the path (a plain name has at most 36 bytes)
-                    const uint32_t d0 = bm_bits(dlb, tpos) & low_bits(int(lpe - tpos));
-                    uint32_t tlen;
-                    if (d0) {
-                        tlen = uint32_t(__ffs(d0) - 1);
-                    } else {
-                        const uint32_t d1 = bm_bits(dlb, tpos + 32u) & low_bits(int(lpe - tpos) - 32);
-                        tlen = d1 ? 32u + uint32_t(__ffs(d1) - 1) : min(lpe - tpos, 64u);
-                    }
-                    plus = win[tpos - 1] == '>';
-                    uint64_t c0 = 0, c1 = 0;
-                    uint32_t c = 0;
-                    bool colon = false, clean = true;
-                    for (; c < tlen && c <= 16; ++c) {                              // chrom: at most 16 bytes, no NUL
-                        const uint32_t ch = win[tpos + c];
-                        if (ch == ':') {
-                            colon = true;
-                            break;
-                        }
-                        if (c == 16) break;
-                        clean &= ch != 0;
-                        if (c < 8) c0 |= uint64_t(ch) << (8 * c);
-                        else c1 |= uint64_t(ch) << (8 * (c - 8));
-                    }
-                    if (colon && clean) {
-                        uint32_t q = tpos + c + 1;
-                        const uint32_t end = tpos + tlen;
-                        const uint32_t q0 = q;
-                        uint32_t v0 = 0;
-                        for (; q < end; ++q) {
-                            const uint32_t d = uint32_t(win[q]) - '0';
-                            if (d > 9) break;
-                            v0 = v0 * 10 + d;
-                        }
-                        const uint32_t nd0 = q - q0;
-                        const uint32_t sep = q < end ? win[q] : 0u;
-                        if (nd0 >= 1 && nd0 <= 9 && !(nd0 > 1 && win[q0] == '0') && (sep == '-' || sep == '.')) {
-                            const uint32_t q1 = ++q;
-                            uint32_t v1 = 0;
-                            for (; q < end; ++q) {
-                                const uint32_t d = uint32_t(win[q]) - '0';
-                                if (d > 9) break;
-                                v1 = v1 * 10 + d;
-                            }
-                            const uint32_t nd1 = q - q1;
-                            if (q == end && nd1 >= 1 && nd1 <= 9 && !(nd1 > 1 && win[q1] == '0')) {
-                                const uint32_t kind = sep == '.' ? PN_ALT : 0u;
-                                uint32_t id = NO_NODE, alt_len = PN_NO_LEN;
-                                const bool found = pnode_find(a.tb, c0, c1, v0, v1 | kind, id, alt_len);
-                                akey = v0 | kind;
-                                if (!kind) {
-                                    if (v1 >= v0) {                                 // get_node_len :343-349
-                                        plain = true;
-                                        nlen = v1 - v0 + 1u;
-                                        nid = found ? id : NO_NODE;
-                                    }
-                                } else if (found && alt_len != PN_NO_LEN) {         // alt_node_len[name] :346
-                                    plain = true;
-                                    nlen = alt_len;
-                                    nid = id;
-                                }
-                            }
-                        }
-                    }
-                }
+                // C: this lane's node
+                Node nd;
+                if (is_tok) nd = resolve_node(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, idx);
+                const uint32_t nid = nd.nid, nlen = nd.nlen, akey = nd.akey, plus = nd.plus;
+                const bool plain = nd.plain;
                 // D: per line -- sums of the node lengths left of every node, names that repeat a start
                 // value (the first-occurrence rules :206 and :269-271 would bite: exact route), verdicts
                 const uint32_t lfirst = uint32_t(lane) - idx;
@@ -1141,6 +1168,70 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                     pend = 0;
                 }
                 __syncwarp();
+            }
+            // ---- lines with more nodes than a round has lanes (up to twice as many): one line at a time,
+            // two nodes per lane -- node `lane` and node `32 + lane` -- same rules as above
+            for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > TOKCAP); longb; longb &= longb - 1) {
+                const int L = __ffs(longb) - 1;
+                const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, want, L);
+                const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), L);
+                const bool has1 = 32u + uint32_t(lane) < cnt;
+                Node n0 = resolve_node(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, uint32_t(lane)), n1;
+                if (has1) n1 = resolve_node(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, 32u + uint32_t(lane));
+                bool clash = false;
+                for (int d = 1; d < 32; ++d) {
+                    const uint32_t p0 = __shfl_up_sync(0xFFFFFFFFu, n0.akey, d), p1 = __shfl_up_sync(0xFFFFFFFFu, n1.akey, d);
+                    if (d <= lane) clash |= p0 == n0.akey || (has1 && p1 == n1.akey);
+                }
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t pj = __shfl_sync(0xFFFFFFFFu, n0.akey, j);          // every lane takes part
+                    clash |= has1 && pj == n1.akey;
+                }
+                const bool bad = __any_sync(0xFFFFFFFFu, clash || !n0.plain || (has1 && !n1.plain));
+                const uint64_t in0 = warp_incl_scan64(n0.nlen, lane), in1 = warp_incl_scan64(n1.nlen, lane);
+                const uint64_t tot0 = __shfl_sync(0xFFFFFFFFu, in0, 31), total = tot0 + __shfl_sync(0xFFFFFFFFu, in1, 31);
+                const uint64_t pre0 = in0 - n0.nlen, pre1 = tot0 + in1 - n1.nlen;
+                const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, L), ltail = __shfl_sync(0xFFFFFFFFu, tail, L);
+                const uint32_t loff = __shfl_sync(0xFFFFFFFFu, s, L);
+                const uint32_t llen = __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), L);
+                // left neighbours: node 32 + lane - 1 is node 31 of the first set for lane 0
+                const uint32_t up_id0 = __shfl_up_sync(0xFFFFFFFFu, n0.nid, 1), up_s0 = __shfl_up_sync(0xFFFFFFFFu, n0.plus, 1);
+                const uint32_t up_id1 = __shfl_up_sync(0xFFFFFFFFu, n1.nid, 1), up_s1 = __shfl_up_sync(0xFFFFFFFFu, n1.plus, 1);
+                const uint32_t last_id0 = __shfl_sync(0xFFFFFFFFu, n0.nid, 31), last_s0 = __shfl_sync(0xFFFFFFFFu, n0.plus, 31);
+                const uint32_t idl1 = lane ? up_id1 : last_id0, sl1 = lane ? up_s1 : last_s0;
+                const bool all_links = (a.flags & FLAG_EXACT_CHECKS) != 0;
+                const bool ok0 = (int64_t(pre0) - lts >= a.d_over) && (int64_t(total - pre0) - ltail >= a.d_over);
+                const bool ok1 = (int64_t(pre1) - lts >= a.d_over) && (int64_t(total - pre1) - ltail >= a.d_over);
+                const bool emit0 = !bad && lane >= 1 && up_id0 != NO_NODE && n0.nid != NO_NODE && (ok0 || all_links);
+                const bool emit1 = !bad && has1 && idl1 != NO_NODE && n1.nid != NO_NODE && (ok1 || all_links);
+                const uint32_t eb0 = __ballot_sync(0xFFFFFFFFu, emit0), eb1 = __ballot_sync(0xFFFFFFFFu, emit1);
+                bool room = true;
+                if (eb0 | eb1) {
+                    const uint32_t n_new = __popc(eb0) + __popc(eb1);
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(a.sc.cnt + 0, n_new);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    room = uint64_t(base) + n_new <= a.sc.cap_links;
+                    const uint32_t slot0 = base + __popc(eb0 & lt_mask), slot1 = base + __popc(eb0) + __popc(eb1 & lt_mask);
+                    if (emit0 && slot0 < a.sc.cap_links) {
+                        LinkRec r;
+                        r.key = room ? link_key(up_id0, up_s0, n0.nid, n0.plus) : LINK_HOLE;
+                        r.off = wbase + loff;
+                        r.len = llen | (ok0 ? LINK_OK : 0u);
+                        *reinterpret_cast<uint4 *>(a.sc.links + slot0) = *reinterpret_cast<const uint4 *>(&r);
+                    }
+                    if (emit1 && slot1 < a.sc.cap_links) {
+                        LinkRec r;
+                        r.key = room ? link_key(idl1, sl1, n1.nid, n1.plus) : LINK_HOLE;
+                        r.off = wbase + loff;
+                        r.len = llen | (ok1 ? LINK_OK : 0u);
+                        *reinterpret_cast<uint4 *>(a.sc.links + slot1) = *reinterpret_cast<const uint4 *>(&r);
+                    }
+                }
+                if (lane == L) {
+                    if (bad || !room) exact = true;
+                    else loc.n_multi++;
+                }
             }
             const uint32_t xb = __ballot_sync(0xFFFFFFFFu, exact);
             if (xb) {
@@ -1224,18 +1315,31 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
 __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_constant__ FilterArgs a) {
     const uint32_t n = min(a.sc.cnt[2], a.sc.cap_exact);
     Local loc;
-    for (uint32_t i = blockIdx.x * FLAT_THREADS + threadIdx.x; i < n; i += gridDim.x * FLAT_THREADS) {
-        const uint32_t off = a.sc.exact[i];
-        uint64_t e = off;
-        while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
-        const uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
-        Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-        const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
-        if (!rec.err && ntok >= 2) {
-            if (ntok != COMMA_PATH) loc.n_multi++;
-            rec.general();
+    // Lines differ wildly in the work they need (general() is quadratic in the path nodes), and lanes
+    // of a warp that run different lines execute one after the other.  While there are few lines,
+    // every line gets a warp of its own (lane 0 works); only a flood of them goes one per thread.
+    const uint32_t n_warps = gridDim.x * (FLAT_THREADS / 32);
+#ifdef SVJG_NO_PER_WARP
+    const bool per_warp = false;
+#else
+    const bool per_warp = n <= 4u * n_warps;
+#endif
+    const uint32_t me = per_warp ? (blockIdx.x * FLAT_THREADS + threadIdx.x) >> 5 : blockIdx.x * FLAT_THREADS + threadIdx.x;
+    const uint32_t stride = per_warp ? n_warps : gridDim.x * FLAT_THREADS;
+    if (!per_warp || (threadIdx.x & 31) == 0) {
+        for (uint32_t i = me; i < n; i += stride) {
+            const uint32_t off = a.sc.exact[i];
+            uint64_t e = off;
+            while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
+            const uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
+            Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+            const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
+            if (!rec.err && ntok >= 2) {
+                if (ntok != COMMA_PATH) loc.n_multi++;
+                rec.general();
+            }
+            if (rec.err) report(a, rec.err, off);
         }
-        if (rec.err) report(a, rec.err, off);
     }
     add_stats(a, loc);
 }

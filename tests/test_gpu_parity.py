@@ -314,3 +314,51 @@ def test_scratch_exhaustion_falls_back_to_the_exact_route(gpu, monkeypatch):
     assert tiny.stats["n_multi"] == normal.stats["n_multi"]
     assert tiny.stats["n_generic"] > normal.stats["n_generic"]
     assert sorted(zip(tiny.hit_sv2.tolist(), tiny.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
+
+
+def test_long_paths_two_nodes_per_lane(gpu):
+    """Paths of 2 .. 90 nodes on a private chain graph: up to 32 nodes go through the ordinary rounds,
+    33 .. 64 through the two-nodes-per-lane section, more through the exact route -- all equal to the
+    oracle, and only the last group may be counted as generic."""
+    alnfilter, capi, genotype, torch = gpu
+    n_nodes, step = 120, 500
+    names = [f"chrL:{i * step + 1}-{(i + 1) * step}" for i in range(n_nodes)]
+    edges = {}
+    for i in range(n_nodes - 1):
+        edges[f"{names[i]}@+@{names[i + 1]}@+"] = [[f"chrL:DEL-{(i + 1) * step}-{(i + 1) * step + 40}", 0]]
+    for i in range(0, n_nodes - 2, 7):                                   # deletions that jump over one node
+        edges[f"{names[i]}@+@{names[i + 2]}@+"] = [[f"chrL:DEL-{(i + 1) * step}-{(i + 2) * step}", 1]]
+    t = alnfilter.Tables.from_memory(json.dumps(edges), "").to_device(0)
+    lines, n_over = [], 0
+    for k in (2, 3, 17, 31, 32, 33, 34, 40, 47, 63, 64, 65, 70, 90):
+        for start in (0, 5, 14):
+            idx = list(range(start, start + k))
+            if k % 2 == 1 and start == 0:
+                idx = [0, 2] + list(range(3, k + 1))                     # uses a jump link
+            tlen = len(idx) * step
+            for ts, te in ((120, tlen - 130), (450, tlen - 50), (0, tlen - 1)):
+                fwd = "".join(">" + names[i] for i in idx)
+                rev = "".join("<" + names[i] for i in reversed(idx))
+                for path in (fwd, rev):
+                    lines.append(f"read{len(lines)}\t{tlen}\t0\t{tlen}\t+\t{path}\t{tlen}\t{ts}\t{te}\t{tlen - 9}\t{tlen}\t60\ttp:A:P\tcm:i:7\n")
+                    n_over += len(idx) > 64
+    gaf = "".join(lines)
+    res = alnfilter.filter_host(t, gaf.encode())
+    want = O.hit_counts(O.filter_alignments(lines, edges, {}))
+    assert want and _counts_dict(t, res.counts) == {k: list(v) for k, v in want.items()}
+    assert res.stats["n_multi"] == len(lines) and res.stats["n_generic"] == n_over
+
+
+@pytest.mark.parametrize("tile", [1024, 1600, 3072, 5024])
+def test_every_tile_size_gives_the_same_result(gpu, monkeypatch, tile):
+    """The probe kernel picks the bytes per tile from the line length; any tile size must give the
+    same counters and hits (SVJG_TILE_BYTES forces one)."""
+    alnfilter, capi, genotype, torch = gpu
+    t, _ = _tables(alnfilter, "s3")
+    gaf = read_golden("s3.gaf.gz").encode()
+    normal = alnfilter.filter_host(t, gaf)
+    monkeypatch.setenv("SVJG_TILE_BYTES", str(tile))
+    forced = alnfilter.filter_host(t, gaf)
+    monkeypatch.delenv("SVJG_TILE_BYTES")
+    assert (forced.counts == normal.counts).all() and forced.stats == normal.stats
+    assert sorted(zip(forced.hit_sv2.tolist(), forced.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
