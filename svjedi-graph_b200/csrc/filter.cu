@@ -94,6 +94,7 @@ struct Scratch {
     uint32_t *cnt;        // [0] link records, [2] exact-route lines
     LinkRec *links;
     uint32_t *exact;      // line start offsets
+    uint4 *slab;          // per warp of scan_parse: nodes of a long line (long_line())
     uint32_t cap_links, cap_exact;
 };
 
@@ -786,14 +787,20 @@ struct Node {
     uint32_t nlen = 0;        // get_node_len (:343-349)
     uint32_t akey = 0;        // start value and kind: equal ones in a path mean the first-occurrence rules may bite
     uint32_t plus = 0;        // the delimiter in front is '>'
+    uint32_t end = 0;         // window position behind the name (a delimiter, or the end of the path)
     bool plain = false;       // chrom:start-end or chrom:pos.k of the exact-key form, with a length
 };
+template <bool LONG>
 __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t *dlb, const DevTables &tb, uint32_t lps,
                                              uint32_t lpe, uint32_t idx) {
     Node n;
     // node starts: a non-delimiter byte right behind a delimiter; take the idx-th
     uint32_t q = lps, rem = idx, carry = 0, st;
     for (;;) {
+        if (LONG && q >= lpe) {       // no such node (only behind a name too long to be plain): not plain
+            n.end = lpe;
+            return n;
+        }
         const uint32_t d = bm_bits(dlb, q);
         st = ((d << 1) | carry) & ~d & low_bits(int(lpe - q));
         const uint32_t c = __popc(st);
@@ -814,6 +821,7 @@ __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t 
         tlen = d1 ? 32u + uint32_t(__ffs(d1) - 1) : min(lpe - tpos, 64u);
     }
     n.plus = win[tpos - 1] == '>';
+    if (LONG) n.end = tpos + tlen;
     uint64_t c0 = 0, c1 = 0;
     uint32_t c = 0;
     bool colon = false, clean = true;
@@ -871,10 +879,76 @@ __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t 
     return n;
 }
 
+// ---- a line with more path nodes than a warp has lanes: 32 nodes a step.  The first sweep resolves
+// the nodes into the warp's slab in device memory (L2) and adds up the lengths; then every node is
+// compared with all nodes in front of it (a repeated start value: exact route); the second sweep
+// writes the links.  All lanes call it together; false: the line must take the exact route.
+#ifdef SVJG_NO_LONG
+constexpr bool LONG_ENABLED = false;
+#else
+constexpr bool LONG_ENABLED = true;
+#endif
+constexpr int SLAB_N = 256;                    // nodes of such a line (more: exact route)
+
+__device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, const uint32_t *dlb, uint4 *slab, int lane,
+                                       uint32_t cnt, uint32_t lps, uint32_t lpe, int64_t lts, int64_t ltail, uint32_t off,
+                                       uint32_t len) {
+    if (cnt > SLAB_N) return false;
+    uint64_t total = 0;
+    bool bad = false;
+    uint32_t from = lps;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const bool act = c0 + uint32_t(lane) < cnt;
+        Node n;
+        if (act) {
+            n = resolve_node<true>(win, dlb, a.tb, from, lpe, uint32_t(lane));
+            __stcg(slab + c0 + lane, make_uint4(n.nid, n.nlen, n.akey, n.plus));
+        }
+        bad |= __any_sync(0xFFFFFFFFu, act && !n.plain);
+        total += __shfl_sync(0xFFFFFFFFu, warp_incl_scan64(n.nlen, lane), 31);
+        from = __shfl_sync(0xFFFFFFFFu, n.end, 31);
+    }
+    __syncwarp();
+    if (bad) return false;
+    bool clash = false;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const uint32_t t = c0 + uint32_t(lane);
+        const uint32_t mine = t < cnt ? __ldcg(&slab[t].z) : 0u;
+        const uint32_t upto = min(c0 + 32u, cnt);
+        for (uint32_t j = 0; j < upto; ++j) clash |= j < t && t < cnt && __ldcg(&slab[j].z) == mine;
+    }
+    if (__any_sync(0xFFFFFFFFu, clash)) return false;
+    // room for every link of the line, taken before the first one is written
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.sc.cnt + 0, cnt - 1u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const bool room = uint64_t(base) + (cnt - 1u) <= a.sc.cap_links;
+    uint64_t before = 0;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+        const uint32_t t = c0 + uint32_t(lane);
+        const bool act = t < cnt;
+        const uint4 me = act ? __ldcg(slab + t) : make_uint4(NO_NODE, 0, 0, 0);
+        const uint4 lf = act && t ? __ldcg(slab + t - 1) : make_uint4(NO_NODE, 0, 0, 0);
+        const uint64_t incl = warp_incl_scan64(me.y, lane);
+        const uint64_t pre = before + incl - me.y;
+        const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
+        const bool emit = room && lf.x != NO_NODE && me.x != NO_NODE && (ok || (a.flags & FLAG_EXACT_CHECKS));
+        if (act && t && base + t - 1u < a.sc.cap_links) {                  // link t-1 of the line: a record or a hole
+            LinkRec r;
+            r.key = emit ? link_key(lf.x, lf.w, me.x, me.w) : LINK_HOLE;
+            r.off = off;
+            r.len = len | (ok ? LINK_OK : 0u);
+            *reinterpret_cast<uint4 *>(a.sc.links + base + t - 1u) = *reinterpret_cast<const uint4 *>(&r);
+        }
+        before += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    return room;
+}
+
 // ===========================================================================
 // scan_parse: newline scan, column split, validation, path walk, node and link resolution
 // ===========================================================================
-__global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
+__global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     __shared__ __align__(8) uint64_t mbars[WARPS];
 
@@ -1077,14 +1151,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
             // Tlen, Ts, Te of the lines that go on (digit-only columns 7-9).  The reference has bigints;
             // this route stops at 18 digits and says so.
             int64_t ts = 0, tail = 0;
-#ifdef SVJG_NO_LONG
-            if (want > TOKCAP) {
-#else
-            if (want > 2 * TOKCAP) {
-#endif
-                exact = true;                  // more nodes than two per lane: the exact route
-                want = 0;
-            } else if (want) {
+            if (want) {
                 int64_t tlen = 0, te = 0;
                 const bool fits = dec_field(win, c6 + 1, c7, tlen) & dec_field(win, c7 + 1, c8, ts) & dec_field(win, c8 + 1, c9, te);
                 tail = tlen - te - 1;
@@ -1117,7 +1184,7 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), own);
                 // C: this lane's node
                 Node nd;
-                if (is_tok) nd = resolve_node(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, idx);
+                if (is_tok) nd = resolve_node<false>(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, idx);
                 const uint32_t nid = nd.nid, nlen = nd.nlen, akey = nd.akey, plus = nd.plus;
                 const bool plain = nd.plain;
                 // D: per line -- sums of the node lengths left of every node, names that repeat a start
@@ -1169,70 +1236,24 @@ __global__ void __launch_bounds__(THREADS, 7) scan_parse_kernel(const __grid_con
                 }
                 __syncwarp();
             }
-            // ---- lines with more nodes than a round has lanes (up to twice as many): one line at a time,
-            // two nodes per lane -- node `lane` and node `32 + lane` -- same rules as above
+            // ---- lines with more nodes than a round has lanes: one line at a time (long_line())
+#ifdef SVJG_NO_LONG
+            if (want > TOKCAP) exact = true;
+#else
             for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > TOKCAP); longb; longb &= longb - 1) {
                 const int L = __ffs(longb) - 1;
-                const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, want, L);
                 const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), L);
-                const bool has1 = 32u + uint32_t(lane) < cnt;
-                Node n0 = resolve_node(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, uint32_t(lane)), n1;
-                if (has1) n1 = resolve_node(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, 32u + uint32_t(lane));
-                bool clash = false;
-                for (int d = 1; d < 32; ++d) {
-                    const uint32_t p0 = __shfl_up_sync(0xFFFFFFFFu, n0.akey, d), p1 = __shfl_up_sync(0xFFFFFFFFu, n1.akey, d);
-                    if (d <= lane) clash |= p0 == n0.akey || (has1 && p1 == n1.akey);
-                }
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t pj = __shfl_sync(0xFFFFFFFFu, n0.akey, j);          // every lane takes part
-                    clash |= has1 && pj == n1.akey;
-                }
-                const bool bad = __any_sync(0xFFFFFFFFu, clash || !n0.plain || (has1 && !n1.plain));
-                const uint64_t in0 = warp_incl_scan64(n0.nlen, lane), in1 = warp_incl_scan64(n1.nlen, lane);
-                const uint64_t tot0 = __shfl_sync(0xFFFFFFFFu, in0, 31), total = tot0 + __shfl_sync(0xFFFFFFFFu, in1, 31);
-                const uint64_t pre0 = in0 - n0.nlen, pre1 = tot0 + in1 - n1.nlen;
-                const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, L), ltail = __shfl_sync(0xFFFFFFFFu, tail, L);
-                const uint32_t loff = __shfl_sync(0xFFFFFFFFu, s, L);
-                const uint32_t llen = __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), L);
-                // left neighbours: node 32 + lane - 1 is node 31 of the first set for lane 0
-                const uint32_t up_id0 = __shfl_up_sync(0xFFFFFFFFu, n0.nid, 1), up_s0 = __shfl_up_sync(0xFFFFFFFFu, n0.plus, 1);
-                const uint32_t up_id1 = __shfl_up_sync(0xFFFFFFFFu, n1.nid, 1), up_s1 = __shfl_up_sync(0xFFFFFFFFu, n1.plus, 1);
-                const uint32_t last_id0 = __shfl_sync(0xFFFFFFFFu, n0.nid, 31), last_s0 = __shfl_sync(0xFFFFFFFFu, n0.plus, 31);
-                const uint32_t idl1 = lane ? up_id1 : last_id0, sl1 = lane ? up_s1 : last_s0;
-                const bool all_links = (a.flags & FLAG_EXACT_CHECKS) != 0;
-                const bool ok0 = (int64_t(pre0) - lts >= a.d_over) && (int64_t(total - pre0) - ltail >= a.d_over);
-                const bool ok1 = (int64_t(pre1) - lts >= a.d_over) && (int64_t(total - pre1) - ltail >= a.d_over);
-                const bool emit0 = !bad && lane >= 1 && up_id0 != NO_NODE && n0.nid != NO_NODE && (ok0 || all_links);
-                const bool emit1 = !bad && has1 && idl1 != NO_NODE && n1.nid != NO_NODE && (ok1 || all_links);
-                const uint32_t eb0 = __ballot_sync(0xFFFFFFFFu, emit0), eb1 = __ballot_sync(0xFFFFFFFFu, emit1);
-                bool room = true;
-                if (eb0 | eb1) {
-                    const uint32_t n_new = __popc(eb0) + __popc(eb1);
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(a.sc.cnt + 0, n_new);
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    room = uint64_t(base) + n_new <= a.sc.cap_links;
-                    const uint32_t slot0 = base + __popc(eb0 & lt_mask), slot1 = base + __popc(eb0) + __popc(eb1 & lt_mask);
-                    if (emit0 && slot0 < a.sc.cap_links) {
-                        LinkRec r;
-                        r.key = room ? link_key(up_id0, up_s0, n0.nid, n0.plus) : LINK_HOLE;
-                        r.off = wbase + loff;
-                        r.len = llen | (ok0 ? LINK_OK : 0u);
-                        *reinterpret_cast<uint4 *>(a.sc.links + slot0) = *reinterpret_cast<const uint4 *>(&r);
-                    }
-                    if (emit1 && slot1 < a.sc.cap_links) {
-                        LinkRec r;
-                        r.key = room ? link_key(idl1, sl1, n1.nid, n1.plus) : LINK_HOLE;
-                        r.off = wbase + loff;
-                        r.len = llen | (ok1 ? LINK_OK : 0u);
-                        *reinterpret_cast<uint4 *>(a.sc.links + slot1) = *reinterpret_cast<const uint4 *>(&r);
-                    }
-                }
+                const bool done = long_line(a, win, dlb, a.sc.slab + size_t(blockIdx.x * WARPS + warp) * SLAB_N, lane,
+                                            __shfl_sync(0xFFFFFFFFu, want, L), lpath & 0xFFFFu, lpath >> 16,
+                                            __shfl_sync(0xFFFFFFFFu, ts, L), __shfl_sync(0xFFFFFFFFu, tail, L),
+                                            wbase + __shfl_sync(0xFFFFFFFFu, s, L),
+                                            __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), L));
                 if (lane == L) {
-                    if (bad || !room) exact = true;
+                    if (!done) exact = true;
                     else loc.n_multi++;
                 }
             }
+#endif
             const uint32_t xb = __ballot_sync(0xFFFFFFFFu, exact);
             if (xb) {
                 uint32_t xbase = 0;
@@ -1452,12 +1473,14 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     }
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_cnt = 0, o_links = up(64), o_ex = o_links + up(size_t(sc.cap_links) * sizeof(LinkRec)),
-                 total = o_ex + up(size_t(sc.cap_exact) * 4);
+                 o_slab = o_ex + up(size_t(sc.cap_exact) * 4),
+                 total = o_slab + up(size_t(g_scan_grid_cap) * WARPS * SLAB_N * sizeof(uint4));
     uint8_t *ws = nullptr;
     SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     sc.cnt = reinterpret_cast<uint32_t *>(ws + o_cnt);
     sc.links = reinterpret_cast<LinkRec *>(ws + o_links);
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
+    sc.slab = reinterpret_cast<uint4 *>(ws + o_slab);
     SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
 
     if (const char *tb = getenv("SVJG_TILE_BYTES")) a.flags |= uint32_t(std::min(65535, std::max(0, atoi(tb)))) << 16;

@@ -316,12 +316,12 @@ def test_scratch_exhaustion_falls_back_to_the_exact_route(gpu, monkeypatch):
     assert sorted(zip(tiny.hit_sv2.tolist(), tiny.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
 
 
-def test_long_paths_two_nodes_per_lane(gpu):
-    """Paths of 2 .. 90 nodes on a private chain graph: up to 32 nodes go through the ordinary rounds,
-    33 .. 64 through the two-nodes-per-lane section, more through the exact route -- all equal to the
-    oracle, and only the last group may be counted as generic."""
+def test_long_paths(gpu):
+    """Paths of 2 .. 300 nodes on a private chain graph: up to 32 nodes go through the ordinary rounds,
+    longer ones (up to 256) through long_line() -- all equal to the oracle and not generic.  A path that
+    revisits a node must take the exact route (first-occurrence rules)."""
     alnfilter, capi, genotype, torch = gpu
-    n_nodes, step = 120, 500
+    n_nodes, step = 330, 37
     names = [f"chrL:{i * step + 1}-{(i + 1) * step}" for i in range(n_nodes)]
     edges = {}
     for i in range(n_nodes - 1):
@@ -329,24 +329,38 @@ def test_long_paths_two_nodes_per_lane(gpu):
     for i in range(0, n_nodes - 2, 7):                                   # deletions that jump over one node
         edges[f"{names[i]}@+@{names[i + 2]}@+"] = [[f"chrL:DEL-{(i + 1) * step}-{(i + 2) * step}", 1]]
     t = alnfilter.Tables.from_memory(json.dumps(edges), "").to_device(0)
+
+    def rec(idx, ts, te, fwd=True):
+        tlen = len(idx) * step
+        path = "".join(">" + names[i] for i in idx) if fwd else "".join("<" + names[i] for i in reversed(idx))
+        return f"read\t{tlen}\t0\t{tlen}\t+\t{path}\t{tlen}\t{ts}\t{te}\t{tlen - 9}\t{tlen}\t60\ttp:A:P\tcm:i:7\n"
+
     lines, n_over = [], 0
-    for k in (2, 3, 17, 31, 32, 33, 34, 40, 47, 63, 64, 65, 70, 90):
+    for k in (2, 3, 17, 31, 32, 33, 34, 40, 47, 63, 64, 65, 70, 96, 97, 128, 200, 256, 257, 300):
         for start in (0, 5, 14):
             idx = list(range(start, start + k))
             if k % 2 == 1 and start == 0:
                 idx = [0, 2] + list(range(3, k + 1))                     # uses a jump link
             tlen = len(idx) * step
-            for ts, te in ((120, tlen - 130), (450, tlen - 50), (0, tlen - 1)):
-                fwd = "".join(">" + names[i] for i in idx)
-                rev = "".join("<" + names[i] for i in reversed(idx))
-                for path in (fwd, rev):
-                    lines.append(f"read{len(lines)}\t{tlen}\t0\t{tlen}\t+\t{path}\t{tlen}\t{ts}\t{te}\t{tlen - 9}\t{tlen}\t60\ttp:A:P\tcm:i:7\n")
-                    n_over += len(idx) > 64
-    gaf = "".join(lines)
-    res = alnfilter.filter_host(t, gaf.encode())
+            for ts, te in ((tlen // 5, tlen - tlen // 4), (3, tlen - 2), (0, tlen - 1)):
+                lines += [rec(idx, ts, te, True), rec(idx, ts, te, False)]
+                n_over += 2 * (len(idx) > 256)                           # more nodes than long_line() keeps: exact route
+    res = alnfilter.filter_host(t, "".join(lines).encode())
     want = O.hit_counts(O.filter_alignments(lines, edges, {}))
     assert want and _counts_dict(t, res.counts) == {k: list(v) for k, v in want.items()}
-    assert res.stats["n_multi"] == len(lines) and res.stats["n_generic"] == n_over
+    # a line longer than the look-ahead (1 KiB) that straddles a tile end also takes the exact route
+    n_big = sum(len(l) > 1000 and l.count(">") + l.count("<") <= 256 for l in lines)
+    assert res.stats["n_multi"] == len(lines) and n_over <= res.stats["n_generic"] <= n_over + n_big
+    short = [l for l in lines if len(l) <= 1000]
+    res1 = alnfilter.filter_host(t, "".join(short).encode())
+    assert res1.stats["n_generic"] == 0 and res1.stats["n_multi"] == len(short) and max(l.count(">") + l.count("<") for l in short) > 64
+    # revisits: node 10 comes twice (first-occurrence rules), once in a short and once in a long path
+    loops = [rec(list(range(0, 20)) + [10, 11, 12], 120, 700), rec(list(range(0, 50)) + [10, 11], 120, 1700),
+             rec(list(range(60, 0, -1)), 100, 2000), rec([0] + list(range(44, 1, -1)) + [45, 46], 20, 1600)]
+    res2 = alnfilter.filter_host(t, "".join(loops).encode())
+    want2 = O.hit_counts(O.filter_alignments(loops, edges, {}))
+    assert _counts_dict(t, res2.counts) == {k: list(v) for k, v in want2.items()}
+    assert res2.stats["n_generic"] == 2 and res2.stats["n_multi"] == 4          # an inverted stretch is no revisit
 
 
 @pytest.mark.parametrize("tile", [1024, 1600, 3072, 5024])
