@@ -160,12 +160,6 @@ __device__ __forceinline__ uint32_t lop_or_and(uint32_t t, uint32_t w, uint32_t 
 __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c4) {                    // c4: four copies of a byte < 0x80
     return lop_nor_and(lop_and_xor(w, SVJG_M7, c4) + SVJG_M7, w, SVJG_H8);
 }
-__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t w) {                           // not '0'..'9'
-    return lop_or_and(lop_and_xor(w, SVJG_M7, 0x30303030u) + 0x76767676u, w, SVJG_H8);
-}
-__device__ __forceinline__ uint32_t delim_bytes(uint32_t w) {                              // '<' 0x3C or '>' 0x3E
-    return lop_nor_and(lop_and_xor(w, 0x7D7D7D7Du, 0x3C3C3C3Cu) + SVJG_M7, w, SVJG_H8);
-}
 // 16 class flags of a 16-byte chunk, bit i = byte i.  dp4a gathers the four bit-7 flags of a
 // word: sum(0x80 * weight) = bits << 7.
 template <class F>
@@ -616,7 +610,9 @@ struct Rec {
     }
 
     // extract_nodes / get_aln_links / lookups for any path (:130-166)
-    __device__ __noinline__ void general() {
+    // `part` of `parts`: the links i with i % parts == part (the lanes of a warp share one heavy line;
+    // every node is still the right end of some lane's link, so every strand() is evaluated)
+    __device__ __noinline__ void general(uint32_t part = 0, uint32_t parts = 1) {
         uint32_t n = 0;
         {
             P cur = ps;
@@ -624,24 +620,36 @@ struct Rec {
             while (next_tok(cur, t)) ++n;
         }
         if (n < 2) return;                                       // :133
-        if (!angle) loc.n_multi++;
-        loc.n_generic++;
+        if (part == 0) {
+            if (!angle) loc.n_multi++;
+            loc.n_generic++;
+        }
         P cur = ps;
         Tok A, B;
         next_tok(cur, A);
-        uint32_t idA = node_id(tok_hash(A), A);
-        int sA = strand(A);
-        if (err) return;
+        uint32_t idA = NO_NODE;
+        int sA = 0;
+        bool have_a = false;
         for (uint32_t i = 1; i < n; ++i) {
             next_tok(cur, B);
-            uint32_t idB = node_id(tok_hash(B), B);
-            int sB = strand(B);
-            if (err) return;
-            link(A, idA, sA, B, idB, sB, false, false);
-            if (err) return;
+            if (i % parts == part) {
+                if (!have_a) {
+                    idA = node_id(tok_hash(A), A);
+                    sA = strand(A);
+                    if (err) return;
+                }
+                const uint32_t idB = node_id(tok_hash(B), B);
+                const int sB = strand(B);
+                if (err) return;
+                link(A, idA, sA, B, idB, sB, false, false);
+                if (err) return;
+                idA = idB;
+                sA = sB;
+                have_a = true;
+            } else {
+                have_a = false;
+            }
             A = B;
-            idA = idB;
-            sA = sB;
         }
     }
 };
@@ -883,11 +891,6 @@ __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t 
 // the nodes into the warp's slab in device memory (L2) and adds up the lengths; then every node is
 // compared with all nodes in front of it (a repeated start value: exact route); the second sweep
 // writes the links.  All lanes call it together; false: the line must take the exact route.
-#ifdef SVJG_NO_LONG
-constexpr bool LONG_ENABLED = false;
-#else
-constexpr bool LONG_ENABLED = true;
-#endif
 constexpr int SLAB_N = 256;                    // nodes of such a line (more: exact route)
 
 __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, const uint32_t *dlb, uint4 *slab, int lane,
@@ -1338,7 +1341,8 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
     Local loc;
     // Lines differ wildly in the work they need (general() is quadratic in the path nodes), and lanes
     // of a warp that run different lines execute one after the other.  While there are few lines,
-    // every line gets a warp of its own (lane 0 works); only a flood of them goes one per thread.
+    // every line gets a warp of its own and the lanes share its links; only a flood of them goes one
+    // line per thread.
     const uint32_t n_warps = gridDim.x * (FLAT_THREADS / 32);
 #ifdef SVJG_NO_PER_WARP
     const bool per_warp = false;
@@ -1347,20 +1351,19 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
 #endif
     const uint32_t me = per_warp ? (blockIdx.x * FLAT_THREADS + threadIdx.x) >> 5 : blockIdx.x * FLAT_THREADS + threadIdx.x;
     const uint32_t stride = per_warp ? n_warps : gridDim.x * FLAT_THREADS;
-    if (!per_warp || (threadIdx.x & 31) == 0) {
-        for (uint32_t i = me; i < n; i += stride) {
-            const uint32_t off = a.sc.exact[i];
-            uint64_t e = off;
-            while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
-            const uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
-            Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-            const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
-            if (!rec.err && ntok >= 2) {
-                if (ntok != COMMA_PATH) loc.n_multi++;
-                rec.general();
-            }
-            if (rec.err) report(a, rec.err, off);
+    const uint32_t part = per_warp ? (threadIdx.x & 31u) : 0u, parts = per_warp ? 32u : 1u;
+    for (uint32_t i = me; i < n; i += stride) {
+        const uint32_t off = a.sc.exact[i];
+        uint64_t e = off;
+        while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
+        const uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
+        Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+        const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
+        if (!rec.err && ntok >= 2) {
+            if (ntok != COMMA_PATH && part == 0) loc.n_multi++;
+            rec.general(part, parts);
         }
+        if (rec.err) report(a, rec.err, off);
     }
     add_stats(a, loc);
 }
