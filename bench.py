@@ -6,8 +6,8 @@ genotype) on the BASELINE.json workload, one JSON line on stdout.
     python bench.py --impl reference ...      # CPU arm: the oracle port on host cores
 
 A "step" is one pass of the hot path over one batch of synthetic GAF: counters
-reset -> fused filter kernel -> (NCCL all-reduce of the counters when N > 1) ->
-genotype kernel.  `value` = alignments/s with the batch resident in HBM;
+reset -> filter chain (probe, scan_parse, link, exact kernels) -> (NCCL all-reduce of
+the counters when N > 1) -> genotype kernel.  `value` = alignments/s with the batch resident in HBM;
 `e2e` = the same through svjg_filter_host (pinned HOST bytes in, counts + hits +
 genotypes back on the host, copies inside the timed region).
 """
@@ -30,7 +30,7 @@ for p in (ROOT, PKG):
 METRIC = "gaf_alignments_filtered_assigned_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of the filter chain per launch, from the ncu --set full
 # capture committed under profiles/ (None where no capture exists for the workload)
-FILTER_TRAFFIC = {"C2": 811_000_000}
+FILTER_TRAFFIC = {"C2": 558_700_000}   # profiles/r1/ncu_chain_v12_summary.txt: scan_parse 517.3+19.1, link 22.0, probe 0.3 MB
 UNIT = "alignments/s"
 
 
@@ -429,7 +429,7 @@ def main():
         "svs_genotyped_per_sec": n_sv / (geno_ms * 1e-3) if geno_ms > 0 else None,
         "kernel_ms": {"filter": filt_ms, "filter_scan_parse_only": scan_ms, "allreduce": comm_ms, "genotype": geno_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": FILTER_TRAFFIC.get(args.workload), "kernel": "filter chain: scan_parse+token+clash+link+exact", "algorithmic_bytes_per_launch": algo_bytes,
+                     "traffic": FILTER_TRAFFIC.get(args.workload), "kernel": "filter chain: probe+scan_parse+link+exact", "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": peak_src,
                      "dominant_kernel": {"name": "scan_parse_kernel", "ms": scan_ms, "share_of_chain": scan_ms / filt_ms,
                                          "achieved": n_bytes / (scan_ms * 1e-3) / 1e9, "frac": n_bytes / (scan_ms * 1e-3) / 1e9 / peak,
@@ -442,7 +442,7 @@ def main():
                                    "single thread like the reference"},
         "e2e": {"value": job_rec * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke},
-        "gpu_launches": 8 * K,   # reset + scan_parse + token + clash + link + exact + genotype (+1 memset node)
+        "gpu_launches": 6 * K,   # reset + probe + scan_parse + link + exact + genotype (plus one memset node per step)
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

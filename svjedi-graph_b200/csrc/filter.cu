@@ -1372,7 +1372,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
 // probe: average line length of the head of the shard -> bytes per tile, so that a tile holds about
 // one line per lane of the warp that parses it
 // ===========================================================================
-constexpr int PROBE_THREADS = 1024, PROBE_BYTES = 256 << 10;
+constexpr int PROBE_THREADS = 1024, PROBE_BYTES = 64 << 10;
 
 __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const __grid_constant__ FilterArgs a) {
     __shared__ uint32_t total;
