@@ -1277,7 +1277,9 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
 // ===========================================================================
 // link: one thread per link record, both keys
 // ===========================================================================
-constexpr int LINK_STAGE = 1024;   // hits a block stages per round of FLAT_THREADS links
+constexpr int LINK_STAGE = 2048;    // hits a block stages between flushes
+constexpr int LINK_PER_THREAD = 2;  // link records a thread takes per round (their probes are in flight together)
+constexpr int LINK_ROUNDS = 3;      // rounds between flushes: at one hit per record 1536 of the 2048 slots
 
 __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_constant__ FilterArgs a) {
     __shared__ uint32_t h_sv[LINK_STAGE], h_off[LINK_STAGE], h_len[LINK_STAGE];
@@ -1287,13 +1289,20 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
     Local loc;
     if (threadIdx.x == 0) h_n = 0;
     __syncthreads();
-    for (uint32_t t0 = blockIdx.x * FLAT_THREADS; t0 < n_links; t0 += gridDim.x * FLAT_THREADS) {
-        const uint32_t t = t0 + threadIdx.x;
-        if (t < n_links) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(a.sc.links) + t);
-            const uint64_t key = (uint64_t(r.y) << 32) | r.x;
+    constexpr uint32_t PER_ROUND = FLAT_THREADS * LINK_PER_THREAD;
+    uint32_t round = 0;
+    for (uint32_t t0 = blockIdx.x * PER_ROUND; t0 < n_links; t0 += gridDim.x * PER_ROUND) {
+        uint4 r[LINK_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < LINK_PER_THREAD; ++k) {
+            const uint32_t t = t0 + uint32_t(k) * FLAT_THREADS + threadIdx.x;
+            r[k] = t < n_links ? __ldg(reinterpret_cast<const uint4 *>(a.sc.links) + t) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < LINK_PER_THREAD; ++k) {
+            const uint64_t key = (uint64_t(r[k].y) << 32) | r[k].x;
             if (key != LINK_HOLE) {
-                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, r.z, r.w & ~LINK_OK, loc);
+                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, r[k].z, r[k].w & ~LINK_OK, loc);
                 rec.stage_sv = h_sv;
                 rec.stage_off = h_off;
                 rec.stage_len = h_len;
@@ -1301,12 +1310,15 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
                 rec.stage_cap = LINK_STAGE;
                 const Rec<GmemSrc>::Tok none{0, 0};
                 rec.link(none, uint32_t(key >> 33), int((key >> 32) & 1u), none, uint32_t(key) >> 1, int(key & 1u), true,
-                         (r.w & LINK_OK) != 0);
-                if (rec.err) report(a, rec.err, r.z);
+                         (r[k].w & LINK_OK) != 0);
+                if (rec.err) report(a, rec.err, r[k].z);
             }
         }
-        // flush the staged hits: one cursor atomic for the block, coalesced tuple stores,
-        // warp-aggregated counter atomics
+        // flush the staged hits every few rounds and at the end: one cursor atomic for the block,
+        // coalesced tuple stores, warp-aggregated counter atomics
+        ++round;
+        const bool last = t0 + gridDim.x * PER_ROUND >= n_links;
+        if (round % LINK_ROUNDS != 0 && !last) continue;
         __syncthreads();
         const uint32_t n = min(h_n, uint32_t(LINK_STAGE));
         if (threadIdx.x == 0 && n) h_base = atomicAdd(a.stats + 0, (unsigned long long)n);
