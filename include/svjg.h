@@ -103,7 +103,7 @@ typedef struct svjg_filter_stats {
     uint64_t status;     /* 0, or the first SVJG_BAD_* reason                    */
     uint64_t err_offset; /* byte offset of the lowest offending line             */
     uint64_t n_generic;  /* records that took the general (quirk-exact) path     */
-    uint64_t reserved;
+    uint64_t n_exact;      /* lines the exact kernel took (irregular shape, too long for the window, no scratch) */
 } svjg_filter_stats;
 
 int svjg_filter_reset(uint32_t *d_counts, uint32_t num_sv, svjg_filter_stats *d_stats, void *stream);

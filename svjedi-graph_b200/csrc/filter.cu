@@ -91,11 +91,12 @@ static_assert(sizeof(LinkRec) == 16, "LinkRec is 16 bytes");
 
 // device scratch of one svjg_filter_device() call
 struct Scratch {
-    uint32_t *cnt;        // [0] link records, [2] exact-route lines
+    uint32_t *cnt;        // [0] link records, [2] exact-route lines, [4] bytes per tile, [5] pool cursor
     LinkRec *links;
     uint32_t *exact;      // line start offsets
     uint4 *slab;          // per warp of scan_parse: nodes of a long line (long_line())
-    uint32_t cap_links, cap_exact;
+    uint4 *pool;          // exact kernel: bitmap and nodes of giant lines, bump-allocated (cnt[5])
+    uint32_t cap_links, cap_exact, cap_pool;
 };
 
 struct FilterArgs {
@@ -893,10 +894,13 @@ __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t 
 // writes the links.  All lanes call it together; false: the line must take the exact route.
 constexpr int SLAB_N = 256;                    // nodes of such a line (more: exact route)
 
-__device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, const uint32_t *dlb, uint4 *slab, int lane,
-                                       uint32_t cnt, uint32_t lps, uint32_t lpe, int64_t lts, int64_t ltail, uint32_t off,
-                                       uint32_t len) {
-    if (cnt > SLAB_N) return false;
+// DIRECT (exact kernel, which runs behind the link kernel): the links are probed here and now instead
+// of being written as records; `win` and `dlb` may then point into device memory.
+template <bool DIRECT>
+__device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, const uint32_t *dlb, uint4 *slab,
+                                       uint32_t slab_cap, int lane, uint32_t cnt, uint32_t lps, uint32_t lpe, int64_t lts,
+                                       int64_t ltail, uint32_t off, uint32_t len, Local &loc) {
+    if (cnt > slab_cap) return false;
     uint64_t total = 0;
     bool bad = false;
     uint32_t from = lps;
@@ -923,9 +927,12 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, 
     if (__any_sync(0xFFFFFFFFu, clash)) return false;
     // room for every link of the line, taken before the first one is written
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(a.sc.cnt + 0, cnt - 1u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    const bool room = uint64_t(base) + (cnt - 1u) <= a.sc.cap_links;
+    bool room = true;
+    if (!DIRECT) {
+        if (lane == 0) base = atomicAdd(a.sc.cnt + 0, cnt - 1u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        room = uint64_t(base) + (cnt - 1u) <= a.sc.cap_links;
+    }
     uint64_t before = 0;
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
         const uint32_t t = c0 + uint32_t(lane);
@@ -936,7 +943,14 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, 
         const uint64_t pre = before + incl - me.y;
         const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
         const bool emit = room && lf.x != NO_NODE && me.x != NO_NODE && (ok || (a.flags & FLAG_EXACT_CHECKS));
-        if (act && t && base + t - 1u < a.sc.cap_links) {                  // link t-1 of the line: a record or a hole
+        if (DIRECT) {
+            if (act && t && emit) {
+                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+                const Rec<GmemSrc>::Tok none{0, 0};
+                rec.link(none, lf.x, int(lf.w), none, me.x, int(me.w), true, ok);
+                if (rec.err) report(a, rec.err, off);
+            }
+        } else if (act && t && base + t - 1u < a.sc.cap_links) {           // link t-1 of the line: a record or a hole
             LinkRec r;
             r.key = emit ? link_key(lf.x, lf.w, me.x, me.w) : LINK_HOLE;
             r.off = off;
@@ -1246,11 +1260,11 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
             for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > TOKCAP); longb; longb &= longb - 1) {
                 const int L = __ffs(longb) - 1;
                 const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), L);
-                const bool done = long_line(a, win, dlb, a.sc.slab + size_t(blockIdx.x * WARPS + warp) * SLAB_N, lane,
-                                            __shfl_sync(0xFFFFFFFFu, want, L), lpath & 0xFFFFu, lpath >> 16,
-                                            __shfl_sync(0xFFFFFFFFu, ts, L), __shfl_sync(0xFFFFFFFFu, tail, L),
-                                            wbase + __shfl_sync(0xFFFFFFFFu, s, L),
-                                            __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), L));
+                const bool done = long_line<false>(a, win, dlb, a.sc.slab + size_t(blockIdx.x * WARPS + warp) * SLAB_N, SLAB_N,
+                                                   lane, __shfl_sync(0xFFFFFFFFu, want, L), lpath & 0xFFFFu, lpath >> 16,
+                                                   __shfl_sync(0xFFFFFFFFu, ts, L), __shfl_sync(0xFFFFFFFFu, tail, L),
+                                                   wbase + __shfl_sync(0xFFFFFFFFu, s, L),
+                                                   __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), L), loc);
                 if (lane == L) {
                     if (!done) exact = true;
                     else loc.n_multi++;
@@ -1348,6 +1362,33 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
 // ===========================================================================
 // exact: one thread per irregular line — the reference's string semantics, literally
 // ===========================================================================
+// A line that is regular but too long for scan_parse's window (thousands of path nodes): the warp
+// builds the delimiter bitmap of its path column in device memory and runs long_line() on the bytes
+// where they lie.  false: general() decides.
+__device__ __noinline__ bool giant_line(const FilterArgs &a, uint32_t ps, uint32_t pe, uint32_t ntok, int64_t ts, int64_t tail,
+                                        uint32_t off, uint32_t len, int lane, Local &loc) {
+    const uint32_t w0 = ps >> 5, nw = (pe >> 5) - w0 + 4u;                 // bitmap words, a few to spare for reads ahead
+    const uint32_t need = (nw + 3u) / 4u + ntok;                            // in 16-byte units: bitmap, then one per node
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.sc.cnt + 5, need);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (uint64_t(base) + need > a.sc.cap_pool) return false;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(a.sc.pool + base);
+    for (uint32_t w = uint32_t(lane); w < nw; w += 32) {
+        const uint64_t pos = uint64_t(w0 + w) * 32u;
+        uint32_t m = 0;
+        if (pos + 32 <= a.n) {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(a.gaf + pos)), v1 = __ldg(reinterpret_cast<const uint4 *>(a.gaf + pos + 16));
+            m = mask16(v0, IsDelim{1u}) | (mask16(v1, IsDelim{1u}) << 16);
+        } else {
+            for (uint32_t k = 0; k < 32 && pos + k < a.n; ++k) m |= uint32_t(is_delim(__ldg(a.gaf + pos + k))) << k;
+        }
+        __stcg(bits + w, m);
+    }
+    __syncwarp();
+    return long_line<true>(a, a.gaf, bits - w0, a.sc.pool + base + (nw + 3u) / 4u, ntok, lane, ntok, ps, pe, ts, tail, off, len, loc);
+}
+
 __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_constant__ FilterArgs a) {
     const uint32_t n = min(a.sc.cnt[2], a.sc.cap_exact);
     Local loc;
@@ -1364,6 +1405,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
     const uint32_t me = per_warp ? (blockIdx.x * FLAT_THREADS + threadIdx.x) >> 5 : blockIdx.x * FLAT_THREADS + threadIdx.x;
     const uint32_t stride = per_warp ? n_warps : gridDim.x * FLAT_THREADS;
     const uint32_t part = per_warp ? (threadIdx.x & 31u) : 0u, parts = per_warp ? 32u : 1u;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(a.stats + 7, (unsigned long long)n);
     for (uint32_t i = me; i < n; i += stride) {
         const uint32_t off = a.sc.exact[i];
         uint64_t e = off;
@@ -1373,7 +1415,11 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
         const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
         if (!rec.err && ntok >= 2) {
             if (ntok != COMMA_PATH && part == 0) loc.n_multi++;
-            rec.general(part, parts);
+            // a warp of its own: first the fast rules on the bytes where they lie; if they do not apply, general()
+            const bool fast = per_warp && ntok != COMMA_PATH && !(a.flags & FLAG_FORCE_GENERAL) && e < 0xFFFFFFFFull &&
+                              giant_line(a, uint32_t(rec.ps), uint32_t(rec.pe), ntok, rec.ts, rec.tlen - rec.te - 1, off, len,
+                                         int(threadIdx.x & 31u), loc);
+            if (!fast) rec.general(part, parts);
         }
         if (rec.err) report(a, rec.err, off);
     }
@@ -1483,19 +1529,22 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     Scratch &sc = a.sc;
     sc.cap_links = uint32_t(n_bytes / 20 + 4096);     // a path node with its delimiter is rarely under 20 bytes
     sc.cap_exact = uint32_t(n_bytes / 16 + 64);       // a line shorter than 16 bytes cannot hold 12 columns
+    sc.cap_pool = uint32_t(std::min<uint64_t>(4u << 20, std::max<uint64_t>(64u << 10, n_bytes / 256)));   // 16-byte units: 1-64 MiB
     if (const char *tiny = getenv("SVJG_TEST_TINY_SCRATCH")) {   // test hook: force the "no room" fallbacks
         if (tiny[0] == '1') sc.cap_links = 64;
     }
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_cnt = 0, o_links = up(64), o_ex = o_links + up(size_t(sc.cap_links) * sizeof(LinkRec)),
                  o_slab = o_ex + up(size_t(sc.cap_exact) * 4),
-                 total = o_slab + up(size_t(g_scan_grid_cap) * WARPS * SLAB_N * sizeof(uint4));
+                 o_pool = o_slab + up(size_t(g_scan_grid_cap) * WARPS * SLAB_N * sizeof(uint4)),
+                 total = o_pool + up(size_t(sc.cap_pool) * sizeof(uint4));
     uint8_t *ws = nullptr;
     SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     sc.cnt = reinterpret_cast<uint32_t *>(ws + o_cnt);
     sc.links = reinterpret_cast<LinkRec *>(ws + o_links);
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
     sc.slab = reinterpret_cast<uint4 *>(ws + o_slab);
+    sc.pool = reinterpret_cast<uint4 *>(ws + o_pool);
     SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
 
     if (const char *tb = getenv("SVJG_TILE_BYTES")) a.flags |= uint32_t(std::min(65535, std::max(0, atoi(tb)))) << 16;

@@ -34,7 +34,7 @@ class SvjgError(RuntimeError):
 
 class FilterStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
-                ("n_hits", "n_records", "n_multi", "n_checks", "status", "err_offset", "n_generic", "reserved")]
+                ("n_hits", "n_records", "n_multi", "n_checks", "status", "err_offset", "n_generic", "n_exact")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -312,7 +312,7 @@ def test_scratch_exhaustion_falls_back_to_the_exact_route(gpu, monkeypatch):
     monkeypatch.delenv("SVJG_TEST_TINY_SCRATCH")
     assert (tiny.counts == normal.counts).all() and tiny.n_hits == normal.n_hits
     assert tiny.stats["n_multi"] == normal.stats["n_multi"]
-    assert tiny.stats["n_generic"] > normal.stats["n_generic"]
+    assert tiny.stats["n_exact"] > normal.stats["n_exact"]          # the lines that found no room went the exact route
     assert sorted(zip(tiny.hit_sv2.tolist(), tiny.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
 
 
@@ -348,12 +348,9 @@ def test_long_paths(gpu):
     res = alnfilter.filter_host(t, "".join(lines).encode())
     want = O.hit_counts(O.filter_alignments(lines, edges, {}))
     assert want and _counts_dict(t, res.counts) == {k: list(v) for k, v in want.items()}
-    # a line longer than the look-ahead (1 KiB) that straddles a tile end also takes the exact route
-    n_big = sum(len(l) > 1000 and l.count(">") + l.count("<") <= 256 for l in lines)
-    assert res.stats["n_multi"] == len(lines) and n_over <= res.stats["n_generic"] <= n_over + n_big
-    short = [l for l in lines if len(l) <= 1000]
-    res1 = alnfilter.filter_host(t, "".join(short).encode())
-    assert res1.stats["n_generic"] == 0 and res1.stats["n_multi"] == len(short) and max(l.count(">") + l.count("<") for l in short) > 64
+    # more than 256 nodes, or longer than the look-ahead (1 KiB) and straddling a tile end: the exact
+    # kernel takes the line, but its giant_line() applies the fast rules there -- still not generic
+    assert res.stats["n_multi"] == len(lines) and res.stats["n_generic"] == 0 and n_over > 0
     # revisits: node 10 comes twice (first-occurrence rules), once in a short and once in a long path
     loops = [rec(list(range(0, 20)) + [10, 11, 12], 120, 700), rec(list(range(0, 50)) + [10, 11], 120, 1700),
              rec(list(range(60, 0, -1)), 100, 2000), rec([0] + list(range(44, 1, -1)) + [45, 46], 20, 1600)]
@@ -374,5 +371,6 @@ def test_every_tile_size_gives_the_same_result(gpu, monkeypatch, tile):
     monkeypatch.setenv("SVJG_TILE_BYTES", str(tile))
     forced = alnfilter.filter_host(t, gaf)
     monkeypatch.delenv("SVJG_TILE_BYTES")
-    assert (forced.counts == normal.counts).all() and forced.stats == normal.stats
+    same = lambda st: {k: v for k, v in st.items() if k != "n_exact"}     # lines past the window depend on the tile
+    assert (forced.counts == normal.counts).all() and same(forced.stats) == same(normal.stats)
     assert sorted(zip(forced.hit_sv2.tolist(), forced.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
