@@ -381,8 +381,10 @@ def main():
     Ke = args.e2e_steps or max(3, min(K, 20))
     hit_cap = n_hits + 1024
 
+    host_out = alnfilter.HostBuffers(tables, hit_cap)     # pinned result arrays, allocated once like h_gaf
+
     def e2e_step():
-        res = alnfilter.filter_host(tables, h_gaf, hit_cap=hit_cap)
+        res = alnfilter.filter_host(tables, h_gaf, out=host_out)
         dc = torch.from_numpy(res.counts.view(np.int32)).to(dev, non_blocking=True)
         if world > 1:
             dist.all_reduce(dc)
@@ -402,7 +404,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     h2d = n_bytes + tables.num_sv * 8 + n_loc * 5 + lut.numel() * 8
-    d2h = tables.num_sv * 8 + 64 + res.n_hits * 12 + n_loc * (24 + 1 + 8 + 1)
+    d2h = tables.num_sv * 8 + 64 + res.n_hits * 16 + n_loc * (24 + 1 + 8 + 1)     # hits: u32 sv, u64 offset, u32 length
 
     if rank != 0:
         if world > 1:

@@ -27,7 +27,7 @@ int cuda_fail(int cuda_err, const char *what) {
 // workspace of svjg_filter_host
 // ---------------------------------------------------------------------------
 struct HostWs {
-    static constexpr uint64_t CHUNK = 256ull << 20;
+    static constexpr uint64_t CHUNK = 64ull << 20;
     uint8_t *d_buf[2] = {nullptr, nullptr};
     uint64_t buf_cap = 0;
     uint32_t *d_counts = nullptr;
@@ -36,10 +36,9 @@ struct HostWs {
     uint64_t hit_cap = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-    unsigned long long *h_cursor = nullptr;   // pinned: hit cursor after each chunk
+    unsigned long long *d_cursor = nullptr;   // device: hit cursor after each chunk
     uint64_t cursor_cap = 0;
-    uint32_t *h_hit[2] = {nullptr, nullptr};  // pinned staging of hit_off / hit_len
-    uint64_t h_hit_cap = 0;
+    uint64_t *d_off64 = nullptr;              // hit offsets made absolute on the device
 };
 
 void free_host_ws(svjg_tables *t) {
@@ -49,13 +48,13 @@ void free_host_ws(svjg_tables *t) {
         if (w->d_buf[i]) cudaFree(w->d_buf[i]);
         if (w->copied[i]) cudaEventDestroy(w->copied[i]);
         if (w->freed[i]) cudaEventDestroy(w->freed[i]);
-        if (w->h_hit[i]) cudaFreeHost(w->h_hit[i]);
     }
     for (int i = 0; i < 3; ++i)
         if (w->d_hit[i]) cudaFree(w->d_hit[i]);
     if (w->d_counts) cudaFree(w->d_counts);
     if (w->d_stats) cudaFree(w->d_stats);
-    if (w->h_cursor) cudaFreeHost(w->h_cursor);
+    if (w->d_cursor) cudaFree(w->d_cursor);
+    if (w->d_off64) cudaFree(w->d_off64);
     if (w->s_copy) cudaStreamDestroy(w->s_copy);
     if (w->s_comp) cudaStreamDestroy(w->s_comp);
     delete w;
@@ -175,14 +174,18 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
         }
         w->hit_cap = 0;
         for (int i = 0; i < 3; ++i) SVJG_CUDA(cudaMalloc(&w->d_hit[i], hit_cap * 4));
+        if (w->d_off64) SVJG_CUDA(cudaFree(w->d_off64));
+        w->d_off64 = nullptr;
+        SVJG_CUDA(cudaMalloc(&w->d_off64, hit_cap * 8));
         w->hit_cap = hit_cap;
     }
     if (w->cursor_cap < n_chunks + 1) {
-        if (w->h_cursor) SVJG_CUDA(cudaFreeHost(w->h_cursor));
-        w->h_cursor = nullptr;
-        SVJG_CUDA(cudaMallocHost(&w->h_cursor, (n_chunks + 1) * sizeof(unsigned long long)));
+        if (w->d_cursor) SVJG_CUDA(cudaFree(w->d_cursor));
+        w->d_cursor = nullptr;
+        SVJG_CUDA(cudaMalloc(&w->d_cursor, (n_chunks + 1) * sizeof(unsigned long long)));
         w->cursor_cap = n_chunks + 1;
     }
+    SVJG_CUDA(cudaMemsetAsync(w->d_cursor, 0, sizeof(unsigned long long), w->s_comp));
 
     int rc = svjg_filter_reset(w->d_counts, num_sv, w->d_stats, w->s_comp);
     if (rc) return rc;
@@ -197,9 +200,13 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
                                 hit_cap, w->d_stats, w->s_comp);
         if (rc) return rc;
         SVJG_CUDA(cudaEventRecord(w->freed[b], w->s_comp));
-        // the hit cursor after this chunk tells which hits carry which chunk base
-        SVJG_CUDA(cudaMemcpyAsync(w->h_cursor + k + 1, &w->d_stats->n_hits, sizeof(unsigned long long),
-                                  cudaMemcpyDeviceToHost, w->s_comp));
+        // the hits of this chunk lie between the cursor before and after it: make their offsets absolute
+        SVJG_CUDA(cudaMemcpyAsync(w->d_cursor + k + 1, &w->d_stats->n_hits, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToDevice, w->s_comp));
+        if (hit_cap) {
+            rc = svjg_hits_absolute(w->d_hit[1], w->d_off64, w->d_cursor + k, cut[k], hit_cap, w->s_comp);
+            if (rc) return rc;
+        }
     }
     SVJG_CUDA(cudaMemcpyAsync(stats, w->d_stats, sizeof(svjg_filter_stats), cudaMemcpyDeviceToHost, w->s_comp));
     SVJG_CUDA(cudaMemcpyAsync(counts, w->d_counts, size_t(num_sv) * 8, cudaMemcpyDeviceToHost, w->s_comp));
@@ -215,24 +222,11 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
     if (stats->n_hits > hit_cap) return set_error(SVJG_E_HITS_OVERFLOW, "hit buffers too small");
     const uint64_t nh = stats->n_hits;
     if (nh) {
-        if (w->h_hit_cap < nh) {
-            for (int i = 0; i < 2; ++i) {
-                if (w->h_hit[i]) SVJG_CUDA(cudaFreeHost(w->h_hit[i]));
-                w->h_hit[i] = nullptr;
-            }
-            w->h_hit_cap = 0;
-            for (int i = 0; i < 2; ++i) SVJG_CUDA(cudaMallocHost(&w->h_hit[i], hit_cap * 4));
-            w->h_hit_cap = hit_cap;
-        }
+        // straight into the caller's arrays: at PCIe speed if they are pinned, staged by the driver if not
         SVJG_CUDA(cudaMemcpyAsync(hit_sv2, w->d_hit[0], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
-        SVJG_CUDA(cudaMemcpyAsync(w->h_hit[0], w->d_hit[1], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
+        SVJG_CUDA(cudaMemcpyAsync(hit_off, w->d_off64, nh * 8, cudaMemcpyDeviceToHost, w->s_comp));
         SVJG_CUDA(cudaMemcpyAsync(hit_len, w->d_hit[2], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
         SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
-        w->h_cursor[0] = 0;
-        for (size_t k = 0; k < n_chunks; ++k) {
-            uint64_t lo = w->h_cursor[k], hi = std::min<uint64_t>(w->h_cursor[k + 1], nh);
-            for (uint64_t i = lo; i < hi; ++i) hit_off[i] = cut[k] + w->h_hit[0][i];
-        }
     }
     return SVJG_OK;
 }

@@ -1466,10 +1466,24 @@ __global__ void reset_kernel(uint32_t *counts, uint64_t n, unsigned long long *s
     if (i < 8) stats[i] = (i == 5) ? ~0ull : 0ull;
 }
 
+__global__ void hits_absolute_kernel(const uint32_t *off32, uint64_t *off64, const unsigned long long *cursor, uint64_t base,
+                                     uint64_t hit_cap) {
+    const uint64_t lo = cursor[0], hi = cursor[1] < hit_cap ? cursor[1] : hit_cap;
+    for (uint64_t i = lo + blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < hi; i += uint64_t(gridDim.x) * blockDim.x)
+        off64[i] = base + off32[i];
+}
+
 int g_scan_grid_cap = 0;   // blocks of scan_parse resident at once (SM count x occupancy), per process
 int g_sms = 0;
 
 }  // namespace
+
+int svjg::svjg_hits_absolute(const uint32_t *d_off32, uint64_t *d_off64, const unsigned long long *d_cursor, uint64_t base,
+                             uint64_t hit_cap, void *stream) {
+    hits_absolute_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(d_off32, d_off64, d_cursor, base, hit_cap);
+    SVJG_CUDA(cudaGetLastError());
+    return SVJG_OK;
+}
 
 extern "C" int svjg_filter_reset(uint32_t *d_counts, uint32_t num_sv, svjg_filter_stats *d_stats, void *stream) {
     if (!d_counts || !d_stats) return set_error(SVJG_E_ARG, "svjg_filter_reset: NULL argument");

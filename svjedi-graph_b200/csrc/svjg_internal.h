@@ -31,6 +31,9 @@ namespace svjg {
 int set_error(int code, const std::string &msg);
 int cuda_fail(int cuda_err, const char *what);   // records the message, returns SVJG_E_CUDA
 void free_host_ws(svjg_tables *t);
+// hit offsets of one chunk (cursor[0] .. cursor[1]) -> absolute 64-bit offsets; filter.cu
+int svjg_hits_absolute(const uint32_t *d_off32, uint64_t *d_off64, const unsigned long long *d_cursor, uint64_t base,
+                       uint64_t hit_cap, void *stream);
 }  // namespace svjg
 
 #define SVJG_CUDA(call)                                                        \

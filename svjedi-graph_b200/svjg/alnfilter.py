@@ -114,20 +114,44 @@ def _raise_input(stats):
     raise InputError(f"GAF line at byte {stats['err_offset']}: {reason} (the reference raises here)")
 
 
-def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None):
+class HostBuffers:
+    """Pinned host arrays for the results of filter_host(): the counters and the hit list come back at
+    PCIe speed instead of through the driver's staging copies.  Reusable: every filter_host(out=...)
+    call overwrites them, so the result of the previous call must have been consumed."""
+
+    def __init__(self, tables, hit_cap):
+        import torch
+        self.hit_cap = int(hit_cap)
+        self._t = [torch.zeros((max(1, tables.num_sv), 2), dtype=torch.int32).pin_memory(),
+                   torch.empty(max(1, hit_cap), dtype=torch.int32).pin_memory(),
+                   torch.empty(max(1, hit_cap), dtype=torch.int64).pin_memory(),
+                   torch.empty(max(1, hit_cap), dtype=torch.int32).pin_memory()]
+        self.counts = self._t[0].numpy().view(np.uint32)[: tables.num_sv]
+        self.sv2 = self._t[1].numpy().view(np.uint32)
+        self.off = self._t[2].numpy().view(np.uint64)
+        self.len = self._t[3].numpy().view(np.uint32)
+
+
+def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None, out=None):
     """The per-line loop of filter-alignments.py:123-166 over GAF bytes in HOST
     memory (pinned memory copies fastest).  Returns counts, stats and, if
-    ``want_hits``, the hit list with absolute byte offsets."""
+    ``want_hits``, the hit list with absolute byte offsets.  ``out``: HostBuffers
+    to receive them (pinned, reused); otherwise fresh numpy arrays."""
     if tables.device is None:
         raise RuntimeError("tables.to_device() first")
     a = _as_u8(gaf)
     n = int(a.size)
-    counts = np.zeros((tables.num_sv, 2), dtype=np.uint32)
+    counts = out.counts if out is not None else np.zeros((tables.num_sv, 2), dtype=np.uint32)
     stats = capi.FilterStats()
-    if hit_cap is None:
+    if out is not None:
+        hit_cap = out.hit_cap if want_hits else 0
+    elif hit_cap is None:
         hit_cap = max(1024, n // 64) if want_hits else 0
     while True:
-        if hit_cap:
+        if hit_cap and out is not None:
+            sv2, off, ln = out.sv2, out.off, out.len
+            ptrs = (sv2.ctypes.data, off.ctypes.data, ln.ctypes.data)
+        elif hit_cap:
             sv2 = np.empty(hit_cap, dtype=np.uint32)
             off = np.empty(hit_cap, dtype=np.uint64)
             ln = np.empty(hit_cap, dtype=np.uint32)
@@ -139,6 +163,8 @@ def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None):
                                        counts.ctypes.data, *ptrs, hit_cap, C.byref(stats))
         st = stats.as_dict()
         if rc == capi.E_HITS_OVERFLOW:
+            if out is not None:
+                raise RuntimeError(f"HostBuffers hold {out.hit_cap} hits, the batch has {st['n_hits']}")
             hit_cap = int(st["n_hits"]) + 16
             continue
         if rc == capi.E_INPUT:
