@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--kernel-only", action="store_true", help="developer mode: print the kernel times and stop")
     ap.add_argument("--cpu-sample", type=int, default=150_000, help="records the CPU baseline is timed on")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: counters summed inside the genotype kernel over NVLink peer memory (p2p), or ncclAllReduce")
     return ap.parse_args()
 
 
@@ -295,22 +297,43 @@ def main():
     sp = C.c_void_p(stream.cuda_stream)
     lib = capi.lib
 
+    xchg = None
+    if world > 1 and args.collective == "p2p":
+        from svjg.shard import CounterExchange
+
+        def gather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        xchg = CounterExchange(tables.num_sv, rank, world, gather_bytes)
+    step_no = [0]
+
     def step(ev=None):
-        capi.check(lib.svjg_filter_reset(filt.counts.data_ptr(), tables.num_sv, filt.stats.data_ptr(), sp))
+        step_no[0] += 1
+        k = step_no[0]
+        # p2p: this rank's counters live in its exchange region (two buffers, alternating by step)
+        counts_ptr = xchg.counts_ptr(k) if xchg else filt.counts.data_ptr()
+        capi.check(lib.svjg_filter_reset(counts_ptr, tables.num_sv, filt.stats.data_ptr(), sp))
         if ev:
             ev[0].record(stream)
-        capi.check(lib.svjg_filter_device(tables._h, d_gaf.data_ptr(), n_bytes, 0, 100, filt.counts.data_ptr(),
+        capi.check(lib.svjg_filter_device(tables._h, d_gaf.data_ptr(), n_bytes, 0, 100, counts_ptr,
                                           filt.hit_sv2.data_ptr(), filt.hit_off.data_ptr(), filt.hit_len.data_ptr(),
                                           filt.hit_cap, filt.stats.data_ptr(), sp))
         if ev:
             ev[1].record(stream)
-        if world > 1:
+        if world > 1 and not xchg:
             dist.all_reduce(filt.counts)                   # per-SV REF/ALT counters, NCCL sum over NVLink
         if ev:
             ev[2].record(stream)
-        capi.check(lib.svjg_genotype_device(filt.counts.data_ptr(), d_idx.data_ptr(), d_ty.data_ptr(), n_loc, 3, la, lb, lh,
-                                            lut.data_ptr(), genotype.LUT_NMAX, None, d_pl.data_ptr(), d_gt.data_ptr(),
-                                            d_ad.data_ptr(), d_fl.data_ptr(), sp))
+        if xchg:
+            # announces this rank's counters, waits on the device for all ranks, then sums their counters
+            # where they lie (NVLink peer reads): all-reduce and genotype step in one kernel
+            xchg.genotype(k, d_idx.data_ptr(), d_ty.data_ptr(), n_loc, 3, la, lb, lh, lut.data_ptr(), genotype.LUT_NMAX,
+                          d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), sp)
+        else:
+            capi.check(lib.svjg_genotype_device(filt.counts.data_ptr(), d_idx.data_ptr(), d_ty.data_ptr(), n_loc, 3, la, lb, lh,
+                                                lut.data_ptr(), genotype.LUT_NMAX, None, d_pl.data_ptr(), d_gt.data_ptr(),
+                                                d_ad.data_ptr(), d_fl.data_ptr(), sp))
         if ev:
             ev[3].record(stream)
 
@@ -320,6 +343,23 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    if xchg:
+        # untimed self-check of the fused exchange: NCCL all-reduce + plain genotype kernel must give the same
+        capi.check(lib.svjg_filter_reset(filt.counts.data_ptr(), tables.num_sv, filt.stats.data_ptr(), sp))
+        capi.check(lib.svjg_filter_device(tables._h, d_gaf.data_ptr(), n_bytes, 0, 100, filt.counts.data_ptr(),
+                                          filt.hit_sv2.data_ptr(), filt.hit_off.data_ptr(), filt.hit_len.data_ptr(),
+                                          filt.hit_cap, filt.stats.data_ptr(), sp))
+        dist.all_reduce(filt.counts)
+        capi.check(lib.svjg_genotype_device(filt.counts.data_ptr(), d_idx.data_ptr(), d_ty.data_ptr(), n_loc, 3, la, lb, lh,
+                                            lut.data_ptr(), genotype.LUT_NMAX, None, d_pl.data_ptr(), d_gt.data_ptr(),
+                                            d_ad.data_ptr(), d_fl.data_ptr(), sp))
+        want = (d_pl.clone(), d_gt.clone(), d_ad.clone(), d_fl.clone())
+        d_pl.zero_(), d_gt.zero_(), d_ad.zero_(), d_fl.zero_()
+        step()
+        torch.cuda.synchronize(dev)
+        got = (d_pl, d_gt, d_ad, d_fl)
+        if xchg.timed_out() or not all(torch.equal(a, b) for a, b in zip(want, got)):
+            raise SystemExit(f"rank {rank}: fused counter exchange disagrees with NCCL all-reduce + genotype")
     for _ in range(max(3, args.warmup)):
         step()
     sync_all()
@@ -350,6 +390,8 @@ def main():
     else:
         job_rec = n_rec
     st = filt.read_stats()
+    if xchg and xchg.timed_out():
+        raise SystemExit(f"rank {rank}: a wait in the fused counter exchange timed out")
 
     # the dominant kernel on its own (profiling hook of the library: stop the chain after scan_parse)
     def timed_filter(n_iter):
@@ -444,6 +486,8 @@ def main():
                                    "single thread like the reference"},
         "e2e": {"value": job_rec * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke},
+        "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
+                       ("nccl all_reduce" if world > 1 else "none (one GPU)")),
         "gpu_launches": 6 * K,   # reset + probe + scan_parse + link + exact + genotype (plus one memset node per step)
         "clocks": clocks,
     }

@@ -146,6 +146,40 @@ int svjg_genotype_device(const uint32_t *d_counts, const uint32_t *d_sv_index, c
                          const double *d_k_override, int64_t *d_pl, uint8_t *d_gt, uint32_t *d_ad2,
                          uint8_t *d_flags, void *stream);
 
+/* ---- counters of several GPUs (one process per GPU, one node) ----------------
+ * The reference has no analogue (single process).  GAF records shard by read, so every rank
+ * filters its shard into its own counters; predict-genotype.py:219-226 needs their sum.
+ * Instead of an all-reduce followed by the genotype kernel, every rank keeps its counters in an
+ * exchange region that the other ranks map (CUDA IPC over NVLink peer access), and the genotype
+ * kernel of a rank sums, for its SVs only, the counters of all ranks where they lie.
+ *   region = 64 flag words, then two counter buffers [num_sv][2] u32 (steps alternate between
+ *   them, so a rank may start its next step while a peer still reads the previous one)
+ *   svjg_xchg_create   allocates the region of this rank, returns its 64-byte IPC handle
+ *   svjg_xchg_open     maps a peer's region from its handle (exchange the handles out of band,
+ *                      e.g. torch.distributed.all_gather_object); _close unmaps it
+ *   svjg_xchg_counts   counter buffer `parity` of a region: pass it to svjg_filter_reset /
+ *                      svjg_filter_device as d_counts
+ *   svjg_xchg_signal   after the filter of step `epoch` (1, 2, ...): tells every rank, in stream
+ *                      order, that this rank's counters are complete
+ *   svjg_genotype_xchg svjg_genotype_device over the sum of all ranks' counters of buffer
+ *                      `parity`; waits (on the device) for the signals of step `epoch`;
+ *                      signal != 0: the kernel sends this rank's signal itself first (it runs
+ *                      behind the filter on the stream), so svjg_xchg_signal is not needed
+ *   svjg_xchg_timed_out  1 if a wait gave up after ~2 s (a rank died): results are invalid
+ * d_regions[q] is the region of rank q as mapped in THIS process (own region at [rank]). */
+int svjg_xchg_create(uint32_t num_sv, void **d_base, uint8_t *ipc_handle64);
+int svjg_xchg_open(const uint8_t *ipc_handle64, void **d_peer);
+int svjg_xchg_close(void *d_peer);
+int svjg_xchg_free(void *d_base);
+uint32_t *svjg_xchg_counts(void *d_base, uint32_t num_sv, uint32_t parity);
+int svjg_xchg_signal(void *const *d_regions, uint32_t world, uint32_t rank, uint32_t epoch, void *stream);
+int svjg_genotype_xchg(void *const *d_regions, uint32_t world, uint32_t rank, uint32_t num_sv, uint32_t parity,
+                       uint32_t epoch, int signal, const uint32_t *d_sv_index, const uint8_t *d_svtype, uint32_t n,
+                       int64_t min_support, double log10_1me, double log10_e, double log10_half,
+                       const double *d_lut, uint32_t lut_nmax, const double *d_k_override, int64_t *d_pl,
+                       uint8_t *d_gt, uint32_t *d_ad2, uint8_t *d_flags, void *stream);
+int svjg_xchg_timed_out(void *d_base, uint32_t *out);
+
 /* ---- informative_aln.json reader (host) -------------------------------------
  * Replaces predict-genotype.py:67-68 (json.load of <prefix>_informative_aln.json) and
  * :219-226 (nbAln = the lengths of the two lists of a key): the stand-alone

@@ -9,6 +9,8 @@
 // which is what the Decimal path amounts to ("PL exactness").
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "svjg_internal.h"
 
 namespace {
@@ -92,20 +94,64 @@ __device__ int64_t pl_of(const F192 &x) {
     return neg ? int64_t(q) : -int64_t(q);
 }
 
-__global__ void genotype_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ sv_index,
+// Counters of all ranks, read where they lie: every rank's exchange region is mapped into this
+// process (CUDA IPC, NVLink peer access).  The kernel first waits until every rank has signalled
+// that its filter is done for this step, then every thread sums the per-rank counters of its SV --
+// the all-reduce and the genotype step are one kernel, and only the counters that are needed cross
+// the links.
+constexpr int XCHG_MAX = 16;
+constexpr uint32_t XCHG_FLAG_WORDS = 64;           // arrive[rank] ... arrive[63] = time-out marker
+struct Xchg {
+    const uint32_t *counts[XCHG_MAX];              // this step's counter buffer of every rank
+    volatile uint32_t *flags[XCHG_MAX];            // flag words of every rank's region ([rank] = own)
+    uint32_t world, rank, epoch;
+    uint32_t signal;                               // 1: this kernel also announces this rank's counters (svjg_xchg_signal not called)
+};
+
+template <bool XCHG>
+__global__ void genotype_kernel(const uint32_t *__restrict__ counts, const __grid_constant__ Xchg xc,
+                                const uint32_t *__restrict__ sv_index,
                                 const uint8_t *__restrict__ svtype, uint32_t n, int64_t min_support, double la,
                                 double lb, double lh, const double *__restrict__ lut, uint32_t lut_nmax,
                                 const double *__restrict__ k_override, int64_t *__restrict__ pl,
                                 uint8_t *__restrict__ gt, uint32_t *__restrict__ ad2, uint8_t *__restrict__ flags) {
+    if (XCHG) {
+        if (threadIdx.x < xc.world) {
+            // the counters of this rank were written by kernels in front of this one on the stream:
+            // block 0 tells every rank so, then every block waits for the word of every rank
+            if (xc.signal && blockIdx.x == 0) {
+                __threadfence_system();
+                xc.flags[threadIdx.x][xc.rank] = xc.epoch;
+            }
+            volatile uint32_t *mine = xc.flags[xc.rank];
+            const long long t0 = clock64();
+            while (mine[threadIdx.x] < xc.epoch) {
+                if (clock64() - t0 > 4000000000ll) {                      // ~2 s: a rank is gone; say so, do not hang
+                    mine[XCHG_FLAG_WORDS - 1] = 0xDEADu;
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t idx = sv_index[i];
     uint32_t ty = svtype[i];
     uint32_t n0 = 0, n1 = 0;
     if (idx != 0xFFFFFFFFu) {
-        uint2 c = *reinterpret_cast<const uint2 *>(counts + 2 * size_t(idx));
-        n0 = c.x;
-        n1 = c.y;
+        if (XCHG) {
+            for (uint32_t q = 0; q < xc.world; ++q) {
+                const uint2 c = __ldcg(reinterpret_cast<const uint2 *>(xc.counts[q] + 2 * size_t(idx)));
+                n0 += c.x;
+                n1 += c.y;
+            }
+        } else {
+            uint2 c = *reinterpret_cast<const uint2 *>(counts + 2 * size_t(idx));
+            n0 = c.x;
+            n1 = c.y;
+        }
     }
     // predict-genotype.py:216 — a key is "in the dict" once it has at least one hit
     bool gate = (ty & 0x3F) <= 3 && !(ty & 0x80) && ty != 255 && idx != 0xFFFFFFFFu && ((n0 | n1) != 0 || (ty & 0x40));
@@ -191,9 +237,97 @@ extern "C" int svjg_genotype_device(const uint32_t *d_counts, const uint32_t *d_
         return svjg::set_error(SVJG_E_ARG, "svjg_genotype_device: NaN constant");
     int threads = 128;
     int blocks = int((uint64_t(n) + threads - 1) / threads);
-    genotype_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_counts, d_sv_index, d_svtype, n, min_support, log10_1me,
-                                                                  log10_e, log10_half, d_lut, lut_nmax, d_k_override,
-                                                                  d_pl, d_gt, d_ad2, d_flags);
+    genotype_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(d_counts, Xchg{}, d_sv_index, d_svtype, n, min_support,
+                                                                         log10_1me, log10_e, log10_half, d_lut, lut_nmax,
+                                                                         d_k_override, d_pl, d_gt, d_ad2, d_flags);
     SVJG_CUDA(cudaGetLastError());
+    return SVJG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// counter exchange between the ranks of one node (one process per GPU)
+// ---------------------------------------------------------------------------
+namespace {
+size_t xchg_counts_bytes(uint32_t num_sv) { return (size_t(num_sv) * 8 + 255) & ~size_t(255); }
+
+__global__ void xchg_signal_kernel(Xchg x) {
+    // the counters were written by kernels in front of this one on the same stream
+    __threadfence_system();
+    if (threadIdx.x < x.world) x.flags[threadIdx.x][x.rank] = x.epoch;
+}
+}  // namespace
+
+extern "C" int svjg_xchg_create(uint32_t num_sv, void **d_base, uint8_t *ipc_handle64) {
+    if (!d_base || !ipc_handle64) return svjg::set_error(SVJG_E_ARG, "svjg_xchg_create: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    const size_t bytes = XCHG_FLAG_WORDS * 4 + 2 * xchg_counts_bytes(num_sv);
+    void *p = nullptr;
+    SVJG_CUDA(cudaMalloc(&p, bytes));
+    SVJG_CUDA(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    SVJG_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(ipc_handle64, &h, 64);
+    *d_base = p;
+    return SVJG_OK;
+}
+extern "C" int svjg_xchg_open(const uint8_t *ipc_handle64, void **d_peer) {
+    if (!d_peer || !ipc_handle64) return svjg::set_error(SVJG_E_ARG, "svjg_xchg_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    SVJG_CUDA(cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess));
+    return SVJG_OK;
+}
+extern "C" int svjg_xchg_close(void *d_peer) {
+    if (d_peer) SVJG_CUDA(cudaIpcCloseMemHandle(d_peer));
+    return SVJG_OK;
+}
+extern "C" int svjg_xchg_free(void *d_base) {
+    if (d_base) SVJG_CUDA(cudaFree(d_base));
+    return SVJG_OK;
+}
+extern "C" uint32_t *svjg_xchg_counts(void *d_base, uint32_t num_sv, uint32_t parity) {
+    return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(d_base) + XCHG_FLAG_WORDS * 4 + (parity & 1u) * xchg_counts_bytes(num_sv));
+}
+extern "C" int svjg_xchg_signal(void *const *d_regions, uint32_t world, uint32_t rank, uint32_t epoch, void *stream) {
+    if (!d_regions || world == 0 || world > XCHG_MAX || rank >= world) return svjg::set_error(SVJG_E_ARG, "svjg_xchg_signal: bad argument");
+    Xchg x{};
+    x.world = world;
+    x.rank = rank;
+    x.epoch = epoch;
+    for (uint32_t q = 0; q < world; ++q) x.flags[q] = static_cast<volatile uint32_t *>(d_regions[q]);   // flag words come first
+    xchg_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(x);
+    SVJG_CUDA(cudaGetLastError());
+    return SVJG_OK;
+}
+extern "C" int svjg_genotype_xchg(void *const *d_regions, uint32_t world, uint32_t rank, uint32_t num_sv, uint32_t parity,
+                                  uint32_t epoch, int signal, const uint32_t *d_sv_index, const uint8_t *d_svtype, uint32_t n,
+                                  int64_t min_support, double log10_1me, double log10_e, double log10_half,
+                                  const double *d_lut, uint32_t lut_nmax, const double *d_k_override, int64_t *d_pl,
+                                  uint8_t *d_gt, uint32_t *d_ad2, uint8_t *d_flags, void *stream) {
+    if (!d_regions || world == 0 || world > XCHG_MAX || rank >= world) return svjg::set_error(SVJG_E_ARG, "svjg_genotype_xchg: bad argument");
+    if (!d_sv_index || !d_svtype || !d_lut || !d_pl || !d_gt || !d_ad2 || !d_flags)
+        return svjg::set_error(SVJG_E_ARG, "svjg_genotype_xchg: NULL argument");
+    Xchg x{};
+    x.world = world;
+    x.rank = rank;
+    x.epoch = epoch;
+    x.signal = signal ? 1u : 0u;
+    for (uint32_t q = 0; q < world; ++q) {
+        x.counts[q] = svjg_xchg_counts(d_regions[q], num_sv, parity);
+        x.flags[q] = static_cast<volatile uint32_t *>(d_regions[q]);
+    }
+    int threads = 128;
+    int blocks = int((uint64_t(n ? n : 1) + threads - 1) / threads);
+    genotype_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(nullptr, x, d_sv_index, d_svtype, n, min_support, log10_1me,
+                                                                        log10_e, log10_half, d_lut, lut_nmax, d_k_override,
+                                                                        d_pl, d_gt, d_ad2, d_flags);
+    SVJG_CUDA(cudaGetLastError());
+    return SVJG_OK;
+}
+extern "C" int svjg_xchg_timed_out(void *d_base, uint32_t *out) {
+    if (!d_base || !out) return svjg::set_error(SVJG_E_ARG, "svjg_xchg_timed_out: NULL argument");
+    uint32_t v = 0;
+    SVJG_CUDA(cudaMemcpy(&v, static_cast<uint8_t *>(d_base) + (XCHG_FLAG_WORDS - 1) * 4, 4, cudaMemcpyDeviceToHost));
+    *out = v == 0xDEADu;
     return SVJG_OK;
 }

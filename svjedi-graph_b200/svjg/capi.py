@@ -68,6 +68,16 @@ def _load():
                                        C.POINTER(FilterStats)]),
         "svjg_genotype_device": (C.c_int, [u32p, u32p, u8p, C.c_uint32, C.c_int64, C.c_double, C.c_double,
                                            C.c_double, f64p, C.c_uint32, f64p, i64p, u8p, u32p, u8p, vp]),
+        "svjg_xchg_create": (C.c_int, [C.c_uint32, C.POINTER(C.c_void_p), C.c_char_p]),
+        "svjg_xchg_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+        "svjg_xchg_close": (C.c_int, [vp]),
+        "svjg_xchg_free": (C.c_int, [vp]),
+        "svjg_xchg_counts": (C.c_void_p, [vp, C.c_uint32, C.c_uint32]),
+        "svjg_xchg_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, vp]),
+        "svjg_genotype_xchg": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_int, u32p, u8p, C.c_uint32, C.c_int64, C.c_double, C.c_double, C.c_double, f64p,
+                                         C.c_uint32, f64p, i64p, u8p, u32p, u8p, vp]),
+        "svjg_xchg_timed_out": (C.c_int, [vp, C.POINTER(C.c_uint32)]),
         "svjg_aln_counts_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
         "svjg_aln_counts_from_memory": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
         "svjg_aln_counts_free": (None, [vp]),

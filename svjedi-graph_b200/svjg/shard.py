@@ -68,3 +68,56 @@ def gather_hits(hit_sv2, hit_off, hit_len, base_offset, group=None):
     if rank != 0:
         return None
     return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+
+
+class CounterExchange:
+    """Per-SV counters of all ranks of one node, summed where they lie (include/svjg.h, svjg_xchg_*):
+    every rank filters into ``counts_ptr(step)`` and then calls ``genotype(step, ...)``, which
+    announces the rank's counters, waits on the device for the other ranks and reads their counters
+    over NVLink peer access -- no all-reduce.  ``exchange`` is a callable that all-gathers a bytes
+    object across the ranks (e.g. a wrapper of torch.distributed.all_gather_object)."""
+
+    def __init__(self, num_sv, rank, world, exchange):
+        import ctypes as C
+        from . import capi
+        self._C, self._capi = C, capi
+        self.num_sv, self.rank, self.world = int(num_sv), int(rank), int(world)
+        base, handle = C.c_void_p(), C.create_string_buffer(64)
+        capi.check(capi.lib.svjg_xchg_create(self.num_sv, C.byref(base), handle))
+        self._base = base
+        handles = exchange(handle.raw)
+        self._regions = (C.c_void_p * self.world)()
+        for q, h in enumerate(handles):
+            if q == self.rank:
+                self._regions[q] = base.value
+            else:
+                p = C.c_void_p()
+                capi.check(capi.lib.svjg_xchg_open(h, C.byref(p)))
+                self._regions[q] = p.value
+
+    def counts_ptr(self, step):
+        """Device address of this rank's counter buffer for ``step`` (1, 2, ...)."""
+        return self._capi.lib.svjg_xchg_counts(self._base, self.num_sv, step & 1)
+
+    def signal(self, step, stream):
+        self._capi.check(self._capi.lib.svjg_xchg_signal(self._regions, self.world, self.rank, step, stream))
+
+    def genotype(self, step, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax, d_pl, d_gt, d_ad, d_fl, stream,
+                 signal=True):
+        """``signal``: the kernel announces this rank's counters itself (no separate signal() launch)."""
+        self._capi.check(self._capi.lib.svjg_genotype_xchg(self._regions, self.world, self.rank, self.num_sv, step & 1, step,
+                                                           1 if signal else 0, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax, None,
+                                                           d_pl, d_gt, d_ad, d_fl, stream))
+
+    def timed_out(self):
+        v = self._C.c_uint32()
+        self._capi.check(self._capi.lib.svjg_xchg_timed_out(self._base, self._C.byref(v)))
+        return bool(v.value)
+
+    def close(self):
+        if self._base:
+            for q in range(self.world):
+                if q != self.rank and self._regions[q]:
+                    self._capi.lib.svjg_xchg_close(self._regions[q])
+            self._capi.lib.svjg_xchg_free(self._base)
+            self._base = None

@@ -92,3 +92,80 @@ def test_two_rank_gloo_run_equals_single_process(tmp_path, world):
             single.append((index[sv] * 2 + allele, pos, len(line.encode())))
         pos += len(line.encode())
     assert list(zip(h["sv2"].tolist(), h["off"].tolist(), h["ln"].tolist())) == single
+
+
+def _xchg_worker(rank, world, port, tag, out_dir):
+    """One process per rank, both on cuda:0 (CUDA IPC works between processes on one device): filter the
+    rank's shard into the exchange region, then the fused exchange + genotype kernel."""
+    import ctypes as C
+    import math
+
+    import torch
+    import torch.distributed as dist
+    from svjg import alnfilter, capi, genotype
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    gaf = read_golden(f"{tag}.gaf.gz").encode()
+    t = alnfilter.Tables.from_memory(read_golden(f"{tag}_svs_edges.json.gz"), read_golden(f"{tag}.gfa.gz")).to_device(0)
+    cuts = shard.shard_cuts(gaf, world)
+    d_gaf = torch.frombuffer(bytearray(gaf[cuts[rank]:cuts[rank + 1]]), dtype=torch.uint8).cuda()
+
+    def gather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    x = shard.CounterExchange(t.num_sv, rank, world, gather)
+    header, recs = genotype.parse_vcf(read_golden(f"{tag}.vcf.gz").splitlines(True))
+    idx = np.array([capi.NO_SV if (r[2] is None or t.find_sv(r[2]) is None) else t.find_sv(r[2]) for r in recs], dtype=np.uint32)
+    ty = np.array([r[1] for r in recs], dtype=np.uint8)
+    n = len(recs)
+    d_idx, d_ty = torch.from_numpy(idx.view(np.int32)).cuda(), torch.from_numpy(ty).cuda()
+    lut = torch.from_numpy(genotype.log10comb_lut()).cuda()
+    d_pl = torch.zeros((n, 3), dtype=torch.int64, device="cuda")
+    d_gt = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_ad = torch.zeros((n, 2), dtype=torch.int32, device="cuda")
+    d_fl = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    la, lb, lh = math.log10(1 - genotype.ERR), math.log10(genotype.ERR), math.log10(1 / 2)
+    for step in (1, 2, 3):                                   # both counter buffers, and a reuse
+        cp = x.counts_ptr(step)
+        capi.check(capi.lib.svjg_filter_reset(cp, t.num_sv, stats.data_ptr(), sp))
+        capi.check(capi.lib.svjg_filter_device(t._h, d_gaf.data_ptr(), d_gaf.numel(), 0, 100, cp, None, None, None, 0,
+                                               stats.data_ptr(), sp))
+        x.genotype(step, d_idx.data_ptr(), d_ty.data_ptr(), n, 3, la, lb, lh, lut.data_ptr(), genotype.LUT_NMAX,
+                   d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), sp)
+        torch.cuda.synchronize()
+        assert not x.timed_out()
+        np.savez(os.path.join(out_dir, f"geno_{rank}_{step}.npz"), pl=d_pl.cpu().numpy(), gt=d_gt.cpu().numpy(),
+                 ad=d_ad.cpu().numpy(), fl=d_fl.cpu().numpy())
+        dist.barrier()
+    x.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_fused_counter_exchange_two_ranks(tmp_path):
+    """svjg_xchg_* / svjg_genotype_xchg: two ranks sum their counters inside the genotype kernel over
+    mapped peer memory; every rank must get what one process gets from the whole file."""
+    import torch
+    import torch.multiprocessing as mp
+    from svjg import alnfilter, capi, genotype
+    assert torch.cuda.is_available()
+    tag, world = "s3", 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_xchg_worker, args=(world, port, tag, str(tmp_path)), nprocs=world, join=True)
+    t = alnfilter.Tables.from_memory(read_golden(f"{tag}_svs_edges.json.gz"), read_golden(f"{tag}.gfa.gz")).to_device(0)
+    res = alnfilter.filter_host(t, read_golden(f"{tag}.gaf.gz").encode(), want_hits=False)
+    header, recs = genotype.parse_vcf(read_golden(f"{tag}.vcf.gz").splitlines(True))
+    idx = np.array([capi.NO_SV if (r[2] is None or t.find_sv(r[2]) is None) else t.find_sv(r[2]) for r in recs], dtype=np.uint32)
+    ty = np.array([r[1] for r in recs], dtype=np.uint8)
+    gt, fl, ad, pl = genotype.genotype_device(torch.from_numpy(res.counts.view(np.int32)).cuda(), idx, ty)
+    for r in range(world):
+        for step in (1, 2, 3):
+            z = np.load(tmp_path / f"geno_{r}_{step}.npz")
+            assert (z["pl"] == pl).all() and (z["gt"] == gt).all() and (z["ad"].view(np.uint32) == ad).all() and (z["fl"] == fl).all()
