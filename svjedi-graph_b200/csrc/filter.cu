@@ -1435,6 +1435,7 @@ constexpr int PROBE_THREADS = 1024, PROBE_BYTES = 64 << 10;
 __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const __grid_constant__ FilterArgs a) {
     __shared__ uint32_t total;
     if (threadIdx.x == 0) total = 0;
+    if (threadIdx.x < 16 && threadIdx.x != 4) a.sc.cnt[threadIdx.x] = 0;      // the lists' cursors
     __syncthreads();
     const uint64_t span = a.n < uint64_t(PROBE_BYTES) ? a.n : uint64_t(PROBE_BYTES);
     const uint32_t n16 = uint32_t(span / 16);
@@ -1455,6 +1456,15 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const __grid_const
             tile = uint32_t(want < uint64_t(TILE_MAX) ? want : uint64_t(TILE_MAX)) & ~31u;
         }
         if (const uint32_t forced = (a.flags >> 16)) tile = forced & ~31u;    // test hook (SVJG_TILE_BYTES)
+        if (total) {
+            // phase A scans 1 KiB a step and stops behind the tile once a line end is found: let a step
+            // end about 1.5 lines behind the tile, so that step is rarely followed by one more
+            const uint64_t s15 = uint64_t(n16) * 24ull / total;                 // 1.5 lines
+            const uint32_t slack = uint32_t(s15 < 512 ? s15 : 512);
+            tile = min(tile, uint32_t(TILE_MAX) & ~31u);
+            const uint32_t steps = (HEAD + tile + slack) / 1024u;
+            if (steps >= 2) tile = (steps * 1024u - HEAD - slack) & ~31u;
+        }
         a.sc.cnt[4] = max(uint32_t(TILE_MIN), min(tile, uint32_t(TILE_MAX) & ~31u));
     }
 }
@@ -1559,7 +1569,6 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
     sc.slab = reinterpret_cast<uint4 *>(ws + o_slab);
     sc.pool = reinterpret_cast<uint4 *>(ws + o_pool);
-    SVJG_CUDA(cudaMemsetAsync(sc.cnt, 0, 64, st));
 
     if (const char *tb = getenv("SVJG_TILE_BYTES")) a.flags |= uint32_t(std::min(65535, std::max(0, atoi(tb)))) << 16;
     const uint32_t max_tiles = uint32_t((n_bytes + TILE_MIN - 1) / TILE_MIN);
@@ -1569,7 +1578,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     scan_parse_kernel<<<scan_grid, THREADS, SMEM_BYTES, st>>>(a);
     if (stop == 0) {
         link_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
-        exact_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
+        exact_kernel<<<g_sms * 2, FLAT_THREADS, 0, st>>>(a);     // a few lines as a rule: a small grid starts faster
     }
     cudaError_t le = cudaGetLastError();
     cudaError_t fe = cudaFreeAsync(ws, st);
