@@ -1208,17 +1208,18 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                 // value (the first-occurrence rules :206 and :269-271 would bite: exact route), verdicts
                 const uint32_t lfirst = uint32_t(lane) - idx;
                 const uint32_t lcnt = __shfl_sync(0xFFFFFFFFu, pend, own);
-                const uint32_t maxidx = __reduce_max_sync(0xFFFFFFFFu, idx);
-                uint64_t pre = 0;
-                bool clash = false;
-                for (uint32_t d = 1; d <= maxidx; ++d) {
-                    const uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, akey, d);
-                    const uint32_t pl = __shfl_up_sync(0xFFFFFFFFu, nlen, d);
-                    if (d <= idx) {
-                        clash |= pa == akey;
-                        pre += pl;
-                    }
+                // a repeated start value: some other lane of the line holds the same key (one MATCH)
+                const uint32_t line_lanes = low_bits(int(lcnt)) << lfirst;
+                const bool clash = (__match_any_sync(0xFFFFFFFFu, akey) & line_lanes & ~(1u << lane)) != 0;
+                // segmented inclusive scan of the lengths: a lane adds what lies `d` to its left while
+                // that is still its own line
+                uint64_t lsum = nlen;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, lsum, d);
+                    if (uint32_t(d) <= idx) lsum += o;
                 }
+                const uint64_t pre = lsum - nlen;
                 const uint32_t bad = __reduce_or_sync(0xFFFFFFFFu, (is_tok && (!plain || clash)) ? (1u << own) : 0u);
                 const uint64_t total = __shfl_sync(0xFFFFFFFFu, pre + nlen, is_tok ? lfirst + lcnt - 1u : 0u);
                 const uint32_t idl = __shfl_up_sync(0xFFFFFFFFu, nid, 1), sl = __shfl_up_sync(0xFFFFFFFFu, plus, 1);
