@@ -803,23 +803,27 @@ template <bool LONG>
 __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t *dlb, const DevTables &tb, uint32_t lps,
                                              uint32_t lpe, uint32_t idx) {
     Node n;
-    // node starts: a non-delimiter byte right behind a delimiter; take the idx-th
-    uint32_t q = lps, rem = idx, carry = 0, st;
+    // node starts: a non-delimiter byte right behind a delimiter; take the idx-th.  Aligned words of
+    // the delimiter bitmap: the bits in front of the path are masked in the first word (the byte in
+    // front of the path is a tab, so no carry comes in)
+    uint32_t w = lps >> 5, rem = idx, carry = 0, st;
+    uint32_t keep = ~low_bits(int(lps & 31u));
     for (;;) {
-        if (LONG && q >= lpe) {       // no such node (only behind a name too long to be plain): not plain
+        if (LONG && w * 32u >= lpe) {  // no such node (only behind a name too long to be plain): not plain
             n.end = lpe;
             return n;
         }
-        const uint32_t d = bm_bits(dlb, q);
-        st = ((d << 1) | carry) & ~d & low_bits(int(lpe - q));
+        const uint32_t d = dlb[w];
+        st = ((d << 1) | carry) & ~d & keep & low_bits(int(lpe) - int(w * 32u));
         const uint32_t c = __popc(st);
         if (rem < c) break;
         rem -= c;
         carry = d >> 31;
-        q += 32;
+        keep = 0xFFFFFFFFu;
+        ++w;
     }
     for (; rem; --rem) st &= st - 1;
-    const uint32_t tpos = q + uint32_t(__ffs(st) - 1);
+    const uint32_t tpos = w * 32u + uint32_t(__ffs(st) - 1);
     // its end: the next delimiter or the end of the path (a plain name has at most 36 bytes)
     const uint32_t d0 = bm_bits(dlb, tpos) & low_bits(int(lpe - tpos));
     uint32_t tlen;
