@@ -146,6 +146,22 @@ int svjg_genotype_device(const uint32_t *d_counts, const uint32_t *d_sv_index, c
                          const double *d_k_override, int64_t *d_pl, uint8_t *d_gt, uint32_t *d_ad2,
                          uint8_t *d_flags, void *stream);
 
+/* The same from HOST arrays (counts [num_counts][2]); device buffers are the call's own.  Synchronous. */
+int svjg_genotype_host(const uint32_t *counts, uint32_t num_counts, const uint32_t *sv_index, const uint8_t *svtype,
+                       uint32_t n, int64_t min_support, double log10_1me, double log10_e, double log10_half,
+                       const double *lut, uint32_t lut_nmax, const double *k_override, int64_t *pl, uint8_t *gt,
+                       uint32_t *ad2, uint8_t *flags);
+
+/* Page-locked host memory (cudaHostAlloc) for file buffers and results: copies to and from it run
+ * at PCIe speed.  For callers that do not want a tensor library just to pin memory. */
+int svjg_host_alloc(uint64_t bytes, void **out);
+int svjg_host_free(void *p);
+/* page-lock / release memory the caller owns; create the CUDA context of a device (about a second:
+ * a front-end calls it from a thread while it reads its input files) */
+int svjg_host_register(void *p, uint64_t bytes);
+int svjg_host_unregister(void *p);
+int svjg_device_init(int device);
+
 /* ---- counters of several GPUs (one process per GPU, one node) ----------------
  * The reference has no analogue (single process).  GAF records shard by read, so every rank
  * filters its shard into its own counters; predict-genotype.py:219-226 needs their sum.

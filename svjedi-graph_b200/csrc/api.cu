@@ -6,7 +6,9 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "svjg_internal.h"
 
@@ -67,6 +69,33 @@ using namespace svjg;
 
 extern "C" const char *svjg_version(void) { return "svjg-b200 0.1.0 (sm_100a)"; }
 extern "C" const char *svjg_last_error(void) { return g_err.c_str(); }
+
+// page-locked host memory without a tensor library (file buffers of the command-line front-ends)
+extern "C" int svjg_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return set_error(SVJG_E_ARG, "svjg_host_alloc: NULL argument");
+    SVJG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SVJG_OK;
+}
+extern "C" int svjg_host_free(void *p) {
+    if (p) SVJG_CUDA(cudaFreeHost(p));
+    return SVJG_OK;
+}
+// page-lock / release memory the caller already owns (e.g. a file read while the context was created)
+extern "C" int svjg_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return SVJG_OK;
+    SVJG_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return SVJG_OK;
+}
+extern "C" int svjg_host_unregister(void *p) {
+    if (p) SVJG_CUDA(cudaHostUnregister(p));
+    return SVJG_OK;
+}
+// creates the CUDA context of `device` (about a second): call it from a thread while the host reads files
+extern "C" int svjg_device_init(int device) {
+    SVJG_CUDA(cudaSetDevice(device));
+    SVJG_CUDA(cudaFree(nullptr));
+    return SVJG_OK;
+}
 
 extern "C" int svjg_tables_to_device(svjg_tables *t, int device) {
     if (!t) return set_error(SVJG_E_ARG, "svjg_tables_to_device: NULL tables");
@@ -236,17 +265,18 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
 // ---------------------------------------------------------------------------
 namespace {
 
-struct Out {
+struct Out {                      // f == nullptr: everything stays in buf (a worker's share of the text)
     FILE *f;
     std::vector<char> buf;
     bool ok = true;
     explicit Out(FILE *fp) : f(fp) { buf.reserve(1 << 22); }
     void flush() {
+        if (!f) return;
         if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) ok = false;
         buf.clear();
     }
     void put(const char *s, size_t n) {
-        if (buf.size() + n > (1u << 22)) flush();
+        if (f && buf.size() + n > (1u << 22)) flush();
         buf.insert(buf.end(), s, s + n);
     }
     void put(const char *s) { put(s, strlen(s)); }
@@ -344,39 +374,91 @@ extern "C" int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *g
 
     FILE *f = fopen(out_path, "wb");
     if (!f) return set_error(SVJG_E_IO, std::string("cannot write ") + out_path);
-    Out o(f);
-    bool any = false, utf8_ok = true;
-    for (uint64_t sv = 0; sv < n2 / 2 && utf8_ok; ++sv) {
-        if (start[2 * sv] == start[2 * sv + 2]) continue;   // a key exists only once something was appended (:163)
-        o.put(any ? ",\n    " : "{\n    ");
-        any = true;
-        const std::string &id = t->sv_ids[sv];
-        utf8_ok &= put_json_string(o, reinterpret_cast<const uint8_t *>(id.data()), id.size());
-        o.put(": [\n        ");
-        for (int al = 0; al < 2 && utf8_ok; ++al) {
-            uint64_t b = start[2 * sv + al], e = start[2 * sv + al + 1];
-            if (b == e) {
-                o.put("[]");
-            } else {
-                o.put("[\n            ");
-                for (uint64_t k = b; k < e && utf8_ok; ++k) {
-                    uint64_t i = order[k];
-                    const uint8_t *line = gaf + hit_off[i];
-                    size_t len = hit_len[i];
-                    const void *cgz = memmem(line, len, "cg:Z:", 5);      // line.split("cg:Z:")[0]  (:166)
-                    if (cgz) len = size_t(static_cast<const uint8_t *>(cgz) - line);
-                    if (k != b) o.put(",\n            ");
-                    utf8_ok &= put_json_string(o, line, len);
+    // The text of a key does not depend on the others: keys are rendered by several threads, a batch
+    // (about 256 MB of lines) at a time, every thread a run of keys with about the same number of
+    // bytes, and written in key order.  Every key starts with ",\n    "; the first one of the file has
+    // its comma turned into the opening brace (same length).
+    auto render = [&](uint64_t sv_lo, uint64_t sv_hi, Out &o, bool &utf8_ok) {
+        for (uint64_t sv = sv_lo; sv < sv_hi && utf8_ok; ++sv) {
+            if (start[2 * sv] == start[2 * sv + 2]) continue;   // a key exists only once something was appended (:163)
+            o.put(",\n    ");
+            const std::string &id = t->sv_ids[sv];
+            utf8_ok &= put_json_string(o, reinterpret_cast<const uint8_t *>(id.data()), id.size());
+            o.put(": [\n        ");
+            for (int al = 0; al < 2 && utf8_ok; ++al) {
+                uint64_t b = start[2 * sv + al], e = start[2 * sv + al + 1];
+                if (b == e) {
+                    o.put("[]");
+                } else {
+                    o.put("[\n            ");
+                    for (uint64_t k = b; k < e && utf8_ok; ++k) {
+                        uint64_t i = order[k];
+                        const uint8_t *line = gaf + hit_off[i];
+                        size_t len = hit_len[i];
+                        const void *cgz = memmem(line, len, "cg:Z:", 5);      // line.split("cg:Z:")[0]  (:166)
+                        if (cgz) len = size_t(static_cast<const uint8_t *>(cgz) - line);
+                        if (k != b) o.put(",\n            ");
+                        utf8_ok &= put_json_string(o, line, len);
+                    }
+                    o.put("\n        ]");
                 }
-                o.put("\n        ]");
+                if (al == 0) o.put(",\n        ");
             }
-            if (al == 0) o.put(",\n        ");
+            o.put("\n    ]");
         }
-        o.put("\n    ]");
+    };
+    const uint64_t n_sv = n2 / 2;
+    std::vector<uint64_t> weight(n_sv + 1, 0);                  // bytes of lines up to key sv (prefix sums)
+    for (uint64_t sv = 0; sv < n_sv; ++sv) {
+        uint64_t w = 0;
+        for (uint64_t k = start[2 * sv]; k < start[2 * sv + 2]; ++k) w += hit_len[order[k]] + 16;
+        weight[sv + 1] = weight[sv] + w;
     }
-    o.put(any ? "\n}" : "{}");
-    o.flush();
-    bool ok = o.ok && fclose(f) == 0;
+    unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (weight[n_sv] < (8u << 20)) n_thr = 1;
+    uint64_t batch_bytes = 256ull << 20;
+    if (const char *e = getenv("SVJG_JSON_THREADS")) n_thr = unsigned(std::max(1, std::min(64, atoi(e))));   // test hooks
+    if (const char *e = getenv("SVJG_JSON_BATCH")) batch_bytes = uint64_t(std::max(1, atoi(e)));
+    bool any = false, utf8_ok = true, io_ok = true;
+    for (uint64_t lo = 0; lo < n_sv && utf8_ok && io_ok;) {
+        uint64_t hi = std::upper_bound(weight.begin() + lo, weight.end(), weight[lo] + batch_bytes) - weight.begin();
+        hi = std::min<uint64_t>(std::max<uint64_t>(hi, lo + 1), n_sv);
+        std::vector<uint64_t> cutv(n_thr + 1, lo);
+        for (unsigned p = 1; p < n_thr; ++p) {
+            const uint64_t target = weight[lo] + (weight[hi] - weight[lo]) * p / n_thr;
+            cutv[p] = std::min<uint64_t>(hi, std::lower_bound(weight.begin() + lo, weight.begin() + hi, target) - weight.begin());
+        }
+        cutv[n_thr] = hi;
+        for (unsigned p = 1; p <= n_thr; ++p) cutv[p] = std::max(cutv[p], cutv[p - 1]);
+        std::vector<Out> outs;
+        outs.reserve(n_thr);
+        for (unsigned p = 0; p < n_thr; ++p) outs.emplace_back(nullptr);
+        std::vector<char> okv(n_thr, 1);
+        std::vector<std::thread> pool;
+        for (unsigned p = 1; p < n_thr; ++p)
+            pool.emplace_back([&, p]() {
+                bool u = true;
+                render(cutv[p], cutv[p + 1], outs[p], u);
+                okv[p] = u;
+            });
+        {
+            bool u = true;
+            render(cutv[0], cutv[1], outs[0], u);
+            okv[0] = u;
+        }
+        for (auto &th : pool) th.join();
+        for (unsigned p = 0; p < n_thr && io_ok; ++p) {
+            utf8_ok &= okv[p] != 0;
+            std::vector<char> &b = outs[p].buf;
+            if (b.empty()) continue;
+            if (!any) b[0] = '{';
+            any = true;
+            io_ok = fwrite(b.data(), 1, b.size(), f) == b.size();
+        }
+        lo = hi;
+    }
+    if (io_ok) io_ok = fputs(any ? "\n}" : "{}", f) >= 0;
+    bool ok = fclose(f) == 0 && io_ok;
     if (!utf8_ok) return set_error(SVJG_E_INPUT, "GAF text is not valid UTF-8 (the reference cannot read it)");
     if (!ok) return set_error(SVJG_E_IO, std::string("write failed: ") + out_path);
     return SVJG_OK;

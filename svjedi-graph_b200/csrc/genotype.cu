@@ -9,6 +9,7 @@
 // which is what the Decimal path amounts to ("PL exactness").
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "svjg_internal.h"
@@ -242,6 +243,52 @@ extern "C" int svjg_genotype_device(const uint32_t *d_counts, const uint32_t *d_
                                                                          d_k_override, d_pl, d_gt, d_ad2, d_flags);
     SVJG_CUDA(cudaGetLastError());
     return SVJG_OK;
+}
+
+// Same from host arrays: device buffers are this call's own (the stand-alone predict-genotype
+// front-end needs nothing else from the GPU, so it does not have to load a tensor library).
+extern "C" int svjg_genotype_host(const uint32_t *counts, uint32_t num_counts, const uint32_t *sv_index, const uint8_t *svtype,
+                                  uint32_t n, int64_t min_support, double log10_1me, double log10_e, double log10_half,
+                                  const double *lut, uint32_t lut_nmax, const double *k_override, int64_t *pl, uint8_t *gt,
+                                  uint32_t *ad2, uint8_t *flags) {
+    if (n == 0) return SVJG_OK;
+    if (!sv_index || !svtype || !lut || !pl || !gt || !ad2 || !flags || (num_counts && !counts))
+        return svjg::set_error(SVJG_E_ARG, "svjg_genotype_host: NULL argument");
+    const size_t n_lut = size_t(lut_nmax + 1) * (lut_nmax + 2) / 2;
+    const size_t b_cnt = std::max<size_t>(8, size_t(num_counts) * 8), b_idx = size_t(n) * 4, b_ty = n, b_lut = n_lut * 8,
+                 b_k = k_override ? size_t(n) * 8 : 0, b_pl = size_t(n) * 24, b_gt = n, b_ad = size_t(n) * 8, b_fl = n;
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_idx = up(b_cnt), o_ty = o_idx + up(b_idx), o_lut = o_ty + up(b_ty), o_k = o_lut + up(b_lut),
+                 o_pl = o_k + up(b_k), o_gt = o_pl + up(b_pl), o_ad = o_gt + up(b_gt), o_fl = o_ad + up(b_ad),
+                 total = o_fl + up(b_fl);
+    uint8_t *d = nullptr;
+    SVJG_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), total));
+    int rc = SVJG_OK;
+    cudaError_t e = cudaSuccess;
+    auto h2d = [&](size_t off, const void *src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(d + off, src, bytes, cudaMemcpyHostToDevice);
+    };
+    if (num_counts) h2d(0, counts, size_t(num_counts) * 8);
+    h2d(o_idx, sv_index, b_idx);
+    h2d(o_ty, svtype, b_ty);
+    h2d(o_lut, lut, b_lut);
+    h2d(o_k, k_override, b_k);
+    if (e == cudaSuccess)
+        rc = svjg_genotype_device(reinterpret_cast<const uint32_t *>(d), reinterpret_cast<const uint32_t *>(d + o_idx), d + o_ty, n,
+                                  min_support, log10_1me, log10_e, log10_half, reinterpret_cast<const double *>(d + o_lut),
+                                  lut_nmax, k_override ? reinterpret_cast<const double *>(d + o_k) : nullptr,
+                                  reinterpret_cast<int64_t *>(d + o_pl), d + o_gt, reinterpret_cast<uint32_t *>(d + o_ad),
+                                  d + o_fl, nullptr);
+    auto d2h = [&](void *dst, size_t off, size_t bytes) {
+        if (e == cudaSuccess && rc == SVJG_OK) e = cudaMemcpy(dst, d + off, bytes, cudaMemcpyDeviceToHost);
+    };
+    d2h(pl, o_pl, b_pl);
+    d2h(gt, o_gt, b_gt);
+    d2h(ad2, o_ad, b_ad);
+    d2h(flags, o_fl, b_fl);
+    cudaFree(d);
+    if (e != cudaSuccess) return svjg::cuda_fail(int(e), "svjg_genotype_host");
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

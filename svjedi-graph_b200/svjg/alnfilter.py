@@ -98,7 +98,9 @@ class FilterResult:
 
 def _as_u8(buf):
     """numpy uint8 view (no copy) of bytes / bytearray / memoryview / ndarray / pinned torch tensor."""
-    if isinstance(buf, np.ndarray):
+    if isinstance(buf, (PinnedBytes, RegisteredBytes)):
+        a = buf.array
+    elif isinstance(buf, np.ndarray):
         a = buf
     elif hasattr(buf, "numpy") and hasattr(buf, "is_pinned"):
         a = buf.numpy()
@@ -242,17 +244,53 @@ def write_informative_json(tables, gaf, result, out_path):
         off.ctypes.data if nh else None, ln.ctypes.data if nh else None, nh, os.fsencode(out_path)))
 
 
+class PinnedBytes:
+    """Page-locked host bytes from libsvjg (cudaHostAlloc) -- no tensor library needed.  ``.array`` is the
+    numpy uint8 view; the memory is released with the object."""
+
+    def __init__(self, n):
+        self._p = C.c_void_p()
+        capi.check(capi.lib.svjg_host_alloc(max(int(n), 1), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(int(n), 1),))[:int(n)]
+
+    def __del__(self):
+        try:
+            if self._p:
+                capi.lib.svjg_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+class RegisteredBytes:
+    """A numpy uint8 array page-locked in place (cudaHostRegister) for the lifetime of the object."""
+
+    def __init__(self, array):
+        self.array = array
+        self._reg = False
+        if array.size:
+            capi.check(capi.lib.svjg_host_register(array.ctypes.data, array.size))
+            self._reg = True
+
+    def __del__(self):
+        try:
+            if self._reg:
+                capi.lib.svjg_host_unregister(self.array.ctypes.data)
+                self._reg = False
+        except Exception:
+            pass
+
+
 def read_file_pinned(path):
-    """Whole file into page-locked host memory (torch pinned uint8 tensor)."""
-    import torch
+    """Whole file into page-locked host memory; returns a PinnedBytes (pass ``.array`` on)."""
     n = os.path.getsize(path)
-    t = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    buf = PinnedBytes(n)
     with open(path, "rb", buffering=0) as fh:
-        view = memoryview(t.numpy())[:n]
+        view = memoryview(buf.array)
         got = 0
         while got < n:
             k = fh.readinto(view[got:])
             if not k:
                 break
             got += k
-    return t[:n]
+    return buf

@@ -14,19 +14,42 @@ def _die(msg):
     sys.exit(1)
 
 
-def _load_tables(prefix, gfa_file):
+def _start_device():
+    """The CUDA context takes about a second to create: do it on a thread while the files are read."""
+    import threading
+    from . import capi
+    box = {}
+
+    def run():
+        box["rc"] = capi.lib.svjg_device_init(0)
+        box["msg"] = capi.lib.svjg_last_error().decode("utf-8", "replace") if box["rc"] else ""
+    th = threading.Thread(target=run, daemon=True)
+    th.start()
+
+    def wait():
+        th.join()
+        if box.get("rc"):
+            raise capi.SvjgError(box["rc"], box["msg"])
+    return wait
+
+
+def _load_tables(prefix, gfa_file, device_ready=None):
     from . import alnfilter
-    return alnfilter.Tables.load(prefix + "_svs_edges.json", gfa_file).to_device(0)
+    t = alnfilter.Tables.load(prefix + "_svs_edges.json", gfa_file)      # host work: JSON + GFA parse, table build
+    if device_ready:
+        device_ready()
+    return t.to_device(0)
 
 
-def _filter_to_json(tables, gaf_file, out_json, dover_given=False):
-    """filter-alignments.py:119-175.  Returns (FilterResult, pinned GAF tensor)."""
+def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None):
+    """filter-alignments.py:119-175.  Returns (FilterResult, page-locked GAF bytes)."""
     from . import alnfilter, capi
     if dover_given:
         # -O leaves a list in d_over and `int >= list` raises at the first overlap test (:269);
         # count every test the reference would make
         tables.set_flags(capi.FLAG_EXACT_CHECKS)
-    gaf = alnfilter.read_file_pinned(gaf_file)
+    if gaf is None:
+        gaf = alnfilter.read_file_pinned(gaf_file)
     res = alnfilter.filter_host(tables, gaf)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
@@ -50,9 +73,13 @@ def filter_main(argv=None):
     if args.outputDir:
         out_json = "/".join([args.outputDir, out_json])
     from . import alnfilter, capi
+    import numpy as np
     try:
-        tables = _load_tables(args.prefix, args.gfa[0])
-        _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100)
+        ready = _start_device()
+        raw = np.fromfile(args.gaf[0], dtype=np.uint8)                     # read while the context comes up
+        tables = _load_tables(args.prefix, args.gfa[0], ready)
+        gaf = alnfilter.RegisteredBytes(raw)                                # page-lock in place
+        _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, gaf=gaf)
     except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
         _die(str(exc))
     return 0
@@ -71,7 +98,9 @@ def genotype_main(argv=None):
     e = args.err[0] if args.err is not None else 0.00005
     from . import capi, genotype
     try:
+        ready = _start_device()
         counts = genotype.AlnCounts.load(args.aln[0])
+        ready()
         with open(args.vcf) as fh:
             lines = fh.readlines()
         with open(output, "w") as out:          # the reference opens the output before it reads the VCF (:92)
@@ -86,7 +115,7 @@ def genotype_main(argv=None):
 def pipeline_main(svjg_dir, argv=None):
     """svjedi-graph.py: graph construction and mapping are external tools exactly as in the
     reference (:85-108); filtering and genotyping run fused in this process — the counters
-    never leave the GPU between the two stages — and still write both output files."""
+    go from one stage to the next in memory, no JSON is read back — and still write both output files."""
     ap = argparse.ArgumentParser()
     ap.add_argument("-v", "--vcf", type=str, help="SV set in vcf format", required=True)
     ap.add_argument("-r", "--ref", type=str, help="Reference genome in fasta format", required=True)
@@ -114,8 +143,6 @@ def pipeline_main(svjg_dir, argv=None):
 
     print("Filtering alignment file...")
     from . import alnfilter, capi, genotype
-    import numpy as np
-    import torch
     try:
         tables = _load_tables(args.prefix, out_gfa)
         res, _gaf = _filter_to_json(tables, out_gaf, args.prefix + "_informative_aln.json")
@@ -127,9 +154,8 @@ def pipeline_main(svjg_dir, argv=None):
     try:
         with open(args.vcf) as fh:
             lines = fh.readlines()
-        d_counts = torch.from_numpy(res.counts.view(np.int32)).cuda()
         with open(args.prefix + "_genotype.vcf", "w") as out:
-            text, n = genotype.genotype_vcf(tables, d_counts, lines, args.minsupport)
+            text, n = genotype.genotype_vcf(tables, res.counts, lines, args.minsupport)
             out.write(text)
     except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
         sys.stderr.write(f"svjg: {exc}\n")

@@ -124,6 +124,56 @@ def _num(twice, halved):
     return f"{twice >> 1}.5" if twice & 1 else f"{twice >> 1}.0"
 
 
+def _k_overrides(flags, ad, n):
+    """log10 C(n,k) from CPython for exactly the SVs whose counts are beyond the table."""
+    need = np.nonzero(flags & capi.GT_NEED_K)[0]
+    if not need.size:
+        return None
+    kov = np.full(n, np.nan)
+    memo = {}
+    for i in need:
+        t1, t2 = int(ad[i, 0]), int(ad[i, 1])
+        r1 = (t1 >> 1) + ((t1 >> 1) & 1 if t1 & 1 else 0)
+        r2 = (t2 >> 1) + ((t2 >> 1) & 1 if t2 & 1 else 0)
+        v = memo.get((r1, r2))
+        if v is None:
+            v = memo[(r1, r2)] = math.log10(math.comb(r1 + r2, r1))
+        kov[i] = v
+    return kov
+
+
+def genotype_host(counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR):
+    """Kernel 4 from host arrays (svjg_genotype_host): ``counts`` numpy uint32 [num, 2].  Returns
+    numpy (gt, flags, ad2, pl).  Needs no tensor library -- the path of the command-line front-ends."""
+    n = int(len(sv_index))
+    if not 0 < e < 1:
+        raise VcfError("error rate must be in (0, 1)")      # math.log10 raises in the reference
+    la, lb, lh = math.log10(1 - e), math.log10(e), math.log10(1 / 2)
+    lut = log10comb_lut()
+    counts = np.ascontiguousarray(counts, dtype=np.uint32).reshape(-1, 2)
+    idx = np.ascontiguousarray(sv_index, dtype=np.uint32)
+    ty = np.ascontiguousarray(svtype, dtype=np.uint8)
+    pl = np.zeros((max(n, 1), 3), np.int64)
+    gt = np.zeros(max(n, 1), np.uint8)
+    ad = np.zeros((max(n, 1), 2), np.uint32)
+    fl = np.zeros(max(n, 1), np.uint8)
+
+    def launch(kov):
+        capi.check(capi.lib.svjg_genotype_host(
+            counts.ctypes.data if counts.size else None, counts.shape[0], idx.ctypes.data, ty.ctypes.data, n, int(min_support),
+            la, lb, lh, lut.ctypes.data, LUT_NMAX, kov.ctypes.data if kov is not None else None,
+            pl.ctypes.data, gt.ctypes.data, ad.ctypes.data, fl.ctypes.data))
+
+    if n:
+        launch(None)
+        kov = _k_overrides(fl[:n], ad[:n], n)
+        if kov is not None:
+            launch(kov)
+            if (fl[:n] & capi.GT_NEED_K).any():
+                raise RuntimeError("genotype kernel could not represent a likelihood exactly")
+    return gt[:n], fl[:n], ad[:n], pl[:n]
+
+
 def genotype_device(d_counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR, device=None):
     """Runs kernel 4 for len(sv_index) SVs; returns numpy (gt, flags, ad2, pl).
     ``d_counts``: torch int32 [num_sv, 2] on the device (the filter's counters)."""
@@ -197,14 +247,18 @@ def format_vcf(header, recs, gt, flags, ad2, pl):
 
 
 def genotype_vcf(tables, d_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR):
-    """decision_vcf (predict-genotype.py:89-279) with the counters already on
-    the device.  Returns (vcf text, number of genotyped SVs)."""
+    """decision_vcf (predict-genotype.py:89-279).  ``d_counts``: the filter's counters, a torch int32
+    tensor on the device or a numpy uint32 array on the host.  Returns (vcf text, number of
+    genotyped SVs)."""
     header, recs = parse_vcf(vcf_lines)
     idx = np.fromiter((capi.NO_SV if r[2] is None else (lambda j: capi.NO_SV if j is None else j)(tables.find_sv(r[2]))
                        for r in recs), dtype=np.uint32, count=len(recs))
     ty = np.fromiter((r[1] for r in recs), dtype=np.uint8, count=len(recs))
     if len(recs):
-        gt, flags, ad2, pl = genotype_device(d_counts, idx, ty, min_support, e)
+        if isinstance(d_counts, np.ndarray):                      # counters on the host: no tensor library needed
+            gt, flags, ad2, pl = genotype_host(d_counts, idx, ty, min_support, e)
+        else:
+            gt, flags, ad2, pl = genotype_device(d_counts, idx, ty, min_support, e)
     else:
         gt = flags = np.zeros(0, np.uint8)
         ad2 = np.zeros((0, 2), np.uint32)
@@ -267,7 +321,6 @@ def genotype_vcf_from_json(aln_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR
     """decision_vcf (predict-genotype.py:89-279) with the counters taken from an
     informative_aln.json, as the stand-alone reference stage does.  A key that is
     present gates the SV in even when both of its lists are empty (:216)."""
-    import torch
     header, recs = parse_vcf(vcf_lines)
     n = len(recs)
     idx = np.full(n, capi.NO_SV, dtype=np.uint32)
@@ -285,10 +338,8 @@ def genotype_vcf_from_json(aln_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR
         if ty[i] != 255:
             ty[i] |= 0x40
     if n:
-        dev = torch.device("cuda", device)
-        d_counts = torch.from_numpy(np.ascontiguousarray(aln_counts.counts).view(np.int32).reshape(-1, 2).copy()).to(dev) \
-            if aln_counts.num else torch.zeros((1, 2), dtype=torch.int32, device=dev)
-        gt, flags, ad2, pl = genotype_device(d_counts, idx, ty, min_support, e)
+        gt, flags, ad2, pl = genotype_host(aln_counts.counts if aln_counts.num else np.zeros((1, 2), np.uint32), idx, ty,
+                                           min_support, e)
     else:
         gt = flags = np.zeros(0, np.uint8)
         ad2 = np.zeros((0, 2), np.uint32)

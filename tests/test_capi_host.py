@@ -73,6 +73,25 @@ def test_json_emitter_byte_equal_c1(tmp_path):
     assert out.read_text() == read_golden("c1_informative_aln.json.gz")
 
 
+@pytest.mark.parametrize("threads,batch", [(1, 1 << 30), (5, 1 << 30), (3, 40_000), (16, 1)])
+def test_json_emitter_threads_and_batches(tmp_path, monkeypatch, threads, batch):
+    """The keys are rendered by several threads, a batch at a time: any split must give the same bytes."""
+    edges_text = read_golden("c1_svs_edges.json")
+    gfa_text = read_golden("c1.gfa.gz")
+    gaf = read_golden("c1.gaf.gz")
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text)
+    sv2, off, ln = _oracle_hits(gaf.splitlines(True), json.loads(edges_text), alt_len_from_gfa_text(gfa_text), t.sv_ids)
+    res = alnfilter.FilterResult(None, {"n_hits": len(sv2)}, sv2, off, ln)
+    monkeypatch.setenv("SVJG_JSON_THREADS", str(threads))
+    monkeypatch.setenv("SVJG_JSON_BATCH", str(batch))
+    out = tmp_path / "x.json"
+    alnfilter.write_informative_json(t, gaf.encode(), res, str(out))
+    assert out.read_text() == read_golden("c1_informative_aln.json.gz")
+    empty = alnfilter.FilterResult(None, {"n_hits": 0}, sv2[:0], off[:0], ln[:0])
+    alnfilter.write_informative_json(t, gaf.encode(), empty, str(out))
+    assert out.read_text() == "{}"
+
+
 def test_json_emitter_quirks_and_empty(tmp_path, quirks):
     edges = json.loads(quirks["edges"])
     alt = alt_len_from_gfa_text(quirks["gfa"])
