@@ -6,6 +6,7 @@
 #include "svjg_internal.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -105,6 +106,42 @@ struct JsonIn {
         }
         return fail("unterminated string");
     }
+    // a string whose content is not needed (the GAF lines of informative_aln.json: hundreds of MB):
+    // jump from quote to quote; a quote is the end unless an odd number of backslashes precedes it.
+    // Escapes are still checked as string() would, so that a malformed file fails the same way.
+    bool skip_string() {
+        if (p >= end || *p != '"') return fail("expected string");
+        const char *q = p + 1;
+        for (;;) {
+            const char *e = static_cast<const char *>(memchr(q, '"', size_t(end - q)));
+            if (!e) {
+                p = end;
+                return fail("unterminated string");
+            }
+            size_t nb = 0;
+            while (e - nb > p + 1 && e[-1 - long(nb)] == '\\') ++nb;
+            if (nb % 2 == 0) {
+                // validate the escapes of [p+1, e)
+                for (const char *b = static_cast<const char *>(memchr(p + 1, '\\', size_t(e - p - 1))); b;) {
+                    const char esc = b[1];
+                    size_t adv = 2;
+                    if (esc == 'u') {
+                        if (e - b < 6) return fail("truncated \\u escape");
+                        for (int i = 2; i < 6; ++i)
+                            if (!isxdigit((unsigned char)b[i])) return fail("bad \\u escape");
+                        adv = 6;
+                    } else if (!strchr("\"\\/bfnrt", esc) || esc == 0) {
+                        return fail("bad escape");
+                    }
+                    const char *from = b + adv;
+                    b = from < e ? static_cast<const char *>(memchr(from, '\\', size_t(e - from))) : nullptr;
+                }
+                p = e + 1;
+                return true;
+            }
+            q = e + 1;
+        }
+    }
     // scalar kinds for the allele slot
     enum Kind { K_INT, K_FLOAT, K_TRUE, K_FALSE, K_NULL, K_STRING, K_ARRAY, K_OBJECT };
     bool skip_value(Kind &kind, long long *ival = nullptr, std::string *sval = nullptr) {
@@ -112,9 +149,8 @@ struct JsonIn {
         if (p >= end) return fail("unexpected end");
         char c = *p;
         if (c == '"') {
-            std::string tmp;
             kind = K_STRING;
-            return string(sval ? *sval : tmp);
+            return sval ? string(*sval) : skip_string();
         }
         if (c == '{') {
             kind = K_OBJECT;
