@@ -430,7 +430,7 @@ def main():
         dc = torch.from_numpy(res.counts.view(np.int32)).to(dev, non_blocking=True)
         if world > 1:
             dist.all_reduce(dc)
-        out = genotype.genotype_device(dc, sv_idx[lo:hi], sv_ty[lo:hi])
+        out = genotype.genotype_device(dc, d_idx, d_ty)           # the catalogue's index / type arrays stay on the device
         return res, out
 
     for _ in range(2):
@@ -445,7 +445,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    h2d = n_bytes + tables.num_sv * 8 + n_loc * 5 + lut.numel() * 8
+    h2d = n_bytes + tables.num_sv * 8
     d2h = tables.num_sv * 8 + 64 + res.n_hits * 16 + n_loc * (24 + 1 + 8 + 1)     # hits: u32 sv, u64 offset, u32 length
 
     if rank != 0:

@@ -38,9 +38,7 @@ struct HostWs {
     uint64_t hit_cap = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-    unsigned long long *d_cursor = nullptr;   // device: hit cursor after each chunk
-    uint64_t cursor_cap = 0;
-    uint64_t *d_off64 = nullptr;              // hit offsets made absolute on the device
+    uint64_t *d_off64 = nullptr;              // absolute hit offsets (written by the kernels)
 };
 
 void free_host_ws(svjg_tables *t) {
@@ -55,7 +53,6 @@ void free_host_ws(svjg_tables *t) {
         if (w->d_hit[i]) cudaFree(w->d_hit[i]);
     if (w->d_counts) cudaFree(w->d_counts);
     if (w->d_stats) cudaFree(w->d_stats);
-    if (w->d_cursor) cudaFree(w->d_cursor);
     if (w->d_off64) cudaFree(w->d_off64);
     if (w->s_copy) cudaStreamDestroy(w->s_copy);
     if (w->s_comp) cudaStreamDestroy(w->s_comp);
@@ -208,13 +205,29 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
         SVJG_CUDA(cudaMalloc(&w->d_off64, hit_cap * 8));
         w->hit_cap = hit_cap;
     }
-    if (w->cursor_cap < n_chunks + 1) {
-        if (w->d_cursor) SVJG_CUDA(cudaFree(w->d_cursor));
-        w->d_cursor = nullptr;
-        SVJG_CUDA(cudaMalloc(&w->d_cursor, (n_chunks + 1) * sizeof(unsigned long long)));
-        w->cursor_cap = n_chunks + 1;
+    // Result arrays in page-locked host memory are written by the kernels themselves (the device can
+    // address them): the hits cross PCIe while later chunks are still coming in, and no copy is left
+    // for the end.  Pageable arrays get the hits by a copy from device buffers.
+    auto device_view = [](void *p) -> void * {
+        cudaPointerAttributes at;
+        if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    uint32_t *k_sv2 = w->d_hit[0], *k_len = w->d_hit[2];
+    uint64_t *k_off = w->d_off64;
+    bool direct = false;
+    if (hit_cap) {
+        void *v0 = device_view(hit_sv2), *v1 = device_view(hit_off), *v2 = device_view(hit_len);
+        if (v0 && v1 && v2) {
+            k_sv2 = static_cast<uint32_t *>(v0);
+            k_off = static_cast<uint64_t *>(v1);
+            k_len = static_cast<uint32_t *>(v2);
+            direct = true;
+        }
     }
-    SVJG_CUDA(cudaMemsetAsync(w->d_cursor, 0, sizeof(unsigned long long), w->s_comp));
 
     int rc = svjg_filter_reset(w->d_counts, num_sv, w->d_stats, w->s_comp);
     if (rc) return rc;
@@ -225,17 +238,10 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
         SVJG_CUDA(cudaMemcpyAsync(w->d_buf[b], gaf + cut[k], len, cudaMemcpyHostToDevice, w->s_copy));
         SVJG_CUDA(cudaEventRecord(w->copied[b], w->s_copy));
         SVJG_CUDA(cudaStreamWaitEvent(w->s_comp, w->copied[b], 0));
-        rc = svjg_filter_device(t, w->d_buf[b], len, cut[k], d_over, w->d_counts, w->d_hit[0], w->d_hit[1], w->d_hit[2],
-                                hit_cap, w->d_stats, w->s_comp);
+        rc = filter_device_abs(t, w->d_buf[b], len, cut[k], d_over, w->d_counts, k_sv2, nullptr, k_off, k_len, hit_cap,
+                               w->d_stats, w->s_comp);
         if (rc) return rc;
         SVJG_CUDA(cudaEventRecord(w->freed[b], w->s_comp));
-        // the hits of this chunk lie between the cursor before and after it: make their offsets absolute
-        SVJG_CUDA(cudaMemcpyAsync(w->d_cursor + k + 1, &w->d_stats->n_hits, sizeof(unsigned long long),
-                                  cudaMemcpyDeviceToDevice, w->s_comp));
-        if (hit_cap) {
-            rc = svjg_hits_absolute(w->d_hit[1], w->d_off64, w->d_cursor + k, cut[k], hit_cap, w->s_comp);
-            if (rc) return rc;
-        }
     }
     SVJG_CUDA(cudaMemcpyAsync(stats, w->d_stats, sizeof(svjg_filter_stats), cudaMemcpyDeviceToHost, w->s_comp));
     SVJG_CUDA(cudaMemcpyAsync(counts, w->d_counts, size_t(num_sv) * 8, cudaMemcpyDeviceToHost, w->s_comp));
@@ -250,8 +256,8 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
     if (hit_cap == 0) return SVJG_OK;
     if (stats->n_hits > hit_cap) return set_error(SVJG_E_HITS_OVERFLOW, "hit buffers too small");
     const uint64_t nh = stats->n_hits;
-    if (nh) {
-        // straight into the caller's arrays: at PCIe speed if they are pinned, staged by the driver if not
+    if (nh && !direct) {
+        // pageable result arrays: staged by the driver
         SVJG_CUDA(cudaMemcpyAsync(hit_sv2, w->d_hit[0], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
         SVJG_CUDA(cudaMemcpyAsync(hit_off, w->d_off64, nh * 8, cudaMemcpyDeviceToHost, w->s_comp));
         SVJG_CUDA(cudaMemcpyAsync(hit_len, w->d_hit[2], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));

@@ -107,6 +107,7 @@ struct FilterArgs {
     DevTables tb;
     uint32_t *counts;
     uint32_t *hit_sv2, *hit_off, *hit_len;
+    uint64_t *hit_off64;         // if set: absolute offsets (base + offset) go here instead of hit_off
     uint64_t hit_cap;
     unsigned long long *stats;   // svjg_filter_stats as 8 x u64
     uint32_t flags;
@@ -492,7 +493,8 @@ struct Rec {
         base = now.shfl(base, 0) + now.thread_rank();
         if (base < a.hit_cap) {
             a.hit_sv2[base] = sv2;
-            a.hit_off[base] = line_off;
+            if (a.hit_off64) a.hit_off64[base] = a.base + line_off;
+            else a.hit_off[base] = line_off;
             a.hit_len[base] = line_len;
         }
     }
@@ -1352,7 +1354,8 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
                 const unsigned long long k = h_base + i;
                 if (k < a.hit_cap) {
                     a.hit_sv2[k] = sv2;
-                    a.hit_off[k] = h_off[i];
+                    if (a.hit_off64) a.hit_off64[k] = a.base + h_off[i];
+                    else a.hit_off[k] = h_off[i];
                     a.hit_len[k] = h_len[i];
                 }
             }
@@ -1481,24 +1484,10 @@ __global__ void reset_kernel(uint32_t *counts, uint64_t n, unsigned long long *s
     if (i < 8) stats[i] = (i == 5) ? ~0ull : 0ull;
 }
 
-__global__ void hits_absolute_kernel(const uint32_t *off32, uint64_t *off64, const unsigned long long *cursor, uint64_t base,
-                                     uint64_t hit_cap) {
-    const uint64_t lo = cursor[0], hi = cursor[1] < hit_cap ? cursor[1] : hit_cap;
-    for (uint64_t i = lo + blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < hi; i += uint64_t(gridDim.x) * blockDim.x)
-        off64[i] = base + off32[i];
-}
-
 int g_scan_grid_cap = 0;   // blocks of scan_parse resident at once (SM count x occupancy), per process
 int g_sms = 0;
 
 }  // namespace
-
-int svjg::svjg_hits_absolute(const uint32_t *d_off32, uint64_t *d_off64, const unsigned long long *d_cursor, uint64_t base,
-                             uint64_t hit_cap, void *stream) {
-    hits_absolute_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(d_off32, d_off64, d_cursor, base, hit_cap);
-    SVJG_CUDA(cudaGetLastError());
-    return SVJG_OK;
-}
 
 extern "C" int svjg_filter_reset(uint32_t *d_counts, uint32_t num_sv, svjg_filter_stats *d_stats, void *stream) {
     if (!d_counts || !d_stats) return set_error(SVJG_E_ARG, "svjg_filter_reset: NULL argument");
@@ -1513,9 +1502,18 @@ extern "C" int svjg_filter_reset(uint32_t *d_counts, uint32_t num_sv, svjg_filte
 extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset,
                                   int64_t d_over, uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off,
                                   uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream) {
+    return svjg::filter_device_abs(t, d_gaf, n_bytes, base_offset, d_over, d_counts, d_hit_sv2, d_hit_off, nullptr, d_hit_len,
+                                   hit_cap, d_stats, stream);
+}
+
+// d_hit_off64 != NULL: absolute 64-bit offsets (base_offset + offset) instead of d_hit_off (svjg_filter_host)
+int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset, int64_t d_over,
+                            uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off, uint64_t *d_hit_off64,
+                            uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream) {
     if (!t || t->device < 0) return set_error(SVJG_E_ARG, "svjg_filter_device: tables are not on a device");
     if (!d_counts || !d_stats || (n_bytes && !d_gaf)) return set_error(SVJG_E_ARG, "svjg_filter_device: NULL argument");
-    if (hit_cap && (!d_hit_sv2 || !d_hit_off || !d_hit_len)) return set_error(SVJG_E_ARG, "svjg_filter_device: NULL hit buffer");
+    if (hit_cap && (!d_hit_sv2 || (!d_hit_off && !d_hit_off64) || !d_hit_len))
+        return set_error(SVJG_E_ARG, "svjg_filter_device: NULL hit buffer");
     if (reinterpret_cast<uintptr_t>(d_gaf) & 15) return set_error(SVJG_E_ARG, "svjg_filter_device: d_gaf must be 16-byte aligned");
     if (n_bytes >= 0xFFFF0000ull) return set_error(SVJG_E_ARG, "svjg_filter_device: shard must be smaller than 4 GiB");
     if (n_bytes == 0) return SVJG_OK;
@@ -1545,6 +1543,7 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
     a.counts = d_counts;
     a.hit_sv2 = d_hit_sv2;
     a.hit_off = d_hit_off;
+    a.hit_off64 = d_hit_off64;
     a.hit_len = d_hit_len;
     a.hit_cap = hit_cap;
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);

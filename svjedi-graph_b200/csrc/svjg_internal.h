@@ -31,9 +31,10 @@ namespace svjg {
 int set_error(int code, const std::string &msg);
 int cuda_fail(int cuda_err, const char *what);   // records the message, returns SVJG_E_CUDA
 void free_host_ws(svjg_tables *t);
-// hit offsets of one chunk (cursor[0] .. cursor[1]) -> absolute 64-bit offsets; filter.cu
-int svjg_hits_absolute(const uint32_t *d_off32, uint64_t *d_off64, const unsigned long long *d_cursor, uint64_t base,
-                       uint64_t hit_cap, void *stream);
+// svjg_filter_device with absolute 64-bit hit offsets (d_hit_off64 != NULL); filter.cu
+int filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset, int64_t d_over,
+                      uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off, uint64_t *d_hit_off64, uint32_t *d_hit_len,
+                      uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream);
 }  // namespace svjg
 
 #define SVJG_CUDA(call)                                                        \

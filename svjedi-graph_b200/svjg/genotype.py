@@ -174,18 +174,26 @@ def genotype_host(counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR):
     return gt[:n], fl[:n], ad[:n], pl[:n]
 
 
+_dev_lut = {}
+
+
 def genotype_device(d_counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR, device=None):
     """Runs kernel 4 for len(sv_index) SVs; returns numpy (gt, flags, ad2, pl).
-    ``d_counts``: torch int32 [num_sv, 2] on the device (the filter's counters)."""
+    ``d_counts``: torch int32 [num_sv, 2] on the device (the filter's counters).  ``sv_index`` /
+    ``svtype``: numpy arrays, or torch tensors already on the device (int32 view of the uint32
+    indices / uint8) when the same catalogue is genotyped again and again."""
     import torch
     dev = d_counts.device if device is None else device
     n = int(len(sv_index))
     if not 0 < e < 1:
         raise VcfError("error rate must be in (0, 1)")      # math.log10 raises in the reference
     la, lb, lh = math.log10(1 - e), math.log10(e), math.log10(1 / 2)
-    lut = torch.from_numpy(log10comb_lut()).to(dev)
-    d_idx = torch.from_numpy(np.ascontiguousarray(sv_index, dtype=np.uint32).view(np.int32)).to(dev)
-    d_ty = torch.from_numpy(np.ascontiguousarray(svtype, dtype=np.uint8)).to(dev)
+    lut = _dev_lut.get(str(dev))
+    if lut is None:
+        lut = _dev_lut[str(dev)] = torch.from_numpy(log10comb_lut()).to(dev)      # constant table: uploaded once
+    d_idx = sv_index if isinstance(sv_index, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(sv_index, dtype=np.uint32).view(np.int32)).to(dev)
+    d_ty = svtype if isinstance(svtype, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(svtype, dtype=np.uint8)).to(dev)
     d_pl = torch.empty((max(n, 1), 3), dtype=torch.int64, device=dev)
     d_gt = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
     d_ad = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
@@ -200,20 +208,8 @@ def genotype_device(d_counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR, 
 
     launch(None)
     flags = d_fl.cpu().numpy()[:n]
-    need = np.nonzero(flags & capi.GT_NEED_K)[0]
-    if need.size:
-        # counts beyond the table: log10 C(n,k) from CPython for exactly those SVs
-        ad = d_ad.cpu().numpy().view(np.uint32)[:n]
-        kov = np.full(n, np.nan)
-        memo = {}
-        for i in need:
-            t1, t2 = int(ad[i, 0]), int(ad[i, 1])
-            r1 = (t1 >> 1) + ((t1 >> 1) & 1 if t1 & 1 else 0)
-            r2 = (t2 >> 1) + ((t2 >> 1) & 1 if t2 & 1 else 0)
-            v = memo.get((r1, r2))
-            if v is None:
-                v = memo[(r1, r2)] = math.log10(math.comb(r1 + r2, r1))
-            kov[i] = v
+    if (flags & capi.GT_NEED_K).any():
+        kov = _k_overrides(flags, d_ad.cpu().numpy().view(np.uint32)[:n], n)
         launch(torch.from_numpy(kov).to(dev))
         flags = d_fl.cpu().numpy()[:n]
         if (flags & capi.GT_NEED_K).any():
