@@ -374,3 +374,36 @@ def test_every_tile_size_gives_the_same_result(gpu, monkeypatch, tile):
     same = lambda st: {k: v for k, v in st.items() if k != "n_exact"}     # lines past the window depend on the tile
     assert (forced.counts == normal.counts).all() and same(forced.stats) == same(normal.stats)
     assert sorted(zip(forced.hit_sv2.tolist(), forced.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
+
+
+def test_host_buffers_and_torch_free_paths(gpu, tmp_path):
+    """Page-locked inputs and outputs (PinnedBytes, RegisteredBytes, HostBuffers: the kernels write the hits
+    straight into them) and svjg_genotype_host give what the pageable / tensor paths give."""
+    alnfilter, capi, genotype, torch = gpu
+    t, _ = _tables(alnfilter, "s3")
+    raw = read_golden("s3.gaf.gz").encode()
+    want = alnfilter.filter_host(t, raw)                               # pageable in, pageable out
+    key = lambda r: sorted(zip(r.hit_sv2.tolist(), r.hit_off.tolist(), r.hit_len.tolist()))
+    p = tmp_path / "s3.gaf"
+    p.write_bytes(raw)
+    pinned = alnfilter.read_file_pinned(str(p))
+    assert bytes(pinned.array) == raw
+    reg = alnfilter.RegisteredBytes(np.frombuffer(bytearray(raw), dtype=np.uint8))
+    out = alnfilter.HostBuffers(t, want.n_hits + 5)
+    for src in (pinned, reg):
+        got = alnfilter.filter_host(t, src, out=out)
+        assert (got.counts == want.counts).all() and got.stats == want.stats and key(got) == key(want)
+    with pytest.raises(RuntimeError):
+        alnfilter.filter_host(t, pinned, out=alnfilter.HostBuffers(t, 3))
+    # genotype from host arrays == genotype from device tensors
+    header, recs = genotype.parse_vcf(read_golden("s3.vcf.gz").splitlines(True))
+    idx = np.array([capi.NO_SV if (r[2] is None or t.find_sv(r[2]) is None) else t.find_sv(r[2]) for r in recs], dtype=np.uint32)
+    ty = np.array([r[1] for r in recs], dtype=np.uint8)
+    a = genotype.genotype_host(want.counts, idx, ty)
+    d_counts = torch.from_numpy(want.counts.view(np.int32)).cuda()
+    b = genotype.genotype_device(d_counts, idx, ty)
+    c = genotype.genotype_device(d_counts, torch.from_numpy(idx.view(np.int32)).cuda(), torch.from_numpy(ty).cuda())
+    for x, y, z in zip(a, b, c):
+        assert (x == y).all() and (x == z).all()
+    text_host, n_host = genotype.genotype_vcf(t, want.counts, read_golden("s3.vcf.gz").splitlines(True))
+    assert text_host == read_golden("s3_genotype.vcf.gz")
