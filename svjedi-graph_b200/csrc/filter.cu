@@ -6,30 +6,34 @@
 // read_gaf_line :184-198, extract_nodes :351-373, get_aln_links :200-219,
 // reverse_link :221-225, check_bkpt_overlap :258-273, get_node_len :343-349.
 //
-// The work is a chain of three kernels; a compacted list of link records in device scratch
-// memory connects the first two:
+// The work is a chain of four kernels; a compacted list of link records in device scratch
+// memory connects scan_parse and link:
+//   probe       one block: line length at the head of the shard -> bytes per tile, so that a tile
+//               holds about one line per lane of the warp that parses it; zeroes the list cursors.
 //   scan_parse  every WARP is an independent worker with its own shared-memory window
-//               (no block barrier).  It walks 4 KiB tiles of the byte buffer; a tile
+//               (no block barrier).  It walks tiles of at most 5 KiB of the byte buffer; a tile
 //               plus 1 KiB of look-ahead is staged by one TMA bulk copy.
-//               A  byte-parallel: every lane classifies 32 bytes with SWAR compares;
-//                  ballots turn the newline flags into the ordered list of line ends;
-//               B  line-parallel: one lane per line finds the 12 columns (tab bitmaps
-//                  of fixed spans, so lanes stay converged), validates the integer
-//                  columns, walks the path column and reads Tlen/Ts/Te of the lines
-//                  with >= 2 path nodes;
+//               A  byte-parallel: every lane classifies 32 bytes with SWAR compares into four
+//                  bitmaps (newline, tab, '<'/'>', non-digit); one warp scan turns the newline
+//                  bitmap into the ordered list of line ends;
+//               B  line-parallel: one lane per line reads the line's shape off runs of the tab and
+//                  non-digit bitmaps (12 columns, integer columns of digits only, none empty),
+//                  counts the path nodes and parses Tlen/Ts/Te of the lines with >= 2 of them;
 //               C  node-parallel: one lane per path node of those lines, still from shared
 //                  memory: chrom:start-end / chrom:pos.k -> exact 24-byte key -> one probe of
 //                  the plain-node table (node id, alt length);
 //               D  same lanes: node-length prefix sums, the breakpoint-overlap verdict of
 //                  every link (:269-273), the first-occurrence hazard (:206), and one 16-byte
 //                  link record (integer link key, line offset, line length) per link that
-//                  can have hits.
-//               Lines that are not of the plain shape go to the "exact" list.
+//                  can have hits.  Lines with 33-256 nodes: long_line(), 32 nodes a step.
+//               Lines that are not of the plain shape, or do not fit the window, go to the
+//               "exact" list.
 //   link        one thread per link record: forward and reverse key probes of the link
 //               hash, warp-aggregated counter atomics and hit tuples.
-//   exact       one thread per irregular line: parse_fields() / general(), which follow
-//               the reference's string semantics literally (odd integers, odd node
-//               names, names that could be substrings of earlier ones, long lines ...).
+//   exact       irregular lines.  parse_fields() / general() follow the reference's string
+//               semantics literally (odd integers, odd node names, names that could be
+//               substrings of earlier ones ...); a regular line that was merely too long for the
+//               window gets the fast rules applied where it lies (giant_line()).
 // The GAF bytes are read from DRAM once (scan_parse); only the exact route reads them again.
 // A line belongs to the tile its first byte is in.
 #include <cooperative_groups.h>
