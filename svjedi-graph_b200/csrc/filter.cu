@@ -254,6 +254,69 @@ __device__ __noinline__ int parse_int(const Src &src, typename Src::pos_t b, typ
     return 0;
 }
 
+// ---- a whole warp on one long line (exact kernel, one line per warp) ------------------------------
+__device__ __forceinline__ uint32_t low_bits(int n);   // the low n bits (defined with the bitmap helpers below)
+struct EqByte {
+    uint32_t c4;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const { return eq_bytes(w, c4); }
+};
+struct DelimByte {
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const {
+        return lop_nor_and(lop_and_xor(w, 0x7D7D7D7Du, 0x3C3C3C3Cu) + SVJG_M7, w, SVJG_H8);
+    }
+};
+// class bits of the 16 shard bytes at p (p % 16 == 0); bytes past the end of the shard count as zero
+template <class F>
+__device__ __forceinline__ uint32_t shard_mask16(const FilterArgs &a, uint64_t p, F cls) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (p + 16 <= a.n) {
+        v = __ldg(reinterpret_cast<const uint4 *>(a.gaf + p));
+    } else {
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (uint32_t k = 0; k < 16 && p + k < a.n; ++k) w[k >> 2] |= uint32_t(__ldg(a.gaf + p + k)) << (8 * (k & 3));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return mask16(v, cls);
+}
+// first byte of class `cls` in shard bytes [from, to), all lanes of the warp together; `to` if there is none
+template <class F>
+__device__ uint64_t coop_find(const FilterArgs &a, uint64_t from, uint64_t to, F cls) {
+    const int lane = threadIdx.x & 31;
+    for (uint64_t base = from & ~15ull; base < to; base += 512) {
+        const uint64_t p = base + 16ull * lane;
+        uint32_t m = 0;
+        if (p < to) {
+            m = shard_mask16(a, p, cls);
+            if (p < from) m &= 0xFFFFFFFFu << uint32_t(from - p);
+            if (p + 16 > to) m &= low_bits(int(to - p));
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m != 0);
+        if (bal) {
+            const int src = __ffs(bal) - 1;
+            return base + 16ull * src + uint32_t(__ffs(__shfl_sync(0xFFFFFFFFu, m, src)) - 1);
+        }
+    }
+    return to;
+}
+// number of path nodes in [ps, pe): non-delimiter bytes right behind a delimiter (extract_nodes :366-367)
+__device__ uint32_t coop_count_nodes(const FilterArgs &a, uint64_t ps, uint64_t pe) {
+    const int lane = threadIdx.x & 31;
+    uint32_t total = 0, carry = 0;
+    for (uint64_t base = ps & ~31ull; base < pe; base += 1024) {
+        const uint64_t p = base + 32ull * lane;
+        uint32_t d = 0;
+        if (p < pe) d = shard_mask16(a, p, DelimByte()) | (shard_mask16(a, p + 16, DelimByte()) << 16);
+        uint32_t left = __shfl_up_sync(0xFFFFFFFFu, d, 1) >> 31;           // the byte in front of this lane's 32
+        if (lane == 0) left = carry;
+        uint32_t st = ((d << 1) | left) & ~d;
+        if (p < ps) st &= 0xFFFFFFFFu << uint32_t(ps - p);
+        if (p + 32 > pe) st &= low_bits(int(pe > p ? pe - p : 0));
+        total += __popc(st);
+        carry = __shfl_sync(0xFFFFFFFFu, d, 31) >> 31;
+    }
+    return __reduce_add_sync(0xFFFFFFFFu, total);
+}
+
 // ---------------------------------------------------------------------------
 // Rec: one GAF line.  parse_fields()/general() are the exact, string-level
 // routines; link()/probe()/emit() are shared with the token-parallel route.
@@ -269,6 +332,7 @@ struct Rec {
     uint32_t line_off, line_len;
     Local &loc;
     int err;
+    bool coop = false;   // all 32 lanes run this line together (exact kernel): long scans are shared
 
     __device__ Rec(const FilterArgs &a_, Src s, uint32_t off, uint32_t len, Local &l)
         : a(a_), src(s), ps(0), pe(0), angle(true), tlen(0), ts(0), te(0), line_off(off), line_len(len), loc(l), err(0) {}
@@ -293,6 +357,10 @@ struct Rec {
             if (col == 5) {
                 // path column: find its end and count tokens on the way (extract_nodes :366-367)
                 bool prev_delim = true;
+                if (coop) {
+                    f = P(coop_find(a, uint64_t(pos), uint64_t(e), EqByte{0x09090909u}));
+                    ntok = coop_count_nodes(a, uint64_t(pos), uint64_t(f));
+                } else
                 for (; f < e; ++f) {
                     uint32_t c = src[f];
                     if (c == '\t') break;
@@ -1421,9 +1489,12 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
     for (uint32_t i = me; i < n; i += stride) {
         const uint32_t off = a.sc.exact[i];
         uint64_t e = off;
-        while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
+        if (per_warp) e = coop_find(a, off, a.n, EqByte{0x0A0A0A0Au});
+        else
+            while (e < a.n && __ldg(a.gaf + e) != '\n') ++e;
         const uint32_t len = uint32_t(e - off) + (e < a.n ? 1u : 0u);
         Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+        rec.coop = per_warp;
         const uint32_t ntok = rec.parse_fields(uint64_t(off), e);
         if (!rec.err && ntok >= 2) {
             if (ntok != COMMA_PATH && part == 0) loc.n_multi++;
