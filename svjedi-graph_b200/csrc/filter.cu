@@ -84,12 +84,14 @@ constexpr uint32_t COMMA_PATH = 0xFFFFFFFFu;
 
 constexpr uint64_t LINK_HOLE = ~0ull;           // link record that was reserved but not filled
 constexpr uint32_t LINK_OK = 0x80000000u;       // in LinkRec::len: the breakpoint-overlap test passed
+constexpr uint32_t LINK_DIRS_SHIFT = 29;        //   bits 29, 30: the forward / the reverse key can exist (link_dirs())
+constexpr uint32_t LINK_LEN = 0x1FFFFFFFu;
 
 // a link of a multi-node line that passed phases C/D
 struct LinkRec {
     uint64_t key;         // link_key(idL, sL, idR, sR)
     uint32_t off;         // first byte of the line (offset into the shard)
-    uint32_t len;         // bytes of the line incl. its newline | LINK_OK
+    uint32_t len;         // bytes of the line incl. its newline | link_dirs() << 29 | LINK_OK
 };
 static_assert(sizeof(LinkRec) == 16, "LinkRec is 16 bytes");
 
@@ -575,13 +577,14 @@ struct Rec {
     // the node ids (NO_NODE: the name is in no key, so no key can match).
     // ok_known: the overlap verdict is already there; otherwise it is computed
     // once, on the first key that has entries, by the general overlap().
-    __device__ void link(const Tok &A, uint32_t idA, int sA, const Tok &B, uint32_t idB, int sB, bool ok_known, bool ok) {
+    // dirs: bit 0 = the forward key can exist, bit 1 = the reverse key can (node roles); 3 = not known
+    __device__ void link(const Tok &A, uint32_t idA, int sA, const Tok &B, uint32_t idB, int sB, bool ok_known, bool ok,
+                         uint32_t dirs = 3u) {
         if (idA == NO_NODE || idB == NO_NODE) return;
-        // both slots are fetched before either is looked at: one round trip
         LinkSlot sl[2];
         bool hit[2];
-        hit[0] = probe(idA, sA, idB, sB, sl[0]);
-        hit[1] = probe(idB, !sB, idA, !sA, sl[1]);
+        hit[0] = (dirs & 1u) && probe(idA, sA, idB, sB, sl[0]);
+        hit[1] = (dirs & 2u) && probe(idB, !sB, idA, !sA, sl[1]);
 #pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
             if (!hit[dir]) continue;
@@ -848,7 +851,7 @@ __device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint3
 
 // plain-node table: exact key -> (node id, alt sequence length)
 __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uint64_t c1, uint32_t ka, uint32_t kb,
-                                           uint32_t &id, uint32_t &alt_len) {
+                                           uint32_t &id, uint32_t &alt_len, uint32_t &roles) {
     uint32_t i = pnode_hash(c0, c1, ka, kb) & tb.pnode_mask;
     for (;;) {
         const uint4 *sp = reinterpret_cast<const uint4 *>(tb.pnodes + i);
@@ -856,12 +859,22 @@ __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uin
         if (!hi.z) return false;
         if (lo.x == uint32_t(c0) && lo.y == uint32_t(c0 >> 32) && lo.z == uint32_t(c1) && lo.w == uint32_t(c1 >> 32) &&
             hi.x == ka && hi.y == kb) {
-            id = hi.z - 1u;
+            id = (hi.z & PN_ID_MASK) - 1u;
+            roles = hi.z >> 28;
             alt_len = hi.w;
             return true;
         }
         i = (i + 1) & tb.pnode_mask;
     }
+}
+
+// which of the two keys of a link can exist, from the roles of its nodes: the forward key (A, sA, B, sB)
+// needs A as a left node with strand sA and B as a right node with strand sB; the reverse key
+// (B, !sB, A, !sA) needs B as a left node with !sB and A as a right node with !sA
+__device__ __forceinline__ uint32_t link_dirs(uint32_t rolesA, uint32_t sA, uint32_t rolesB, uint32_t sB) {
+    const uint32_t fwd = (rolesA >> sA) & (rolesB >> (2u + sB)) & 1u;
+    const uint32_t rev = (rolesB >> (sB ^ 1u)) & (rolesA >> (2u + (sA ^ 1u))) & 1u;
+    return fwd | (rev << 1);
 }
 
 // ---- phase C: the idx-th node of the path [lps, lpe) -- strand, exact key, table probe, length
@@ -870,6 +883,7 @@ struct Node {
     uint32_t nlen = 0;        // get_node_len (:343-349)
     uint32_t akey = 0;        // start value and kind: equal ones in a path mean the first-occurrence rules may bite
     uint32_t plus = 0;        // the delimiter in front is '>'
+    uint32_t roles = 0;       // PNodeSlot roles: bit s = left node of some key with strand s, bit 2+s = right node
     uint32_t end = 0;         // window position behind the name (a delimiter, or the end of the path)
     bool plain = false;       // chrom:start-end or chrom:pos.k of the exact-key form, with a length
 };
@@ -947,7 +961,7 @@ __device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t 
             if (q == end && nd1 >= 1 && nd1 <= 9 && !(nd1 > 1 && win[q1] == '0')) {
                 const uint32_t kind = sep == '.' ? PN_ALT : 0u;
                 uint32_t id = NO_NODE, alt_len = PN_NO_LEN;
-                const bool found = pnode_find(tb, c0, c1, v0, v1 | kind, id, alt_len);
+                const bool found = pnode_find(tb, c0, c1, v0, v1 | kind, id, alt_len, n.roles);
                 n.akey = v0 | kind;
                 if (!kind) {
                     if (v1 >= v0) {                                 // get_node_len :343-349
@@ -987,7 +1001,7 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, 
         Node n;
         if (act) {
             n = resolve_node<true>(win, dlb, a.tb, from, lpe, uint32_t(lane));
-            __stcg(slab + c0 + lane, make_uint4(n.nid, n.nlen, n.akey, n.plus));
+            __stcg(slab + c0 + lane, make_uint4(n.nid, n.nlen, n.akey, n.plus | (n.roles << 1)));
         }
         bad |= __any_sync(0xFFFFFFFFu, act && !n.plain);
         total += __shfl_sync(0xFFFFFFFFu, warp_incl_scan64(n.nlen, lane), 31);
@@ -1020,19 +1034,20 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, 
         const uint64_t incl = warp_incl_scan64(me.y, lane);
         const uint64_t pre = before + incl - me.y;
         const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
-        const bool emit = room && lf.x != NO_NODE && me.x != NO_NODE && (ok || (a.flags & FLAG_EXACT_CHECKS));
+        const uint32_t dirs = link_dirs(lf.w >> 1, lf.w & 1u, me.w >> 1, me.w & 1u);
+        const bool emit = room && lf.x != NO_NODE && me.x != NO_NODE && dirs && (ok || (a.flags & FLAG_EXACT_CHECKS));
         if (DIRECT) {
             if (act && t && emit) {
                 Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
                 const Rec<GmemSrc>::Tok none{0, 0};
-                rec.link(none, lf.x, int(lf.w), none, me.x, int(me.w), true, ok);
+                rec.link(none, lf.x, int(lf.w & 1u), none, me.x, int(me.w & 1u), true, ok, dirs);
                 if (rec.err) report(a, rec.err, off);
             }
         } else if (act && t && base + t - 1u < a.sc.cap_links) {           // link t-1 of the line: a record or a hole
             LinkRec r;
-            r.key = emit ? link_key(lf.x, lf.w, me.x, me.w) : LINK_HOLE;
+            r.key = emit ? link_key(lf.x, lf.w & 1u, me.x, me.w & 1u) : LINK_HOLE;
             r.off = off;
-            r.len = len | (ok ? LINK_OK : 0u);
+            r.len = len | (ok ? LINK_OK : 0u) | (dirs << LINK_DIRS_SHIFT);
             *reinterpret_cast<uint4 *>(a.sc.links + base + t - 1u) = *reinterpret_cast<const uint4 *>(&r);
         }
         before += __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -1305,7 +1320,8 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                 const uint32_t loff = __shfl_sync(0xFFFFFFFFu, s, own);
                 const uint32_t llen = __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), own);
                 const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
-                const bool emit = is_tok && idx >= 1 && !((bad >> own) & 1u) && idl != NO_NODE && nid != NO_NODE &&
+                const uint32_t dirs = link_dirs(__shfl_up_sync(0xFFFFFFFFu, nd.roles, 1), sl, nd.roles, plus);
+                const bool emit = is_tok && idx >= 1 && !((bad >> own) & 1u) && idl != NO_NODE && nid != NO_NODE && dirs &&
                                   (ok || (a.flags & FLAG_EXACT_CHECKS));
                 uint32_t redo = bad;                                                // lines of this round for the exact route
                 const uint32_t eb = __ballot_sync(0xFFFFFFFFu, emit);
@@ -1321,7 +1337,7 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                         LinkRec r;
                         r.key = room ? link_key(idl, sl, nid, plus) : LINK_HOLE;
                         r.off = wbase + loff;
-                        r.len = llen | (ok ? LINK_OK : 0u);
+                        r.len = llen | (ok ? LINK_OK : 0u) | (dirs << LINK_DIRS_SHIFT);
                         *reinterpret_cast<uint4 *>(a.sc.links + slot) = *reinterpret_cast<const uint4 *>(&r);
                     }
                 }
@@ -1395,7 +1411,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
         for (int k = 0; k < LINK_PER_THREAD; ++k) {
             const uint64_t key = (uint64_t(r[k].y) << 32) | r[k].x;
             if (key != LINK_HOLE) {
-                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, r[k].z, r[k].w & ~LINK_OK, loc);
+                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, r[k].z, r[k].w & LINK_LEN, loc);
                 rec.stage_sv = h_sv;
                 rec.stage_off = h_off;
                 rec.stage_len = h_len;
@@ -1403,7 +1419,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
                 rec.stage_cap = LINK_STAGE;
                 const Rec<GmemSrc>::Tok none{0, 0};
                 rec.link(none, uint32_t(key >> 33), int((key >> 32) & 1u), none, uint32_t(key) >> 1, int(key & 1u), true,
-                         (r[k].w & LINK_OK) != 0);
+                         (r[k].w & LINK_OK) != 0, (r[k].w >> LINK_DIRS_SHIFT) & 3u);
                 if (rec.err) report(a, rec.err, r[k].z);
             }
         }

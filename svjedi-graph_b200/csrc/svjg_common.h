@@ -72,11 +72,15 @@ static_assert(sizeof(NodeSlot) == 32, "NodeSlot must be one sector");
 // other name is reachable only through the name-hash table above (the exact route).
 constexpr uint32_t PN_ALT = 0x80000000u;       // in PNodeSlot::b: chrom:pos.k
 constexpr uint32_t PN_NO_LEN = 0xFFFFFFFFu;    // alt node without a usable GFA sequence length
+constexpr uint32_t PN_ID_MASK = 0x0FFFFFFFu;   // PNodeSlot::id1: node id + 1
 struct PNodeSlot {
     uint64_t c0, c1;       // chrom bytes, little endian, zero padded
     uint32_t a;            // start / pos
     uint32_t b;            // end, or k | PN_ALT
-    uint32_t id1;          // node id + 1 (same ids as NodeSlot); 0 = empty slot
+    uint32_t id1;          // low 28 bits: node id + 1 (same ids as NodeSlot), 0 = empty slot; high 4 bits: the
+                           // roles the node has in link keys -- bit 28+s: left node with strand s, bit 30+s:
+                           // right node with strand s (s = 1 for '+').  A key (L, sL, R, sR) can exist only if
+                           // L has role 28+sL and R has role 30+sR: most reverse-key probes are never made.
     uint32_t alt_len;      // alt node: GFA sequence length (1 .. 2^31-1) or PN_NO_LEN
 };
 static_assert(sizeof(PNodeSlot) == 32, "PNodeSlot must be one sector");

@@ -559,6 +559,7 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
     };
     for (auto &a : alts) nodes[intern(a.first)].second = a.second;
 
+    std::vector<uint8_t> roles;                              // per node: bit s = left node with strand s, bit 2+s = right
     uint32_t cap = pow2_at_least(parses.size() * 2 + 2);
     t->links.assign(cap, LinkSlot{});
     for (auto &ps : parses) {
@@ -571,6 +572,9 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         }
         uint32_t sl = k[ps.split + 1] == '+', sr = k[n - 1] == '+';
         uint32_t idl = intern(k.substr(0, len_l)), idr = intern(k.substr(off_r, len_r));
+        if (roles.size() < nodes.size()) roles.resize(nodes.size(), 0);
+        roles[idl] |= uint8_t(1u << sl);
+        roles[idr] |= uint8_t(4u << sr);
         if (nodes.size() >= 0x7FFFFFFFull) {
             err = "too many distinct node names";
             return false;
@@ -619,7 +623,11 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         for (size_t id = 0; id < nodes.size(); ++id) {
             PNodeSlot s{};
             if (!plain_key(nodes[id].first, s)) continue;
-            s.id1 = uint32_t(id) + 1;
+            if (id + 1 > PN_ID_MASK) {
+                err = "too many distinct node names";
+                return false;
+            }
+            s.id1 = (uint32_t(id) + 1) | (uint32_t(id < roles.size() ? roles[id] : 0) << 28);
             const int64_t sl = nodes[id].second;
             s.alt_len = (sl > 0 && sl <= 0x7FFFFFFF) ? uint32_t(sl) : PN_NO_LEN;
             plain.push_back(s);
