@@ -523,8 +523,7 @@ struct Rec {
     }
 
     // link table: exact integer key -> entries
-    __device__ bool probe(uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr, LinkSlot &out) const {
-        const uint64_t key = link_key(idl, sl, idr, sr);
+    __device__ bool probe_key(uint64_t key, LinkSlot &out) const {
         uint32_t i = uint32_t(link_hash(key)) & a.tb.link_mask;
         for (;;) {
             const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
@@ -581,10 +580,13 @@ struct Rec {
     __device__ void link(const Tok &A, uint32_t idA, int sA, const Tok &B, uint32_t idB, int sB, bool ok_known, bool ok,
                          uint32_t dirs = 3u) {
         if (idA == NO_NODE || idB == NO_NODE) return;
+        // one probe where only one key can exist -- the lanes of a warp then probe together whichever
+        // key each of them needs; the second probe is for links with both keys possible (forward first)
+        const uint64_t fwd = link_key(idA, uint32_t(sA), idB, uint32_t(sB)), rev = link_key(idB, uint32_t(!sB), idA, uint32_t(!sA));
         LinkSlot sl[2];
         bool hit[2];
-        hit[0] = (dirs & 1u) && probe(idA, sA, idB, sB, sl[0]);
-        hit[1] = (dirs & 2u) && probe(idB, !sB, idA, !sA, sl[1]);
+        hit[0] = dirs != 0u && probe_key((dirs & 1u) ? fwd : rev, sl[0]);
+        hit[1] = dirs == 3u && probe_key(rev, sl[1]);
 #pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
             if (!hit[dir]) continue;
