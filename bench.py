@@ -30,7 +30,7 @@ for p in (ROOT, PKG):
 METRIC = "gaf_alignments_filtered_assigned_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of the filter chain per launch, from the ncu --set full
 # capture committed under profiles/ (None where no capture exists for the workload)
-FILTER_TRAFFIC = {"C2": 558_700_000}   # profiles/r1/ncu_chain_v12_summary.txt: scan_parse 517.3+19.1, link 22.0, probe 0.3 MB
+FILTER_TRAFFIC = {"C2": 557_700_000}   # profiles/r1/ncu_chain_v15_summary.txt: scan_parse 517.4+18.7, link 21.4, probe+exact 0.2 MB
 UNIT = "alignments/s"
 
 
