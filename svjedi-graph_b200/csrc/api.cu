@@ -219,7 +219,10 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
     uint32_t *k_sv2 = w->d_hit[0], *k_len = w->d_hit[2];
     uint64_t *k_off = w->d_off64;
     bool direct = false;
-    if (hit_cap) {
+    // Up to 64 MB of hit tuples; beyond that the copy engines take them at the end.  (Measured: 0.5 GB
+    // of tuples per GPU written by the kernels is fine on one GPU -- 5 ms, hidden behind the upload --
+    // but took 1.3 s when eight GPUs of a node did it at once.)
+    if (hit_cap && hit_cap * 16 <= (64ull << 20)) {
         void *v0 = device_view(hit_sv2), *v1 = device_view(hit_off), *v2 = device_view(hit_len);
         if (v0 && v1 && v2) {
             k_sv2 = static_cast<uint32_t *>(v0);
