@@ -1351,9 +1351,6 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                 __syncwarp();
             }
             // ---- lines with more nodes than a round has lanes: one line at a time (long_line())
-#ifdef SVJG_NO_LONG
-            if (want > TOKCAP) exact = true;
-#else
             for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > TOKCAP); longb; longb &= longb - 1) {
                 const int L = __ffs(longb) - 1;
                 const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), L);
@@ -1367,7 +1364,6 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                     else loc.n_multi++;
                 }
             }
-#endif
             const uint32_t xb = __ballot_sync(0xFFFFFFFFu, exact);
             if (xb) {
                 uint32_t xbase = 0;
@@ -1495,11 +1491,7 @@ __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_consta
     // every line gets a warp of its own and the lanes share its links; only a flood of them goes one
     // line per thread.
     const uint32_t n_warps = gridDim.x * (FLAT_THREADS / 32);
-#ifdef SVJG_NO_PER_WARP
-    const bool per_warp = false;
-#else
     const bool per_warp = n <= 4u * n_warps;
-#endif
     const uint32_t me = per_warp ? (blockIdx.x * FLAT_THREADS + threadIdx.x) >> 5 : blockIdx.x * FLAT_THREADS + threadIdx.x;
     const uint32_t stride = per_warp ? n_warps : gridDim.x * FLAT_THREADS;
     const uint32_t part = per_warp ? (threadIdx.x & 31u) : 0u, parts = per_warp ? 32u : 1u;
