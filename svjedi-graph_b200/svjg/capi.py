@@ -40,11 +40,6 @@ class FilterStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
-# every kernel of the library is used by every run: loading them with the context is faster than on
-# first launch (measured: 0.5 s per process)
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
-
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
