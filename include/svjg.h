@@ -111,7 +111,11 @@ int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_by
                        int64_t d_over, uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off,
                        uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream);
 
-/* Same, from HOST memory: stages the bytes to the device in pinned chunks cut at
+/* Lines end at '\n'.  The reference opens the GAF in text mode, where "\r\n" and a lone "\r" end a
+ * line as well (and are stored as "\n"): a caller whose bytes may contain carriage returns translates
+ * them first, as the drop-in front-ends do (svjg/alnfilter.py: translate_newlines).
+ *
+ * Same, from HOST memory: stages the bytes to the device in pinned chunks cut at
  * line ends, overlapping copies with the kernel; returns counts, stats and the
  * hits (offsets are absolute in `gaf`) in host arrays.  `hit_*` may be NULL to
  * skip the hit list (counts only).  Synchronous.  Returns SVJG_E_INPUT with

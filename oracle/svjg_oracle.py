@@ -125,6 +125,14 @@ def parse_record(line):
     return cols[5], tlen, ts, te
 
 
+def text_mode_lines(text):
+    """The lines `for line in open(path)` yields for a file with this content (filter-alignments.py
+    :123-124 reads the GAF in text mode): universal newlines -- "\r\n" and a lone "\r" end a line
+    just like "\n", and all of them come out as "\n"."""
+    import io
+    return list(io.StringIO(text, newline=None))
+
+
 def record_hits(line, d_link_sv, alt_len, d_over=D_OVER_DEFAULT):
     """All (sv_id, allele) appends one GAF line causes, in reference order
     (link, then fwd/rev key, then entry) — filter-alignments.py:126-166."""

@@ -111,6 +111,22 @@ def _as_u8(buf):
     return a
 
 
+def translate_newlines(buf):
+    """The reference reads the GAF in text mode (filter-alignments.py:123): "\r\n" and a lone "\r" are
+    line ends too and become "\n" in the stored lines.  The kernels split at "\n" only, so a buffer
+    that contains a carriage return is translated first (a copy); any other buffer is returned as it
+    is.  One memchr over the bytes."""
+    a = _as_u8(buf)
+    if a.size == 0:
+        return buf
+    libc = C.CDLL(None)
+    libc.memchr.restype = C.c_void_p
+    libc.memchr.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+    if not libc.memchr(a.ctypes.data, 13, a.size):
+        return buf
+    return np.frombuffer(a.tobytes().replace(b"\r\n", b"\n").replace(b"\r", b"\n"), dtype=np.uint8)
+
+
 def _raise_input(stats):
     reason = capi.BAD_REASONS.get(stats["status"], "malformed input")
     raise InputError(f"GAF line at byte {stats['err_offset']}: {reason} (the reference raises here)")

@@ -54,6 +54,8 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None):
         tables.set_flags(capi.FLAG_EXACT_CHECKS)
     if gaf is None:
         gaf = alnfilter.read_file_pinned(gaf_file)
+        if alnfilter.translate_newlines(gaf) is not gaf:                   # carriage returns: text-mode line ends
+            gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
     res = alnfilter.filter_host(tables, gaf)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
@@ -81,6 +83,7 @@ def filter_main(argv=None):
     try:
         ready = _start_device()
         raw = np.fromfile(args.gaf[0], dtype=np.uint8)                     # read while the context comes up
+        raw = alnfilter.translate_newlines(raw)                            # text-mode line ends, like the reference
         tables = _load_tables(args.prefix, args.gfa[0], ready)
         gaf = alnfilter.RegisteredBytes(raw)                                # page-lock in place
         _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, gaf=gaf)

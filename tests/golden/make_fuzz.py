@@ -1,0 +1,119 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/fuzz_lines.json.gz: randomly damaged GAF lines on the c1 graph, each run
+ALONE through the UNMODIFIED reference filter (/root/reference/filter-alignments.py, imported and its
+main() called in-process).  Stored per line: the text, whether the reference raised (exit status 1),
+and otherwise the list lengths of its informative_aln.json.
+
+    python tests/golden/make_fuzz.py            # build container only (needs /root/reference)
+"""
+import gzip
+import importlib.util
+import io
+import json
+import os
+import random
+import sys
+import tempfile
+from contextlib import redirect_stderr, redirect_stdout
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def read_golden(name):
+    p = os.path.join(HERE, name)
+    if name.endswith(".gz"):
+        return gzip.open(p, "rt").read()
+    return open(p).read()
+
+
+def mutated_lines(n, seed=20261017):
+    """Deterministic damage: byte edits, column edits, truncation, revisited nodes.  Avoids the two
+    documented deviations of the CUDA path ('_' in integers, more than 18 digits in Tlen/Ts/Te)."""
+    base = [l for l in read_golden("c1.gaf.gz").splitlines(True) if l.count(">") + l.count("<") >= 2][:300]
+    rng = random.Random(seed)
+    alphabet = "\t\t\t 09a><:-.,+\r\x0b;|"
+    out = []
+    while len(out) < n:
+        line = rng.choice(base).rstrip("\n")
+        for _ in range(rng.choice((1, 1, 2, 3))):
+            k = rng.randrange(6)
+            pos = rng.randrange(len(line) + 1)
+            if k == 0 and pos < len(line):
+                line = line[:pos] + rng.choice(alphabet) + line[pos + 1:]
+            elif k == 1 and pos < len(line):
+                line = line[:pos] + line[pos + 1:]
+            elif k == 2:
+                line = line[:pos] + rng.choice(alphabet) + line[pos:]
+            elif k == 3:
+                cols = line.split("\t")
+                j = rng.randrange(len(cols))
+                cols[j] = rng.choice(("", "0", "00", "+5", " 7 ", "12x", cols[j] + cols[j], cols[j][::-1]))
+                line = "\t".join(cols)
+            elif k == 4:
+                line = line[:pos]
+            else:
+                cols = line.split("\t")
+                if len(cols) > 5:
+                    toks = [x for x in cols[5].replace("<", ">").split(">") if x]
+                    if toks:
+                        cols[5] = cols[5] + rng.choice(">< ") + rng.choice(toks)      # revisit / odd tail
+                        line = "\t".join(cols)
+        if "_" in line or "\n" in line or not line:
+            continue
+        cols = line.split("\t")
+        if any(len(c.strip().lstrip("+-").lstrip("0")) > 18 for c in cols[6:9]):
+            continue
+        out.append(line + rng.choice(("\n", "\n", "")))
+    return out
+
+
+def main():
+    spec = importlib.util.spec_from_file_location("ref_filter", os.path.join(REF, "filter-alignments.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    lines = mutated_lines(2500)
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "p.gfa"), "w").write(read_golden("c1.gfa.gz"))
+        open(os.path.join(tmp, "p_svs_edges.json"), "w").write(read_golden("c1_svs_edges.json"))
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            for line in lines:
+                with open("p.gaf", "w", newline="") as fh:
+                    fh.write(line)
+                if os.path.exists("p_informative_aln.json"):
+                    os.remove("p_informative_aln.json")
+                try:
+                    sys.argv = ["filter-alignments.py", "-a", "p.gaf", "-g", "p.gfa", "-p", "p"]   # main() parses sys.argv
+                    with redirect_stdout(io.StringIO()), redirect_stderr(io.StringIO()):
+                        ref.main(sys.argv[1:])
+                    d = json.load(open("p_informative_aln.json"))
+                    cases.append({"line": line, "rc": 0, "counts": {k: [len(v[0]), len(v[1])] for k, v in d.items()}})
+                except BaseException:                                   # any traceback or sys.exit: status 1
+                    cases.append({"line": line, "rc": 1})
+        finally:
+            os.chdir(cwd)
+        # a whole file with CR LF line ends, one line with a lone CR in its read name: Python's text mode
+        # makes every one of them a line break and stores "\n" in the JSON
+        os.chdir(tmp)
+        try:
+            src = read_golden("c1.gaf.gz").splitlines()[:400]
+            src = [l for l in src if "cg:Z:" not in l]
+            crlf = "\r\n".join(src) + "\r\n"
+            with open("p.gaf", "w", newline="") as fh:
+                fh.write(crlf)
+            sys.argv = ["filter-alignments.py", "-a", "p.gaf", "-g", "p.gfa", "-p", "p"]
+            with redirect_stdout(io.StringIO()), redirect_stderr(io.StringIO()):
+                ref.main(sys.argv[1:])
+            crlf_json = open("p_informative_aln.json").read()
+        finally:
+            os.chdir(cwd)
+    with gzip.GzipFile(os.path.join(HERE, "fuzz_lines.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps({"cases": cases, "crlf": {"gaf": crlf, "json": crlf_json}}, ensure_ascii=True).encode())
+    print(len(cases), "cases;", sum(c["rc"] for c in cases), "raise;", sum(1 for c in cases if c.get("counts")), "with hits")
+
+
+if __name__ == "__main__":
+    main()

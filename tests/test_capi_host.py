@@ -107,3 +107,15 @@ def test_json_emitter_quirks_and_empty(tmp_path, quirks):
         assert out.read_text() == case["json"], case["name"]
         n += 1
     assert n >= 15
+
+
+def test_translate_newlines_is_text_mode():
+    """Carriage returns end lines for the reference (text-mode open()): the host mirror translates them
+    exactly as Python does, and leaves buffers without one untouched (same object)."""
+    import io
+    plain = b"a\tb\nc\n"
+    assert alnfilter.translate_newlines(plain) is plain
+    assert alnfilter.translate_newlines(b"") == b""
+    for text in ("a\r\nb\r\n", "a\rb\nc", "\r\r\n\n\r", "x\ty\r"):
+        want = "".join(io.StringIO(text, newline=None))
+        assert bytes(alnfilter.translate_newlines(text.encode())) == want.encode()

@@ -75,3 +75,31 @@ def test_scaled_configs_byte_equal(tag):
     text, n = O.genotype_vcf(O.hit_counts(d), read_golden(f"{tag}.vcf.gz").splitlines(True))
     assert text == read_golden(f"{tag}_genotype.vcf.gz")
     assert f"Genotyped svs: {n}\n" == read_golden(f"{tag}_stdout.txt")
+
+
+def test_oracle_on_damaged_lines_matches_the_reference():
+    """tests/golden/fuzz_lines.json.gz: 2500 randomly damaged GAF lines, each run alone as a file through
+    the unmodified reference filter (tests/golden/make_fuzz.py).  The oracle must raise exactly where
+    the reference exits with status 1, and count the same hits elsewhere.  A carriage return is a line
+    end for the reference (text mode): O.text_mode_lines."""
+    import json
+    edges = json.loads(read_golden("c1_svs_edges.json"))
+    alt = alt_len_from_gfa_text(read_golden("c1.gfa.gz"))
+    fx = json.loads(read_golden("fuzz_lines.json.gz"))
+    cases = fx["cases"]
+    assert len(cases) == 2500 and 500 < sum(c["rc"] for c in cases) < 2000
+    for c in cases:
+        try:
+            got = {}
+            for line in O.text_mode_lines(c["line"]):
+                for sv, allele in O.record_hits(line, edges, alt):
+                    got.setdefault(sv, [0, 0])[allele] += 1
+            raised = False
+        except Exception:
+            raised = True
+        assert raised == bool(c["rc"]), c["line"]
+        if not raised:
+            assert got == c["counts"], c["line"]
+    # a file with CR LF line ends: same JSON as the reference, "\n" stored
+    d = O.filter_alignments(O.text_mode_lines(fx["crlf"]["gaf"]), edges, alt)
+    assert O.dumps_informative(d) == fx["crlf"]["json"]
