@@ -115,5 +115,82 @@ def main():
     print(len(cases), "cases;", sum(c["rc"] for c in cases), "raise;", sum(1 for c in cases if c.get("counts")), "with hits")
 
 
+def damaged_vcfs(n, seed=20261018):
+    """Small VCFs: the header of c1.vcf, a few of its body lines, one of them damaged."""
+    text = read_golden("c1.vcf")
+    header = [l for l in text.splitlines(True) if l.startswith("#")]
+    body = [l for l in text.splitlines(True) if not l.startswith("#")]
+    rng = random.Random(seed)
+    alphabet = "\t;=:[]09ANt-,. <>"
+    out = []
+    while len(out) < n:
+        pick = [rng.choice(body) for _ in range(rng.choice((2, 3, 4)))]
+        j = rng.randrange(len(pick))
+        line = pick[j].rstrip("\n")
+        for _ in range(rng.choice((1, 1, 2))):
+            k = rng.randrange(7)
+            pos = rng.randrange(len(line) + 1)
+            cols = line.split("\t")
+            if k == 0 and pos < len(line):
+                line = line[:pos] + rng.choice(alphabet) + line[pos + 1:]
+            elif k == 1 and pos < len(line):
+                line = line[:pos] + line[pos + 1:]
+            elif k == 2:
+                line = line[:pos] + rng.choice(alphabet) + line[pos:]
+            elif k == 3 and len(cols) > 7:
+                info = cols[7].split(";")
+                rng.shuffle(info)
+                if rng.random() < 0.5 and len(info) > 1:
+                    info.pop(rng.randrange(len(info)))
+                cols[7] = ";".join(info)
+                line = "\t".join(cols)
+            elif k == 4:
+                line = "\t".join(cols[:rng.randrange(len(cols) + 1)])
+            elif k == 5 and len(cols) > 7:
+                cols[7] = cols[7].replace("SVTYPE=" + rng.choice(("DEL", "INS", "INV", "BND")), "SVTYPE=" + rng.choice(("DEL", "INS", "INV", "BND", "DUP", "")))
+                line = "\t".join(cols)
+            elif len(cols) > 4:
+                cols[rng.choice((1, 4))] = rng.choice(("", "0", "x", "12", cols[4] * 3, "N[1:500[", "]2:7000]N", "A" * 70))
+                line = "\t".join(cols)
+        pick[j] = line + "\n"
+        hdr = list(header)
+        if rng.random() < 0.15:
+            hdr.insert(rng.randrange(len(hdr)), rng.choice(("#odd header line\n", "##FORMAT=<ID=XX>\n", "##extra=1\n")))
+        out.append("".join(hdr + pick))
+    return out
+
+
+def main_vcf():
+    spec = importlib.util.spec_from_file_location("ref_pg", os.path.join(REF, "predict-genotype.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "aln.json"), "w").write(read_golden("c1_informative_aln.json.gz"))
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            for text in damaged_vcfs(800):
+                with open("in.vcf", "w", newline="") as fh:
+                    fh.write(text)
+                if os.path.exists("out.vcf"):
+                    os.remove("out.vcf")
+                ms = random.Random(len(cases)).choice((3, 3, 1, 10))
+                buf = io.StringIO()
+                try:
+                    sys.argv = ["predict-genotype.py", "-d", "aln.json", "-v", "in.vcf", "-o", "out.vcf", "-ms", str(ms)]
+                    with redirect_stdout(buf), redirect_stderr(io.StringIO()):
+                        ref.main(sys.argv[1:])
+                    cases.append({"vcf": text, "ms": ms, "rc": 0, "out": open("out.vcf").read(), "stdout": buf.getvalue()})
+                except BaseException:
+                    cases.append({"vcf": text, "ms": ms, "rc": 1})
+        finally:
+            os.chdir(cwd)
+    with gzip.GzipFile(os.path.join(HERE, "fuzz_vcf.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(cases, ensure_ascii=True).encode())
+    print(len(cases), "vcf cases;", sum(c["rc"] for c in cases), "raise")
+
+
 if __name__ == "__main__":
     main()
+    main_vcf()

@@ -438,3 +438,27 @@ def test_damaged_lines_match_the_reference(gpu, tmp_path):
     out = tmp_path / "crlf.json"
     alnfilter.write_informative_json(t, raw, res, str(out))
     assert out.read_text() == fx["crlf"]["json"]
+
+
+def test_damaged_vcfs_match_the_reference(gpu):
+    """tests/golden/fuzz_vcf.json.gz: 800 small VCFs with one damaged body line, run through the UNMODIFIED
+    predict-genotype.py.  The host mirror + genotype kernel must fail where it exits with status 1 and
+    write the same text and count elsewhere."""
+    import io
+    alnfilter, capi, genotype, torch = gpu
+    counts = genotype.AlnCounts.from_memory(read_golden("c1_informative_aln.json.gz"))
+    cases = json.loads(read_golden("fuzz_vcf.json.gz"))
+    n_err = 0
+    for c in cases:
+        lines = list(io.StringIO(c["vcf"], newline=None))                 # text mode, like open()
+        try:
+            text, n = genotype.genotype_vcf_from_json(counts, lines, c["ms"], 0.00005)
+            failed = False
+        except (genotype.VcfError, capi.SvjgError, ValueError):
+            failed = True
+        assert failed == bool(c["rc"]), c["vcf"][-400:]
+        if not failed:
+            assert text == c["out"], c["vcf"][-400:]
+            assert f"Genotyped svs: {n}\n" == c["stdout"]
+        n_err += failed
+    assert n_err > 100

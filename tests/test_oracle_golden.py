@@ -103,3 +103,24 @@ def test_oracle_on_damaged_lines_matches_the_reference():
     # a file with CR LF line ends: same JSON as the reference, "\n" stored
     d = O.filter_alignments(O.text_mode_lines(fx["crlf"]["gaf"]), edges, alt)
     assert O.dumps_informative(d) == fx["crlf"]["json"]
+
+
+def test_oracle_on_damaged_vcfs_matches_the_reference():
+    """tests/golden/fuzz_vcf.json.gz: 800 small VCFs with one damaged body line each, run through the
+    unmodified predict-genotype.py with the c1 informative_aln.json.  Exit status, output text and the
+    'Genotyped svs' line must agree."""
+    import json
+    d = json.loads(read_golden("c1_informative_aln.json.gz"))
+    counts = {k: (len(v[0]), len(v[1])) for k, v in d.items()}
+    cases = json.loads(read_golden("fuzz_vcf.json.gz"))
+    assert len(cases) == 800 and 100 < sum(c["rc"] for c in cases) < 600
+    for c in cases:
+        try:
+            text, n = O.genotype_vcf(counts, O.text_mode_lines(c["vcf"]), c["ms"])
+            raised = False
+        except Exception:
+            raised = True
+        assert raised == bool(c["rc"]), c["vcf"][-400:]
+        if not raised:
+            assert text == c["out"], c["vcf"][-400:]
+            assert f"Genotyped svs: {n}\n" == c["stdout"]
