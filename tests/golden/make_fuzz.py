@@ -7,6 +7,7 @@ and otherwise the list lengths of its informative_aln.json.
     python tests/golden/make_fuzz.py            # build container only (needs /root/reference)
 """
 import gzip
+import hashlib
 import importlib.util
 import io
 import json
@@ -191,6 +192,71 @@ def main_vcf():
     print(len(cases), "vcf cases;", sum(c["rc"] for c in cases), "raise")
 
 
+def damaged_edges(n, seed=7):
+    """svs_edges.json of c1 with a few entries damaged: odd allele values, sv ids without ':', wrong
+    shapes.  Deterministic, shared with tests/test_oracle_golden.py."""
+    edges0 = json.loads(read_golden("c1_svs_edges.json"))
+    rng = random.Random(seed)
+    odd_alleles = [0, 1, 2, -1, -2, -3, True, False, None, "1", 1.0, [0]]
+    odd_ids = ["noColon", "", "a:b", 5, None, ["x:y"], "1:DEL-1-2"]
+    out = []
+    for _ in range(n):
+        e = json.loads(json.dumps(edges0))
+        keys = list(e)
+        for _ in range(rng.choice((1, 2, 4))):
+            k = rng.choice(keys)
+            m = rng.randrange(6)
+            if m == 0:
+                e[k][0][1] = rng.choice(odd_alleles)
+            elif m == 1:
+                e[k][0][0] = rng.choice(odd_ids)
+            elif m == 2:
+                e[k][0] = e[k][0] + [7]
+            elif m == 3:
+                e[k] = rng.choice((5, "ab", "abc", None, {}, {"x:y": 1}, [], [[]], "x"))
+            elif m == 4:
+                e[k].append(rng.choice((["9:ZZ-1", 0], ["bad", 1], "ab", 3)))
+            else:
+                e[k][0] = e[k][0][:1]
+        out.append(json.dumps(e))
+    return out
+
+
+def edges_gaf_lines():
+    return [l for l in read_golden("c1.gaf.gz").splitlines(True) if "cg:Z:" not in l][:150]
+
+
+def main_edges():
+    spec = importlib.util.spec_from_file_location("ref_filter", os.path.join(REF, "filter-alignments.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            open("p.gfa", "w").write(read_golden("c1.gfa.gz"))
+            open("p.gaf", "w").write("".join(edges_gaf_lines()))
+            for text in damaged_edges(300):
+                open("p_svs_edges.json", "w").write(text)
+                if os.path.exists("p_informative_aln.json"):
+                    os.remove("p_informative_aln.json")
+                try:
+                    sys.argv = ["filter-alignments.py", "-a", "p.gaf", "-g", "p.gfa", "-p", "p"]
+                    with redirect_stdout(io.StringIO()), redirect_stderr(io.StringIO()):
+                        ref.main(sys.argv[1:])
+                    js = open("p_informative_aln.json").read()
+                    cases.append({"rc": 0, "sha256": hashlib.sha256(js.encode()).hexdigest()})
+                except BaseException:
+                    cases.append({"rc": 1})
+        finally:
+            os.chdir(cwd)
+    with open(os.path.join(HERE, "fuzz_edges.json"), "w") as fh:
+        json.dump(cases, fh)
+    print(len(cases), "edges cases;", sum(c["rc"] for c in cases), "raise")
+
+
 if __name__ == "__main__":
     main()
     main_vcf()
+    main_edges()

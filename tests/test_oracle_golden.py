@@ -124,3 +124,30 @@ def test_oracle_on_damaged_vcfs_matches_the_reference():
         if not raised:
             assert text == c["out"], c["vcf"][-400:]
             assert f"Genotyped svs: {n}\n" == c["stdout"]
+
+
+def test_oracle_on_damaged_link_tables_matches_the_reference():
+    """tests/golden/fuzz_edges.json: 300 svs_edges.json variants with damaged entries (odd allele values,
+    sv ids without ':', wrong shapes; regenerated here from the same seed by make_fuzz.damaged_edges),
+    each run through the unmodified reference filter on 150 c1 lines: exit status and JSON hash."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    spec = importlib.util.spec_from_file_location("make_fuzz", os.path.join(os.path.dirname(__file__), "golden", "make_fuzz.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    alt = alt_len_from_gfa_text(read_golden("c1.gfa.gz"))
+    lines = mf.edges_gaf_lines()
+    want = json.loads(read_golden("fuzz_edges.json"))
+    texts = mf.damaged_edges(len(want))
+    assert len(want) == 300 and 50 < sum(c["rc"] for c in want) < 290
+    for text, c in zip(texts, want):
+        try:
+            js = O.dumps_informative(O.filter_alignments(lines, json.loads(text), alt))
+            raised = False
+        except Exception:
+            raised = True
+        assert raised == bool(c["rc"])
+        if not raised:
+            assert hashlib.sha256(js.encode()).hexdigest() == c["sha256"]
