@@ -462,3 +462,32 @@ def test_damaged_vcfs_match_the_reference(gpu):
             assert f"Genotyped svs: {n}\n" == c["stdout"]
         n_err += failed
     assert n_err > 100
+
+
+def test_damaged_link_tables_match_the_reference(gpu, tmp_path):
+    """tests/golden/fuzz_edges.json: 300 svs_edges.json variants with damaged entries, each run through the
+    UNMODIFIED reference filter on 150 c1 lines (tests/golden/make_fuzz.py regenerates the variants from
+    its seed): same exit status, same informative_aln.json bytes."""
+    import hashlib
+    import importlib.util
+    import os
+    alnfilter, capi, genotype, torch = gpu
+    spec = importlib.util.spec_from_file_location("make_fuzz", os.path.join(os.path.dirname(__file__), "golden", "make_fuzz.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    gfa = read_golden("c1.gfa.gz")
+    raw = "".join(mf.edges_gaf_lines()).encode()
+    want = json.loads(read_golden("fuzz_edges.json"))
+    out = tmp_path / "x.json"
+    for text, c in zip(mf.damaged_edges(len(want)), want):
+        t = alnfilter.Tables.from_memory(text, gfa).to_device(0)
+        try:
+            res = alnfilter.filter_host(t, raw)
+            alnfilter.write_informative_json(t, raw, res, str(out))
+            got = (0, hashlib.sha256(out.read_bytes()).hexdigest())
+        except alnfilter.InputError:
+            got = (1, None)
+        assert got[0] == c["rc"]
+        if not got[0]:
+            assert got[1] == c["sha256"]
+        t.close()
