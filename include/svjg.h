@@ -63,6 +63,13 @@ uint32_t svjg_tables_num_sv(const svjg_tables *t);
 uint32_t svjg_tables_num_links(const svjg_tables *t);     /* distinct link keys        */
 uint32_t svjg_tables_num_alt_nodes(const svjg_tables *t);
 uint64_t svjg_tables_device_bytes(const svjg_tables *t);  /* size of the device image  */
+/* alt_node_len[name] of filter-alignments.py:103-113 as the kernels will find it (the same hash
+ * probes, on the host copy of the tables): the sequence length, -1 when the GFA gave the name no
+ * length, -2 if the two node tables of the image disagree (never, short of a bug).  The GFA is read
+ * as the reference reads it: text mode ("\n", "\r\n" and a lone "\r" end a line), an 'S' line
+ * whose name has a '.' after its last ':' is an alt node, its length is len() of the third column
+ * of the right-stripped line; a damaged 'S' line the reference raises on is SVJG_E_INPUT. */
+int64_t svjg_tables_alt_node_len(const svjg_tables *t, const char *name, uint32_t len);
 /* sv id string of index i (not NUL terminated); NULL when i is out of range */
 const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len);
 /* index of an sv id, or UINT32_MAX — what `in_sv in dict` needs (predict-genotype.py:216) */

@@ -400,24 +400,45 @@ static inline bool py_space(unsigned char c) {
     return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f);
 }
 
+// str.rstrip() also removes the non-ASCII white space of Unicode; as UTF-8, ending at `e`: its length or 0
+static inline int py_space_utf8_before(const char *b, const char *e) {
+    const unsigned char *u = (const unsigned char *)e;
+    if (e - b >= 2 && u[-2] == 0xC2 && (u[-1] == 0x85 || u[-1] == 0xA0)) return 2;
+    if (e - b >= 3) {
+        const unsigned a = u[-3], m = u[-2], z = u[-1];
+        if (a == 0xE1 && m == 0x9A && z == 0x80) return 3;                                          // U+1680
+        if (a == 0xE2 && m == 0x80 && ((z >= 0x80 && z <= 0x8A) || z == 0xA8 || z == 0xA9 || z == 0xAF)) return 3;
+        if (a == 0xE2 && m == 0x81 && z == 0x9F) return 3;                                          // U+205F
+        if (a == 0xE3 && m == 0x80 && z == 0x80) return 3;                                          // U+3000
+    }
+    return 0;
+}
+
 static bool scan_gfa(const char *text, size_t len, std::vector<std::pair<std::string, int64_t>> &alts,
                      std::string &err) {
     std::unordered_map<std::string, size_t> seen;
     const char *p = text, *end = text + len;
+    // the reference reads the GFA in text mode: "\n", "\r\n" and a lone "\r" all end a line
+    const char *cr = (const char *)memchr(text, '\r', len);
     while (p < end) {
         const char *nl = (const char *)memchr(p, '\n', size_t(end - p));
-        const char *le = nl ? nl : end;            // line without '\n'
+        const char *le = nl ? nl : end;            // line without its line end
         const char *next = nl ? nl + 1 : end;
+        if (cr && cr < p) cr = (const char *)memchr(p, '\r', size_t(end - p));
+        if (cr && cr < le) {
+            le = cr;
+            next = (cr + 1 < end && cr[1] == '\n') ? cr + 2 : cr + 1;
+        }
         if (*p == 'S') {
             // cols of the raw line (with its newline, as the reference splits before stripping)
-            const char *t1 = (const char *)memchr(p, '\t', size_t(next - p));
+            const char *t1 = (const char *)memchr(p, '\t', size_t(le - p));
             if (!t1) {
                 err = "GFA: S line without a name column";
                 return false;
             }
             const char *name_b = t1 + 1;
-            const char *t2 = (const char *)memchr(name_b, '\t', size_t(next - name_b));
-            const char *name_e = t2 ? t2 : next;
+            const char *t2 = (const char *)memchr(name_b, '\t', size_t(le - name_b));
+            const char *name_e = t2 ? t2 : le;     // two columns: the name would keep the "\n", and [2] raises below
             // last ':' piece
             const char *q = name_e;
             while (q > name_b && q[-1] != ':') --q;
@@ -425,7 +446,15 @@ static bool scan_gfa(const char *text, size_t len, std::vector<std::pair<std::st
             if (alt) {
                 // line.rstrip().split("\t")[2]
                 const char *re = le;
-                while (re > p && py_space((unsigned char)re[-1])) --re;
+                for (;;) {
+                    if (re > p && py_space((unsigned char)re[-1])) {
+                        --re;
+                        continue;
+                    }
+                    const int k = py_space_utf8_before(p, re);
+                    if (!k) break;
+                    re -= k;
+                }
                 if (!t2 || t2 >= re) {   // fewer than 3 columns once stripped -> IndexError in the reference
                     err = "GFA: alt-node S line without a sequence column";
                     return false;
@@ -867,6 +896,37 @@ extern "C" uint32_t svjg_aln_counts_find(const svjg_aln_counts *c, const char *k
     auto it = std::lower_bound(c->keys.begin(), c->keys.end(), k);
     if (it == c->keys.end() || *it != k) return UINT32_MAX;
     return uint32_t(it - c->keys.begin());
+}
+
+extern "C" int64_t svjg_tables_alt_node_len(const svjg_tables *t, const char *name, uint32_t len) {
+    if (!t || (!name && len) || t->nodes.empty()) return -1;
+    // the probe the kernels make: token hash of the name, then the name bytes
+    const uint64_t h = node_hash(hash_bytes(name, len));
+    const uint32_t mask = uint32_t(t->nodes.size()) - 1;
+    int64_t found = -1;
+    for (uint32_t i = uint32_t(h) & mask; t->nodes[i].id1; i = (i + 1) & mask) {
+        const NodeSlot &s = t->nodes[i];
+        if (s.hash == h && s.name_len == len && (len == 0 || memcmp(t->blob.data() + s.name_off, name, len) == 0)) {
+            found = s.seq_len;
+            break;
+        }
+    }
+    // a plain name is resolved through its exact key on the fast path: both tables must agree
+    PNodeSlot k{};
+    if (plain_key(std::string(name ? name : "", len), k)) {
+        const uint32_t pmask = uint32_t(t->pnodes.size()) - 1;
+        int64_t pfound = -1;
+        for (uint32_t i = pnode_hash(k.c0, k.c1, k.a, k.b) & pmask; t->pnodes[i].id1; i = (i + 1) & pmask) {
+            const PNodeSlot &s = t->pnodes[i];
+            if (s.c0 == k.c0 && s.c1 == k.c1 && s.a == k.a && s.b == k.b) {
+                pfound = s.alt_len == PN_NO_LEN ? -1 : int64_t(s.alt_len);
+                break;
+            }
+        }
+        const int64_t want = (found > 0 && found <= 0x7FFFFFFF) ? found : -1;   // what the fast path may hold
+        if (pfound != want) return -2;
+    }
+    return found;
 }
 
 extern "C" int svjg_tables_from_memory(const char *edges_json, size_t edges_len, const char *gfa, size_t gfa_len,

@@ -73,6 +73,14 @@ class Tables:
         i = capi.lib.svjg_tables_find_sv(self._h, b, len(b))
         return None if i == capi.NO_SV else int(i)
 
+    def alt_node_len(self, name):
+        """``alt_node_len.get(name)`` of filter-alignments.py:103-113, read from the tables the kernels probe."""
+        b = name.encode("utf-8")
+        n = int(capi.lib.svjg_tables_alt_node_len(self._h, b, len(b)))
+        if n == -2:
+            raise capi.SvjgError("node tables disagree on " + repr(name))
+        return None if n < 0 else n
+
     def close(self):
         if self._h:
             capi.lib.svjg_tables_free(self._h)

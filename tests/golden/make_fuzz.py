@@ -255,8 +255,101 @@ def main_edges():
         json.dump(cases, fh)
     print(len(cases), "edges cases;", sum(c["rc"] for c in cases), "raise")
 
-
-if __name__ == "__main__":
-    main()
     main_vcf()
     main_edges()
+
+
+def damaged_gfas(n, seed=11):
+    """Small GFAs cut from c1.gfa (sequences of reference nodes shortened), a few lines damaged:
+    byte edits, columns dropped or doubled, odd white space (ASCII and Unicode), CR and CR LF line ends."""
+    src = read_golden("c1.gfa.gz").splitlines()
+    alt = [l for l in src if l.startswith("S") and "." in l.split("\t")[1]]
+    other = []
+    for l in src:
+        if l.startswith("S") and "." not in l.split("\t")[1]:
+            c = l.split("\t")
+            other.append("\t".join(c[:2] + [c[2][:24]]))
+        elif l.startswith(("L", "#")):
+            other.append(l[:200])
+        elif l.startswith("P"):
+            other.append(l[:120])
+    rng = random.Random(seed)
+    alphabet = "\t\t .:S-+ACGTacgt\r\x0b\x1c\xa0\u2003\u3000\x85é"
+    out = []
+    while len(out) < n:
+        lines = [rng.choice(alt) for _ in range(rng.choice((1, 2, 4)))] + [rng.choice(other) for _ in range(rng.choice((0, 2, 5)))]
+        rng.shuffle(lines)
+        for _ in range(rng.choice((0, 1, 1, 2, 3))):
+            j = rng.randrange(len(lines))
+            line = lines[j]
+            k = rng.randrange(8)
+            pos = rng.randrange(len(line) + 1)
+            cols = line.split("\t")
+            if k == 0 and pos < len(line):
+                line = line[:pos] + rng.choice(alphabet) + line[pos + 1:]
+            elif k == 1:
+                line = line[:pos] + rng.choice(alphabet) + line[pos:]
+            elif k == 2:
+                line = "\t".join(cols[:rng.randrange(len(cols) + 1)])
+            elif k == 3:
+                line = line + rng.choice((" ", "\t", " \t ", "\xa0", "\u2003\t", "\tLN:i:5", "\x1c", "é"))
+            elif k == 4 and len(cols) > 2:
+                cols[2] = rng.choice(("", "*", " ", "ACGT ", "ÀÉ", cols[2] + "\t" + cols[2], "A" * 300))
+                line = "\t".join(cols)
+            elif k == 5 and len(cols) > 1:
+                cols[1] = rng.choice(("", "x", "a.b", "chr1:5.1", "1:2:3.4", "chr1:5.1:7", ".", cols[1] + ".2", "é:1.1", "chr1:0123456789.1"))
+                line = "\t".join(cols)
+            elif k == 6:
+                line = rng.choice(("S", "Sx", "", "S\t", "S\t\t", "SEQ\tchr1:9.9\tAC")) + (line[pos:] if rng.random() < 0.5 else "")
+            else:
+                lines.insert(j, line)                       # the same node twice: the last length wins
+            lines[j] = line
+        eol = rng.choice(("\n", "\n", "\n", "\r\n", "\r"))
+        text = eol.join(lines) + rng.choice((eol, eol, ""))
+        out.append(text)
+    return out
+
+
+def main_gfa():
+    """alt_node_len as the unmodified reference builds it (filter-alignments.py:103-113): main() is run
+    on an empty GAF and the local dictionary is read from its frame when it returns."""
+    spec = importlib.util.spec_from_file_location("ref_filter", os.path.join(REF, "filter-alignments.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    seen = {}
+
+    def prof(frame, event, arg):
+        if event == "return" and frame.f_code.co_name == "main" and frame.f_code.co_filename.endswith("filter-alignments.py"):
+            seen["alt"] = dict(frame.f_locals.get("alt_node_len") or {})
+
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            open("p.gaf", "w").write("")
+            open("p_svs_edges.json", "w").write("{}")
+            for text in damaged_gfas(1200):
+                with open("p.gfa", "w", newline="") as fh:
+                    fh.write(text)
+                seen.clear()
+                try:
+                    sys.argv = ["filter-alignments.py", "-a", "p.gaf", "-g", "p.gfa", "-p", "p"]
+                    sys.setprofile(prof)
+                    try:
+                        with redirect_stdout(io.StringIO()), redirect_stderr(io.StringIO()):
+                            ref.main(sys.argv[1:])
+                    finally:
+                        sys.setprofile(None)
+                    cases.append({"gfa": text, "rc": 0, "alt": seen["alt"]})
+                except BaseException:
+                    cases.append({"gfa": text, "rc": 1})
+        finally:
+            os.chdir(cwd)
+    with gzip.GzipFile(os.path.join(HERE, "fuzz_gfa.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(cases, ensure_ascii=True).encode())
+    print(len(cases), "gfa cases;", sum(c["rc"] for c in cases), "raise;", sum(len(c.get("alt", ())) for c in cases), "alt nodes")
+
+
+if __name__ == "__main__":
+    {"lines": main, "vcf": main_vcf, "edges": main_edges, "gfa": main_gfa}[sys.argv[1] if len(sys.argv) > 1 else "lines"]()

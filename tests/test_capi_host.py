@@ -119,3 +119,28 @@ def test_translate_newlines_is_text_mode():
     for text in ("a\r\nb\r\n", "a\rb\nc", "\r\r\n\n\r", "x\ty\r"):
         want = "".join(io.StringIO(text, newline=None))
         assert bytes(alnfilter.translate_newlines(text.encode())) == want.encode()
+
+
+def test_gfa_loader_on_damaged_gfas_matches_the_reference():
+    """tests/golden/fuzz_gfa.json.gz: 1200 small GFAs with damaged lines (columns dropped, odd white
+    space, CR / CR LF line ends, repeated nodes), each loaded by the unmodified reference filter
+    (tests/golden/make_fuzz.py gfa; its alt_node_len dictionary read from the frame of main()).  The C
+    loader must refuse exactly the files the reference raises on and hold the same length under every
+    name, in the tables the kernels probe (svjg_tables_alt_node_len)."""
+    cases = json.loads(read_golden("fuzz_gfa.json.gz"))
+    assert len(cases) == 1200 and 50 < sum(c["rc"] for c in cases) < 600
+    n_names = 0
+    for c in cases:
+        try:
+            t = alnfilter.Tables.from_memory("{}", c["gfa"])
+        except capi.SvjgError as exc:
+            assert c["rc"] == 1, (c["gfa"], str(exc))
+            continue
+        assert c["rc"] == 0, c["gfa"]
+        assert t.num_alt_nodes == len(c["alt"]), c["gfa"]
+        for name, n in c["alt"].items():
+            assert t.alt_node_len(name) == n, (c["gfa"], name)
+            n_names += 1
+        assert t.alt_node_len("chr1:1-2") is None and t.alt_node_len("") is None
+        t.close()
+    assert n_names > 1500

@@ -151,3 +151,22 @@ def test_oracle_on_damaged_link_tables_matches_the_reference():
         assert raised == bool(c["rc"])
         if not raised:
             assert hashlib.sha256(js.encode()).hexdigest() == c["sha256"]
+
+
+def test_oracle_gfa_loader_on_damaged_gfas_matches_the_reference(tmp_path):
+    """tests/golden/fuzz_gfa.json.gz (see tests/test_capi_host.py): the oracle's loader must raise where
+    the reference's does and build the same alt_node_len dictionary elsewhere."""
+    import json
+    cases = json.loads(read_golden("fuzz_gfa.json.gz"))
+    p = tmp_path / "g.gfa"
+    for c in cases:
+        with open(p, "w", newline="") as fh:
+            fh.write(c["gfa"])
+        try:
+            got = O.load_alt_node_len(str(p))
+            raised = False
+        except Exception:
+            raised = True
+        assert raised == bool(c["rc"]), c["gfa"]
+        if not raised:
+            assert got == c["alt"], c["gfa"]
