@@ -47,15 +47,20 @@ def _load_tables(prefix, gfa_file, device_ready=None):
 
 def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None):
     """filter-alignments.py:119-175.  Returns (FilterResult, page-locked GAF bytes)."""
-    from . import alnfilter, capi
+    from . import alnfilter, capi, gzio
     if dover_given:
         # -O leaves a list in d_over and `int >= list` raises at the first overlap test (:269);
         # count every test the reference would make
         tables.set_flags(capi.FLAG_EXACT_CHECKS)
     if gaf is None:
-        gaf = alnfilter.read_file_pinned(gaf_file)
-        if alnfilter.translate_newlines(gaf) is not gaf:                   # carriage returns: text-mode line ends
-            gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
+        with open(gaf_file, "rb") as fh:
+            head = fh.read(2)
+        if gzio.is_gzip(head):                                              # extension: gzip / bgzip input
+            gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gzio.read_bytes(gaf_file)))
+        else:
+            gaf = alnfilter.read_file_pinned(gaf_file)
+            if alnfilter.translate_newlines(gaf) is not gaf:               # carriage returns: text-mode line ends
+                gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
     res = alnfilter.filter_host(tables, gaf)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
@@ -78,11 +83,10 @@ def filter_main(argv=None):
     out_json = args.prefix + "_informative_aln.json"
     if args.outputDir:
         out_json = "/".join([args.outputDir, out_json])
-    from . import alnfilter, capi
-    import numpy as np
+    from . import alnfilter, capi, gzio
     try:
         ready = _start_device()
-        raw = np.fromfile(args.gaf[0], dtype=np.uint8)                     # read while the context comes up
+        raw = gzio.read_bytes(args.gaf[0])                                 # read (gzip / bgzip: inflate) while the context comes up
         raw = alnfilter.translate_newlines(raw)                            # text-mode line ends, like the reference
         tables = _load_tables(args.prefix, args.gfa[0], ready)
         gaf = alnfilter.RegisteredBytes(raw)                                # page-lock in place
@@ -103,13 +107,12 @@ def genotype_main(argv=None):
     args = ap.parse_args(argv)
     output = "genotype_results.txt" if args.output is None else args.output[0]
     e = args.err[0] if args.err is not None else 0.00005
-    from . import capi, genotype
+    from . import capi, genotype, gzio
     try:
         ready = _start_device()
         counts = genotype.AlnCounts.load(args.aln[0])
         ready()
-        with open(args.vcf) as fh:
-            lines = fh.readlines()
+        lines = gzio.read_text_lines(args.vcf)
         with open(output, "w") as out:          # the reference opens the output before it reads the VCF (:92)
             text, n = genotype.genotype_vcf_from_json(counts, lines, args.minsupport, e)
             out.write(text)
@@ -149,7 +152,7 @@ def pipeline_main(svjg_dir, argv=None):
         sys.exit("Failed to map the reads on the graph.\nExiting SVJedi-graph.")
 
     print("Filtering alignment file...")
-    from . import alnfilter, capi, genotype
+    from . import alnfilter, capi, genotype, gzio
     try:
         tables = _load_tables(args.prefix, out_gfa)
         res, _gaf = _filter_to_json(tables, out_gaf, args.prefix + "_informative_aln.json")
@@ -159,8 +162,7 @@ def pipeline_main(svjg_dir, argv=None):
 
     print("Genotyping SVs...")
     try:
-        with open(args.vcf) as fh:
-            lines = fh.readlines()
+        lines = gzio.read_text_lines(args.vcf)
         with open(args.prefix + "_genotype.vcf", "w") as out:
             text, n = genotype.genotype_vcf(tables, res.counts, lines, args.minsupport)
             out.write(text)

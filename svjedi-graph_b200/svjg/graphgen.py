@@ -336,8 +336,15 @@ def load_fasta(path):
     lone CR end lines; the name is the first word of the header; a header followed by no sequence is
     dropped unless it is the last one), without a Python-level loop over the lines."""
     import re
-    with open(path, "r") as fh:
-        text = fh.read()
+    from . import gzio
+    with open(path, "rb") as fh:
+        head = fh.read(2)
+    if gzio.is_gzip(head):                          # extension (row N4): gzip / bgzip FASTA
+        import io
+        text = io.TextIOWrapper(io.BytesIO(gzio.read_bytes(path).tobytes())).read()
+    else:
+        with open(path, "r") as fh:
+            text = fh.read()
     heads = [m.start() for m in re.finditer(r"^>", text, re.M)]
     if not heads or text[:heads[0]].replace("\n", "") != "":
         # sequence lines in front of the first header, or no header at all
@@ -379,8 +386,8 @@ def construct_main(argv=None):
     try:
         seqs = load_fasta(args.ref[0])
         g = Graph(OrderedDict((c, len(s)) for c, s in seqs.items()), seqs, warn=print)
-        with open(args.vcf[0], "r") as fh:
-            g.parse(fh)
+        from . import gzio
+        g.parse(gzio.read_text_lines(args.vcf[0]))          # open(vcf).readlines(); a gzip / bgzip VCF is inflated (row N4)
     except stops as exc:
         stop(exc)
     with open(f"{prefix}ignored_svs.txt", "w") as fh:

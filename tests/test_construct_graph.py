@@ -118,3 +118,19 @@ def test_script_default_output_names(tmp_path):
     p = subprocess.run([sys.executable, os.path.join(PKG, "construct-graph.py"), "-v", "v.vcf", "-r", "missing.fa"],
                        cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode == 1
+
+
+def test_compressed_inputs_give_the_same_files(tmp_path, monkeypatch):
+    """Extension (row N4): a gzip VCF / FASTA gives the bytes the plain files give."""
+    import gzip as gz
+    monkeypatch.chdir(tmp_path)
+    with gz.open(os.path.join(GOLDEN, "fuzz_graph.json.gz")) as fh:
+        fix = json.loads(fh.read())
+    case = next(c for c in fix["cases"] if c["rc"] == 0 and c["vcf"].count("\n") > 20)
+    fa, vcf = fix["fastas"][case["fa"]].encode(), case["vcf"].encode()
+    (tmp_path / "x.fa.gz").write_bytes(gz.compress(fa))
+    (tmp_path / "x.vcf.gz").write_bytes(gz.compress(vcf))
+    rc, out, msg = _run(["-v", "x.vcf.gz", "-r", "x.fa.gz", "-o", "x.gfa"])
+    assert rc == 0 and out == case["stdout"], msg
+    for f in OUT_FILES:
+        assert _sha(f) == case["files"][f], f
