@@ -31,6 +31,7 @@ extern "C" {
 #define SVJG_E_INPUT 5         /* input on which the reference raises (exit status 1) */
 #define SVJG_E_HITS_OVERFLOW 6 /* hit buffers too small: re-run with >= n_hits slots  */
 #define SVJG_E_NOMEM 7
+#define SVJG_E_UNSUPPORTED 8   /* a spelling this library does not reproduce (see svjg_vcf_parse)  */
 
 /* reason codes stored in svjg_filter_stats.status when a GAF line would make the
  * reference raise */
@@ -221,6 +222,37 @@ uint32_t svjg_aln_counts_num(const svjg_aln_counts *c);
 const char *svjg_aln_counts_key(const svjg_aln_counts *c, uint32_t i, uint32_t *len);
 const uint32_t *svjg_aln_counts_data(const svjg_aln_counts *c);
 uint32_t svjg_aln_counts_find(const svjg_aln_counts *c, const char *key, uint32_t len);
+
+/* ---- VCF keys and VCF text (host) ---------------------------------------------
+ * Replaces the per-record string work of decision_vcf (predict-genotype.py:100-271) around the
+ * genotype kernel: svjg_vcf_parse builds, for every body line, the key the reference looks up
+ * (:118-211: "chr:DEL-pos-END", "chr:INS-pos-k" with k counted per POS string over all chromosomes,
+ * "chr:INV-pos-END", "chr:BND-" + ALT with the REF base replaced by POS, "wrong_format") and the
+ * svtype code svjg_genotype_* expects (bit 7 = |length| < 50, :216), keeps the header lines in place
+ * (##FORMAT lines dropped, the four FORMAT lines and the column header written for the "#C" line,
+ * :102-115) and the first eight columns of the line (:250-256).  `translate_cr` != 0 reads the
+ * bytes as text mode does ("\r\n" and a lone "\r" end a line and become "\n"), 0 takes "\n" only
+ * (lines already split by the caller).  SVJG_E_INPUT where the reference raises (fewer than 8
+ * columns, a missing END=, a non-integer POS/END, a one-piece BND ALT); SVJG_E_UNSUPPORTED for a file
+ * with non-ASCII bytes or a POS/END of more than 18 digits (Python's len() / int() semantics are not
+ * reproduced for those: use the caller's own string handling).
+ * svjg_vcf_index_tables: sv_index[i] for counters that come from the filter (key -> rank among the
+ * tables' sv ids).  svjg_vcf_index_counts: the same against an informative_aln.json, plus the
+ * svtype array with bit 6 set where the key is present (:216); SVJG_E_INPUT if a gated key's entry is
+ * not a pair of lists (:219-226 raises).
+ * svjg_vcf_format: the output file's bytes (:248-271) from the kernel's gt / flags / ad2 / pl arrays,
+ * in a buffer to release with svjg_buffer_free; *n_genotyped = the "Genotyped svs" count (:275). */
+typedef struct svjg_vcf svjg_vcf;
+int svjg_vcf_parse(const char *text, size_t len, int translate_cr, svjg_vcf **out);
+void svjg_vcf_free(svjg_vcf *v);
+uint32_t svjg_vcf_num_records(const svjg_vcf *v);
+const uint8_t *svjg_vcf_svtype(const svjg_vcf *v);
+const char *svjg_vcf_key(const svjg_vcf *v, uint32_t i, uint32_t *len);   /* NULL: the record has no key */
+int svjg_vcf_index_tables(const svjg_vcf *v, const svjg_tables *t, uint32_t *sv_index);
+int svjg_vcf_index_counts(const svjg_vcf *v, const svjg_aln_counts *c, uint32_t *sv_index, uint8_t *svtype);
+int svjg_vcf_format(const svjg_vcf *v, const uint8_t *gt, const uint8_t *flags, const uint32_t *ad2,
+                    const int64_t *pl, char **out, uint64_t *out_len, uint64_t *n_genotyped);
+void svjg_buffer_free(char *p);
 
 /* ---- output (host) ------------------------------------------------------------
  * Replaces filter-alignments.py:174-175: writes json.dumps(dict, sort_keys=True,

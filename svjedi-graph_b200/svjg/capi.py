@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsvjg.so")
 
-OK, E_CUDA, E_ARG, E_IO, E_JSON, E_INPUT, E_HITS_OVERFLOW, E_NOMEM = range(8)
+OK, E_CUDA, E_ARG, E_IO, E_JSON, E_INPUT, E_HITS_OVERFLOW, E_NOMEM, E_UNSUPPORTED = range(9)
 GT_GENOTYPED, GT_HALVED_0, GT_HALVED_1, GT_NEED_K = 1, 2, 4, 8
 NO_SV = 0xFFFFFFFF
 FLAG_EXACT_CHECKS, FLAG_FORCE_GENERAL = 1, 2
@@ -93,6 +93,16 @@ def _load():
         "svjg_aln_counts_key": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "svjg_aln_counts_data": (C.c_void_p, [vp]),
         "svjg_aln_counts_find": (C.c_uint32, [vp, C.c_char_p, C.c_uint32]),
+        "svjg_vcf_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+        "svjg_vcf_free": (None, [vp]),
+        "svjg_vcf_num_records": (C.c_uint32, [vp]),
+        "svjg_vcf_svtype": (C.c_void_p, [vp]),
+        "svjg_vcf_key": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "svjg_vcf_index_tables": (C.c_int, [vp, vp, u32p]),
+        "svjg_vcf_index_counts": (C.c_int, [vp, vp, u32p, u8p]),
+        "svjg_vcf_format": (C.c_int, [vp, u8p, u8p, u32p, i64p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint64)]),
+        "svjg_buffer_free": (None, [vp]),
         "svjg_emit_informative_json": (C.c_int, [vp, u8p, C.c_uint64, u32p, u64p, u32p, C.c_uint64, C.c_char_p]),
     }
     for name, (res, args) in sig.items():

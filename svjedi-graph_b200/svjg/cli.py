@@ -112,10 +112,9 @@ def genotype_main(argv=None):
         ready = _start_device()
         counts = genotype.AlnCounts.load(args.aln[0])
         ready()
-        lines = gzio.read_text_lines(args.vcf)
-        with open(output, "w") as out:          # the reference opens the output before it reads the VCF (:92)
-            text, n = genotype.genotype_vcf_from_json(counts, lines, args.minsupport, e)
-            out.write(text)
+        lines = gzio.read_bytes(args.vcf)                      # the file's bytes: keys and text are built by the library
+        with open(output, "wb") as out:         # the reference opens the output before it reads the VCF (:92)
+            _, n = genotype.genotype_vcf_from_json(counts, lines, args.minsupport, e, out=out)
     except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
         _die(str(exc))
     print(f"Genotyped svs: {n}")
@@ -162,10 +161,9 @@ def pipeline_main(svjg_dir, argv=None):
 
     print("Genotyping SVs...")
     try:
-        lines = gzio.read_text_lines(args.vcf)
-        with open(args.prefix + "_genotype.vcf", "w") as out:
-            text, n = genotype.genotype_vcf(tables, res.counts, lines, args.minsupport)
-            out.write(text)
+        lines = gzio.read_bytes(args.vcf)                      # the file's bytes: keys and text are built by the library
+        with open(args.prefix + "_genotype.vcf", "wb") as out:
+            _, n = genotype.genotype_vcf(tables, res.counts, lines, args.minsupport, out=out)
     except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
         sys.stderr.write(f"svjg: {exc}\n")
         sys.exit("Failed to predict the genotypes.\nExiting SVJedi-graph.")

@@ -118,6 +118,119 @@ def parse_vcf(lines):
     return header, recs
 
 
+class NativeVcf:
+    """svjg_vcf_* (csrc/vcf.cpp): the keys, svtype codes and output text of a whole VCF without a
+    Python-level loop over its records.  :func:`parse_vcf` / :func:`format_vcf` state the same rules
+    line by line and take over for the spellings the library declines (non-ASCII bytes, POS/END of
+    more than 18 digits)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        self.n = int(capi.lib.svjg_vcf_num_records(self._h))
+
+    @classmethod
+    def parse(cls, data, translate_cr=True):
+        """``data``: bytes of the file.  None if the library declines the file; VcfError where the
+        reference raises."""
+        h = C.c_void_p()
+        rc = capi.lib.svjg_vcf_parse(data, len(data), 1 if translate_cr else 0, C.byref(h))
+        if rc == capi.E_UNSUPPORTED:
+            return None
+        if rc == capi.E_INPUT:
+            raise VcfError(capi.lib.svjg_last_error().decode("utf-8", "replace"))
+        capi.check(rc)
+        return cls(h.value)
+
+    @classmethod
+    def from_input(cls, vcf):
+        """From what the callers hold: the file's bytes (bytes / bytearray / uint8 array: read as text
+        mode reads them) or a list of lines as ``readlines()`` gives them."""
+        if isinstance(vcf, np.ndarray):
+            return cls.parse(vcf.tobytes(), True)
+        if isinstance(vcf, (bytes, bytearray, memoryview)):
+            return cls.parse(bytes(vcf), True)
+        lines = vcf if isinstance(vcf, list) else list(vcf)
+        for i, line in enumerate(lines):
+            # joined and cut at "\n" again these must give the same lines
+            if line.find("\n") != len(line) - 1 and not (i == len(lines) - 1 and "\n" not in line and line):
+                return None
+        try:
+            data = "".join(lines).encode("ascii")
+        except UnicodeEncodeError:
+            return None
+        return cls.parse(data, False)
+
+    @property
+    def svtype(self):
+        if not self.n:
+            return np.zeros(0, np.uint8)
+        p = capi.lib.svjg_vcf_svtype(self._h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(self.n,)).copy()
+
+    def key(self, i):
+        n = C.c_uint32()
+        p = capi.lib.svjg_vcf_key(self._h, i, C.byref(n))
+        return None if not p else C.string_at(p, n.value).decode("ascii")
+
+    def index_tables(self, tables):
+        idx = np.empty(max(self.n, 1), np.uint32)
+        capi.check(capi.lib.svjg_vcf_index_tables(self._h, tables._h, idx.ctypes.data))
+        return idx[:self.n]
+
+    def index_counts(self, aln_counts):
+        idx = np.empty(max(self.n, 1), np.uint32)
+        ty = np.empty(max(self.n, 1), np.uint8)
+        rc = capi.lib.svjg_vcf_index_counts(self._h, aln_counts._h, idx.ctypes.data, ty.ctypes.data)
+        if rc == capi.E_INPUT:
+            raise VcfError(capi.lib.svjg_last_error().decode("utf-8", "replace"))
+        capi.check(rc)
+        return idx[:self.n], ty[:self.n]
+
+    def format(self, gt, flags, ad2, pl, out=None):
+        """(text, number of genotyped SVs) — predict-genotype.py:248-275.  With ``out`` (a binary
+        file object) the bytes go straight to it and the text returned is None."""
+        gt = np.ascontiguousarray(gt, dtype=np.uint8)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        ad2 = np.ascontiguousarray(ad2, dtype=np.uint32)
+        pl = np.ascontiguousarray(pl, dtype=np.int64)
+        if not (len(gt) == len(flags) == len(ad2) == len(pl) == self.n):
+            raise ValueError("result arrays do not match the number of VCF records")
+        buf, n_out, n_gt = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib.svjg_vcf_format(self._h, gt.ctypes.data, flags.ctypes.data, ad2.ctypes.data, pl.ctypes.data,
+                                            C.byref(buf), C.byref(n_out), C.byref(n_gt)))
+        try:
+            if out is not None:
+                text = None
+                if n_out.value:
+                    out.write(memoryview((C.c_char * n_out.value).from_address(buf.value)))
+            else:
+                text = C.string_at(buf.value, n_out.value).decode("ascii")
+        finally:
+            capi.lib.svjg_buffer_free(buf)
+        return text, int(n_gt.value)
+
+    def close(self):
+        if self._h:
+            capi.lib.svjg_vcf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_lines(vcf):
+    """Lines as ``open(path).readlines()`` gives them, for the line-by-line statement of the rules."""
+    if isinstance(vcf, np.ndarray):
+        vcf = vcf.tobytes()
+    if isinstance(vcf, (bytes, bytearray, memoryview)):
+        import io
+        return io.TextIOWrapper(io.BytesIO(bytes(vcf))).readlines()
+    return vcf
+
+
 def _num(twice, halved):
     if not halved:
         return str(twice >> 1)
@@ -242,24 +355,41 @@ def format_vcf(header, recs, gt, flags, ad2, pl):
     return "".join(out), genotyped
 
 
-def genotype_vcf(tables, d_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR):
+def _run_kernel(counts, idx, ty, n, min_support, e):
+    if not n:
+        return np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros((0, 2), np.uint32), np.zeros((0, 3), np.int64)
+    if isinstance(counts, np.ndarray):                            # counters on the host: no tensor library needed
+        return genotype_host(counts, idx, ty, min_support, e)
+    return genotype_device(counts, idx, ty, min_support, e)
+
+
+def _emit(text_n, out):
+    """The line-by-line statement returns text: written as the text-mode file of the reference would."""
+    text, n = text_n
+    if out is None:
+        return text, n
+    import io
+    w = io.TextIOWrapper(out, write_through=True)
+    w.write(text)
+    w.detach()
+    return None, n
+
+
+def genotype_vcf(tables, d_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR, out=None):
     """decision_vcf (predict-genotype.py:89-279).  ``d_counts``: the filter's counters, a torch int32
-    tensor on the device or a numpy uint32 array on the host.  Returns (vcf text, number of
-    genotyped SVs)."""
-    header, recs = parse_vcf(vcf_lines)
+    tensor on the device or a numpy uint32 array on the host.  ``vcf_lines``: the VCF as a list of
+    lines, or the bytes of the file.  Returns (vcf text, number of genotyped SVs); with ``out`` (a
+    binary file object) the text is written there instead of being returned."""
+    v = NativeVcf.from_input(vcf_lines)
+    if v is not None:
+        gt, flags, ad2, pl = _run_kernel(d_counts, v.index_tables(tables), v.svtype, v.n, min_support, e)
+        return v.format(gt, flags, ad2, pl, out)
+    header, recs = parse_vcf(_as_lines(vcf_lines))
     idx = np.fromiter((capi.NO_SV if r[2] is None else (lambda j: capi.NO_SV if j is None else j)(tables.find_sv(r[2]))
                        for r in recs), dtype=np.uint32, count=len(recs))
     ty = np.fromiter((r[1] for r in recs), dtype=np.uint8, count=len(recs))
-    if len(recs):
-        if isinstance(d_counts, np.ndarray):                      # counters on the host: no tensor library needed
-            gt, flags, ad2, pl = genotype_host(d_counts, idx, ty, min_support, e)
-        else:
-            gt, flags, ad2, pl = genotype_device(d_counts, idx, ty, min_support, e)
-    else:
-        gt = flags = np.zeros(0, np.uint8)
-        ad2 = np.zeros((0, 2), np.uint32)
-        pl = np.zeros((0, 3), np.int64)
-    return format_vcf(header, recs, gt, flags, ad2, pl)
+    gt, flags, ad2, pl = _run_kernel(d_counts, idx, ty, len(recs), min_support, e)
+    return _emit(format_vcf(header, recs, gt, flags, ad2, pl), out)
 
 
 class AlnCounts:
@@ -313,11 +443,17 @@ class AlnCounts:
             pass
 
 
-def genotype_vcf_from_json(aln_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR, device=0):
+def genotype_vcf_from_json(aln_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR, device=0, out=None):
     """decision_vcf (predict-genotype.py:89-279) with the counters taken from an
     informative_aln.json, as the stand-alone reference stage does.  A key that is
     present gates the SV in even when both of its lists are empty (:216)."""
-    header, recs = parse_vcf(vcf_lines)
+    counts = aln_counts.counts if aln_counts.num else np.zeros((1, 2), np.uint32)
+    v = NativeVcf.from_input(vcf_lines)
+    if v is not None:
+        idx, ty = v.index_counts(aln_counts)
+        gt, flags, ad2, pl = _run_kernel(counts, idx, ty, v.n, min_support, e)
+        return v.format(gt, flags, ad2, pl, out)
+    header, recs = parse_vcf(_as_lines(vcf_lines))
     n = len(recs)
     idx = np.full(n, capi.NO_SV, dtype=np.uint32)
     ty = np.fromiter((r[1] for r in recs), dtype=np.uint8, count=n)
@@ -333,11 +469,5 @@ def genotype_vcf_from_json(aln_counts, vcf_lines, min_support=MIN_SUPPORT, e=ERR
         idx[i] = j
         if ty[i] != 255:
             ty[i] |= 0x40
-    if n:
-        gt, flags, ad2, pl = genotype_host(aln_counts.counts if aln_counts.num else np.zeros((1, 2), np.uint32), idx, ty,
-                                           min_support, e)
-    else:
-        gt = flags = np.zeros(0, np.uint8)
-        ad2 = np.zeros((0, 2), np.uint32)
-        pl = np.zeros((0, 3), np.int64)
-    return format_vcf(header, recs, gt, flags, ad2, pl)
+    gt, flags, ad2, pl = _run_kernel(counts, idx, ty, n, min_support, e)
+    return _emit(format_vcf(header, recs, gt, flags, ad2, pl), out)
