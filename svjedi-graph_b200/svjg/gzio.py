@@ -8,6 +8,7 @@ members) as one stream — and everything behind the reader sees the bytes of th
 from __future__ import annotations
 
 import os
+import stat
 import struct
 import zlib
 from concurrent.futures import ThreadPoolExecutor
@@ -114,7 +115,11 @@ def inflate(buf, threads=None):
 
 def read_bytes(path, threads=None):
     """The file as a uint8 array; inflated when it starts with the gzip magic."""
-    raw = np.fromfile(path, dtype=np.uint8)
+    if stat.S_ISREG(os.stat(path).st_mode):
+        raw = np.fromfile(path, dtype=np.uint8)
+    else:                                            # a pipe (`minigraph ... | filter-alignments.py -a /dev/stdin`): no size to ask for
+        with open(path, "rb") as fh:
+            raw = np.frombuffer(bytearray(fh.read()), dtype=np.uint8)
     if raw.size >= 2 and is_gzip(raw):
         return inflate(raw, threads)
     return raw
@@ -123,11 +128,5 @@ def read_bytes(path, threads=None):
 def read_text_lines(path):
     """``open(path).readlines()`` (text mode: universal newlines, locale encoding) for a plain or
     compressed file — what predict-genotype.py:95-96 iterates over."""
-    with open(path, "rb") as fh:
-        head = fh.read(2)
-    if is_gzip(head):
-        import io
-        data = read_bytes(path)
-        return io.TextIOWrapper(io.BytesIO(data.tobytes())).readlines()
-    with open(path) as fh:
-        return fh.readlines()
+    import io
+    return io.TextIOWrapper(io.BytesIO(read_bytes(path).tobytes())).readlines()

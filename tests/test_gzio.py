@@ -88,3 +88,20 @@ def test_text_lines_like_open(tmp_path):
     b.write_bytes(gzip.compress(text.encode()))
     want = ["##h\n", "#c\tp\n", "chr1\t5\n", "last"]
     assert gzio.read_text_lines(str(a)) == want == gzio.read_text_lines(str(b))
+
+
+def test_reads_from_a_pipe(tmp_path, gaf):
+    """`minigraph ... | filter-alignments.py -a /dev/stdin`: the reader must not ask a pipe for its size."""
+    import os
+    import threading
+    fifo = str(tmp_path / "p.fifo")
+    os.mkfifo(fifo)
+    for payload in (gaf[:200000], gzip.compress(gaf[:200000])):
+        def feed(data=payload):
+            with open(fifo, "wb") as fh:
+                fh.write(data)
+        th = threading.Thread(target=feed)
+        th.start()
+        got = gzio.read_bytes(fifo)
+        th.join()
+        assert got.tobytes() == gaf[:200000] and got.flags.writeable
