@@ -11,6 +11,7 @@
 #include <cstring>
 #include <fstream>
 #include <unordered_map>
+#include <unordered_set>
 
 namespace svjg {
 
@@ -72,6 +73,7 @@ struct JsonIn {
         while (p < end) {
             unsigned char c = (unsigned char)*p++;
             if (c == '"') return true;
+            if (c < 0x20) return fail("control character in a string");     // json.load is strict about these
             if (c != '\\') {
                 out.push_back(char(c));
                 continue;
@@ -106,6 +108,19 @@ struct JsonIn {
         }
         return fail("unterminated string");
     }
+    // any byte below 0x20 (json.load rejects them inside strings), eight bytes a step
+    static bool has_control(const char *b, size_t n) {
+        size_t i = 0;
+        uint64_t hit = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint64_t w;
+            memcpy(&w, b + i, 8);
+            // bytes < 0x20: the top three bits are clear
+            hit |= ~(w | (w << 1) | (w << 2)) & 0x8080808080808080ull;
+        }
+        for (; i < n; ++i) hit |= uint64_t((unsigned char)b[i] < 0x20);
+        return hit != 0;
+    }
     // a string whose content is not needed (the GAF lines of informative_aln.json: hundreds of MB):
     // jump from quote to quote; a quote is the end unless an odd number of backslashes precedes it.
     // Escapes are still checked as string() would, so that a malformed file fails the same way.
@@ -121,6 +136,7 @@ struct JsonIn {
             size_t nb = 0;
             while (e - nb > p + 1 && e[-1 - long(nb)] == '\\') ++nb;
             if (nb % 2 == 0) {
+                if (has_control(p + 1, size_t(e - p - 1))) return fail("control character in a string");
                 // validate the escapes of [p+1, e)
                 for (const char *b = static_cast<const char *>(memchr(p + 1, '\\', size_t(e - p - 1))); b;) {
                     const char esc = b[1];
@@ -220,22 +236,28 @@ struct JsonIn {
             kind = K_FLOAT;
             return true;
         }
-        // number
+        // number, by json's own pattern  -?(0|[1-9]\d*)(\.\d+)?([eE][-+]?\d+)?  : a part that is not complete
+        // is left unread and trips the delimiter check of the caller, as in the reference
         const char *s = p;
         bool is_float = false;
         if (p < end && *p == '-') ++p;
         if (p >= end || *p < '0' || *p > '9') return fail("bad value");
-        while (p < end && *p >= '0' && *p <= '9') ++p;
-        if (p < end && *p == '.') {
+        if (*p == '0') ++p;
+        else
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        if (end - p >= 2 && *p == '.' && p[1] >= '0' && p[1] <= '9') {
             is_float = true;
             ++p;
             while (p < end && *p >= '0' && *p <= '9') ++p;
         }
         if (p < end && (*p == 'e' || *p == 'E')) {
-            is_float = true;
-            ++p;
-            if (p < end && (*p == '+' || *p == '-')) ++p;
-            while (p < end && *p >= '0' && *p <= '9') ++p;
+            const char *q = p + 1;
+            if (q < end && (*q == '+' || *q == '-')) ++q;
+            if (q < end && *q >= '0' && *q <= '9') {
+                is_float = true;
+                while (q < end && *q >= '0' && *q <= '9') ++q;
+                p = q;
+            }
         }
         kind = is_float ? K_FLOAT : K_INT;
         if (!is_float && ival) {
@@ -738,6 +760,7 @@ static bool iter_len(JsonIn &in, uint32_t &n) {
         ++sub.p;
         sub.ws();
         if (sub.p < sub.end && *sub.p == '}') return true;
+        std::unordered_set<std::string> seen;                  // a repeated key is one key of the dict
         for (;;) {
             std::string key;
             sub.ws();
@@ -746,7 +769,7 @@ static bool iter_len(JsonIn &in, uint32_t &n) {
             ++sub.p;                      // ':'
             JsonIn::Kind kk;
             if (!sub.skip_value(kk)) return true;
-            ++n;                          // duplicate keys collapse in a dict; rare enough to ignore here
+            if (seen.insert(key).second) ++n;
             sub.ws();
             if (sub.p < sub.end && *sub.p == ',') {
                 ++sub.p;

@@ -351,5 +351,92 @@ def main_gfa():
     print(len(cases), "gfa cases;", sum(c["rc"] for c in cases), "raise;", sum(len(c.get("alt", ())) for c in cases), "alt nodes")
 
 
+def damaged_jsons(n, seed=23):
+    """informative_aln.json files as a user (or another tool) could hand them to predict-genotype.py: the
+    c1 dictionary with short stand-in strings for the GAF lines (only the list lengths matter, :219-226),
+    then odd values, escapes, repeated keys and byte-level damage."""
+    base = json.loads(read_golden("c1_informative_aln.json.gz"))
+    base = {k: [[f"r{i}\tx\n" for i in range(len(v[0]))], [f"a{i}\n" for i in range(len(v[1]))]] for k, v in base.items()}
+    keys = sorted(base)
+    rng = random.Random(seed)
+    odd_values = ['"xyz"', '"x"', '""', '5', 'null', 'true', '[]', '[[]]', '[[],[]]', '[[], [], 5]', '{"0": [], "1": []}', '[5, []]',
+                  '["ab", "c"]', '["é€", ""]', '[{"x":1,"x":2,"y":3}, [1,2,3]]', '[[1e5, -0.5, true, null, {"k": [1]}], [[[]]]]',
+                  '[[NaN, Infinity], [-Infinity]]', '[[01],[]]', '[[1.],[]]', '[[1.5e],[]]', '[[-0, 0.0e0, 1E+2],[]]', '[["\t"],[]]',
+                  '[["\\t\\u00e9\\ud83d\\ude00"],["\\ud800"]]', '[["\\x"],[]]', '[[1,],[]]', '[[1 2],[]]', '[["a" "b"],[]]',
+                  '[null, null]', '[[], null]', '[3.5, "abc"]', '{"a": 1}', '[[], {"p": 1, "q": 2}]', '[["x"],["y"]] ', '[["x"]\r\n,\t["y"]]']
+    alphabet = '"\\,:[]{}019eE.+-tfn \t\n\x01\xe9'
+    out = []
+    while len(out) < n:
+        d = dict(base)
+        text_keys = {}
+        for _ in range(rng.choice((0, 1, 2, 3))):
+            k = rng.choice(keys)
+            m = rng.randrange(5)
+            if m == 0:
+                text_keys[k] = rng.choice(odd_values)
+            elif m == 1:                                   # the key spelled with escapes
+                text_keys[k] = None
+            elif m == 2:
+                d.pop(k, None)
+            elif m == 3:
+                d[k] = [d[k][0][: rng.randrange(4)], d[k][1][: rng.randrange(4)]] if k in d else [[], []]
+            else:
+                d[k + rng.choice(("", " ", "x"))] = [[], []]
+        parts = []
+        for k in rng.sample(sorted(d), len(d)) if rng.random() < 0.3 else sorted(d):
+            ks = json.dumps(k)
+            if k in text_keys and text_keys[k] is None:
+                j = rng.randrange(len(k))
+                ks = '"' + k[:j] + "\\u%04x" % ord(k[j]) + k[j + 1:] + '"'
+            v = text_keys[k] if text_keys.get(k) is not None else json.dumps(d[k])
+            parts.append(ks + ": " + v)
+            if rng.random() < 0.03:                        # the same key again: the last one wins
+                parts.append(ks + ": " + rng.choice(('[[],[]]', '[["q"],["q","q"]]', '7')))
+        text = "{" + rng.choice((", ", ",\n    ")).join(parts) + "}" + rng.choice(("", "\n", " "))
+        if rng.random() < 0.35:
+            for _ in range(rng.choice((1, 1, 2))):
+                pos = rng.randrange(len(text) + 1)
+                k = rng.randrange(3)
+                if k == 0 and pos < len(text):
+                    text = text[:pos] + rng.choice(alphabet) + text[pos + 1:]
+                elif k == 1 and pos < len(text):
+                    text = text[:pos] + text[pos + 1:]
+                else:
+                    text = text[:pos] + rng.choice(alphabet) + text[pos:]
+        out.append(text)
+    return out
+
+
+def main_json():
+    spec = importlib.util.spec_from_file_location("ref_pg", os.path.join(REF, "predict-genotype.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            open("in.vcf", "w").write(read_golden("c1.vcf"))
+            for text in damaged_jsons(600):
+                with open("aln.json", "w", newline="") as fh:
+                    fh.write(text)
+                if os.path.exists("out.vcf"):
+                    os.remove("out.vcf")
+                buf = io.StringIO()
+                try:
+                    sys.argv = ["predict-genotype.py", "-d", "aln.json", "-v", "in.vcf", "-o", "out.vcf"]
+                    with redirect_stdout(buf), redirect_stderr(io.StringIO()):
+                        ref.main(sys.argv[1:])
+                    cases.append({"in": hashlib.sha256(text.encode()).hexdigest()[:12], "rc": 0,
+                                  "sha256": hashlib.sha256(open("out.vcf", "rb").read()).hexdigest(), "stdout": buf.getvalue()})
+                except BaseException:
+                    cases.append({"in": hashlib.sha256(text.encode()).hexdigest()[:12], "rc": 1})
+        finally:
+            os.chdir(cwd)
+    with open(os.path.join(HERE, "fuzz_json.json"), "w") as fh:      # the inputs are regenerated from the seed (damaged_jsons)
+        json.dump(cases, fh)
+    print(len(cases), "json cases;", sum(c["rc"] for c in cases), "raise;", len({c.get("sha256") for c in cases}), "distinct outputs")
+
+
 if __name__ == "__main__":
-    {"lines": main, "vcf": main_vcf, "edges": main_edges, "gfa": main_gfa}[sys.argv[1] if len(sys.argv) > 1 else "lines"]()
+    {"lines": main, "vcf": main_vcf, "edges": main_edges, "gfa": main_gfa, "json": main_json}[sys.argv[1] if len(sys.argv) > 1 else "lines"]()

@@ -201,3 +201,37 @@ def test_predict_genotype_command_line_wiring(tmp_path, monkeypatch, capsys, com
     (tmp_path / "u.vcf").write_bytes(vcf.replace(b"##fileformat", "##note=é\n##fileformat".encode(), 1))
     assert cli.genotype_main(["-d", "a.json", "-v", "u.vcf", "-o", "u_out.vcf"]) == 0
     assert (tmp_path / "u_out.vcf").read_text() == "##note=é\n" + read_golden("c1_genotype.vcf")
+
+
+def test_damaged_informative_aln_json_matches_the_reference():
+    """tests/golden/fuzz_json.json: 600 informative_aln.json variants (odd values, escapes in keys, repeated
+    keys, byte damage; regenerated here from the seed by make_fuzz.damaged_jsons), each run through the
+    unmodified predict-genotype.py with c1.vcf.  The library's JSON reader + VCF side (kernel: stand-in)
+    must stop exactly where the reference exits 1 and write the same file elsewhere."""
+    import hashlib
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_fuzz", os.path.join(os.path.dirname(__file__), "golden", "make_fuzz.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    want = json.loads(read_golden("fuzz_json.json"))
+    texts = mf.damaged_jsons(len(want))
+    vcf = read_golden("c1.vcf").encode()
+    n_stop = 0
+    for text, c in zip(texts, want):
+        assert hashlib.sha256(text.encode()).hexdigest()[:12] == c["in"]          # same inputs as when the fixture was made
+        try:
+            aln = genotype.AlnCounts.from_memory(text)
+            v = genotype.NativeVcf.from_input(vcf)
+            idx, ty = v.index_counts(aln)
+            counts = aln.counts if aln.num else np.zeros((1, 2), np.uint32)
+            out = v.format(*stand_in_genotype_host(counts, idx, ty))
+            failed = False
+        except (capi.SvjgError, genotype.VcfError):
+            failed = True
+        assert failed == bool(c["rc"]), text[:300]
+        n_stop += failed
+        if not failed:
+            assert hashlib.sha256(out[0].encode()).hexdigest() == c["sha256"], text[:300]
+            assert f"Genotyped svs: {out[1]}\n" == c["stdout"]
+    assert 100 < n_stop < 500
