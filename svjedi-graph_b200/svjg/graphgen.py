@@ -94,6 +94,10 @@ class Graph:
     def edges_json(self):
         return json.dumps(self.link_sv, sort_keys=True, indent=4)
 
+    def link_sv_as_json(self):
+        """The table as ``json.load`` of the file gives it back (tuples become lists)."""
+        return {k: [[sv, a] for sv, a in v] for k, v in self.link_sv.items()}
+
     def write_edges_json(self, fh):
         """The bytes of ``json.dumps(d_link_sv, sort_keys=True, indent=4)`` (construct-graph.py:553-554)
         without the pure-Python indenting encoder: one formatted block per key."""

@@ -1,0 +1,83 @@
+"""svjedi-graph.py's wiring end to end on the CPU: the drop-in construct-graph.py runs for real, minigraph
+is a stub that prints a synthetic GAF, and the two GPU calls (filter, genotype) are replaced by oracle
+stand-ins — so every file the orchestrator handles (svjedi-graph.py:84-128) is produced and checked
+against the oracle's own run of the same stages.  The GPU version of this test is
+tests/test_cli_and_json.py::test_pipeline_front_end_with_stub_tools."""
+import io
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from conftest import PKG, alt_len_from_gfa_text
+from oracle import svjg_oracle as O
+from svjg import alnfilter, cli, genotype, graphgen, synth
+from test_vcf_native import stand_in_genotype_host
+
+
+def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd):
+    rng = np.random.Generator(np.random.PCG64(3))
+    chrom_len = OrderedDict((("chr1", 60000), ("chr2", 40000)))
+    seqs = OrderedDict((c, rng.choice(np.frombuffer(b"ACGT", dtype="S1"), size=n).tobytes().decode()) for c, n in chrom_len.items())
+    (tmp_path / "ref.fa").write_text("".join(f">{c} test\n{s}\n" for c, s in seqs.items()))
+    rows = synth.catalogue("mix", 60, chrom_len, 11, ins_max=300, del_max=900)
+    vcf = synth.vcf_text(rows)
+    (tmp_path / "in.vcf").write_text(vcf)
+    g = graphgen.build_graph(chrom_len, rows)
+    gaf = synth.simulate_gaf(g, 1500, seed=5, mean_len=4000)
+    (tmp_path / "reads.gaf").write_text(gaf)
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    mg = bindir / "minigraph"
+    mg.write_text(f"#!/bin/sh\ncat {tmp_path}/reads.gaf\n")
+    mg.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{bindir}:{os.environ['PATH']}")
+    monkeypatch.delenv("SVJG_CONSTRUCT_GRAPH", raising=False)
+    (tmp_path / "reads.fq").write_text("")
+    prefix = str(tmp_path / "run")
+
+    def load_tables(pfx, gfa_file, device_ready=None):               # host half of cli._load_tables
+        return alnfilter.Tables.load(pfx + "_svs_edges.json", gfa_file)
+
+    def filter_host(tables, gaf_bytes, **kw):                         # svjg_filter_host's contract, by the oracle
+        edges = json.load(open(prefix + "_svs_edges.json"))
+        alt = alt_len_from_gfa_text(open(prefix + ".gfa").read())
+        counts = np.zeros((tables.num_sv, 2), np.uint32)
+        sv2, off, ln = [], [], []
+        pos = 0
+        for line in bytes(alnfilter._as_u8(gaf_bytes)).decode().splitlines(True):
+            for sv, allele in O.record_hits(line, edges, alt):
+                i = tables.find_sv(sv)
+                counts[i, allele] += 1
+                sv2.append(2 * i + allele)
+                off.append(pos)
+                ln.append(len(line))
+            pos += len(line)
+        stats = {"n_hits": len(sv2), "n_checks": 0}
+        return alnfilter.FilterResult(counts, stats, np.array(sv2, np.uint32), np.array(off, np.uint64), np.array(ln, np.uint32))
+
+    monkeypatch.setattr(cli, "_load_tables", load_tables)
+    monkeypatch.setattr(alnfilter, "filter_host", filter_host)
+    monkeypatch.setattr(alnfilter, "read_file_pinned", lambda path: np.fromfile(path, dtype=np.uint8))
+    monkeypatch.setattr(genotype, "genotype_host", stand_in_genotype_host)
+    monkeypatch.chdir(tmp_path)
+    assert cli.pipeline_main(PKG, ["-v", "in.vcf", "-r", "ref.fa", "-q", "reads.fq", "-p", prefix]) == 0
+    out = capfd.readouterr().out
+
+    # the graph stage wrote the reference's three files (this builder, with sequences)
+    g2 = graphgen.build_graph(chrom_len, rows, seqs)
+    buf = io.StringIO()
+    g2.write_gfa(buf)
+    assert open(prefix + ".gfa").read() == buf.getvalue()
+    assert open(prefix + "_svs_edges.json").read() == g2.edges_json()
+    assert open(prefix + "_ignored_svs.txt").read() == g2.ignored_text()
+    assert open(prefix + ".gaf").read() == gaf
+    # stages 3-4 against the oracle's own run
+    d = O.filter_alignments(gaf.splitlines(True), g2.link_sv_as_json(), alt_len_from_gfa_text(buf.getvalue()))
+    assert open(prefix + "_informative_aln.json").read() == O.dumps_informative(d)
+    text, n = O.genotype_vcf(O.hit_counts(d), vcf.splitlines(True))
+    assert n > 10
+    assert open(prefix + "_genotype.vcf").read() == text
+    assert out == ("Constructing variation graph...\nMapping reads on graph...\nFiltering alignment file...\n"
+                   f"Genotyping SVs...\nGenotyped svs: {n}\n")
