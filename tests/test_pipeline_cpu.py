@@ -81,3 +81,56 @@ def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd):
     assert open(prefix + "_genotype.vcf").read() == text
     assert out == ("Constructing variation graph...\nMapping reads on graph...\nFiltering alignment file...\n"
                    f"Genotyping SVs...\nGenotyped svs: {n}\n")
+
+
+def test_filter_command_line_wiring(tmp_path, monkeypatch):
+    """filter-alignments.py's front-end around the GPU call (stand-in): -p/-o file naming, gzip input,
+    CR LF line ends read as text mode reads them, and the two flag defects kept from the reference."""
+    import gzip
+    import pytest
+    from conftest import read_golden
+    edges_text, gfa_text = read_golden("c1_svs_edges.json"), read_golden("c1.gfa.gz")
+    edges, alt = json.loads(edges_text), alt_len_from_gfa_text(gfa_text)
+    lines = [l for l in read_golden("c1.gaf.gz").splitlines(True) if "cg:Z:" not in l][:300]
+    want = O.dumps_informative(O.filter_alignments(lines, edges, alt))
+    (tmp_path / "p_svs_edges.json").write_text(edges_text)
+    (tmp_path / "p.gfa").write_text(gfa_text)
+    (tmp_path / "p.gaf").write_text("".join(lines))
+    (tmp_path / "crlf.gaf.gz").write_bytes(gzip.compress("".join(lines).replace("\n", "\r\n").encode()))
+    (tmp_path / "out").mkdir()
+
+    def filter_host(tables, gaf_bytes, **kw):
+        counts = np.zeros((tables.num_sv, 2), np.uint32)
+        sv2, off, ln = [], [], []
+        pos = n_checks = 0
+        for line in bytes(alnfilter._as_u8(gaf_bytes)).decode().splitlines(True):
+            for sv, allele in O.record_hits(line, edges, alt):
+                i = tables.find_sv(sv)
+                counts[i, allele] += 1
+                sv2.append(2 * i + allele)
+                off.append(pos)
+                ln.append(len(line))
+                n_checks += 1
+            pos += len(line)
+        return alnfilter.FilterResult(counts, {"n_hits": len(sv2), "n_checks": n_checks}, np.array(sv2, np.uint32),
+                                      np.array(off, np.uint64), np.array(ln, np.uint32))
+
+    monkeypatch.setattr(cli, "_start_device", lambda: (lambda: None))
+    monkeypatch.setattr(cli, "_load_tables", lambda pfx, gfa, ready=None: alnfilter.Tables.load(pfx + "_svs_edges.json", gfa))
+    monkeypatch.setattr(alnfilter, "filter_host", filter_host)
+    # page-locking needs the CUDA runtime: keep the wrapper, skip the registration
+    monkeypatch.setattr(alnfilter.RegisteredBytes, "__init__", lambda self, array: (setattr(self, "array", array), setattr(self, "_reg", False)) and None)
+    monkeypatch.chdir(tmp_path)
+    assert cli.filter_main(["-a", "p.gaf", "-g", "p.gfa", "-p", "p"]) == 0
+    assert (tmp_path / "p_informative_aln.json").read_text() == want
+    assert cli.filter_main(["-a", "crlf.gaf.gz", "-g", "p.gfa", "-p", "p", "-o", "out"]) == 0
+    assert (tmp_path / "out" / "p_informative_aln.json").read_text() == want
+    with pytest.raises(SystemExit) as exc:                       # no -p: the reference never finds its link table (:95)
+        cli.filter_main(["-a", "p.gaf", "-g", "p.gfa"])
+    assert exc.value.code == 1
+    with pytest.raises(SystemExit) as exc:                       # -O: TypeError at the first overlap test (:269)
+        cli.filter_main(["-a", "p.gaf", "-g", "p.gfa", "-p", "p", "-O", "50"])
+    assert exc.value.code == 1
+    with pytest.raises(SystemExit) as exc:
+        cli.filter_main(["-a", "missing.gaf", "-g", "p.gfa", "-p", "p"])
+    assert exc.value.code == 1
