@@ -152,7 +152,7 @@ class NativeVcf:
         lines = vcf if isinstance(vcf, list) else list(vcf)
         for i, line in enumerate(lines):
             # joined and cut at "\n" again these must give the same lines
-            if line.find("\n") != len(line) - 1 and not (i == len(lines) - 1 and "\n" not in line and line):
+            if not line or (line.find("\n") != len(line) - 1 and not (i == len(lines) - 1 and "\n" not in line)):
                 return None
         try:
             data = "".join(lines).encode("ascii")

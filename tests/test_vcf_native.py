@@ -146,6 +146,7 @@ def test_declined_spellings_fall_to_the_python_statement():
     assert genotype.NativeVcf.from_input((head + "1\t7\ta\tN\t<DEL>\t.\t.\tSVTYPE=DEL;END=" + "9" * 19 + "\n").encode()) is None
     assert genotype.NativeVcf.from_input(["a\nb\n"]) is None            # not lines as readlines() gives them
     assert genotype.NativeVcf.from_input(["a", "b\n"]) is None
+    assert genotype.NativeVcf.from_input(["##h\n", ""]) is None            # an empty string is a (bad) line for the line-by-line rules
     assert genotype.NativeVcf.from_input([]).n == 0
     assert genotype.NativeVcf.from_input(b"").format(np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros((0, 2), np.uint32),
                                                      np.zeros((0, 3), np.int64)) == ("", 0)
