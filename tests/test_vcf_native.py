@@ -236,3 +236,49 @@ def test_damaged_informative_aln_json_matches_the_reference():
             assert hashlib.sha256(out[0].encode()).hexdigest() == c["sha256"], text[:300]
             assert f"Genotyped svs: {out[1]}\n" == c["stdout"]
     assert 100 < n_stop < 500
+
+
+# ---- the same fixtures through the real genotype kernel (torch-free path of the command lines) ----
+@pytest.mark.gpu
+def test_golden_and_damaged_vcfs_on_the_device():
+    aln = genotype.AlnCounts.from_memory(read_golden("c1_informative_aln.json.gz"))
+    vcf = read_golden("c1.vcf")
+    for src in (vcf.encode(), vcf.splitlines(True)):
+        assert genotype.genotype_vcf_from_json(aln, src) == (read_golden("c1_genotype.vcf"), int(read_golden("c1_stdout.txt").split()[-1]))
+        assert genotype.genotype_vcf_from_json(aln, src, 40, 0.001)[0] == read_golden("c1_genotype_ms40_e1e-3.vcf")
+    cases = json.loads(read_golden("fuzz_vcf.json.gz"))
+    n_err = 0
+    for c in cases:
+        try:
+            text, n = genotype.genotype_vcf_from_json(aln, c["vcf"].encode(), c["ms"], 0.00005)
+            failed = False
+        except (genotype.VcfError, capi.SvjgError, ValueError):
+            failed = True
+        assert failed == bool(c["rc"]), c["vcf"][-300:]
+        n_err += failed
+        if not failed:
+            assert text == c["out"], c["vcf"][-300:]
+            assert f"Genotyped svs: {n}\n" == c["stdout"]
+    assert n_err > 100
+
+
+@pytest.mark.gpu
+def test_damaged_informative_aln_json_on_the_device():
+    import hashlib
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_fuzz", os.path.join(os.path.dirname(__file__), "golden", "make_fuzz.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    want = json.loads(read_golden("fuzz_json.json"))
+    vcf = read_golden("c1.vcf").encode()
+    for text, c in zip(mf.damaged_jsons(len(want)), want):
+        try:
+            out = genotype.genotype_vcf_from_json(genotype.AlnCounts.from_memory(text), vcf)
+            failed = False
+        except (capi.SvjgError, genotype.VcfError):
+            failed = True
+        assert failed == bool(c["rc"]), text[:300]
+        if not failed:
+            assert hashlib.sha256(out[0].encode()).hexdigest() == c["sha256"], text[:300]
+            assert f"Genotyped svs: {out[1]}\n" == c["stdout"]
