@@ -114,3 +114,28 @@ def test_pipeline_front_end_with_stub_tools(tmp_path):
     assert open(prefix + "_genotype.vcf").read() == read_golden("c1_genotype.vcf")
     assert r.stdout.endswith(read_golden("c1_stdout.txt"))
     assert "Constructing variation graph...\nMapping reads on graph...\nFiltering alignment file...\nGenotyping SVs...\n" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["s2", "s3", "s4"])
+def test_front_ends_on_scaled_configs(tmp_path, tag):
+    """The three scaled-down BASELINE.json shapes through the command lines (no tensor library in these
+    processes): informative_aln.json by its SHA-256, genotype VCF and stdout byte for byte; the GAF and
+    the VCF are handed over gzip-compressed for s3 (extension, svjg/gzio.py)."""
+    import gzip
+    import hashlib
+    p = _write_inputs(tmp_path, tag)
+    gaf, vcf = p + ".gaf", p + ".vcf"
+    if tag == "s3":
+        for f in (gaf, vcf):
+            with open(f, "rb") as src, open(f + ".gz", "wb") as dst:
+                dst.write(gzip.compress(src.read(), 1))
+        gaf, vcf = gaf + ".gz", vcf + ".gz"
+    r = _run("filter-alignments.py", "-a", gaf, "-g", p + ".gfa", "-p", p)
+    assert r.returncode == 0, r.stderr
+    with open(p + "_informative_aln.json", "rb") as fh:
+        assert hashlib.sha256(fh.read()).hexdigest() == read_golden(f"{tag}_informative_aln.sha256").strip()
+    r = _run("predict-genotype.py", "-d", p + "_informative_aln.json", "-v", vcf, "-o", p + "_genotype.vcf")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == read_golden(f"{tag}_stdout.txt")
+    assert open(p + "_genotype.vcf").read() == read_golden(f"{tag}_genotype.vcf.gz")
