@@ -1,0 +1,50 @@
+"""BASELINE.json's C2 at FULL size (25 k SVs, 3 M records, 0.5 GB) bit for bit: every counter and every
+hit tuple of the CUDA path against the C restatement of the reference filter (oracle/svjg_oracle.c,
+pinned on the reference's outputs by tests/test_c_oracle.py), and the genotype VCF from those counters.
+Runs last (file name) and loads no tensor library.  SVJG_TEST_FULL_SCALE shrinks it for a quick run."""
+import io
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, alt_len_from_gfa_text
+from oracle import svjg_oracle as O
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C2"])
+def test_full_size_exact_against_the_c_oracle(name):
+    from svjg import alnfilter, genotype, synth
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    from oracle import c_oracle as CO
+    scale = float(os.environ.get("SVJG_TEST_FULL_SCALE", "1.0"))
+    g, vcf, gaf_text = synth.make_workload(name, scale=scale)
+    buf = io.StringIO()
+    g.write_gfa(buf)
+    edges_text, gfa_text = g.edges_json(), buf.getvalue()
+    gaf = gaf_text.encode()
+    del gaf_text
+    # checker
+    ct = CO.Tables(json.loads(edges_text), alt_len_from_gfa_text(gfa_text))
+    want_counts, want_stats, w_sv2, w_off, w_len = CO.filter_counts(ct, gaf, want_hits=True)
+    # CUDA path through the C ABI, host buffers
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text).to_device(0)
+    assert t.sv_ids == ct.sv_ids
+    res = alnfilter.filter_host(t, gaf)
+    assert res.stats["n_records"] == want_stats["n_records"] == gaf.count(b"\n")
+    assert res.stats["n_multi"] == want_stats["n_multi"]
+    assert res.n_hits == want_stats["n_hits"] > 1000 * scale
+    assert (res.counts == want_counts).all()
+    # the hit tuples: the kernels append in any order, the reference in file order
+    got = np.stack([res.hit_off.astype(np.uint64), res.hit_sv2.astype(np.uint64), res.hit_len.astype(np.uint64)])
+    want = np.stack([w_off.astype(np.uint64), w_sv2.astype(np.uint64), w_len.astype(np.uint64)])
+    got = got[:, np.lexsort(got[::-1])]
+    want = want[:, np.lexsort(want[::-1])]
+    assert (got == want).all()
+    # genotypes from those counters: the VCF text against the line-by-line oracle
+    text, n = genotype.genotype_vcf(t, res.counts, vcf.encode())
+    assert (text, n) == O.genotype_vcf(CO.counts_dict(ct, want_counts), vcf.splitlines(True))
+    assert n > 100 * scale
