@@ -163,6 +163,42 @@ def cpu_baseline(gaf_text, edges_text, gfa_text, vcf_text, n_sample):
     return len(lines), t1 - t0, t2 - t1, n_gt
 
 
+def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None):
+    """The C restatement of the reference filter (oracle/svjg_oracle.c) on the host cores: filter only
+    (no JSON text, no genotypes), one thread and all threads.  An extra line of context beside
+    cpu_baseline — the reference itself is single-threaded Python — never the thing measured."""
+    try:
+        import subprocess
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        from oracle import c_oracle as CO
+        alt = {}
+        for line in gfa_text.splitlines(True):
+            if line.startswith("S"):
+                c = line.split("\t")
+                if "." in c[1].split(":")[-1]:
+                    alt[c[1]] = len(line.rstrip().split("\t")[2])
+        t = CO.Tables(json.loads(edges_text), alt)
+        if n_sample:
+            pos = 0
+            for _ in range(n_sample):
+                j = gaf_text.find("\n", pos)
+                if j < 0:
+                    break
+                pos = j + 1
+            gaf_text = gaf_text[:pos]
+        gaf = gaf_text.encode()
+        n_rec = gaf.count(b"\n")
+        cores = min(32, os.cpu_count() or 1)
+        out = {"unit": UNIT, "kind": "port (C)", "records": n_rec, "what": "oracle/svjg_oracle.c, filter + counters + hit tuples only"}
+        for label, th in (("one_thread", 1), ("all_threads", cores)):
+            t0 = time.perf_counter()
+            _c, st = CO.filter_counts(t, gaf, threads=th)
+            out[label] = {"value": st["n_records"] / (time.perf_counter() - t0), "threads": th}
+        return out
+    except Exception as exc:                      # context only: never fails the bench
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+
 _SHARD = {}
 
 
@@ -232,6 +268,7 @@ def run_reference(args):
                                    f"{n_rec} records, plus genotyping all {n_vcf} SVs once per step; oracle/svjg_oracle.py "
                                    "(the reference itself is single-threaded)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline_c": cpu_baseline_c("".join(lines), edges_text, gfa_text),
     }
     print(json.dumps(line), flush=True)
 
@@ -484,6 +521,7 @@ def main():
                          "sample": f"first {sample_n} records of the batch (filter + json.dumps {tf:.2f}s) projected to "
                                    f"{n_rec} records, plus genotyping all {n_sv} SVs ({tg:.2f}s); oracle/svjg_oracle.py, "
                                    "single thread like the reference"},
+        "cpu_baseline_c": cpu_baseline_c(gaf, edges_text, gfa_text) if rank == 0 else None,
         "e2e": {"value": job_rec * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke},
         "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
