@@ -14,8 +14,13 @@ from conftest import ROOT, alt_len_from_gfa_text
 from oracle import svjg_oracle as O
 
 
+# C2 is the configuration the metric is quoted on; SVJG_TEST_FULL_ALL=1 adds the other single-GPU shapes
+# (C3: 100 k clustered SVs / 6 M records with long paths, C4: 20 k BND / 3 M records) — minutes of generation.
+NAMES = ["C2", "C3", "C4"] if os.environ.get("SVJG_TEST_FULL_ALL") else ["C2"]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["C2"])
+@pytest.mark.parametrize("name", NAMES)
 def test_full_size_exact_against_the_c_oracle(name):
     from svjg import alnfilter, genotype, synth
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
