@@ -163,10 +163,12 @@ def cpu_baseline(gaf_text, edges_text, gfa_text, vcf_text, n_sample):
     return len(lines), t1 - t0, t2 - t1, n_gt
 
 
-def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None):
+def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None, check=None):
     """The C restatement of the reference filter (oracle/svjg_oracle.c) on the host cores: filter only
     (no JSON text, no genotypes), one thread and all threads.  An extra line of context beside
-    cpu_baseline — the reference itself is single-threaded Python — never the thing measured."""
+    cpu_baseline — the reference itself is single-threaded Python — never the thing measured.
+    ``check`` = (sv ids, counters [num_sv, 2], number of hits) of the GPU path for the same batch: the
+    whole batch is then compared counter by counter (key "parity")."""
     try:
         import subprocess
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
@@ -192,8 +194,14 @@ def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None):
         out = {"unit": UNIT, "kind": "port (C)", "records": n_rec, "what": "oracle/svjg_oracle.c, filter + counters + hit tuples only"}
         for label, th in (("one_thread", 1), ("all_threads", cores)):
             t0 = time.perf_counter()
-            _c, st = CO.filter_counts(t, gaf, threads=th)
+            counts, st = CO.filter_counts(t, gaf, threads=th)
             out[label] = {"value": st["n_records"] / (time.perf_counter() - t0), "threads": th}
+        if check is not None:
+            ids, got, n_hits = check
+            same = list(ids) == list(t.sv_ids) and got.shape == counts.shape and bool((got == counts).all()) \
+                and int(n_hits) == st["n_hits"]
+            out["parity"] = {"ok": same, "checked": f"all {n_rec} records of rank 0's batch: {counts.shape[0]} x 2 counters and the "
+                                                     f"number of hits ({st['n_hits']}) against the C oracle, bit for bit"}
         return out
     except Exception as exc:                      # context only: never fails the bench
         return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
@@ -521,7 +529,7 @@ def main():
                          "sample": f"first {sample_n} records of the batch (filter + json.dumps {tf:.2f}s) projected to "
                                    f"{n_rec} records, plus genotyping all {n_sv} SVs ({tg:.2f}s); oracle/svjg_oracle.py, "
                                    "single thread like the reference"},
-        "cpu_baseline_c": cpu_baseline_c(gaf, edges_text, gfa_text) if rank == 0 else None,
+        "cpu_baseline_c": cpu_baseline_c(gaf, edges_text, gfa_text, check=(tables.sv_ids, res.counts, res.n_hits)),
         "e2e": {"value": job_rec * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke},
         "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
