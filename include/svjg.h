@@ -71,6 +71,9 @@ uint64_t svjg_tables_device_bytes(const svjg_tables *t);  /* size of the device 
  * whose name has a '.' after its last ':' is an alt node, its length is len() of the third column
  * of the right-stripped line; a damaged 'S' line the reference raises on is SVJG_E_INPUT. */
 int64_t svjg_tables_alt_node_len(const svjg_tables *t, const char *name, uint32_t len);
+/* FNV-1a over the whole host image (hash tables, name blob, entries, sv ids, flags): two handles with
+ * the same value upload the same bytes (regression hook for the table builder) */
+uint64_t svjg_tables_image_hash(const svjg_tables *t);
 /* sv id string of index i (not NUL terminated); NULL when i is out of range */
 const char *svjg_tables_sv_id(const svjg_tables *t, uint32_t i, uint32_t *len);
 /* index of an sv id, or UINT32_MAX — what `in_sv in dict` needs (predict-genotype.py:216) */

@@ -8,12 +8,29 @@
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <string_view>
 #include <unordered_map>
 #include <unordered_set>
 
 namespace svjg {
+
+// SVJG_TIMING=1: wall clock of the host stages on stderr (profiling hook, no effect on results)
+struct StageTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    StageTimer() : on(getenv("SVJG_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "svjg timing: %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 
 // ---------------------------------------------------------------------------
 // a small strict JSON reader (only what svs_edges.json needs, but any valid
@@ -69,6 +86,15 @@ struct JsonIn {
     bool string(std::string &out) {
         out.clear();
         if (p >= end || *p != '"') return fail("expected string");
+        // nearly every string of these files has no escape: one memchr to the closing quote, one copy
+        if (const char *q = static_cast<const char *>(memchr(p + 1, '"', size_t(end - p - 1)))) {
+            const size_t n = size_t(q - p - 1);
+            if (!memchr(p + 1, '\\', n) && !has_control(p + 1, n)) {
+                out.assign(p + 1, n);
+                p = q + 1;
+                return true;
+            }
+        }
         ++p;
         while (p < end) {
             unsigned char c = (unsigned char)*p++;
@@ -289,6 +315,7 @@ static bool parse_edges(const char *text, size_t len, std::vector<RawKey> &keys,
     }
     ++in.p;
     std::unordered_map<std::string, size_t> seen;  // duplicate keys: the last one wins (dict)
+    bool ascending = true;
     in.ws();
     if (in.p < in.end && *in.p == '}') {
         ++in.p;
@@ -383,12 +410,22 @@ static bool parse_edges(const char *text, size_t len, std::vector<RawKey> &keys,
                 rk.poison_key = true;
             }
             if (!in.err.empty()) break;
-            auto it = seen.find(rk.key);
-            if (it == seen.end()) {
-                seen.emplace(rk.key, keys.size());
+            // json.dumps(sort_keys=True) wrote the keys in ascending order: no key can repeat while that holds,
+            // and the dictionary of seen keys is only built once it stops holding
+            if (ascending && (keys.empty() || keys.back().key < rk.key)) {
                 keys.push_back(std::move(rk));
             } else {
-                keys[it->second] = std::move(rk);
+                if (ascending) {
+                    ascending = false;
+                    for (size_t i = 0; i < keys.size(); ++i) seen.emplace(keys[i].key, i);
+                }
+                auto it = seen.find(rk.key);
+                if (it == seen.end()) {
+                    seen.emplace(rk.key, keys.size());
+                    keys.push_back(std::move(rk));
+                } else {
+                    keys[it->second] = std::move(rk);
+                }
             }
             in.ws();
             if (in.p < in.end && *in.p == ',') {
@@ -553,16 +590,22 @@ static uint32_t pow2_at_least(uint64_t n) {
 
 static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pair<std::string, int64_t>> &alts,
                   std::string &err) {
+    StageTimer tm;
     // distinct sv ids, byte-sorted == the order json.dumps(sort_keys=True) prints them
-    for (auto &k : keys)
-        for (auto &e : k.ents)
-            if (e.second >= 0) t->sv_ids.push_back(e.first);
-    std::sort(t->sv_ids.begin(), t->sv_ids.end());
-    t->sv_ids.erase(std::unique(t->sv_ids.begin(), t->sv_ids.end()), t->sv_ids.end());
+    {
+        std::unordered_set<std::string_view> distinct;      // views into keys[].ents, which outlive this block
+        for (auto &k : keys)
+            for (auto &e : k.ents)
+                if (e.second >= 0) distinct.insert(std::string_view(e.first));
+        t->sv_ids.reserve(distinct.size());
+        for (const std::string_view &v : distinct) t->sv_ids.emplace_back(v);
+        std::sort(t->sv_ids.begin(), t->sv_ids.end());
+    }
     if (t->sv_ids.size() >= 0x7FFFFFFFull) {
         err = "too many distinct sv ids";
         return false;
     }
+    tm.lap("  sv ids sorted");
     t->n_keys = uint32_t(keys.size());
     // entries on which the reference raises make skipping any probe unsafe
     for (auto &k : keys) {
@@ -595,20 +638,23 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         }
     }
     ent_begin[keys.size()] = uint32_t(t->entries.size());
+    tm.lap("  entries + key parses");
     if (t->entries.empty()) t->entries.push_back(ENTRY_POISON);  // never empty on the device
 
     // node names: every name a link key can be read with, plus the GFA's alt nodes
-    std::unordered_map<std::string, uint32_t> node_id;
+    // the views point into keys[].key and alts[].first, neither of which changes during the build
+    std::unordered_map<std::string_view, uint32_t> node_id;
     std::vector<std::pair<std::string, int64_t>> nodes;      // name, alt sequence length or -1
-    auto intern = [&](const std::string &name) -> uint32_t {
+    node_id.reserve(keys.size() + alts.size());
+    auto intern = [&](std::string_view name) -> uint32_t {
         auto it = node_id.find(name);
         if (it != node_id.end()) return it->second;
         uint32_t id = uint32_t(nodes.size());
         node_id.emplace(name, id);
-        nodes.push_back({name, -1});
+        nodes.push_back({std::string(name), -1});
         return id;
     };
-    for (auto &a : alts) nodes[intern(a.first)].second = a.second;
+    for (auto &a : alts) nodes[intern(std::string_view(a.first))].second = a.second;
 
     std::vector<uint8_t> roles;                              // per node: bit s = left node with strand s, bit 2+s = right
     uint32_t cap = pow2_at_least(parses.size() * 2 + 2);
@@ -622,7 +668,8 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
             return false;
         }
         uint32_t sl = k[ps.split + 1] == '+', sr = k[n - 1] == '+';
-        uint32_t idl = intern(k.substr(0, len_l)), idr = intern(k.substr(off_r, len_r));
+        const std::string_view kv(k);
+        uint32_t idl = intern(kv.substr(0, len_l)), idr = intern(kv.substr(off_r, len_r));
         if (roles.size() < nodes.size()) roles.resize(nodes.size(), 0);
         roles[idl] |= uint8_t(1u << sl);
         roles[idr] |= uint8_t(4u << sr);
@@ -644,6 +691,7 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         t->links[i] = s;
     }
     t->n_link_slots = uint32_t(parses.size());
+    tm.lap("  node interning + link table");
 
     t->n_alt = uint32_t(alts.size());
     t->n_nodes = uint32_t(nodes.size());
@@ -668,6 +716,7 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         while (t->nodes[i].id1) i = (i + 1) & (ncap - 1);
         t->nodes[i] = s;
     }
+    tm.lap("  name-hash node table");
     // plain names once more under their exact key (same ids)
     {
         std::vector<PNodeSlot> plain;
@@ -691,6 +740,7 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
             t->pnodes[i] = s;
         }
     }
+    tm.lap("  plain-node table");
     // pad the blob so 4-byte reads at the tail stay in bounds
     t->blob.insert(t->blob.end(), 16, 0);
     return true;
@@ -699,6 +749,17 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
 static bool read_file(const char *path, std::string &out) {
     FILE *f = fopen(path, "rb");
     if (!f) return false;
+    // a regular file: one read into a string of its size; anything else (a pipe): append as it comes
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long n = ftell(f);
+        if (n > 0 && fseek(f, 0, SEEK_SET) == 0) {
+            out.resize(size_t(n));
+            const size_t got = fread(&out[0], 1, size_t(n), f);
+            out.resize(got);
+        } else {
+            rewind(f);
+        }
+    }
     char buf[1 << 16];
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
@@ -921,6 +982,25 @@ extern "C" uint32_t svjg_aln_counts_find(const svjg_aln_counts *c, const char *k
     return uint32_t(it - c->keys.begin());
 }
 
+extern "C" uint64_t svjg_tables_image_hash(const svjg_tables *t) {
+    if (!t) return 0;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+        h = (h ^ n) * 1099511628211ull;
+    };
+    mix(t->links.data(), t->links.size() * sizeof(LinkSlot));
+    mix(t->nodes.data(), t->nodes.size() * sizeof(NodeSlot));
+    mix(t->pnodes.data(), t->pnodes.size() * sizeof(PNodeSlot));
+    mix(t->blob.data(), t->blob.size());
+    mix(t->entries.data(), t->entries.size() * sizeof(uint32_t));
+    for (const std::string &s : t->sv_ids) mix(s.data(), s.size());
+    const uint32_t tail[5] = {t->n_keys, t->n_link_slots, t->n_alt, t->n_nodes, t->filter_flags};
+    mix(tail, sizeof tail);
+    return h;
+}
+
 extern "C" int64_t svjg_tables_alt_node_len(const svjg_tables *t, const char *name, uint32_t len) {
     if (!t || (!name && len) || t->nodes.empty()) return -1;
     // the probe the kernels make: token hash of the name, then the name bytes
@@ -958,13 +1038,17 @@ extern "C" int svjg_tables_from_memory(const char *edges_json, size_t edges_len,
     std::vector<RawKey> keys;
     std::vector<std::pair<std::string, int64_t>> alts;
     std::string err;
+    StageTimer tm;
     if (!parse_edges(edges_json, edges_len, keys, err)) return set_error(SVJG_E_JSON, err);
+    tm.lap("svs_edges.json parse");
     if (!scan_gfa(gfa, gfa_len, alts, err)) return set_error(SVJG_E_INPUT, err);
+    tm.lap("GFA scan");
     svjg_tables *t = new svjg_tables();
     if (!build(t, keys, alts, err)) {
         delete t;
         return set_error(SVJG_E_ARG, err);
     }
+    tm.lap("table build");
     *out = t;
     return SVJG_OK;
 }

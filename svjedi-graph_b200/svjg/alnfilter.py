@@ -73,6 +73,10 @@ class Tables:
         i = capi.lib.svjg_tables_find_sv(self._h, b, len(b))
         return None if i == capi.NO_SV else int(i)
 
+    @property
+    def image_hash(self):
+        return int(capi.lib.svjg_tables_image_hash(self._h))
+
     def alt_node_len(self, name):
         """``alt_node_len.get(name)`` of filter-alignments.py:103-113, read from the tables the kernels probe."""
         b = name.encode("utf-8")

@@ -58,6 +58,7 @@ def _load():
         "svjg_tables_num_alt_nodes": (C.c_uint32, [vp]),
         "svjg_tables_device_bytes": (C.c_uint64, [vp]),
         "svjg_tables_alt_node_len": (C.c_int64, [vp, C.c_char_p, C.c_uint32]),
+        "svjg_tables_image_hash": (C.c_uint64, [vp]),
         "svjg_tables_sv_id": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "svjg_tables_find_sv": (C.c_uint32, [vp, C.c_char_p, C.c_uint32]),
         "svjg_tables_to_device": (C.c_int, [vp, C.c_int]),
