@@ -1,10 +1,16 @@
 #!/usr/bin/env python3
-"""Regenerates tests/golden/fuzz_lines.json.gz: randomly damaged GAF lines on the c1 graph, each run
-ALONE through the UNMODIFIED reference filter (/root/reference/filter-alignments.py, imported and its
-main() called in-process).  Stored per line: the text, whether the reference raised (exit status 1),
-and otherwise the list lengths of its informative_aln.json.
+"""Regenerates the damaged-input fixtures, each case run through the UNMODIFIED reference scripts
+(imported from /root/reference and their main() called in-process):
 
-    python tests/golden/make_fuzz.py            # build container only (needs /root/reference)
+    python tests/golden/make_fuzz.py lines   # fuzz_lines.json.gz  2 500 damaged GAF lines on the c1 graph (+ a CR LF file)
+    python tests/golden/make_fuzz.py vcf     # fuzz_vcf.json.gz    800 VCFs with a damaged body line (predict-genotype.py)
+    python tests/golden/make_fuzz.py edges   # fuzz_edges.json     300 svs_edges.json with damaged entries
+    python tests/golden/make_fuzz.py gfa     # fuzz_gfa.json.gz    1 200 damaged GFAs: the reference's alt_node_len dictionary
+    python tests/golden/make_fuzz.py json    # fuzz_json.json      600 damaged informative_aln.json (predict-genotype.py)
+
+Stored per case: the input (or, where it is regenerated from the seed, a hash of it), whether the
+reference raised (exit status 1), and otherwise its output (list lengths, text, or a SHA-256 of it).
+Build container only (needs /root/reference); the tests read the committed fixtures.
 """
 import gzip
 import hashlib
