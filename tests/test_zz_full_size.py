@@ -49,6 +49,24 @@ def test_full_size_exact_against_the_c_oracle(name):
     got = got[:, np.lexsort(got[::-1])]
     want = want[:, np.lexsort(want[::-1])]
     assert (got == want).all()
+    # informative_aln.json of the whole batch: the library's emitter against json.dumps of the reference's dictionary
+    # rebuilt from the checker's hit tuples (file order)
+    import hashlib
+    import tempfile
+    d = {}
+    view = memoryview(gaf)
+    for s2, o, n in zip(w_sv2.tolist(), w_off.tolist(), w_len.tolist()):
+        d.setdefault(ct.sv_ids[s2 >> 1], [[], []])[s2 & 1].append(O.kept_text(str(view[o:o + n], "ascii")))
+    want_sha = hashlib.sha256(O.dumps_informative(d).encode()).hexdigest()
+    del d
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "informative_aln.json")
+        alnfilter.write_informative_json(t, gaf, res, out)
+        h = hashlib.sha256()
+        with open(out, "rb") as fh:
+            for block in iter(lambda: fh.read(1 << 24), b""):
+                h.update(block)
+    assert h.hexdigest() == want_sha
     # genotypes from those counters: the VCF text against the line-by-line oracle
     text, n = genotype.genotype_vcf(t, res.counts, vcf.encode())
     assert (text, n) == O.genotype_vcf(CO.counts_dict(ct, want_counts), vcf.splitlines(True))
