@@ -94,7 +94,7 @@ def _load():
         "svjg_aln_counts_key": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "svjg_aln_counts_data": (C.c_void_p, [vp]),
         "svjg_aln_counts_find": (C.c_uint32, [vp, C.c_char_p, C.c_uint32]),
-        "svjg_vcf_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+        "svjg_vcf_parse": (C.c_int, [vp, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
         "svjg_vcf_free": (None, [vp]),
         "svjg_vcf_num_records": (C.c_uint32, [vp]),
         "svjg_vcf_svtype": (C.c_void_p, [vp]),

@@ -133,7 +133,11 @@ class NativeVcf:
         """``data``: bytes of the file.  None if the library declines the file; VcfError where the
         reference raises."""
         h = C.c_void_p()
-        rc = capi.lib.svjg_vcf_parse(data, len(data), 1 if translate_cr else 0, C.byref(h))
+        if isinstance(data, np.ndarray):                 # the file's bytes where they lie (no copy)
+            a = np.ascontiguousarray(data, dtype=np.uint8)
+            rc = capi.lib.svjg_vcf_parse(a.ctypes.data if a.size else None, a.size, 1 if translate_cr else 0, C.byref(h))
+        else:
+            rc = capi.lib.svjg_vcf_parse(data, len(data), 1 if translate_cr else 0, C.byref(h))
         if rc == capi.E_UNSUPPORTED:
             return None
         if rc == capi.E_INPUT:
@@ -146,7 +150,7 @@ class NativeVcf:
         """From what the callers hold: the file's bytes (bytes / bytearray / uint8 array: read as text
         mode reads them) or a list of lines as ``readlines()`` gives them."""
         if isinstance(vcf, np.ndarray):
-            return cls.parse(vcf.tobytes(), True)
+            return cls.parse(vcf, True)
         if isinstance(vcf, (bytes, bytearray, memoryview)):
             return cls.parse(bytes(vcf), True)
         lines = vcf if isinstance(vcf, list) else list(vcf)
