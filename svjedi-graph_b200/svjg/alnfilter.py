@@ -207,6 +207,77 @@ def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None, out=No
     return FilterResult(counts, st)
 
 
+def filter_stream(tables, fileobj, chunk_bytes=64 << 20, d_over=D_OVER):
+    """the filter fed from a pipe (``minigraph ... | filter-alignments.py -a
+    /dev/stdin``) while the mapper is still writing.  The stream is cut into segments of whole lines of
+    about ``chunk_bytes``; each segment goes through :func:`filter_host` on a worker thread (ctypes
+    releases the GIL) while the next one is being read, its counters are added up and its hit offsets
+    moved to their place in the whole input.  Text-mode line ends are translated per segment exactly as
+    for a file (a "\r" at the end of a read is held back until the next byte is known).  Returns
+    (FilterResult, the whole translated GAF as one uint8 array) — what the JSON writer needs."""
+    from concurrent.futures import ThreadPoolExecutor
+    segments, results = [], []
+    pending = b""
+    pool = ThreadPoolExecutor(1)
+    job = None
+    base = 0
+
+    def one_segment(arr, b):
+        try:
+            return b, filter_host(tables, arr, d_over)
+        except InputError as exc:
+            raise InputError(f"{exc} [offset within the segment that starts at byte {b} of the stream]") from None
+
+    def submit(seg):
+        nonlocal job, base
+        if job is not None:
+            results.append(job.result())                  # raises InputError where the reference raises
+        arr = np.frombuffer(seg, dtype=np.uint8)
+        segments.append(arr)
+        job = pool.submit(one_segment, arr, base)
+        base += arr.size
+
+    try:
+        eof = False
+        while not eof:
+            block = fileobj.read(chunk_bytes)
+            eof = not block
+            data = pending + block
+            held = b""
+            if not eof and data.endswith(b"\r"):           # "\r\n" may straddle two reads
+                data, held = data[:-1], b"\r"
+            if b"\r" in data:
+                data = data.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+            if eof:
+                cut = len(data)
+            else:
+                cut = data.rfind(b"\n") + 1                 # whole lines only; the rest waits for more bytes
+            if cut and (eof or cut >= chunk_bytes // 2 or len(data) >= 2 * chunk_bytes):
+                submit(data[:cut])
+                pending = data[cut:] + held
+            else:
+                pending = data + held
+        if job is not None:
+            results.append(job.result())
+    finally:
+        pool.shutdown(wait=True)
+    counts = np.zeros((tables.num_sv, 2), dtype=np.uint32)
+    stats = {}
+    sv2, off, ln = [], [], []
+    for b, r in results:
+        counts += r.counts
+        for k, v in r.stats.items():
+            stats[k] = stats.get(k, 0) + v if k not in ("status", "err_offset") else 0
+        sv2.append(r.hit_sv2)
+        off.append(r.hit_off.astype(np.uint64) + np.uint64(b))
+        ln.append(r.hit_len)
+    cat = (lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt))
+    gaf = np.concatenate(segments) if segments else np.zeros(0, np.uint8)
+    for k in ("n_hits", "n_records", "n_multi", "n_checks", "status", "err_offset", "n_generic", "n_exact"):
+        stats.setdefault(k, 0)
+    return FilterResult(counts, stats, cat(sv2, np.uint32), cat(off, np.uint64), cat(ln, np.uint32)), gaf
+
+
 class DeviceFilter:
     """Device-resident variant: GAF shard already in HBM (torch uint8 tensor).
     Buffers are torch tensors; launches go to torch's current stream."""

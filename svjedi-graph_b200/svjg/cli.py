@@ -45,14 +45,15 @@ def _load_tables(prefix, gfa_file, device_ready=None):
     return t.to_device(0)
 
 
-def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None):
-    """filter-alignments.py:119-175.  Returns (FilterResult, page-locked GAF bytes)."""
+def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, stream=None):
+    """filter-alignments.py:119-175.  Returns (FilterResult, page-locked GAF bytes).  ``stream``: an open
+    pipe to filter while it is being written (alnfilter.filter_stream) instead of a file."""
     from . import alnfilter, capi, gzio
     if dover_given:
         # -O leaves a list in d_over and `int >= list` raises at the first overlap test (:269);
         # count every test the reference would make
         tables.set_flags(capi.FLAG_EXACT_CHECKS)
-    if gaf is None:
+    if gaf is None and stream is None:
         with open(gaf_file, "rb") as fh:
             head = fh.read(2)
         if gzio.is_gzip(head):                                              # extension: gzip / bgzip input
@@ -61,7 +62,10 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None):
             gaf = alnfilter.read_file_pinned(gaf_file)
             if alnfilter.translate_newlines(gaf) is not gaf:               # carriage returns: text-mode line ends
                 gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
-    res = alnfilter.filter_host(tables, gaf)
+    if stream is not None:
+        res, gaf = alnfilter.filter_stream(tables, stream)
+    else:
+        res = alnfilter.filter_host(tables, gaf)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
     alnfilter.write_informative_json(tables, gaf, res, out_json)
@@ -85,8 +89,23 @@ def filter_main(argv=None):
         out_json = "/".join([args.outputDir, out_json])
     from . import alnfilter, capi, gzio
     try:
+        import os
+        import stat
         ready = _start_device()
-        raw = gzio.read_bytes(args.gaf[0])                                 # read (gzip / bgzip: inflate) while the context comes up
+        pipe = None
+        if not stat.S_ISREG(os.stat(args.gaf[0]).st_mode):                 # `minigraph ... | filter-alignments.py -a /dev/stdin`
+            pipe = open(args.gaf[0], "rb")
+            if gzio.is_gzip(pipe.peek(2)[:2]):                             # compressed: inflate it whole (below)
+                raw = gzio.inflate(pipe.read())
+                pipe.close()
+                pipe = None
+        else:
+            raw = gzio.read_bytes(args.gaf[0])                             # read (gzip / bgzip: inflate) while the context comes up
+        if pipe is not None:
+            with pipe:                                                     # filtered segment by segment while the mapper writes
+                tables = _load_tables(args.prefix, args.gfa[0], ready)
+                _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, stream=pipe)
+            return 0
         raw = alnfilter.translate_newlines(raw)                            # text-mode line ends, like the reference
         tables = _load_tables(args.prefix, args.gfa[0], ready)
         gaf = alnfilter.RegisteredBytes(raw)                                # page-lock in place

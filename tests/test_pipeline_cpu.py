@@ -99,7 +99,7 @@ def test_filter_command_line_wiring(tmp_path, monkeypatch):
     (tmp_path / "crlf.gaf.gz").write_bytes(gzip.compress("".join(lines).replace("\n", "\r\n").encode()))
     (tmp_path / "out").mkdir()
 
-    def filter_host(tables, gaf_bytes, **kw):
+    def filter_host(tables, gaf_bytes, d_over=100, **kw):
         counts = np.zeros((tables.num_sv, 2), np.uint32)
         sv2, off, ln = [], [], []
         pos = n_checks = 0
@@ -125,6 +125,16 @@ def test_filter_command_line_wiring(tmp_path, monkeypatch):
     assert (tmp_path / "p_informative_aln.json").read_text() == want
     assert cli.filter_main(["-a", "crlf.gaf.gz", "-g", "p.gfa", "-p", "p", "-o", "out"]) == 0
     assert (tmp_path / "out" / "p_informative_aln.json").read_text() == want
+    # the same records through a pipe: filtered as a stream (row N3)
+    import threading
+    fifo = str(tmp_path / "gaf.fifo")
+    os.mkfifo(fifo)
+    th = threading.Thread(target=lambda: open(fifo, "wb").write("".join(lines).replace("\n", "\r\n").encode()))
+    th.start()
+    (tmp_path / "piped_svs_edges.json").write_text(edges_text)
+    assert cli.filter_main(["-a", fifo, "-g", "p.gfa", "-p", "piped"]) == 0
+    th.join()
+    assert (tmp_path / "piped_informative_aln.json").read_text() == want
     with pytest.raises(SystemExit) as exc:                       # no -p: the reference never finds its link table (:95)
         cli.filter_main(["-a", "p.gaf", "-g", "p.gfa"])
     assert exc.value.code == 1
@@ -134,3 +144,60 @@ def test_filter_command_line_wiring(tmp_path, monkeypatch):
     with pytest.raises(SystemExit) as exc:
         cli.filter_main(["-a", "missing.gaf", "-g", "p.gfa", "-p", "p"])
     assert exc.value.code == 1
+
+
+def test_streamed_input_equals_the_whole_file(monkeypatch):
+    """alnfilter.filter_stream (row N3): segments of whole lines, CR LF / CR translated across read
+    boundaries, offsets moved to their place — against one pass over the whole (translated) input.  The GPU
+    call is the oracle stand-in; what is tested is the cutting and the bookkeeping."""
+    import io
+    import threading
+    from conftest import read_golden
+    edges, alt = json.loads(read_golden("c1_svs_edges.json")), alt_len_from_gfa_text(read_golden("c1.gfa.gz"))
+    lines = [l for l in read_golden("c1.gaf.gz").splitlines(True) if "cg:Z:" not in l][:400]
+    text = "".join(l if i % 3 else l.replace("\n", "\r\n") for i, l in enumerate(lines))
+    text = text[:-1]                                            # no line end after the last record
+    raw = text.encode()
+    t = alnfilter.Tables.from_memory(read_golden("c1_svs_edges.json"), read_golden("c1.gfa.gz"))
+
+    def filter_host(tables, gaf_bytes, d_over=100, **kw):
+        counts = np.zeros((tables.num_sv, 2), np.uint32)
+        sv2, off, ln = [], [], []
+        pos = 0
+        for line in bytes(alnfilter._as_u8(gaf_bytes)).decode().splitlines(True):
+            for sv, allele in O.record_hits(line, edges, alt):
+                i = tables.find_sv(sv)
+                counts[i, allele] += 1
+                sv2.append(2 * i + allele)
+                off.append(pos)
+                ln.append(len(line))
+            pos += len(line)
+        return alnfilter.FilterResult(counts, {"n_hits": len(sv2), "n_records": pos and 1}, np.array(sv2, np.uint32),
+                                      np.array(off, np.uint64), np.array(ln, np.uint32))
+
+    monkeypatch.setattr(alnfilter, "filter_host", filter_host)
+    whole_bytes = bytes(alnfilter._as_u8(alnfilter.translate_newlines(np.frombuffer(raw, np.uint8))))
+    whole = filter_host(t, whole_bytes)
+    assert whole.stats["n_hits"] > 50
+    want = sorted(zip(whole.hit_off.tolist(), whole.hit_sv2.tolist(), whole.hit_len.tolist()))
+    for chunk in (7, 64, 1000, 5000, 1 << 20):
+        res, gaf = alnfilter.filter_stream(t, io.BytesIO(raw), chunk_bytes=chunk)
+        assert gaf.tobytes() == whole_bytes, chunk
+        assert (res.counts == whole.counts).all() and res.n_hits == whole.stats["n_hits"], chunk
+        assert sorted(zip(res.hit_off.tolist(), res.hit_sv2.tolist(), res.hit_len.tolist())) == want, chunk
+    # a real pipe that delivers odd-sized pieces
+    r, w = os.pipe()
+
+    def feed():
+        with os.fdopen(w, "wb", buffering=0) as fh:
+            for i in range(0, len(raw), 777):
+                fh.write(raw[i:i + 777])
+    th = threading.Thread(target=feed)
+    th.start()
+    with os.fdopen(r, "rb", buffering=0) as fh:                 # raw reads: short counts are normal
+        res, gaf = alnfilter.filter_stream(t, fh, chunk_bytes=4096)
+    th.join()
+    assert gaf.tobytes() == whole_bytes and (res.counts == whole.counts).all()
+    assert sorted(zip(res.hit_off.tolist(), res.hit_sv2.tolist(), res.hit_len.tolist())) == want
+    empty, gaf = alnfilter.filter_stream(t, io.BytesIO(b""))
+    assert gaf.size == 0 and empty.n_hits == 0 and not empty.counts.any()
