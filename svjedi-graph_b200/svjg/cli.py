@@ -140,6 +140,50 @@ def genotype_main(argv=None):
     return 0
 
 
+class _MapperOutput:
+    """File-like view (read(n) only) of what ends up in <prefix>.gaf: what the file already holds (the
+    reference appends, svjedi-graph.py:100-104), then the standard output of one mapper process after the
+    other; every byte read from a mapper is also appended to the file.  ``returncode`` is the last
+    mapper's, the one the reference looks at (:107)."""
+
+    def __init__(self, commands, gaf_path):
+        self._commands = list(commands)
+        self._path = gaf_path
+        self._old = open(gaf_path, "rb")
+        self._out = open(gaf_path, "ab")
+        self._proc = None
+        self.returncode = None
+
+    def read(self, n):
+        if self._old is not None:
+            data = self._old.read(n)
+            if data:
+                return data
+            self._old.close()
+            self._old = None
+        while True:
+            if self._proc is None:
+                if not self._commands:
+                    return b""
+                self._proc = subprocess.Popen(self._commands.pop(0), shell=True, stdout=subprocess.PIPE)
+            data = self._proc.stdout.read(n)
+            if data:
+                self._out.write(data)
+                return data
+            self._proc.stdout.close()
+            self.returncode = self._proc.wait()
+            self._proc = None
+
+    def drain(self):
+        while self.read(1 << 24):
+            pass
+
+    def close(self):
+        if self._old is not None:
+            self._old.close()
+        self._out.close()
+
+
 def pipeline_main(svjg_dir, argv=None):
     """svjedi-graph.py: graph construction and mapping are external tools exactly as in the
     reference (:85-108); filtering and genotyping run fused in this process — the counters
@@ -161,6 +205,9 @@ def pipeline_main(svjg_dir, argv=None):
     if subprocess.run(f"python3 {construct} -v {args.vcf} -r {args.ref} -o {out_gfa}", shell=True).returncode == 1:
         sys.exit("Failed to contruct the variation graph.\nExiting SVJedi-graph.")
 
+    if os.environ.get("SVJG_STREAM"):
+        return _pipeline_streamed(args, out_gfa, out_gaf)
+
     print("Mapping reads on graph...")
     subprocess.run(f"touch {out_gaf}", shell=True)
     proc = None
@@ -181,6 +228,47 @@ def pipeline_main(svjg_dir, argv=None):
     print("Genotyping SVs...")
     try:
         lines = gzio.read_bytes(args.vcf)                      # the file's bytes: keys and text are built by the library
+        with open(args.prefix + "_genotype.vcf", "wb") as out:
+            _, n = genotype.genotype_vcf(tables, res.counts, lines, args.minsupport, out=out)
+    except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
+        sys.stderr.write(f"svjg: {exc}\n")
+        sys.exit("Failed to predict the genotypes.\nExiting SVJedi-graph.")
+    print(f"Genotyped svs: {n}")
+    return 0
+
+
+def _pipeline_streamed(args, out_gfa, out_gaf):
+    """SVJG_STREAM=1: stages 2-3 overlapped.  The mappers' output is appended to
+    <prefix>.gaf as in the reference and filtered segment by segment while they run; the messages, files and
+    exit statuses are those of the sequential run (a mapper failure is reported before a filter failure)."""
+    from . import alnfilter, capi, genotype, gzio
+    print("Mapping reads on graph...")
+    subprocess.run(f"touch {out_gaf}", shell=True)
+    chain = _MapperOutput([f"minigraph -x lr -t{args.threads} {out_gfa} {fq}" for fq in args.reads.split(",")], out_gaf)
+    failure = None
+    tables = res = gaf = None
+    try:
+        try:
+            tables = _load_tables(args.prefix, out_gfa)
+            res, gaf = alnfilter.filter_stream(tables, chain)
+        except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
+            failure = exc
+            chain.drain()                                    # the reference maps everything before it filters
+    finally:
+        chain.close()
+    if chain.returncode == 1:
+        sys.exit("Failed to map the reads on the graph.\nExiting SVJedi-graph.")
+    print("Filtering alignment file...")
+    try:
+        if failure is not None:
+            raise failure
+        alnfilter.write_informative_json(tables, gaf, res, args.prefix + "_informative_aln.json")
+    except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
+        sys.stderr.write(f"svjg: {exc}\n")
+        sys.exit("Failed to filter the alignments.\nExiting SVJedi-graph.")
+    print("Genotyping SVs...")
+    try:
+        lines = gzio.read_bytes(args.vcf)
         with open(args.prefix + "_genotype.vcf", "wb") as out:
             _, n = genotype.genotype_vcf(tables, res.counts, lines, args.minsupport, out=out)
     except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:

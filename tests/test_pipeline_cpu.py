@@ -9,6 +9,7 @@ import os
 from collections import OrderedDict
 
 import numpy as np
+import pytest
 
 from conftest import PKG, alt_len_from_gfa_text
 from oracle import svjg_oracle as O
@@ -16,7 +17,8 @@ from svjg import alnfilter, cli, genotype, graphgen, synth
 from test_vcf_native import stand_in_genotype_host
 
 
-def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd):
+@pytest.mark.parametrize("streamed", [False, True])
+def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd, streamed):
     rng = np.random.Generator(np.random.PCG64(3))
     chrom_len = OrderedDict((("chr1", 60000), ("chr2", 40000)))
     seqs = OrderedDict((c, rng.choice(np.frombuffer(b"ACGT", dtype="S1"), size=n).tobytes().decode()) for c, n in chrom_len.items())
@@ -40,7 +42,7 @@ def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd):
     def load_tables(pfx, gfa_file, device_ready=None):               # host half of cli._load_tables
         return alnfilter.Tables.load(pfx + "_svs_edges.json", gfa_file)
 
-    def filter_host(tables, gaf_bytes, **kw):                         # svjg_filter_host's contract, by the oracle
+    def filter_host(tables, gaf_bytes, d_over=100, **kw):             # svjg_filter_host's contract, by the oracle
         edges = json.load(open(prefix + "_svs_edges.json"))
         alt = alt_len_from_gfa_text(open(prefix + ".gfa").read())
         counts = np.zeros((tables.num_sv, 2), np.uint32)
@@ -62,6 +64,10 @@ def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd):
     monkeypatch.setattr(alnfilter, "read_file_pinned", lambda path: np.fromfile(path, dtype=np.uint8))
     monkeypatch.setattr(genotype, "genotype_host", stand_in_genotype_host)
     monkeypatch.chdir(tmp_path)
+    if streamed:                                              # SVJG_STREAM=1: mapping and filtering overlapped (row N3)
+        monkeypatch.setenv("SVJG_STREAM", "1")
+    else:
+        monkeypatch.delenv("SVJG_STREAM", raising=False)
     assert cli.pipeline_main(PKG, ["-v", "in.vcf", "-r", "ref.fa", "-q", "reads.fq", "-p", prefix]) == 0
     out = capfd.readouterr().out
 
@@ -201,3 +207,74 @@ def test_streamed_input_equals_the_whole_file(monkeypatch):
     assert sorted(zip(res.hit_off.tolist(), res.hit_sv2.tolist(), res.hit_len.tolist())) == want
     empty, gaf = alnfilter.filter_stream(t, io.BytesIO(b""))
     assert gaf.size == 0 and empty.n_hits == 0 and not empty.counts.any()
+
+
+def test_streamed_orchestrator_appends_and_reports_like_the_reference(tmp_path, monkeypatch, capfd):
+    """SVJG_STREAM=1 edge semantics: <prefix>.gaf is appended to (what it already holds is filtered too,
+    svjedi-graph.py:100-104), every FASTQ of a comma list is mapped in turn, and exit status 1 of the LAST
+    mapper stops the run with the reference's message (:107) after the file has been written."""
+    from conftest import read_golden
+    edges_text, gfa_text = read_golden("c1_svs_edges.json"), read_golden("c1.gfa.gz")
+    edges, alt = json.loads(edges_text), alt_len_from_gfa_text(gfa_text)
+    lines = [l for l in read_golden("c1.gaf.gz").splitlines(True) if "cg:Z:" not in l]
+    old, new = "".join(lines[:40]), "".join(lines[40:200])
+    prefix = str(tmp_path / "run")
+    stub = tmp_path / "construct_stub.py"                       # the graph files of c1 (its FASTA is not in this repository)
+    (tmp_path / "c1.gfa").write_text(gfa_text)
+    (tmp_path / "c1_edges.json").write_text(edges_text)
+    stub.write_text("import shutil, sys\nout = sys.argv[sys.argv.index('-o') + 1]\n"
+                    f"shutil.copy({str(tmp_path / 'c1.gfa')!r}, out)\n"
+                    f"shutil.copy({str(tmp_path / 'c1_edges.json')!r}, out[:-4] + '_svs_edges.json')\n")
+    (tmp_path / "new.gaf").write_text(new)
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    mg = bindir / "minigraph"
+    mg.write_text(f"#!/bin/sh\ncat {tmp_path}/new.gaf\nexit ${{MG_RC:-0}}\n")
+    mg.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{bindir}:{os.environ['PATH']}")
+    monkeypatch.setenv("SVJG_CONSTRUCT_GRAPH", str(stub))
+    monkeypatch.setenv("SVJG_STREAM", "1")
+    (tmp_path / "in.vcf").write_text(read_golden("c1.vcf"))
+
+    def filter_host(tables, gaf_bytes, d_over=100, **kw):
+        counts = np.zeros((tables.num_sv, 2), np.uint32)
+        sv2, off, ln = [], [], []
+        pos = 0
+        for line in bytes(alnfilter._as_u8(gaf_bytes)).decode().splitlines(True):
+            for sv, allele in O.record_hits(line, edges, alt):
+                i = tables.find_sv(sv)
+                counts[i, allele] += 1
+                sv2.append(2 * i + allele)
+                off.append(pos)
+                ln.append(len(line))
+            pos += len(line)
+        return alnfilter.FilterResult(counts, {"n_hits": len(sv2)}, np.array(sv2, np.uint32), np.array(off, np.uint64),
+                                      np.array(ln, np.uint32))
+
+    monkeypatch.setattr(cli, "_load_tables", lambda pfx, gfa, ready=None: alnfilter.Tables.load(pfx + "_svs_edges.json", gfa))
+    monkeypatch.setattr(alnfilter, "filter_host", filter_host)
+    monkeypatch.setattr(genotype, "genotype_host", stand_in_genotype_host)
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "run.gaf").write_text(old)                      # left over from an earlier run
+    assert cli.pipeline_main(PKG, ["-v", "in.vcf", "-r", "ref.fa", "-q", "a.fq,b.fq", "-p", prefix]) == 0
+    capfd.readouterr()
+    assert (tmp_path / "run.gaf").read_text() == old + new + new
+    want = O.filter_alignments((old + new + new).splitlines(True), edges, alt)
+    assert (tmp_path / "run_informative_aln.json").read_text() == O.dumps_informative(want)
+    assert (tmp_path / "run_genotype.vcf").read_text() == O.genotype_vcf(O.hit_counts(want), read_golden("c1.vcf").splitlines(True))[0]
+    # the last mapper fails: the file is complete, the run stops with the reference's message
+    monkeypatch.setenv("MG_RC", "1")
+    (tmp_path / "run.gaf").write_text("")
+    with pytest.raises(SystemExit) as exc:
+        cli.pipeline_main(PKG, ["-v", "in.vcf", "-r", "ref.fa", "-q", "a.fq", "-p", prefix])
+    assert str(exc.value.code).startswith("Failed to map the reads on the graph.")
+    assert (tmp_path / "run.gaf").read_text() == new
+    # a line the reference raises on: mapping completes, then the filter's failure is reported
+    monkeypatch.setenv("MG_RC", "0")
+    (tmp_path / "new.gaf").write_text(new + "only\tthree\tcolumns\n" + new)
+    (tmp_path / "run.gaf").write_text("")
+    monkeypatch.setattr(alnfilter, "filter_host", lambda *a, **k: (_ for _ in ()).throw(alnfilter.InputError("GAF line: fewer than 12 columns")))
+    with pytest.raises(SystemExit) as exc:
+        cli.pipeline_main(PKG, ["-v", "in.vcf", "-r", "ref.fa", "-q", "a.fq", "-p", prefix])
+    assert str(exc.value.code).startswith("Failed to filter the alignments.")
+    assert (tmp_path / "run.gaf").read_text() == new + "only\tthree\tcolumns\n" + new
