@@ -170,9 +170,8 @@ def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None, check=None):
     ``check`` = (sv ids, counters [num_sv, 2], number of hits) of the GPU path for the same batch: the
     whole batch is then compared counter by counter (key "parity")."""
     try:
-        import subprocess
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
         from oracle import c_oracle as CO
+        CO.ensure_built()
         alt = {}
         for line in gfa_text.splitlines(True):
             if line.startswith("S"):

@@ -19,9 +19,19 @@ LIB_PATH = os.path.join(_HERE, "_build", "libsvjg_oracle.so")
 _lib = None
 
 
+def ensure_built():
+    """Builds oracle/_build/libsvjg_oracle.so if it is not there (gcc, a second); a library that travelled
+    with the tree is used as it is."""
+    if not os.path.exists(LIB_PATH):
+        import subprocess
+        subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    return LIB_PATH
+
+
 def lib():
     global _lib
     if _lib is None:
+        ensure_built()
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} not found: `make -C oracle` (or __graft_entry__.build())")
         _lib = C.CDLL(LIB_PATH)

@@ -5,12 +5,11 @@ Runs last (file name) and loads no tensor library.  SVJG_TEST_FULL_SCALE shrinks
 import io
 import json
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
-from conftest import ROOT, alt_len_from_gfa_text
+from conftest import alt_len_from_gfa_text
 from oracle import svjg_oracle as O
 
 
@@ -23,8 +22,8 @@ NAMES = ["C2", "C3", "C4"] if os.environ.get("SVJG_TEST_FULL_ALL") else ["C2"]
 @pytest.mark.parametrize("name", NAMES)
 def test_full_size_exact_against_the_c_oracle(name):
     from svjg import alnfilter, genotype, synth
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     from oracle import c_oracle as CO
+    CO.ensure_built()
     scale = float(os.environ.get("SVJG_TEST_FULL_SCALE", "1.0"))
     g, vcf, gaf_text = synth.make_workload(name, scale=scale)
     buf = io.StringIO()
