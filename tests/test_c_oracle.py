@@ -129,3 +129,21 @@ def test_generated_workloads_match_the_python_oracle(CO, name, scale):
     assert CO.counts_dict(t, counts) == O.hit_counts(want)
     assert O.dumps_informative(d) == O.dumps_informative(want)
     assert stats["n_hits"] > 100 and stats["n_multi"] > 0
+
+
+def test_full_c2_batch_has_the_counts_the_gpu_reported(CO):
+    """The whole BASELINE.json C2 batch (3 M records, 0.5 GB) through the C oracle on the CPU: the hit and
+    multi-node record counts are the ones the CUDA path printed in every bench.py run of round 1
+    (profiles/r1/bench_final_c2.json: hits_per_gpu, multi_node_records) — and stay so if the generator or
+    either side changes."""
+    from svjg import synth
+    g, _vcf, gaf_text = synth.make_workload("C2", scale=1.0)
+    buf = io.StringIO()
+    g.write_gfa(buf)
+    t = CO.Tables(json.loads(g.edges_json()), alt_len_from_gfa_text(buf.getvalue()))
+    gaf = gaf_text.encode()
+    del gaf_text
+    counts, stats = CO.filter_counts(t, gaf)
+    assert len(gaf) == 512_635_132                              # gaf_bytes_per_gpu of that run
+    assert stats == {"n_hits": 1_108_909, "n_records": 3_000_000, "n_multi": 789_043}
+    assert int(counts.sum()) == 1_108_909
