@@ -13,9 +13,10 @@ from conftest import alt_len_from_gfa_text
 from oracle import svjg_oracle as O
 
 
-# C2 is the configuration the metric is quoted on; SVJG_TEST_FULL_ALL=1 adds the other single-GPU shapes
-# (C3: 100 k clustered SVs / 6 M records with long paths, C4: 20 k BND / 3 M records) — minutes of generation.
-NAMES = ["C2", "C3", "C4"] if os.environ.get("SVJG_TEST_FULL_ALL") else ["C2"]
+# C2 is the configuration the metric is quoted on, C4 (20 k BND / 3 M records) the one with both link directions
+# in play; SVJG_TEST_FULL_ALL=1 adds C3 (100 k clustered SVs / 6 M records with long paths: a minute of generation).
+# The C oracle alone already reproduces the hit and record counts the GPU printed for all three.
+NAMES = ["C2", "C4", "C3"] if os.environ.get("SVJG_TEST_FULL_ALL") else ["C2", "C4"]
 
 
 @pytest.mark.gpu
