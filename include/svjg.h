@@ -114,13 +114,33 @@ typedef struct svjg_filter_stats {
     uint64_t status;     /* 0, or the first SVJG_BAD_* reason                    */
     uint64_t err_offset; /* byte offset of the lowest offending line             */
     uint64_t n_generic;  /* records that took the general (quirk-exact) path     */
-    uint64_t n_exact;      /* lines the exact kernel took (irregular shape, too long for the window, no scratch) */
+    uint64_t n_exact;      /* lines the exact kernel took (irregular shape, too long for the window) */
 } svjg_filter_stats;
 
 int svjg_filter_reset(uint32_t *d_counts, uint32_t num_sv, svjg_filter_stats *d_stats, void *stream);
 int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset,
                        int64_t d_over, uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off,
                        uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream);
+
+/* Measurement and test aids of the filter (no reference analogue; process-wide, not thread-safe against
+ * running filter calls).
+ *   svjg_filter_profile(1)   every later svjg_filter_device call records CUDA events around its scan
+ *                            kernel on the caller's stream; svjg_filter_scan_ms() waits for the last such
+ *                            call on the current device and returns that kernel's duration
+ *   svjg_filter_tune(knob, value)   value 0 restores the default
+ *     SVJG_TUNE_TILE_BYTES   bytes of the shard a warp owns per step, instead of the probe kernel's choice
+ *     SVJG_TUNE_TILE_LINES   lines a tile should hold (the probe kernel's target; default 30)
+ *     SVJG_TUNE_SCAN_BLOCKS  blocks per SM the scan kernel is sized for (6 or 8): trades window size for warps
+ *     SVJG_TUNE_SCAN_ONLY    1: the scan kernel stops behind its byte-class phase, nothing else runs
+ *     SVJG_TUNE_POOL_UNITS   16-byte units of the exact kernel's bump pool (forces its no-room fallbacks) */
+#define SVJG_TUNE_TILE_BYTES 1
+#define SVJG_TUNE_TILE_LINES 2
+#define SVJG_TUNE_SCAN_BLOCKS 3
+#define SVJG_TUNE_SCAN_ONLY 4
+#define SVJG_TUNE_POOL_UNITS 5
+int svjg_filter_tune(int knob, int value);
+int svjg_filter_profile(int enable);
+int svjg_filter_scan_ms(float *ms);
 
 /* Lines end at '\n'.  The reference opens the GAF in text mode, where "\r\n" and a lone "\r" end a
  * line as well (and are stored as "\n"): a caller whose bytes may contain carriage returns translates

@@ -6,41 +6,43 @@
 // read_gaf_line :184-198, extract_nodes :351-373, get_aln_links :200-219,
 // reverse_link :221-225, check_bkpt_overlap :258-273, get_node_len :343-349.
 //
-// The work is a chain of four kernels; a compacted list of link records in device scratch
-// memory connects scan_parse and link:
+// The work is a chain of three kernels:
 //   probe       one block: line length at the head of the shard -> bytes per tile, so that a tile
 //               holds about one line per lane of the warp that parses it; zeroes the list cursors.
-//   scan_parse  every WARP is an independent worker with its own shared-memory window
-//               (no block barrier).  It walks tiles of at most 5 KiB of the byte buffer; a tile
-//               plus 1 KiB of look-ahead is staged by one TMA bulk copy.
+//   scan        every WARP is an independent worker with its own shared-memory window
+//               (no block barrier).  It walks tiles of the byte buffer; a tile plus 1 KiB of
+//               look-ahead is staged by one TMA bulk copy (the warp's next tile is prefetched into L2).
 //               A  byte-parallel: every lane classifies 32 bytes with SWAR compares into four
-//                  bitmaps (newline, tab, '<'/'>', non-digit); one warp scan turns the newline
-//                  bitmap into the ordered list of line ends;
+//                  classes (newline, tab, '<'/'>', non-digit); the newlines go straight into the
+//                  ordered list of line ends, the others into three bitmaps (tabs, non-digits, node
+//                  starts = a byte that is no delimiter right behind one);
 //               B  line-parallel: one lane per line reads the line's shape off runs of the tab and
 //                  non-digit bitmaps (12 columns, integer columns of digits only, none empty),
 //                  counts the path nodes and parses Tlen/Ts/Te of the lines with >= 2 of them;
 //               C  node-parallel: one lane per path node of those lines, still from shared
-//                  memory: chrom:start-end / chrom:pos.k -> exact 24-byte key -> one probe of
-//                  the plain-node table (node id, alt length);
+//                  memory: the name is read from its end (digits, '-' or '.', digits, ':', chrom)
+//                  with SWAR decimal parses -> exact 24-byte key -> one probe of the plain-node
+//                  table (node id, alt length, the roles the node has in link keys);
 //               D  same lanes: node-length prefix sums, the breakpoint-overlap verdict of
-//                  every link (:269-273), the first-occurrence hazard (:206), and one 16-byte
-//                  link record (integer link key, line offset, line length) per link that
-//                  can have hits.  Lines with 33-256 nodes: long_line(), 32 nodes a step.
+//                  every link (:269-273), the first-occurrence hazard (:206), and for every link
+//                  that can have hits ONE probe of the link table, made by all lanes together;
+//                  hit tuples are appended with one cursor atomic per round, counters by RED.
+//                  Lines with 33-256 nodes: long_line(), 32 nodes a step.
 //               Lines that are not of the plain shape, or do not fit the window, go to the
 //               "exact" list.
-//   link        one thread per link record: forward and reverse key probes of the link
-//               hash, warp-aggregated counter atomics and hit tuples.
 //   exact       irregular lines.  parse_fields() / general() follow the reference's string
 //               semantics literally (odd integers, odd node names, names that could be
 //               substrings of earlier ones ...); a regular line that was merely too long for the
 //               window gets the fast rules applied where it lies (giant_line()).
-// The GAF bytes are read from DRAM once (scan_parse); only the exact route reads them again.
+// The GAF bytes are read from DRAM once (scan); only the exact route reads them again.
 // A line belongs to the tile its first byte is in.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "svjg_internal.h"
 
@@ -49,60 +51,54 @@ using namespace svjg;
 
 namespace {
 
-constexpr int TILE_MAX = 5024;                 // most bytes a warp owns per step; the launch picks the tile so that a
-constexpr int TILE_MIN = 1024;                 // tile holds about TILE_LINES lines = one line per lane (probe_kernel)
-constexpr int TILE_LINES = 30;
+constexpr int TILE_MIN = 1024;                 // the launch picks the tile so that a tile holds about TILE_LINES lines
+constexpr int TILE_LINES = 30;                 // = one line per lane (probe_kernel), within Geo::tile_max
 constexpr int LOOKAHEAD = 1024;                // staged behind the tile so that lines starting in it are whole
 constexpr int HEAD = 32;                       // staged in front of it (the newline that starts the first line)
-constexpr int WIN = HEAD + TILE_MAX + LOOKAHEAD;   // 6080 = 32 * 190
 constexpr int WARPS = 4;                       // per block; warps never synchronise with each other
 constexpr int THREADS = WARPS * 32;
-constexpr int NPAIRS = WIN / 32;               // 32-byte pairs of 16-byte chunks
 constexpr int SPARE = 32;                      // readable (zero) bytes behind the window
-constexpr int NLCAP = 320;                     // newlines per window (more => some line is shorter than 20 bytes)
-constexpr int TOKCAP = 32;                     // path nodes resolved per round of phases C/D (one lane each)
-static_assert(WIN % 32 == 0 && WIN + SPARE <= 65536, "window offsets are 16 bit");
 
-// shared memory map of ONE warp of scan_parse (bytes)
-constexpr int OFF_WIN = 0;
-constexpr int BMWORDS = NPAIRS + 3;                         // bitmap words: reads may run a few words past the window
-constexpr int NLW = (NPAIRS + 31) / 32;                     // newline bitmap words a lane turns into list entries
-constexpr int OFF_NL = OFF_WIN + WIN + SPARE;               // newline bitmap u32[BMWORDS] during phase A, then the
-constexpr int NL_BYTES = BMWORDS * 4 > NLCAP * 2 ? BMWORDS * 4 : NLCAP * 2;   // newline positions, ascending, u16[NLCAP]
-constexpr int OFF_TABB = (OFF_NL + NL_BYTES + 15) & ~15;    // tab bitmap        u32[BMWORDS]
-constexpr int OFF_DLB = OFF_TABB + BMWORDS * 4;             // delimiter bitmap  u32[BMWORDS]
-constexpr int OFF_XDB = OFF_DLB + BMWORDS * 4;              // non-digit bitmap  u32[BMWORDS]
-constexpr int OFF_TKO = OFF_XDB + BMWORDS * 4;              // lanes of the lines of a round, in order  u8[TOKCAP]
-constexpr int WARP_SMEM = (OFF_TKO + TOKCAP + 127) & ~127;
-constexpr int SMEM_BYTES = WARP_SMEM * WARPS;
+// shared memory of ONE warp of the scan kernel, fixed per device at the first launch (svjg::DevCfg):
+// the window, the newline list, three bitmaps over the window's bytes, the lanes of a round's lines
+struct Geo {
+    uint32_t tile_max;    // most bytes a warp owns per step, a multiple of 32
+    uint32_t win;         // HEAD + tile_max + LOOKAHEAD: window bytes (a multiple of 32, < 64 Ki: offsets are 16 bit)
+    uint32_t nlcap;       // newline list entries (more newlines in a window => some line is shorter than 20 bytes)
+    uint32_t bmwords;     // words per bitmap: reads may run a few words past the window
+    uint32_t off_nl, off_tab, off_xd, off_ns, off_tko, warp_smem;
+    uint32_t tile_lines;  // lines a tile should hold (probe_kernel): about one per lane
+};
+Geo make_geo(uint32_t tile_max) {
+    Geo g;
+    g.tile_max = tile_max & ~31u;
+    g.win = HEAD + g.tile_max + LOOKAHEAD;
+    g.nlcap = g.win / 20u + 1u;
+    g.bmwords = g.win / 32u + 3u;
+    g.off_nl = g.win + SPARE;
+    g.off_tab = (g.off_nl + 2u * g.nlcap + 15u) & ~15u;
+    g.off_xd = g.off_tab + 4u * g.bmwords;
+    g.off_ns = g.off_xd + 4u * g.bmwords;
+    g.off_tko = g.off_ns + 4u * g.bmwords;
+    g.warp_smem = (g.off_tko + 32u + 127u) & ~127u;
+    g.tile_lines = TILE_LINES;
+    return g;
+}
 
 constexpr int FLAT_THREADS = 256;              // block size of the flat (grid-stride) kernels
 
 constexpr uint32_t FLAG_EXACT_CHECKS = SVJG_FLAG_EXACT_CHECKS;   // probe links whose overlap test fails too
 constexpr uint32_t FLAG_FORCE_GENERAL = SVJG_FLAG_FORCE_GENERAL; // test hook: every multi-node line through general()
+constexpr uint32_t FLAG_STOP_AFTER_SCAN = 1u << 8;               // measurement aid: phase A only (SVJG_TUNE_SCAN_ONLY)
 constexpr uint32_t COMMA_PATH = 0xFFFFFFFFu;
-
-constexpr uint64_t LINK_HOLE = ~0ull;           // link record that was reserved but not filled
-constexpr uint32_t LINK_OK = 0x80000000u;       // in LinkRec::len: the breakpoint-overlap test passed
-constexpr uint32_t LINK_DIRS_SHIFT = 29;        //   bits 29, 30: the forward / the reverse key can exist (link_dirs())
-constexpr uint32_t LINK_LEN = 0x1FFFFFFFu;
-
-// a link of a multi-node line that passed phases C/D
-struct LinkRec {
-    uint64_t key;         // link_key(idL, sL, idR, sR)
-    uint32_t off;         // first byte of the line (offset into the shard)
-    uint32_t len;         // bytes of the line incl. its newline | link_dirs() << 29 | LINK_OK
-};
-static_assert(sizeof(LinkRec) == 16, "LinkRec is 16 bytes");
 
 // device scratch of one svjg_filter_device() call
 struct Scratch {
-    uint32_t *cnt;        // [0] link records, [2] exact-route lines, [4] bytes per tile, [5] pool cursor
-    LinkRec *links;
+    uint32_t *cnt;        // [2] exact-route lines, [4] bytes per tile, [5] pool cursor
     uint32_t *exact;      // line start offsets
-    uint4 *slab;          // per warp of scan_parse: nodes of a long line (long_line())
-    uint4 *pool;          // exact kernel: bitmap and nodes of giant lines, bump-allocated (cnt[5])
-    uint32_t cap_links, cap_exact, cap_pool;
+    uint4 *slab;          // per warp of the scan kernel: nodes of a long line (long_line())
+    uint4 *pool;          // exact kernel: bitmaps and nodes of giant lines, bump-allocated (cnt[5])
+    uint32_t cap_exact, cap_pool;
 };
 
 struct FilterArgs {
@@ -119,6 +115,7 @@ struct FilterArgs {
     uint32_t flags;
     uint32_t one;                // 1 (see IsNewline)
     Scratch sc;
+    Geo geo;
 };
 
 struct Local {
@@ -761,6 +758,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// hint: bring [src, src + bytes) into L2 (16-byte aligned, a multiple of 16 bytes)
+__device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lds32(const uint8_t *win, uint32_t a) { return *reinterpret_cast<const uint32_t *>(win + a); }
 
 // any ',' in window bytes [lo, hi), hi > lo
@@ -879,135 +881,188 @@ __device__ __forceinline__ uint32_t link_dirs(uint32_t rolesA, uint32_t sA, uint
     return fwd | (rev << 1);
 }
 
-// ---- phase C: the idx-th node of the path [lps, lpe) -- strand, exact key, table probe, length
+// ---- byte sources of the node parser: a warp's window in shared memory, or the shard where it lies
+struct SmemBytes {
+    const uint8_t *p;
+    __device__ __forceinline__ uint32_t u8(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ uint32_t u32(uint32_t al) const { return *reinterpret_cast<const uint32_t *>(p + al); }
+};
+struct ShardBytes {
+    const FilterArgs *a;
+    __device__ __forceinline__ uint32_t u8(uint32_t i) const { return i < a->n ? __ldg(a->gaf + i) : 0u; }
+    __device__ __forceinline__ uint32_t u32(uint32_t al) const { return gaf_word(*a, al); }
+};
+
+// the n (1..9) decimal digits that end in front of byte `hi` (validated: digits only)
+template <class B>
+__device__ __forceinline__ uint32_t dec9(const B &src, uint32_t hi, uint32_t n) {
+    const uint32_t base = hi - 8u, al = base & ~3u, sh = (base & 3u) * 8u;
+    const uint32_t r0 = src.u32(al), r1 = src.u32(al + 4), r2 = src.u32(al + 8);
+    const int m = 8 - int(min(n, 8u));           // bytes of the eight that are not ours
+    const uint32_t g0 = dec4(clear_low_bytes(__funnelshift_r(r0, r1, sh), m));
+    const uint32_t g1 = dec4(clear_low_bytes(__funnelshift_r(r1, r2, sh), m - 4));
+    uint32_t v = g0 * 10000u + g1;
+    if (n == 9u) v += (src.u8(hi - 9u) - '0') * 100000000u;
+    return v;
+}
+
+// ---- phase C: the node whose name is the bytes [tpos, tend) -- exact key, table probe, length.
+// Read from the end: digits, '-' or '.', digits, ':', chrom (see PNodeSlot).  xdb: the non-digit bitmap.
 struct Node {
     uint32_t nid = NO_NODE;   // node id; NO_NODE: the name is in no link key
     uint32_t nlen = 0;        // get_node_len (:343-349)
     uint32_t akey = 0;        // start value and kind: equal ones in a path mean the first-occurrence rules may bite
-    uint32_t plus = 0;        // the delimiter in front is '>'
     uint32_t roles = 0;       // PNodeSlot roles: bit s = left node of some key with strand s, bit 2+s = right node
-    uint32_t end = 0;         // window position behind the name (a delimiter, or the end of the path)
-    bool plain = false;       // chrom:start-end or chrom:pos.k of the exact-key form, with a length
+    bool plain = false;       // a plain name with a length
 };
-template <bool LONG>
-__device__ __forceinline__ Node resolve_node(const uint8_t *win, const uint32_t *dlb, const DevTables &tb, uint32_t lps,
-                                             uint32_t lpe, uint32_t idx) {
+template <class B>
+__device__ __forceinline__ Node resolve_node(const B &src, const uint32_t *xdb, const DevTables &tb, uint32_t tpos, uint32_t tend) {
     Node n;
-    // node starts: a non-delimiter byte right behind a delimiter; take the idx-th.  Aligned words of
-    // the delimiter bitmap: the bits in front of the path are masked in the first word (the byte in
-    // front of the path is a tab, so no carry comes in)
-    uint32_t w = lps >> 5, rem = idx, carry = 0, st;
-    uint32_t keep = ~low_bits(int(lps & 31u));
-    for (;;) {
-        if (LONG && w * 32u >= lpe) {  // no such node (only behind a name too long to be plain): not plain
-            n.end = lpe;
-            return n;
-        }
-        const uint32_t d = dlb[w];
-        st = ((d << 1) | carry) & ~d & keep & low_bits(int(lpe) - int(w * 32u));
-        const uint32_t c = __popc(st);
-        if (rem < c) break;
-        rem -= c;
-        carry = d >> 31;
-        keep = 0xFFFFFFFFu;
-        ++w;
-    }
-    for (; rem; --rem) st &= st - 1;
-    const uint32_t tpos = w * 32u + uint32_t(__ffs(st) - 1);
-    // its end: the next delimiter or the end of the path (a plain name has at most 36 bytes)
-    const uint32_t d0 = bm_bits(dlb, tpos) & low_bits(int(lpe - tpos));
-    uint32_t tlen;
-    if (d0) {
-        tlen = uint32_t(__ffs(d0) - 1);
-    } else {
-        const uint32_t d1 = bm_bits(dlb, tpos + 32u) & low_bits(int(lpe - tpos) - 32);
-        tlen = d1 ? 32u + uint32_t(__ffs(d1) - 1) : min(lpe - tpos, 64u);
-    }
-    n.plus = win[tpos - 1] == '>';
-    if (LONG) n.end = tpos + tlen;
-    uint64_t c0 = 0, c1 = 0;
-    uint32_t c = 0;
-    bool colon = false, clean = true;
-    for (; c < tlen && c <= 16; ++c) {                              // chrom: at most 16 bytes, no NUL
-        const uint32_t ch = win[tpos + c];
-        if (ch == ':') {
-            colon = true;
-            break;
-        }
-        if (c == 16) break;
-        clean &= ch != 0;
-        if (c < 8) c0 |= uint64_t(ch) << (8 * c);
-        else c1 |= uint64_t(ch) << (8 * (c - 8));
-    }
-    if (colon && clean) {
-        uint32_t q = tpos + c + 1;
-        const uint32_t end = tpos + tlen;
-        const uint32_t q0 = q;
-        uint32_t v0 = 0;
-        for (; q < end; ++q) {
-            const uint32_t d = uint32_t(win[q]) - '0';
-            if (d > 9) break;
-            v0 = v0 * 10 + d;
-        }
-        const uint32_t nd0 = q - q0;
-        const uint32_t sep = q < end ? win[q] : 0u;
-        if (nd0 >= 1 && nd0 <= 9 && !(nd0 > 1 && win[q0] == '0') && (sep == '-' || sep == '.')) {
-            const uint32_t q1 = ++q;
-            uint32_t v1 = 0;
-            for (; q < end; ++q) {
-                const uint32_t d = uint32_t(win[q]) - '0';
-                if (d > 9) break;
-                v1 = v1 * 10 + d;
-            }
-            const uint32_t nd1 = q - q1;
-            if (q == end && nd1 >= 1 && nd1 <= 9 && !(nd1 > 1 && win[q1] == '0')) {
-                const uint32_t kind = sep == '.' ? PN_ALT : 0u;
-                uint32_t id = NO_NODE, alt_len = PN_NO_LEN;
-                const bool found = pnode_find(tb, c0, c1, v0, v1 | kind, id, alt_len, n.roles);
-                n.akey = v0 | kind;
-                if (!kind) {
-                    if (v1 >= v0) {                                 // get_node_len :343-349
-                        n.plain = true;
-                        n.nlen = v1 - v0 + 1u;
-                        n.nid = found ? id : NO_NODE;
-                    }
-                } else if (found && alt_len != PN_NO_LEN) {         // alt_node_len[name] :346
+    const uint32_t L = tend - tpos;
+    // non-digit flags of the 32 bytes that end at tend: bit 31 = the last byte of the name; whatever
+    // lies in front of the name counts as a non-digit
+    const uint32_t Y = bm_bits(xdb, tend - 32u) | low_bits(32 - int(L));
+    const uint32_t n2 = uint32_t(__clz(int(Y)));                        // digits of the second number
+    const uint32_t n1 = uint32_t(__clz(int(Y << ((n2 + 1u) & 31u))));   // ... of the first (garbage if n2 > 9: rejected)
+    const int clen = int(L) - int(n1 + n2 + 2u);                        // bytes in front of the colon
+    if (n2 - 1u <= 8u && n1 - 1u <= 8u && uint32_t(clen) <= 15u) {
+        const uint32_t q2 = tend - n2, sep = q2 - 1u, q1 = sep - n1, col = q1 - 1u;
+        const uint32_t cs = src.u8(sep);
+        bool ok = (cs == '-' || cs == '.') && src.u8(col) == ':';
+        ok = ok && !(n1 > 1u && src.u8(q1) == '0') && !(n2 > 1u && src.u8(q2) == '0');
+        // chrom: the bytes in front of the colon as four words, cleared from the colon on; no second colon
+        const uint32_t al = tpos & ~3u, sh = (tpos & 3u) * 8u;
+        const uint32_t r0 = src.u32(al), r1 = src.u32(al + 4), r2 = src.u32(al + 8), r3 = src.u32(al + 12), r4 = src.u32(al + 16);
+        const uint32_t w0 = __funnelshift_r(r0, r1, sh) & low_bits(8 * clen);
+        const uint32_t w1 = __funnelshift_r(r1, r2, sh) & low_bits(8 * clen - 32);
+        const uint32_t w2 = __funnelshift_r(r2, r3, sh) & low_bits(8 * clen - 64);
+        const uint32_t w3 = (__funnelshift_r(r3, r4, sh) & low_bits(8 * clen - 96)) | (uint32_t(clen) << 24);
+        auto has_colon = [](uint32_t w) {
+            const uint32_t x = w ^ 0x3A3A3A3Au;
+            return (x - 0x01010101u) & ~x & SVJG_H8;
+        };
+        ok = ok && (has_colon(w0) | has_colon(w1) | has_colon(w2) | has_colon(w3 & 0x00FFFFFFu)) == 0u;
+        if (ok) {
+            const uint32_t v0 = dec9(src, sep, n1), v1 = dec9(src, tend, n2);
+            const uint32_t kind = cs == '.' ? PN_ALT : 0u;
+            uint32_t id = NO_NODE, alt_len = PN_NO_LEN;
+            const bool found = pnode_find(tb, (uint64_t(w1) << 32) | w0, (uint64_t(w3) << 32) | w2, v0, v1 | kind, id, alt_len, n.roles);
+            n.akey = v0 | kind;
+            if (!kind) {
+                if (v1 >= v0) {                                 // get_node_len :343-349
                     n.plain = true;
-                    n.nlen = alt_len;
-                    n.nid = id;
+                    n.nlen = v1 - v0 + 1u;
+                    n.nid = found ? id : NO_NODE;
                 }
+            } else if (found && alt_len != PN_NO_LEN) {         // alt_node_len[name] :346
+                n.plain = true;
+                n.nlen = alt_len;
+                n.nid = id;
             }
         }
     }
     return n;
 }
 
+// the idx-th node start of the path [lps, lpe) in the node-start bitmap (the path has more than idx nodes)
+__device__ __forceinline__ uint32_t find_node(const uint32_t *nsb, uint32_t lps, uint32_t idx) {
+    uint32_t w = lps >> 5, rem = idx;
+    uint32_t bits = nsb[w] & ~low_bits(int(lps & 31u));
+    for (;;) {
+        const uint32_t c = __popc(bits);
+        if (rem < c) break;
+        rem -= c;
+        bits = nsb[++w];
+    }
+    for (; rem; --rem) bits &= bits - 1;
+    return w * 32u + uint32_t(__ffs(bits) - 1);
+}
+// first node start at or behind `pos` and in front of `end`; `end` if there is none
+__device__ __forceinline__ uint32_t next_node(const uint32_t *nsb, uint32_t pos, uint32_t end) { return next_tab(nsb, pos, end); }
+
+// ---- hits of one link whose table slot is not the common case (a key with several entries, a poisoned
+// entry, both directions possible, a displaced slot): the general link() of the exact route
+__device__ __noinline__ void link_slow(const FilterArgs &a, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr, bool ok,
+                                       uint32_t dirs, uint32_t off, uint32_t len, Local &loc) {
+    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
+    const Rec<GmemSrc>::Tok none{0, 0};
+    rec.link(none, idl, int(sl), none, idr, int(sr), true, ok, dirs);
+    if (rec.err) report(a, rec.err, off);
+}
+
+// ---- the links of up to 32 adjacent node pairs, one per lane, all lanes of the warp together: one probe
+// of the link table each (the key the node roles allow), hit tuples appended with one cursor atomic.
+// `want`: this lane has a link to look up (both ids known, some key possible, verdict `ok` or exact checks).
+__device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr,
+                                            uint32_t dirs, bool ok, uint32_t off, uint32_t len, uint32_t lt_mask, Local &loc) {
+    uint4 sv = make_uint4(0, 0, 0, 0);
+    uint64_t key = 0;
+    if (want) {
+        key = (dirs & 1u) ? link_key(idl, sl, idr, sr) : link_key(idr, sr ^ 1u, idl, sl ^ 1u);
+        sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + (link_hash(key) & a.tb.link_mask)));
+    }
+    const bool used = (sv.w & 1u) != 0, match = used && sv.x == uint32_t(key) && sv.y == uint32_t(key >> 32);
+    // settled by this one slot: the only key that can exist is absent, or present with exactly one sound entry
+    const bool simple = want && dirs != 3u && (!used || (match && (sv.w >> 3) == 2u && sv.z != ENTRY_POISON));
+    const bool hit = simple && match;
+    if (hit) loc.n_checks++;
+    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit && ok);
+    if (hb) {
+        unsigned long long base = 0;
+        if ((hb & lt_mask) == 0u && ((hb >> (threadIdx.x & 31)) & 1u))      // the first hit lane takes the room for all
+            base = atomicAdd(a.stats + 0, (unsigned long long)__popc(hb));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(hb) - 1);
+        if (hit && ok) {
+            atomicAdd(a.counts + sv.z, 1u);
+            const unsigned long long k = base + __popc(hb & lt_mask);
+            if (k < a.hit_cap) {
+                a.hit_sv2[k] = sv.z;
+                if (a.hit_off64) a.hit_off64[k] = a.base + off;
+                else a.hit_off[k] = off;
+                a.hit_len[k] = len;
+            }
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, want && !simple)) {
+        if (want && !simple) link_slow(a, idl, sl, idr, sr, ok, dirs, off, len, loc);
+        __syncwarp();
+    }
+}
+
 // ---- a line with more path nodes than a warp has lanes: 32 nodes a step.  The first sweep resolves
 // the nodes into the warp's slab in device memory (L2) and adds up the lengths; then every node is
 // compared with all nodes in front of it (a repeated start value: exact route); the second sweep
-// writes the links.  All lanes call it together; false: the line must take the exact route.
-constexpr int SLAB_N = 256;                    // nodes of such a line (more: exact route)
+// looks the links up.  All lanes call it together; false: the line must take the exact route.
+// src / nsb / xdb: the line's bytes and bitmaps -- a warp's window (scan kernel) or the shard itself and
+// bitmaps in device memory (exact kernel: giant_line()).
+constexpr int SLAB_N = 256;                    // nodes of such a line in the scan kernel (more: exact route)
 
-// DIRECT (exact kernel, which runs behind the link kernel): the links are probed here and now instead
-// of being written as records; `win` and `dlb` may then point into device memory.
-template <bool DIRECT>
-__device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, const uint32_t *dlb, uint4 *slab,
+template <class B>
+__device__ __noinline__ bool long_line(const FilterArgs &a, const B src, const uint32_t *nsb, const uint32_t *xdb, uint4 *slab,
                                        uint32_t slab_cap, int lane, uint32_t cnt, uint32_t lps, uint32_t lpe, int64_t lts,
                                        int64_t ltail, uint32_t off, uint32_t len, Local &loc) {
     if (cnt > slab_cap) return false;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint64_t total = 0;
     bool bad = false;
-    uint32_t from = lps;
+    uint32_t from = lps;                       // the next step's first node starts at or behind this byte
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
         const bool act = c0 + uint32_t(lane) < cnt;
         Node n;
+        uint32_t tpos = lpe, plus = 0;
+        if (act) tpos = find_node(nsb, from, uint32_t(lane));
+        // the name ends in front of the delimiter of the next node, or with the path
+        uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, tpos, 1);
+        if (lane == 31 && act && c0 + 32u < cnt) nxt = next_node(nsb, tpos + 1u, lpe);
         if (act) {
-            n = resolve_node<true>(win, dlb, a.tb, from, lpe, uint32_t(lane));
-            __stcg(slab + c0 + lane, make_uint4(n.nid, n.nlen, n.akey, n.plus | (n.roles << 1)));
+            const uint32_t tend = c0 + uint32_t(lane) + 1u < cnt ? nxt - 1u : lpe;
+            plus = src.u8(tpos - 1u) == '>';
+            n = resolve_node(src, xdb, a.tb, tpos, tend);
+            __stcg(slab + c0 + lane, make_uint4(n.nid, n.nlen, n.akey, plus | (n.roles << 1)));
         }
         bad |= __any_sync(0xFFFFFFFFu, act && !n.plain);
         total += __shfl_sync(0xFFFFFFFFu, warp_incl_scan64(n.nlen, lane), 31);
-        from = __shfl_sync(0xFFFFFFFFu, n.end, 31);
+        from = __shfl_sync(0xFFFFFFFFu, nxt, 31);
     }
     __syncwarp();
     if (bad) return false;
@@ -1019,14 +1074,6 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, 
         for (uint32_t j = 0; j < upto; ++j) clash |= j < t && t < cnt && __ldcg(&slab[j].z) == mine;
     }
     if (__any_sync(0xFFFFFFFFu, clash)) return false;
-    // room for every link of the line, taken before the first one is written
-    uint32_t base = 0;
-    bool room = true;
-    if (!DIRECT) {
-        if (lane == 0) base = atomicAdd(a.sc.cnt + 0, cnt - 1u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        room = uint64_t(base) + (cnt - 1u) <= a.sc.cap_links;
-    }
     uint64_t before = 0;
     for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
         const uint32_t t = c0 + uint32_t(lane);
@@ -1037,53 +1084,47 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const uint8_t *win, 
         const uint64_t pre = before + incl - me.y;
         const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
         const uint32_t dirs = link_dirs(lf.w >> 1, lf.w & 1u, me.w >> 1, me.w & 1u);
-        const bool emit = room && lf.x != NO_NODE && me.x != NO_NODE && dirs && (ok || (a.flags & FLAG_EXACT_CHECKS));
-        if (DIRECT) {
-            if (act && t && emit) {
-                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-                const Rec<GmemSrc>::Tok none{0, 0};
-                rec.link(none, lf.x, int(lf.w & 1u), none, me.x, int(me.w & 1u), true, ok, dirs);
-                if (rec.err) report(a, rec.err, off);
-            }
-        } else if (act && t && base + t - 1u < a.sc.cap_links) {           // link t-1 of the line: a record or a hole
-            LinkRec r;
-            r.key = emit ? link_key(lf.x, lf.w & 1u, me.x, me.w & 1u) : LINK_HOLE;
-            r.off = off;
-            r.len = len | (ok ? LINK_OK : 0u) | (dirs << LINK_DIRS_SHIFT);
-            *reinterpret_cast<uint4 *>(a.sc.links + base + t - 1u) = *reinterpret_cast<const uint4 *>(&r);
-        }
+        const bool want = act && t && lf.x != NO_NODE && me.x != NO_NODE && dirs && (ok || (a.flags & FLAG_EXACT_CHECKS));
+        probe_links(a, want, lf.x, lf.w & 1u, me.x, me.w & 1u, dirs, ok, off, len, lt_mask, loc);
         before += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    return room;
+    return true;
 }
 
 // ===========================================================================
-// scan_parse: newline scan, column split, validation, path walk, node and link resolution
+// scan: newline scan, column split, validation, path walk, node and link resolution, hits
 // ===========================================================================
-__global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_constant__ FilterArgs a) {
+// Geometry of one warp's shared memory (chosen at launch, FilterArgs::geo): the window
+// (HEAD + tile_max + LOOKAHEAD bytes + SPARE), the list of newline positions, three bitmaps over the
+// window's bytes -- tabs, non-digits, node starts (a byte that is no '<' / '>' right behind one) --
+// and the lanes of a round's lines.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) scan_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     __shared__ __align__(8) uint64_t mbars[WARPS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint8_t *win = smem_all + warp * WARP_SMEM + OFF_WIN;
-    uint16_t *nl = reinterpret_cast<uint16_t *>(smem_all + warp * WARP_SMEM + OFF_NL);
-    uint32_t *tabb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_TABB);   // bit i: window byte i is a tab
-    uint32_t *dlb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_DLB);     // bit i: ... is '<' or '>'
-    uint32_t *xdb = reinterpret_cast<uint32_t *>(smem_all + warp * WARP_SMEM + OFF_XDB);     // bit i: ... is not '0'..'9'
-    uint32_t *nlb = reinterpret_cast<uint32_t *>(nl);                                        // bit i: ... is a newline (phase A only)
-    uint8_t *tko = smem_all + warp * WARP_SMEM + OFF_TKO;
+    uint8_t *wmem = smem_all + warp * a.geo.warp_smem;
+    uint8_t *win = wmem;
+    uint16_t *nl = reinterpret_cast<uint16_t *>(wmem + a.geo.off_nl);      // newline positions, ascending
+    uint32_t *tabb = reinterpret_cast<uint32_t *>(wmem + a.geo.off_tab);   // bit i: window byte i is a tab
+    uint32_t *xdb = reinterpret_cast<uint32_t *>(wmem + a.geo.off_xd);     // bit i: ... is not '0'..'9'
+    uint32_t *nsb = reinterpret_cast<uint32_t *>(wmem + a.geo.off_ns);     // bit i: ... starts a path node
+    uint8_t *tko = wmem + a.geo.off_tko;
     uint64_t *mbar = &mbars[warp];
+    const SmemBytes src{win};
 
     if (lane == 0) mbar_init(mbar, 1);
-    for (int i = lane; i < BMWORDS; i += 32) tabb[i] = 0, dlb[i] = 0, xdb[i] = 0;
-    for (int i = WIN + lane; i < WIN + SPARE; i += 32) win[i] = 0;   // never written by the copies
+    for (uint32_t i = lane; i < a.geo.bmwords; i += 32) tabb[i] = 0, xdb[i] = 0, nsb[i] = 0;
+    for (uint32_t i = a.geo.win + lane; i < a.geo.win + SPARE; i += 32) win[i] = 0;   // never written by the copies
     __syncwarp();
     uint32_t phase = 0;
     Local loc;
-    const bool stop_after_scan = ((a.flags >> 8) & 7u) == 1u;     // profiling hook (SVJG_STOP_AFTER=A)
+    uint32_t u_rec = 0, u_multi = 0;              // warp-uniform tallies (lines, lines with >= 2 nodes)
     const uint32_t one = a.one;
     const uint32_t n_workers = gridDim.x * WARPS;
+    const uint32_t nlcap = a.geo.nlcap;
 
     const uint32_t tile_bytes = a.sc.cnt[4];                       // chosen by probe_kernel: a multiple of 32
     const uint32_t n_tiles = uint32_t((a.n + tile_bytes - 1) / tile_bytes);
@@ -1105,21 +1146,26 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(mbar, bulk);
             bulk_g2s(win + dst0, a.gaf + g0, bulk, mbar);
+            // the tile this warp takes next: on its way into L2 while this one is parsed
+            const uint64_t nx = tile_start + uint64_t(n_workers) * tile_bytes;
+            if (nx + tile_bytes + LOOKAHEAD <= a.n) l2_prefetch(a.gaf + nx - HEAD, win_bytes);
         }
-        for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
-        if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;               // "newline" in front of byte 0 of the file
-        for (uint32_t i = valid_end + lane; i < win_bytes; i += 32) win[i] = 0;
+        if (bulk != nbytes || dst0 || valid_end < win_bytes) {                       // the first and the last tiles of the shard
+            for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
+            if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;           // "newline" in front of byte 0 of the file
+            for (uint32_t i = valid_end + lane; i < win_bytes; i += 32) win[i] = 0;
+        }
         if (bulk) {
             mbar_wait(mbar, phase);
             phase ^= 1;
         }
         __syncwarp();
 
-        // ---- phase A: byte classes.  A lane takes two adjacent 16-byte chunks = one word of each of the
-        // three bitmaps (newlines, tabs, path delimiters).  The scan stops behind the tile once the last
+        // ---- phase A: byte classes.  A lane takes two adjacent 16-byte chunks = one word of each bitmap;
+        // the newlines go straight into the ordered list.  The scan stops behind the tile once the last
         // owned line has its end.
         const uint32_t own_end = min(HEAD + tile_bytes, valid_end);   // lines starting before own_end are ours
-        uint32_t n_words = 0;
+        uint32_t n_nl = 0, own = 0;
         for (uint32_t c0 = 0; c0 < n_pairs; c0 += 32) {
             const uint32_t c = c0 + uint32_t(lane);
             const uint32_t p0 = c * 32u;
@@ -1129,56 +1175,48 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                 const uint4 v1 = *reinterpret_cast<const uint4 *>(win + p0 + 16);
                 m = mask16(v0, IsNewline{one}) | (mask16(v1, IsNewline{one}) << 16);
                 tabb[c] = mask16(v0, IsTab{one}) | (mask16(v1, IsTab{one}) << 16);
-                dlb[c] = mask16(v0, IsDelim{one}) | (mask16(v1, IsDelim{one}) << 16);
                 xdb[c] = mask16(v0, IsNonDigit{one}) | (mask16(v1, IsNonDigit{one}) << 16);
+                const uint32_t d = mask16(v0, IsDelim{one}) | (mask16(v1, IsDelim{one}) << 16);
+                const uint32_t left = c ? uint32_t(is_delim(win[p0 - 1u])) : 0u;     // the byte in front of these 32
+                nsb[c] = ((d << 1) | left) & ~d;
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
-                nlb[c] = m;
             }
-            n_words = min(c0 + 32u, n_pairs);
+            // newline positions, in order
+            if (__any_sync(0xFFFFFFFFu, (m & (m - 1u)) != 0u)) {
+                // two line ends in 32 bytes (hardly ever): the general placement
+                const uint32_t cnt = __popc(m), incl = warp_incl_scan(cnt, lane);
+                uint32_t idx = n_nl + incl - cnt;
+                for (uint32_t mm = m; mm; mm &= mm - 1) {
+                    const uint32_t pos = p0 + uint32_t(__ffs(mm) - 1);
+                    if (idx < nlcap) nl[idx] = uint16_t(pos);
+                    own += pos + 1u < own_end;
+                    ++idx;
+                }
+                n_nl += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            } else {
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, m != 0u);
+                if (m) {
+                    const uint32_t pos = p0 + uint32_t(__ffs(m) - 1), idx = n_nl + __popc(b & lt_mask);
+                    if (idx < nlcap) nl[idx] = uint16_t(pos);
+                    own += pos + 1u < own_end;                                 // the newline at pos starts an owned line
+                }
+                n_nl += __popc(b);
+            }
             // behind the tile: a newline at or after own_end - 1 ends the last owned line
             const bool ends_it = (m & ~low_bits(int(own_end) - 1 - int(p0))) != 0;
             if ((c0 + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, ends_it)) break;
         }
+        const uint32_t n_own = __reduce_add_sync(0xFFFFFFFFu, own);
         __syncwarp();
-        // newline bitmap -> ordered list of line ends from HEAD-1 on: every lane takes a run of words
-        // (held in registers: the list overwrites the bitmap), one warp scan places its newlines
-        uint32_t n_nl, n_own;
-        {
-            const uint32_t per = (n_words + 31u) >> 5, j0 = uint32_t(lane) * per;
-            uint32_t mw[NLW];
-            uint32_t cnt = 0, own = 0;
-#pragma unroll
-            for (int i = 0; i < NLW; ++i) {
-                const uint32_t j = j0 + uint32_t(i);
-                mw[i] = (uint32_t(i) < per && j < n_words) ? nlb[j] : 0u;
-                cnt += __popc(mw[i]);
-            }
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            n_nl = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            uint32_t idx = incl - cnt;
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < NLW; ++i) {
-                uint32_t m = mw[i];
-                while (m) {
-                    const uint32_t pos = (j0 + uint32_t(i)) * 32u + uint32_t(__ffs(m) - 1);
-                    if (idx < NLCAP) nl[idx] = uint16_t(pos);
-                    own += pos + 1u < own_end;                                 // the newline at pos starts an owned line
-                    ++idx;
-                    m &= m - 1;
-                }
-            }
-            n_own = __reduce_add_sync(0xFFFFFFFFu, own);
-        }
-        __syncwarp();
-        if (stop_after_scan) continue;
+        if (a.flags & FLAG_STOP_AFTER_SCAN) continue;                 // profiling hook (svjg_tables_set_flags)
 
-        if (n_nl > NLCAP) {
-            // that many lines in 5 KiB: some line is shorter than 20 bytes and cannot hold 12 columns
+        if (n_nl > nlcap) {
+            // that many lines in the window: some line is shorter than 20 bytes and cannot hold 12 columns
             if (lane == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
             __syncwarp();
             continue;
         }
+        u_rec += n_own;
         // ---- phase B: one lane per line, mostly bit work on the class bitmaps
         for (uint32_t k0 = 0; k0 < n_own; k0 += 32) {
             const uint32_t k = k0 + lane;
@@ -1189,7 +1227,6 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
             bool has_nl = false;
             if (k < n_own) {
                 s = uint32_t(nl[k]) + 1u;
-                loc.n_rec++;
                 if (k + 1 < n_nl) {
                     e = nl[k + 1];
                     has_nl = true;
@@ -1204,7 +1241,11 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                     // A run of digits and single tabs must follow the first tab up to the strand, and the
                     // sixth tab up to the tags (or the end of the line).  Anything else: the exact route.
                     bool plain = e > s && !py_space(win[e - 1]);
-                    const uint32_t t1 = next_tab(tabb, s, e);
+                    uint32_t t1;
+                    {
+                        const uint64_t t64 = bm64(tabb, s) & low_bits64(int(e - s));      // a read name is rarely longer
+                        t1 = t64 ? s + uint32_t(__ffsll((long long)t64)) - 1u : next_tab(tabb, min(s + 64u, e), e);
+                    }
                     plain &= t1 < e;
                     const uint32_t n2 = t1 + 1u;                                          // first byte of column 2
                     const uint32_t tw = bm_bits(tabb, n2);
@@ -1215,10 +1256,24 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                     // tabs 2, 3 and 4 and nothing else, the last one right in front of the strand, no empty column
                     plain &= __popc(ta) == 3 && (ta >> ((l2 - 1u) & 31u)) == 1u && (ta & ((ta >> 1) | 1u)) == 0;
                     const uint32_t n5 = n2 + l2;                                          // strand
-                    ps = next_tab(tabb, n5, e) + 1u;
-                    pe = next_tab(tabb, ps, e);
+                    // a one-byte strand column as a rule: its tab is in the bits at hand
+                    ps = (l2 < 31u && ((tw >> (l2 + 1u)) & 1u)) ? n5 + 2u : next_tab(tabb, min(n5, e), e) + 1u;
+                    // the path column ends at the next tab; its node starts are counted on the way
+                    uint32_t ntok = 0;
+                    pe = e;
+                    for (uint32_t q = ps; q < e; q += 32) {
+                        const uint32_t tb = bm_bits(tabb, q) & low_bits(int(e - q));
+                        const uint32_t nb = bm_bits(nsb, q);
+                        if (tb) {
+                            const uint32_t r = uint32_t(__ffs(tb)) - 1u;
+                            pe = q + r;
+                            ntok += __popc(nb & low_bits(int(r)));
+                            break;
+                        }
+                        ntok += __popc(nb);
+                    }
                     plain &= pe < e && pe > ps;
-                    const uint32_t n7 = pe + 1u;                                          // first byte of column 7
+                    const uint32_t n7 = min(pe + 1u, e);                                  // first byte of column 7
                     uint64_t tt = bm64(tabb, n7);
                     const uint64_t xt = bm64(xdb, n7) & ~tt;
                     plain &= xt != 0;
@@ -1244,18 +1299,9 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                     } else if (!is_delim(win[ps])) {
                         // bare name or GFA-style a+,b+ (extract_nodes :369-373): one piece without ',' is one node
                         exact = has_comma(win, ps, pe);
-                    } else {
-                        // token starts: a non-delimiter byte right after a delimiter
-                        uint32_t ntok = 0, carry = 0;
-                        for (uint32_t q = ps; q < pe; q += 32) {
-                            const uint32_t d = bm_bits(dlb, q);
-                            ntok += __popc(((d << 1) | carry) & ~d & low_bits(int(pe - q)));
-                            carry = d >> 31;
-                        }
-                        if (ntok >= 2) {                                                   // :133
-                            if (a.flags & FLAG_FORCE_GENERAL) exact = true;
-                            else want = ntok;
-                        }
+                    } else if (ntok >= 2) {                                                // :133
+                        if (a.flags & FLAG_FORCE_GENERAL) exact = true;
+                        else want = ntok;
                     }
                 }
             }
@@ -1272,37 +1318,43 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                     want = 0;
                 }
             }
-            // ---- phases C and D: rounds of at most TOKCAP path nodes, whole lines only, one lane per node
-            uint32_t pend = want > TOKCAP ? 0u : want;
-            for (;;) {
-                if (__ballot_sync(0xFFFFFFFFu, pend != 0) == 0) break;
+            const uint32_t l_off = wbase + s, l_len = e - s + (has_nl ? 1u : 0u);
+            // ---- phases C and D: rounds of at most 32 path nodes, whole lines only, one lane per node
+            uint32_t pend = want > 32u ? 0u : want;
+            while (__any_sync(0xFFFFFFFFu, pend != 0)) {
                 const uint32_t incl = warp_incl_scan(pend, lane);
-                const bool take = pend != 0 && incl <= TOKCAP;                  // a prefix of the pending lines
+                const bool take = pend != 0 && incl <= 32u;                     // a prefix of the pending lines
                 const uint32_t takeb = __ballot_sync(0xFFFFFFFFu, take);
                 const uint32_t ntk = __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(takeb));
                 const uint32_t first = incl - pend;                             // list slot of this line's first node
                 // no list of nodes is written: a node lane finds its line from the bit mask of the lines'
-                // first slots, and its own start and end in the delimiter bitmap
+                // first slots, and its own start in the node-start bitmap
                 const uint32_t startmask = __reduce_or_sync(0xFFFFFFFFu, take ? (1u << first) : 0u);
                 if (take) tko[__popc(takeb & lt_mask)] = uint8_t(lane);             // ordinal among the taken lines -> lane
                 __syncwarp();
                 const bool is_tok = uint32_t(lane) < ntk;
-                uint32_t own = 0, idx = 0;
+                uint32_t own_l = 0, idx = 0;
                 if (is_tok) {
                     const uint32_t below = startmask & (0xFFFFFFFFu >> (31 - lane));
-                    own = tko[__popc(below) - 1];
+                    own_l = tko[__popc(below) - 1];
                     idx = uint32_t(lane) - uint32_t(31 - __clz(below));             // number of this node in its line
                 }
-                const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), own);
-                // C: this lane's node
+                const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), own_l);
+                const uint32_t lcnt = __shfl_sync(0xFFFFFFFFu, pend, own_l);
+                // C: this lane's node; its name ends in front of the next node's delimiter, or with the path
+                uint32_t tpos = 0;
+                if (is_tok) tpos = find_node(nsb, lpath & 0xFFFFu, idx);
+                const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, tpos, 1);
                 Node nd;
-                if (is_tok) nd = resolve_node<false>(win, dlb, a.tb, lpath & 0xFFFFu, lpath >> 16, idx);
-                const uint32_t nid = nd.nid, nlen = nd.nlen, akey = nd.akey, plus = nd.plus;
-                const bool plain = nd.plain;
+                uint32_t plus = 0;
+                if (is_tok) {
+                    plus = win[tpos - 1u] == '>';
+                    nd = resolve_node(src, xdb, a.tb, tpos, idx + 1u < lcnt ? nxt - 1u : lpath >> 16);
+                }
+                const uint32_t nid = nd.nid, nlen = nd.nlen, akey = nd.akey;
                 // D: per line -- sums of the node lengths left of every node, names that repeat a start
                 // value (the first-occurrence rules :206 and :269-271 would bite: exact route), verdicts
                 const uint32_t lfirst = uint32_t(lane) - idx;
-                const uint32_t lcnt = __shfl_sync(0xFFFFFFFFu, pend, own);
                 // a repeated start value: some other lane of the line holds the same key (one MATCH)
                 const uint32_t line_lanes = low_bits(int(lcnt)) << lfirst;
                 const bool clash = (__match_any_sync(0xFFFFFFFFu, akey) & line_lanes & ~(1u << lane)) != 0;
@@ -1315,54 +1367,33 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
                     if (uint32_t(d) <= idx) lsum += o;
                 }
                 const uint64_t pre = lsum - nlen;
-                const uint32_t bad = __reduce_or_sync(0xFFFFFFFFu, (is_tok && (!plain || clash)) ? (1u << own) : 0u);
-                const uint64_t total = __shfl_sync(0xFFFFFFFFu, pre + nlen, is_tok ? lfirst + lcnt - 1u : 0u);
+                const uint32_t bad = __reduce_or_sync(0xFFFFFFFFu, (is_tok && (!nd.plain || clash)) ? (1u << own_l) : 0u);
+                const uint64_t total = __shfl_sync(0xFFFFFFFFu, lsum, is_tok ? lfirst + lcnt - 1u : 0u);
                 const uint32_t idl = __shfl_up_sync(0xFFFFFFFFu, nid, 1), sl = __shfl_up_sync(0xFFFFFFFFu, plus, 1);
-                const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, own), ltail = __shfl_sync(0xFFFFFFFFu, tail, own);
-                const uint32_t loff = __shfl_sync(0xFFFFFFFFu, s, own);
-                const uint32_t llen = __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), own);
+                const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, own_l), ltail = __shfl_sync(0xFFFFFFFFu, tail, own_l);
+                const uint32_t loff = __shfl_sync(0xFFFFFFFFu, l_off, own_l), llen = __shfl_sync(0xFFFFFFFFu, l_len, own_l);
                 const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
                 const uint32_t dirs = link_dirs(__shfl_up_sync(0xFFFFFFFFu, nd.roles, 1), sl, nd.roles, plus);
-                const bool emit = is_tok && idx >= 1 && !((bad >> own) & 1u) && idl != NO_NODE && nid != NO_NODE && dirs &&
+                const bool look = is_tok && idx >= 1 && !((bad >> own_l) & 1u) && idl != NO_NODE && nid != NO_NODE && dirs &&
                                   (ok || (a.flags & FLAG_EXACT_CHECKS));
-                uint32_t redo = bad;                                                // lines of this round for the exact route
-                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, emit);
-                if (eb) {
-                    const uint32_t n_new = __popc(eb);
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(a.sc.cnt + 0, n_new);
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    const uint32_t slot = base + __popc(eb & lt_mask);
-                    const bool room = uint64_t(base) + n_new <= a.sc.cap_links;
-                    if (!room) redo = takeb;                                        // scratch exhausted: exact route for all
-                    if (emit && slot < a.sc.cap_links) {
-                        LinkRec r;
-                        r.key = room ? link_key(idl, sl, nid, plus) : LINK_HOLE;
-                        r.off = wbase + loff;
-                        r.len = llen | (ok ? LINK_OK : 0u) | (dirs << LINK_DIRS_SHIFT);
-                        *reinterpret_cast<uint4 *>(a.sc.links + slot) = *reinterpret_cast<const uint4 *>(&r);
-                    }
-                }
+                probe_links(a, look, idl, sl, nid, plus, dirs, ok, loff, llen, lt_mask, loc);
                 if (take) {
-                    if ((redo >> lane) & 1u) exact = true;
-                    else loc.n_multi++;
+                    if ((bad >> lane) & 1u) exact = true;
                     pend = 0;
                 }
+                u_multi += __popc(takeb & ~bad);
                 __syncwarp();
             }
             // ---- lines with more nodes than a round has lanes: one line at a time (long_line())
-            for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > TOKCAP); longb; longb &= longb - 1) {
+            for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > 32u); longb; longb &= longb - 1) {
                 const int L = __ffs(longb) - 1;
                 const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), L);
-                const bool done = long_line<false>(a, win, dlb, a.sc.slab + size_t(blockIdx.x * WARPS + warp) * SLAB_N, SLAB_N,
-                                                   lane, __shfl_sync(0xFFFFFFFFu, want, L), lpath & 0xFFFFu, lpath >> 16,
-                                                   __shfl_sync(0xFFFFFFFFu, ts, L), __shfl_sync(0xFFFFFFFFu, tail, L),
-                                                   wbase + __shfl_sync(0xFFFFFFFFu, s, L),
-                                                   __shfl_sync(0xFFFFFFFFu, e - s + (has_nl ? 1u : 0u), L), loc);
-                if (lane == L) {
-                    if (!done) exact = true;
-                    else loc.n_multi++;
-                }
+                const bool done = long_line(a, src, nsb, xdb, a.sc.slab + size_t(blockIdx.x * WARPS + warp) * SLAB_N, SLAB_N, lane,
+                                            __shfl_sync(0xFFFFFFFFu, want, L), lpath & 0xFFFFu, lpath >> 16,
+                                            __shfl_sync(0xFFFFFFFFu, ts, L), __shfl_sync(0xFFFFFFFFu, tail, L),
+                                            __shfl_sync(0xFFFFFFFFu, l_off, L), __shfl_sync(0xFFFFFFFFu, l_len, L), loc);
+                if (!done && lane == L) exact = true;
+                u_multi += done;
             }
             const uint32_t xb = __ballot_sync(0xFFFFFFFFu, exact);
             if (xb) {
@@ -1378,77 +1409,9 @@ __global__ void __launch_bounds__(THREADS, 6) scan_parse_kernel(const __grid_con
         }
         __syncwarp();
     }
-    add_stats(a, loc);
-}
-
-// ===========================================================================
-// link: one thread per link record, both keys
-// ===========================================================================
-constexpr int LINK_STAGE = 2048;    // hits a block stages between flushes
-constexpr int LINK_PER_THREAD = 2;  // link records a thread takes per round (their probes are in flight together)
-constexpr int LINK_ROUNDS = 3;      // rounds between flushes: at one hit per record 1536 of the 2048 slots
-
-__global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_constant__ FilterArgs a) {
-    __shared__ uint32_t h_sv[LINK_STAGE], h_off[LINK_STAGE], h_len[LINK_STAGE];
-    __shared__ uint32_t h_n;
-    __shared__ unsigned long long h_base;
-    const uint32_t n_links = min(a.sc.cnt[0], a.sc.cap_links);
-    Local loc;
-    if (threadIdx.x == 0) h_n = 0;
-    __syncthreads();
-    constexpr uint32_t PER_ROUND = FLAT_THREADS * LINK_PER_THREAD;
-    uint32_t round = 0;
-    for (uint32_t t0 = blockIdx.x * PER_ROUND; t0 < n_links; t0 += gridDim.x * PER_ROUND) {
-        uint4 r[LINK_PER_THREAD];
-#pragma unroll
-        for (int k = 0; k < LINK_PER_THREAD; ++k) {
-            const uint32_t t = t0 + uint32_t(k) * FLAT_THREADS + threadIdx.x;
-            r[k] = t < n_links ? __ldg(reinterpret_cast<const uint4 *>(a.sc.links) + t) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
-        }
-#pragma unroll
-        for (int k = 0; k < LINK_PER_THREAD; ++k) {
-            const uint64_t key = (uint64_t(r[k].y) << 32) | r[k].x;
-            if (key != LINK_HOLE) {
-                Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, r[k].z, r[k].w & LINK_LEN, loc);
-                rec.stage_sv = h_sv;
-                rec.stage_off = h_off;
-                rec.stage_len = h_len;
-                rec.stage_n = &h_n;
-                rec.stage_cap = LINK_STAGE;
-                const Rec<GmemSrc>::Tok none{0, 0};
-                rec.link(none, uint32_t(key >> 33), int((key >> 32) & 1u), none, uint32_t(key) >> 1, int(key & 1u), true,
-                         (r[k].w & LINK_OK) != 0, (r[k].w >> LINK_DIRS_SHIFT) & 3u);
-                if (rec.err) report(a, rec.err, r[k].z);
-            }
-        }
-        // flush the staged hits every few rounds and at the end: one cursor atomic for the block,
-        // coalesced tuple stores, warp-aggregated counter atomics
-        ++round;
-        const bool last = t0 + gridDim.x * PER_ROUND >= n_links;
-        if (round % LINK_ROUNDS != 0 && !last) continue;
-        __syncthreads();
-        const uint32_t n = min(h_n, uint32_t(LINK_STAGE));
-        if (threadIdx.x == 0 && n) h_base = atomicAdd(a.stats + 0, (unsigned long long)n);
-        __syncthreads();
-        for (uint32_t i0 = 0; i0 < n; i0 += FLAT_THREADS) {
-            const uint32_t i = i0 + threadIdx.x;
-            const bool act = i < n;
-            const uint32_t sv2 = act ? h_sv[i] : 0xFFFFFFFFu;
-            const unsigned peers = __match_any_sync(0xFFFFFFFFu, sv2);
-            if (act) {
-                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(a.counts + sv2, uint32_t(__popc(peers)));
-                const unsigned long long k = h_base + i;
-                if (k < a.hit_cap) {
-                    a.hit_sv2[k] = sv2;
-                    if (a.hit_off64) a.hit_off64[k] = a.base + h_off[i];
-                    else a.hit_off[k] = h_off[i];
-                    a.hit_len[k] = h_len[i];
-                }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) h_n = 0;
-        __syncthreads();
+    if (lane == 0) {
+        loc.n_rec = u_rec;
+        loc.n_multi = u_multi;
     }
     add_stats(a, loc);
 }
@@ -1456,31 +1419,41 @@ __global__ void __launch_bounds__(FLAT_THREADS, 4) link_kernel(const __grid_cons
 // ===========================================================================
 // exact: one thread per irregular line — the reference's string semantics, literally
 // ===========================================================================
-// A line that is regular but too long for scan_parse's window (thousands of path nodes): the warp
-// builds the delimiter bitmap of its path column in device memory and runs long_line() on the bytes
-// where they lie.  false: general() decides.
+// A line that is regular but too long for the scan kernel's window (thousands of path nodes): the warp
+// builds the node-start and non-digit bitmaps of its path column in device memory and runs long_line() on
+// the bytes where they lie.  false: general() decides.
 __device__ __noinline__ bool giant_line(const FilterArgs &a, uint32_t ps, uint32_t pe, uint32_t ntok, int64_t ts, int64_t tail,
                                         uint32_t off, uint32_t len, int lane, Local &loc) {
-    const uint32_t w0 = ps >> 5, nw = (pe >> 5) - w0 + 4u;                 // bitmap words, a few to spare for reads ahead
-    const uint32_t need = (nw + 3u) / 4u + ntok;                            // in 16-byte units: bitmap, then one per node
+    if (ps < 64u) return false;                                             // the node parser looks 32 bytes back
+    const uint32_t w0 = (ps >> 5) - 1u, nw = (pe >> 5) - w0 + 4u;          // bitmap words, a few to spare on both sides
+    const uint32_t bm16 = (nw + 3u) / 4u;                                   // one bitmap in 16-byte units
+    const uint32_t need = 2u * bm16 + ntok;                                 // two bitmaps, then one unit per node
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(a.sc.cnt + 5, need);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (uint64_t(base) + need > a.sc.cap_pool) return false;
-    uint32_t *bits = reinterpret_cast<uint32_t *>(a.sc.pool + base);
+    uint32_t *nsb = reinterpret_cast<uint32_t *>(a.sc.pool + base), *xdb = reinterpret_cast<uint32_t *>(a.sc.pool + base + bm16);
     for (uint32_t w = uint32_t(lane); w < nw; w += 32) {
         const uint64_t pos = uint64_t(w0 + w) * 32u;
-        uint32_t m = 0;
+        uint32_t d = 0, x = 0;
         if (pos + 32 <= a.n) {
             const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(a.gaf + pos)), v1 = __ldg(reinterpret_cast<const uint4 *>(a.gaf + pos + 16));
-            m = mask16(v0, IsDelim{1u}) | (mask16(v1, IsDelim{1u}) << 16);
+            d = mask16(v0, IsDelim{1u}) | (mask16(v1, IsDelim{1u}) << 16);
+            x = mask16(v0, IsNonDigit{1u}) | (mask16(v1, IsNonDigit{1u}) << 16);
         } else {
-            for (uint32_t k = 0; k < 32 && pos + k < a.n; ++k) m |= uint32_t(is_delim(__ldg(a.gaf + pos + k))) << k;
+            for (uint32_t k = 0; k < 32; ++k) {
+                const uint32_t c = pos + k < a.n ? uint32_t(__ldg(a.gaf + pos + k)) : 0u;
+                d |= uint32_t(is_delim(c)) << k;
+                x |= uint32_t(c - '0' > 9u) << k;
+            }
         }
-        __stcg(bits + w, m);
+        const uint32_t left = uint32_t(is_delim(__ldg(a.gaf + pos - 1)));   // pos >= 32
+        __stcg(nsb + w, ((d << 1) | left) & ~d);
+        __stcg(xdb + w, x);
     }
     __syncwarp();
-    return long_line<true>(a, a.gaf, bits - w0, a.sc.pool + base + (nw + 3u) / 4u, ntok, lane, ntok, ps, pe, ts, tail, off, len, loc);
+    return long_line(a, ShardBytes{&a}, nsb - w0, xdb - w0, a.sc.pool + base + 2u * bm16, ntok, lane, ntok, ps, pe, ts, tail, off, len,
+                     loc);
 }
 
 __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_constant__ FilterArgs a) {
@@ -1543,22 +1516,23 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const __grid_const
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&total, cnt);
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t tile = TILE_MAX;
+        const uint32_t tile_max = a.geo.tile_max;
+        uint32_t tile = tile_max;
         if (total) {
-            const uint64_t want = uint64_t(n16) * 16ull * TILE_LINES / total;
-            tile = uint32_t(want < uint64_t(TILE_MAX) ? want : uint64_t(TILE_MAX)) & ~31u;
+            const uint64_t want = uint64_t(n16) * 16ull * a.geo.tile_lines / total;
+            tile = uint32_t(want < uint64_t(tile_max) ? want : uint64_t(tile_max)) & ~31u;
         }
-        if (const uint32_t forced = (a.flags >> 16)) tile = forced & ~31u;    // test hook (SVJG_TILE_BYTES)
+        if (const uint32_t forced = (a.flags >> 16)) tile = forced & ~31u;    // SVJG_TUNE_TILE_BYTES
         if (total) {
             // phase A scans 1 KiB a step and stops behind the tile once a line end is found: let a step
             // end about 1.5 lines behind the tile, so that step is rarely followed by one more
             const uint64_t s15 = uint64_t(n16) * 24ull / total;                 // 1.5 lines
             const uint32_t slack = uint32_t(s15 < 512 ? s15 : 512);
-            tile = min(tile, uint32_t(TILE_MAX) & ~31u);
+            tile = min(tile, tile_max);
             const uint32_t steps = (HEAD + tile + slack) / 1024u;
             if (steps >= 2) tile = (steps * 1024u - HEAD - slack) & ~31u;
         }
-        a.sc.cnt[4] = max(uint32_t(TILE_MIN), min(tile, uint32_t(TILE_MAX) & ~31u));
+        a.sc.cnt[4] = max(uint32_t(TILE_MIN), min(tile, tile_max));
     }
 }
 
@@ -1569,8 +1543,69 @@ __global__ void reset_kernel(uint32_t *counts, uint64_t n, unsigned long long *s
     if (i < 8) stats[i] = (i == 5) ? ~0ull : 0ull;
 }
 
-int g_scan_grid_cap = 0;   // blocks of scan_parse resident at once (SM count x occupancy), per process
-int g_sms = 0;
+// ---- launch configuration, fixed per device the first time a shard is filtered there
+struct DevCfg {
+    int sms = 0;
+    int grid_cap = 0;            // blocks of the scan kernel resident at once (SM count x occupancy)
+    int min_blocks = 0;          // the scan kernel's instantiation
+    Geo geo{};
+    uint32_t smem = 0;           // dynamic shared memory of one block
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the scan kernel of the last call (svjg_filter_profile)
+    bool timed = false;
+};
+std::mutex g_cfg_mu;
+std::map<int, DevCfg> g_cfg;
+bool g_profile = false;
+
+// measurement / test knobs (svjg_filter_tune); 0 = default
+struct Knobs {
+    int tile_bytes = 0, tile_lines = 0, scan_blocks = 0, scan_only = 0, pool_units = 0;
+};
+Knobs g_knobs;
+
+template <int MB>
+int configure_scan(DevCfg &c, int dev) {
+    // the largest tile whose window, list and bitmaps fit MB blocks of WARPS warps into an SM's shared memory
+    int smem_sm = 0, smem_res = 0;
+    SVJG_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    SVJG_CUDA(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, dev));
+    const uint32_t per_warp = uint32_t((smem_sm / MB - smem_res - 64) / WARPS);
+    uint32_t tile = 8192;
+    while (tile > uint32_t(TILE_MIN) && make_geo(tile).warp_smem > per_warp) tile -= 32;
+    c.geo = make_geo(tile);
+    c.geo.tile_lines = g_knobs.tile_lines > 0 ? uint32_t(g_knobs.tile_lines) : uint32_t(TILE_LINES);
+    c.smem = c.geo.warp_smem * WARPS;
+    c.min_blocks = MB;
+    SVJG_CUDA(cudaFuncSetAttribute(scan_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
+    int occ = 0;
+    SVJG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<MB>, THREADS, c.smem));
+    if (occ < 1) return set_error(SVJG_E_CUDA, "scan kernel does not fit on an SM");
+    c.grid_cap = c.sms * occ;
+    return SVJG_OK;
+}
+
+int device_config(DevCfg **out) {
+    int dev = 0;
+    SVJG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    auto it = g_cfg.find(dev);
+    if (it == g_cfg.end()) {
+        DevCfg c;
+        SVJG_CUDA(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        const int rc = g_knobs.scan_blocks == 8 ? configure_scan<8>(c, dev) : configure_scan<6>(c, dev);
+        if (rc) return rc;
+        // scratch comes from the device's default memory pool: keep freed blocks cached in the pool
+        cudaMemPool_t pool;
+        SVJG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = ~0ull;
+        SVJG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        SVJG_CUDA(cudaEventCreate(&c.ev0));
+        SVJG_CUDA(cudaEventCreate(&c.ev1));
+        it = g_cfg.emplace(dev, c).first;
+    }
+    *out = &it->second;
+    return SVJG_OK;
+}
 
 }  // namespace
 
@@ -1591,6 +1626,45 @@ extern "C" int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, ui
                                    hit_cap, d_stats, stream);
 }
 
+// Measurement aid: with profiling on, every svjg_filter_device call records CUDA events around its scan
+// kernel on the caller's stream; svjg_filter_scan_ms waits for the last such call on the current device
+// and gives the kernel's duration.
+extern "C" int svjg_filter_tune(int knob, int value) {
+    if (value < 0) return set_error(SVJG_E_ARG, "svjg_filter_tune: negative value");
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    switch (knob) {
+        case SVJG_TUNE_TILE_BYTES: g_knobs.tile_bytes = value; break;
+        case SVJG_TUNE_SCAN_ONLY: g_knobs.scan_only = value; break;
+        case SVJG_TUNE_POOL_UNITS: g_knobs.pool_units = value; break;
+        case SVJG_TUNE_TILE_LINES:
+        case SVJG_TUNE_SCAN_BLOCKS:
+            // part of the per-device launch configuration: drop it, the next call configures anew
+            if (knob == SVJG_TUNE_TILE_LINES) g_knobs.tile_lines = value;
+            else g_knobs.scan_blocks = value;
+            for (auto &kv : g_cfg) {
+                cudaEventDestroy(kv.second.ev0);
+                cudaEventDestroy(kv.second.ev1);
+            }
+            g_cfg.clear();
+            break;
+        default: return set_error(SVJG_E_ARG, "svjg_filter_tune: unknown knob");
+    }
+    return SVJG_OK;
+}
+extern "C" int svjg_filter_profile(int enable) {
+    g_profile = enable != 0;
+    return SVJG_OK;
+}
+extern "C" int svjg_filter_scan_ms(float *ms) {
+    if (!ms) return set_error(SVJG_E_ARG, "svjg_filter_scan_ms: NULL argument");
+    DevCfg *c = nullptr;
+    if (int rc = device_config(&c)) return rc;
+    if (!c->timed) return set_error(SVJG_E_ARG, "svjg_filter_scan_ms: no profiled call on this device");
+    SVJG_CUDA(cudaEventSynchronize(c->ev1));
+    SVJG_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return SVJG_OK;
+}
+
 // d_hit_off64 != NULL: absolute 64-bit offsets (base_offset + offset) instead of d_hit_off (svjg_filter_host)
 int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset, int64_t d_over,
                             uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off, uint64_t *d_hit_off64,
@@ -1603,22 +1677,8 @@ int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t
     if (n_bytes >= 0xFFFF0000ull) return set_error(SVJG_E_ARG, "svjg_filter_device: shard must be smaller than 4 GiB");
     if (n_bytes == 0) return SVJG_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    static bool configured = false;
-    if (!configured) {
-        SVJG_CUDA(cudaFuncSetAttribute(scan_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        int dev = 0, occ = 0;
-        SVJG_CUDA(cudaGetDevice(&dev));
-        SVJG_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-        SVJG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_parse_kernel, THREADS, SMEM_BYTES));
-        if (occ < 1) return set_error(SVJG_E_CUDA, "scan_parse kernel does not fit on an SM");
-        g_scan_grid_cap = g_sms * occ;
-        // scratch comes from the device's default memory pool: keep freed blocks cached in the pool
-        cudaMemPool_t pool;
-        SVJG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = ~0ull;
-        SVJG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        configured = true;
-    }
+    DevCfg *cfg = nullptr;
+    if (int rc = device_config(&cfg)) return rc;
     FilterArgs a;
     a.gaf = d_gaf;
     a.n = n_bytes;
@@ -1634,41 +1694,35 @@ int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.flags = t->filter_flags;
     a.one = 1;
-    const char *stop_env = getenv("SVJG_STOP_AFTER");          // profiling hook: run the chain up to A/B/C/D only
-    const int stop = (stop_env && stop_env[0] >= 'A' && stop_env[0] <= 'B') ? stop_env[0] - 'A' + 1 : 0;
-    if (stop == 1) a.flags |= 1u << 8;
+    a.geo = cfg->geo;
+    if (g_knobs.scan_only) a.flags |= FLAG_STOP_AFTER_SCAN;
+    if (g_knobs.tile_bytes) a.flags |= uint32_t(std::min(65535, g_knobs.tile_bytes)) << 16;
 
     // scratch: one stream-ordered allocation, carved into the lists
     Scratch &sc = a.sc;
-    sc.cap_links = uint32_t(n_bytes / 20 + 4096);     // a path node with its delimiter is rarely under 20 bytes
     sc.cap_exact = uint32_t(n_bytes / 16 + 64);       // a line shorter than 16 bytes cannot hold 12 columns
     sc.cap_pool = uint32_t(std::min<uint64_t>(4u << 20, std::max<uint64_t>(64u << 10, n_bytes / 256)));   // 16-byte units: 1-64 MiB
-    if (const char *tiny = getenv("SVJG_TEST_TINY_SCRATCH")) {   // test hook: force the "no room" fallbacks
-        if (tiny[0] == '1') sc.cap_links = 64;
-    }
+    if (g_knobs.pool_units) sc.cap_pool = uint32_t(g_knobs.pool_units);
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t o_cnt = 0, o_links = up(64), o_ex = o_links + up(size_t(sc.cap_links) * sizeof(LinkRec)),
-                 o_slab = o_ex + up(size_t(sc.cap_exact) * 4),
-                 o_pool = o_slab + up(size_t(g_scan_grid_cap) * WARPS * SLAB_N * sizeof(uint4)),
+    const size_t o_cnt = 0, o_ex = up(64), o_slab = o_ex + up(size_t(sc.cap_exact) * 4),
+                 o_pool = o_slab + up(size_t(cfg->grid_cap) * WARPS * SLAB_N * sizeof(uint4)),
                  total = o_pool + up(size_t(sc.cap_pool) * sizeof(uint4));
     uint8_t *ws = nullptr;
     SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     sc.cnt = reinterpret_cast<uint32_t *>(ws + o_cnt);
-    sc.links = reinterpret_cast<LinkRec *>(ws + o_links);
     sc.exact = reinterpret_cast<uint32_t *>(ws + o_ex);
     sc.slab = reinterpret_cast<uint4 *>(ws + o_slab);
     sc.pool = reinterpret_cast<uint4 *>(ws + o_pool);
 
-    if (const char *tb = getenv("SVJG_TILE_BYTES")) a.flags |= uint32_t(std::min(65535, std::max(0, atoi(tb)))) << 16;
     const uint32_t max_tiles = uint32_t((n_bytes + TILE_MIN - 1) / TILE_MIN);
-    const int scan_grid = int(std::min<uint32_t>((max_tiles + WARPS - 1) / WARPS, uint32_t(g_scan_grid_cap)));
+    const int scan_grid = int(std::min<uint32_t>((max_tiles + WARPS - 1) / WARPS, uint32_t(cfg->grid_cap)));
     probe_kernel<<<1, PROBE_THREADS, 0, st>>>(a);
-    const int flat_grid = g_sms * 8;
-    scan_parse_kernel<<<scan_grid, THREADS, SMEM_BYTES, st>>>(a);
-    if (stop == 0) {
-        link_kernel<<<flat_grid, FLAT_THREADS, 0, st>>>(a);
-        exact_kernel<<<g_sms * 2, FLAT_THREADS, 0, st>>>(a);     // a few lines as a rule: a small grid starts faster
-    }
+    if (g_profile) cudaEventRecord(cfg->ev0, st);
+    if (cfg->min_blocks == 8) scan_kernel<8><<<scan_grid, THREADS, cfg->smem, st>>>(a);
+    else scan_kernel<6><<<scan_grid, THREADS, cfg->smem, st>>>(a);
+    if (g_profile) cudaEventRecord(cfg->ev1, st), cfg->timed = true;
+    if (!(a.flags & FLAG_STOP_AFTER_SCAN))
+        exact_kernel<<<cfg->sms * 2, FLAT_THREADS, 0, st>>>(a);     // a few lines as a rule: a small grid starts faster
     cudaError_t le = cudaGetLastError();
     cudaError_t fe = cudaFreeAsync(ws, st);
     SVJG_CUDA(le);

@@ -47,7 +47,12 @@ constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
 SVJG_HD uint64_t link_key(uint32_t idL, uint32_t sL, uint32_t idR, uint32_t sR) {
     return (uint64_t(idL) << 33) | (uint64_t(sL) << 32) | (uint64_t(idR) << 1) | uint64_t(sR);
 }
-SVJG_HD uint64_t link_hash(uint64_t key) { return mix64(key + 0x9E3779B97F4A7C15ull); }
+// 32-bit mixing only: the probe is made for every link of every multi-node line
+SVJG_HD uint32_t link_hash(uint64_t key) {
+    uint32_t h = uint32_t(key) * 0x9E3779B1u ^ uint32_t(key >> 32) * 0x85EBCA77u;
+    h = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+    return h ^ (h >> 13);
+}
 
 struct LinkSlot {          // open addressing, linear probing, capacity = power of two; two slots per sector
     uint64_t key;          // link_key()
@@ -66,15 +71,17 @@ struct NodeSlot {
 };
 static_assert(sizeof(NodeSlot) == 32, "NodeSlot must be one sector");
 
-// Plain node names -- chrom:start-end (reference node) or chrom:pos.k (alt node), chrom of at most
-// 16 bytes without NUL, numbers of 1-9 digits without leading zeros -- have an exact 24-byte key, so
-// scan_parse resolves them from shared memory with one probe and no name bytes are compared.  Any
-// other name is reachable only through the name-hash table above (the exact route).
+// Plain node names -- chrom:start-end (reference node) or chrom:pos.k (alt node), read from the END of
+// the name: 1-9 digits, '-' or '.', 1-9 digits (neither number with a leading zero), ':', and in front
+// of that colon a chrom of at most 15 bytes (any bytes) -- have an exact 24-byte key, so the scan
+// kernel resolves them from shared memory with one probe and no name bytes are compared.  The last
+// byte of the 16-byte chrom field is the chrom's length, so the key determines the name whatever bytes
+// the chrom holds.  Any other name is reachable only through the name-hash table above (the exact route).
 constexpr uint32_t PN_ALT = 0x80000000u;       // in PNodeSlot::b: chrom:pos.k
 constexpr uint32_t PN_NO_LEN = 0xFFFFFFFFu;    // alt node without a usable GFA sequence length
 constexpr uint32_t PN_ID_MASK = 0x0FFFFFFFu;   // PNodeSlot::id1: node id + 1
 struct PNodeSlot {
-    uint64_t c0, c1;       // chrom bytes, little endian, zero padded
+    uint64_t c0, c1;       // chrom bytes, little endian, zero padded to 15; byte 15 (top byte of c1) = chrom length
     uint32_t a;            // start / pos
     uint32_t b;            // end, or k | PN_ALT
     uint32_t id1;          // low 28 bits: node id + 1 (same ids as NodeSlot), 0 = empty slot; high 4 bits: the

@@ -551,34 +551,33 @@ static uint64_t hash_bytes(const char *s, size_t n) {
     return tok_value(h, uint32_t(n));
 }
 
-// exact key of a plain node name (see PNodeSlot); false for any other name
+// exact key of a plain node name (see PNodeSlot); false for any other name.  Read from the end, as the
+// scan kernel reads it: digits, '-' or '.', digits, ':', chrom.
 static bool plain_key(const std::string &name, PNodeSlot &k) {
     const size_t n = name.size();
-    const size_t c = name.find(':');
-    if (c == std::string::npos || c > 16 || name.find(':', c + 1) != std::string::npos) return false;
+    auto digit = [&](size_t i) { return name[i] >= '0' && name[i] <= '9'; };
+    size_t q = n;
+    while (q > 0 && digit(q - 1)) --q;
+    const size_t n2 = n - q;                                   // digits of the second number
+    if (n2 < 1 || n2 > 9 || q == 0 || (name[q - 1] != '-' && name[q - 1] != '.')) return false;
+    const size_t sep = q - 1;
+    size_t p = sep;
+    while (p > 0 && digit(p - 1)) --p;
+    const size_t n1 = sep - p;                                 // digits of the first number
+    if (n1 < 1 || n1 > 9 || p == 0 || name[p - 1] != ':') return false;
+    const size_t c = p - 1;                                    // the colon; chrom = name[0, c)
+    if (c > 15) return false;
+    if ((n1 > 1 && name[p] == '0') || (n2 > 1 && name[q] == '0')) return false;
     uint8_t chrom[16] = {0};
-    for (size_t i = 0; i < c; ++i) {
-        if (name[i] == '\0') return false;
-        chrom[i] = uint8_t(name[i]);
-    }
-    auto number = [&](size_t b, size_t e, uint32_t &v) {     // 1-9 digits, no leading zero
-        if (e <= b || e - b > 9 || (e - b > 1 && name[b] == '0')) return false;
-        v = 0;
-        for (size_t i = b; i < e; ++i) {
-            if (name[i] < '0' || name[i] > '9') return false;
-            v = v * 10 + uint32_t(name[i] - '0');
-        }
-        return true;
-    };
-    size_t q = c + 1;
-    while (q < n && name[q] >= '0' && name[q] <= '9') ++q;
-    if (q >= n || (name[q] != '-' && name[q] != '.')) return false;
-    uint32_t a, b;
-    if (!number(c + 1, q, a) || !number(q + 1, n, b)) return false;
+    for (size_t i = 0; i < c; ++i) chrom[i] = uint8_t(name[i]);
+    chrom[15] = uint8_t(c);
+    uint32_t a = 0, b = 0;
+    for (size_t i = p; i < sep; ++i) a = a * 10 + uint32_t(name[i] - '0');
+    for (size_t i = q; i < n; ++i) b = b * 10 + uint32_t(name[i] - '0');
     memcpy(&k.c0, chrom, 8);
     memcpy(&k.c1, chrom + 8, 8);
     k.a = a;
-    k.b = b | (name[q] == '.' ? PN_ALT : 0u);
+    k.b = b | (name[sep] == '.' ? PN_ALT : 0u);
     return true;
 }
 
@@ -686,7 +685,7 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
         s.key = link_key(idl, sl, idr, sr);
         s.val = cnt == 1 ? t->entries[ent_begin[ps.key]] : ent_begin[ps.key];
         s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | 1u;
-        uint32_t i = uint32_t(link_hash(s.key)) & (cap - 1);
+        uint32_t i = link_hash(s.key) & (cap - 1);
         while (t->links[i].meta & 1u) i = (i + 1) & (cap - 1);
         t->links[i] = s;
     }

@@ -324,7 +324,12 @@ class DeviceFilter:
         st = self.read_stats()
         if st["status"]:
             _raise_input(st)
-        nh = min(st["n_hits"], self.hit_cap)
+        nh = st["n_hits"]
+        if nh > self.hit_cap:
+            # the cursor counts every hit, the arrays hold the first hit_cap of them: a list cut short
+            # would print an informative_aln.json with alignments missing
+            raise capi.SvjgError(capi.E_HITS_OVERFLOW, f"hit buffers too small: {nh} hits, room for {self.hit_cap} "
+                                                       "(DeviceFilter(hit_cap=...); counters and stats are complete)")
         counts = self.counts.cpu().numpy().view(np.uint32)[: self.tables.num_sv]
         return FilterResult(counts, st, self.hit_sv2[:nh].cpu().numpy().view(np.uint32),
                             self.hit_off[:nh].cpu().numpy().view(np.uint32).astype(np.uint64),

@@ -12,6 +12,7 @@ OK, E_CUDA, E_ARG, E_IO, E_JSON, E_INPUT, E_HITS_OVERFLOW, E_NOMEM, E_UNSUPPORTE
 GT_GENOTYPED, GT_HALVED_0, GT_HALVED_1, GT_NEED_K = 1, 2, 4, 8
 NO_SV = 0xFFFFFFFF
 FLAG_EXACT_CHECKS, FLAG_FORCE_GENERAL = 1, 2
+TUNE_TILE_BYTES, TUNE_TILE_LINES, TUNE_SCAN_BLOCKS, TUNE_SCAN_ONLY, TUNE_POOL_UNITS = 1, 2, 3, 4, 5
 
 BAD_REASONS = {
     1: "blank line or fewer than 12 columns",
@@ -68,6 +69,9 @@ def _load():
                                          C.c_uint64, vp, vp]),
         "svjg_filter_host": (C.c_int, [vp, u8p, C.c_uint64, C.c_int64, u32p, u32p, u64p, u32p, C.c_uint64,
                                        C.POINTER(FilterStats)]),
+        "svjg_filter_tune": (C.c_int, [C.c_int, C.c_int]),
+        "svjg_filter_profile": (C.c_int, [C.c_int]),
+        "svjg_filter_scan_ms": (C.c_int, [C.POINTER(C.c_float)]),
         "svjg_genotype_device": (C.c_int, [u32p, u32p, u8p, C.c_uint32, C.c_int64, C.c_double, C.c_double,
                                            C.c_double, f64p, C.c_uint32, f64p, i64p, u8p, u32p, u8p, vp]),
         "svjg_genotype_host": (C.c_int, [u32p, C.c_uint32, u32p, u8p, C.c_uint32, C.c_int64, C.c_double, C.c_double,

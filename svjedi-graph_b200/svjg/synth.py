@@ -399,14 +399,18 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, scale=1.0, seed=None, stream0=0, **gaf_kw):
+def make_workload(name, scale=1.0, seed=None, stream0=0, catalogue_scale=None, **gaf_kw):
     """(Graph, vcf_text, gaf_text) for a named config shrunk by ``scale`` in both
-    SV count and record count (genome scaled alike so densities stay put)."""
+    SV count and record count (genome scaled alike so densities stay put).
+    ``catalogue_scale`` sizes the SV catalogue and the genome on their own:
+    ``make_workload("C5", 0.02, catalogue_scale=1.0)`` is a 4 M-record shard of the
+    population config against its full 1 M-SV tables."""
     kind, n_sv, n_rec, gscale, mean_len = WORKLOADS[name]
     seed = seed if seed is not None else 1000 + int(name[1:])
-    n_sv = max(24, int(n_sv * scale))
+    cscale = scale if catalogue_scale is None else catalogue_scale
+    n_sv = max(24, int(n_sv * cscale))
     n_rec = max(100, int(n_rec * scale))
-    chrom_len = human_like_chroms(gscale * max(scale, 0.002))
+    chrom_len = human_like_chroms(gscale * max(cscale, 0.002))
     ins_max = 5000 if name != "C5" else 600
     rows = catalogue(kind, n_sv, chrom_len, seed, ins_max=ins_max)
     g = graphgen.build_graph(chrom_len, rows)

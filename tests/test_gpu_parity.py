@@ -76,6 +76,14 @@ def test_device_resident_path_equals_host_path(gpu):
     # accumulate semantics: a second pass doubles the counters
     f.run(d)
     assert (f.counts.cpu().numpy().view(np.uint32) == 2 * host.counts).all()
+    # more hits than the arrays hold: result() refuses to hand out a list cut short
+    small = alnfilter.DeviceFilter(t, hit_cap=max(1, host.n_hits // 2))
+    small.reset()
+    small.run(d)
+    with pytest.raises(capi.SvjgError) as exc:
+        small.result()
+    assert exc.value.code == capi.E_HITS_OVERFLOW
+    assert (small.counts.cpu().numpy().view(np.uint32) == host.counts).all()
 
 
 def test_quirk_cases(gpu, quirks, tmp_path):
@@ -302,17 +310,30 @@ def test_irregular_lines_take_the_exact_route(gpu):
     assert _counts_dict(t2, res2.counts) == {k: list(v) for k, v in want2.items()} and want2
 
 
-def test_scratch_exhaustion_falls_back_to_the_exact_route(gpu, monkeypatch):
+def test_pool_exhaustion_falls_back_to_the_general_routine(gpu):
+    """A line too long for the window is parsed where it lies with bitmaps from the exact kernel's bump
+    pool (giant_line()); without room there, general() takes it: same counters and hits either way."""
     alnfilter, capi, genotype, torch = gpu
-    t, _ = _tables(alnfilter, "s3")
-    gaf = read_golden("s3.gaf.gz").encode()
+    step, n_nodes = 37, 700
+    names = [f"chrL:{i * step + 1}-{(i + 1) * step}" for i in range(n_nodes)]
+    edges = {f"{names[i]}@+@{names[i + 1]}@+": [[f"chrL:DEL-{(i + 1) * step}-{(i + 1) * step + 40}", 0]] for i in range(n_nodes - 1)}
+    t = alnfilter.Tables.from_memory(json.dumps(edges), "").to_device(0)
+    lines = []
+    for k in (300, 450, 699):
+        tlen = k * step
+        path = "".join(">" + names[i] for i in range(k))
+        lines.append(f"{'r' * 70}{k}\t{tlen}\t0\t{tlen}\t+\t{path}\t{tlen}\t150\t{tlen - 150}\t{tlen - 9}\t{tlen}\t60\ttp:A:P\n")
+    gaf = "".join(lines).encode()
     normal = alnfilter.filter_host(t, gaf)
-    monkeypatch.setenv("SVJG_TEST_TINY_SCRATCH", "1")
-    tiny = alnfilter.filter_host(t, gaf)
-    monkeypatch.delenv("SVJG_TEST_TINY_SCRATCH")
+    capi.check(capi.lib.svjg_filter_tune(capi.TUNE_POOL_UNITS, 8))
+    try:
+        tiny = alnfilter.filter_host(t, gaf)
+    finally:
+        capi.check(capi.lib.svjg_filter_tune(capi.TUNE_POOL_UNITS, 0))
+    want = O.hit_counts(O.filter_alignments(lines, edges, {}))
+    assert want and _counts_dict(t, normal.counts) == {k: list(v) for k, v in want.items()}
     assert (tiny.counts == normal.counts).all() and tiny.n_hits == normal.n_hits
-    assert tiny.stats["n_multi"] == normal.stats["n_multi"]
-    assert tiny.stats["n_exact"] > normal.stats["n_exact"]          # the lines that found no room went the exact route
+    assert normal.stats["n_generic"] == 0 and tiny.stats["n_generic"] == len(lines)
     assert sorted(zip(tiny.hit_sv2.tolist(), tiny.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
 
 
@@ -361,16 +382,18 @@ def test_long_paths(gpu):
 
 
 @pytest.mark.parametrize("tile", [1024, 1600, 3072, 5024])
-def test_every_tile_size_gives_the_same_result(gpu, monkeypatch, tile):
+def test_every_tile_size_gives_the_same_result(gpu, tile):
     """The probe kernel picks the bytes per tile from the line length; any tile size must give the
-    same counters and hits (SVJG_TILE_BYTES forces one)."""
+    same counters and hits (SVJG_TUNE_TILE_BYTES forces one)."""
     alnfilter, capi, genotype, torch = gpu
     t, _ = _tables(alnfilter, "s3")
     gaf = read_golden("s3.gaf.gz").encode()
     normal = alnfilter.filter_host(t, gaf)
-    monkeypatch.setenv("SVJG_TILE_BYTES", str(tile))
-    forced = alnfilter.filter_host(t, gaf)
-    monkeypatch.delenv("SVJG_TILE_BYTES")
+    capi.check(capi.lib.svjg_filter_tune(capi.TUNE_TILE_BYTES, tile))
+    try:
+        forced = alnfilter.filter_host(t, gaf)
+    finally:
+        capi.check(capi.lib.svjg_filter_tune(capi.TUNE_TILE_BYTES, 0))
     same = lambda st: {k: v for k, v in st.items() if k != "n_exact"}     # lines past the window depend on the tile
     assert (forced.counts == normal.counts).all() and same(forced.stats) == same(normal.stats)
     assert sorted(zip(forced.hit_sv2.tolist(), forced.hit_off.tolist())) == sorted(zip(normal.hit_sv2.tolist(), normal.hit_off.tolist()))
