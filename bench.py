@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--kernel-only", action="store_true", help="developer mode: print the kernel times and stop")
     ap.add_argument("--cpu-sample", type=int, default=150_000, help="records the CPU baseline is timed on")
+    ap.add_argument("--scan-blocks", type=int, default=0, help="developer: blocks per SM the scan kernel is sized for (6 or 8)")
+    ap.add_argument("--tile-lines", type=int, default=0, help="developer: lines a tile of the scan kernel should hold")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: counters summed inside the genotype kernel over NVLink peer memory (p2p), or ncclAllReduce")
     return ap.parse_args()
@@ -305,6 +307,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.scan_blocks:
+        capi.check(capi.lib.svjg_filter_tune(capi.TUNE_SCAN_BLOCKS, args.scan_blocks))
+    if args.tile_lines:
+        capi.check(capi.lib.svjg_filter_tune(capi.TUNE_TILE_LINES, args.tile_lines))
     g, vcf, gaf, gfa_text, scale, gen_s = workload(args, rank)
     edges_text = g.edges_json()
     tables = alnfilter.Tables.from_memory(edges_text, gfa_text).to_device(local)

@@ -59,31 +59,28 @@ constexpr int WARPS = 4;                       // per block; warps never synchro
 constexpr int THREADS = WARPS * 32;
 constexpr int SPARE = 32;                      // readable (zero) bytes behind the window
 
-// shared memory of ONE warp of the scan kernel, fixed per device at the first launch (svjg::DevCfg):
-// the window, the newline list, three bitmaps over the window's bytes, the lanes of a round's lines
+// shared memory of ONE warp of the scan kernel: the window, the newline list, three bitmaps over the
+// window's bytes, the lanes of a round's lines.  Two geometries are compiled: MB blocks of WARPS warps per
+// SM trade window size (lines per tile, i.e. busy lanes in the line-parallel phase) for resident warps.
+template <int MB_, int TILE_MAX_>
 struct Geo {
-    uint32_t tile_max;    // most bytes a warp owns per step, a multiple of 32
-    uint32_t win;         // HEAD + tile_max + LOOKAHEAD: window bytes (a multiple of 32, < 64 Ki: offsets are 16 bit)
-    uint32_t nlcap;       // newline list entries (more newlines in a window => some line is shorter than 20 bytes)
-    uint32_t bmwords;     // words per bitmap: reads may run a few words past the window
-    uint32_t off_nl, off_tab, off_xd, off_ns, off_tko, warp_smem;
-    uint32_t tile_lines;  // lines a tile should hold (probe_kernel): about one per lane
+    static constexpr int MB = MB_;                               // blocks per SM the kernel is bounded for
+    static constexpr int TILE_MAX = TILE_MAX_;                   // most bytes a warp owns per step, a multiple of 32
+    static constexpr int WIN = HEAD + TILE_MAX + LOOKAHEAD;      // window bytes (a multiple of 32, < 64 Ki: offsets are 16 bit)
+    static constexpr int NLCAP = WIN / 20 + 1;                   // newline list entries (more newlines in a window => some line is shorter than 20 bytes)
+    static constexpr int BMWORDS = WIN / 32 + 3;                 // words per bitmap: reads may run a few words past the window
+    static constexpr int OFF_NL = WIN + SPARE;                   // u16[NLCAP]  newline positions, ascending
+    static constexpr int OFF_TAB = (OFF_NL + 2 * NLCAP + 15) & ~15;   // u32[BMWORDS]  bit i: window byte i is a tab
+    static constexpr int OFF_XD = OFF_TAB + 4 * BMWORDS;         // ... is not '0'..'9'
+    static constexpr int OFF_NS = OFF_XD + 4 * BMWORDS;          // ... starts a path node (no '<' / '>', right behind one)
+    static constexpr int OFF_TKO = OFF_NS + 4 * BMWORDS;         // u8[32]  lanes of the lines of a round, in order
+    static constexpr int WARP_SMEM = (OFF_TKO + 32 + 127) & ~127;
+    static constexpr int SMEM = WARP_SMEM * WARPS;
+    static_assert(TILE_MAX % 32 == 0 && WIN + SPARE < 65536, "window offsets are 16 bit");
+    static_assert((SMEM + 1024 + 64) * MB <= 233472, "MB blocks must fit an SM's 228 KB of shared memory");
 };
-Geo make_geo(uint32_t tile_max) {
-    Geo g;
-    g.tile_max = tile_max & ~31u;
-    g.win = HEAD + g.tile_max + LOOKAHEAD;
-    g.nlcap = g.win / 20u + 1u;
-    g.bmwords = g.win / 32u + 3u;
-    g.off_nl = g.win + SPARE;
-    g.off_tab = (g.off_nl + 2u * g.nlcap + 15u) & ~15u;
-    g.off_xd = g.off_tab + 4u * g.bmwords;
-    g.off_ns = g.off_xd + 4u * g.bmwords;
-    g.off_tko = g.off_ns + 4u * g.bmwords;
-    g.warp_smem = (g.off_tko + 32u + 127u) & ~127u;
-    g.tile_lines = TILE_LINES;
-    return g;
-}
+typedef Geo<6, 5184> Geo6;      // 24 warps per SM, tiles of up to ~30 lines of 170 bytes
+typedef Geo<8, 3552> Geo8;      // 32 warps per SM, ~21 such lines
 
 constexpr int FLAT_THREADS = 256;              // block size of the flat (grid-stride) kernels
 
@@ -115,7 +112,8 @@ struct FilterArgs {
     uint32_t flags;
     uint32_t one;                // 1 (see IsNewline)
     Scratch sc;
-    Geo geo;
+    uint32_t tile_max;           // most bytes per tile (the scan kernel's geometry)
+    uint32_t tile_lines;         // lines a tile should hold (probe_kernel): about one per lane
 };
 
 struct Local {
@@ -827,21 +825,8 @@ __device__ __forceinline__ uint32_t dec4(uint32_t w) {
 __device__ __forceinline__ uint32_t clear_low_bytes(uint32_t w, int n) {
     return w & __funnelshift_lc(0u, 0xFFFFFFFFu, uint32_t(max(n, 0)) * 8u);
 }
-// value of the decimal digits in window bytes [lo, hi) (validated: digits only, hi > lo); false
-// when there are more than 18 significant digits.  Up to 12 digits without a loop: the 12 bytes
-// that end at hi as three words, the bytes in front of lo masked away.
-__device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
-    const uint32_t n = hi - lo;
-    if (n <= 12) {
-        const uint32_t base = hi - 12u, al = base & ~3u, sh = (base & 3u) * 8u;
-        const uint32_t r0 = lds32(win, al), r1 = lds32(win, al + 4), r2 = lds32(win, al + 8), r3 = lds32(win, al + 12);
-        const int m = 12 - int(n);              // bytes of the 12 that are not ours
-        const uint32_t g0 = dec4(clear_low_bytes(__funnelshift_r(r0, r1, sh), m));
-        const uint32_t g1 = dec4(clear_low_bytes(__funnelshift_r(r1, r2, sh), m - 4));
-        const uint32_t g2 = dec4(clear_low_bytes(__funnelshift_r(r2, r3, sh), m - 8));
-        out = int64_t(uint64_t(g0) * 100000000ull + uint64_t(g1 * 10000u + g2));
-        return true;
-    }
+// more than 12 digits (hardly ever): digit by digit; false when there are more than 18 significant ones
+__device__ __noinline__ bool dec_field_long(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
     int64_t x = 0;
     uint32_t nd = 0;
     for (uint32_t q = lo; q < hi; ++q) {
@@ -851,6 +836,21 @@ __device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint3
     }
     out = x;
     return nd <= 18;
+}
+// value of the decimal digits in window bytes [lo, hi) (validated: digits only, hi > lo); false
+// when there are more than 18 significant digits.  Up to 12 digits without a loop: the 12 bytes
+// that end at hi as three words, the bytes in front of lo masked away.
+__device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
+    const uint32_t n = hi - lo;
+    if (n > 12) return dec_field_long(win, lo, hi, out);
+    const uint32_t base = hi - 12u, al = base & ~3u, sh = (base & 3u) * 8u;
+    const uint32_t r0 = lds32(win, al), r1 = lds32(win, al + 4), r2 = lds32(win, al + 8), r3 = lds32(win, al + 12);
+    const int m = 12 - int(n);              // bytes of the 12 that are not ours
+    const uint32_t g0 = dec4(clear_low_bytes(__funnelshift_r(r0, r1, sh), m));
+    const uint32_t g1 = dec4(clear_low_bytes(__funnelshift_r(r1, r2, sh), m - 4));
+    const uint32_t g2 = dec4(clear_low_bytes(__funnelshift_r(r2, r3, sh), m - 8));
+    out = int64_t(uint64_t(g0) * 100000000ull + uint64_t(g1 * 10000u + g2));
+    return true;
 }
 
 // plain-node table: exact key -> (node id, alt sequence length)
@@ -994,24 +994,36 @@ __device__ __noinline__ void link_slow(const FilterArgs &a, uint32_t idl, uint32
 // of the link table each (the key the node roles allow), hit tuples appended with one cursor atomic.
 // `want`: this lane has a link to look up (both ids known, some key possible, verdict `ok` or exact checks).
 __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr,
-                                            uint32_t dirs, bool ok, uint32_t off, uint32_t len, uint32_t lt_mask, Local &loc) {
+                                            uint32_t dirs, bool ok, uint32_t off, uint32_t len, uint32_t lt_mask, uint32_t &n_checks,
+                                            Local &loc) {
     uint4 sv = make_uint4(0, 0, 0, 0);
-    uint64_t key = 0;
-    if (want) {
-        key = (dirs & 1u) ? link_key(idl, sl, idr, sr) : link_key(idr, sr ^ 1u, idl, sl ^ 1u);
-        sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + (link_hash(key) & a.tb.link_mask)));
+    // the one key that can exist; where both can (dirs == 3) the general routine looks them up
+    const bool fwd = (dirs & 1u) != 0;
+    const uint32_t kl = fwd ? idl : idr, kr = fwd ? idr : idl, ksl = fwd ? sl : sr ^ 1u, ksr = fwd ? sr : sl ^ 1u;
+    const uint32_t key_lo = (kr << 1) | ksr, key_hi = (kl << 1) | ksl;              // link_key() in halves
+    bool go = want && dirs != 3u;
+    uint32_t i = link_hash((uint64_t(key_hi) << 32) | key_lo);
+    bool match = false;
+    // linear probing: nearly always the first slot settles it (the key, or an empty slot)
+    while (__any_sync(0xFFFFFFFFu, go)) {
+        if (go) {
+            i &= a.tb.link_mask;
+            sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
+            match = (sv.w & 1u) && sv.x == key_lo && sv.y == key_hi;
+            go = (sv.w & 1u) && !match;
+            ++i;
+        }
     }
-    const bool used = (sv.w & 1u) != 0, match = used && sv.x == uint32_t(key) && sv.y == uint32_t(key >> 32);
-    // settled by this one slot: the only key that can exist is absent, or present with exactly one sound entry
-    const bool simple = want && dirs != 3u && (!used || (match && (sv.w >> 3) == 2u && sv.z != ENTRY_POISON));
+    // settled here: the key is absent, or present with exactly one sound entry
+    const bool simple = want && dirs != 3u && (!match || ((sv.w >> 3) == 2u && sv.z != ENTRY_POISON));
     const bool hit = simple && match;
-    if (hit) loc.n_checks++;
+    n_checks += hit;
     const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit && ok);
     if (hb) {
         unsigned long long base = 0;
-        if ((hb & lt_mask) == 0u && ((hb >> (threadIdx.x & 31)) & 1u))      // the first hit lane takes the room for all
-            base = atomicAdd(a.stats + 0, (unsigned long long)__popc(hb));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(hb) - 1);
+        const int leader = __ffs(hb) - 1;
+        if (int(threadIdx.x & 31) == leader) base = atomicAdd(a.stats + 0, (unsigned long long)__popc(hb));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
         if (hit && ok) {
             atomicAdd(a.counts + sv.z, 1u);
             const unsigned long long k = base + __popc(hb & lt_mask);
@@ -1043,6 +1055,7 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const B src, const u
                                        int64_t ltail, uint32_t off, uint32_t len, Local &loc) {
     if (cnt > slab_cap) return false;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t n_checks = 0;
     uint64_t total = 0;
     bool bad = false;
     uint32_t from = lps;                       // the next step's first node starts at or behind this byte
@@ -1085,48 +1098,43 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const B src, const u
         const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
         const uint32_t dirs = link_dirs(lf.w >> 1, lf.w & 1u, me.w >> 1, me.w & 1u);
         const bool want = act && t && lf.x != NO_NODE && me.x != NO_NODE && dirs && (ok || (a.flags & FLAG_EXACT_CHECKS));
-        probe_links(a, want, lf.x, lf.w & 1u, me.x, me.w & 1u, dirs, ok, off, len, lt_mask, loc);
+        probe_links(a, want, lf.x, lf.w & 1u, me.x, me.w & 1u, dirs, ok, off, len, lt_mask, n_checks, loc);
         before += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
+    loc.n_checks += n_checks;
     return true;
 }
 
 // ===========================================================================
 // scan: newline scan, column split, validation, path walk, node and link resolution, hits
 // ===========================================================================
-// Geometry of one warp's shared memory (chosen at launch, FilterArgs::geo): the window
-// (HEAD + tile_max + LOOKAHEAD bytes + SPARE), the list of newline positions, three bitmaps over the
-// window's bytes -- tabs, non-digits, node starts (a byte that is no '<' / '>' right behind one) --
-// and the lanes of a round's lines.
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) scan_kernel(const __grid_constant__ FilterArgs a) {
+template <class G>
+__global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_constant__ FilterArgs a) {
     extern __shared__ __align__(128) uint8_t smem_all[];
     __shared__ __align__(8) uint64_t mbars[WARPS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint8_t *wmem = smem_all + warp * a.geo.warp_smem;
-    uint8_t *win = wmem;
-    uint16_t *nl = reinterpret_cast<uint16_t *>(wmem + a.geo.off_nl);      // newline positions, ascending
-    uint32_t *tabb = reinterpret_cast<uint32_t *>(wmem + a.geo.off_tab);   // bit i: window byte i is a tab
-    uint32_t *xdb = reinterpret_cast<uint32_t *>(wmem + a.geo.off_xd);     // bit i: ... is not '0'..'9'
-    uint32_t *nsb = reinterpret_cast<uint32_t *>(wmem + a.geo.off_ns);     // bit i: ... starts a path node
-    uint8_t *tko = wmem + a.geo.off_tko;
+    uint8_t *win = smem_all + warp * G::WARP_SMEM;                         // the window; everything else at fixed offsets behind it
+    uint16_t *nl = reinterpret_cast<uint16_t *>(win + G::OFF_NL);          // newline positions, ascending
+    uint32_t *tabb = reinterpret_cast<uint32_t *>(win + G::OFF_TAB);       // bit i: window byte i is a tab
+    uint32_t *xdb = reinterpret_cast<uint32_t *>(win + G::OFF_XD);         // bit i: ... is not '0'..'9'
+    uint32_t *nsb = reinterpret_cast<uint32_t *>(win + G::OFF_NS);         // bit i: ... starts a path node
+    uint8_t *tko = win + G::OFF_TKO;
     uint64_t *mbar = &mbars[warp];
     const SmemBytes src{win};
 
     if (lane == 0) mbar_init(mbar, 1);
-    for (uint32_t i = lane; i < a.geo.bmwords; i += 32) tabb[i] = 0, xdb[i] = 0, nsb[i] = 0;
-    for (uint32_t i = a.geo.win + lane; i < a.geo.win + SPARE; i += 32) win[i] = 0;   // never written by the copies
+    for (int i = lane; i < G::BMWORDS; i += 32) tabb[i] = 0, xdb[i] = 0, nsb[i] = 0;
+    for (int i = G::WIN + lane; i < G::WIN + SPARE; i += 32) win[i] = 0;   // never written by the copies
     __syncwarp();
     uint32_t phase = 0;
     Local loc;
-    uint32_t u_rec = 0, u_multi = 0;              // warp-uniform tallies (lines, lines with >= 2 nodes)
+    uint32_t u_rec = 0, u_multi = 0, n_checks = 0;   // tallies: lines, lines with >= 2 nodes (both warp-uniform), overlap tests
     const uint32_t one = a.one;
     const uint32_t n_workers = gridDim.x * WARPS;
-    const uint32_t nlcap = a.geo.nlcap;
 
-    const uint32_t tile_bytes = a.sc.cnt[4];                       // chosen by probe_kernel: a multiple of 32
+    const uint32_t tile_bytes = a.sc.cnt[4];                       // chosen by probe_kernel: a multiple of 32, at most G::TILE_MAX
     const uint32_t n_tiles = uint32_t((a.n + tile_bytes - 1) / tile_bytes);
     const uint32_t win_bytes = HEAD + tile_bytes + LOOKAHEAD, n_pairs = win_bytes / 32u;
 
@@ -1165,7 +1173,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) scan_kernel(const __grid_
         // the newlines go straight into the ordered list.  The scan stops behind the tile once the last
         // owned line has its end.
         const uint32_t own_end = min(HEAD + tile_bytes, valid_end);   // lines starting before own_end are ours
-        uint32_t n_nl = 0, own = 0;
+        uint32_t n_nl = 0, n_own = 0;
         for (uint32_t c0 = 0; c0 < n_pairs; c0 += 32) {
             const uint32_t c = c0 + uint32_t(lane);
             const uint32_t p0 = c * 32u;
@@ -1181,36 +1189,36 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) scan_kernel(const __grid_
                 nsb[c] = ((d << 1) | left) & ~d;
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
             }
-            // newline positions, in order
+            // newline positions, in order: one per 32 bytes as a rule
             if (__any_sync(0xFFFFFFFFu, (m & (m - 1u)) != 0u)) {
                 // two line ends in 32 bytes (hardly ever): the general placement
                 const uint32_t cnt = __popc(m), incl = warp_incl_scan(cnt, lane);
-                uint32_t idx = n_nl + incl - cnt;
+                uint32_t idx = n_nl + incl - cnt, own = 0;
                 for (uint32_t mm = m; mm; mm &= mm - 1) {
                     const uint32_t pos = p0 + uint32_t(__ffs(mm) - 1);
-                    if (idx < nlcap) nl[idx] = uint16_t(pos);
+                    if (idx < uint32_t(G::NLCAP)) nl[idx] = uint16_t(pos);
                     own += pos + 1u < own_end;
                     ++idx;
                 }
                 n_nl += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                n_own += __reduce_add_sync(0xFFFFFFFFu, own);
             } else {
+                const uint32_t pos = p0 + uint32_t(__ffs(m)) - 1u;                 // if this lane has one
                 const uint32_t b = __ballot_sync(0xFFFFFFFFu, m != 0u);
-                if (m) {
-                    const uint32_t pos = p0 + uint32_t(__ffs(m) - 1), idx = n_nl + __popc(b & lt_mask);
-                    if (idx < nlcap) nl[idx] = uint16_t(pos);
-                    own += pos + 1u < own_end;                                 // the newline at pos starts an owned line
-                }
+                const uint32_t bo = __ballot_sync(0xFFFFFFFFu, m != 0u && pos + 1u < own_end);   // ... that starts an owned line
+                const uint32_t idx = n_nl + __popc(b & lt_mask);
+                if (m != 0u && idx < uint32_t(G::NLCAP)) nl[idx] = uint16_t(pos);
                 n_nl += __popc(b);
+                n_own += __popc(bo);
             }
             // behind the tile: a newline at or after own_end - 1 ends the last owned line
             const bool ends_it = (m & ~low_bits(int(own_end) - 1 - int(p0))) != 0;
             if ((c0 + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, ends_it)) break;
         }
-        const uint32_t n_own = __reduce_add_sync(0xFFFFFFFFu, own);
         __syncwarp();
-        if (a.flags & FLAG_STOP_AFTER_SCAN) continue;                 // profiling hook (svjg_tables_set_flags)
+        if (a.flags & FLAG_STOP_AFTER_SCAN) continue;                 // measurement aid (SVJG_TUNE_SCAN_ONLY)
 
-        if (n_nl > nlcap) {
+        if (n_nl > uint32_t(G::NLCAP)) {
             // that many lines in the window: some line is shorter than 20 bytes and cannot hold 12 columns
             if (lane == 0) report(a, SVJG_BAD_SHORTLINE, tile_start);
             __syncwarp();
@@ -1376,7 +1384,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) scan_kernel(const __grid_
                 const uint32_t dirs = link_dirs(__shfl_up_sync(0xFFFFFFFFu, nd.roles, 1), sl, nd.roles, plus);
                 const bool look = is_tok && idx >= 1 && !((bad >> own_l) & 1u) && idl != NO_NODE && nid != NO_NODE && dirs &&
                                   (ok || (a.flags & FLAG_EXACT_CHECKS));
-                probe_links(a, look, idl, sl, nid, plus, dirs, ok, loff, llen, lt_mask, loc);
+                probe_links(a, look, idl, sl, nid, plus, dirs, ok, loff, llen, lt_mask, n_checks, loc);
                 if (take) {
                     if ((bad >> lane) & 1u) exact = true;
                     pend = 0;
@@ -1413,6 +1421,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) scan_kernel(const __grid_
         loc.n_rec = u_rec;
         loc.n_multi = u_multi;
     }
+    loc.n_checks += n_checks;
     add_stats(a, loc);
 }
 
@@ -1516,10 +1525,10 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_kernel(const __grid_const
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&total, cnt);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t tile_max = a.geo.tile_max;
+        const uint32_t tile_max = a.tile_max;
         uint32_t tile = tile_max;
         if (total) {
-            const uint64_t want = uint64_t(n16) * 16ull * a.geo.tile_lines / total;
+            const uint64_t want = uint64_t(n16) * 16ull * a.tile_lines / total;
             tile = uint32_t(want < uint64_t(tile_max) ? want : uint64_t(tile_max)) & ~31u;
         }
         if (const uint32_t forced = (a.flags >> 16)) tile = forced & ~31u;    // SVJG_TUNE_TILE_BYTES
@@ -1548,7 +1557,7 @@ struct DevCfg {
     int sms = 0;
     int grid_cap = 0;            // blocks of the scan kernel resident at once (SM count x occupancy)
     int min_blocks = 0;          // the scan kernel's instantiation
-    Geo geo{};
+    uint32_t tile_max = 0, tile_lines = 0;
     uint32_t smem = 0;           // dynamic shared memory of one block
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the scan kernel of the last call (svjg_filter_profile)
     bool timed = false;
@@ -1563,22 +1572,15 @@ struct Knobs {
 };
 Knobs g_knobs;
 
-template <int MB>
-int configure_scan(DevCfg &c, int dev) {
-    // the largest tile whose window, list and bitmaps fit MB blocks of WARPS warps into an SM's shared memory
-    int smem_sm = 0, smem_res = 0;
-    SVJG_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    SVJG_CUDA(cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, dev));
-    const uint32_t per_warp = uint32_t((smem_sm / MB - smem_res - 64) / WARPS);
-    uint32_t tile = 8192;
-    while (tile > uint32_t(TILE_MIN) && make_geo(tile).warp_smem > per_warp) tile -= 32;
-    c.geo = make_geo(tile);
-    c.geo.tile_lines = g_knobs.tile_lines > 0 ? uint32_t(g_knobs.tile_lines) : uint32_t(TILE_LINES);
-    c.smem = c.geo.warp_smem * WARPS;
-    c.min_blocks = MB;
-    SVJG_CUDA(cudaFuncSetAttribute(scan_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
+template <class G>
+int configure_scan(DevCfg &c) {
+    c.tile_max = G::TILE_MAX;
+    c.tile_lines = g_knobs.tile_lines > 0 ? uint32_t(g_knobs.tile_lines) : uint32_t(TILE_LINES);
+    c.smem = G::SMEM;
+    c.min_blocks = G::MB;
+    SVJG_CUDA(cudaFuncSetAttribute(scan_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
     int occ = 0;
-    SVJG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<MB>, THREADS, c.smem));
+    SVJG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<G>, THREADS, c.smem));
     if (occ < 1) return set_error(SVJG_E_CUDA, "scan kernel does not fit on an SM");
     c.grid_cap = c.sms * occ;
     return SVJG_OK;
@@ -1592,7 +1594,7 @@ int device_config(DevCfg **out) {
     if (it == g_cfg.end()) {
         DevCfg c;
         SVJG_CUDA(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
-        const int rc = g_knobs.scan_blocks == 8 ? configure_scan<8>(c, dev) : configure_scan<6>(c, dev);
+        const int rc = g_knobs.scan_blocks == 8 ? configure_scan<Geo8>(c) : configure_scan<Geo6>(c);
         if (rc) return rc;
         // scratch comes from the device's default memory pool: keep freed blocks cached in the pool
         cudaMemPool_t pool;
@@ -1694,7 +1696,8 @@ int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.flags = t->filter_flags;
     a.one = 1;
-    a.geo = cfg->geo;
+    a.tile_max = cfg->tile_max;
+    a.tile_lines = cfg->tile_lines;
     if (g_knobs.scan_only) a.flags |= FLAG_STOP_AFTER_SCAN;
     if (g_knobs.tile_bytes) a.flags |= uint32_t(std::min(65535, g_knobs.tile_bytes)) << 16;
 
@@ -1718,8 +1721,8 @@ int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t
     const int scan_grid = int(std::min<uint32_t>((max_tiles + WARPS - 1) / WARPS, uint32_t(cfg->grid_cap)));
     probe_kernel<<<1, PROBE_THREADS, 0, st>>>(a);
     if (g_profile) cudaEventRecord(cfg->ev0, st);
-    if (cfg->min_blocks == 8) scan_kernel<8><<<scan_grid, THREADS, cfg->smem, st>>>(a);
-    else scan_kernel<6><<<scan_grid, THREADS, cfg->smem, st>>>(a);
+    if (cfg->min_blocks == 8) scan_kernel<Geo8><<<scan_grid, THREADS, cfg->smem, st>>>(a);
+    else scan_kernel<Geo6><<<scan_grid, THREADS, cfg->smem, st>>>(a);
     if (g_profile) cudaEventRecord(cfg->ev1, st), cfg->timed = true;
     if (!(a.flags & FLAG_STOP_AFTER_SCAN))
         exact_kernel<<<cfg->sms * 2, FLAT_THREADS, 0, st>>>(a);     // a few lines as a rule: a small grid starts faster
