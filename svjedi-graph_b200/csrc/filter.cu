@@ -74,13 +74,14 @@ struct Geo {
     static constexpr int OFF_XD = OFF_TAB + 4 * BMWORDS;         // ... is not '0'..'9'
     static constexpr int OFF_NS = OFF_XD + 4 * BMWORDS;          // ... starts a path node (no '<' / '>', right behind one)
     static constexpr int OFF_TKO = OFF_NS + 4 * BMWORDS;         // u8[32]  lanes of the lines of a round, in order
-    static constexpr int WARP_SMEM = (OFF_TKO + 32 + 127) & ~127;
+    static constexpr int OFF_LREC = (OFF_TKO + 32 + 15) & ~15;   // uint2[32]  the multi-node lines of a phase B pass, by lane
+    static constexpr int WARP_SMEM = (OFF_LREC + 32 * 8 + 127) & ~127;
     static constexpr int SMEM = WARP_SMEM * WARPS;
     static_assert(TILE_MAX % 32 == 0 && WIN + SPARE < 65536, "window offsets are 16 bit");
     static_assert((SMEM + 1024 + 64) * MB <= 233472, "MB blocks must fit an SM's 228 KB of shared memory");
 };
-typedef Geo<6, 5184> Geo6;      // 24 warps per SM, tiles of up to ~30 lines of 170 bytes
-typedef Geo<8, 3552> Geo8;      // 32 warps per SM, ~21 such lines
+typedef Geo<6, 4992> Geo6;      // 24 warps per SM, tiles of up to ~29 lines of 170 bytes
+typedef Geo<8, 3360> Geo8;      // 32 warps per SM, ~21 such lines
 
 constexpr int FLAT_THREADS = 256;              // block size of the flat (grid-stride) kernels
 
@@ -172,6 +173,16 @@ __device__ __forceinline__ uint32_t mask16(const uint4 &v, F cls) {
     uint32_t hi = __dp4a(cls(v.z), 0x08040201u, 0u);
     hi = __dp4a(cls(v.w), 0x80402010u, hi);
     return (lo >> 7) | (hi << 1);
+}
+// 32 class flags of two adjacent 16-byte chunks: four dp4a chains of two words each (8 flags << 7),
+// joined by multiply-adds (the fields do not overlap, so + is |)
+template <class F>
+__device__ __forceinline__ uint32_t mask32(const uint4 &v0, const uint4 &v1, F cls) {
+    const uint32_t a0 = __dp4a(cls(v0.y), 0x80402010u, __dp4a(cls(v0.x), 0x08040201u, 0u));
+    const uint32_t a1 = __dp4a(cls(v0.w), 0x80402010u, __dp4a(cls(v0.z), 0x08040201u, 0u));
+    const uint32_t a2 = __dp4a(cls(v1.y), 0x80402010u, __dp4a(cls(v1.x), 0x08040201u, 0u));
+    const uint32_t a3 = __dp4a(cls(v1.w), 0x80402010u, __dp4a(cls(v1.z), 0x08040201u, 0u));
+    return (a0 >> 7) + a1 * 2u + a2 * 512u + a3 * 131072u;
 }
 // The same classes for the byte-parallel phase.  `one` is 1 at run time but opaque to the compiler: the
 // carry add becomes an IMAD on the FMA pipe, next to the LOP3s on the ALU pipe (each pipe takes one
@@ -825,34 +836,6 @@ __device__ __forceinline__ uint32_t dec4(uint32_t w) {
 __device__ __forceinline__ uint32_t clear_low_bytes(uint32_t w, int n) {
     return w & __funnelshift_lc(0u, 0xFFFFFFFFu, uint32_t(max(n, 0)) * 8u);
 }
-// more than 12 digits (hardly ever): digit by digit; false when there are more than 18 significant ones
-__device__ __noinline__ bool dec_field_long(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
-    int64_t x = 0;
-    uint32_t nd = 0;
-    for (uint32_t q = lo; q < hi; ++q) {
-        const uint32_t d = uint32_t(win[q]) - '0';
-        nd += (x != 0 || d != 0);
-        x = x * 10 + int64_t(d);
-    }
-    out = x;
-    return nd <= 18;
-}
-// value of the decimal digits in window bytes [lo, hi) (validated: digits only, hi > lo); false
-// when there are more than 18 significant digits.  Up to 12 digits without a loop: the 12 bytes
-// that end at hi as three words, the bytes in front of lo masked away.
-__device__ __forceinline__ bool dec_field(const uint8_t *win, uint32_t lo, uint32_t hi, int64_t &out) {
-    const uint32_t n = hi - lo;
-    if (n > 12) return dec_field_long(win, lo, hi, out);
-    const uint32_t base = hi - 12u, al = base & ~3u, sh = (base & 3u) * 8u;
-    const uint32_t r0 = lds32(win, al), r1 = lds32(win, al + 4), r2 = lds32(win, al + 8), r3 = lds32(win, al + 12);
-    const int m = 12 - int(n);              // bytes of the 12 that are not ours
-    const uint32_t g0 = dec4(clear_low_bytes(__funnelshift_r(r0, r1, sh), m));
-    const uint32_t g1 = dec4(clear_low_bytes(__funnelshift_r(r1, r2, sh), m - 4));
-    const uint32_t g2 = dec4(clear_low_bytes(__funnelshift_r(r2, r3, sh), m - 8));
-    out = int64_t(uint64_t(g0) * 100000000ull + uint64_t(g1 * 10000u + g2));
-    return true;
-}
-
 // plain-node table: exact key -> (node id, alt sequence length)
 __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uint64_t c1, uint32_t ka, uint32_t kb,
                                            uint32_t &id, uint32_t &alt_len, uint32_t &roles) {
@@ -983,19 +966,20 @@ __device__ __forceinline__ uint32_t next_node(const uint32_t *nsb, uint32_t pos,
 // ---- hits of one link whose table slot is not the common case (a key with several entries, a poisoned
 // entry, both directions possible, a displaced slot): the general link() of the exact route
 __device__ __noinline__ void link_slow(const FilterArgs &a, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr, bool ok,
-                                       uint32_t dirs, uint32_t off, uint32_t len, Local &loc) {
+                                       uint32_t dirs, uint32_t off, uint32_t len) {
+    Local loc;                                   // a rare route: its tallies go straight to the statistics
     Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
     const Rec<GmemSrc>::Tok none{0, 0};
     rec.link(none, idl, int(sl), none, idr, int(sr), true, ok, dirs);
     if (rec.err) report(a, rec.err, off);
+    if (loc.n_checks) atomicAdd(a.stats + 3, (unsigned long long)loc.n_checks);
 }
 
 // ---- the links of up to 32 adjacent node pairs, one per lane, all lanes of the warp together: one probe
 // of the link table each (the key the node roles allow), hit tuples appended with one cursor atomic.
 // `want`: this lane has a link to look up (both ids known, some key possible, verdict `ok` or exact checks).
 __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr,
-                                            uint32_t dirs, bool ok, uint32_t off, uint32_t len, uint32_t lt_mask, uint32_t &n_checks,
-                                            Local &loc) {
+                                            uint32_t dirs, bool ok, uint32_t off, uint32_t len, uint32_t lt_mask, uint32_t &n_checks) {
     uint4 sv = make_uint4(0, 0, 0, 0);
     // the one key that can exist; where both can (dirs == 3) the general routine looks them up
     const bool fwd = (dirs & 1u) != 0;
@@ -1036,7 +1020,7 @@ __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint
         }
     }
     if (__any_sync(0xFFFFFFFFu, want && !simple)) {
-        if (want && !simple) link_slow(a, idl, sl, idr, sr, ok, dirs, off, len, loc);
+        if (want && !simple) link_slow(a, idl, sl, idr, sr, ok, dirs, off, len);
         __syncwarp();
     }
 }
@@ -1052,7 +1036,7 @@ constexpr int SLAB_N = 256;                    // nodes of such a line in the sc
 template <class B>
 __device__ __noinline__ bool long_line(const FilterArgs &a, const B src, const uint32_t *nsb, const uint32_t *xdb, uint4 *slab,
                                        uint32_t slab_cap, int lane, uint32_t cnt, uint32_t lps, uint32_t lpe, int64_t lts,
-                                       int64_t ltail, uint32_t off, uint32_t len, Local &loc) {
+                                       int64_t ltail, uint32_t off, uint32_t len) {
     if (cnt > slab_cap) return false;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t n_checks = 0;
@@ -1098,10 +1082,11 @@ __device__ __noinline__ bool long_line(const FilterArgs &a, const B src, const u
         const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
         const uint32_t dirs = link_dirs(lf.w >> 1, lf.w & 1u, me.w >> 1, me.w & 1u);
         const bool want = act && t && lf.x != NO_NODE && me.x != NO_NODE && dirs && (ok || (a.flags & FLAG_EXACT_CHECKS));
-        probe_links(a, want, lf.x, lf.w & 1u, me.x, me.w & 1u, dirs, ok, off, len, lt_mask, n_checks, loc);
+        probe_links(a, want, lf.x, lf.w & 1u, me.x, me.w & 1u, dirs, ok, off, len, lt_mask, n_checks);
         before += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    loc.n_checks += n_checks;
+    n_checks = __reduce_add_sync(0xFFFFFFFFu, n_checks);
+    if (lane == 0 && n_checks) atomicAdd(a.stats + 3, (unsigned long long)n_checks);
     return true;
 }
 
@@ -1121,6 +1106,7 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
     uint32_t *xdb = reinterpret_cast<uint32_t *>(win + G::OFF_XD);         // bit i: ... is not '0'..'9'
     uint32_t *nsb = reinterpret_cast<uint32_t *>(win + G::OFF_NS);         // bit i: ... starts a path node
     uint8_t *tko = win + G::OFF_TKO;
+    uint2 *lrec = reinterpret_cast<uint2 *>(win + G::OFF_LREC);            // {s | line bytes << 16, ps | pe << 16}
     uint64_t *mbar = &mbars[warp];
     const SmemBytes src{win};
 
@@ -1129,7 +1115,6 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
     for (int i = G::WIN + lane; i < G::WIN + SPARE; i += 32) win[i] = 0;   // never written by the copies
     __syncwarp();
     uint32_t phase = 0;
-    Local loc;
     uint32_t u_rec = 0, u_multi = 0, n_checks = 0;   // tallies: lines, lines with >= 2 nodes (both warp-uniform), overlap tests
     const uint32_t one = a.one;
     const uint32_t n_workers = gridDim.x * WARPS;
@@ -1181,10 +1166,10 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
             if (c < n_pairs) {
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(win + p0);
                 const uint4 v1 = *reinterpret_cast<const uint4 *>(win + p0 + 16);
-                m = mask16(v0, IsNewline{one}) | (mask16(v1, IsNewline{one}) << 16);
-                tabb[c] = mask16(v0, IsTab{one}) | (mask16(v1, IsTab{one}) << 16);
-                xdb[c] = mask16(v0, IsNonDigit{one}) | (mask16(v1, IsNonDigit{one}) << 16);
-                const uint32_t d = mask16(v0, IsDelim{one}) | (mask16(v1, IsDelim{one}) << 16);
+                m = mask32(v0, v1, IsNewline{one});
+                tabb[c] = mask32(v0, v1, IsTab{one});
+                xdb[c] = mask32(v0, v1, IsNonDigit{one});
+                const uint32_t d = mask32(v0, v1, IsDelim{one});
                 const uint32_t left = c ? uint32_t(is_delim(win[p0 - 1u])) : 0u;     // the byte in front of these 32
                 nsb[c] = ((d << 1) | left) & ~d;
                 if (c == 0) m &= 0x80000000u;                             // positions before HEAD-1 are not ours to see
@@ -1212,8 +1197,7 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
                 n_own += __popc(bo);
             }
             // behind the tile: a newline at or after own_end - 1 ends the last owned line
-            const bool ends_it = (m & ~low_bits(int(own_end) - 1 - int(p0))) != 0;
-            if ((c0 + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, ends_it)) break;
+            if ((c0 + 32u) * 32u >= own_end && __any_sync(0xFFFFFFFFu, (m & ~low_bits(int(own_end) - 1 - int(p0))) != 0)) break;
         }
         __syncwarp();
         if (a.flags & FLAG_STOP_AFTER_SCAN) continue;                 // measurement aid (SVJG_TUNE_SCAN_ONLY)
@@ -1314,19 +1298,21 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
                 }
             }
             __syncwarp();
-            // Tlen, Ts, Te of the lines that go on (digit-only columns 7-9).  The reference has bigints;
-            // this route stops at 18 digits and says so.
-            int64_t ts = 0, tail = 0;
+            // Tlen, Ts, Te of the lines that go on (digit-only columns 7-9): values of up to nine digits here,
+            // anything longer (a path of a billion bases) is the exact route's
+            int32_t ts = 0, tail = 0;
             if (want) {
-                int64_t tlen = 0, te = 0;
-                const bool fits = dec_field(win, c6 + 1, c7, tlen) & dec_field(win, c7 + 1, c8, ts) & dec_field(win, c8 + 1, c9, te);
-                tail = tlen - te - 1;
-                if (!fits) {
-                    report(a, SVJG_BAD_RANGE, wbase + s);
+                const uint32_t n_tlen = c7 - c6 - 1u, n_ts = c8 - c7 - 1u, n_te = c9 - c8 - 1u;
+                if (max(n_tlen, max(n_ts, n_te)) <= 9u) {
+                    ts = int32_t(dec9(src, c8, n_ts));
+                    tail = int32_t(dec9(src, c7, n_tlen)) - int32_t(dec9(src, c9, n_te)) - 1;
+                    lrec[lane] = make_uint2(s | ((e - s + (has_nl ? 1u : 0u)) << 16), ps | (pe << 16));
+                } else {
+                    exact = true;
                     want = 0;
                 }
             }
-            const uint32_t l_off = wbase + s, l_len = e - s + (has_nl ? 1u : 0u);
+            __syncwarp();
             // ---- phases C and D: rounds of at most 32 path nodes, whole lines only, one lane per node
             uint32_t pend = want > 32u ? 0u : want;
             while (__any_sync(0xFFFFFFFFu, pend != 0)) {
@@ -1347,7 +1333,8 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
                     own_l = tko[__popc(below) - 1];
                     idx = uint32_t(lane) - uint32_t(31 - __clz(below));             // number of this node in its line
                 }
-                const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), own_l);
+                const uint2 lr = lrec[own_l];
+                const uint32_t lpath = lr.y;
                 const uint32_t lcnt = __shfl_sync(0xFFFFFFFFu, pend, own_l);
                 // C: this lane's node; its name ends in front of the next node's delimiter, or with the path
                 uint32_t tpos = 0;
@@ -1379,12 +1366,12 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
                 const uint64_t total = __shfl_sync(0xFFFFFFFFu, lsum, is_tok ? lfirst + lcnt - 1u : 0u);
                 const uint32_t idl = __shfl_up_sync(0xFFFFFFFFu, nid, 1), sl = __shfl_up_sync(0xFFFFFFFFu, plus, 1);
                 const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, own_l), ltail = __shfl_sync(0xFFFFFFFFu, tail, own_l);
-                const uint32_t loff = __shfl_sync(0xFFFFFFFFu, l_off, own_l), llen = __shfl_sync(0xFFFFFFFFu, l_len, own_l);
+                const uint32_t loff = wbase + (lr.x & 0xFFFFu), llen = lr.x >> 16;
                 const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
                 const uint32_t dirs = link_dirs(__shfl_up_sync(0xFFFFFFFFu, nd.roles, 1), sl, nd.roles, plus);
                 const bool look = is_tok && idx >= 1 && !((bad >> own_l) & 1u) && idl != NO_NODE && nid != NO_NODE && dirs &&
                                   (ok || (a.flags & FLAG_EXACT_CHECKS));
-                probe_links(a, look, idl, sl, nid, plus, dirs, ok, loff, llen, lt_mask, n_checks, loc);
+                probe_links(a, look, idl, sl, nid, plus, dirs, ok, loff, llen, lt_mask, n_checks);
                 if (take) {
                     if ((bad >> lane) & 1u) exact = true;
                     pend = 0;
@@ -1395,11 +1382,11 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
             // ---- lines with more nodes than a round has lanes: one line at a time (long_line())
             for (uint32_t longb = __ballot_sync(0xFFFFFFFFu, want > 32u); longb; longb &= longb - 1) {
                 const int L = __ffs(longb) - 1;
-                const uint32_t lpath = __shfl_sync(0xFFFFFFFFu, ps | (pe << 16), L);
+                const uint2 lr = lrec[L];
                 const bool done = long_line(a, src, nsb, xdb, a.sc.slab + size_t(blockIdx.x * WARPS + warp) * SLAB_N, SLAB_N, lane,
-                                            __shfl_sync(0xFFFFFFFFu, want, L), lpath & 0xFFFFu, lpath >> 16,
+                                            __shfl_sync(0xFFFFFFFFu, want, L), lr.y & 0xFFFFu, lr.y >> 16,
                                             __shfl_sync(0xFFFFFFFFu, ts, L), __shfl_sync(0xFFFFFFFFu, tail, L),
-                                            __shfl_sync(0xFFFFFFFFu, l_off, L), __shfl_sync(0xFFFFFFFFu, l_len, L), loc);
+                                            wbase + (lr.x & 0xFFFFu), lr.x >> 16);
                 if (!done && lane == L) exact = true;
                 u_multi += done;
             }
@@ -1417,12 +1404,12 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
         }
         __syncwarp();
     }
+    n_checks = __reduce_add_sync(0xFFFFFFFFu, n_checks);
     if (lane == 0) {
-        loc.n_rec = u_rec;
-        loc.n_multi = u_multi;
+        if (u_rec) atomicAdd(a.stats + 1, (unsigned long long)u_rec);
+        if (u_multi) atomicAdd(a.stats + 2, (unsigned long long)u_multi);
+        if (n_checks) atomicAdd(a.stats + 3, (unsigned long long)n_checks);
     }
-    loc.n_checks += n_checks;
-    add_stats(a, loc);
 }
 
 // ===========================================================================
@@ -1461,8 +1448,7 @@ __device__ __noinline__ bool giant_line(const FilterArgs &a, uint32_t ps, uint32
         __stcg(xdb + w, x);
     }
     __syncwarp();
-    return long_line(a, ShardBytes{&a}, nsb - w0, xdb - w0, a.sc.pool + base + 2u * bm16, ntok, lane, ntok, ps, pe, ts, tail, off, len,
-                     loc);
+    return long_line(a, ShardBytes{&a}, nsb - w0, xdb - w0, a.sc.pool + base + 2u * bm16, ntok, lane, ntok, ps, pe, ts, tail, off, len);
 }
 
 __global__ void __launch_bounds__(FLAT_THREADS) exact_kernel(const __grid_constant__ FilterArgs a) {
