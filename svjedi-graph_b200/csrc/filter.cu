@@ -963,65 +963,67 @@ __device__ __forceinline__ uint32_t find_node(const uint32_t *nsb, uint32_t lps,
 // first node start at or behind `pos` and in front of `end`; `end` if there is none
 __device__ __forceinline__ uint32_t next_node(const uint32_t *nsb, uint32_t pos, uint32_t end) { return next_tab(nsb, pos, end); }
 
-// ---- hits of one link whose table slot is not the common case (a key with several entries, a poisoned
-// entry, both directions possible, a displaced slot): the general link() of the exact route
-__device__ __noinline__ void link_slow(const FilterArgs &a, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr, bool ok,
-                                       uint32_t dirs, uint32_t off, uint32_t len) {
-    Local loc;                                   // a rare route: its tallies go straight to the statistics
-    Rec<GmemSrc> rec(a, GmemSrc{a.gaf}, off, len, loc);
-    const Rec<GmemSrc>::Tok none{0, 0};
-    rec.link(none, idl, int(sl), none, idr, int(sr), true, ok, dirs);
-    if (rec.err) report(a, rec.err, off);
-    if (loc.n_checks) atomicAdd(a.stats + 3, (unsigned long long)loc.n_checks);
-}
-
-// ---- the links of up to 32 adjacent node pairs, one per lane, all lanes of the warp together: one probe
-// of the link table each (the key the node roles allow), hit tuples appended with one cursor atomic.
+// ---- the links of up to 32 adjacent node pairs, one per lane, all lanes of the warp together: the keys the
+// node roles allow are looked up in the link table -- the forward key first, then the reverse one
+// (:141-148; a second pass, run only when some link can have both) -- and the entries of the keys found
+// become hit tuples, appended with one cursor atomic per pass, and counter increments (:150-166).
 // `want`: this lane has a link to look up (both ids known, some key possible, verdict `ok` or exact checks).
 __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint32_t idl, uint32_t sl, uint32_t idr, uint32_t sr,
                                             uint32_t dirs, bool ok, uint32_t off, uint32_t len, uint32_t lt_mask, uint32_t &n_checks) {
-    uint4 sv = make_uint4(0, 0, 0, 0);
-    // the one key that can exist; where both can (dirs == 3) the general routine looks them up
-    const bool fwd = (dirs & 1u) != 0;
-    const uint32_t kl = fwd ? idl : idr, kr = fwd ? idr : idl, ksl = fwd ? sl : sr ^ 1u, ksr = fwd ? sr : sl ^ 1u;
-    const uint32_t key_lo = (kr << 1) | ksr, key_hi = (kl << 1) | ksl;              // link_key() in halves
-    bool go = want && dirs != 3u;
-    uint32_t i = link_hash((uint64_t(key_hi) << 32) | key_lo);
-    bool match = false;
-    // linear probing: nearly always the first slot settles it (the key, or an empty slot)
-    while (__any_sync(0xFFFFFFFFu, go)) {
-        if (go) {
-            i &= a.tb.link_mask;
-            sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
-            match = (sv.w & 1u) && sv.x == key_lo && sv.y == key_hi;
-            go = (sv.w & 1u) && !match;
-            ++i;
-        }
-    }
-    // settled here: the key is absent, or present with exactly one sound entry
-    const bool simple = want && dirs != 3u && (!match || ((sv.w >> 3) == 2u && sv.z != ENTRY_POISON));
-    const bool hit = simple && match;
-    n_checks += hit;
-    const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit && ok);
-    if (hb) {
-        unsigned long long base = 0;
-        const int leader = __ffs(hb) - 1;
-        if (int(threadIdx.x & 31) == leader) base = atomicAdd(a.stats + 0, (unsigned long long)__popc(hb));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (hit && ok) {
-            atomicAdd(a.counts + sv.z, 1u);
-            const unsigned long long k = base + __popc(hb & lt_mask);
-            if (k < a.hit_cap) {
-                a.hit_sv2[k] = sv.z;
-                if (a.hit_off64) a.hit_off64[k] = a.base + off;
-                else a.hit_off[k] = off;
-                a.hit_len[k] = len;
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < 2; ++pass) {
+        const bool act = want && (pass ? dirs == 3u : dirs != 0u);
+        if (pass && !__any_sync(0xFFFFFFFFu, act)) break;
+        const bool fwd = pass == 0 && (dirs & 1u);
+        const uint32_t kl = fwd ? idl : idr, kr = fwd ? idr : idl, ksl = fwd ? sl : sr ^ 1u, ksr = fwd ? sr : sl ^ 1u;
+        const uint32_t key_lo = (kr << 1) | ksr, key_hi = (kl << 1) | ksl;              // link_key() in halves
+        uint4 sv = make_uint4(0, 0, 0, 0);
+        uint32_t i = link_hash((uint64_t(key_hi) << 32) | key_lo);
+        bool go = act, match = false;
+        // linear probing: nearly always the first slot settles it (the key, or an empty slot)
+        while (__any_sync(0xFFFFFFFFu, go)) {
+            if (go) {
+                i &= a.tb.link_mask;
+                sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
+                match = (sv.w & 1u) && sv.x == key_lo && sv.y == key_hi;
+                go = (sv.w & 1u) && !match;
+                ++i;
             }
         }
-    }
-    if (__any_sync(0xFFFFFFFFu, want && !simple)) {
-        if (want && !simple) link_slow(a, idl, sl, idr, sr, ok, dirs, off, len);
-        __syncwarp();
+        const bool poisoned = match && (sv.w & 8u);                      // a key whose value is no list: the reference raises
+        const uint32_t cnt = (match && !poisoned) ? sv.w >> 4 : 0u;
+        n_checks += cnt;
+        const uint32_t mine = ok ? cnt : 0u;                             // tuples of this lane
+        uint32_t before, total;
+        if (__any_sync(0xFFFFFFFFu, mine > 1u)) {
+            const uint32_t incl = warp_incl_scan(mine, int(threadIdx.x & 31));
+            before = incl - mine;
+            total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        } else {
+            const uint32_t hb = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+            before = __popc(hb & lt_mask);
+            total = __popc(hb);
+        }
+        if (total) {
+            unsigned long long base = 0;
+            if ((threadIdx.x & 31) == 0) base = atomicAdd(a.stats + 0, (unsigned long long)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + before;
+            for (uint32_t k = 0; k < mine; ++k) {
+                const uint32_t sv2 = cnt == 1u ? sv.z : __ldg(a.tb.entries + sv.z + k);
+                if (sv2 == ENTRY_POISON) {                               // an entry the reference raises on, reached with ok
+                    report(a, SVJG_BAD_ENTRY, off);
+                    break;
+                }
+                atomicAdd(a.counts + sv2, 1u);
+                if (base + k < a.hit_cap) {
+                    a.hit_sv2[base + k] = sv2;
+                    if (a.hit_off64) a.hit_off64[base + k] = a.base + off;
+                    else a.hit_off[base + k] = off;
+                    a.hit_len[base + k] = len;
+                }
+            }
+        }
+        if (poisoned) report(a, SVJG_BAD_ENTRY, off);
     }
 }
 
