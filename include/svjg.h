@@ -284,6 +284,10 @@ void svjg_buffer_free(char *p);
 int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes,
                                const uint32_t *hit_sv2, const uint64_t *hit_off, const uint32_t *hit_len,
                                uint64_t n_hits, const char *out_path);
+/* the same text in memory (*out: malloc'd, released with svjg_buffer_free) */
+int svjg_emit_informative_json_mem(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, const uint32_t *hit_sv2,
+                                   const uint64_t *hit_off, const uint32_t *hit_len, uint64_t n_hits, char **out,
+                                   uint64_t *out_len);
 
 #ifdef __cplusplus
 }

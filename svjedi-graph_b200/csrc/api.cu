@@ -358,10 +358,10 @@ bool put_json_string(Out &o, const uint8_t *s, size_t n) {
 
 }  // namespace
 
-extern "C" int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes,
-                                          const uint32_t *hit_sv2, const uint64_t *hit_off, const uint32_t *hit_len,
-                                          uint64_t n_hits, const char *out_path) {
-    if (!t || !out_path || (n_hits && (!gaf || !hit_sv2 || !hit_off || !hit_len)))
+// out_path: the file to write; or mem: the text is appended there instead
+static int emit_json(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, const uint32_t *hit_sv2, const uint64_t *hit_off,
+                     const uint32_t *hit_len, uint64_t n_hits, const char *out_path, std::vector<char> *mem) {
+    if (!t || (!out_path && !mem) || (n_hits && (!gaf || !hit_sv2 || !hit_off || !hit_len)))
         return set_error(SVJG_E_ARG, "svjg_emit_informative_json: NULL argument");
     const uint64_t n2 = uint64_t(t->sv_ids.size()) * 2;
     // counting sort by (sv, allele); inside a list the reference appends in file order
@@ -381,8 +381,15 @@ extern "C" int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *g
         std::sort(order.begin() + start[k], order.begin() + start[k + 1],
                   [&](uint64_t x, uint64_t y) { return hit_off[x] < hit_off[y]; });
 
-    FILE *f = fopen(out_path, "wb");
-    if (!f) return set_error(SVJG_E_IO, std::string("cannot write ") + out_path);
+    FILE *f = mem ? nullptr : fopen(out_path, "wb");
+    if (!mem && !f) return set_error(SVJG_E_IO, std::string("cannot write ") + out_path);
+    auto sink = [&](const char *p, size_t n) {
+        if (mem) {
+            mem->insert(mem->end(), p, p + n);
+            return true;
+        }
+        return fwrite(p, 1, n, f) == n;
+    };
     // The text of a key does not depend on the others: keys are rendered by several threads, a batch
     // (about 256 MB of lines) at a time, every thread a run of keys with about the same number of
     // bytes, and written in key order.  Every key starts with ",\n    "; the first one of the file has
@@ -462,13 +469,36 @@ extern "C" int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *g
             if (b.empty()) continue;
             if (!any) b[0] = '{';
             any = true;
-            io_ok = fwrite(b.data(), 1, b.size(), f) == b.size();
+            io_ok = sink(b.data(), b.size());
         }
         lo = hi;
     }
-    if (io_ok) io_ok = fputs(any ? "\n}" : "{}", f) >= 0;
-    bool ok = fclose(f) == 0 && io_ok;
+    if (io_ok) io_ok = any ? sink("\n}", 2) : sink("{}", 2);
+    bool ok = (f ? fclose(f) == 0 : true) && io_ok;
     if (!utf8_ok) return set_error(SVJG_E_INPUT, "GAF text is not valid UTF-8 (the reference cannot read it)");
-    if (!ok) return set_error(SVJG_E_IO, std::string("write failed: ") + out_path);
+    if (!ok) return set_error(SVJG_E_IO, std::string("write failed: ") + (out_path ? out_path : "(memory)"));
+    return SVJG_OK;
+}
+
+extern "C" int svjg_emit_informative_json(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes,
+                                          const uint32_t *hit_sv2, const uint64_t *hit_off, const uint32_t *hit_len,
+                                          uint64_t n_hits, const char *out_path) {
+    if (!out_path) return set_error(SVJG_E_ARG, "svjg_emit_informative_json: NULL argument");
+    return emit_json(t, gaf, n_bytes, hit_sv2, hit_off, hit_len, n_hits, out_path, nullptr);
+}
+
+// the same text in memory: *out is released with svjg_buffer_free
+extern "C" int svjg_emit_informative_json_mem(const svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes,
+                                              const uint32_t *hit_sv2, const uint64_t *hit_off, const uint32_t *hit_len,
+                                              uint64_t n_hits, char **out, uint64_t *out_len) {
+    if (!out || !out_len) return set_error(SVJG_E_ARG, "svjg_emit_informative_json_mem: NULL argument");
+    std::vector<char> mem;
+    const int rc = emit_json(t, gaf, n_bytes, hit_sv2, hit_off, hit_len, n_hits, nullptr, &mem);
+    if (rc) return rc;
+    char *p = static_cast<char *>(malloc(mem.size() ? mem.size() : 1));
+    if (!p) return set_error(SVJG_E_NOMEM, "out of memory");
+    memcpy(p, mem.data(), mem.size());
+    *out = p;
+    *out_len = mem.size();
     return SVJG_OK;
 }

@@ -109,6 +109,8 @@ def _load():
                                       C.POINTER(C.c_uint64)]),
         "svjg_buffer_free": (None, [vp]),
         "svjg_emit_informative_json": (C.c_int, [vp, u8p, C.c_uint64, u32p, u64p, u32p, C.c_uint64, C.c_char_p]),
+        "svjg_emit_informative_json_mem": (C.c_int, [vp, u8p, C.c_uint64, u32p, u64p, u32p, C.c_uint64,
+                                                     C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
