@@ -1,23 +1,30 @@
 #!/usr/bin/env python3
-"""bench.py — throughput of the B200 hot path (GAF filter + allele counts +
-genotype) on the BASELINE.json workload, one JSON line on stdout.
+"""bench.py — throughput of the B200 hot path (GAF filter + allele counts + genotype) on the
+BASELINE.json workload, one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--scale 1.0]
-    python bench.py --impl reference ...      # CPU arm: the oracle port on host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--scale 1.0] [--catalogue full]
+    python bench.py --impl reference ...      # CPU arm: the UNMODIFIED reference scripts on the host cores
+    torchrun ... bench.py --gpus N [--scaling strong]
 
-A "step" is one pass of the hot path over one batch of synthetic GAF: counters
-reset -> filter chain (probe, scan_parse, link, exact kernels) -> (NCCL all-reduce of
-the counters when N > 1) -> genotype kernel.  `value` = alignments/s with the batch resident in HBM;
-`e2e` = the same through svjg_filter_host (pinned HOST bytes in, counts + hits +
-genotypes back on the host, copies inside the timed region).
+A "step" is one pass of the hot path over one batch of synthetic GAF (one file of the named config per
+GPU): counters reset -> filter chain (probe, scan, exact kernels) -> counters of all ranks summed (inside
+the genotype kernel over NVLink peer memory, or ncclAllReduce) -> genotype kernel.
+`value`  alignments/s with the batch resident in HBM (CUDA events, max over ranks).
+`e2e`    the same job through the C ABI with HOST buffers: pinned GAF bytes in ->
+         `informative_aln.json` bytes + `genotype.vcf` bytes out, in host memory; every copy, the JSON
+         text and the VCF text inside the timed region.  At N > 1: one such job per GPU at once.
+`--scaling strong`: ONE batch cut by bytes at line ends over the N ranks (svjg.shard.shard_cuts), the
+         hits of all ranks checked against a one-GPU pass over the whole batch before timing.
 """
 import argparse
 import ctypes as C
 import json
 import math
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -28,10 +35,9 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 METRIC = "gaf_alignments_filtered_assigned_per_sec"
-# dram__bytes_read.sum + dram__bytes_write.sum of the filter chain per launch, from the ncu --set full
-# capture committed under profiles/ (None where no capture exists for the workload)
-FILTER_TRAFFIC = {"C2": 557_700_000}   # profiles/r1/ncu_chain_v15_summary.txt: scan_parse 517.4+18.7, link 21.4, probe+exact 0.2 MB
 UNIT = "alignments/s"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")          # the three unmodified scripts, copied by __graft_entry__.build()
+REF_SCRIPTS = ("filter-alignments.py", "predict-genotype.py")
 
 
 def parse_args():
@@ -45,9 +51,11 @@ def parse_args():
     ap.add_argument("--catalogue", default="scaled", choices=["scaled", "full"],
                     help="full: the SV catalogue (and genome) at the config's stated size whatever --scale says; "
                          "C5 then probes its 1 M-SV tables (459 MB, beyond L2) with a --scale shard of the records")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: one batch per GPU (weak), or one batch cut by bytes over the GPUs (strong)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--kernel-only", action="store_true", help="developer mode: print the kernel times and stop")
-    ap.add_argument("--cpu-sample", type=int, default=150_000, help="records the CPU baseline is timed on")
+    ap.add_argument("--cpu-sample", type=int, default=20_000, help="records per host process the CPU arm is timed on")
     ap.add_argument("--scan-blocks", type=int, default=0, help="developer: blocks per SM the scan kernel is sized for (6 or 8)")
     ap.add_argument("--tile-lines", type=int, default=0, help="developer: lines a tile of the scan kernel should hold")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
@@ -55,24 +63,23 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload(args, rank):
-    """Synthetic batch of the named config (per-GPU batch: weak scaling).
-    Tables are identical on every rank; reads differ by rank."""
+def workload(args, stream):
+    """Synthetic batch of the named config.  Tables are identical on every rank; `stream` selects the reads."""
     from svjg import synth
     scale = args.scale
     if scale is None:
-        # C5 (1M SVs / 200M records over 8 GPUs) is sized per GPU: 1/8 of the records
+        # C5 (1M SVs / 200M records over 8 GPUs) is sized per GPU: 1/8 of the records would be 25 M; 4 M by default
         scale = 1.0 if args.workload != "C5" else 0.02
     t0 = time.time()
     # synthetic inputs are deterministic; keep them for later runs on the same box (untimed either way)
     import pickle
     cscale = 1.0 if args.catalogue == "full" else None
-    cache = os.path.join(os.environ.get("SVJG_CACHE", "/tmp"), f"svjg_wl_{args.workload}_{scale:g}_{args.catalogue}_{rank}.pkl")
+    cache = os.path.join(os.environ.get("SVJG_CACHE", "/tmp"), f"svjg_wl_{args.workload}_{scale:g}_{args.catalogue}_{stream}.pkl")
     if os.path.exists(cache):
         with open(cache, "rb") as fh:
             g, vcf, gaf = pickle.load(fh)
     else:
-        g, vcf, gaf = synth.make_workload(args.workload, scale=scale, stream0=rank, catalogue_scale=cscale)
+        g, vcf, gaf = synth.make_workload(args.workload, scale=scale, stream0=stream, catalogue_scale=cscale)
         try:
             with open(cache + f".{os.getpid()}", "wb") as fh:
                 pickle.dump((g, vcf, gaf), fh, protocol=pickle.HIGHEST_PROTOCOL)
@@ -92,6 +99,16 @@ def load_peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the filter chain per launch, from the ncu --set full
+    captures summarised under profiles/ (profiles/ncu_traffic.py writes the table); None where no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(key, {}).get("dram_bytes")
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -141,40 +158,171 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(gaf_text, edges_text, gfa_text, vcf_text, n_sample):
-    """The oracle port (oracle/svjg_oracle.py) timed on the first n_sample
-    records of the same batch, single-threaded like the reference."""
-    from oracle import svjg_oracle as O
-    lines = []
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the unmodified reference scripts (baseline/_ref/, copied from /root/reference by build())
+# as subprocesses with their own command lines; the oracle port only where they are not there
+# --------------------------------------------------------------------------------------------------
+def reference_available():
+    return all(os.path.exists(os.path.join(REF_DIR, s)) for s in REF_SCRIPTS)
+
+
+def first_lines(text, n):
     pos = 0
-    for _ in range(n_sample):
-        j = gaf_text.find("\n", pos)
+    for _ in range(n):
+        j = text.find("\n", pos)
         if j < 0:
-            break
-        lines.append(gaf_text[pos:j + 1])
+            return text
         pos = j + 1
-    edges = json.loads(edges_text)
-    alt = {}
-    for line in gfa_text.splitlines(True):
-        if line.startswith("S"):
-            c = line.split("\t")
-            if "." in c[1].split(":")[-1]:
-                alt[c[1]] = len(line.rstrip().split("\t")[2])
-    t0 = time.perf_counter()
-    d = O.filter_alignments(lines, edges, alt)
+    return text[:pos]
+
+
+class ReferenceRun:
+    """One directory with the inputs of filter-alignments.py / predict-genotype.py as files:
+    `<tmp>/wl.gfa`, `<tmp>/wl.vcf`, and per shard k `<tmp>/s<k>.gaf` + `<tmp>/s<k>_svs_edges.json` (a link to
+    the one table file; the script finds it through its -p prefix, filter-alignments.py:78)."""
+
+    def __init__(self, gaf_text, edges_text, gfa_text, vcf_text, n_procs, per_proc):
+        self.dir = tempfile.mkdtemp(prefix="svjg_ref_")
+        self.n_procs = n_procs
+        with open(os.path.join(self.dir, "wl.gfa"), "w") as fh:
+            fh.write(gfa_text)
+        with open(os.path.join(self.dir, "wl.vcf"), "w") as fh:
+            fh.write(vcf_text)
+        with open(os.path.join(self.dir, "edges.json"), "w") as fh:
+            fh.write(edges_text)
+        sample = first_lines(gaf_text, n_procs * per_proc)
+        lines = sample.splitlines(True)
+        self.n_sample = len(lines)
+        share = (len(lines) + n_procs - 1) // n_procs
+        for k in range(n_procs):
+            with open(os.path.join(self.dir, f"s{k}.gaf"), "w") as fh:
+                fh.writelines(lines[k * share:(k + 1) * share])
+            os.symlink("edges.json", os.path.join(self.dir, f"s{k}_svs_edges.json"))
+        open(os.path.join(self.dir, "empty.gaf"), "w").close()
+        os.symlink("edges.json", os.path.join(self.dir, "empty_svs_edges.json"))
+
+    def _filter(self, tags):
+        procs = [subprocess.Popen([sys.executable, os.path.join(REF_DIR, "filter-alignments.py"), "-a", f"{t}.gaf", "-g", "wl.gfa",
+                                   "-p", t], cwd=self.dir, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE) for t in tags]
+        for p in procs:
+            _, err = p.communicate()
+            if p.returncode:
+                raise SystemExit("reference filter-alignments.py failed: " + err.decode()[-300:])
+
+    def startup_seconds(self):
+        """filter-alignments.py on an empty GAF: interpreter start + table load, which do not grow with the records"""
+        t0 = time.perf_counter()
+        self._filter(["empty"])
+        return time.perf_counter() - t0
+
+    def step(self):
+        """(seconds of the line-sharded filter processes, seconds of predict-genotype.py on the merged JSON)"""
+        t0 = time.perf_counter()
+        self._filter([f"s{k}" for k in range(self.n_procs)])
+        t1 = time.perf_counter()
+        # harness, untimed: per-key lists concatenated in shard order = what one process would have appended (:166)
+        merged = {}
+        for k in range(self.n_procs):
+            with open(os.path.join(self.dir, f"s{k}_informative_aln.json")) as fh:
+                for key, (ref, alt) in json.load(fh).items():
+                    m = merged.setdefault(key, [[], []])
+                    m[0] += ref
+                    m[1] += alt
+        with open(os.path.join(self.dir, "merged.json"), "w") as fh:
+            fh.write(json.dumps(merged, sort_keys=True, indent=4))
+        t2 = time.perf_counter()
+        r = subprocess.run([sys.executable, os.path.join(REF_DIR, "predict-genotype.py"), "-d", "merged.json", "-v", "wl.vcf",
+                            "-o", "out.vcf"], cwd=self.dir, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if r.returncode:
+            raise SystemExit("reference predict-genotype.py failed: " + r.stderr.decode()[-300:])
+        return t1 - t0, time.perf_counter() - t2
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+_PORT = None
+
+
+def _port_shard(k):
+    from oracle import svjg_oracle as O
+    d = O.filter_alignments(_PORT[0][k], _PORT[1], _PORT[2])
     O.dumps_informative(d)
+    return O.hit_counts(d)
+
+
+def port_step(lines_by_shard, edges, alt, vcf_lines):
+    """The oracle port in forked workers: only when baseline/_ref/ is not there."""
+    import multiprocessing as mp
+    from oracle import svjg_oracle as O
+    global _PORT
+    _PORT = (lines_by_shard, edges, alt)
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(len(lines_by_shard)) as pool:
+        parts = pool.map(_port_shard, range(len(lines_by_shard)), chunksize=1)
+    counts = {}
+    for c in parts:
+        for k, (a, b) in c.items():
+            x = counts.get(k, (0, 0))
+            counts[k] = (x[0] + a, x[1] + b)
     t1 = time.perf_counter()
-    _, n_gt = O.genotype_vcf(O.hit_counts(d), vcf_text.splitlines(True))
-    t2 = time.perf_counter()
-    return len(lines), t1 - t0, t2 - t1, n_gt
+    O.genotype_vcf(counts, vcf_lines)
+    return t1 - t0, time.perf_counter() - t1
+
+
+def cpu_arm(gaf_text, edges_text, gfa_text, vcf_text, n_rec, n_procs, per_proc, steps, warmup):
+    """Times `steps` steps of the CPU implementation on a bounded sample: n_procs processes x per_proc records
+    through the filter (+ JSON), then the genotyper over the whole VCF.  Returns the projection to the whole
+    batch: the filter grows with the records, its start-up and the genotyper do not."""
+    if reference_available():
+        run = ReferenceRun(gaf_text, edges_text, gfa_text, vcf_text, n_procs, per_proc)
+        try:
+            t0 = run.startup_seconds()
+            tf, tg = [], []
+            for i in range(warmup + steps):
+                a, b = run.step()
+                if i >= warmup:
+                    tf.append(a)
+                    tg.append(b)
+            n_sample = run.n_sample
+        finally:
+            run.close()
+        kind = "reference"
+        what = "unmodified filter-alignments.py + predict-genotype.py (baseline/_ref) as subprocesses"
+    else:
+        lines = first_lines(gaf_text, n_procs * per_proc).splitlines(True)
+        share = (len(lines) + n_procs - 1) // n_procs
+        shards = [lines[k * share:(k + 1) * share] for k in range(n_procs)]
+        alt = {}
+        for line in gfa_text.splitlines(True):
+            if line.startswith("S"):
+                c = line.split("\t")
+                if "." in c[1].split(":")[-1]:
+                    alt[c[1]] = len(line.rstrip().split("\t")[2])
+        edges = json.loads(edges_text)
+        vcf_lines = vcf_text.splitlines(True)
+        t0, tf, tg = 0.0, [], []
+        for i in range(warmup + steps):
+            a, b = port_step(shards, edges, alt, vcf_lines)
+            if i >= warmup:
+                tf.append(a)
+                tg.append(b)
+        n_sample = len(lines)
+        kind = "port"
+        what = "oracle/svjg_oracle.py in forked workers (baseline/_ref is not there)"
+    f = sum(tf) / len(tf)
+    gsec = sum(tg) / len(tg)
+    start = min(t0, f)
+    projected = start + (f - start) * n_rec / max(1, n_sample) + gsec
+    return {"value": n_rec / projected, "kind": kind, "what": what, "n_sample": n_sample, "filter_s": f, "startup_s": start,
+            "genotype_s": gsec, "step_s": f + gsec, "projected_s": projected}
 
 
 def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None, check=None):
     """The C restatement of the reference filter (oracle/svjg_oracle.c) on the host cores: filter only
     (no JSON text, no genotypes), one thread and all threads.  An extra line of context beside
-    cpu_baseline — the reference itself is single-threaded Python — never the thing measured.
-    ``check`` = (sv ids, counters [num_sv, 2], number of hits) of the GPU path for the same batch: the
-    whole batch is then compared counter by counter (key "parity")."""
+    cpu_baseline, never the thing measured.  ``check`` = (sv ids, counters [num_sv, 2], number of hits) of
+    the GPU path for the same batch: the whole batch is then compared counter by counter (key "parity")."""
     try:
         from oracle import c_oracle as CO
         CO.ensure_built()
@@ -186,13 +334,7 @@ def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None, check=None):
                     alt[c[1]] = len(line.rstrip().split("\t")[2])
         t = CO.Tables(json.loads(edges_text), alt)
         if n_sample:
-            pos = 0
-            for _ in range(n_sample):
-                j = gaf_text.find("\n", pos)
-                if j < 0:
-                    break
-                pos = j + 1
-            gaf_text = gaf_text[:pos]
+            gaf_text = first_lines(gaf_text, n_sample)
         gaf = gaf_text.encode()
         n_rec = gaf.count(b"\n")
         cores = min(32, os.cpu_count() or 1)
@@ -212,80 +354,35 @@ def cpu_baseline_c(gaf_text, edges_text, gfa_text, n_sample=None, check=None):
         return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
 
-_SHARD = {}
-
-
-def _ref_shard(k):
-    """One line shard through the oracle port (filter + json.dumps), in a forked worker."""
-    from oracle import svjg_oracle as O
-    t0 = time.perf_counter()
-    d = O.filter_alignments(_SHARD["lines"][k], _SHARD["edges"], _SHARD["alt"])
-    O.dumps_informative(d)
-    return O.hit_counts(d), time.perf_counter() - t0
-
-
 def run_reference(args):
-    """CPU arm: the oracle port on ALL host cores — one process per core over a
-    line-sharded sample (appends are in file order, so per-shard outputs
-    concatenate to the single-process result)."""
-    import multiprocessing as mp
-    from oracle import svjg_oracle as O
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """CPU arm of the driver: rank 0 alone, all host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     g, vcf, gaf, gfa_text, scale, gen_s = workload(args, 0)
     edges_text = g.edges_json()
-    vcf_lines = vcf.splitlines(True)
-    n_vcf = sum(1 for l in vcf_lines if not l.startswith("#"))
+    n_vcf = sum(1 for l in vcf.splitlines() if l and not l.startswith("#"))
     n_rec = gaf.count("\n")
     cores = max(1, os.cpu_count() or 1)
-    per_step = max(1000 * cores, (args.cpu_sample * cores) // max(1, args.steps))
-    per_step = min(per_step, n_rec)
-    lines, pos = [], 0
-    for _ in range(per_step):
-        j = gaf.find("\n", pos)
-        lines.append(gaf[pos:j + 1])
-        pos = j + 1
-    shard = (len(lines) + cores - 1) // cores
-    _SHARD["lines"] = [lines[i:i + shard] for i in range(0, len(lines), shard)]
-    _SHARD["edges"] = json.loads(edges_text)
-    _SHARD["alt"] = {k: len(v) for k, v in g.alt_nodes.items()}
-    n_shards = len(_SHARD["lines"])
-    tfs, tgs = [], []
-    with mp.get_context("fork").Pool(n_shards) as pool:
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            parts = pool.map(_ref_shard, range(n_shards), chunksize=1)
-            counts = {}
-            for c, _ in parts:
-                for k, (a, b) in c.items():
-                    x = counts.get(k, (0, 0))
-                    counts[k] = (x[0] + a, x[1] + b)
-            t1 = time.perf_counter()
-            O.genotype_vcf(counts, vcf_lines)
-            t2 = time.perf_counter()
-            if i >= args.warmup:
-                tfs.append(t1 - t0)
-                tgs.append(t2 - t1)
-    n = len(lines)
-    # whole-batch projection: the filter scales with records, the genotyper with SVs
-    proj_s = (sum(tfs) / len(tfs)) * n_rec / n + sum(tgs) / len(tgs)
-    val = n_rec / proj_s
+    per_proc = max(1000, min(args.cpu_sample, n_rec // cores))
+    r = cpu_arm(gaf, edges_text, gfa_text, vcf, n_rec, cores, per_proc, args.steps, args.warmup)
+    sample = (f"{r['n_sample']} records per step ({cores} processes x {per_proc}) through the filter ({r['filter_s']:.2f} s, of which "
+              f"start-up {r['startup_s']:.2f} s) projected to {n_rec} records, plus the genotyper over all {n_vcf} SVs once per step "
+              f"({r['genotype_s']:.2f} s, one process: it is quadratic in the SVs); {r['what']}")
     line = {
-        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000 * (sum(tfs) + sum(tgs)) / len(tfs), "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000 * r["step_s"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{args.workload} x{scale:g}: {n_rec} GAF records, {n_vcf} VCF SVs ({n} records timed per step)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_shards, "kind": "port",
-                         "sample": f"{n} records per step over {n_shards} processes (filter + json.dumps), projected to "
-                                   f"{n_rec} records, plus genotyping all {n_vcf} SVs once per step; oracle/svjg_oracle.py "
-                                   "(the reference itself is single-threaded)"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "cpu_baseline_c": cpu_baseline_c("".join(lines), edges_text, gfa_text),
+        "config": {"workload": f"{args.workload} x{scale:g}: {n_rec} GAF records, {n_vcf} VCF SVs ({r['n_sample']} records timed per step)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline_c": cpu_baseline_c(first_lines(gaf, r["n_sample"]), edges_text, gfa_text),
     }
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -295,7 +392,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from svjg import alnfilter, capi, genotype
+    from svjg import alnfilter, capi, genotype, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -306,26 +403,35 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    strong = args.scaling == "strong" and world > 1
 
     if args.scan_blocks:
         capi.check(capi.lib.svjg_filter_tune(capi.TUNE_SCAN_BLOCKS, args.scan_blocks))
     if args.tile_lines:
         capi.check(capi.lib.svjg_filter_tune(capi.TUNE_TILE_LINES, args.tile_lines))
-    g, vcf, gaf, gfa_text, scale, gen_s = workload(args, rank)
+    g, vcf, gaf, gfa_text, scale, gen_s = workload(args, 0 if strong else rank)
     edges_text = g.edges_json()
     tables = alnfilter.Tables.from_memory(edges_text, gfa_text).to_device(local)
-    gaf_bytes = gaf.encode()
+    gaf_all = gaf.encode()
+    whole, cuts = None, None
+    if strong:
+        # one batch, cut by bytes at line ends: rank r filters [cuts[r], cuts[r+1])
+        cuts = shard.shard_cuts(gaf_all, world)
+        whole = gaf_all
+        gaf_bytes = gaf_all[cuts[rank]:cuts[rank + 1]]
+    else:
+        gaf_bytes = gaf_all
     n_bytes = len(gaf_bytes)
     n_rec = gaf_bytes.count(b"\n")
     h_gaf = torch.frombuffer(bytearray(gaf_bytes), dtype=torch.uint8).pin_memory()
+    h_gaf_np = h_gaf.numpy()
     d_gaf = h_gaf.to(dev)
 
     # genotype inputs (host string work done once, untimed: it is per-catalogue, not per-read)
-    header, recs = genotype.parse_vcf(vcf.splitlines(True))
-    n_sv = len(recs)
-    sv_idx = np.array([capi.NO_SV if (r[2] is None or tables.find_sv(r[2]) is None) else tables.find_sv(r[2]) for r in recs],
-                      dtype=np.uint32)
-    sv_ty = np.array([r[1] for r in recs], dtype=np.uint8)
+    nvcf = genotype.NativeVcf.from_input(vcf.encode())
+    sv_idx = nvcf.index_tables(tables)
+    sv_ty = nvcf.svtype
+    n_sv = int(nvcf.n)
     lo, hi = (n_sv * rank) // world, (n_sv * (rank + 1)) // world      # SV shard of this rank
     n_loc = hi - lo
     d_idx = torch.from_numpy(sv_idx[lo:hi].view(np.int32).copy()).to(dev)
@@ -336,7 +442,6 @@ def main():
     d_gt = torch.empty(max(1, n_loc), dtype=torch.uint8, device=dev)
     d_ad = torch.empty((max(1, n_loc), 2), dtype=torch.int32, device=dev)
     d_fl = torch.empty(max(1, n_loc), dtype=torch.uint8, device=dev)
-    pl_all = torch.empty((world, max(1, (n_sv + world - 1) // world), 3), dtype=torch.int64, device=dev) if world > 1 else None
 
     # size the hit buffers from one untimed pass
     filt = alnfilter.DeviceFilter(tables, hit_cap=1024, device=local)
@@ -350,6 +455,44 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
     lib = capi.lib
+
+    def hit_digest(sv2, off, ln, base):
+        """order-free digest of a hit list (the kernels append in any order)"""
+        with np.errstate(over="ignore"):
+            x = (sv2.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ ((off.astype(np.uint64) + np.uint64(base)) * np.uint64(0xC2B2AE3D27D4EB4F)) \
+                ^ (ln.astype(np.uint64) * np.uint64(0x165667B19E3779F9))
+            return (int(np.bitwise_xor.reduce(x)), int(x.sum(dtype=np.uint64))) if x.size else (0, 0)
+
+    strong_check = None
+    if strong:
+        # the ranks' shards together must be the one-GPU result: counters summed, hit lists united
+        filt.reset()
+        filt.run(d_gaf)
+        mine = filt.result()
+        part = torch.from_numpy(mine.counts.view(np.int32).copy()).to(dev)
+        dist.all_reduce(part)
+        dx, ds = hit_digest(mine.hit_sv2, mine.hit_off, mine.hit_len, cuts[rank])
+        dig = torch.tensor([dx & 0x7FFFFFFFFFFFFFFF, dx >> 63, ds & 0x7FFFFFFFFFFFFFFF, ds >> 63, mine.n_hits], dtype=torch.int64, device=dev)
+        digs = [torch.zeros_like(dig) for _ in range(world)]
+        dist.all_gather(digs, dig)
+        if rank == 0:
+            d_whole = torch.frombuffer(bytearray(whole), dtype=torch.uint8).to(dev)
+            one = alnfilter.DeviceFilter(tables, hit_cap=sum(int(d[4]) for d in digs) + 1024, device=local)
+            one.reset()
+            one.run(d_whole)
+            ref = one.result()
+            wx, ws = hit_digest(ref.hit_sv2, ref.hit_off, ref.hit_len, 0)
+            gx = gs = 0
+            for d in digs:
+                gx ^= int(d[0]) | (int(d[1]) << 63)
+                gs = (gs + (int(d[2]) | (int(d[3]) << 63))) & 0xFFFFFFFFFFFFFFFF
+            same = bool((part.cpu().numpy().view(np.uint32) == ref.counts).all()) and (gx, gs) == (wx, ws) \
+                and sum(int(d[4]) for d in digs) == ref.n_hits
+            strong_check = {"ok": same, "checked": f"counters and the united hit list of {world} byte-range shards against one GPU over "
+                                                   f"the whole batch ({ref.n_hits} hits)"}
+            if not same:
+                raise SystemExit("strong scaling: the shards' results differ from the one-GPU result")
+            del d_whole, one
 
     xchg = None
     if world > 1 and args.collective == "p2p":
@@ -440,9 +583,9 @@ def main():
         total_ms, filt_ms, geno_ms, comm_ms = t.tolist()
         tot = torch.tensor([n_rec, n_bytes, n_hits], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
-        job_rec = int(tot[0])
+        job_rec, job_bytes, job_hits = (int(x) for x in tot)
     else:
-        job_rec = n_rec
+        job_rec, job_bytes, job_hits = n_rec, n_bytes, n_hits
     st = filt.read_stats()
     if xchg and xchg.timed_out():
         raise SystemExit(f"rank {rank}: a wait in the fused counter exchange timed out")
@@ -450,54 +593,53 @@ def main():
     # the dominant kernel on its own: the library records CUDA events around its scan kernel on this stream
     def timed_scan(n_iter):
         capi.check(lib.svjg_filter_profile(1))
-        tot, ms = 0.0, C.c_float()
+        tot_ms, ms = 0.0, C.c_float()
         for _ in range(n_iter):
             capi.check(lib.svjg_filter_reset(filt.counts.data_ptr(), tables.num_sv, filt.stats.data_ptr(), sp))
             capi.check(lib.svjg_filter_device(tables._h, d_gaf.data_ptr(), n_bytes, 0, 100, filt.counts.data_ptr(),
                                               filt.hit_sv2.data_ptr(), filt.hit_off.data_ptr(), filt.hit_len.data_ptr(),
                                               filt.hit_cap, filt.stats.data_ptr(), sp))
             capi.check(lib.svjg_filter_scan_ms(C.byref(ms)))
-            tot += ms.value
+            tot_ms += ms.value
         capi.check(lib.svjg_filter_profile(0))
-        return tot / n_iter
+        return tot_ms / n_iter
     timed_scan(2)
     scan_ms = timed_scan(max(3, min(K, 10)))
     if args.kernel_only:
         if rank == 0:
-            print(json.dumps({"kernel_ms": {"filter": filt_ms, "allreduce": comm_ms, "genotype": geno_ms},
-                              "scan_ms": scan_ms, "GBps": n_bytes / filt_ms / 1e6, "stats": st}))
+            print(json.dumps({"kernel_ms": {"filter": filt_ms, "allreduce": comm_ms, "genotype": geno_ms}, "scan_ms": scan_ms,
+                              "GBps": n_bytes / filt_ms / 1e6, "stats": st, "strong_check": strong_check}))
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- end to end through the C ABI with host buffers (copies inside the timed region)
+    # ---- end to end through the C ABI with host buffers: pinned GAF bytes in, JSON bytes + VCF bytes out
     Ke = args.e2e_steps or max(3, min(K, 20))
-    hit_cap = n_hits + 1024
-
-    host_out = alnfilter.HostBuffers(tables, hit_cap)     # pinned result arrays, allocated once like h_gaf
+    host_out = alnfilter.HostBuffers(tables, n_hits + 1024)     # pinned result arrays, allocated once like h_gaf
+    out_bytes = [0, 0]
 
     def e2e_step():
-        res = alnfilter.filter_host(tables, h_gaf, out=host_out)
-        dc = torch.from_numpy(res.counts.view(np.int32)).to(dev, non_blocking=True)
-        if world > 1:
-            dist.all_reduce(dc)
-        out = genotype.genotype_device(dc, d_idx, d_ty)           # the catalogue's index / type arrays stay on the device
-        return res, out
+        res = alnfilter.filter_host(tables, h_gaf, out=host_out)                       # H2D in chunks, kernels, hits + counters back
+        gt, fl, ad, pl = genotype.genotype_host(res.counts, sv_idx, sv_ty)              # counters up, kernel 4, genotypes back
+        text, n_gt = nvcf.format(gt, fl, ad, pl)                                       # genotype.vcf text (predict-genotype.py:248-275)
+        js = alnfilter.JsonText(tables, h_gaf_np, res)                                 # informative_aln.json text (:174-175)
+        out_bytes[0], out_bytes[1] = js.nbytes, len(text)
+        return res
 
     for _ in range(2):
-        res, out = e2e_step()
+        res = e2e_step()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        res, out = e2e_step()
+        res = e2e_step()
     sync_all()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    h2d = n_bytes + tables.num_sv * 8
-    d2h = tables.num_sv * 8 + 64 + res.n_hits * 16 + n_loc * (24 + 1 + 8 + 1)     # hits: u32 sv, u64 offset, u32 length
+    h2d = n_bytes + tables.num_sv * 8 + n_sv * 5
+    d2h = tables.num_sv * 8 + 64 + res.n_hits * 16 + n_sv * (24 + 1 + 8 + 1)     # hits: u32 sv, u64 offset, u32 length
 
     if rank != 0:
         if world > 1:
@@ -508,15 +650,26 @@ def main():
     algo_bytes = n_bytes + 16 * n_hits            # line bytes once + 12 B hit tuple + 4 B counter RMW
     achieved = algo_bytes / (filt_ms * 1e-3) / 1e9
     geno_bytes = 42 * n_loc
-    sample_n, tf, tg, n_gt = cpu_baseline(gaf, edges_text, gfa_text, vcf, args.cpu_sample)
+    if world == 1:
+        r = cpu_arm(gaf, edges_text, gfa_text, vcf, n_rec, 1, min(100_000, n_rec), 1, 0)
+        cpu_line = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+                    "sample": f"first {r['n_sample']} records of the batch through the filter ({r['filter_s']:.2f} s, of which start-up "
+                              f"{r['startup_s']:.2f} s) projected to {n_rec} records, plus the genotyper over all {n_sv} SVs "
+                              f"({r['genotype_s']:.2f} s); {r['what']}, one process like the reference"}
+        cpu_c = cpu_baseline_c(gaf, edges_text, gfa_text, check=(tables.sv_ids, res.counts, res.n_hits))
+    else:
+        cpu_line = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "timed at N=1 only"}
+        cpu_c = None
+    key = f"{args.workload}:{args.catalogue}"
     line = {
         "metric": METRIC, "value": job_rec * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-        "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload} x{scale:g} per GPU: {n_rec} GAF records ({n_bytes / 1e6:.1f} MB), "
+            "workload": f"{args.workload} x{scale:g}{' (catalogue at full size)' if args.catalogue == 'full' else ''} "
+                        f"{'cut by bytes over the GPUs' if strong else 'per GPU'}: {n_rec} GAF records ({n_bytes / 1e6:.1f} MB) on rank 0, "
                         f"{n_sv} VCF SVs, {tables.num_links} link keys, {tables.num_sv} sv keys",
-            "records_per_gpu": n_rec, "gaf_bytes_per_gpu": n_bytes, "hits_per_gpu": n_hits, "svs": n_sv,
+            "records_per_gpu": n_rec, "gaf_bytes_per_gpu": n_bytes, "hits_per_gpu": n_hits, "job_records": job_rec, "svs": n_sv,
             "multi_node_records": st["n_multi"], "l2": "input larger than L2 (no flush needed)" if n_bytes > 200e6
             else "input smaller than L2: resident re-reads possible",
             "tables_device_bytes": tables.device_bytes, "gen_seconds": round(gen_s, 1),
@@ -524,22 +677,24 @@ def main():
         "svs_genotyped_per_sec": n_sv / (geno_ms * 1e-3) if geno_ms > 0 else None,
         "kernel_ms": {"filter": filt_ms, "filter_scan_only": scan_ms, "allreduce": comm_ms, "genotype": geno_ms},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": FILTER_TRAFFIC.get(args.workload), "kernel": "filter chain: probe+scan+exact", "algorithmic_bytes_per_launch": algo_bytes,
+                     "traffic": load_traffic(key), "kernel": "filter chain: probe+scan+exact", "algorithmic_bytes_per_launch": algo_bytes,
                      "peak_source": peak_src,
                      "dominant_kernel": {"name": "scan_kernel", "ms": scan_ms, "share_of_chain": scan_ms / filt_ms,
-                                         "achieved": n_bytes / (scan_ms * 1e-3) / 1e9, "frac": n_bytes / (scan_ms * 1e-3) / 1e9 / peak,
-                                         "algorithmic_bytes_per_launch": n_bytes},
+                                         "achieved": algo_bytes / (scan_ms * 1e-3) / 1e9, "frac": algo_bytes / (scan_ms * 1e-3) / 1e9 / peak,
+                                         "algorithmic_bytes_per_launch": algo_bytes},
                      "genotype_kernel": {"achieved": geno_bytes / (geno_ms * 1e-3) / 1e9 if geno_ms > 0 else None,
                                          "bytes_per_launch": geno_bytes}},
-        "cpu_baseline": {"value": n_rec / (tf * n_rec / sample_n + tg), "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"first {sample_n} records of the batch (filter + json.dumps {tf:.2f}s) projected to "
-                                   f"{n_rec} records, plus genotyping all {n_sv} SVs ({tg:.2f}s); oracle/svjg_oracle.py, "
-                                   "single thread like the reference"},
-        "cpu_baseline_c": cpu_baseline_c(gaf, edges_text, gfa_text, check=(tables.sv_ids, res.counts, res.n_hits)),
-        "e2e": {"value": job_rec * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke},
+        "cpu_baseline": cpu_line,
+        "cpu_baseline_c": cpu_c,
+        "e2e": {"value": (n_rec * world if not strong else job_rec) * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke,
+                "json_bytes_per_step": out_bytes[0], "vcf_bytes_per_step": out_bytes[1],
+                "what": "svjg_filter_host (pinned GAF bytes in, hits + counters out) -> svjg_genotype_host -> genotype.vcf text "
+                        "(svjg_vcf_format) + informative_aln.json text (svjg_emit_informative_json_mem), all in host memory"
+                        + ("; one such job per GPU at once" if world > 1 else "")},
         "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
                        ("nccl all_reduce" if world > 1 else "none (one GPU)")),
+        "strong_check": strong_check,
         "gpu_launches": 5 * K,   # reset + probe + scan + exact + genotype
         "clocks": clocks,
     }

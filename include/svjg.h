@@ -155,6 +155,15 @@ int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64
                      uint32_t *hit_sv2, uint64_t *hit_off, uint32_t *hit_len, uint64_t hit_cap,
                      svjg_filter_stats *stats);
 
+/* The same, with `informative_aln.json` (filter-alignments.py:160-175) rendered ON THE DEVICE: the file stays
+ * resident in device memory while it is filtered, the hit tuples never leave the device; they are put into
+ * list order there (by sv id and allele, then file order, :166), the escaped text is assembled in device
+ * memory and crosses PCIe once, as text.  *json points into a page-locked buffer owned by `t`, valid until the
+ * next call with `t` or svjg_tables_free.  SVJG_E_UNSUPPORTED: the device renderer declines (a non-ASCII byte
+ * in a stored line, a list beyond 64 Ki entries) -- use svjg_filter_host + svjg_emit_informative_json. */
+int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                          svjg_filter_stats *stats, const char **json, uint64_t *json_len);
+
 /* ---- genotype (kernel 4) ----------------------------------------------------
  * Replaces likelihood() / allele_normalization() / encode_genotype()
  * (predict-genotype.py:281-346) and the gate at :216 for n SVs of a VCF.

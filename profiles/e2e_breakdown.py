@@ -1,0 +1,20 @@
+import sys, time, os
+sys.path.insert(0, "."); sys.path.insert(0, "svjedi-graph_b200")
+import numpy as np, torch, io
+from svjg import alnfilter, capi, genotype, synth
+import pickle
+g, vcf, gaf = pickle.load(open("/tmp/svjg_wl_C2_1_scaled_0.pkl","rb")) if os.path.exists("/tmp/svjg_wl_C2_1_scaled_0.pkl") else synth.make_workload("C2")
+buf = io.StringIO(); g.write_gfa(buf)
+tables = alnfilter.Tables.from_memory(g.edges_json(), buf.getvalue()).to_device(0)
+h = torch.frombuffer(bytearray(gaf.encode()), dtype=torch.uint8).pin_memory()
+hnp = h.numpy()
+nvcf = genotype.NativeVcf.from_input(vcf.encode()); idx = nvcf.index_tables(tables); ty = nvcf.svtype
+res = alnfilter.filter_host(tables, h)
+out = alnfilter.HostBuffers(tables, res.n_hits + 1024)
+for rep in range(3):
+    t0 = time.perf_counter(); res = alnfilter.filter_host(tables, h, out=out)
+    t1 = time.perf_counter(); gt, fl, ad, pl = genotype.genotype_host(res.counts, idx, ty)
+    t2 = time.perf_counter(); text, n = nvcf.format(gt, fl, ad, pl)
+    t3 = time.perf_counter(); js = alnfilter.JsonText(tables, hnp, res)
+    t4 = time.perf_counter()
+    print(f"filter_host {1e3*(t1-t0):.1f} ms  genotype_host {1e3*(t2-t1):.1f}  vcf format {1e3*(t3-t2):.1f}  json {1e3*(t4-t3):.1f}  ({js.nbytes} B)")

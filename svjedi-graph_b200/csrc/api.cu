@@ -39,6 +39,12 @@ struct HostWs {
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
     uint64_t *d_off64 = nullptr;              // absolute hit offsets (written by the kernels)
+    // svjg_filter_json_host: the whole file resident, the text it renders, and the page-locked copy the caller reads
+    uint8_t *d_all = nullptr;
+    uint64_t all_cap = 0;
+    char *h_json = nullptr;
+    uint64_t json_cap = 0;
+    uint64_t hits_per_gib = 0;                // what the last file needed: the first guess for the next one
 };
 
 void free_host_ws(svjg_tables *t) {
@@ -54,6 +60,8 @@ void free_host_ws(svjg_tables *t) {
     if (w->d_counts) cudaFree(w->d_counts);
     if (w->d_stats) cudaFree(w->d_stats);
     if (w->d_off64) cudaFree(w->d_off64);
+    if (w->d_all) cudaFree(w->d_all);
+    if (w->h_json) cudaFreeHost(w->h_json);
     if (w->s_copy) cudaStreamDestroy(w->s_copy);
     if (w->s_comp) cudaStreamDestroy(w->s_comp);
     delete w;
@@ -127,6 +135,7 @@ extern "C" void svjg_tables_free(svjg_tables *t) {
     if (t->device >= 0) {
         cudaSetDevice(t->device);
         free_host_ws(t);
+        free_json_keys(t);
         cudaFree(t->d_links);
         cudaFree(t->d_nodes);
         cudaFree(t->d_blob);
@@ -266,6 +275,139 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
         SVJG_CUDA(cudaMemcpyAsync(hit_len, w->d_hit[2], nh * 4, cudaMemcpyDeviceToHost, w->s_comp));
         SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
     }
+    return SVJG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer filter with the informative_aln.json text rendered on the device
+// ---------------------------------------------------------------------------
+static int ensure_ws(svjg_tables *t, uint32_t num_sv) {
+    if (t->ws) return SVJG_OK;
+    t->ws = new HostWs();
+    HostWs *w = t->ws;
+    SVJG_CUDA(cudaStreamCreateWithFlags(&w->s_copy, cudaStreamNonBlocking));
+    SVJG_CUDA(cudaStreamCreateWithFlags(&w->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SVJG_CUDA(cudaEventCreateWithFlags(&w->copied[i], cudaEventDisableTiming));
+        SVJG_CUDA(cudaEventCreateWithFlags(&w->freed[i], cudaEventDisableTiming));
+    }
+    SVJG_CUDA(cudaMalloc(&w->d_counts, std::max<size_t>(16, size_t(num_sv) * 8)));
+    SVJG_CUDA(cudaMalloc(&w->d_stats, sizeof(svjg_filter_stats)));
+    return SVJG_OK;
+}
+
+static int ensure_hit_arrays(HostWs *w, uint64_t hit_cap) {
+    if (w->hit_cap >= hit_cap) return SVJG_OK;
+    for (int i = 0; i < 3; ++i) {
+        if (w->d_hit[i]) SVJG_CUDA(cudaFree(w->d_hit[i]));
+        w->d_hit[i] = nullptr;
+    }
+    if (w->d_off64) SVJG_CUDA(cudaFree(w->d_off64));
+    w->d_off64 = nullptr;
+    w->hit_cap = 0;
+    for (int i = 0; i < 3; ++i) SVJG_CUDA(cudaMalloc(&w->d_hit[i], hit_cap * 4));
+    SVJG_CUDA(cudaMalloc(&w->d_off64, hit_cap * 8));
+    w->hit_cap = hit_cap;
+    return SVJG_OK;
+}
+
+extern "C" int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                                     svjg_filter_stats *stats, const char **json, uint64_t *json_len) {
+    if (!t || t->device < 0) return set_error(SVJG_E_ARG, "svjg_filter_json_host: tables are not on a device");
+    if (!counts || !stats || !json || !json_len || (n_bytes && !gaf)) return set_error(SVJG_E_ARG, "svjg_filter_json_host: NULL argument");
+    SVJG_CUDA(cudaSetDevice(t->device));
+    const uint32_t num_sv = uint32_t(t->sv_ids.size());
+    if (int rc = ensure_ws(t, num_sv)) return rc;
+    HostWs *w = t->ws;
+    // the file stays on the device until its text is rendered: one buffer, filled chunk by chunk (cut at line
+    // ends) while the chunks already there are filtered
+    if (w->all_cap < n_bytes + 64) {
+        if (w->d_all) SVJG_CUDA(cudaFree(w->d_all));
+        w->d_all = nullptr;
+        w->all_cap = 0;
+        const uint64_t cap = ((n_bytes + 64) + (1ull << 20)) & ~((1ull << 20) - 1);
+        SVJG_CUDA(cudaMalloc(&w->d_all, cap));
+        w->all_cap = cap;
+    }
+    std::vector<uint64_t> cut{0};
+    while (cut.back() < n_bytes) {
+        uint64_t b = cut.back(), e = std::min(n_bytes, b + HostWs::CHUNK);
+        if (e < n_bytes) {
+            const void *nl = memrchr(gaf + b, '\n', size_t(e - b));
+            if (nl) {
+                e = uint64_t(static_cast<const uint8_t *>(nl) - gaf) + 1;
+            } else {
+                const void *fw = memchr(gaf + e, '\n', size_t(n_bytes - e));
+                e = fw ? uint64_t(static_cast<const uint8_t *>(fw) - gaf) + 1 : n_bytes;
+            }
+        }
+        if (e - b >= 0xFFFF0000ull) return set_error(SVJG_E_ARG, "a single GAF line exceeds 4 GiB");
+        cut.push_back(e);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    uint64_t guess = w->hits_per_gib ? (w->hits_per_gib * ((n_bytes >> 30) + 1) * 5) / 4 : n_bytes / 96;
+    if (int rc = ensure_hit_arrays(w, std::max<uint64_t>(guess, 1u << 16))) return rc;
+
+    cudaEvent_t up_done = w->copied[0];
+    for (int attempt = 0;; ++attempt) {
+        int rc = svjg_filter_reset(w->d_counts, num_sv, w->d_stats, w->s_comp);
+        if (rc) return rc;
+        for (size_t k = 0; k < n_chunks; ++k) {
+            const uint64_t len = cut[k + 1] - cut[k];
+            if (attempt == 0) {
+                SVJG_CUDA(cudaMemcpyAsync(w->d_all + cut[k], gaf + cut[k], len, cudaMemcpyHostToDevice, w->s_copy));
+                SVJG_CUDA(cudaEventRecord(up_done, w->s_copy));
+                SVJG_CUDA(cudaStreamWaitEvent(w->s_comp, up_done, 0));
+            }
+            rc = filter_device_abs(t, w->d_all + cut[k], len, cut[k], d_over, w->d_counts, w->d_hit[0], nullptr, w->d_off64, w->d_hit[2],
+                                   w->hit_cap, w->d_stats, w->s_comp, true);
+            if (rc) {
+                cudaStreamSynchronize(w->s_copy);
+                cudaStreamSynchronize(w->s_comp);
+                return rc;
+            }
+        }
+        SVJG_CUDA(cudaMemcpyAsync(stats, w->d_stats, sizeof(svjg_filter_stats), cudaMemcpyDeviceToHost, w->s_comp));
+        SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
+        if (n_bytes == 0) memset(stats, 0, sizeof *stats), stats->err_offset = ~0ull;
+        if (stats->status) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "GAF line at byte %llu: the reference raises here (reason %llu)",
+                     (unsigned long long)stats->err_offset, (unsigned long long)stats->status);
+            return set_error(SVJG_E_INPUT, msg);
+        }
+        if (stats->n_hits <= w->hit_cap) break;
+        // more hits than there was room for: the file is resident, only the kernels run again
+        if (attempt) return set_error(SVJG_E_HITS_OVERFLOW, "hit buffers too small");
+        if (int rc2 = ensure_hit_arrays(w, stats->n_hits + 1024)) return rc2;
+    }
+    w->hits_per_gib = stats->n_hits / ((n_bytes >> 30) + 1);
+    SVJG_CUDA(cudaMemcpyAsync(counts, w->d_counts, size_t(num_sv) * 8, cudaMemcpyDeviceToHost, w->s_comp));
+    uint8_t *d_text = nullptr;
+    uint64_t len = 0;
+    int rc = json_render_device(t, w->d_all, w->d_hit[0], w->d_off64, w->d_hit[2], stats->n_hits, w->d_counts, &d_text, &len, w->s_comp);
+    if (rc) {
+        cudaStreamSynchronize(w->s_comp);
+        return rc;
+    }
+    if (w->json_cap < len) {
+        if (w->h_json) cudaFreeHost(w->h_json);
+        w->h_json = nullptr;
+        w->json_cap = 0;
+        const uint64_t cap = (len + len / 8 + (1ull << 20)) & ~((1ull << 20) - 1);
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&w->h_json), cap, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(d_text, w->s_comp);
+            cudaStreamSynchronize(w->s_comp);
+            return cuda_fail(int(e), "page-locked buffer for the JSON text");
+        }
+        w->json_cap = cap;
+    }
+    SVJG_CUDA(cudaMemcpyAsync(w->h_json, d_text, len, cudaMemcpyDeviceToHost, w->s_comp));
+    SVJG_CUDA(cudaFreeAsync(d_text, w->s_comp));
+    SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
+    *json = w->h_json;
+    *json_len = len;
     return SVJG_OK;
 }
 

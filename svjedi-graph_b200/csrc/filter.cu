@@ -113,6 +113,7 @@ struct FilterArgs {
     uint32_t flags;
     uint32_t one;                // 1 (see IsNewline)
     Scratch sc;
+    uint32_t skip;               // bytes at the head of the shard that belong to the line in front of it (svjg_filter_json_host)
     uint32_t tile_max;           // most bytes per tile (the scan kernel's geometry)
     uint32_t tile_lines;         // lines a tile should hold (probe_kernel): about one per lane
 };
@@ -1147,7 +1148,7 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
         }
         if (bulk != nbytes || dst0 || valid_end < win_bytes) {                       // the first and the last tiles of the shard
             for (uint32_t i = bulk + lane; i < nbytes; i += 32) win[dst0 + i] = __ldg(a.gaf + g0 + i);
-            if (dst0) win[lane] = lane == HEAD - 1 ? '\n' : 0;           // "newline" in front of byte 0 of the file
+            if (dst0) win[lane] = (lane == HEAD - 1 && a.skip == 0u) ? '\n' : 0;   // "newline" in front of byte 0 of the file
             for (uint32_t i = valid_end + lane; i < win_bytes; i += 32) win[i] = 0;
         }
         if (bulk) {
@@ -1658,8 +1659,18 @@ extern "C" int svjg_filter_scan_ms(float *ms) {
 // d_hit_off64 != NULL: absolute 64-bit offsets (base_offset + offset) instead of d_hit_off (svjg_filter_host)
 int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset, int64_t d_over,
                             uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off, uint64_t *d_hit_off64,
-                            uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream) {
+                            uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream, bool inside_buffer) {
     if (!t || t->device < 0) return set_error(SVJG_E_ARG, "svjg_filter_device: tables are not on a device");
+    // a shard that starts right behind a line end somewhere inside a larger device buffer: the kernels start at the
+    // 16-byte boundary in front of it and see the tail of that line first, which is nobody's line
+    uint32_t skip = 0;
+    if (inside_buffer) {
+        skip = uint32_t(reinterpret_cast<uintptr_t>(d_gaf) & 15);
+        if (base_offset < skip) return set_error(SVJG_E_ARG, "svjg_filter_device: shard inside a buffer without the bytes in front of it");
+        d_gaf -= skip;
+        n_bytes += n_bytes ? skip : 0;
+        base_offset -= skip;
+    }
     if (!d_counts || !d_stats || (n_bytes && !d_gaf)) return set_error(SVJG_E_ARG, "svjg_filter_device: NULL argument");
     if (hit_cap && (!d_hit_sv2 || (!d_hit_off && !d_hit_off64) || !d_hit_len))
         return set_error(SVJG_E_ARG, "svjg_filter_device: NULL hit buffer");
@@ -1684,6 +1695,7 @@ int svjg::filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t
     a.stats = reinterpret_cast<unsigned long long *>(d_stats);
     a.flags = t->filter_flags;
     a.one = 1;
+    a.skip = skip;
     a.tile_max = cfg->tile_max;
     a.tile_lines = cfg->tile_lines;
     if (g_knobs.scan_only) a.flags |= FLAG_STOP_AFTER_SCAN;

@@ -1,5 +1,7 @@
 // Internal declarations shared by the translation units of libsvjg.so.
 #pragma once
+#include <cuda_runtime.h>
+
 #include <string>
 #include <vector>
 
@@ -8,6 +10,7 @@
 
 namespace svjg {
 struct HostWs;
+struct JsonKeys;
 }
 
 struct svjg_tables {
@@ -25,16 +28,23 @@ struct svjg_tables {
     svjg::DevTables dev{};
     // lazily created workspace of svjg_filter_host
     svjg::HostWs *ws = nullptr;
+    // lazily created device copy of the sv ids as JSON strings (json.cu)
+    svjg::JsonKeys *json_keys = nullptr;
 };
 
 namespace svjg {
 int set_error(int code, const std::string &msg);
 int cuda_fail(int cuda_err, const char *what);   // records the message, returns SVJG_E_CUDA
 void free_host_ws(svjg_tables *t);
+void free_json_keys(svjg_tables *t);
+// informative_aln.json rendered on the device from hits in device memory (json.cu); *d_out is released with cudaFreeAsync
+int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
+                       const uint32_t *d_hit_len, uint64_t n_hits, const uint32_t *d_counts, uint8_t **d_out, uint64_t *out_len,
+                       cudaStream_t st);
 // svjg_filter_device with absolute 64-bit hit offsets (d_hit_off64 != NULL); filter.cu
 int filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset, int64_t d_over,
                       uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off, uint64_t *d_hit_off64, uint32_t *d_hit_len,
-                      uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream);
+                      uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream, bool inside_buffer = false);
 }  // namespace svjg
 
 #define SVJG_CUDA(call)                                                        \

@@ -207,6 +207,31 @@ def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None, out=No
     return FilterResult(counts, st)
 
 
+def filter_json_host(tables, gaf, d_over=D_OVER, counts=None):
+    """svjg_filter_json_host: the filter over GAF bytes in HOST memory with ``informative_aln.json``
+    (filter-alignments.py:160-175) rendered on the device.  Returns (FilterResult without a hit list, memoryview
+    of the JSON text: it lives in a buffer of ``tables`` and is valid until the next call), or None in place
+    of the text when the device renderer declines (non-ASCII bytes in a stored line, a list beyond 64 Ki
+    entries): the caller then runs filter_host + write_informative_json."""
+    if tables.device is None:
+        raise RuntimeError("tables.to_device() first")
+    a = _as_u8(gaf)
+    n = int(a.size)
+    counts = counts if counts is not None else np.zeros((tables.num_sv, 2), dtype=np.uint32)
+    stats = capi.FilterStats()
+    p, ln = C.c_void_p(), C.c_uint64()
+    rc = capi.lib.svjg_filter_json_host(tables._h, a.ctypes.data if n else None, n, int(d_over), counts.ctypes.data,
+                                        C.byref(stats), C.byref(p), C.byref(ln))
+    st = stats.as_dict()
+    if rc == capi.E_INPUT:
+        _raise_input(st)
+    if rc == capi.E_UNSUPPORTED:
+        return FilterResult(counts, st), None
+    capi.check(rc)
+    text = memoryview((C.c_char * ln.value).from_address(p.value)) if ln.value else memoryview(b"")
+    return FilterResult(counts, st), text
+
+
 def filter_stream(tables, fileobj, chunk_bytes=64 << 20, d_over=D_OVER):
     """the filter fed from a pipe (``minigraph ... | filter-alignments.py -a
     /dev/stdin``) while the mapper is still writing.  The stream is cut into segments of whole lines of
@@ -346,6 +371,33 @@ def write_informative_json(tables, gaf, result, out_path):
     capi.check(capi.lib.svjg_emit_informative_json(
         tables._h, a.ctypes.data if a.size else None, int(a.size), sv2.ctypes.data if nh else None,
         off.ctypes.data if nh else None, ln.ctypes.data if nh else None, nh, os.fsencode(out_path)))
+
+
+class JsonText:
+    """``informative_aln.json`` in memory (svjg_emit_informative_json_mem): ``.view`` is a memoryview of the
+    text, valid until the object goes away."""
+
+    def __init__(self, tables, gaf, result):
+        a = _as_u8(gaf)
+        nh = int(result.hit_sv2.size)
+        sv2 = np.ascontiguousarray(result.hit_sv2, dtype=np.uint32)
+        off = np.ascontiguousarray(result.hit_off, dtype=np.uint64)
+        ln = np.ascontiguousarray(result.hit_len, dtype=np.uint32)
+        self._p, n = C.c_void_p(), C.c_uint64()
+        capi.check(capi.lib.svjg_emit_informative_json_mem(
+            tables._h, a.ctypes.data if a.size else None, int(a.size), sv2.ctypes.data if nh else None,
+            off.ctypes.data if nh else None, ln.ctypes.data if nh else None, nh, C.byref(self._p), C.byref(n)))
+        self.nbytes = int(n.value)
+        self.view = memoryview((C.c_char * self.nbytes).from_address(self._p.value)) if self.nbytes else memoryview(b"")
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.view = None
+                capi.lib.svjg_buffer_free(self._p)
+                self._p = None
+        except Exception:
+            pass
 
 
 class PinnedBytes:

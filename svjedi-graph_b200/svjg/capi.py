@@ -69,6 +69,8 @@ def _load():
                                          C.c_uint64, vp, vp]),
         "svjg_filter_host": (C.c_int, [vp, u8p, C.c_uint64, C.c_int64, u32p, u32p, u64p, u32p, C.c_uint64,
                                        C.POINTER(FilterStats)]),
+        "svjg_filter_json_host": (C.c_int, [vp, u8p, C.c_uint64, C.c_int64, u32p, C.POINTER(FilterStats), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_uint64)]),
         "svjg_filter_tune": (C.c_int, [C.c_int, C.c_int]),
         "svjg_filter_profile": (C.c_int, [C.c_int]),
         "svjg_filter_scan_ms": (C.c_int, [C.POINTER(C.c_float)]),
