@@ -18,6 +18,7 @@ the genotype kernel over NVLink peer memory, or ncclAllReduce) -> genotype kerne
 """
 import argparse
 import ctypes as C
+import io
 import json
 import math
 import os
@@ -86,7 +87,6 @@ def workload(args, stream):
             os.replace(cache + f".{os.getpid()}", cache)
         except Exception:
             pass
-    import io
     buf = io.StringIO()
     g.write_gfa(buf)
     return g, vcf, gaf, buf.getvalue(), scale, time.time() - t0
@@ -619,11 +619,13 @@ def main():
     out_bytes = [0, 0]
 
     def e2e_step():
-        res = alnfilter.filter_host(tables, h_gaf, out=host_out)                       # H2D in chunks, kernels, hits + counters back
+        # H2D in chunks, kernels, informative_aln.json assembled on the device (:160-175), text + counters back
+        res, js = alnfilter.filter_json_host(tables, h_gaf, counts=host_out.counts)
+        if js is None:
+            raise SystemExit("the device JSON renderer declined the synthetic batch")
         gt, fl, ad, pl = genotype.genotype_host(res.counts, sv_idx, sv_ty)              # counters up, kernel 4, genotypes back
-        text, n_gt = nvcf.format(gt, fl, ad, pl)                                       # genotype.vcf text (predict-genotype.py:248-275)
-        js = alnfilter.JsonText(tables, h_gaf_np, res)                                 # informative_aln.json text (:174-175)
-        out_bytes[0], out_bytes[1] = js.nbytes, len(text)
+        vt, n_gt = nvcf.format_buffer(gt, fl, ad, pl)                                   # genotype.vcf text (predict-genotype.py:248-275)
+        out_bytes[0], out_bytes[1] = len(js), vt.nbytes
         return res
 
     for _ in range(2):
@@ -639,7 +641,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     h2d = n_bytes + tables.num_sv * 8 + n_sv * 5
-    d2h = tables.num_sv * 8 + 64 + res.n_hits * 16 + n_sv * (24 + 1 + 8 + 1)     # hits: u32 sv, u64 offset, u32 length
+    d2h = tables.num_sv * 8 + 64 + out_bytes[0] + n_sv * (24 + 1 + 8 + 1)        # counters, stats, the JSON text, genotypes
 
     if rank != 0:
         if world > 1:
@@ -689,8 +691,8 @@ def main():
         "e2e": {"value": (n_rec * world if not strong else job_rec) * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke,
                 "json_bytes_per_step": out_bytes[0], "vcf_bytes_per_step": out_bytes[1],
-                "what": "svjg_filter_host (pinned GAF bytes in, hits + counters out) -> svjg_genotype_host -> genotype.vcf text "
-                        "(svjg_vcf_format) + informative_aln.json text (svjg_emit_informative_json_mem), all in host memory"
+                "what": "svjg_filter_json_host (pinned GAF bytes in; informative_aln.json text rendered on the device + counters out) "
+                        "-> svjg_genotype_host -> genotype.vcf text (svjg_vcf_format), all in host memory"
                         + ("; one such job per GPU at once" if world > 1 else "")},
         "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
                        ("nccl all_reduce" if world > 1 else "none (one GPU)")),

@@ -1,3 +1,4 @@
+"""Where an end-to-end step spends its time (page-locked GAF bytes in, JSON + VCF text out): python profiles/e2e_breakdown.py"""
 import sys, time, os
 sys.path.insert(0, "."); sys.path.insert(0, "svjedi-graph_b200")
 import numpy as np, torch, io
@@ -16,5 +17,9 @@ for rep in range(3):
     t1 = time.perf_counter(); gt, fl, ad, pl = genotype.genotype_host(res.counts, idx, ty)
     t2 = time.perf_counter(); text, n = nvcf.format(gt, fl, ad, pl)
     t3 = time.perf_counter(); js = alnfilter.JsonText(tables, hnp, res)
-    t4 = time.perf_counter()
-    print(f"filter_host {1e3*(t1-t0):.1f} ms  genotype_host {1e3*(t2-t1):.1f}  vcf format {1e3*(t3-t2):.1f}  json {1e3*(t4-t3):.1f}  ({js.nbytes} B)")
+    t4 = time.perf_counter(); r2, text = alnfilter.filter_json_host(tables, h)
+    t5 = time.perf_counter()
+    sink = io.BytesIO(); nvcf.format(gt, fl, ad, pl, out=sink)
+    t6 = time.perf_counter()
+    print(f"filter_host {1e3*(t1-t0):.1f} ms  genotype_host {1e3*(t2-t1):.1f}  vcf format {1e3*(t3-t2):.1f}  host json {1e3*(t4-t3):.1f}  ({js.nbytes} B) | "
+          f"filter + device json {1e3*(t5-t4):.1f} ms ({len(text)} B)  vcf format to sink {1e3*(t6-t5):.1f}")

@@ -11,6 +11,7 @@
 #include <string>
 #include <string_view>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "../../include/svjg.h"
@@ -358,21 +359,15 @@ extern "C" int svjg_vcf_format(const svjg_vcf *v, const uint8_t *gt, const uint8
         if (h.len == UINT32_MAX) cap += sizeof FORMAT_LINES;
     char *buf = (char *)malloc(cap);
     if (!buf) return set_error(SVJG_E_NOMEM, "svjg_vcf_format: out of memory");
-    char *o = buf;
     const char *text = v->text.data();
-    size_t hi = 0;
-    uint64_t genotyped = 0;
-    auto put_hdr = [&](const Hdr &h) {
-        o = h.len == UINT32_MAX ? put_mem(o, FORMAT_LINES, sizeof FORMAT_LINES - 1) : put_mem(o, text + h.off, h.len);
+    auto put_hdr = [&](char *o, const Hdr &h) {
+        return h.len == UINT32_MAX ? put_mem(o, FORMAT_LINES, sizeof FORMAT_LINES - 1) : put_mem(o, text + h.off, h.len);
     };
-    for (size_t i = 0; i < n; ++i) {
-        while (hi < v->hdrs.size() && v->hdrs[hi].before <= i) put_hdr(v->hdrs[hi++]);
-        const Rec &r = v->recs[i];
-        o = put_mem(o, text + r.head_off, r.head_len);
+    // the sample column of record i (at most 150 bytes)
+    auto put_sample = [&](char *o, size_t i) {
         o = put_mem(o, "\tGT:DP:AD:PL\t", 13);
         const uint8_t f = flags[i];
         if (f & SVJG_GT_GENOTYPED) {
-            ++genotyped;
             const uint64_t t1 = ad2[2 * i], t2 = ad2[2 * i + 1];
             const bool h0 = f & SVJG_GT_HALVED_0, h1 = f & SVJG_GT_HALVED_1;
             o = put_mem(o, GT_TEXT[gt[i]], 3);
@@ -392,8 +387,69 @@ extern "C" int svjg_vcf_format(const svjg_vcf *v, const uint8_t *gt, const uint8
             o = put_mem(o, "./.:0:0,0:.,.,.", 15);
         }
         *o++ = '\n';
+        return o;
+    };
+    // where every record starts: its head is copied as it is, the sample column is rendered once to learn
+    // its length (cheap next to the copies); then the records are filled in by several threads
+    std::vector<uint64_t> at(n + 1, 0);
+    uint64_t genotyped = 0;
+    {
+        char tmp[192];
+        size_t hi = 0;
+        uint64_t pos = 0;
+        for (size_t i = 0; i < n; ++i) {
+            while (hi < v->hdrs.size() && v->hdrs[hi].before <= i) {
+                const Hdr &h = v->hdrs[hi++];
+                pos += h.len == UINT32_MAX ? sizeof FORMAT_LINES - 1 : h.len;
+            }
+            at[i] = pos;
+            genotyped += (flags[i] & SVJG_GT_GENOTYPED) != 0;
+            pos += v->recs[i].head_len + uint64_t(put_sample(tmp, i) - tmp);
+        }
+        at[n] = pos;
     }
-    while (hi < v->hdrs.size()) put_hdr(v->hdrs[hi++]);
+    auto fill = [&](size_t lo, size_t hi_rec) {
+        size_t hi = 0;
+        while (hi < v->hdrs.size() && v->hdrs[hi].before < lo) ++hi;          // header lines in front of record lo: not ours
+        // (those with before == lo sit right in front of record lo: ours, they end where it starts)
+        for (size_t i = lo; i < hi_rec; ++i) {
+            uint64_t back = 0;
+            size_t h2 = hi;
+            while (h2 < v->hdrs.size() && v->hdrs[h2].before <= i) {
+                back += v->hdrs[h2].len == UINT32_MAX ? sizeof FORMAT_LINES - 1 : v->hdrs[h2].len;
+                ++h2;
+            }
+            char *o = buf + at[i] - back;
+            while (hi < h2) o = put_hdr(o, v->hdrs[hi++]);
+            const Rec &r = v->recs[i];
+            o = put_mem(o, text + r.head_off, r.head_len);
+            put_sample(o, i);
+        }
+    };
+    const uint64_t body = at[n];
+    unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (body < (4u << 20) || n < 64) n_thr = 1;
+    if (n_thr == 1) {
+        fill(0, n);
+    } else {
+        // ranges of about equal bytes
+        std::vector<size_t> cutv(n_thr + 1, 0);
+        for (unsigned p = 1; p < n_thr; ++p)
+            cutv[p] = size_t(std::lower_bound(at.begin(), at.begin() + n, body * p / n_thr) - at.begin());
+        cutv[n_thr] = n;
+        for (unsigned p = 1; p <= n_thr; ++p) cutv[p] = std::max(cutv[p], cutv[p - 1]);
+        std::vector<std::thread> pool;
+        for (unsigned p = 1; p < n_thr; ++p) pool.emplace_back(fill, cutv[p], cutv[p + 1]);
+        fill(cutv[0], cutv[1]);
+        for (auto &th : pool) th.join();
+    }
+    // header lines behind the last record
+    char *o = buf + at[n];
+    {
+        size_t hi = 0;
+        while (hi < v->hdrs.size() && (n == 0 ? false : v->hdrs[hi].before <= n - 1)) ++hi;
+        while (hi < v->hdrs.size()) o = put_hdr(o, v->hdrs[hi++]);
+    }
     *out = buf;
     *out_len = uint64_t(o - buf);
     if (n_genotyped) *n_genotyped = genotyped;

@@ -62,13 +62,22 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
             gaf = alnfilter.read_file_pinned(gaf_file)
             if alnfilter.translate_newlines(gaf) is not gaf:               # carriage returns: text-mode line ends
                 gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
+    text = None
     if stream is not None:
         res, gaf = alnfilter.filter_stream(tables, stream)
     else:
-        res = alnfilter.filter_host(tables, gaf)
+        # the text of informative_aln.json is assembled on the device and comes back as text; the host emitter
+        # takes over where the device renderer declines (non-ASCII bytes in a stored line, a giant list)
+        res, text = alnfilter.filter_json_host(tables, gaf)
+        if text is None:
+            res = alnfilter.filter_host(tables, gaf)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
-    alnfilter.write_informative_json(tables, gaf, res, out_json)
+    if text is not None:
+        with open(out_json, "wb") as fh:
+            fh.write(text)
+    else:
+        alnfilter.write_informative_json(tables, gaf, res, out_json)
     return res, gaf
 
 

@@ -118,6 +118,23 @@ def parse_vcf(lines):
     return header, recs
 
 
+class VcfText:
+    """genotype.vcf text in a buffer of the library (svjg_vcf_format); ``.view`` until the object goes away."""
+
+    def __init__(self, ptr, nbytes):
+        self._p, self.nbytes = ptr, nbytes
+        self.view = memoryview((C.c_char * nbytes).from_address(ptr.value)) if nbytes else memoryview(b"")
+
+    def __del__(self):
+        try:
+            if self._p:
+                self.view = None
+                capi.lib.svjg_buffer_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
 class NativeVcf:
     """svjg_vcf_* (csrc/vcf.cpp): the keys, svtype codes and output text of a whole VCF without a
     Python-level loop over its records.  :func:`parse_vcf` / :func:`format_vcf` state the same rules
@@ -212,6 +229,19 @@ class NativeVcf:
         finally:
             capi.lib.svjg_buffer_free(buf)
         return text, int(n_gt.value)
+
+    def format_buffer(self, gt, flags, ad2, pl):
+        """(VcfText, number of genotyped SVs): the text where the library put it, without a Python copy."""
+        gt = np.ascontiguousarray(gt, dtype=np.uint8)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        ad2 = np.ascontiguousarray(ad2, dtype=np.uint32)
+        pl = np.ascontiguousarray(pl, dtype=np.int64)
+        if not (len(gt) == len(flags) == len(ad2) == len(pl) == self.n):
+            raise ValueError("result arrays do not match the number of VCF records")
+        buf, n_out, n_gt = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        capi.check(capi.lib.svjg_vcf_format(self._h, gt.ctypes.data, flags.ctypes.data, ad2.ctypes.data, pl.ctypes.data,
+                                            C.byref(buf), C.byref(n_out), C.byref(n_gt)))
+        return VcfText(buf, int(n_out.value)), int(n_gt.value)
 
     def close(self):
         if self._h:

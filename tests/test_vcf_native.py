@@ -140,6 +140,33 @@ def test_native_and_python_statements_agree():
             assert v.format(gt, fl, ad, pl) == genotype.format_vcf(header, recs, gt, fl, ad, pl), body
 
 
+def test_big_vcf_text_filled_by_several_threads():
+    """svjg_vcf_format fills texts of more than 4 MB with several threads (record ranges of equal bytes): the
+    same bytes as the line-by-line statement, header lines between and behind the records included."""
+    rng = np.random.default_rng(11)
+    parts = ["##fileformat=VCFv4.2\n##FORMAT=<ID=XX>\n#CHROM\tPOS\n"]
+    for i in range(6000):
+        if i in (1, 2500, 5999):
+            parts.append(f"##odd header in front of record {i}\n")
+        if i % 3 == 0:
+            parts.append(f"chr{i % 7}\t{1000 + i}\tv{i}\tN\t{'ACGT' * int(rng.integers(200, 1200))}\t.\t.\tSVTYPE=INS;END={1001 + i}\n")
+        else:
+            parts.append(f"chr{i % 7}\t{1000 + i}\tv{i}\tN\t<DEL>\t.\t.\tSVTYPE=DEL;END={1100 + i};NOTE={'x' * int(rng.integers(0, 300))}\n")
+    parts.append("##behind the last record\n##and one more\n")
+    text = "".join(parts)
+    assert len(text) > (5 << 20)
+    lines = genotype._as_lines(text.encode())
+    header, recs = genotype.parse_vcf(lines)
+    v = genotype.NativeVcf.from_input(text.encode())
+    n = v.n
+    assert n == 6000 == len(recs)
+    gt = rng.integers(0, 4, n).astype(np.uint8)
+    fl = rng.integers(0, 8, n).astype(np.uint8)
+    ad = rng.integers(0, 5000, (n, 2)).astype(np.uint32)
+    pl = rng.integers(-10, 10**15, (n, 3)).astype(np.int64)
+    assert v.format(gt, fl, ad, pl) == genotype.format_vcf(header, recs, gt, fl, ad, pl)
+
+
 def test_declined_spellings_fall_to_the_python_statement():
     head = "#CHROM\n"
     assert genotype.NativeVcf.from_input((head + "é\t7\ta\tN\t<DEL>\t.\t.\tSVTYPE=DEL;END=99\n").encode()) is None
