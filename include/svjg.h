@@ -88,6 +88,8 @@ uint32_t svjg_tables_find_sv(const svjg_tables *t, const char *sv_id, uint32_t l
 #define SVJG_FLAG_EXACT_CHECKS 1u
 #define SVJG_FLAG_FORCE_GENERAL 2u
 int svjg_tables_set_flags(svjg_tables *t, uint32_t flags);
+/* a second handle with the same host image and no device image: several GPUs of a node get one handle each */
+int svjg_tables_clone(const svjg_tables *t, svjg_tables **out);
 /* copies the device image to `device` (cudaMalloc inside; freed by svjg_tables_free) */
 int svjg_tables_to_device(svjg_tables *t, int device);
 

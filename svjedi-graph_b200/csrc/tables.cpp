@@ -1060,6 +1060,25 @@ extern "C" int svjg_tables_load(const char *svs_edges_json_path, const char *gfa
     return svjg_tables_from_memory(edges.data(), edges.size(), gfa.data(), gfa.size(), out);
 }
 
+// a second handle with the same host image and no device image: one handle per GPU of a node
+extern "C" int svjg_tables_clone(const svjg_tables *t, svjg_tables **out) {
+    if (!t || !out) return set_error(SVJG_E_ARG, "svjg_tables_clone: NULL argument");
+    svjg_tables *c = new svjg_tables();
+    c->sv_ids = t->sv_ids;
+    c->links = t->links;
+    c->nodes = t->nodes;
+    c->pnodes = t->pnodes;
+    c->blob = t->blob;
+    c->entries = t->entries;
+    c->n_keys = t->n_keys;
+    c->n_link_slots = t->n_link_slots;
+    c->n_alt = t->n_alt;
+    c->n_nodes = t->n_nodes;
+    c->filter_flags = t->filter_flags;
+    *out = c;
+    return SVJG_OK;
+}
+
 extern "C" int svjg_tables_set_flags(svjg_tables *t, uint32_t flags) {
     if (!t) return set_error(SVJG_E_ARG, "svjg_tables_set_flags: NULL tables");
     t->filter_flags |= flags & (SVJG_FLAG_EXACT_CHECKS | SVJG_FLAG_FORCE_GENERAL);

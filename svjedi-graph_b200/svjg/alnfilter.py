@@ -47,6 +47,12 @@ class Tables:
         self.device = int(device)
         return self
 
+    def clone(self):
+        """A second handle with the same host image and no device image (one handle per GPU)."""
+        h = C.c_void_p()
+        capi.check(capi.lib.svjg_tables_clone(self._h, C.byref(h)))
+        return Tables(h.value)
+
     def set_flags(self, flags):
         capi.check(capi.lib.svjg_tables_set_flags(self._h, int(flags)))
         return self
@@ -139,9 +145,11 @@ def translate_newlines(buf):
     return np.frombuffer(a.tobytes().replace(b"\r\n", b"\n").replace(b"\r", b"\n"), dtype=np.uint8)
 
 
-def _raise_input(stats):
+def _raise_input(stats, base=0):
     reason = capi.BAD_REASONS.get(stats["status"], "malformed input")
-    raise InputError(f"GAF line at byte {stats['err_offset']}: {reason} (the reference raises here)")
+    err = InputError(f"GAF line at byte {stats['err_offset'] + base}: {reason} (the reference raises here)")
+    err.stats = dict(stats)
+    raise err
 
 
 class HostBuffers:
@@ -205,6 +213,41 @@ def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None, out=No
     if hit_cap:
         return FilterResult(counts, st, sv2[:nh], off[:nh], ln[:nh])
     return FilterResult(counts, st)
+
+
+def filter_host_multi(tables_by_device, gaf, d_over=D_OVER):
+    """The per-line loop over ONE buffer on several GPUs of the node (the stage boundary svjedi-graph.py:113-118
+    with the records sharded): the buffer is cut by bytes at line ends (shard.shard_cuts), device k filters range k
+    from the host (svjg_filter_host on a thread of its own; the tables are replicated, one handle per device), the
+    counters are summed and the hit lists concatenated in range order = file order, offsets made absolute.
+    The result equals filter_host on one device."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import shard
+    a = _as_u8(gaf)
+    world = len(tables_by_device)
+    cuts = shard.shard_cuts(a, world)
+    def one(k):
+        try:
+            return filter_host(tables_by_device[k], a[cuts[k]:cuts[k + 1]], d_over=d_over)
+        except InputError as exc:                         # offsets of a shard are its own: make them the file's
+            _raise_input(exc.stats, base=cuts[k])
+
+    with ThreadPoolExecutor(world) as pool:
+        parts = list(pool.map(one, range(world)))          # in range order: the first failure is the reference's
+    counts = np.zeros((tables_by_device[0].num_sv, 2), dtype=np.uint32)
+    stats = {}
+    for k, r in enumerate(parts):
+        counts += r.counts
+        for key, v in r.stats.items():
+            if key == "err_offset":
+                continue
+            stats[key] = stats.get(key, 0) + v
+    stats["status"] = 0
+    stats["err_offset"] = parts[0].stats["err_offset"]
+    sv2 = np.concatenate([r.hit_sv2 for r in parts])
+    off = np.concatenate([r.hit_off.astype(np.uint64) + np.uint64(cuts[k]) for k, r in enumerate(parts)])
+    ln = np.concatenate([r.hit_len for r in parts])
+    return FilterResult(counts, stats, sv2, off, ln)
 
 
 def filter_json_host(tables, gaf, d_over=D_OVER, counts=None):

@@ -62,6 +62,7 @@ def _load():
         "svjg_tables_image_hash": (C.c_uint64, [vp]),
         "svjg_tables_sv_id": (C.c_void_p, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "svjg_tables_find_sv": (C.c_uint32, [vp, C.c_char_p, C.c_uint32]),
+        "svjg_tables_clone": (C.c_int, [vp, C.POINTER(C.c_void_p)]),
         "svjg_tables_to_device": (C.c_int, [vp, C.c_int]),
         "svjg_tables_set_flags": (C.c_int, [vp, C.c_uint32]),
         "svjg_filter_reset": (C.c_int, [u32p, C.c_uint32, vp, vp]),

@@ -37,12 +37,31 @@ def _start_device():
     return wait
 
 
+def _n_gpus():
+    """SVJG_GPUS=N: the filter stage shards its GAF over N GPUs of the node (an extension; the reference has
+    one process and no device).  Default 1."""
+    import os
+    try:
+        return max(1, int(os.environ.get("SVJG_GPUS", "1")))
+    except ValueError:
+        _die("SVJG_GPUS must be a number of GPUs")
+
+
 def _load_tables(prefix, gfa_file, device_ready=None):
     from . import alnfilter
     t = alnfilter.Tables.load(prefix + "_svs_edges.json", gfa_file)      # host work: JSON + GFA parse, table build
     if device_ready:
         device_ready()
     return t.to_device(0)
+
+
+def _replicas(tables, n):
+    """`tables` on device 0 plus a copy on each of the devices 1 .. n-1 (uploaded on threads)."""
+    from concurrent.futures import ThreadPoolExecutor
+    if n <= 1:
+        return [tables]
+    with ThreadPoolExecutor(n - 1) as pool:
+        return [tables] + list(pool.map(lambda d: tables.clone().to_device(d), range(1, n)))
 
 
 def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, stream=None):
@@ -63,8 +82,12 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
             if alnfilter.translate_newlines(gaf) is not gaf:               # carriage returns: text-mode line ends
                 gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
     text = None
+    n_gpus = _n_gpus()
     if stream is not None:
         res, gaf = alnfilter.filter_stream(tables, stream)
+    elif n_gpus > 1:
+        # one file, N byte ranges cut at line ends, one GPU each; counters summed, hits merged in range order
+        res = alnfilter.filter_host_multi(_replicas(tables, n_gpus), gaf)
     else:
         # the text of informative_aln.json is assembled on the device and comes back as text; the host emitter
         # takes over where the device renderer declines (non-ASCII bytes in a stored line, a giant list)
