@@ -166,6 +166,14 @@ int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64
 int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
                           svjg_filter_stats *stats, const char **json, uint64_t *json_len);
 
+/* Optional identity filter (an extension, off by default; the reference parses the identity of every alignment,
+ * filter-alignments.py:193-196, and never uses it; predict-genotype.py:222 carries the gate commented out):
+ * drops from a HOST hit list the hits whose line has Aid < min_identity -- Aid as :193-196 defines it, float() of
+ * the text behind the last "id:f:" up to the next tab, else Am / Alen -- compacting the three arrays in place and
+ * taking the dropped hits off the counters.  SVJG_E_INPUT where float() would raise. */
+int svjg_hits_min_identity(const uint8_t *gaf, uint64_t n_bytes, uint32_t *hit_sv2, uint64_t *hit_off, uint32_t *hit_len,
+                           uint64_t *n_hits, double min_identity, uint32_t *counts, uint32_t num_sv);
+
 /* ---- genotype (kernel 4) ----------------------------------------------------
  * Replaces likelihood() / allele_normalization() / encode_genotype()
  * (predict-genotype.py:281-346) and the gate at :216 for n SVs of a VCF.

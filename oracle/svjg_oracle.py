@@ -180,12 +180,27 @@ def kept_text(line):
     return line if j < 0 else line[:j]
 
 
-def filter_alignments(lines, d_link_sv, alt_len, d_over=D_OVER_DEFAULT):
-    """sv_id -> [[ref texts], [alt texts]]  (filter-alignments.py:119-166)."""
+def record_identity(line):
+    """``aln["Aid"]`` as filter-alignments.py:193-196 computes it (and never uses it): float() of the text behind
+    the last "id:f:" up to the next tab where the stripped line holds that tag, else Am / Alen."""
+    s = line.rstrip()
+    if "id:f:" in s:
+        return float(s.split("id:f:")[-1].split("\t")[0])
+    cols = s.split("\t")
+    return int(cols[9]) / int(cols[10])
+
+
+def filter_alignments(lines, d_link_sv, alt_len, d_over=D_OVER_DEFAULT, min_identity=None):
+    """sv_id -> [[ref texts], [alt texts]]  (filter-alignments.py:119-166).  ``d_over``: the threshold of :56
+    (what -O was meant to set).  ``min_identity``: the extension of the new front-end, off by default -- an
+    alignment whose Aid (:193-196) is below it is appended nowhere (the gate predict-genotype.py:222 has
+    commented out, applied where the identity is parsed)."""
     out = {}
     for line in lines:
         hits = record_hits(line, d_link_sv, alt_len, d_over)
         if not hits:
+            continue
+        if min_identity is not None and record_identity(line) < min_identity:
             continue
         text = kept_text(line)
         for sv_id, allele in hits:

@@ -412,6 +412,77 @@ extern "C" int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_
 }
 
 // ---------------------------------------------------------------------------
+// optional identity filter over the hit list (an extension, off by default)
+// ---------------------------------------------------------------------------
+// Aid of a stored line as filter-alignments.py:193-196 parses it: float() of what follows the LAST "id:f:" up to
+// the next tab where the line holds that tag, else Am / Alen (columns 10 and 11).  The reference parses it and
+// never uses it; its genotyper carries the gate commented out (predict-genotype.py:222).  false: float() raises.
+static bool line_identity(const uint8_t *line, size_t len, double &out) {
+    while (len && (line[len - 1] == ' ' || (line[len - 1] >= 9 && line[len - 1] <= 13) || (line[len - 1] >= 0x1c && line[len - 1] <= 0x1f)))
+        --len;                                                        // line.rstrip() (:126)
+    const uint8_t *tag = nullptr;
+    for (size_t i = 0; i + 5 <= len; ++i)
+        if (memcmp(line + i, "id:f:", 5) == 0) tag = line + i + 5;
+    if (tag) {
+        const uint8_t *e = tag;
+        while (e < line + len && *e != '\t') ++e;
+        std::string v(reinterpret_cast<const char *>(tag), size_t(e - tag));
+        // float(): surrounding blanks, then a decimal literal, inf or nan; no hex, no underscores handled here
+        size_t b = 0, n = v.size();
+        while (b < n && (v[b] == ' ' || (v[b] >= 9 && v[b] <= 13))) ++b;
+        while (n > b && (v[n - 1] == ' ' || (v[n - 1] >= 9 && v[n - 1] <= 13))) --n;
+        v = v.substr(b, n - b);
+        if (v.empty()) return false;
+        for (char c : v)
+            if (!(c >= '0' && c <= '9') && c != '.' && c != '+' && c != '-' && c != 'e' && c != 'E' && !strchr("infatyINFATY", c)) return false;
+        if (v.find_first_of("xX") != std::string::npos) return false;
+        char *end = nullptr;
+        out = strtod(v.c_str(), &end);
+        return end == v.c_str() + v.size();
+    }
+    // columns 10 and 11 (validated by the filter: digits only, Alen != 0)
+    size_t col = 0, i = 0;
+    uint64_t am = 0, alen = 0;
+    for (; i < len && col < 11; ++i) {
+        if (line[i] == '\t') {
+            ++col;
+            continue;
+        }
+        if (col == 9) am = am * 10 + uint64_t(line[i] - '0');
+        else if (col == 10) alen = alen * 10 + uint64_t(line[i] - '0');
+    }
+    if (alen == 0) return false;
+    out = double(am) / double(alen);
+    return true;
+}
+
+extern "C" int svjg_hits_min_identity(const uint8_t *gaf, uint64_t n_bytes, uint32_t *hit_sv2, uint64_t *hit_off, uint32_t *hit_len,
+                                      uint64_t *n_hits, double min_identity, uint32_t *counts, uint32_t num_sv) {
+    if (!n_hits || (*n_hits && (!gaf || !hit_sv2 || !hit_off || !hit_len || !counts)))
+        return set_error(SVJG_E_ARG, "svjg_hits_min_identity: NULL argument");
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < *n_hits; ++i) {
+        if (hit_off[i] + hit_len[i] > n_bytes || hit_sv2[i] >= 2ull * num_sv) return set_error(SVJG_E_ARG, "hit outside the GAF buffer");
+        double id = 0;
+        if (!line_identity(gaf + hit_off[i], hit_len[i], id)) {
+            char msg[128];
+            snprintf(msg, sizeof msg, "GAF line at byte %llu: the value of its id:f: tag is no number", (unsigned long long)hit_off[i]);
+            return set_error(SVJG_E_INPUT, msg);
+        }
+        if (id >= min_identity) {
+            hit_sv2[w] = hit_sv2[i];
+            hit_off[w] = hit_off[i];
+            hit_len[w] = hit_len[i];
+            ++w;
+        } else {
+            --counts[hit_sv2[i]];
+        }
+    }
+    *n_hits = w;
+    return SVJG_OK;
+}
+
+// ---------------------------------------------------------------------------
 // informative_aln.json   (json.dumps(d, sort_keys=True, indent=4))
 // ---------------------------------------------------------------------------
 namespace {

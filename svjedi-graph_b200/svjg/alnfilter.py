@@ -215,6 +215,26 @@ def filter_host(tables, gaf, d_over=D_OVER, want_hits=True, hit_cap=None, out=No
     return FilterResult(counts, st)
 
 
+def apply_min_identity(tables, gaf, result, min_identity):
+    """Extension (off by default): drops the hits whose alignment has Aid < ``min_identity``, Aid as
+    filter-alignments.py:193-196 parses it (float() behind the last "id:f:", else Am / Alen); the counters follow.
+    InputError where float() raises on a stored line."""
+    a = _as_u8(gaf)
+    sv2 = np.ascontiguousarray(result.hit_sv2, dtype=np.uint32).copy()
+    off = np.ascontiguousarray(result.hit_off, dtype=np.uint64).copy()
+    ln = np.ascontiguousarray(result.hit_len, dtype=np.uint32).copy()
+    counts = np.ascontiguousarray(result.counts, dtype=np.uint32).copy()
+    n = C.c_uint64(int(sv2.size))
+    rc = capi.lib.svjg_hits_min_identity(a.ctypes.data if a.size else None, int(a.size), sv2.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                         C.byref(n), float(min_identity), counts.ctypes.data, tables.num_sv)
+    if rc == capi.E_INPUT:
+        raise InputError(capi.lib.svjg_last_error().decode("utf-8", "replace"))
+    capi.check(rc)
+    k = int(n.value)
+    stats = dict(result.stats, n_hits=k)
+    return FilterResult(counts, stats, sv2[:k], off[:k], ln[:k])
+
+
 def filter_host_multi(tables_by_device, gaf, d_over=D_OVER):
     """The per-line loop over ONE buffer on several GPUs of the node (the stage boundary svjedi-graph.py:113-118
     with the records sharded): the buffer is cut by bytes at line ends (shard.shard_cuts), device k filters range k
@@ -275,20 +295,45 @@ def filter_json_host(tables, gaf, d_over=D_OVER, counts=None):
     return FilterResult(counts, st), text
 
 
-def filter_stream(tables, fileobj, chunk_bytes=64 << 20, d_over=D_OVER):
+def filter_stream(tables, fileobj, chunk_bytes=16 << 20, d_over=D_OVER):
     """the filter fed from a pipe (``minigraph ... | filter-alignments.py -a
-    /dev/stdin``) while the mapper is still writing.  The stream is cut into segments of whole lines of
-    about ``chunk_bytes``; each segment goes through :func:`filter_host` on a worker thread (ctypes
+    /dev/stdin``) while the mapper is still writing.  The stream is read straight into PAGE-LOCKED buffers
+    (three of them in turn: one being read into, one being filtered, one spare) and cut into segments of whole
+    lines of about ``chunk_bytes``; each segment goes through :func:`filter_host` on a worker thread (ctypes
     releases the GIL) while the next one is being read, its counters are added up and its hit offsets
     moved to their place in the whole input.  Text-mode line ends are translated per segment exactly as
     for a file (a "\r" at the end of a read is held back until the next byte is known).  Returns
     (FilterResult, the whole translated GAF as one uint8 array) — what the JSON writer needs."""
     from concurrent.futures import ThreadPoolExecutor
     segments, results = [], []
-    pending = b""
     pool = ThreadPoolExecutor(1)
-    job = None
+    jobs = []                                              # (future, ring slot) in flight, oldest first
     base = 0
+    cap = 2 * chunk_bytes                                  # a segment is cut once chunk_bytes are there; a longer line: grow()
+    keep, bufs = [], [None, None, None]
+
+    def alloc(n):
+        try:
+            keep.append(PinnedBytes(n))                    # page-locked; alive until the jobs that read it are done
+            return keep[-1].array
+        except capi.SvjgError:                             # no device (the CPU tests of the cutting logic)
+            return np.empty(n, np.uint8)
+
+    def buffer(k):
+        """ring buffer k, made when first needed (a short stream needs one)"""
+        if bufs[k] is None or bufs[k].size < cap:
+            bufs[k] = alloc(cap)
+        return bufs[k]
+
+    def grow():
+        """a line longer than a buffer: twice the room from here on, what is there moves along"""
+        nonlocal cap
+        old = bufs[slot]
+        cap *= 2
+        bufs[slot] = alloc(cap)
+        bufs[slot][:fill] = old[:fill]
+    slot, fill = 0, 0                                      # bufs[slot][:fill]: bytes read and not yet submitted
+    held_cr = False
 
     def one_segment(arr, b):
         try:
@@ -296,37 +341,60 @@ def filter_stream(tables, fileobj, chunk_bytes=64 << 20, d_over=D_OVER):
         except InputError as exc:
             raise InputError(f"{exc} [offset within the segment that starts at byte {b} of the stream]") from None
 
-    def submit(seg):
-        nonlocal job, base
-        if job is not None:
-            results.append(job.result())                  # raises InputError where the reference raises
-        arr = np.frombuffer(seg, dtype=np.uint8)
-        segments.append(arr)
-        job = pool.submit(one_segment, arr, base)
-        base += arr.size
+    def reap(upto):
+        while len(jobs) > upto:
+            results.append(jobs.pop(0)[0].result())        # raises InputError where the reference raises
+
+    def submit(n):
+        """bufs[slot][:n] is a segment; what lies behind it moves to the head of the next free buffer"""
+        nonlocal slot, fill, base
+        cur = buffer(slot)
+        segments.append(cur[:n].copy())                    # the JSON writer needs the whole text at the end
+        reap(1)                                            # at most two segments in flight: the third buffer is free
+        jobs.append((pool.submit(one_segment, cur[:n], base), slot))
+        base += n
+        nxt = (slot + 1) % 3
+        rest = fill - n
+        if rest:
+            buffer(nxt)[:rest] = cur[n:fill]
+        slot, fill = nxt, rest
 
     try:
         eof = False
+        readinto = getattr(fileobj, "readinto", None)
         while not eof:
-            block = fileobj.read(chunk_bytes)
-            eof = not block
-            data = pending + block
-            held = b""
-            if not eof and data.endswith(b"\r"):           # "\r\n" may straddle two reads
-                data, held = data[:-1], b"\r"
-            if b"\r" in data:
-                data = data.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+            cur = buffer(slot)
+            room = memoryview(cur)[fill + (1 if held_cr else 0):min(cap, fill + chunk_bytes)]
+            if readinto is not None:
+                got = readinto(room) or 0
+            else:
+                block = fileobj.read(chunk_bytes)
+                got = len(block)
+                room[:got] = block
+            eof = got == 0
+            new0 = fill
+            if held_cr:                                    # the "\r" held back belongs in front of these bytes (room was left)
+                cur[fill] = 13
+                got += 1
+                held_cr = False
+            fill += got
+            if not eof and fill > new0 and cur[fill - 1] == 13:     # "\r\n" may straddle two reads
+                fill -= 1
+                held_cr = True
+            if fill > new0 and (cur[new0:fill] == 13).any():
+                t = np.frombuffer(bytes(cur[new0:fill]).replace(b"\r\n", b"\n").replace(b"\r", b"\n"), dtype=np.uint8)
+                cur[new0:new0 + t.size] = t
+                fill = new0 + t.size
             if eof:
-                cut = len(data)
+                cut = fill
             else:
-                cut = data.rfind(b"\n") + 1                 # whole lines only; the rest waits for more bytes
-            if cut and (eof or cut >= chunk_bytes // 2 or len(data) >= 2 * chunk_bytes):
-                submit(data[:cut])
-                pending = data[cut:] + held
-            else:
-                pending = data + held
-        if job is not None:
-            results.append(job.result())
+                nl = np.flatnonzero(cur[:fill][::-1] == 10)
+                cut = fill - int(nl[0]) if nl.size else 0   # whole lines only; the rest waits for more bytes
+            if cut and (eof or fill >= chunk_bytes):
+                submit(cut)
+            if fill >= cap - 1:
+                grow()
+        reap(0)
     finally:
         pool.shutdown(wait=True)
     counts = np.zeros((tables.num_sv, 2), dtype=np.uint32)

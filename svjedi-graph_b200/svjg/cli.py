@@ -64,7 +64,7 @@ def _replicas(tables, n):
         return [tables] + list(pool.map(lambda d: tables.clone().to_device(d), range(1, n)))
 
 
-def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, stream=None):
+def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, stream=None, d_over=100, min_identity=None):
     """filter-alignments.py:119-175.  Returns (FilterResult, page-locked GAF bytes).  ``stream``: an open
     pipe to filter while it is being written (alnfilter.filter_stream) instead of a file."""
     from . import alnfilter, capi, gzio
@@ -84,16 +84,20 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
     text = None
     n_gpus = _n_gpus()
     if stream is not None:
-        res, gaf = alnfilter.filter_stream(tables, stream)
+        res, gaf = alnfilter.filter_stream(tables, stream, d_over=d_over)
     elif n_gpus > 1:
         # one file, N byte ranges cut at line ends, one GPU each; counters summed, hits merged in range order
-        res = alnfilter.filter_host_multi(_replicas(tables, n_gpus), gaf)
+        res = alnfilter.filter_host_multi(_replicas(tables, n_gpus), gaf, d_over=d_over)
+    elif min_identity is not None:
+        res = alnfilter.filter_host(tables, gaf, d_over=d_over)                # the hit list on the host: it is thinned below
     else:
         # the text of informative_aln.json is assembled on the device and comes back as text; the host emitter
         # takes over where the device renderer declines (non-ASCII bytes in a stored line, a giant list)
-        res, text = alnfilter.filter_json_host(tables, gaf)
+        res, text = alnfilter.filter_json_host(tables, gaf, d_over=d_over)
         if text is None:
-            res = alnfilter.filter_host(tables, gaf)
+            res = alnfilter.filter_host(tables, gaf, d_over=d_over)
+    if min_identity is not None:
+        res = alnfilter.apply_min_identity(tables, gaf, res, min_identity)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
     if text is not None:
@@ -112,6 +116,13 @@ def filter_main(argv=None):
     ap.add_argument("-O", "--dover", metavar="<min_breakpoint_overlap>", nargs=1, required=False, default=100)
     ap.add_argument("-o", "--outputDir", metavar="<outputDirectory>", type=str, required=False)
     ap.add_argument("-p", "--prefix", metavar="<prefix", type=str, required=False)
+    # two switches the reference does not have (its -O cannot be used, :269; its identity is parsed and dropped, :193-196)
+    ap.add_argument("--min-overlap", metavar="<bases>", type=int, default=None,
+                    help="NOT in the reference: aligned bases required on each side of a breakpoint (default 100, "
+                         "filter-alignments.py:56); the reference's own -O/--dover stops at its first overlap test and so does ours")
+    ap.add_argument("--min-identity", metavar="<fraction>", type=float, default=None,
+                    help="NOT in the reference, off by default: drop alignments whose identity (the id:f: tag, else "
+                         "matches / alignment length: filter-alignments.py:193-196) is below this")
     args = ap.parse_args(argv)
     if not args.prefix:
         # the reference never assigns svs_edges_dict without -p (UnboundLocalError, :95)
@@ -136,12 +147,14 @@ def filter_main(argv=None):
         if pipe is not None:
             with pipe:                                                     # filtered segment by segment while the mapper writes
                 tables = _load_tables(args.prefix, args.gfa[0], ready)
-                _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, stream=pipe)
+                _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, stream=pipe,
+                                d_over=100 if args.min_overlap is None else args.min_overlap, min_identity=args.min_identity)
             return 0
         raw = alnfilter.translate_newlines(raw)                            # text-mode line ends, like the reference
         tables = _load_tables(args.prefix, args.gfa[0], ready)
         gaf = alnfilter.RegisteredBytes(raw)                                # page-lock in place
-        _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, gaf=gaf)
+        _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, gaf=gaf,
+                        d_over=100 if args.min_overlap is None else args.min_overlap, min_identity=args.min_identity)
     except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
         _die(str(exc))
     return 0

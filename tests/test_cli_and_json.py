@@ -117,6 +117,91 @@ def test_pipeline_front_end_with_stub_tools(tmp_path):
 
 
 @pytest.mark.gpu
+def test_new_switches_min_overlap_and_min_identity(tmp_path):
+    """The two switches the reference does not have, each against its oracle-side statement
+    (oracle.filter_alignments d_over / min_identity): --min-overlap N is the threshold -O was meant to set
+    (filter-alignments.py:56, :269; -O itself still stops the run), --min-identity X drops alignments by the
+    identity :193-196 parses (id:f: tag, else Am / Alen).  Both leave the default run untouched."""
+    from conftest import alt_len_from_gfa_text
+    from oracle import svjg_oracle as O
+    tag = "s3"
+    p = _write_inputs(tmp_path, tag)
+    edges = json.loads(read_golden(f"{tag}_svs_edges.json.gz"))
+    alt = alt_len_from_gfa_text(read_golden(f"{tag}.gfa.gz"))
+    lines = read_golden(f"{tag}.gaf.gz").splitlines(True)
+    # identities: every third line gets an id:f: tag (some below, some above, odd spellings float() accepts)
+    vals = ["0.5", "0.91", "0.899999", " 0.95 ", "9e-1", "1", ".97", "0.90000000000000002"]
+    lines = [l[:-1] + f"\tid:f:{vals[i % len(vals)]}\n" if i % 3 == 0 else l for i, l in enumerate(lines)]
+    with open(p + ".gaf", "w") as fh:
+        fh.writelines(lines)
+    for args, kw in ((["--min-overlap", "250"], {"d_over": 250}), (["--min-overlap", "0"], {"d_over": 0}),
+                     (["--min-identity", "0.9"], {"min_identity": 0.9}), (["--min-identity", "0.9", "--min-overlap", "150"], {"min_identity": 0.9, "d_over": 150}),
+                     ([], {})):
+        r = _run("filter-alignments.py", "-a", p + ".gaf", "-g", p + ".gfa", "-p", p, *args)
+        assert r.returncode == 0, r.stderr
+        want = O.dumps_informative(O.filter_alignments(lines, edges, alt, **kw))
+        assert open(p + "_informative_aln.json").read() == want, args
+    base = O.filter_alignments(lines, edges, alt)
+    assert O.filter_alignments(lines, edges, alt, min_identity=0.9) != base != O.filter_alignments(lines, edges, alt, d_over=250)
+    # a value float() rejects on a line that is stored: exit status 1 (the reference raises on such a line at :194)
+    bad = list(lines)
+    k = next(i for i, l in enumerate(bad) if i % 3 == 0 and O.record_hits(l, edges, alt))
+    bad[k] = bad[k].replace("id:f:", "id:f:x")
+    with open(p + ".gaf", "w") as fh:
+        fh.writelines(bad)
+    r = _run("filter-alignments.py", "-a", p + ".gaf", "-g", p + ".gfa", "-p", p, "--min-identity", "0.9")
+    assert r.returncode == 1 and "id:f:" in r.stderr
+    # -O keeps the reference's behaviour
+    r = _run("filter-alignments.py", "-a", p + ".gaf", "-g", p + ".gfa", "-p", p, "-O", "50")
+    assert r.returncode == 1
+
+
+@pytest.mark.gpu
+def test_streamed_stages_on_the_device(tmp_path):
+    """Row N3 on a GPU: a GAF piped into `filter-alignments.py -a /dev/stdin` (segments of whole lines read into
+    page-locked buffers and filtered while the writer is still writing), and `SVJG_STREAM=1 svjedi-graph.py` with
+    stub tools (mapping and filtering overlapped): the reference's files, byte for byte."""
+    import hashlib
+    import subprocess
+    tag = "s3"
+    p = _write_inputs(tmp_path, tag)
+    with open(p + ".gaf", "rb") as fh:
+        raw = fh.read()
+    # the writer delivers the file in odd pieces with pauses, through a real pipe
+    writer = tmp_path / "writer.py"
+    writer.write_text("import sys, time\nraw = open(sys.argv[1], 'rb').read()\nstep = 1 + len(raw) // 37\n"
+                      "for i in range(0, len(raw), step):\n    sys.stdout.buffer.write(raw[i:i + step]); sys.stdout.buffer.flush(); time.sleep(0.01)\n")
+    cmd = f"{sys.executable} {writer} {p}.gaf | {sys.executable} {os.path.join(PKG, 'filter-alignments.py')} -a /dev/stdin -g {p}.gfa -p {p}"
+    r = subprocess.run(cmd, shell=True, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with open(p + "_informative_aln.json", "rb") as fh:
+        assert hashlib.sha256(fh.read()).hexdigest() == read_golden(f"{tag}_informative_aln.sha256").strip()
+    os.remove(p + "_informative_aln.json")
+    # the orchestrator with mapping and filtering overlapped
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    stub = bindir / "construct_stub.py"
+    stub.write_text(
+        "import shutil, sys\n"
+        "out = sys.argv[sys.argv.index('-o') + 1]\n"
+        f"shutil.copy({p + '.gfa'!r}, out)\n"
+        f"shutil.copy({p + '_svs_edges.json'!r}, out[:-4] + '_svs_edges.json')\n")
+    mg = bindir / "minigraph"
+    mg.write_text(f"#!/bin/sh\n{sys.executable} {writer} {p}.gaf\n")
+    mg.chmod(0o755)
+    env = dict(os.environ, PATH=f"{bindir}:{os.environ['PATH']}", SVJG_CONSTRUCT_GRAPH=str(stub), SVJG_STREAM="1")
+    prefix = str(tmp_path / "run")
+    open(tmp_path / "reads.fq", "w").write("")
+    r = _run("svjedi-graph.py", "-v", p + ".vcf", "-r", "ref.fa", "-q", str(tmp_path / "reads.fq"), "-p", prefix, env=env)
+    assert r.returncode == 0, r.stderr
+    with open(prefix + "_informative_aln.json", "rb") as fh:
+        assert hashlib.sha256(fh.read()).hexdigest() == read_golden(f"{tag}_informative_aln.sha256").strip()
+    assert open(prefix + "_genotype.vcf").read() == read_golden(f"{tag}_genotype.vcf.gz")
+    assert open(prefix + ".gaf", "rb").read() == raw
+    assert r.stdout.endswith(read_golden(f"{tag}_stdout.txt"))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["s2", "s3", "s4"])
 def test_front_ends_on_scaled_configs(tmp_path, tag):
     """The three scaled-down BASELINE.json shapes through the command lines (no tensor library in these
