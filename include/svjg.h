@@ -124,6 +124,11 @@ int svjg_filter_device(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_by
                        int64_t d_over, uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off,
                        uint32_t *d_hit_len, uint64_t hit_cap, svjg_filter_stats *d_stats, void *stream);
 
+/* Text-mode line ends as the reference's `open(gaf)` gives them (filter-alignments.py:123): "\r\n" and a lone
+ * "\r" become "\n", in place, one pass; returns the new length.  A front-end calls it before the filter when
+ * its bytes may hold carriage returns (the kernels split at "\n" only). */
+uint64_t svjg_translate_newlines(uint8_t *p, uint64_t n);
+
 /* Measurement and test aids of the filter (no reference analogue; process-wide, not thread-safe against
  * running filter calls).
  *   svjg_filter_profile(1)   every later svjg_filter_device call records CUDA events around its scan

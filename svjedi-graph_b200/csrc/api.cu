@@ -102,6 +102,29 @@ extern "C" int svjg_device_init(int device) {
     return SVJG_OK;
 }
 
+// Text-mode line ends (filter-alignments.py:123 reads the GAF in text mode): "\r\n" and a lone "\r" become "\n".
+// In place, one pass; returns the new length.
+extern "C" uint64_t svjg_translate_newlines(uint8_t *p, uint64_t n) {
+    if (!p) return 0;
+    uint8_t *cr = static_cast<uint8_t *>(memchr(p, '\r', n));
+    if (!cr) return n;
+    uint64_t r = uint64_t(cr - p), w = r;
+    while (r < n) {
+        if (p[r] == '\r') {
+            p[w++] = '\n';
+            r += (r + 1 < n && p[r + 1] == '\n') ? 2 : 1;
+            continue;
+        }
+        // copy the run up to the next carriage return in one go
+        const uint8_t *nx = static_cast<const uint8_t *>(memchr(p + r, '\r', n - r));
+        const uint64_t run = nx ? uint64_t(nx - (p + r)) : n - r;
+        if (w != r) memmove(p + w, p + r, run);
+        w += run;
+        r += run;
+    }
+    return w;
+}
+
 extern "C" int svjg_tables_to_device(svjg_tables *t, int device) {
     if (!t) return set_error(SVJG_E_ARG, "svjg_tables_to_device: NULL tables");
     if (t->device == device) return SVJG_OK;
@@ -252,7 +275,12 @@ extern "C" int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_b
         SVJG_CUDA(cudaStreamWaitEvent(w->s_comp, w->copied[b], 0));
         rc = filter_device_abs(t, w->d_buf[b], len, cut[k], d_over, w->d_counts, k_sv2, nullptr, k_off, k_len, hit_cap,
                                w->d_stats, w->s_comp);
-        if (rc) return rc;
+        if (rc) {
+            // copies out of the caller's buffer and kernels may still be in flight: not behind the caller's back
+            cudaStreamSynchronize(w->s_copy);
+            cudaStreamSynchronize(w->s_comp);
+            return rc;
+        }
         SVJG_CUDA(cudaEventRecord(w->freed[b], w->s_comp));
     }
     SVJG_CUDA(cudaMemcpyAsync(stats, w->d_stats, sizeof(svjg_filter_stats), cudaMemcpyDeviceToHost, w->s_comp));

@@ -132,8 +132,8 @@ def _as_u8(buf):
 def translate_newlines(buf):
     """The reference reads the GAF in text mode (filter-alignments.py:123): "\r\n" and a lone "\r" are
     line ends too and become "\n" in the stored lines.  The kernels split at "\n" only, so a buffer
-    that contains a carriage return is translated first (a copy); any other buffer is returned as it
-    is.  One memchr over the bytes."""
+    that contains a carriage return is translated first (one copy, one pass: svjg_translate_newlines);
+    any other buffer is returned as it is.  One memchr over the bytes."""
     a = _as_u8(buf)
     if a.size == 0:
         return buf
@@ -142,7 +142,9 @@ def translate_newlines(buf):
     libc.memchr.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     if not libc.memchr(a.ctypes.data, 13, a.size):
         return buf
-    return np.frombuffer(a.tobytes().replace(b"\r\n", b"\n").replace(b"\r", b"\n"), dtype=np.uint8)
+    out = a.copy()                                          # the caller's bytes stay as they are
+    n = int(capi.lib.svjg_translate_newlines(out.ctypes.data, out.size))
+    return out[:n]
 
 
 def _raise_input(stats, base=0):

@@ -294,7 +294,12 @@ def genotype_host(counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR):
     numpy (gt, flags, ad2, pl).  Needs no tensor library -- the path of the command-line front-ends."""
     n = int(len(sv_index))
     if not 0 < e < 1:
-        raise VcfError("error rate must be in (0, 1)")      # math.log10 raises in the reference
+        # math.log10 raises inside likelihood() (predict-genotype.py:295-299), i.e. only once a record passes the gate
+        # at :216; a VCF without such a record is written out with "./." everywhere
+        out = genotype_host(counts, sv_index, svtype, min_support, ERR)
+        if (out[1] & capi.GT_GENOTYPED).any():
+            raise VcfError("error rate must be in (0, 1)")
+        return out
     la, lb, lh = math.log10(1 - e), math.log10(e), math.log10(1 / 2)
     lut = log10comb_lut()
     counts = np.ascontiguousarray(counts, dtype=np.uint32).reshape(-1, 2)
@@ -333,7 +338,11 @@ def genotype_device(d_counts, sv_index, svtype, min_support=MIN_SUPPORT, e=ERR, 
     dev = d_counts.device if device is None else device
     n = int(len(sv_index))
     if not 0 < e < 1:
-        raise VcfError("error rate must be in (0, 1)")      # math.log10 raises in the reference
+        # as in genotype_host: the reference raises only when some record passes the gate (:216)
+        out = genotype_device(d_counts, sv_index, svtype, min_support, ERR, device)
+        if (out[1] & capi.GT_GENOTYPED).any():
+            raise VcfError("error rate must be in (0, 1)")
+        return out
     la, lb, lh = math.log10(1 - e), math.log10(e), math.log10(1 / 2)
     lut = _dev_lut.get(str(dev))
     if lut is None:

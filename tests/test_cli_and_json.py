@@ -117,6 +117,23 @@ def test_pipeline_front_end_with_stub_tools(tmp_path):
 
 
 @pytest.mark.gpu
+def test_error_rate_outside_0_1_fails_only_with_a_genotyped_record(tmp_path):
+    """predict-genotype.py -e 2: math.log10 raises inside likelihood() (:295-299), so the reference stops only when
+    some record passes the gate at :216; otherwise it writes "./." everywhere and exits 0 (checked on the
+    unmodified script when this test was written)."""
+    vcf = ("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+           "chr1\t1000\ta\tN\t<DEL>\t.\t.\tSVTYPE=DEL;END=1200\n")
+    (tmp_path / "in.vcf").write_text(vcf)
+    (tmp_path / "empty.json").write_text("{}")
+    (tmp_path / "one.json").write_text('{"chr1:DEL-1000-1200": [["x\\n", "y\\n", "z\\n"], []]}')
+    r = _run("predict-genotype.py", "-d", str(tmp_path / "empty.json"), "-v", str(tmp_path / "in.vcf"), "-o", str(tmp_path / "o1.vcf"), "-e", "2")
+    assert r.returncode == 0 and r.stdout == "Genotyped svs: 0\n", r.stderr
+    assert open(tmp_path / "o1.vcf").read().endswith("SVTYPE=DEL;END=1200\tGT:DP:AD:PL\t./.:0:0,0:.,.,.\n")
+    r = _run("predict-genotype.py", "-d", str(tmp_path / "one.json"), "-v", str(tmp_path / "in.vcf"), "-o", str(tmp_path / "o2.vcf"), "-e", "2")
+    assert r.returncode == 1
+
+
+@pytest.mark.gpu
 def test_new_switches_min_overlap_and_min_identity(tmp_path):
     """The two switches the reference does not have, each against its oracle-side statement
     (oracle.filter_alignments d_over / min_identity): --min-overlap N is the threshold -O was meant to set
