@@ -103,11 +103,38 @@ class CounterExchange:
         self._capi.check(self._capi.lib.svjg_xchg_signal(self._regions, self.world, self.rank, step, stream))
 
     def genotype(self, step, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax, d_pl, d_gt, d_ad, d_fl, stream,
-                 signal=True):
-        """``signal``: the kernel announces this rank's counters itself (no separate signal() launch)."""
+                 signal=True, k_override=None):
+        """Asynchronous launch.  ``signal``: the kernel announces this rank's counters itself (no separate signal()
+        launch).  The caller either uses :meth:`genotype_checked` or looks at the outcome itself: ``timed_out()``
+        after a synchronise, and the SVJG_GT_NEED_K flag of the SVs whose counts lie beyond the log10 C(n,k) table."""
         self._capi.check(self._capi.lib.svjg_genotype_xchg(self._regions, self.world, self.rank, self.num_sv, step & 1, step,
-                                                           1 if signal else 0, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax, None,
-                                                           d_pl, d_gt, d_ad, d_fl, stream))
+                                                           1 if signal else 0, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax,
+                                                           k_override, d_pl, d_gt, d_ad, d_fl, stream))
+
+    def genotype_checked(self, step, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax, d_pl, d_gt, d_ad, d_fl, stream, sync):
+        """:meth:`genotype`, then the checks the plain launch leaves to its caller: waits (``sync()``), raises if a
+        peer never announced its counters (the kernel gives up after ~2 s and its sums are partial), and re-runs the
+        SVs that need log10 C(n,k) beyond the table with CPython's own values, as the one-GPU path does
+        (genotype.genotype_device).  ``d_fl`` / ``d_ad``: torch tensors (the flags and counts are read back)."""
+        import numpy as np
+        from . import genotype as G
+        self.genotype(step, d_idx.data_ptr(), d_ty.data_ptr(), n, min_support, la, lb, lh, d_lut.data_ptr(), lut_nmax,
+                      d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), stream)
+        sync()
+        if self.timed_out():
+            raise RuntimeError(f"rank {self.rank}: a peer did not announce its counters for step {step} (fused counter exchange)")
+        flags = d_fl.cpu().numpy()[:n]
+        if (flags & self._capi.GT_NEED_K).any():
+            import torch
+            kov = G._k_overrides(flags, d_ad.cpu().numpy().view(np.uint32)[:n], n)
+            d_kov = torch.from_numpy(kov).to(d_fl.device)
+            # the counters of this step are announced and summed where they lie: no second announcement
+            self.genotype(step, d_idx.data_ptr(), d_ty.data_ptr(), n, min_support, la, lb, lh, d_lut.data_ptr(), lut_nmax,
+                          d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), stream, signal=False,
+                          k_override=d_kov.data_ptr())
+            sync()
+            if (d_fl.cpu().numpy()[:n] & self._capi.GT_NEED_K).any():
+                raise RuntimeError("genotype kernel could not represent a likelihood exactly")
 
     def timed_out(self):
         v = self._C.c_uint32()

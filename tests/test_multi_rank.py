@@ -136,9 +136,13 @@ def _xchg_worker(rank, world, port, tag, out_dir):
         capi.check(capi.lib.svjg_filter_reset(cp, t.num_sv, stats.data_ptr(), sp))
         capi.check(capi.lib.svjg_filter_device(t._h, d_gaf.data_ptr(), d_gaf.numel(), 0, 100, cp, None, None, None, 0,
                                                stats.data_ptr(), sp))
-        x.genotype(step, d_idx.data_ptr(), d_ty.data_ptr(), n, 3, la, lb, lh, lut.data_ptr(), genotype.LUT_NMAX,
-                   d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), sp)
-        torch.cuda.synchronize()
+        if step == 3:                                        # the launch with its checks (time-out, counts beyond the table)
+            x.genotype_checked(step, d_idx, d_ty, n, 3, la, lb, lh, lut, genotype.LUT_NMAX, d_pl, d_gt, d_ad, d_fl, sp,
+                               torch.cuda.synchronize)
+        else:
+            x.genotype(step, d_idx.data_ptr(), d_ty.data_ptr(), n, 3, la, lb, lh, lut.data_ptr(), genotype.LUT_NMAX,
+                       d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), sp)
+            torch.cuda.synchronize()
         assert not x.timed_out()
         np.savez(os.path.join(out_dir, f"geno_{rank}_{step}.npz"), pl=d_pl.cpu().numpy(), gt=d_gt.cpu().numpy(),
                  ad=d_ad.cpu().numpy(), fl=d_fl.cpu().numpy())
