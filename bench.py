@@ -504,12 +504,22 @@ def main():
             return out
         xchg = CounterExchange(tables.num_sv, rank, world, gather_bytes)
     step_no = [0]
+    # N > 1 with the fused exchange: the genotype kernel of step k waits (on the device) for the filter of the slowest
+    # rank; it runs on a stream of its own so that this rank's filter of step k + 1 does not wait with it.  The three
+    # counter buffers of the exchange region are taken in turn; step k + 3 reuses buffer k % 3 behind this rank's
+    # genotype kernel of step k + 1 (include/svjg.h).
+    side = torch.cuda.Stream(dev) if xchg else None
+    side_p = C.c_void_p(side.cuda_stream) if xchg else None
+    filt_done = [torch.cuda.Event() for _ in range(3)]
+    geno_done = [torch.cuda.Event() for _ in range(3)]
 
     def step(ev=None):
         step_no[0] += 1
         k = step_no[0]
-        # p2p: this rank's counters live in its exchange region (two buffers, alternating by step)
+        # p2p: this rank's counters live in its exchange region (three buffers, taken in turn)
         counts_ptr = xchg.counts_ptr(k) if xchg else filt.counts.data_ptr()
+        if xchg and k > 2:
+            stream.wait_event(geno_done[(k - 2) % 3])      # every rank has read buffer k % 3 of step k - 3
         capi.check(lib.svjg_filter_reset(counts_ptr, tables.num_sv, filt.stats.data_ptr(), sp))
         if ev:
             ev[0].record(stream)
@@ -525,14 +535,19 @@ def main():
         if xchg:
             # announces this rank's counters, waits on the device for all ranks, then sums their counters
             # where they lie (NVLink peer reads): all-reduce and genotype step in one kernel
+            filt_done[k % 3].record(stream)
+            side.wait_event(filt_done[k % 3])
             xchg.genotype(k, d_idx.data_ptr(), d_ty.data_ptr(), n_loc, 3, la, lb, lh, lut.data_ptr(), genotype.LUT_NMAX,
-                          d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), sp)
+                          d_pl.data_ptr(), d_gt.data_ptr(), d_ad.data_ptr(), d_fl.data_ptr(), side_p)
+            geno_done[k % 3].record(side)
+            if ev:
+                ev[3].record(side)
         else:
             capi.check(lib.svjg_genotype_device(filt.counts.data_ptr(), d_idx.data_ptr(), d_ty.data_ptr(), n_loc, 3, la, lb, lh,
                                                 lut.data_ptr(), genotype.LUT_NMAX, None, d_pl.data_ptr(), d_gt.data_ptr(),
                                                 d_ad.data_ptr(), d_fl.data_ptr(), sp))
-        if ev:
-            ev[3].record(stream)
+            if ev:
+                ev[3].record(stream)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -569,6 +584,8 @@ def main():
     e0.record(stream)
     for k in range(K):
         step(evs[k])
+    if side is not None:
+        stream.wait_stream(side)                           # the last genotype kernels belong to the timed steps
     e1.record(stream)
     sync_all()
     t_wall1 = time.time()
@@ -576,7 +593,7 @@ def main():
     total_ms = e0.elapsed_time(e1)
     filt_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     comm_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / K
-    geno_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    geno_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K     # with the fused exchange: until every rank's counters were there
     if world > 1:
         t = torch.tensor([total_ms, filt_ms, geno_ms, comm_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -227,12 +227,15 @@ int svjg_device_init(int device);
  * Instead of an all-reduce followed by the genotype kernel, every rank keeps its counters in an
  * exchange region that the other ranks map (CUDA IPC over NVLink peer access), and the genotype
  * kernel of a rank sums, for its SVs only, the counters of all ranks where they lie.
- *   region = 64 flag words, then two counter buffers [num_sv][2] u32 (steps alternate between
- *   them, so a rank may start its next step while a peer still reads the previous one)
+ *   region = 64 flag words, then three counter buffers [num_sv][2] u32 taken in turn by the steps (buffer
+ *   `parity` = step % 3): a rank may filter step k + 1 -- on another stream even while its own genotype kernel of
+ *   step k still waits for the slowest rank -- while peers read step k; buffer k % 3 is written again by step
+ *   k + 3, which the caller starts behind its genotype kernel of step k + 1 (that one has seen every rank announce
+ *   step k + 1, i.e. finish reading step k)
  *   svjg_xchg_create   allocates the region of this rank, returns its 64-byte IPC handle
  *   svjg_xchg_open     maps a peer's region from its handle (exchange the handles out of band,
  *                      e.g. torch.distributed.all_gather_object); _close unmaps it
- *   svjg_xchg_counts   counter buffer `parity` of a region: pass it to svjg_filter_reset /
+ *   svjg_xchg_counts   counter buffer `parity` (taken modulo 3) of a region: pass it to svjg_filter_reset /
  *                      svjg_filter_device as d_counts
  *   svjg_xchg_signal   after the filter of step `epoch` (1, 2, ...): tells every rank, in stream
  *                      order, that this rank's counters are complete

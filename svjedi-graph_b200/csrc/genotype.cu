@@ -295,6 +295,9 @@ extern "C" int svjg_genotype_host(const uint32_t *counts, uint32_t num_counts, c
 // counter exchange between the ranks of one node (one process per GPU)
 // ---------------------------------------------------------------------------
 namespace {
+// counter buffers of a region, taken in turn by the steps: with three of them the genotype kernel of step k (which
+// waits for every rank's filter k) can run beside the filter of step k + 1 on another stream
+constexpr uint32_t XCHG_BUFS = 3;
 size_t xchg_counts_bytes(uint32_t num_sv) { return (size_t(num_sv) * 8 + 255) & ~size_t(255); }
 
 __global__ void xchg_signal_kernel(Xchg x) {
@@ -307,7 +310,7 @@ __global__ void xchg_signal_kernel(Xchg x) {
 extern "C" int svjg_xchg_create(uint32_t num_sv, void **d_base, uint8_t *ipc_handle64) {
     if (!d_base || !ipc_handle64) return svjg::set_error(SVJG_E_ARG, "svjg_xchg_create: NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
-    const size_t bytes = XCHG_FLAG_WORDS * 4 + 2 * xchg_counts_bytes(num_sv);
+    const size_t bytes = XCHG_FLAG_WORDS * 4 + XCHG_BUFS * xchg_counts_bytes(num_sv);
     void *p = nullptr;
     SVJG_CUDA(cudaMalloc(&p, bytes));
     SVJG_CUDA(cudaMemset(p, 0, bytes));
@@ -333,7 +336,7 @@ extern "C" int svjg_xchg_free(void *d_base) {
     return SVJG_OK;
 }
 extern "C" uint32_t *svjg_xchg_counts(void *d_base, uint32_t num_sv, uint32_t parity) {
-    return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(d_base) + XCHG_FLAG_WORDS * 4 + (parity & 1u) * xchg_counts_bytes(num_sv));
+    return reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(d_base) + XCHG_FLAG_WORDS * 4 + (parity % XCHG_BUFS) * xchg_counts_bytes(num_sv));
 }
 extern "C" int svjg_xchg_signal(void *const *d_regions, uint32_t world, uint32_t rank, uint32_t epoch, void *stream) {
     if (!d_regions || world == 0 || world > XCHG_MAX || rank >= world) return svjg::set_error(SVJG_E_ARG, "svjg_xchg_signal: bad argument");

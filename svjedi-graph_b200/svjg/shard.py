@@ -72,7 +72,7 @@ def gather_hits(hit_sv2, hit_off, hit_len, base_offset, group=None):
 
 class CounterExchange:
     """Per-SV counters of all ranks of one node, summed where they lie (include/svjg.h, svjg_xchg_*):
-    every rank filters into ``counts_ptr(step)`` and then calls ``genotype(step, ...)``, which
+    every rank filters into ``counts_ptr(step)`` (three buffers taken in turn) and then calls ``genotype(step, ...)``, which
     announces the rank's counters, waits on the device for the other ranks and reads their counters
     over NVLink peer access -- no all-reduce.  ``exchange`` is a callable that all-gathers a bytes
     object across the ranks (e.g. a wrapper of torch.distributed.all_gather_object)."""
@@ -97,7 +97,7 @@ class CounterExchange:
 
     def counts_ptr(self, step):
         """Device address of this rank's counter buffer for ``step`` (1, 2, ...)."""
-        return self._capi.lib.svjg_xchg_counts(self._base, self.num_sv, step & 1)
+        return self._capi.lib.svjg_xchg_counts(self._base, self.num_sv, step % 3)
 
     def signal(self, step, stream):
         self._capi.check(self._capi.lib.svjg_xchg_signal(self._regions, self.world, self.rank, step, stream))
@@ -107,7 +107,7 @@ class CounterExchange:
         """Asynchronous launch.  ``signal``: the kernel announces this rank's counters itself (no separate signal()
         launch).  The caller either uses :meth:`genotype_checked` or looks at the outcome itself: ``timed_out()``
         after a synchronise, and the SVJG_GT_NEED_K flag of the SVs whose counts lie beyond the log10 C(n,k) table."""
-        self._capi.check(self._capi.lib.svjg_genotype_xchg(self._regions, self.world, self.rank, self.num_sv, step & 1, step,
+        self._capi.check(self._capi.lib.svjg_genotype_xchg(self._regions, self.world, self.rank, self.num_sv, step % 3, step,
                                                            1 if signal else 0, d_idx, d_ty, n, min_support, la, lb, lh, d_lut, lut_nmax,
                                                            k_override, d_pl, d_gt, d_ad, d_fl, stream))
 
