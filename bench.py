@@ -635,13 +635,20 @@ def main():
     host_out = alnfilter.HostBuffers(tables, n_hits + 1024)     # pinned result arrays, allocated once like h_gaf
     out_bytes = [0, 0]
 
+    from concurrent.futures import ThreadPoolExecutor
+    side_pool = ThreadPoolExecutor(1)
+
     def e2e_step():
-        # H2D in chunks, kernels, informative_aln.json assembled on the device (:160-175), text + counters back
-        res, js = alnfilter.filter_json_host(tables, h_gaf, counts=host_out.counts)
+        # H2D in chunks + kernels; the counters come back first ...
+        res = alnfilter.filter_json_begin(tables, h_gaf, counts=host_out.counts)
+        # ... informative_aln.json is assembled on the device (:160-175) and copied back as text on a thread of its own
+        job = side_pool.submit(alnfilter.filter_json_finish, tables)
+        # ... while the counters are genotyped and genotype.vcf is written (predict-genotype.py:216-275)
+        gt, fl, ad, pl = genotype.genotype_host(res.counts, sv_idx, sv_ty)
+        vt, n_gt = nvcf.format_buffer(gt, fl, ad, pl)
+        js = job.result()
         if js is None:
             raise SystemExit("the device JSON renderer declined the synthetic batch")
-        gt, fl, ad, pl = genotype.genotype_host(res.counts, sv_idx, sv_ty)              # counters up, kernel 4, genotypes back
-        vt, n_gt = nvcf.format_buffer(gt, fl, ad, pl)                                   # genotype.vcf text (predict-genotype.py:248-275)
         out_bytes[0], out_bytes[1] = len(js), vt.nbytes
         return res
 
@@ -708,8 +715,8 @@ def main():
         "e2e": {"value": (n_rec * world if not strong else job_rec) * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke,
                 "json_bytes_per_step": out_bytes[0], "vcf_bytes_per_step": out_bytes[1],
-                "what": "svjg_filter_json_host (pinned GAF bytes in; informative_aln.json text rendered on the device + counters out) "
-                        "-> svjg_genotype_host -> genotype.vcf text (svjg_vcf_format), all in host memory"
+                "what": "svjg_filter_json_begin (pinned GAF bytes in, counters out) -> [svjg_filter_json_finish: informative_aln.json text "
+                        "rendered on the device, copied back] beside [svjg_genotype_host -> genotype.vcf text (svjg_vcf_format)], all in host memory"
                         + ("; one such job per GPU at once" if world > 1 else "")},
         "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
                        ("nccl all_reduce" if world > 1 else "none (one GPU)")),

@@ -170,6 +170,12 @@ int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64
  * in a stored line, a list beyond 64 Ki entries) -- use svjg_filter_host + svjg_emit_informative_json. */
 int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
                           svjg_filter_stats *stats, const char **json, uint64_t *json_len);
+/* The same in two halves, for a caller that genotypes (which needs the counters only) while the text is rendered
+ * and copied: _begin returns once counters and stats are on the host; _finish renders the text and waits for it.
+ * Both may be called from different threads, one after the other. */
+int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                           svjg_filter_stats *stats);
+int svjg_filter_json_finish(svjg_tables *t, const char **json, uint64_t *json_len);
 
 /* Optional identity filter (an extension, off by default; the reference parses the identity of every alignment,
  * filter-alignments.py:193-196, and never uses it; predict-genotype.py:222 carries the gate commented out):

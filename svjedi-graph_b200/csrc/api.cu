@@ -45,6 +45,8 @@ struct HostWs {
     char *h_json = nullptr;
     uint64_t json_cap = 0;
     uint64_t hits_per_gib = 0;                // what the last file needed: the first guess for the next one
+    bool pending = false;                     // svjg_filter_json_begin done, svjg_filter_json_finish to come
+    uint64_t pending_hits = 0;
 };
 
 void free_host_ws(svjg_tables *t) {
@@ -339,10 +341,10 @@ static int ensure_hit_arrays(HostWs *w, uint64_t hit_cap) {
     return SVJG_OK;
 }
 
-extern "C" int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
-                                     svjg_filter_stats *stats, const char **json, uint64_t *json_len) {
+extern "C" int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                                      svjg_filter_stats *stats) {
     if (!t || t->device < 0) return set_error(SVJG_E_ARG, "svjg_filter_json_host: tables are not on a device");
-    if (!counts || !stats || !json || !json_len || (n_bytes && !gaf)) return set_error(SVJG_E_ARG, "svjg_filter_json_host: NULL argument");
+    if (!counts || !stats || (n_bytes && !gaf)) return set_error(SVJG_E_ARG, "svjg_filter_json_host: NULL argument");
     SVJG_CUDA(cudaSetDevice(t->device));
     const uint32_t num_sv = uint32_t(t->sv_ids.size());
     if (int rc = ensure_ws(t, num_sv)) return rc;
@@ -411,9 +413,21 @@ extern "C" int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_
     }
     w->hits_per_gib = stats->n_hits / ((n_bytes >> 30) + 1);
     SVJG_CUDA(cudaMemcpyAsync(counts, w->d_counts, size_t(num_sv) * 8, cudaMemcpyDeviceToHost, w->s_comp));
+    SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
+    w->pending_hits = stats->n_hits;
+    w->pending = true;
+    return SVJG_OK;
+}
+
+extern "C" int svjg_filter_json_finish(svjg_tables *t, const char **json, uint64_t *json_len) {
+    if (!t || !t->ws || !t->ws->pending) return set_error(SVJG_E_ARG, "svjg_filter_json_finish: no svjg_filter_json_begin before it");
+    if (!json || !json_len) return set_error(SVJG_E_ARG, "svjg_filter_json_finish: NULL argument");
+    SVJG_CUDA(cudaSetDevice(t->device));
+    HostWs *w = t->ws;
+    w->pending = false;
     uint8_t *d_text = nullptr;
     uint64_t len = 0;
-    int rc = json_render_device(t, w->d_all, w->d_hit[0], w->d_off64, w->d_hit[2], stats->n_hits, w->d_counts, &d_text, &len, w->s_comp);
+    int rc = json_render_device(t, w->d_all, w->d_hit[0], w->d_off64, w->d_hit[2], w->pending_hits, w->d_counts, &d_text, &len, w->s_comp);
     if (rc) {
         cudaStreamSynchronize(w->s_comp);
         return rc;
@@ -437,6 +451,13 @@ extern "C" int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_
     *json = w->h_json;
     *json_len = len;
     return SVJG_OK;
+}
+
+extern "C" int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
+                                     svjg_filter_stats *stats, const char **json, uint64_t *json_len) {
+    if (!json || !json_len) return set_error(SVJG_E_ARG, "svjg_filter_json_host: NULL argument");
+    if (int rc = svjg_filter_json_begin(t, gaf, n_bytes, d_over, counts, stats)) return rc;
+    return svjg_filter_json_finish(t, json, json_len);
 }
 
 // ---------------------------------------------------------------------------

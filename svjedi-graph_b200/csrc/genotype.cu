@@ -261,12 +261,19 @@ extern "C" int svjg_genotype_host(const uint32_t *counts, uint32_t num_counts, c
     const size_t o_idx = up(b_cnt), o_ty = o_idx + up(b_idx), o_lut = o_ty + up(b_ty), o_k = o_lut + up(b_lut),
                  o_pl = o_k + up(b_k), o_gt = o_pl + up(b_pl), o_ad = o_gt + up(b_gt), o_fl = o_ad + up(b_ad),
                  total = o_fl + up(b_fl);
+    // a stream of the call's own and stream-ordered memory: nothing here waits for other work on the device
+    // (the JSON text of the same file may be on its way back, svjg_filter_json_finish)
+    cudaStream_t st = nullptr;
+    SVJG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     uint8_t *d = nullptr;
-    SVJG_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), total));
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d), total, st);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(st);
+        return svjg::cuda_fail(int(e), "svjg_genotype_host: device memory");
+    }
     int rc = SVJG_OK;
-    cudaError_t e = cudaSuccess;
     auto h2d = [&](size_t off, const void *src, size_t bytes) {
-        if (e == cudaSuccess && bytes) e = cudaMemcpy(d + off, src, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, st);
     };
     if (num_counts) h2d(0, counts, size_t(num_counts) * 8);
     h2d(o_idx, sv_index, b_idx);
@@ -278,15 +285,18 @@ extern "C" int svjg_genotype_host(const uint32_t *counts, uint32_t num_counts, c
                                   min_support, log10_1me, log10_e, log10_half, reinterpret_cast<const double *>(d + o_lut),
                                   lut_nmax, k_override ? reinterpret_cast<const double *>(d + o_k) : nullptr,
                                   reinterpret_cast<int64_t *>(d + o_pl), d + o_gt, reinterpret_cast<uint32_t *>(d + o_ad),
-                                  d + o_fl, nullptr);
+                                  d + o_fl, st);
     auto d2h = [&](void *dst, size_t off, size_t bytes) {
-        if (e == cudaSuccess && rc == SVJG_OK) e = cudaMemcpy(dst, d + off, bytes, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && rc == SVJG_OK) e = cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, st);
     };
     d2h(pl, o_pl, b_pl);
     d2h(gt, o_gt, b_gt);
     d2h(ad2, o_ad, b_ad);
     d2h(flags, o_fl, b_fl);
-    cudaFree(d);
+    cudaFreeAsync(d, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = es;
+    cudaStreamDestroy(st);
     if (e != cudaSuccess) return svjg::cuda_fail(int(e), "svjg_genotype_host");
     return rc;
 }

@@ -297,6 +297,34 @@ def filter_json_host(tables, gaf, d_over=D_OVER, counts=None):
     return FilterResult(counts, st), text
 
 
+def filter_json_begin(tables, gaf, d_over=D_OVER, counts=None):
+    """First half of :func:`filter_json_host` (svjg_filter_json_begin): upload + filter; returns the FilterResult
+    (counters, stats) as soon as they are on the host.  The caller may genotype from the counters while
+    :func:`filter_json_finish` -- on another thread if it likes -- renders the text and waits for it."""
+    if tables.device is None:
+        raise RuntimeError("tables.to_device() first")
+    a = _as_u8(gaf)
+    n = int(a.size)
+    counts = counts if counts is not None else np.zeros((tables.num_sv, 2), dtype=np.uint32)
+    stats = capi.FilterStats()
+    rc = capi.lib.svjg_filter_json_begin(tables._h, a.ctypes.data if n else None, n, int(d_over), counts.ctypes.data, C.byref(stats))
+    st = stats.as_dict()
+    if rc == capi.E_INPUT:
+        _raise_input(st)
+    capi.check(rc)
+    return FilterResult(counts, st)
+
+
+def filter_json_finish(tables):
+    """Second half: the JSON text (memoryview into a buffer of ``tables``), or None where the device renderer declines."""
+    p, ln = C.c_void_p(), C.c_uint64()
+    rc = capi.lib.svjg_filter_json_finish(tables._h, C.byref(p), C.byref(ln))
+    if rc == capi.E_UNSUPPORTED:
+        return None
+    capi.check(rc)
+    return memoryview((C.c_char * ln.value).from_address(p.value)) if ln.value else memoryview(b"")
+
+
 def filter_stream(tables, fileobj, chunk_bytes=16 << 20, d_over=D_OVER):
     """the filter fed from a pipe (``minigraph ... | filter-alignments.py -a
     /dev/stdin``) while the mapper is still writing.  The stream is read straight into PAGE-LOCKED buffers

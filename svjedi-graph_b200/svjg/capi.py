@@ -74,6 +74,8 @@ def _load():
                                             C.POINTER(C.c_uint64)]),
         "svjg_hits_min_identity": (C.c_int, [u8p, C.c_uint64, u32p, u64p, u32p, C.POINTER(C.c_uint64), C.c_double, u32p, C.c_uint32]),
         "svjg_translate_newlines": (C.c_uint64, [u8p, C.c_uint64]),
+        "svjg_filter_json_begin": (C.c_int, [vp, u8p, C.c_uint64, C.c_int64, u32p, C.POINTER(FilterStats)]),
+        "svjg_filter_json_finish": (C.c_int, [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
         "svjg_filter_tune": (C.c_int, [C.c_int, C.c_int]),
         "svjg_filter_profile": (C.c_int, [C.c_int]),
         "svjg_filter_scan_ms": (C.c_int, [C.POINTER(C.c_float)]),
