@@ -167,7 +167,8 @@ int svjg_filter_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64
  * list order there (by sv id and allele, then file order, :166), the escaped text is assembled in device
  * memory and crosses PCIe once, as text.  *json points into a page-locked buffer owned by `t`, valid until the
  * next call with `t` or svjg_tables_free.  SVJG_E_UNSUPPORTED: the device renderer declines (a non-ASCII byte
- * in a stored line, a list beyond 64 Ki entries) -- use svjg_filter_host + svjg_emit_informative_json. */
+ * in a stored line, a list beyond 64 Ki entries, a file that does not fit device memory beside its hits and its
+ * text) -- use svjg_filter_host + svjg_emit_informative_json; nothing is lost, those stream the file in chunks. */
 int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
                           svjg_filter_stats *stats, const char **json, uint64_t *json_len);
 /* The same in two halves, for a caller that genotypes (which needs the counters only) while the text is rendered

@@ -356,6 +356,11 @@ extern "C" int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64
         w->d_all = nullptr;
         w->all_cap = 0;
         const uint64_t cap = ((n_bytes + 64) + (1ull << 20)) & ~((1ull << 20) - 1);
+        // a file that does not fit beside its hits and its text: decline, svjg_filter_host streams it in chunks
+        size_t mem_free = 0, mem_total = 0;
+        SVJG_CUDA(cudaMemGetInfo(&mem_free, &mem_total));
+        if (cap + cap / 2 > mem_free)
+            return set_error(SVJG_E_UNSUPPORTED, "the file does not fit the device with its text: svjg_filter_host takes it in chunks");
         SVJG_CUDA(cudaMalloc(&w->d_all, cap));
         w->all_cap = cap;
     }

@@ -409,7 +409,11 @@ int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_h
                  o_kpos = o_epos + up((n + 1) * 8), o_tmp = o_kpos + up((size_t(num_sv) + 1) * 8),
                  o_flags = o_tmp + up((std::max<uint64_t>(n, n2) / SCAN_BLOCK + 4) * 8), total = o_flags + 256;
     uint8_t *ws = nullptr;
-    SVJG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
+    if (cudaError_t me = cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st)) {
+        if (me != cudaErrorMemoryAllocation) return cuda_fail(int(me), "json_render_device: scratch");
+        cudaGetLastError();                                       // not sticky: the host emitter takes over
+        return set_error(SVJG_E_UNSUPPORTED, "no device memory for the renderer's scratch: the host emitter writes the text");
+    }
     uint64_t *seg = reinterpret_cast<uint64_t *>(ws + o_seg), *s_off = reinterpret_cast<uint64_t *>(ws + o_soff),
              *r_off = reinterpret_cast<uint64_t *>(ws + o_roff), *epos = reinterpret_cast<uint64_t *>(ws + o_epos),
              *kpos = reinterpret_cast<uint64_t *>(ws + o_kpos), *tmp = reinterpret_cast<uint64_t *>(ws + o_tmp);
@@ -446,6 +450,10 @@ int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_h
     const uint64_t out_bytes = h_total + 2;
     uint8_t *out = nullptr;
     e = cudaMallocAsync(reinterpret_cast<void **>(&out), out_bytes, st);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(set_error(SVJG_E_UNSUPPORTED, "no device memory for the text: the host emitter writes it"));
+    }
     if (e != cudaSuccess) return fail(cuda_fail(int(e), "json_render_device: output buffer"));
     render_keys<<<blocks(uint64_t(num_sv) + 1), T, 0, st>>>(seg, epos, kpos, kt, num_sv, out);
     if (n) render_hits<<<blocks(n * 32), T, 0, st>>>(d_gaf, r_off, r_len, r_key, n, seg, epos, kpos, kt, out);

@@ -299,8 +299,9 @@ def filter_json_host(tables, gaf, d_over=D_OVER, counts=None):
 
 def filter_json_begin(tables, gaf, d_over=D_OVER, counts=None):
     """First half of :func:`filter_json_host` (svjg_filter_json_begin): upload + filter; returns the FilterResult
-    (counters, stats) as soon as they are on the host.  The caller may genotype from the counters while
-    :func:`filter_json_finish` -- on another thread if it likes -- renders the text and waits for it."""
+    (counters, stats) as soon as they are on the host, or None where the file does not fit the device (use
+    :func:`filter_host`).  The caller may genotype from the counters while :func:`filter_json_finish` -- on
+    another thread if it likes -- renders the text and waits for it."""
     if tables.device is None:
         raise RuntimeError("tables.to_device() first")
     a = _as_u8(gaf)
@@ -311,6 +312,8 @@ def filter_json_begin(tables, gaf, d_over=D_OVER, counts=None):
     st = stats.as_dict()
     if rc == capi.E_INPUT:
         _raise_input(st)
+    if rc == capi.E_UNSUPPORTED:                      # the file does not fit the device: filter_host streams it
+        return None
     capi.check(rc)
     return FilterResult(counts, st)
 
