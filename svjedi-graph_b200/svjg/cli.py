@@ -37,6 +37,21 @@ def _start_device():
     return wait
 
 
+_T0 = [None]
+
+
+def _lap(what):
+    """SVJG_TIMING=1: wall clock of the front-end's stages on stderr (profiling hook, as in csrc/tables.cpp)."""
+    import os
+    import time
+    if "SVJG_TIMING" not in os.environ:
+        return
+    now = time.perf_counter()
+    if _T0[0] is not None:
+        sys.stderr.write(f"svjg timing: {what:<28s} {now - _T0[0]:8.3f} s\n")
+    _T0[0] = now
+
+
 def _n_gpus():
     """SVJG_GPUS=N: the filter stage shards its GAF over N GPUs of the node (an extension; the reference has
     one process and no device).  Default 1."""
@@ -94,6 +109,7 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
         # the text of informative_aln.json is assembled on the device and comes back as text; the host emitter
         # takes over where the device renderer declines (non-ASCII bytes in a stored line, a giant list)
         res, text = alnfilter.filter_json_host(tables, gaf, d_over=d_over)
+        _lap("filter + JSON text")
         if text is None:
             res = alnfilter.filter_host(tables, gaf, d_over=d_over)
     if min_identity is not None:
@@ -105,6 +121,7 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
             fh.write(text)
     else:
         alnfilter.write_informative_json(tables, gaf, res, out_json)
+    _lap("JSON file written")
     return res, gaf
 
 
@@ -134,6 +151,7 @@ def filter_main(argv=None):
     try:
         import os
         import stat
+        _lap("")
         ready = _start_device()
         pipe = None
         if not stat.S_ISREG(os.stat(args.gaf[0]).st_mode):                 # `minigraph ... | filter-alignments.py -a /dev/stdin`
@@ -150,9 +168,13 @@ def filter_main(argv=None):
                 _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, stream=pipe,
                                 d_over=100 if args.min_overlap is None else args.min_overlap, min_identity=args.min_identity)
             return 0
+        _lap("GAF read")
         raw = alnfilter.translate_newlines(raw)                            # text-mode line ends, like the reference
+        _lap("line ends")
         tables = _load_tables(args.prefix, args.gfa[0], ready)
+        _lap("tables + context")
         gaf = alnfilter.RegisteredBytes(raw)                                # page-lock in place
+        _lap("page-lock")
         _filter_to_json(tables, args.gaf[0], out_json, dover_given=args.dover != 100, gaf=gaf,
                         d_over=100 if args.min_overlap is None else args.min_overlap, min_identity=args.min_identity)
     except (alnfilter.InputError, capi.SvjgError, OSError) as exc:
@@ -173,12 +195,16 @@ def genotype_main(argv=None):
     e = args.err[0] if args.err is not None else 0.00005
     from . import capi, genotype, gzio
     try:
+        _lap("")
         ready = _start_device()
         counts = genotype.AlnCounts.load(args.aln[0])
+        _lap("informative_aln.json read")
         ready()
+        _lap("context")
         lines = gzio.read_bytes(args.vcf)                      # the file's bytes: keys and text are built by the library
         with open(output, "wb") as out:         # the reference opens the output before it reads the VCF (:92)
             _, n = genotype.genotype_vcf_from_json(counts, lines, args.minsupport, e, out=out)
+        _lap("genotypes + VCF written")
     except (genotype.VcfError, capi.SvjgError, OSError, ValueError) as exc:
         _die(str(exc))
     print(f"Genotyped svs: {n}")

@@ -72,3 +72,75 @@ def test_full_size_exact_against_the_c_oracle(name, rec_scale, cat_scale):
     text, n = genotype.genotype_vcf(t, res.counts, vcf.encode())
     assert (text, n) == O.genotype_vcf(CO.counts_dict(ct, want_counts), vcf.splitlines(True))
     assert n > 100 * scale / rec_scale
+
+
+@pytest.mark.gpu
+def test_offsets_beyond_4_gib():
+    """A per-GPU shard of C5 is 8 GB: byte offsets into it do not fit 32 bits.  A 25 MB block of records is
+    laid out ~190 times (4.6 GiB); every counter must be that multiple of the block's, every hit tuple the
+    block's moved by a multiple of the block length (checker: the C oracle on ONE block), and the JSON text
+    rendered on the device from the resident 4.6 GiB must hold every list that many times over."""
+    import hashlib
+    from svjg import alnfilter, synth
+    from oracle import c_oracle as CO
+    CO.ensure_built()
+    g, vcf, gaf_text = synth.make_workload("C2", scale=0.05)
+    buf = io.StringIO()
+    g.write_gfa(buf)
+    edges_text, gfa_text = g.edges_json(), buf.getvalue()
+    block = np.frombuffer(gaf_text.encode(), dtype=np.uint8)
+    L = int(block.size)
+    K = int(float(os.environ.get("SVJG_TEST_BIG_GIB", "4.3")) * (1 << 30)) // L + 1
+    ct = CO.Tables(json.loads(edges_text), alt_len_from_gfa_text(gfa_text))
+    b_counts, b_stats, b_sv2, b_off, b_len = CO.filter_counts(ct, block.tobytes(), want_hits=True)
+    nb = int(b_stats["n_hits"])
+    assert nb > 1000
+    big = np.tile(block, K)
+    assert big.size == K * L and (big.size > (1 << 32) or "SVJG_TEST_BIG_GIB" in os.environ)
+    pinned = alnfilter.RegisteredBytes(big)
+    t = alnfilter.Tables.from_memory(edges_text, gfa_text).to_device(0)
+    # chunked route (64 MB pieces cut at line ends, hits with absolute offsets)
+    res = alnfilter.filter_host(t, big)
+    assert res.stats["n_records"] == K * b_stats["n_records"]
+    assert res.n_hits == K * nb
+    assert (res.counts.astype(np.uint64) == b_counts.astype(np.uint64) * K).all()
+    order = np.lexsort((res.hit_sv2, res.hit_off))
+    off = res.hit_off[order].astype(np.uint64)
+    sv2 = res.hit_sv2[order]
+    ln = res.hit_len[order]
+    # the block's tuples in file order (several tuples may share a line: sort both sides alike)
+    bo = np.lexsort((b_sv2, b_off))
+    w_off = (b_off[bo].astype(np.uint64)[None, :] + (np.arange(K, dtype=np.uint64) * np.uint64(L))[:, None]).ravel()
+    assert int(w_off.max()) > (1 << 32) or "SVJG_TEST_BIG_GIB" in os.environ
+    assert (off == w_off).all()
+    assert (sv2 == np.tile(b_sv2[bo], K)).all()
+    assert (ln == np.tile(b_len[bo], K)).all()
+    del res, order, off, sv2, ln, w_off
+    # whole-file-resident route with the text rendered on the device
+    res2, text = alnfilter.filter_json_host(t, big)
+    assert text is not None
+    assert (res2.counts.astype(np.uint64) == b_counts.astype(np.uint64) * K).all()
+    d = {}
+    view = memoryview(block.tobytes())
+    for s2, o, n in zip(b_sv2.tolist(), b_off.tolist(), b_len.tolist()):
+        d.setdefault(ct.sv_ids[s2 >> 1], [[], []])[s2 & 1].append(O.kept_text(str(view[o:o + n], "ascii")))
+
+    def pieces(times):
+        """json.dumps(d, sort_keys=True, indent=4) with every list `times` times over, key by key."""
+        def lst(elems):
+            if not elems:
+                return "        []"
+            return "        [\n" + ",\n".join(["            " + json.dumps(e) for e in elems] * times) + "\n        ]"
+        yield "{\n" if d else "{"
+        for i, key in enumerate(sorted(d)):
+            yield ("" if i == 0 else ",\n") + "    " + json.dumps(key) + ": [\n" + lst(d[key][0]) + ",\n" + lst(d[key][1]) + "\n    ]"
+        yield "\n}" if d else "}"
+    assert "".join(pieces(1)) == O.dumps_informative(d)                  # the helper writes what json.dumps writes
+    h = hashlib.sha256()
+    for piece in pieces(K):
+        h.update(piece.encode())
+    got = hashlib.sha256()
+    for i in range(0, len(text), 1 << 26):
+        got.update(text[i:i + (1 << 26)])
+    assert got.hexdigest() == h.hexdigest()
+    del pinned
