@@ -177,6 +177,12 @@ int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, 
 int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
                            svjg_filter_stats *stats);
 int svjg_filter_json_finish(svjg_tables *t, const char **json, uint64_t *json_len);
+/* The second half for a text that goes to a file (the `with open(...)` of filter-alignments.py:174-175): whole keys
+ * are rendered slice by slice (about `slice_bytes` each, 0 = 64 MiB), copied into one of two page-locked slices and
+ * written by a thread of its own while the next slice is rendered and copied; neither the device nor the host hold
+ * the whole text.  *json_len (may be NULL) = bytes written.  Declines like svjg_filter_json_finish (nothing is
+ * written then); a file that cannot be written: SVJG_E_IO, and what was written of it is removed. */
+int svjg_filter_json_write(svjg_tables *t, const char *path, uint64_t slice_bytes, uint64_t *json_len);
 
 /* Optional identity filter (an extension, off by default; the reference parses the identity of every alignment,
  * filter-alignments.py:193-196, and never uses it; predict-genotype.py:222 carries the gate commented out):

@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 #include "svjg_internal.h"
@@ -47,6 +50,10 @@ struct HostWs {
     uint64_t hits_per_gib = 0;                // what the last file needed: the first guess for the next one
     bool pending = false;                     // svjg_filter_json_begin done, svjg_filter_json_finish to come
     uint64_t pending_hits = 0;
+    // svjg_filter_json_write: two slices of the text on the device and two page-locked ones on the host
+    uint8_t *d_slice[2] = {nullptr, nullptr};
+    char *h_slice[2] = {nullptr, nullptr};
+    uint64_t slice_cap = 0;
 };
 
 void free_host_ws(svjg_tables *t) {
@@ -64,6 +71,10 @@ void free_host_ws(svjg_tables *t) {
     if (w->d_off64) cudaFree(w->d_off64);
     if (w->d_all) cudaFree(w->d_all);
     if (w->h_json) cudaFreeHost(w->h_json);
+    for (int i = 0; i < 2; ++i) {
+        if (w->d_slice[i]) cudaFree(w->d_slice[i]);
+        if (w->h_slice[i]) cudaFreeHost(w->h_slice[i]);
+    }
     if (w->s_copy) cudaStreamDestroy(w->s_copy);
     if (w->s_comp) cudaStreamDestroy(w->s_comp);
     delete w;
@@ -455,6 +466,152 @@ extern "C" int svjg_filter_json_finish(svjg_tables *t, const char **json, uint64
     SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
     *json = w->h_json;
     *json_len = len;
+    return SVJG_OK;
+}
+
+// The second half for a text that goes to a file: rendered key range by key range into one of two device slices,
+// copied to one of two page-locked slices and written from there by a thread of its own, so the slice behind it is
+// rendered and copied meanwhile.  Neither side ever holds the whole text (it is 10 x the GAF where records sit
+// in many lists); nothing is written where the renderer declines.
+extern "C" int svjg_filter_json_write(svjg_tables *t, const char *path, uint64_t slice_bytes, uint64_t *json_len) {
+    if (!t || !t->ws || !t->ws->pending) return set_error(SVJG_E_ARG, "svjg_filter_json_write: no svjg_filter_json_begin before it");
+    if (!path) return set_error(SVJG_E_ARG, "svjg_filter_json_write: NULL path");
+    SVJG_CUDA(cudaSetDevice(t->device));
+    HostWs *w = t->ws;
+    w->pending = false;
+    if (!slice_bytes) slice_bytes = 64ull << 20;
+    JsonPlan *plan = nullptr;
+    if (int rc = json_plan(t, w->d_all, w->d_hit[0], w->d_off64, w->d_hit[2], w->pending_hits, w->d_counts, &plan, w->s_comp)) {
+        cudaStreamSynchronize(w->s_comp);
+        return rc;
+    }
+    const uint32_t num_sv = json_plan_keys(plan);
+    std::vector<uint64_t> pos(size_t(num_sv) + 1), first_hit(size_t(num_sv) + 1);
+    int rc = json_plan_key_positions(plan, pos.data(), first_hit.data(), w->s_comp);
+    struct Slice {
+        uint32_t lo, hi;
+        uint64_t len;
+    };
+    std::vector<Slice> slices;
+    uint64_t max_len = 2;
+    if (!rc) {
+        // whole keys per slice, as many as fit slice_bytes (a key with more text than that is a slice of its own);
+        // the slice with the last key carries the two closing bytes
+        uint32_t lo = 0;
+        do {
+            uint32_t hi = uint32_t(std::upper_bound(pos.begin() + lo, pos.end(), pos[lo] + slice_bytes) - pos.begin()) - 1;
+            if (hi <= lo) hi = lo + 1;
+            if (hi > num_sv) hi = num_sv;
+            slices.push_back({lo, hi, pos[hi] - pos[lo] + (hi == num_sv ? 2u : 0u)});
+            max_len = std::max(max_len, slices.back().len);
+            lo = hi;
+        } while (lo < num_sv);
+        if (w->slice_cap < max_len) {
+            for (int i = 0; i < 2 && !rc; ++i) {
+                if (w->d_slice[i]) cudaFree(w->d_slice[i]);
+                if (w->h_slice[i]) cudaFreeHost(w->h_slice[i]);
+                w->d_slice[i] = nullptr, w->h_slice[i] = nullptr;
+            }
+            w->slice_cap = 0;
+            for (int i = 0; i < 2 && !rc; ++i) {
+                cudaError_t e = cudaMalloc(&w->d_slice[i], max_len);
+                if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&w->h_slice[i]), max_len, cudaHostAllocDefault);
+                if (e != cudaSuccess) rc = cuda_fail(int(e), "svjg_filter_json_write: slice buffers");
+            }
+            if (!rc) w->slice_cap = max_len;
+        }
+    }
+    FILE *f = rc ? nullptr : fopen(path, "wb");
+    if (!rc && !f) rc = set_error(SVJG_E_IO, std::string("cannot write ") + path);
+    if (rc) {
+        json_plan_free(plan, w->s_comp);
+        cudaStreamSynchronize(w->s_comp);
+        return rc;
+    }
+    cudaEvent_t rendered[2], copied[2];
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&rendered[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+    }
+    struct Job {
+        int buf;
+        uint64_t len;
+    };
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<Job> jobs;
+    bool no_more = false, buf_free[2] = {true, true}, io_failed = false;
+    cudaError_t copy_err = cudaSuccess;
+    const int device = t->device;
+    std::thread writer([&] {
+        cudaSetDevice(device);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return no_more || !jobs.empty(); });
+                if (jobs.empty()) return;
+                j = jobs.front();
+                jobs.pop_front();
+            }
+            const cudaError_t e = cudaEventSynchronize(copied[j.buf]);
+            const bool ok = e == cudaSuccess && !io_failed && fwrite(w->h_slice[j.buf], 1, size_t(j.len), f) == size_t(j.len);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (e != cudaSuccess) copy_err = e;
+                else if (!ok) io_failed = true;
+                buf_free[j.buf] = true;
+            }
+            cv.notify_all();
+        }
+    });
+    for (size_t i = 0; i < slices.size() && !rc; ++i) {
+        const int b = int(i & 1);
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return buf_free[b]; });
+            if (io_failed || copy_err != cudaSuccess) break;
+            buf_free[b] = false;
+        }
+        const Slice &sl = slices[i];
+        rc = json_render_range(plan, sl.lo, sl.hi, pos[sl.lo], first_hit[sl.lo], first_hit[sl.hi], w->d_slice[b], w->s_comp);
+        cudaError_t e = rc ? cudaSuccess : cudaEventRecord(rendered[b], w->s_comp);
+        if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(w->s_copy, rendered[b], 0);
+        if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(w->h_slice[b], w->d_slice[b], sl.len, cudaMemcpyDeviceToHost, w->s_copy);
+        if (e == cudaSuccess && !rc) e = cudaEventRecord(copied[b], w->s_copy);
+        if (e != cudaSuccess) rc = cuda_fail(int(e), "svjg_filter_json_write: slice");
+        if (rc) {
+            std::lock_guard<std::mutex> lk(m);
+            buf_free[b] = true;
+            break;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            jobs.push_back({b, sl.len});
+        }
+        cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(m);
+        no_more = true;
+    }
+    cv.notify_all();
+    writer.join();
+    cudaStreamSynchronize(w->s_copy);
+    json_plan_free(plan, w->s_comp);
+    cudaStreamSynchronize(w->s_comp);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(rendered[i]);
+        cudaEventDestroy(copied[i]);
+    }
+    const bool closed = fclose(f) == 0;
+    if (!rc && copy_err != cudaSuccess) rc = cuda_fail(int(copy_err), "svjg_filter_json_write: copy");
+    if (!rc && (io_failed || !closed)) rc = set_error(SVJG_E_IO, std::string("cannot write ") + path);
+    if (rc) {
+        remove(path);
+        return rc;
+    }
+    if (json_len) *json_len = pos[num_sv] + 2;
     return SVJG_OK;
 }
 

@@ -217,18 +217,21 @@ __device__ __forceinline__ void put(uint8_t *dst, const char *s, uint32_t n) {
 }
 
 // 5a: the framing of every key that has something: ',\n    "key": [\n        ' ... '\n    ]'
-__global__ void render_keys(const uint64_t *seg, const uint64_t *epos, const uint64_t *kpos, KeyText kt, uint32_t num_sv, uint8_t *out) {
-    const uint32_t sv = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sv > num_sv) return;
-    if (sv == num_sv) {                                           // the end of the file
-        const uint64_t total = kpos[num_sv];
-        if (total) put(out + total, "\n}", 2);
+// Keys [sv_lo, sv_hi) go to out[position - base]; the thread behind the last key of all closes the file.
+__global__ void render_keys(const uint64_t *seg, const uint64_t *epos, const uint64_t *kpos, KeyText kt, uint32_t num_sv, uint32_t sv_lo,
+                            uint32_t sv_hi, uint64_t base, uint8_t *out) {
+    const uint32_t sv = sv_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (sv > sv_hi) return;
+    if (sv == sv_hi) {
+        if (sv_hi != num_sv) return;
+        const uint64_t total = kpos[num_sv];                       // the end of the file
+        if (total) put(out + (total - base), "\n}", 2);
         else put(out, "{}", 2);
         return;
     }
     const uint64_t s0 = seg[2 * sv], s1 = seg[2 * sv + 1], s2 = seg[2 * sv + 2];
     if (s2 == s0) return;
-    uint8_t *p = out + kpos[sv];
+    uint8_t *p = out + (kpos[sv] - base);
     put(p, kpos[sv] ? ",\n    " : "{\n    ", 6);
     p += 6;
     const uint32_t kb = kt.off[sv], kn = kt.off[sv + 1] - kb;
@@ -257,18 +260,19 @@ __global__ void render_keys(const uint64_t *seg, const uint64_t *epos, const uin
     put(p, "\n    ]", 6);
 }
 
-// 5b: one warp per hit: '[\n' or ',\n' + 12 blanks, then the line as a JSON string
+// 5b: one warp per hit: '[\n' or ',\n' + 12 blanks, then the line as a JSON string.  Hits [h_lo, h_hi) of the
+// ordered list (= the hits of a range of keys) go to out[position - base].
 __global__ void __launch_bounds__(T) render_hits(const uint8_t *gaf, const uint64_t *r_off, const uint32_t *r_len, const uint32_t *r_key,
-                                                 uint64_t n, const uint64_t *seg, const uint64_t *epos, const uint64_t *kpos, KeyText kt,
-                                                 uint8_t *out) {
-    const uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+                                                 uint64_t h_lo, uint64_t h_hi, const uint64_t *seg, const uint64_t *epos, const uint64_t *kpos,
+                                                 KeyText kt, uint64_t base, uint8_t *out) {
+    const uint64_t i = h_lo + ((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31;
-    if (i >= n) return;
+    if (i >= h_hi) return;
     const uint32_t k = r_key[i], sv = k >> 1;
     const uint64_t s0 = seg[2 * sv], s1 = seg[2 * sv + 1], lb = seg[k];
     uint64_t at = kpos[sv] + 6 + (kt.off[sv + 1] - kt.off[sv]) + 12;                          // the first list
     if (k & 1u) at += (s1 > s0 ? epos[s1] - epos[s0] + 10 : 2) + 10;                          // ... the second
-    uint8_t *dst = out + at + (epos[i] - epos[lb]);
+    uint8_t *dst = out + (at + (epos[i] - epos[lb]) - base);
     if (lane < 14) dst[lane] = lane == 0 ? (i == lb ? '[' : ',') : (lane == 1 ? '\n' : ' ');
     if (lane == 14) dst[14] = '"';
     dst += 15;
@@ -373,12 +377,30 @@ void free_json_keys(svjg_tables *t) {
     t->json_keys = nullptr;
 }
 
-// Renders the text into *d_out (cudaMallocAsync on `st`, the caller frees it with cudaFreeAsync) from hits in
-// DEVICE memory; *out_len on the host after the call (it synchronises `st` once to learn the size).
-// d_counts must be the counters the same filter pass(es) produced: they are the list lengths.
-int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
-                       const uint32_t *d_hit_len, uint64_t n_hits, const uint32_t *d_counts, uint8_t **d_out, uint64_t *out_len,
-                       cudaStream_t st) {
+// ---- the plan of a rendering: everything up to the sizes (steps 1-4); the text itself is rendered from it whole
+// (json_render_device) or key range by key range (json_render_range)
+struct JsonPlan {
+    uint8_t *ws = nullptr;            // one stream-ordered allocation holding the arrays below
+    uint64_t *seg = nullptr, *epos = nullptr, *kpos = nullptr;
+    uint64_t *r_off = nullptr;
+    uint32_t *r_len = nullptr, *r_key = nullptr;
+    const uint8_t *d_gaf = nullptr;
+    KeyText kt{};
+    uint32_t num_sv = 0;
+    uint64_t n_hits = 0;
+    uint64_t total = 0;               // bytes of the text without the closing "\n}" (or "{}" of an empty dictionary)
+};
+
+void json_plan_free(JsonPlan *plan, cudaStream_t st) {
+    if (!plan) return;
+    if (plan->ws) cudaFreeAsync(plan->ws, st);
+    delete plan;
+}
+
+// Steps 1-4 on `st` from hits in DEVICE memory; synchronises `st` once to learn the size and whether the renderer
+// declines.  d_counts must be the counters the same filter pass(es) produced: they are the list lengths.
+int json_plan(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off, const uint32_t *d_hit_len,
+              uint64_t n_hits, const uint32_t *d_counts, JsonPlan **out_plan, cudaStream_t st) {
     const uint32_t num_sv = uint32_t(t->sv_ids.size());
     const uint64_t n2 = uint64_t(num_sv) * 2;
     if (!t->json_keys) {
@@ -400,28 +422,38 @@ int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_h
     }
     const KeyText kt{t->json_keys->d_blob, t->json_keys->d_off};
 
-    // scratch: segments [n2 + 1], cursors [n2], scattered + ranked hit arrays, element positions [n + 1],
-    // key positions [num_sv + 1], scan block sums, flags
+    // one allocation: segments [n2 + 1], element positions [n + 1], key positions [num_sv + 1], ranked hits -- kept
+    // for the rendering -- then cursors [n2], scattered hits, scan block sums, flags
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const uint64_t n = n_hits;
-    const size_t o_seg = 0, o_cur = o_seg + up((n2 + 1) * 8), o_soff = o_cur + up(n2 * 4), o_slen = o_soff + up(n * 8),
-                 o_roff = o_slen + up(n * 4), o_rlen = o_roff + up(n * 8), o_rkey = o_rlen + up(n * 4), o_epos = o_rkey + up(n * 4),
-                 o_kpos = o_epos + up((n + 1) * 8), o_tmp = o_kpos + up((size_t(num_sv) + 1) * 8),
+    const size_t o_seg = 0, o_epos = o_seg + up((n2 + 1) * 8), o_kpos = o_epos + up((n + 1) * 8),
+                 o_roff = o_kpos + up((size_t(num_sv) + 1) * 8), o_rlen = o_roff + up(n * 8), o_rkey = o_rlen + up(n * 4),
+                 o_cur = o_rkey + up(n * 4), o_soff = o_cur + up(n2 * 4), o_slen = o_soff + up(n * 8), o_tmp = o_slen + up(n * 4),
                  o_flags = o_tmp + up((std::max<uint64_t>(n, n2) / SCAN_BLOCK + 4) * 8), total = o_flags + 256;
     uint8_t *ws = nullptr;
     if (cudaError_t me = cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st)) {
-        if (me != cudaErrorMemoryAllocation) return cuda_fail(int(me), "json_render_device: scratch");
+        if (me != cudaErrorMemoryAllocation) return cuda_fail(int(me), "json_plan: scratch");
         cudaGetLastError();                                       // not sticky: the host emitter takes over
         return set_error(SVJG_E_UNSUPPORTED, "no device memory for the renderer's scratch: the host emitter writes the text");
     }
-    uint64_t *seg = reinterpret_cast<uint64_t *>(ws + o_seg), *s_off = reinterpret_cast<uint64_t *>(ws + o_soff),
-             *r_off = reinterpret_cast<uint64_t *>(ws + o_roff), *epos = reinterpret_cast<uint64_t *>(ws + o_epos),
-             *kpos = reinterpret_cast<uint64_t *>(ws + o_kpos), *tmp = reinterpret_cast<uint64_t *>(ws + o_tmp);
+    JsonPlan *plan = new JsonPlan();
+    plan->ws = ws;
+    plan->seg = reinterpret_cast<uint64_t *>(ws + o_seg);
+    plan->epos = reinterpret_cast<uint64_t *>(ws + o_epos);
+    plan->kpos = reinterpret_cast<uint64_t *>(ws + o_kpos);
+    plan->r_off = reinterpret_cast<uint64_t *>(ws + o_roff);
+    plan->r_len = reinterpret_cast<uint32_t *>(ws + o_rlen);
+    plan->r_key = reinterpret_cast<uint32_t *>(ws + o_rkey);
+    plan->d_gaf = d_gaf;
+    plan->kt = kt;
+    plan->num_sv = num_sv;
+    plan->n_hits = n;
+    uint64_t *seg = plan->seg, *epos = plan->epos, *kpos = plan->kpos, *s_off = reinterpret_cast<uint64_t *>(ws + o_soff),
+             *tmp = reinterpret_cast<uint64_t *>(ws + o_tmp);
     uint32_t *cursor = reinterpret_cast<uint32_t *>(ws + o_cur), *s_len = reinterpret_cast<uint32_t *>(ws + o_slen),
-             *r_len = reinterpret_cast<uint32_t *>(ws + o_rlen), *r_key = reinterpret_cast<uint32_t *>(ws + o_rkey),
              *flags = reinterpret_cast<uint32_t *>(ws + o_flags);
     auto fail = [&](int rc) {
-        cudaFreeAsync(ws, st);
+        json_plan_free(plan, st);
         return rc;
     };
     auto blocks = [](uint64_t items) { return unsigned(std::max<uint64_t>(1, (items + T - 1) / T)); };
@@ -431,8 +463,8 @@ int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_h
     exclusive_scan(seg, n2, tmp, st);
     if (n) {
         scatter_hits<<<blocks(n), T, 0, st>>>(d_hit_sv2, d_hit_off, d_hit_len, n, seg, cursor, s_off, s_len);
-        rank_hits<<<blocks(n2 * 32), T, 0, st>>>(seg, uint32_t(n2), s_off, s_len, r_off, r_len, r_key);
-        size_hits<<<blocks(n * 32), T, 0, st>>>(d_gaf, r_off, r_len, n, epos, flags);
+        rank_hits<<<blocks(n2 * 32), T, 0, st>>>(seg, uint32_t(n2), s_off, s_len, plan->r_off, plan->r_len, plan->r_key);
+        size_hits<<<blocks(n * 32), T, 0, st>>>(d_gaf, plan->r_off, plan->r_len, n, epos, flags);
     }
     exclusive_scan(epos, n, tmp, st);
     size_keys<<<blocks(num_sv), T, 0, st>>>(seg, epos, kt, num_sv, kpos);
@@ -443,25 +475,69 @@ int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_h
     cudaMemcpyAsync(&h_seg_total, seg + n2, 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&h_flags, flags, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return fail(cuda_fail(int(e), "json_render_device"));
+    if (e != cudaSuccess) return fail(cuda_fail(int(e), "json_plan"));
     if (h_seg_total != n) return fail(set_error(SVJG_E_ARG, "counters and hit list do not belong together"));
     if (h_flags & 1u) return fail(set_error(SVJG_E_UNSUPPORTED, "a stored line holds non-ASCII bytes: the host emitter decodes UTF-8"));
     if (h_flags & 2u) return fail(set_error(SVJG_E_UNSUPPORTED, "a list beyond 64 Ki entries: the host emitter sorts it"));
-    const uint64_t out_bytes = h_total + 2;
+    plan->total = h_total;
+    *out_plan = plan;
+    return SVJG_OK;
+}
+
+uint64_t json_plan_bytes(const JsonPlan *plan) { return plan->total + 2; }
+uint32_t json_plan_keys(const JsonPlan *plan) { return plan->num_sv; }
+
+// positions of the keys, on the host: pos[sv] .. pos[sv + 1] are the bytes of key sv in the text (none if it has no
+// hits), pos[num_sv] = the text without its closing two bytes; first_hit[sv] .. first_hit[sv + 1] its hits in the
+// ordered list.  Both arrays have num_sv + 1 entries.  Synchronises `st`.
+int json_plan_key_positions(const JsonPlan *plan, uint64_t *pos, uint64_t *first_hit, cudaStream_t st) {
+    const size_t n1 = size_t(plan->num_sv) + 1;
+    SVJG_CUDA(cudaMemcpyAsync(pos, plan->kpos, n1 * 8, cudaMemcpyDeviceToHost, st));
+    SVJG_CUDA(cudaMemcpy2DAsync(first_hit, 8, plan->seg, 16, 8, n1, cudaMemcpyDeviceToHost, st));     // seg[2 * sv]
+    SVJG_CUDA(cudaStreamSynchronize(st));
+    return SVJG_OK;
+}
+
+// Step 5 for the keys [sv_lo, sv_hi) = the hits [h_lo, h_hi) of the ordered list: their bytes [base, pos[sv_hi]) go to
+// d_out[0 ..), base = pos[sv_lo]; the range that ends with the last key also gets the two closing bytes.
+// Asynchronous on `st`.
+int json_render_range(const JsonPlan *plan, uint32_t sv_lo, uint32_t sv_hi, uint64_t base, uint64_t h_lo, uint64_t h_hi, uint8_t *d_out,
+                      cudaStream_t st) {
+    auto blocks = [](uint64_t items) { return unsigned(std::max<uint64_t>(1, (items + T - 1) / T)); };
+    render_keys<<<blocks(uint64_t(sv_hi - sv_lo) + 1), T, 0, st>>>(plan->seg, plan->epos, plan->kpos, plan->kt, plan->num_sv, sv_lo, sv_hi,
+                                                                    base, d_out);
+    if (h_hi > h_lo)
+        render_hits<<<blocks((h_hi - h_lo) * 32), T, 0, st>>>(plan->d_gaf, plan->r_off, plan->r_len, plan->r_key, h_lo, h_hi, plan->seg,
+                                                              plan->epos, plan->kpos, plan->kt, base, d_out);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return cuda_fail(int(le), "json_render_range: launch");
+    return SVJG_OK;
+}
+
+// Renders the whole text into *d_out (cudaMallocAsync on `st`, the caller frees it with cudaFreeAsync) from hits in
+// DEVICE memory; *out_len on the host after the call.
+int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
+                       const uint32_t *d_hit_len, uint64_t n_hits, const uint32_t *d_counts, uint8_t **d_out, uint64_t *out_len,
+                       cudaStream_t st) {
+    JsonPlan *plan = nullptr;
+    if (int rc = json_plan(t, d_gaf, d_hit_sv2, d_hit_off, d_hit_len, n_hits, d_counts, &plan, st)) return rc;
+    const uint64_t out_bytes = json_plan_bytes(plan);
     uint8_t *out = nullptr;
-    e = cudaMallocAsync(reinterpret_cast<void **>(&out), out_bytes, st);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&out), out_bytes, st);
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
-        return fail(set_error(SVJG_E_UNSUPPORTED, "no device memory for the text: the host emitter writes it"));
+        json_plan_free(plan, st);
+        return set_error(SVJG_E_UNSUPPORTED, "no device memory for the text: the host emitter writes it");
     }
-    if (e != cudaSuccess) return fail(cuda_fail(int(e), "json_render_device: output buffer"));
-    render_keys<<<blocks(uint64_t(num_sv) + 1), T, 0, st>>>(seg, epos, kpos, kt, num_sv, out);
-    if (n) render_hits<<<blocks(n * 32), T, 0, st>>>(d_gaf, r_off, r_len, r_key, n, seg, epos, kpos, kt, out);
-    cudaError_t le = cudaGetLastError();
-    cudaFreeAsync(ws, st);
-    if (le != cudaSuccess) {
+    if (e != cudaSuccess) {
+        json_plan_free(plan, st);
+        return cuda_fail(int(e), "json_render_device: output buffer");
+    }
+    const int rc = json_render_range(plan, 0, plan->num_sv, 0, 0, plan->n_hits, out, st);
+    json_plan_free(plan, st);
+    if (rc) {
         cudaFreeAsync(out, st);
-        return cuda_fail(int(le), "json_render_device: launch");
+        return rc;
     }
     *d_out = out;
     *out_len = out_bytes;

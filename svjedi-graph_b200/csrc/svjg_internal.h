@@ -11,6 +11,7 @@
 namespace svjg {
 struct HostWs;
 struct JsonKeys;
+struct JsonPlan;
 }
 
 struct svjg_tables {
@@ -41,6 +42,15 @@ void free_json_keys(svjg_tables *t);
 int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
                        const uint32_t *d_hit_len, uint64_t n_hits, const uint32_t *d_counts, uint8_t **d_out, uint64_t *out_len,
                        cudaStream_t st);
+// the same in steps, for a text that leaves the device slice by slice (json.cu; see there)
+int json_plan(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off, const uint32_t *d_hit_len,
+              uint64_t n_hits, const uint32_t *d_counts, JsonPlan **out_plan, cudaStream_t st);
+uint64_t json_plan_bytes(const JsonPlan *plan);
+uint32_t json_plan_keys(const JsonPlan *plan);
+int json_plan_key_positions(const JsonPlan *plan, uint64_t *pos, uint64_t *first_hit, cudaStream_t st);
+int json_render_range(const JsonPlan *plan, uint32_t sv_lo, uint32_t sv_hi, uint64_t base, uint64_t h_lo, uint64_t h_hi, uint8_t *d_out,
+                      cudaStream_t st);
+void json_plan_free(JsonPlan *plan, cudaStream_t st);
 // svjg_filter_device with absolute 64-bit hit offsets (d_hit_off64 != NULL); filter.cu
 int filter_device_abs(const svjg_tables *t, const uint8_t *d_gaf, uint64_t n_bytes, uint64_t base_offset, int64_t d_over,
                       uint32_t *d_counts, uint32_t *d_hit_sv2, uint32_t *d_hit_off, uint64_t *d_hit_off64, uint32_t *d_hit_len,

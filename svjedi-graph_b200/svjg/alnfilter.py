@@ -328,6 +328,18 @@ def filter_json_finish(tables):
     return memoryview((C.c_char * ln.value).from_address(p.value)) if ln.value else memoryview(b"")
 
 
+def filter_json_write(tables, path, slice_bytes=0):
+    """Second half, to a file (svjg_filter_json_write): the text leaves the device in slices of whole keys that are
+    written while the next one is rendered and copied; neither side holds the whole text.  Returns the bytes
+    written, or None where the device renderer declines (nothing is written then)."""
+    ln = C.c_uint64()
+    rc = capi.lib.svjg_filter_json_write(tables._h, os.fsencode(path), int(slice_bytes), C.byref(ln))
+    if rc == capi.E_UNSUPPORTED:
+        return None
+    capi.check(rc)
+    return int(ln.value)
+
+
 def filter_stream(tables, fileobj, chunk_bytes=16 << 20, d_over=D_OVER):
     """the filter fed from a pipe (``minigraph ... | filter-alignments.py -a
     /dev/stdin``) while the mapper is still writing.  The stream is read straight into PAGE-LOCKED buffers

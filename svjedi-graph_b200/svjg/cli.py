@@ -96,7 +96,7 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
             gaf = alnfilter.read_file_pinned(gaf_file)
             if alnfilter.translate_newlines(gaf) is not gaf:               # carriage returns: text-mode line ends
                 gaf = alnfilter.RegisteredBytes(alnfilter.translate_newlines(gaf))
-    text = None
+    written = None                      # bytes of the JSON file where the device has written it
     n_gpus = _n_gpus()
     if stream is not None:
         res, gaf = alnfilter.filter_stream(tables, stream, d_over=d_over)
@@ -106,20 +106,21 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
     elif min_identity is not None:
         res = alnfilter.filter_host(tables, gaf, d_over=d_over)                # the hit list on the host: it is thinned below
     else:
-        # the text of informative_aln.json is assembled on the device and comes back as text; the host emitter
-        # takes over where the device renderer declines (non-ASCII bytes in a stored line, a giant list)
-        res, text = alnfilter.filter_json_host(tables, gaf, d_over=d_over)
-        _lap("filter + JSON text")
-        if text is None:
+        # the text of informative_aln.json is assembled on the device and written slice by slice as it comes back;
+        # the host emitter takes over where the device renderer declines (non-ASCII bytes in a stored line, a giant list)
+        res = alnfilter.filter_json_begin(tables, gaf, d_over=d_over)
+        _lap("filter")
+        if res is None:                                                        # the file does not fit the device
             res = alnfilter.filter_host(tables, gaf, d_over=d_over)
+        elif not (dover_given and res.stats["n_checks"] > 0):                  # (-O: the reference stops before it writes)
+            written = alnfilter.filter_json_write(tables, out_json)
+            if written is None:
+                res = alnfilter.filter_host(tables, gaf, d_over=d_over)
     if min_identity is not None:
         res = alnfilter.apply_min_identity(tables, gaf, res, min_identity)
     if dover_given and res.stats["n_checks"] > 0:
         _die("-O/--dover makes the reference fail at its first breakpoint-overlap test (TypeError); same here")
-    if text is not None:
-        with open(out_json, "wb") as fh:
-            fh.write(text)
-    else:
+    if written is None:
         alnfilter.write_informative_json(tables, gaf, res, out_json)
     _lap("JSON file written")
     return res, gaf

@@ -119,3 +119,50 @@ def test_full_c2_batch_equals_host_emitter(gpu, tmp_path):
         for block in iter(lambda: fh.read(1 << 24), b""):
             h.update(block)
     assert text is not None and hashlib.sha256(text).hexdigest() == h.hexdigest()
+
+
+@pytest.mark.parametrize("tag,slice_bytes", [("c1", 0), ("c1", 1), ("c1", 4096), ("s2", 1 << 16), ("s3", 1 << 20), ("s4", 3000)])
+def test_sliced_file_equals_the_text_in_one_piece(gpu, tmp_path, tag, slice_bytes):
+    """svjg_filter_json_write: the text rendered key range by key range into slices (of one key each at
+    slice_bytes = 1) and written by the library -- the same bytes as the one-piece rendering and as the
+    reference's file."""
+    alnfilter, capi = gpu
+    t = _tables(alnfilter, tag)
+    gaf = read_golden(f"{tag}.gaf.gz").encode()
+    _, text = alnfilter.filter_json_host(t, gaf)
+    whole = bytes(text)
+    res = alnfilter.filter_json_begin(t, gaf)
+    out = tmp_path / "sliced.json"
+    n = alnfilter.filter_json_write(t, str(out), slice_bytes)
+    got = out.read_bytes()
+    assert n == len(got) == len(whole) and got == whole
+    if tag == "c1":
+        assert got == read_golden("c1_informative_aln.json.gz").encode()
+    assert res.n_hits > 0
+
+
+def test_sliced_file_corner_cases(gpu, tmp_path):
+    alnfilter, capi = gpu
+    t = _tables(alnfilter, "s2")
+    out = tmp_path / "x.json"
+    # nothing appended at all: "{}"
+    alnfilter.filter_json_begin(t, b"")
+    assert alnfilter.filter_json_write(t, str(out), 64) == 2 and out.read_bytes() == b"{}"
+    # no second half without a first
+    with pytest.raises(capi.SvjgError):
+        alnfilter.filter_json_write(t, str(out))
+    # a path that cannot be written: an error, no file
+    gaf = read_golden("s2.gaf.gz").encode()
+    alnfilter.filter_json_begin(t, gaf)
+    with pytest.raises(capi.SvjgError):
+        alnfilter.filter_json_write(t, str(tmp_path / "no_such_dir" / "x.json"))
+    # a stored line with a non-ASCII byte: the renderer declines and writes nothing
+    lines = gaf.split(b"\n")
+    res0 = alnfilter.filter_host(t, gaf)
+    first = int(np.sort(res0.hit_off)[0])
+    k = gaf[:first].count(b"\n")
+    lines[k] = lines[k] + b"\txx:Z:\xc3\xa9"
+    odd = b"\n".join(lines)
+    out2 = tmp_path / "y.json"
+    assert alnfilter.filter_json_begin(t, odd) is not None
+    assert alnfilter.filter_json_write(t, str(out2)) is None and not out2.exists()

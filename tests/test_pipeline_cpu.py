@@ -61,7 +61,7 @@ def test_orchestrator_files_and_order(tmp_path, monkeypatch, capfd, streamed):
 
     monkeypatch.setattr(cli, "_load_tables", load_tables)
     monkeypatch.setattr(alnfilter, "filter_host", filter_host)
-    monkeypatch.setattr(alnfilter, "filter_json_host", lambda tables, gaf, **kw: (None, None))   # no device: the host route
+    monkeypatch.setattr(alnfilter, "filter_json_begin", lambda tables, gaf, **kw: None)   # no device: the host route
     monkeypatch.setattr(alnfilter, "read_file_pinned", lambda path: np.fromfile(path, dtype=np.uint8))
     monkeypatch.setattr(genotype, "genotype_host", stand_in_genotype_host)
     monkeypatch.chdir(tmp_path)
@@ -125,7 +125,7 @@ def test_filter_command_line_wiring(tmp_path, monkeypatch):
     monkeypatch.setattr(cli, "_start_device", lambda: (lambda: None))
     monkeypatch.setattr(cli, "_load_tables", lambda pfx, gfa, ready=None: alnfilter.Tables.load(pfx + "_svs_edges.json", gfa))
     monkeypatch.setattr(alnfilter, "filter_host", filter_host)
-    monkeypatch.setattr(alnfilter, "filter_json_host", lambda tables, gaf, **kw: (None, None))   # no device: the host route
+    monkeypatch.setattr(alnfilter, "filter_json_begin", lambda tables, gaf, **kw: None)   # no device: the host route
     # page-locking needs the CUDA runtime: keep the wrapper, skip the registration
     monkeypatch.setattr(alnfilter.RegisteredBytes, "__init__", lambda self, array: (setattr(self, "array", array), setattr(self, "_reg", False)) and None)
     monkeypatch.chdir(tmp_path)
@@ -185,7 +185,7 @@ def test_streamed_input_equals_the_whole_file(monkeypatch):
 
     monkeypatch.setattr(alnfilter, "filter_host", filter_host)
 
-    monkeypatch.setattr(alnfilter, "filter_json_host", lambda tables, gaf, **kw: (None, None))   # no device: the host route
+    monkeypatch.setattr(alnfilter, "filter_json_begin", lambda tables, gaf, **kw: None)   # no device: the host route
     whole_bytes = bytes(alnfilter._as_u8(alnfilter.translate_newlines(np.frombuffer(raw, np.uint8))))
     whole = filter_host(t, whole_bytes)
     assert whole.stats["n_hits"] > 50
@@ -257,7 +257,7 @@ def test_streamed_orchestrator_appends_and_reports_like_the_reference(tmp_path, 
 
     monkeypatch.setattr(cli, "_load_tables", lambda pfx, gfa, ready=None: alnfilter.Tables.load(pfx + "_svs_edges.json", gfa))
     monkeypatch.setattr(alnfilter, "filter_host", filter_host)
-    monkeypatch.setattr(alnfilter, "filter_json_host", lambda tables, gaf, **kw: (None, None))   # no device: the host route
+    monkeypatch.setattr(alnfilter, "filter_json_begin", lambda tables, gaf, **kw: None)   # no device: the host route
     monkeypatch.setattr(genotype, "genotype_host", stand_in_genotype_host)
     monkeypatch.chdir(tmp_path)
     (tmp_path / "run.gaf").write_text(old)                      # left over from an earlier run
@@ -279,7 +279,7 @@ def test_streamed_orchestrator_appends_and_reports_like_the_reference(tmp_path, 
     (tmp_path / "new.gaf").write_text(new + "only\tthree\tcolumns\n" + new)
     (tmp_path / "run.gaf").write_text("")
     monkeypatch.setattr(alnfilter, "filter_host", lambda *a, **k: (_ for _ in ()).throw(alnfilter.InputError("GAF line: fewer than 12 columns")))
-    monkeypatch.setattr(alnfilter, "filter_json_host", lambda tables, gaf, **kw: (None, None))   # no device: the host route
+    monkeypatch.setattr(alnfilter, "filter_json_begin", lambda tables, gaf, **kw: None)   # no device: the host route
     with pytest.raises(SystemExit) as exc:
         cli.pipeline_main(PKG, ["-v", "in.vcf", "-r", "ref.fa", "-q", "a.fq", "-p", prefix])
     assert str(exc.value.code).startswith("Failed to filter the alignments.")
