@@ -177,6 +177,15 @@ int svjg_filter_json_host(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, 
 int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
                            svjg_filter_stats *stats);
 int svjg_filter_json_finish(svjg_tables *t, const char **json, uint64_t *json_len);
+/* One file on several devices: range k of the file (cut at line ends, in file order) goes through
+ * svjg_filter_json_begin_at with the tables on device k -- `gaf` points at the range, `base` is its offset in the
+ * file, hits carry file offsets; one host thread per device.  svjg_filter_json_gather then copies the hit tuples of
+ * devices 1.. to device 0 (peer copies), uploads the counters the caller has summed, and lets ts[0]'s
+ * svjg_filter_json_finish / _write render the whole text, reading every line where it lies: device 0's memory or a
+ * peer's over NVLink.  At most 8 ranges.  SVJG_E_UNSUPPORTED: no peer access between the devices. */
+int svjg_filter_json_begin_at(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, uint64_t base, int64_t d_over,
+                              uint32_t *counts, svjg_filter_stats *stats);
+int svjg_filter_json_gather(svjg_tables **ts, int n, const uint32_t *counts_sum);
 /* The second half for a text that goes to a file (the `with open(...)` of filter-alignments.py:174-175): whole keys
  * are rendered slice by slice (about `slice_bytes` each, 0 = 64 MiB), copied into one of two page-locked slices and
  * written by a thread of its own while the next slice is rendered and copied; neither the device nor the host hold

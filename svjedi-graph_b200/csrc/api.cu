@@ -50,6 +50,8 @@ struct HostWs {
     uint64_t hits_per_gib = 0;                // what the last file needed: the first guess for the next one
     bool pending = false;                     // svjg_filter_json_begin done, svjg_filter_json_finish to come
     uint64_t pending_hits = 0;
+    uint64_t range_base = 0;                  // file offset of the bytes in d_all (svjg_filter_json_begin_at)
+    LineSrc src{};                            // where the renderer finds the lines: d_all, or several devices' after a gather
     // svjg_filter_json_write: two slices of the text on the device and two page-locked ones on the host
     uint8_t *d_slice[2] = {nullptr, nullptr};
     char *h_slice[2] = {nullptr, nullptr};
@@ -354,6 +356,11 @@ static int ensure_hit_arrays(HostWs *w, uint64_t hit_cap) {
 
 extern "C" int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, int64_t d_over, uint32_t *counts,
                                       svjg_filter_stats *stats) {
+    return svjg_filter_json_begin_at(t, gaf, n_bytes, 0, d_over, counts, stats);
+}
+
+extern "C" int svjg_filter_json_begin_at(svjg_tables *t, const uint8_t *gaf, uint64_t n_bytes, uint64_t base, int64_t d_over,
+                                         uint32_t *counts, svjg_filter_stats *stats) {
     if (!t || t->device < 0) return set_error(SVJG_E_ARG, "svjg_filter_json_host: tables are not on a device");
     if (!counts || !stats || (n_bytes && !gaf)) return set_error(SVJG_E_ARG, "svjg_filter_json_host: NULL argument");
     SVJG_CUDA(cudaSetDevice(t->device));
@@ -405,8 +412,8 @@ extern "C" int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64
                 SVJG_CUDA(cudaEventRecord(up_done, w->s_copy));
                 SVJG_CUDA(cudaStreamWaitEvent(w->s_comp, up_done, 0));
             }
-            rc = filter_device_abs(t, w->d_all + cut[k], len, cut[k], d_over, w->d_counts, w->d_hit[0], nullptr, w->d_off64, w->d_hit[2],
-                                   w->hit_cap, w->d_stats, w->s_comp, true);
+            rc = filter_device_abs(t, w->d_all + cut[k], len, base + cut[k], d_over, w->d_counts, w->d_hit[0], nullptr, w->d_off64,
+                                   w->d_hit[2], w->hit_cap, w->d_stats, w->s_comp, true);
             if (rc) {
                 cudaStreamSynchronize(w->s_copy);
                 cudaStreamSynchronize(w->s_comp);
@@ -432,6 +439,80 @@ extern "C" int svjg_filter_json_begin(svjg_tables *t, const uint8_t *gaf, uint64
     SVJG_CUDA(cudaStreamSynchronize(w->s_comp));
     w->pending_hits = stats->n_hits;
     w->pending = true;
+    w->range_base = base;
+    w->src = LineSrc{};
+    w->src.n = 1;
+    w->src.base[0] = w->d_all;
+    w->src.start[0] = base;
+    return SVJG_OK;
+}
+
+// Ranges of one file filtered on several devices (svjg_filter_json_begin_at, range k on ts[k], in file order): the hit
+// tuples of devices 1.. are copied to device 0 (peer copies), the summed counters uploaded there, and the renderer of
+// ts[0] (svjg_filter_json_finish / _write) reads every line where it lies -- its own memory or a peer's over NVLink.
+extern "C" int svjg_filter_json_gather(svjg_tables **ts, int n, const uint32_t *counts_sum) {
+    if (!ts || n < 1 || n > MAX_RANGES || !counts_sum) return set_error(SVJG_E_ARG, "svjg_filter_json_gather: bad argument");
+    for (int d = 0; d < n; ++d)
+        if (!ts[d] || !ts[d]->ws || !ts[d]->ws->pending || ts[d]->device < 0)
+            return set_error(SVJG_E_ARG, "svjg_filter_json_gather: a device without svjg_filter_json_begin_at before it");
+    HostWs *w0 = ts[0]->ws;
+    const int dev0 = ts[0]->device;
+    SVJG_CUDA(cudaSetDevice(dev0));
+    uint64_t total = 0;
+    for (int d = 0; d < n; ++d) {
+        if (d && ts[d]->ws->range_base < ts[d - 1]->ws->range_base)
+            return set_error(SVJG_E_ARG, "svjg_filter_json_gather: ranges out of file order");
+        total += ts[d]->ws->pending_hits;
+        if (d == 0 || ts[d]->device == dev0) continue;
+        int can = 0;
+        SVJG_CUDA(cudaDeviceCanAccessPeer(&can, dev0, ts[d]->device));
+        if (!can) return set_error(SVJG_E_UNSUPPORTED, "no peer access between the devices: the host emitter writes the text");
+        cudaError_t e = cudaDeviceEnablePeerAccess(ts[d]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return cuda_fail(int(e), "cudaDeviceEnablePeerAccess");
+    }
+    const uint64_t n0 = w0->pending_hits;
+    if (w0->hit_cap < total) {
+        // larger arrays that keep device 0's own tuples (sv2, offsets, lengths; d_hit[1] is not used on this route)
+        uint32_t *sv2 = nullptr, *len = nullptr;
+        uint64_t *off = nullptr;
+        const uint64_t cap = total + 1024;
+        SVJG_CUDA(cudaMalloc(&sv2, cap * 4));
+        SVJG_CUDA(cudaMalloc(&len, cap * 4));
+        SVJG_CUDA(cudaMalloc(&off, cap * 8));
+        SVJG_CUDA(cudaMemcpyAsync(sv2, w0->d_hit[0], n0 * 4, cudaMemcpyDeviceToDevice, w0->s_comp));
+        SVJG_CUDA(cudaMemcpyAsync(len, w0->d_hit[2], n0 * 4, cudaMemcpyDeviceToDevice, w0->s_comp));
+        SVJG_CUDA(cudaMemcpyAsync(off, w0->d_off64, n0 * 8, cudaMemcpyDeviceToDevice, w0->s_comp));
+        SVJG_CUDA(cudaStreamSynchronize(w0->s_comp));
+        SVJG_CUDA(cudaFree(w0->d_hit[0]));
+        SVJG_CUDA(cudaFree(w0->d_hit[2]));
+        SVJG_CUDA(cudaFree(w0->d_off64));
+        if (w0->d_hit[1]) SVJG_CUDA(cudaFree(w0->d_hit[1]));
+        w0->d_hit[1] = nullptr;
+        SVJG_CUDA(cudaMalloc(&w0->d_hit[1], cap * 4));
+        w0->d_hit[0] = sv2, w0->d_hit[2] = len, w0->d_off64 = off;
+        w0->hit_cap = cap;
+    }
+    LineSrc src{};
+    src.n = uint32_t(n);
+    uint64_t at = 0;
+    for (int d = 0; d < n; ++d) {
+        HostWs *w = ts[d]->ws;
+        src.base[d] = w->d_all;
+        src.start[d] = w->range_base;
+        const uint64_t nh = w->pending_hits;
+        if (d && nh) {
+            SVJG_CUDA(cudaMemcpyPeerAsync(w0->d_hit[0] + at, dev0, w->d_hit[0], ts[d]->device, nh * 4, w0->s_comp));
+            SVJG_CUDA(cudaMemcpyPeerAsync(w0->d_hit[2] + at, dev0, w->d_hit[2], ts[d]->device, nh * 4, w0->s_comp));
+            SVJG_CUDA(cudaMemcpyPeerAsync(w0->d_off64 + at, dev0, w->d_off64, ts[d]->device, nh * 8, w0->s_comp));
+        }
+        at += nh;
+        if (d) w->pending = false;
+    }
+    SVJG_CUDA(cudaMemcpyAsync(w0->d_counts, counts_sum, ts[0]->sv_ids.size() * 8, cudaMemcpyHostToDevice, w0->s_comp));
+    SVJG_CUDA(cudaStreamSynchronize(w0->s_comp));
+    w0->pending_hits = total;
+    w0->src = src;
     return SVJG_OK;
 }
 
@@ -443,7 +524,7 @@ extern "C" int svjg_filter_json_finish(svjg_tables *t, const char **json, uint64
     w->pending = false;
     uint8_t *d_text = nullptr;
     uint64_t len = 0;
-    int rc = json_render_device(t, w->d_all, w->d_hit[0], w->d_off64, w->d_hit[2], w->pending_hits, w->d_counts, &d_text, &len, w->s_comp);
+    int rc = json_render_device(t, w->src, w->d_hit[0], w->d_off64, w->d_hit[2], w->pending_hits, w->d_counts, &d_text, &len, w->s_comp);
     if (rc) {
         cudaStreamSynchronize(w->s_comp);
         return rc;
@@ -481,7 +562,7 @@ extern "C" int svjg_filter_json_write(svjg_tables *t, const char *path, uint64_t
     w->pending = false;
     if (!slice_bytes) slice_bytes = 64ull << 20;
     JsonPlan *plan = nullptr;
-    if (int rc = json_plan(t, w->d_all, w->d_hit[0], w->d_off64, w->d_hit[2], w->pending_hits, w->d_counts, &plan, w->s_comp)) {
+    if (int rc = json_plan(t, w->src, w->d_hit[0], w->d_off64, w->d_hit[2], w->pending_hits, w->d_counts, &plan, w->s_comp)) {
         cudaStreamSynchronize(w->s_comp);
         return rc;
     }

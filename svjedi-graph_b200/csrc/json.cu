@@ -154,6 +154,13 @@ __global__ void rank_hits(const uint64_t *seg, uint32_t n2, const uint64_t *s_of
     }
 }
 
+// the bytes of the file at offset `off`: in the range that holds it (this device's memory or a peer's)
+__device__ __forceinline__ const uint8_t *line_ptr(const LineSrc &s, uint64_t off) {
+    uint32_t k = 0;
+    for (uint32_t j = 1; j < s.n; ++j) k += off >= s.start[j];
+    return s.base[k] + (off - s.start[k]);
+}
+
 // bytes a byte takes inside a JSON string (json.dumps, ensure_ascii); 0 = not restated here (non-ASCII)
 __device__ __forceinline__ uint32_t json_width(uint32_t c) {
     if (c >= 0x80u) return 0u;
@@ -163,12 +170,12 @@ __device__ __forceinline__ uint32_t json_width(uint32_t c) {
 
 // 3: one warp per hit (in list order): where "cg:Z:" cuts the line, and the size of its element:
 // 14 bytes of separator and indent + two quotes + the escaped text
-__global__ void __launch_bounds__(T) size_hits(const uint8_t *gaf, const uint64_t *r_off, uint32_t *r_len, uint64_t n, uint64_t *esz,
+__global__ void __launch_bounds__(T) size_hits(const LineSrc gaf, const uint64_t *r_off, uint32_t *r_len, uint64_t n, uint64_t *esz,
                                                uint32_t *flags) {
     const uint64_t i = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (i >= n) return;
-    const uint8_t *p = gaf + r_off[i];
+    const uint8_t *p = line_ptr(gaf, r_off[i]);
     uint32_t len = r_len[i];
     // the first "cg:Z:" (line.split("cg:Z:")[0], :166)
     uint32_t cut = len;
@@ -262,7 +269,7 @@ __global__ void render_keys(const uint64_t *seg, const uint64_t *epos, const uin
 
 // 5b: one warp per hit: '[\n' or ',\n' + 12 blanks, then the line as a JSON string.  Hits [h_lo, h_hi) of the
 // ordered list (= the hits of a range of keys) go to out[position - base].
-__global__ void __launch_bounds__(T) render_hits(const uint8_t *gaf, const uint64_t *r_off, const uint32_t *r_len, const uint32_t *r_key,
+__global__ void __launch_bounds__(T) render_hits(const LineSrc gaf, const uint64_t *r_off, const uint32_t *r_len, const uint32_t *r_key,
                                                  uint64_t h_lo, uint64_t h_hi, const uint64_t *seg, const uint64_t *epos, const uint64_t *kpos,
                                                  KeyText kt, uint64_t base, uint8_t *out) {
     const uint64_t i = h_lo + ((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(T) render_hits(const uint8_t *gaf, const uint6
     if (lane < 14) dst[lane] = lane == 0 ? (i == lb ? '[' : ',') : (lane == 1 ? '\n' : ' ');
     if (lane == 14) dst[14] = '"';
     dst += 15;
-    const uint8_t *p = gaf + r_off[i];
+    const uint8_t *p = line_ptr(gaf, r_off[i]);
     const uint32_t len = r_len[i];
     auto hex = [](uint32_t h) { return uint8_t(h < 10u ? '0' + h : 'a' + h - 10u); };
     for (uint32_t b0 = 0; b0 < len; b0 += 32) {
@@ -384,7 +391,7 @@ struct JsonPlan {
     uint64_t *seg = nullptr, *epos = nullptr, *kpos = nullptr;
     uint64_t *r_off = nullptr;
     uint32_t *r_len = nullptr, *r_key = nullptr;
-    const uint8_t *d_gaf = nullptr;
+    LineSrc src{};
     KeyText kt{};
     uint32_t num_sv = 0;
     uint64_t n_hits = 0;
@@ -399,7 +406,7 @@ void json_plan_free(JsonPlan *plan, cudaStream_t st) {
 
 // Steps 1-4 on `st` from hits in DEVICE memory; synchronises `st` once to learn the size and whether the renderer
 // declines.  d_counts must be the counters the same filter pass(es) produced: they are the list lengths.
-int json_plan(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off, const uint32_t *d_hit_len,
+int json_plan(svjg_tables *t, const LineSrc &src, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off, const uint32_t *d_hit_len,
               uint64_t n_hits, const uint32_t *d_counts, JsonPlan **out_plan, cudaStream_t st) {
     const uint32_t num_sv = uint32_t(t->sv_ids.size());
     const uint64_t n2 = uint64_t(num_sv) * 2;
@@ -444,7 +451,7 @@ int json_plan(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, c
     plan->r_off = reinterpret_cast<uint64_t *>(ws + o_roff);
     plan->r_len = reinterpret_cast<uint32_t *>(ws + o_rlen);
     plan->r_key = reinterpret_cast<uint32_t *>(ws + o_rkey);
-    plan->d_gaf = d_gaf;
+    plan->src = src;
     plan->kt = kt;
     plan->num_sv = num_sv;
     plan->n_hits = n;
@@ -464,7 +471,7 @@ int json_plan(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, c
     if (n) {
         scatter_hits<<<blocks(n), T, 0, st>>>(d_hit_sv2, d_hit_off, d_hit_len, n, seg, cursor, s_off, s_len);
         rank_hits<<<blocks(n2 * 32), T, 0, st>>>(seg, uint32_t(n2), s_off, s_len, plan->r_off, plan->r_len, plan->r_key);
-        size_hits<<<blocks(n * 32), T, 0, st>>>(d_gaf, plan->r_off, plan->r_len, n, epos, flags);
+        size_hits<<<blocks(n * 32), T, 0, st>>>(src, plan->r_off, plan->r_len, n, epos, flags);
     }
     exclusive_scan(epos, n, tmp, st);
     size_keys<<<blocks(num_sv), T, 0, st>>>(seg, epos, kt, num_sv, kpos);
@@ -507,7 +514,7 @@ int json_render_range(const JsonPlan *plan, uint32_t sv_lo, uint32_t sv_hi, uint
     render_keys<<<blocks(uint64_t(sv_hi - sv_lo) + 1), T, 0, st>>>(plan->seg, plan->epos, plan->kpos, plan->kt, plan->num_sv, sv_lo, sv_hi,
                                                                     base, d_out);
     if (h_hi > h_lo)
-        render_hits<<<blocks((h_hi - h_lo) * 32), T, 0, st>>>(plan->d_gaf, plan->r_off, plan->r_len, plan->r_key, h_lo, h_hi, plan->seg,
+        render_hits<<<blocks((h_hi - h_lo) * 32), T, 0, st>>>(plan->src, plan->r_off, plan->r_len, plan->r_key, h_lo, h_hi, plan->seg,
                                                               plan->epos, plan->kpos, plan->kt, base, d_out);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return cuda_fail(int(le), "json_render_range: launch");
@@ -516,11 +523,11 @@ int json_render_range(const JsonPlan *plan, uint32_t sv_lo, uint32_t sv_hi, uint
 
 // Renders the whole text into *d_out (cudaMallocAsync on `st`, the caller frees it with cudaFreeAsync) from hits in
 // DEVICE memory; *out_len on the host after the call.
-int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
+int json_render_device(svjg_tables *t, const LineSrc &src, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
                        const uint32_t *d_hit_len, uint64_t n_hits, const uint32_t *d_counts, uint8_t **d_out, uint64_t *out_len,
                        cudaStream_t st) {
     JsonPlan *plan = nullptr;
-    if (int rc = json_plan(t, d_gaf, d_hit_sv2, d_hit_off, d_hit_len, n_hits, d_counts, &plan, st)) return rc;
+    if (int rc = json_plan(t, src, d_hit_sv2, d_hit_off, d_hit_len, n_hits, d_counts, &plan, st)) return rc;
     const uint64_t out_bytes = json_plan_bytes(plan);
     uint8_t *out = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&out), out_bytes, st);

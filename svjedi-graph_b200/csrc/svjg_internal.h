@@ -34,16 +34,24 @@ struct svjg_tables {
 };
 
 namespace svjg {
+// where the bytes of a file lie on the device(s): range k = file offsets [start[k], start[k + 1]) at base[k]
+// (device 0's own memory or a peer's, read over NVLink).  One range for a file resident on one device.
+constexpr int MAX_RANGES = 8;
+struct LineSrc {
+    const uint8_t *base[MAX_RANGES];
+    uint64_t start[MAX_RANGES];
+    uint32_t n;
+};
 int set_error(int code, const std::string &msg);
 int cuda_fail(int cuda_err, const char *what);   // records the message, returns SVJG_E_CUDA
 void free_host_ws(svjg_tables *t);
 void free_json_keys(svjg_tables *t);
 // informative_aln.json rendered on the device from hits in device memory (json.cu); *d_out is released with cudaFreeAsync
-int json_render_device(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
+int json_render_device(svjg_tables *t, const LineSrc &src, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off,
                        const uint32_t *d_hit_len, uint64_t n_hits, const uint32_t *d_counts, uint8_t **d_out, uint64_t *out_len,
                        cudaStream_t st);
 // the same in steps, for a text that leaves the device slice by slice (json.cu; see there)
-int json_plan(svjg_tables *t, const uint8_t *d_gaf, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off, const uint32_t *d_hit_len,
+int json_plan(svjg_tables *t, const LineSrc &src, const uint32_t *d_hit_sv2, const uint64_t *d_hit_off, const uint32_t *d_hit_len,
               uint64_t n_hits, const uint32_t *d_counts, JsonPlan **out_plan, cudaStream_t st);
 uint64_t json_plan_bytes(const JsonPlan *plan);
 uint32_t json_plan_keys(const JsonPlan *plan);

@@ -272,6 +272,57 @@ def filter_host_multi(tables_by_device, gaf, d_over=D_OVER):
     return FilterResult(counts, stats, sv2, off, ln)
 
 
+def filter_json_multi_begin(tables_by_device, gaf, d_over=D_OVER):
+    """:func:`filter_json_begin` for ONE buffer on several GPUs of the node: range k (shard.shard_cuts) is uploaded
+    to and filtered on device k (svjg_filter_json_begin_at on a thread of its own) and stays there; the hit tuples
+    are gathered on device 0 and the counters summed (svjg_filter_json_gather), so that
+    ``filter_json_finish(tables_by_device[0])`` / ``filter_json_write(tables_by_device[0], path)`` render the whole
+    text there, reading the lines of the other ranges from their devices over NVLink.  Returns the FilterResult
+    (summed counters and stats), or None where this route is not available (a range that does not fit its device,
+    no peer access): use :func:`filter_host_multi`."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import shard
+    a = _as_u8(gaf)
+    world = len(tables_by_device)
+    cuts = shard.shard_cuts(a, world)
+    num_sv = tables_by_device[0].num_sv
+
+    def one(k):
+        t = tables_by_device[k]
+        part = a[cuts[k]:cuts[k + 1]]
+        counts = np.zeros((num_sv, 2), dtype=np.uint32)
+        stats = capi.FilterStats()
+        rc = capi.lib.svjg_filter_json_begin_at(t._h, part.ctypes.data if part.size else None, int(part.size), int(cuts[k]),
+                                                int(d_over), counts.ctypes.data, C.byref(stats))
+        st = stats.as_dict()
+        if rc == capi.E_INPUT:
+            _raise_input(st)                             # err_offset is already the file's
+        if rc == capi.E_UNSUPPORTED:
+            return None
+        capi.check(rc)
+        return counts, st
+
+    with ThreadPoolExecutor(world) as pool:
+        parts = list(pool.map(one, range(world)))          # in range order: the first failure is the reference's
+    if any(p is None for p in parts):
+        return None
+    counts = np.zeros((num_sv, 2), dtype=np.uint32)
+    stats = {}
+    for c, st in parts:
+        counts += c
+        for key, v in st.items():
+            if key != "err_offset":
+                stats[key] = stats.get(key, 0) + v
+    stats["status"] = 0
+    stats["err_offset"] = parts[0][1]["err_offset"]
+    handles = (C.c_void_p * world)(*[t._h.value for t in tables_by_device])
+    rc = capi.lib.svjg_filter_json_gather(handles, world, counts.ctypes.data)
+    if rc == capi.E_UNSUPPORTED:
+        return None
+    capi.check(rc)
+    return FilterResult(counts, stats)
+
+
 def filter_json_host(tables, gaf, d_over=D_OVER, counts=None):
     """svjg_filter_json_host: the filter over GAF bytes in HOST memory with ``informative_aln.json``
     (filter-alignments.py:160-175) rendered on the device.  Returns (FilterResult without a hit list, memoryview

@@ -77,6 +77,8 @@ def _load():
         "svjg_filter_json_begin": (C.c_int, [vp, u8p, C.c_uint64, C.c_int64, u32p, C.POINTER(FilterStats)]),
         "svjg_filter_json_finish": (C.c_int, [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
         "svjg_filter_json_write": (C.c_int, [vp, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+        "svjg_filter_json_begin_at": (C.c_int, [vp, u8p, C.c_uint64, C.c_uint64, C.c_int64, u32p, C.POINTER(FilterStats)]),
+        "svjg_filter_json_gather": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, u32p]),
         "svjg_filter_tune": (C.c_int, [C.c_int, C.c_int]),
         "svjg_filter_profile": (C.c_int, [C.c_int]),
         "svjg_filter_scan_ms": (C.c_int, [C.POINTER(C.c_float)]),

@@ -102,7 +102,16 @@ def _filter_to_json(tables, gaf_file, out_json, dover_given=False, gaf=None, str
         res, gaf = alnfilter.filter_stream(tables, stream, d_over=d_over)
     elif n_gpus > 1:
         # one file, N byte ranges cut at line ends, one GPU each; counters summed, hits merged in range order
-        res = alnfilter.filter_host_multi(_replicas(tables, n_gpus), gaf, d_over=d_over)
+        # (an extension; SVJG_GPUS=N).  Each range stays on its device, the text is rendered on device 0 with the
+        # lines of the other ranges read over NVLink; without peer access: hit lists to the host, host emitter
+        replicas = _replicas(tables, n_gpus)
+        res = None if min_identity is not None else alnfilter.filter_json_multi_begin(replicas, gaf, d_over=d_over)
+        if res is None:
+            res = alnfilter.filter_host_multi(replicas, gaf, d_over=d_over)
+        elif not (dover_given and res.stats["n_checks"] > 0):
+            written = alnfilter.filter_json_write(tables, out_json)
+            if written is None:
+                res = alnfilter.filter_host_multi(replicas, gaf, d_over=d_over)
     elif min_identity is not None:
         res = alnfilter.filter_host(tables, gaf, d_over=d_over)                # the hit list on the host: it is thinned below
     else:

@@ -74,3 +74,44 @@ def test_command_line_on_two_gpus(n_dev, tmp_path):
     r = subprocess.run([sys.executable, os.path.join(PKG, "filter-alignments.py"), "-a", "bad.gaf", "-g", f"{tag}.gfa", "-p", "bad"],
                        cwd=tmp_path, env=env, capture_output=True, text=True)
     assert r.returncode == 1 and f"byte {sum(len(x) for x in lines[:k])}:" in r.stderr, r.stderr
+
+
+@pytest.mark.parametrize("tag", ["s2", "s3", "s4"])
+def test_text_rendered_on_device_0_from_all_ranges(n_dev, tag, tmp_path):
+    """filter_json_multi_begin + filter_json_finish / filter_json_write: every range stays on its device, device 0
+    renders the whole text and reads the other ranges' lines over peer access -- the reference's file."""
+    from svjg import alnfilter
+    edges, gfa = read_golden(f"{tag}_svs_edges.json.gz"), read_golden(f"{tag}.gfa.gz")
+    gaf = read_golden(f"{tag}.gaf.gz").encode()
+    t0 = alnfilter.Tables.from_memory(edges, gfa).to_device(0)
+    tables = [t0] + [t0.clone().to_device(d) for d in range(1, n_dev)]
+    want_sha = read_golden(f"{tag}_informative_aln.sha256").strip()
+    one = alnfilter.filter_host(t0, gaf)
+    res = alnfilter.filter_json_multi_begin(tables, gaf)
+    assert res is not None, "no peer access on this box?"
+    assert (res.counts == one.counts).all()
+    assert {k: v for k, v in res.stats.items() if k != "n_exact"} == {k: v for k, v in one.stats.items() if k != "n_exact"}
+    text = alnfilter.filter_json_finish(t0)
+    assert text is not None and hashlib.sha256(text).hexdigest() == want_sha
+    # again, to a file in small slices; the workspace is reused (hit arrays grown by the first gather)
+    assert alnfilter.filter_json_multi_begin(tables, gaf) is not None
+    out = tmp_path / "sliced.json"
+    n = alnfilter.filter_json_write(t0, str(out), 50_000)
+    assert n == out.stat().st_size and hashlib.sha256(out.read_bytes()).hexdigest() == want_sha
+    # a single device afterwards: the same handle renders its own file again
+    res1, text1 = alnfilter.filter_json_host(t0, gaf)
+    assert hashlib.sha256(text1).hexdigest() == want_sha
+
+
+def test_damaged_line_on_the_multi_device_json_route(n_dev):
+    from svjg import alnfilter
+    tag = "s3"
+    edges, gfa = read_golden(f"{tag}_svs_edges.json.gz"), read_golden(f"{tag}.gfa.gz")
+    lines = read_golden(f"{tag}.gaf.gz").splitlines(True)
+    k = (3 * len(lines)) // 4
+    lines[k] = "short\tline\n"
+    t0 = alnfilter.Tables.from_memory(edges, gfa).to_device(0)
+    tables = [t0, t0.clone().to_device(1)]
+    with pytest.raises(alnfilter.InputError) as exc:
+        alnfilter.filter_json_multi_begin(tables, "".join(lines).encode())
+    assert f"byte {sum(len(x) for x in lines[:k])}:" in str(exc.value)
