@@ -13,6 +13,7 @@
 #include <cstring>
 #include <fstream>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -587,24 +588,61 @@ static uint32_t pow2_at_least(uint64_t n) {
     return uint32_t(c);
 }
 
+// strings -> dense ids in the order they first appear: open addressing over the ids, the hashes kept for the
+// compares and for growing (std::unordered_map spends most of a million-SV build in its nodes)
+struct FlatIndex {
+    std::vector<uint32_t> slot;                 // id + 1, 0 = free
+    std::vector<std::string_view> keys;         // views the caller keeps alive
+    std::vector<uint64_t> hashes;
+    explicit FlatIndex(size_t expect) { slot.assign(size_t(pow2_at_least(expect * 2 + 16)), 0); }
+    static uint64_t hash(std::string_view v) {
+        uint64_t h = 0xcbf29ce484222325ull;
+        size_t i = 0;
+        for (; i + 8 <= v.size(); i += 8) {
+            uint64_t w;
+            memcpy(&w, v.data() + i, 8);
+            h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
+        }
+        uint64_t w = 0;
+        memcpy(&w, v.data() + i, v.size() - i);
+        h = (h ^ w ^ (uint64_t(v.size()) << 56)) * 0x9E3779B97F4A7C15ull;
+        return h ^ (h >> 32);
+    }
+    void grow() {
+        std::vector<uint32_t> bigger(slot.size() * 2, 0);
+        const size_t mask = bigger.size() - 1;
+        for (size_t id = 0; id < keys.size(); ++id) {
+            size_t i = size_t(hashes[id]) & mask;
+            while (bigger[i]) i = (i + 1) & mask;
+            bigger[i] = uint32_t(id) + 1;
+        }
+        slot.swap(bigger);
+    }
+    uint32_t intern(std::string_view v) {
+        const uint64_t h = hash(v);
+        size_t mask = slot.size() - 1, i = size_t(h) & mask;
+        while (slot[i]) {
+            const uint32_t id = slot[i] - 1;
+            if (hashes[id] == h && keys[id] == v) return id;
+            i = (i + 1) & mask;
+        }
+        if ((keys.size() + 1) * 2 > slot.size()) {
+            grow();
+            mask = slot.size() - 1;
+            i = size_t(h) & mask;
+            while (slot[i]) i = (i + 1) & mask;
+        }
+        slot[i] = uint32_t(keys.size()) + 1;
+        keys.push_back(v);
+        hashes.push_back(h);
+        return uint32_t(keys.size()) - 1;
+    }
+};
+
 static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pair<std::string, int64_t>> &alts,
                   std::string &err) {
     StageTimer tm;
-    // distinct sv ids, byte-sorted == the order json.dumps(sort_keys=True) prints them
-    {
-        std::unordered_set<std::string_view> distinct;      // views into keys[].ents, which outlive this block
-        for (auto &k : keys)
-            for (auto &e : k.ents)
-                if (e.second >= 0) distinct.insert(std::string_view(e.first));
-        t->sv_ids.reserve(distinct.size());
-        for (const std::string_view &v : distinct) t->sv_ids.emplace_back(v);
-        std::sort(t->sv_ids.begin(), t->sv_ids.end());
-    }
-    if (t->sv_ids.size() >= 0x7FFFFFFFull) {
-        err = "too many distinct sv ids";
-        return false;
-    }
-    tm.lap("  sv ids sorted");
     t->n_keys = uint32_t(keys.size());
     // entries on which the reference raises make skipping any probe unsafe
     for (auto &k : keys) {
@@ -613,118 +651,140 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
             if (e.second < 0) t->filter_flags |= SVJG_FLAG_EXACT_CHECKS;
     }
 
-    struct Parse {
-        uint32_t key, split;   // nL = key[0:split), sL = key[split+1], nR = key[split+3 : len-2)
-    };
-    std::vector<Parse> parses;
+    // Two halves that do not depend on each other run side by side: (1) the sv ids and the entry lists,
+    // (2) the readings of the link keys and the node names.
     std::vector<uint32_t> ent_begin(keys.size() + 1, 0);
-    for (size_t ki = 0; ki < keys.size(); ++ki) {
-        const std::string &k = keys[ki].key;
-        ent_begin[ki] = uint32_t(t->entries.size());
-        for (auto &e : keys[ki].ents) {
-            if (e.second < 0) {
-                t->entries.push_back(ENTRY_POISON);
-            } else {
-                auto it = std::lower_bound(t->sv_ids.begin(), t->sv_ids.end(), e.first);
-                t->entries.push_back(uint32_t(it - t->sv_ids.begin()) * 2 + uint32_t(e.second));
+    std::string err1;
+    std::thread sv_side([&] {
+        StageTimer tm1;
+        // distinct sv ids, byte-sorted == the order json.dumps(sort_keys=True) prints them
+        size_t n_ents = 0;
+        for (auto &k : keys) n_ents += k.ents.size();
+        FlatIndex ids(std::min<size_t>(n_ents, 1u << 20));   // views into keys[].ents, which outlive the build
+        std::vector<uint32_t> ent_id;                          // per entry: its sv id in order of first appearance
+        ent_id.reserve(n_ents);
+        for (auto &k : keys)
+            for (auto &e : k.ents) ent_id.push_back(e.second >= 0 ? ids.intern(std::string_view(e.first)) : 0u);
+        if (ids.keys.size() >= 0x7FFFFFFFull) {
+            err1 = "too many distinct sv ids";
+            return;
+        }
+        std::vector<uint32_t> order(ids.keys.size()), rank(ids.keys.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = uint32_t(i);
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ids.keys[a] < ids.keys[b]; });
+        t->sv_ids.reserve(order.size());
+        for (size_t i = 0; i < order.size(); ++i) {
+            rank[order[i]] = uint32_t(i);
+            t->sv_ids.emplace_back(ids.keys[order[i]]);
+        }
+        t->entries.reserve(n_ents + 1);
+        size_t at = 0;
+        for (size_t ki = 0; ki < keys.size(); ++ki) {
+            ent_begin[ki] = uint32_t(t->entries.size());
+            for (auto &e : keys[ki].ents) {
+                t->entries.push_back(e.second < 0 ? ENTRY_POISON : rank[ent_id[at]] * 2 + uint32_t(e.second));
+                ++at;
             }
         }
+        ent_begin[keys.size()] = uint32_t(t->entries.size());
+        tm1.lap("    (sv ids + entries)");
+    });
+
+    struct Parse {
+        uint32_t key, split;   // nL = key[0:split), sL = key[split+1], nR = key[split+3 : len-2)
+        uint32_t idl, idr;     // node ids of the two names
+    };
+    std::vector<Parse> parses;
+    for (size_t ki = 0; ki < keys.size(); ++ki) {
+        const std::string &k = keys[ki].key;
         size_t n = k.size();
         if (n < 7 || k[n - 2] != '@' || (k[n - 1] != '+' && k[n - 1] != '-')) continue;
         // every "@+@" / "@-@" with a non-empty name on both sides is a possible reading of the key
         for (size_t s = 1; s + 3 < n - 2; ++s) {
-            if (k[s] == '@' && k[s + 2] == '@' && (k[s + 1] == '+' || k[s + 1] == '-')) parses.push_back({uint32_t(ki), uint32_t(s)});
+            if (k[s] == '@' && k[s + 2] == '@' && (k[s + 1] == '+' || k[s + 1] == '-')) parses.push_back({uint32_t(ki), uint32_t(s), 0, 0});
         }
     }
-    ent_begin[keys.size()] = uint32_t(t->entries.size());
-    tm.lap("  entries + key parses");
-    if (t->entries.empty()) t->entries.push_back(ENTRY_POISON);  // never empty on the device
 
     // node names: every name a link key can be read with, plus the GFA's alt nodes
     // the views point into keys[].key and alts[].first, neither of which changes during the build
-    std::unordered_map<std::string_view, uint32_t> node_id;
+    FlatIndex node_id(keys.size() + alts.size());
     std::vector<std::pair<std::string, int64_t>> nodes;      // name, alt sequence length or -1
-    node_id.reserve(keys.size() + alts.size());
     auto intern = [&](std::string_view name) -> uint32_t {
-        auto it = node_id.find(name);
-        if (it != node_id.end()) return it->second;
-        uint32_t id = uint32_t(nodes.size());
-        node_id.emplace(name, id);
-        nodes.push_back({std::string(name), -1});
+        const uint32_t id = node_id.intern(name);
+        if (id == nodes.size()) nodes.push_back({std::string(name), -1});
         return id;
     };
     for (auto &a : alts) nodes[intern(std::string_view(a.first))].second = a.second;
 
     std::vector<uint8_t> roles;                              // per node: bit s = left node with strand s, bit 2+s = right
-    uint32_t cap = pow2_at_least(parses.size() * 2 + 2);
-    t->links.assign(cap, LinkSlot{});
+    std::string err2;
     for (auto &ps : parses) {
         const std::string &k = keys[ps.key].key;
         size_t n = k.size();
         size_t len_l = ps.split, off_r = ps.split + 3, len_r = n - 2 - off_r;
         if (len_l > 0xFFFF || len_r > 0xFFFF) {
-            err = "node name longer than 65535 bytes in svs_edges key";
-            return false;
+            err2 = "node name longer than 65535 bytes in svs_edges key";
+            break;
         }
         uint32_t sl = k[ps.split + 1] == '+', sr = k[n - 1] == '+';
         const std::string_view kv(k);
-        uint32_t idl = intern(kv.substr(0, len_l)), idr = intern(kv.substr(off_r, len_r));
+        ps.idl = intern(kv.substr(0, len_l));
+        ps.idr = intern(kv.substr(off_r, len_r));
         if (roles.size() < nodes.size()) roles.resize(nodes.size(), 0);
-        roles[idl] |= uint8_t(1u << sl);
-        roles[idr] |= uint8_t(4u << sr);
+        roles[ps.idl] |= uint8_t(1u << sl);
+        roles[ps.idr] |= uint8_t(4u << sr);
         if (nodes.size() >= 0x7FFFFFFFull) {
-            err = "too many distinct node names";
-            return false;
+            err2 = "too many distinct node names";
+            break;
         }
-        uint32_t cnt = ent_begin[ps.key + 1] - ent_begin[ps.key];
-        if (cnt >= (1u << 28)) {
-            err = "too many entries under one link key";
-            return false;
-        }
-        LinkSlot s{};
-        s.key = link_key(idl, sl, idr, sr);
-        s.val = cnt == 1 ? t->entries[ent_begin[ps.key]] : ent_begin[ps.key];
-        s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | 1u;
-        uint32_t i = link_hash(s.key) & (cap - 1);
-        while (t->links[i].meta & 1u) i = (i + 1) & (cap - 1);
-        t->links[i] = s;
     }
-    t->n_link_slots = uint32_t(parses.size());
-    tm.lap("  node interning + link table");
+    tm.lap("    (node names)");
+    sv_side.join();
+    tm.lap("  sv ids, entries | node names");
+    if (!err1.empty() || !err2.empty()) {
+        err = !err1.empty() ? err1 : err2;
+        return false;
+    }
+    if (t->entries.empty()) t->entries.push_back(ENTRY_POISON);  // never empty on the device
 
+    // the name-hash node table and the plain-node table need the nodes only: beside the link table
     t->n_alt = uint32_t(alts.size());
     t->n_nodes = uint32_t(nodes.size());
-    uint32_t ncap = pow2_at_least(nodes.size() * 2 + 2);
-    t->nodes.assign(ncap, NodeSlot{});
-    for (size_t id = 0; id < nodes.size(); ++id) {
-        const std::string &name = nodes[id].first;
-        NodeSlot s{};
-        s.hash = node_hash(hash_bytes(name.data(), name.size()));
-        s.name_off = uint32_t(t->blob.size());
-        s.name_len = uint32_t(name.size());
-        s.seq_len = nodes[id].second;
-        s.id1 = uint32_t(id) + 1;
-        // every name starts on a 4-byte boundary and is zero padded: the kernel compares words
-        t->blob.insert(t->blob.end(), name.begin(), name.end());
-        t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
-        if (t->blob.size() >= 0xFFFF0000ull) {
-            err = "node name blob exceeds 4 GiB";
-            return false;
+    std::string err3, err4;
+    std::thread name_side([&] {
+        uint32_t ncap = pow2_at_least(nodes.size() * 2 + 2);
+        t->nodes.assign(ncap, NodeSlot{});
+        for (size_t id = 0; id < nodes.size(); ++id) {
+            const std::string &name = nodes[id].first;
+            NodeSlot s{};
+            s.hash = node_hash(hash_bytes(name.data(), name.size()));
+            s.name_off = uint32_t(t->blob.size());
+            s.name_len = uint32_t(name.size());
+            s.seq_len = nodes[id].second;
+            s.id1 = uint32_t(id) + 1;
+            // every name starts on a 4-byte boundary and is zero padded: the kernel compares words
+            t->blob.insert(t->blob.end(), name.begin(), name.end());
+            t->blob.resize((t->blob.size() + 3) & ~size_t(3), 0);
+            if (t->blob.size() >= 0xFFFF0000ull) {
+                err3 = "node name blob exceeds 4 GiB";
+                return;
+            }
+            uint32_t i = uint32_t(s.hash) & (ncap - 1);
+            while (t->nodes[i].id1) i = (i + 1) & (ncap - 1);
+            t->nodes[i] = s;
         }
-        uint32_t i = uint32_t(s.hash) & (ncap - 1);
-        while (t->nodes[i].id1) i = (i + 1) & (ncap - 1);
-        t->nodes[i] = s;
-    }
-    tm.lap("  name-hash node table");
+        // pad the blob so 4-byte reads at the tail stay in bounds
+        t->blob.insert(t->blob.end(), 16, 0);
+    });
     // plain names once more under their exact key (same ids)
-    {
+    std::thread plain_side([&] {
         std::vector<PNodeSlot> plain;
         for (size_t id = 0; id < nodes.size(); ++id) {
             PNodeSlot s{};
             if (!plain_key(nodes[id].first, s)) continue;
             if (id + 1 > PN_ID_MASK) {
-                err = "too many distinct node names";
-                return false;
+                err4 = "too many distinct node names";
+                return;
             }
             s.id1 = (uint32_t(id) + 1) | (uint32_t(id < roles.size() ? roles[id] : 0) << 28);
             const int64_t sl = nodes[id].second;
@@ -738,10 +798,36 @@ static bool build(svjg_tables *t, std::vector<RawKey> &keys, std::vector<std::pa
             while (t->pnodes[i].id1) i = (i + 1) & (pcap - 1);
             t->pnodes[i] = s;
         }
+    });
+
+    std::string err5;
+    uint32_t cap = pow2_at_least(parses.size() * 2 + 2);
+    t->links.assign(cap, LinkSlot{});
+    for (auto &ps : parses) {
+        const std::string &k = keys[ps.key].key;
+        uint32_t sl = k[ps.split + 1] == '+', sr = k[k.size() - 1] == '+';
+        uint32_t cnt = ent_begin[ps.key + 1] - ent_begin[ps.key];
+        if (cnt >= (1u << 28)) {
+            err5 = "too many entries under one link key";
+            break;
+        }
+        LinkSlot s{};
+        s.key = link_key(ps.idl, sl, ps.idr, sr);
+        s.val = cnt == 1 ? t->entries[ent_begin[ps.key]] : ent_begin[ps.key];
+        s.meta = (cnt << 4) | (keys[ps.key].poison_key ? 8u : 0u) | 1u;
+        uint32_t i = link_hash(s.key) & (cap - 1);
+        while (t->links[i].meta & 1u) i = (i + 1) & (cap - 1);
+        t->links[i] = s;
     }
-    tm.lap("  plain-node table");
-    // pad the blob so 4-byte reads at the tail stay in bounds
-    t->blob.insert(t->blob.end(), 16, 0);
+    t->n_link_slots = uint32_t(parses.size());
+    name_side.join();
+    plain_side.join();
+    tm.lap("  link | name-hash | plain-node tables");
+    for (const std::string *e : {&err5, &err3, &err4})
+        if (!e->empty()) {
+            err = *e;
+            return false;
+        }
     return true;
 }
 
@@ -1038,10 +1124,15 @@ extern "C" int svjg_tables_from_memory(const char *edges_json, size_t edges_len,
     std::vector<std::pair<std::string, int64_t>> alts;
     std::string err;
     StageTimer tm;
-    if (!parse_edges(edges_json, edges_len, keys, err)) return set_error(SVJG_E_JSON, err);
-    tm.lap("svs_edges.json parse");
-    if (!scan_gfa(gfa, gfa_len, alts, err)) return set_error(SVJG_E_INPUT, err);
-    tm.lap("GFA scan");
+    // the GFA is scanned on a thread of its own while the JSON is parsed
+    std::string gfa_err;
+    bool gfa_ok = true;
+    std::thread gfa_side([&] { gfa_ok = scan_gfa(gfa, gfa_len, alts, gfa_err); });
+    const bool edges_ok = parse_edges(edges_json, edges_len, keys, err);
+    gfa_side.join();
+    if (!edges_ok) return set_error(SVJG_E_JSON, err);
+    if (!gfa_ok) return set_error(SVJG_E_INPUT, gfa_err);
+    tm.lap("svs_edges.json parse | GFA scan");
     svjg_tables *t = new svjg_tables();
     if (!build(t, keys, alts, err)) {
         delete t;
@@ -1055,8 +1146,12 @@ extern "C" int svjg_tables_from_memory(const char *edges_json, size_t edges_len,
 extern "C" int svjg_tables_load(const char *svs_edges_json_path, const char *gfa_path, svjg_tables **out) {
     if (!svs_edges_json_path || !gfa_path || !out) return set_error(SVJG_E_ARG, "svjg_tables_load: NULL argument");
     std::string edges, gfa;
-    if (!read_file(svs_edges_json_path, edges)) return set_error(SVJG_E_IO, std::string("cannot read ") + svs_edges_json_path);
-    if (!read_file(gfa_path, gfa)) return set_error(SVJG_E_IO, std::string("cannot read ") + gfa_path);
+    bool gfa_read = false;
+    std::thread gfa_side([&] { gfa_read = read_file(gfa_path, gfa); });
+    const bool edges_read = read_file(svs_edges_json_path, edges);
+    gfa_side.join();
+    if (!edges_read) return set_error(SVJG_E_IO, std::string("cannot read ") + svs_edges_json_path);
+    if (!gfa_read) return set_error(SVJG_E_IO, std::string("cannot read ") + gfa_path);
     return svjg_tables_from_memory(edges.data(), edges.size(), gfa.data(), gfa.size(), out);
 }
 
