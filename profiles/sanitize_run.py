@@ -12,3 +12,9 @@ for tag in ("c1", "s3", "s4"):
     vcf = read_golden("c1.vcf" if tag == "c1" else f"{tag}.vcf.gz")
     out, n = genotype.genotype_vcf(t, res.counts, vcf.encode())
     print(tag, res.n_hits, len(text), n)
+    # the text once more slice by slice (key ranges rendered into slices of about 20 kB)
+    import tempfile, os
+    assert alnfilter.filter_json_begin(t, gaf) is not None
+    with tempfile.TemporaryDirectory() as tmp:
+        nb = alnfilter.filter_json_write(t, os.path.join(tmp, "x.json"), 20_000)
+        assert open(os.path.join(tmp, "x.json"), "rb").read() == bytes(text) and nb == len(text)
