@@ -12,7 +12,8 @@ the genotype kernel over NVLink peer memory, or ncclAllReduce) -> genotype kerne
 `value`  alignments/s with the batch resident in HBM (CUDA events, max over ranks).
 `e2e`    the same job through the C ABI with HOST buffers: pinned GAF bytes in ->
          `informative_aln.json` bytes + `genotype.vcf` bytes out, in host memory; every copy, the JSON
-         text and the VCF text inside the timed region.  At N > 1: one such job per GPU at once.
+         text and the VCF text inside the timed region; two batches in flight (the text of batch k is copied
+         back while batch k + 1 is uploaded), `one_batch_at_a_time` beside it.  At N > 1: one such job per GPU at once.
 `--scaling strong`: ONE batch cut by bytes at line ends over the N ranks (svjg.shard.shard_cuts), the
          hits of all ranks checked against a one-GPU pass over the whole batch before timing.
 """
@@ -656,34 +657,66 @@ def main():
     out_bytes = [0, 0]
 
     from concurrent.futures import ThreadPoolExecutor
-    side_pool = ThreadPoolExecutor(1)
+    side_pool = ThreadPoolExecutor(4)
+    # two batches in flight, like a run over several samples: a second handle of the same tables (own workspace and
+    # streams) takes every other batch, so the text of batch k is rendered and copied back (D2H) and its genotypes
+    # and VCF text are made while batch k + 1 is uploaded (H2D) and filtered.  Every batch still pays all of its
+    # copies inside the timed region.
+    handles = [tables, tables.clone().to_device(dev.index)]
+    host_out2 = alnfilter.HostBuffers(tables, 16)
+    counts_of = [host_out.counts, host_out2.counts]
+    text_job, vcf_job = [None, None], [None, None]
 
-    def e2e_step():
-        # H2D in chunks + kernels; the counters come back first ...
-        res = alnfilter.filter_json_begin(tables, h_gaf, counts=host_out.counts)
-        # ... informative_aln.json is assembled on the device (:160-175) and copied back as text on a thread of its own
-        job = side_pool.submit(alnfilter.filter_json_finish, tables)
-        # ... while the counters are genotyped and genotype.vcf is written (predict-genotype.py:216-275)
-        gt, fl, ad, pl = genotype.genotype_host(res.counts, sv_idx, sv_ty)
+    def take(b):
+        """the results of the batch that used handle b last are in host memory"""
+        if text_job[b] is not None:
+            js = text_job[b].result()
+            text_job[b] = None
+            if js is None:
+                raise SystemExit("the device JSON renderer declined the synthetic batch")
+            out_bytes[0] = len(js)
+        if vcf_job[b] is not None:
+            out_bytes[1] = vcf_job[b].result()
+            vcf_job[b] = None
+
+    def vcf_of(counts):
+        # the counters are genotyped and genotype.vcf is written (predict-genotype.py:216-275)
+        gt, fl, ad, pl = genotype.genotype_host(counts, sv_idx, sv_ty)
         vt, n_gt = nvcf.format_buffer(gt, fl, ad, pl)
-        js = job.result()
-        if js is None:
-            raise SystemExit("the device JSON renderer declined the synthetic batch")
-        out_bytes[0], out_bytes[1] = len(js), vt.nbytes
+        return vt.nbytes
+
+    def e2e_step(k, overlap):
+        b = k & 1 if overlap else 0
+        take(b)                             # batch k - 2 is done before its handle and its counters are used again
+        # H2D in chunks + kernels; the counters come back first ...
+        res = alnfilter.filter_json_begin(handles[b], h_gaf, counts=counts_of[b])
+        # ... informative_aln.json is assembled on the device (:160-175) and copied back as text on a thread of its own ...
+        text_job[b] = side_pool.submit(alnfilter.filter_json_finish, handles[b])
+        # ... beside the genotypes and the VCF text
+        vcf_job[b] = side_pool.submit(vcf_of, res.counts)
+        if not overlap:
+            take(b)
         return res
 
-    for _ in range(2):
-        res = e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        res = e2e_step()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    def e2e_run(overlap):
+        for k in range(2):
+            res = e2e_step(k, overlap)
+        take(0), take(1)
+        sync_all()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            res = e2e_step(k, overlap)
+        take(0), take(1)
+        sync_all()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t[0])
+        return sec, res
+
+    e2e_serial_s, res = e2e_run(False)       # one batch at a time: the latency of a batch
+    e2e_s, res = e2e_run(True)
     h2d = n_bytes + tables.num_sv * 8 + n_sv * 5
     d2h = tables.num_sv * 8 + 64 + out_bytes[0] + n_sv * (24 + 1 + 8 + 1)        # counters, stats, the JSON text, genotypes
 
@@ -735,8 +768,12 @@ def main():
         "e2e": {"value": (n_rec * world if not strong else job_rec) * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1000 * e2e_s / Ke,
                 "json_bytes_per_step": out_bytes[0], "vcf_bytes_per_step": out_bytes[1],
+                "one_batch_at_a_time": {"value": (n_rec * world if not strong else job_rec) * Ke / e2e_serial_s, "unit": UNIT,
+                                        "ms_per_step": 1000 * e2e_serial_s / Ke},
                 "what": "svjg_filter_json_begin (pinned GAF bytes in, counters out) -> [svjg_filter_json_finish: informative_aln.json text "
-                        "rendered on the device, copied back] beside [svjg_genotype_host -> genotype.vcf text (svjg_vcf_format)], all in host memory"
+                        "rendered on the device, copied back] beside [svjg_genotype_host -> genotype.vcf text (svjg_vcf_format)], all in host memory; "
+                        "two batches in flight on two handles of the tables (the text of batch k goes back while batch k + 1 comes in); "
+                        "one_batch_at_a_time = the same steps strictly one after the other"
                         + ("; one such job per GPU at once" if world > 1 else "")},
         "collective": ("p2p-fused: counters summed inside the genotype kernel over NVLink peer memory" if xchg else
                        ("nccl all_reduce" if world > 1 else "none (one GPU)")),
