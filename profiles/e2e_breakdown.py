@@ -23,3 +23,23 @@ for rep in range(3):
     t6 = time.perf_counter()
     print(f"filter_host {1e3*(t1-t0):.1f} ms  genotype_host {1e3*(t2-t1):.1f}  vcf format {1e3*(t3-t2):.1f}  host json {1e3*(t4-t3):.1f}  ({js.nbytes} B) | "
           f"filter + device json {1e3*(t5-t4):.1f} ms ({len(text)} B)  vcf format to sink {1e3*(t6-t5):.1f}")
+
+# the halves of the pipelined end-to-end step (bench.py: two batches in flight), each alone
+def avg(fn, n=10):
+    fn(); fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    return 1e3 * (time.perf_counter() - t0) / n
+cnt = out.counts
+print(f"begin alone (upload + filter + counters back)   {avg(lambda: alnfilter.filter_json_begin(tables, h, counts=cnt)):.2f} ms")
+def both():
+    alnfilter.filter_json_begin(tables, h, counts=cnt); alnfilter.filter_json_finish(tables)
+print(f"begin + finish (text rendered, copied back)     {avg(both):.2f} ms")
+def vcf_only():
+    gt, fl, ad, pl = genotype.genotype_host(cnt, idx, ty); nvcf.format_buffer(gt, fl, ad, pl)
+print(f"genotype_host + VCF text                        {avg(vcf_only):.2f} ms")
+d = torch.empty(h.numel(), dtype=torch.uint8, device="cuda")
+print(f"plain cudaMemcpyAsync of the {h.numel() / 1e6:.0f} MB               {avg(lambda: d.copy_(h, non_blocking=True)):.2f} ms")
