@@ -8,4 +8,4 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from svjg import cli  # noqa: E402
 
 if __name__ == "__main__":
-    sys.exit(cli.filter_main())
+    cli.leave(cli.filter_main())

@@ -8,4 +8,4 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from svjg import cli  # noqa: E402
 
 if __name__ == "__main__":
-    sys.exit(cli.pipeline_main(os.path.dirname(os.path.abspath(sys.argv[0]))))
+    cli.leave(cli.pipeline_main(os.path.dirname(os.path.abspath(sys.argv[0]))))

@@ -14,6 +14,15 @@ def _die(msg):
     sys.exit(1)
 
 
+def leave(status):
+    """Ends a front-end process: every output file is closed by now, so the page-locked buffers and the CUDA
+    context are not taken down one by one (0.3 s); an exception (SystemExit from _die included) never gets here."""
+    import os
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(int(status or 0))
+
+
 def _start_device():
     """The CUDA context takes about a second to create: do it on a thread while the files are read."""
     import os
@@ -21,6 +30,8 @@ def _start_device():
     # the front-end processes use every kernel of the library and nothing else on the GPU: loading the
     # kernels with the context is 0.5 s faster than on first launch (set before the first CUDA call)
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    # the driver brings up every GPU it can see (a good 0.1 s each on an 8-GPU node): show it the ones that are used
+    os.environ.setdefault("CUDA_VISIBLE_DEVICES", ",".join(str(d) for d in range(_n_gpus())))
     from . import capi
     box = {}
 
