@@ -750,10 +750,14 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The records are read once: their lines are marked first to leave L2, which keeps the node and link tables there
+// (they are what is read again and again)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+    uint64_t once;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(once));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(once)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -837,13 +841,34 @@ __device__ __forceinline__ uint32_t dec4(uint32_t w) {
 __device__ __forceinline__ uint32_t clear_low_bytes(uint32_t w, int n) {
     return w & __funnelshift_lc(0u, 0xFFFFFFFFu, uint32_t(max(n, 0)) * 8u);
 }
+// Loads from the node and link tables: read-only, and marked last to leave L2 -- with a million SVs the tables are
+// several times the L2 and every line of them that stays saves a DRAM access; the records stream past them
+// (bulk_g2s).  A plain-node slot is one 32-byte load.
+struct Slot32 {
+    uint4 lo, hi;
+};
+__device__ __forceinline__ Slot32 ldg_slot32(const void *p) {
+    Slot32 r;
+    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_slot16(const void *p) {
+    uint64_t keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(keep));
+    return v;
+}
+
 // plain-node table: exact key -> (node id, alt sequence length)
 __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uint64_t c1, uint32_t ka, uint32_t kb,
                                            uint32_t &id, uint32_t &alt_len, uint32_t &roles) {
     uint32_t i = pnode_hash(c0, c1, ka, kb) & tb.pnode_mask;
     for (;;) {
-        const uint4 *sp = reinterpret_cast<const uint4 *>(tb.pnodes + i);
-        const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+        const Slot32 slot = ldg_slot32(tb.pnodes + i);
+        const uint4 lo = slot.lo, hi = slot.hi;
         if (!hi.z) return false;
         if (lo.x == uint32_t(c0) && lo.y == uint32_t(c0 >> 32) && lo.z == uint32_t(c1) && lo.w == uint32_t(c1 >> 32) &&
             hi.x == ka && hi.y == kb) {
@@ -985,7 +1010,7 @@ __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint
         while (__any_sync(0xFFFFFFFFu, go)) {
             if (go) {
                 i &= a.tb.link_mask;
-                sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
+                sv = ldg_slot16(a.tb.links + i);
                 match = (sv.w & 1u) && sv.x == key_lo && sv.y == key_hi;
                 go = (sv.w & 1u) && !match;
                 ++i;
@@ -1017,10 +1042,11 @@ __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint
                 }
                 atomicAdd(a.counts + sv2, 1u);
                 if (base + k < a.hit_cap) {
-                    a.hit_sv2[base + k] = sv2;
-                    if (a.hit_off64) a.hit_off64[base + k] = a.base + off;
-                    else a.hit_off[base + k] = off;
-                    a.hit_len[base + k] = len;
+                    // written once, read by another kernel much later: streaming stores (first to leave L2)
+                    __stcs(a.hit_sv2 + base + k, sv2);
+                    if (a.hit_off64) __stcs(reinterpret_cast<unsigned long long *>(a.hit_off64) + base + k, (unsigned long long)(a.base + off));
+                    else __stcs(a.hit_off + base + k, off);
+                    __stcs(a.hit_len + base + k, len);
                 }
             }
         }
