@@ -477,9 +477,13 @@ extern "C" int svjg_filter_json_gather(svjg_tables **ts, int n, const uint32_t *
         uint32_t *sv2 = nullptr, *len = nullptr;
         uint64_t *off = nullptr;
         const uint64_t cap = total + 1024;
-        SVJG_CUDA(cudaMalloc(&sv2, cap * 4));
-        SVJG_CUDA(cudaMalloc(&len, cap * 4));
-        SVJG_CUDA(cudaMalloc(&off, cap * 8));
+        cudaError_t me = cudaMalloc(&sv2, cap * 4);
+        if (me == cudaSuccess) me = cudaMalloc(&len, cap * 4);
+        if (me == cudaSuccess) me = cudaMalloc(&off, cap * 8);
+        if (me != cudaSuccess) {
+            cudaFree(sv2), cudaFree(len), cudaFree(off);        // cudaFree(NULL) is a no-op
+            return cuda_fail(int(me), "svjg_filter_json_gather: hit arrays");
+        }
         SVJG_CUDA(cudaMemcpyAsync(sv2, w0->d_hit[0], n0 * 4, cudaMemcpyDeviceToDevice, w0->s_comp));
         SVJG_CUDA(cudaMemcpyAsync(len, w0->d_hit[2], n0 * 4, cudaMemcpyDeviceToDevice, w0->s_comp));
         SVJG_CUDA(cudaMemcpyAsync(off, w0->d_off64, n0 * 8, cudaMemcpyDeviceToDevice, w0->s_comp));
