@@ -843,18 +843,9 @@ __device__ __forceinline__ uint32_t clear_low_bytes(uint32_t w, int n) {
 }
 // Loads from the node and link tables: read-only, and marked last to leave L2 -- with a million SVs the tables are
 // several times the L2 and every line of them that stays saves a DRAM access; the records stream past them
-// (bulk_g2s).  A plain-node slot is one 32-byte load.
-struct Slot32 {
-    uint4 lo, hi;
-};
-__device__ __forceinline__ Slot32 ldg_slot32(const void *p) {
-    Slot32 r;
-    asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint4 ldg_slot16(const void *p) {
+// (bulk_g2s).  (One 256-bit ld.global.nc.L2::evict_last.v8.b32 per plain-node slot would do as well, but ptxas
+// 12.9 does not survive it inside the scan kernel.)
+__device__ __forceinline__ uint4 ldg_keep(const void *p) {
     uint64_t keep;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
     uint4 v;
@@ -867,8 +858,8 @@ __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uin
                                            uint32_t &id, uint32_t &alt_len, uint32_t &roles) {
     uint32_t i = pnode_hash(c0, c1, ka, kb) & tb.pnode_mask;
     for (;;) {
-        const Slot32 slot = ldg_slot32(tb.pnodes + i);
-        const uint4 lo = slot.lo, hi = slot.hi;
+        const uint4 *sp = reinterpret_cast<const uint4 *>(tb.pnodes + i);
+        const uint4 lo = ldg_keep(sp), hi = ldg_keep(sp + 1);
         if (!hi.z) return false;
         if (lo.x == uint32_t(c0) && lo.y == uint32_t(c0 >> 32) && lo.z == uint32_t(c1) && lo.w == uint32_t(c1 >> 32) &&
             hi.x == ka && hi.y == kb) {
@@ -1010,7 +1001,7 @@ __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint
         while (__any_sync(0xFFFFFFFFu, go)) {
             if (go) {
                 i &= a.tb.link_mask;
-                sv = ldg_slot16(a.tb.links + i);
+                sv = ldg_keep(a.tb.links + i);
                 match = (sv.w & 1u) && sv.x == key_lo && sv.y == key_hi;
                 go = (sv.w & 1u) && !match;
                 ++i;
@@ -1377,11 +1368,12 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
                 }
                 const uint32_t nid = nd.nid, nlen = nd.nlen, akey = nd.akey;
                 // D: per line -- sums of the node lengths left of every node, names that repeat a start
-                // value (the first-occurrence rules :206 and :269-271 would bite: exact route), verdicts
+                // value (the first-occurrence rules :206 and :269-271 bite), verdicts
                 const uint32_t lfirst = uint32_t(lane) - idx;
                 // a repeated start value: some other lane of the line holds the same key (one MATCH)
                 const uint32_t line_lanes = low_bits(int(lcnt)) << lfirst;
-                const bool clash = (__match_any_sync(0xFFFFFFFFu, akey) & line_lanes & ~(1u << lane)) != 0;
+                const uint32_t twins = __match_any_sync(0xFFFFFFFFu, akey) & line_lanes;
+                bool clash = (twins & ~(1u << lane)) != 0;
                 // segmented inclusive scan of the lengths: a lane adds what lies `d` to its left while
                 // that is still its own line
                 uint64_t lsum = nlen;
@@ -1390,17 +1382,35 @@ __global__ void __launch_bounds__(THREADS, G::MB) scan_kernel(const __grid_const
                     const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, lsum, d);
                     if (uint32_t(d) <= idx) lsum += o;
                 }
-                const uint64_t pre = lsum - nlen;
+                // left of a link = the nodes up to and with its left node, right = from its right node on (:269-271)
+                uint64_t pre_l = lsum - nlen, pre_r = pre_l;
+                uint32_t splus = plus, sl = __shfl_up_sync(0xFFFFFFFFu, plus, 1);
+                if (__any_sync(0xFFFFFFFFu, is_tok && clash)) {
+                    // The same NAME again (a read through both ends of a breakend in one node): the reference takes
+                    // the strand of a name from its first occurrence in the path (:206) and sums the lengths up to /
+                    // from its first index (nodes.index, :269-271) -- the lane of the first twin has both (a lane
+                    // without twins is its own first).  Twins that are different names with one start value (one
+                    // may be a substring of the other) stay with the exact route.
+                    const int twin0 = is_tok ? __ffs(twins) - 1 : lane;
+                    const uint32_t f_nid = __shfl_sync(0xFFFFFFFFu, nid, twin0);
+                    const uint64_t f_sum = __shfl_sync(0xFFFFFFFFu, lsum, twin0);
+                    const uint32_t f_len = __shfl_sync(0xFFFFFFFFu, nlen, twin0);
+                    splus = __shfl_sync(0xFFFFFFFFu, plus, twin0);
+                    sl = __shfl_up_sync(0xFFFFFFFFu, splus, 1);
+                    pre_l = __shfl_up_sync(0xFFFFFFFFu, f_sum, 1);           // through the first occurrence of the left node
+                    pre_r = f_sum - f_len;                                   // in front of the first occurrence of this one
+                    clash = clash && !(nid != NO_NODE && f_nid == nid);
+                }
                 const uint32_t bad = __reduce_or_sync(0xFFFFFFFFu, (is_tok && (!nd.plain || clash)) ? (1u << own_l) : 0u);
                 const uint64_t total = __shfl_sync(0xFFFFFFFFu, lsum, is_tok ? lfirst + lcnt - 1u : 0u);
-                const uint32_t idl = __shfl_up_sync(0xFFFFFFFFu, nid, 1), sl = __shfl_up_sync(0xFFFFFFFFu, plus, 1);
+                const uint32_t idl = __shfl_up_sync(0xFFFFFFFFu, nid, 1);
                 const int64_t lts = __shfl_sync(0xFFFFFFFFu, ts, own_l), ltail = __shfl_sync(0xFFFFFFFFu, tail, own_l);
                 const uint32_t loff = wbase + (lr.x & 0xFFFFu), llen = lr.x >> 16;
-                const bool ok = (int64_t(pre) - lts >= a.d_over) && (int64_t(total - pre) - ltail >= a.d_over);
-                const uint32_t dirs = link_dirs(__shfl_up_sync(0xFFFFFFFFu, nd.roles, 1), sl, nd.roles, plus);
+                const bool ok = (int64_t(pre_l) - lts >= a.d_over) && (int64_t(total - pre_r) - ltail >= a.d_over);
+                const uint32_t dirs = link_dirs(__shfl_up_sync(0xFFFFFFFFu, nd.roles, 1), sl, nd.roles, splus);
                 const bool look = is_tok && idx >= 1 && !((bad >> own_l) & 1u) && idl != NO_NODE && nid != NO_NODE && dirs &&
                                   (ok || (a.flags & FLAG_EXACT_CHECKS));
-                probe_links(a, look, idl, sl, nid, plus, dirs, ok, loff, llen, lt_mask, n_checks);
+                probe_links(a, look, idl, sl, nid, splus, dirs, ok, loff, llen, lt_mask, n_checks);
                 if (take) {
                     if ((bad >> lane) & 1u) exact = true;
                     pend = 0;
