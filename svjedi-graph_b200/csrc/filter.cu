@@ -841,25 +841,13 @@ __device__ __forceinline__ uint32_t dec4(uint32_t w) {
 __device__ __forceinline__ uint32_t clear_low_bytes(uint32_t w, int n) {
     return w & __funnelshift_lc(0u, 0xFFFFFFFFu, uint32_t(max(n, 0)) * 8u);
 }
-// Loads from the node and link tables: read-only, and marked last to leave L2 -- with a million SVs the tables are
-// several times the L2 and every line of them that stays saves a DRAM access; the records stream past them
-// (bulk_g2s).  (One 256-bit ld.global.nc.L2::evict_last.v8.b32 per plain-node slot would do as well, but ptxas
-// 12.9 does not survive it inside the scan kernel.)
-__device__ __forceinline__ uint4 ldg_keep(const void *p) {
-    uint64_t keep;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    uint4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(keep));
-    return v;
-}
-
 // plain-node table: exact key -> (node id, alt sequence length)
 __device__ __forceinline__ bool pnode_find(const DevTables &tb, uint64_t c0, uint64_t c1, uint32_t ka, uint32_t kb,
                                            uint32_t &id, uint32_t &alt_len, uint32_t &roles) {
     uint32_t i = pnode_hash(c0, c1, ka, kb) & tb.pnode_mask;
     for (;;) {
         const uint4 *sp = reinterpret_cast<const uint4 *>(tb.pnodes + i);
-        const uint4 lo = ldg_keep(sp), hi = ldg_keep(sp + 1);
+        const uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
         if (!hi.z) return false;
         if (lo.x == uint32_t(c0) && lo.y == uint32_t(c0 >> 32) && lo.z == uint32_t(c1) && lo.w == uint32_t(c1 >> 32) &&
             hi.x == ka && hi.y == kb) {
@@ -1001,7 +989,7 @@ __device__ __forceinline__ void probe_links(const FilterArgs &a, bool want, uint
         while (__any_sync(0xFFFFFFFFu, go)) {
             if (go) {
                 i &= a.tb.link_mask;
-                sv = ldg_keep(a.tb.links + i);
+                sv = __ldg(reinterpret_cast<const uint4 *>(a.tb.links + i));
                 match = (sv.w & 1u) && sv.x == key_lo && sv.y == key_hi;
                 go = (sv.w & 1u) && !match;
                 ++i;
