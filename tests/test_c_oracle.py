@@ -6,12 +6,13 @@ import importlib.util
 import io
 import json
 import os
+import re
 import subprocess
 
 import numpy as np
 import pytest
 
-from conftest import ROOT, alt_len_from_gfa_text, read_golden
+from conftest import ROOT, alt_len_from_gfa_text, read_golden, revisit_walks
 from oracle import svjg_oracle as O
 
 
@@ -147,3 +148,15 @@ def test_full_c2_batch_has_the_counts_the_gpu_reported(CO):
     assert len(gaf) == 512_635_132                              # gaf_bytes_per_gpu of that run
     assert stats == {"n_hits": 1_108_909, "n_records": 3_000_000, "n_multi": 789_043}
     assert int(counts.sum()) == 1_108_909
+
+
+def test_paths_that_revisit_nodes_equal_the_python_oracle(CO):
+    """conftest.revisit_walks: the C restatement (the checker of the full-size GPU tests, where such paths are
+    resolved in the fast route) against the line-by-line Python restatement."""
+    edges, lines = revisit_walks()
+    want = O.filter_alignments(lines, edges, {})
+    assert sum(len(v[0]) + len(v[1]) for v in want.values()) > 500
+    assert sum(len(set(re.findall(r"chr7:\d+-\d+", l.split("\t")[5]))) < l.split("\t")[5].count("chr7") for l in lines) > 300
+    t = CO.Tables(edges, {})
+    d, counts, stats = _informative(CO, t, "".join(lines).encode())
+    assert d == want

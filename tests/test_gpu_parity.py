@@ -384,6 +384,29 @@ def test_long_paths(gpu):
     assert res2.stats["n_generic"] == 1 and res2.stats["n_multi"] == 4
 
 
+def test_paths_that_revisit_nodes(gpu):
+    """conftest.revisit_walks: names that come twice in a path (loops, `>A>A`, `>A<A`) are resolved in the ordinary
+    rounds from the lane of their first occurrence -- counters and the stored lines equal the oracle's, and no
+    such line needs the general routine; with the general routine forced the result is the same."""
+    from conftest import revisit_walks
+    alnfilter, capi, genotype, torch = gpu
+    edges, lines = revisit_walks()
+    gaf = "".join(lines).encode()
+    want = O.filter_alignments(lines, edges, {})
+    t = alnfilter.Tables.from_memory(json.dumps(edges), "").to_device(0)
+    res = alnfilter.filter_host(t, gaf)
+    assert _counts_dict(t, res.counts) == {k: list(v) for k, v in O.hit_counts(want).items()}
+    got = {}
+    order = np.lexsort((res.hit_sv2, res.hit_off))
+    for s2, o, n in zip(res.hit_sv2[order].tolist(), res.hit_off[order].tolist(), res.hit_len[order].tolist()):
+        got.setdefault(t.sv_ids[s2 >> 1], [[], []])[s2 & 1].append(O.kept_text(gaf[o:o + n].decode()))
+    assert {k: [sorted(v[0]), sorted(v[1])] for k, v in got.items()} == {k: [sorted(v[0]), sorted(v[1])] for k, v in want.items()}
+    assert res.stats["n_generic"] == 0 and res.stats["n_multi"] == len(lines)
+    t.set_flags(capi.FLAG_FORCE_GENERAL)
+    gen = alnfilter.filter_host(t, gaf)
+    assert (gen.counts == res.counts).all() and gen.stats["n_generic"] == gen.stats["n_multi"] == len(lines)
+
+
 @pytest.mark.parametrize("tile", [1024, 1600, 3072, 5024])
 def test_every_tile_size_gives_the_same_result(gpu, tile):
     """The probe kernel picks the bytes per tile from the line length; any tile size must give the
