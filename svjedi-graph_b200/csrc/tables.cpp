@@ -306,7 +306,191 @@ struct RawKey {
     std::vector<std::pair<std::string, int>> ents;  // allele -1 = poison entry
 };
 
+// one member of the top-level object: "nL@sL@nR@sR": [["sv id", allele], ...]   (in.p at the opening quote of the key)
+static bool parse_member(JsonIn &in, RawKey &rk) {
+    if (!in.string(rk.key)) return false;
+    in.ws();
+    if (in.p >= in.end || *in.p != ':') {
+        in.fail("expected ':'");
+        return false;
+    }
+    ++in.p;
+    in.ws();
+    if (in.p < in.end && *in.p == '[') {
+        ++in.p;
+        in.ws();
+        if (in.p < in.end && *in.p == ']') {
+            ++in.p;
+        } else {
+            for (;;) {
+                in.ws();
+                // one entry: [ "sv id", allele ]
+                if (in.p < in.end && *in.p == '[') {
+                    ++in.p;
+                    int n_el = 0;
+                    std::string sv;
+                    bool sv_is_str = false;
+                    int allele = -1;
+                    in.ws();
+                    if (in.p < in.end && *in.p == ']') {
+                        ++in.p;
+                    } else {
+                        for (;;) {
+                            JsonIn::Kind kind;
+                            long long iv = 0;
+                            std::string sval;
+                            if (!in.skip_value(kind, &iv, &sval)) break;
+                            if (n_el == 0 && kind == JsonIn::K_STRING) {
+                                sv_is_str = true;
+                                sv.swap(sval);
+                            }
+                            if (n_el == 1) {
+                                // list index semantics of Python: 0,1,-1,-2 and bools are valid
+                                if (kind == JsonIn::K_INT) {
+                                    if (iv == 0 || iv == -2) allele = 0;
+                                    else if (iv == 1 || iv == -1) allele = 1;
+                                } else if (kind == JsonIn::K_TRUE) allele = 1;
+                                else if (kind == JsonIn::K_FALSE) allele = 0;
+                            }
+                            ++n_el;
+                            in.ws();
+                            if (in.p < in.end && *in.p == ',') {
+                                ++in.p;
+                                continue;
+                            }
+                            if (in.p < in.end && *in.p == ']') {
+                                ++in.p;
+                                break;
+                            }
+                            in.fail("expected ',' or ']'");
+                            break;
+                        }
+                    }
+                    if (!in.err.empty()) break;
+                    if (n_el != 2) rk.poison_key = true;  // tuple unpack raises as soon as the key is found
+                    else if (!sv_is_str || sv.find(':') == std::string::npos) rk.ents.push_back({std::string(), -1});
+                    else rk.ents.push_back({sv, allele});
+                } else {
+                    JsonIn::Kind kind;
+                    if (!in.skip_value(kind)) break;
+                    // a 2-character string would unpack; everything else raises
+                    rk.poison_key = true;
+                }
+                in.ws();
+                if (in.p < in.end && *in.p == ',') {
+                    ++in.p;
+                    continue;
+                }
+                if (in.p < in.end && *in.p == ']') {
+                    ++in.p;
+                    break;
+                }
+                in.fail("expected ',' or ']'");
+                break;
+            }
+        }
+    } else {
+        JsonIn::Kind kind;
+        if (!in.skip_value(kind)) return false;
+        rk.poison_key = true;
+    }
+    return in.err.empty();
+}
+
+// json.dumps(sort_keys=True) wrote the keys in ascending order: no key can repeat while that holds, and the
+// dictionary of seen keys is only built once it stops holding.  Duplicate keys: the last one wins (dict).
+struct KeySink {
+    std::vector<RawKey> &keys;
+    std::unordered_map<std::string, size_t> seen;
+    bool ascending = true;
+    void add(RawKey &&rk) {
+        if (ascending && (keys.empty() || keys.back().key < rk.key)) {
+            keys.push_back(std::move(rk));
+            return;
+        }
+        if (ascending) {
+            ascending = false;
+            for (size_t i = 0; i < keys.size(); ++i) seen.emplace(keys[i].key, i);
+        }
+        auto it = seen.find(rk.key);
+        if (it == seen.end()) {
+            seen.emplace(rk.key, keys.size());
+            keys.push_back(std::move(rk));
+        } else {
+            keys[it->second] = std::move(rk);
+        }
+    }
+};
+
+// The file as json.dumps(indent=4) writes it (construct-graph.py:554) has every top-level member start with
+// "\n    \"" -- a raw line feed cannot occur inside a JSON string, deeper levels are indented further -- so a large
+// file is cut there into pieces that are parsed side by side.  A piece must consist of whole members, each
+// followed by a comma (the last piece by the closing brace and nothing else): if every piece does, the cuts were
+// member boundaries and the pieces together are the sequential parse.  Anything else (another layout, a damaged
+// file): false, and the sequential parser decides and reports.
+static bool parse_edges_pieces(const char *text, size_t len, std::vector<RawKey> &keys) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t n_pieces = std::min<size_t>(std::min<unsigned>(hw ? hw : 1u, 8u), len >> 24);      // >= 16 MiB each
+    if (n_pieces < 2) return false;
+    JsonIn head{text, text + len, {}};
+    head.ws();
+    if (head.p >= head.end || *head.p != '{') return false;
+    ++head.p;
+    head.ws();
+    if (head.p >= head.end || *head.p != '"') return false;
+    std::vector<const char *> cut{head.p};
+    static const char mark[] = "\n    \"";
+    for (size_t k = 1; k < n_pieces; ++k) {
+        const char *from = std::max(cut.back(), text + len / n_pieces * k);
+        const void *hit = memmem(from, size_t(text + len - from), mark, 6);
+        if (!hit) break;
+        const char *q = static_cast<const char *>(hit) + 5;
+        if (q > cut.back()) cut.push_back(q);
+    }
+    cut.push_back(text + len);
+    const size_t n = cut.size() - 1;
+    if (n < 2) return false;
+    std::vector<std::vector<RawKey>> part(n);
+    std::vector<char> ok(n, 0);
+    std::vector<std::thread> pool;
+    for (size_t k = 0; k < n; ++k)
+        pool.emplace_back([&, k] {
+            JsonIn in{cut[k], cut[k + 1], {}};
+            const bool last = k + 1 == n;
+            for (;;) {
+                RawKey rk;
+                if (!parse_member(in, rk)) return;
+                part[k].push_back(std::move(rk));
+                in.ws();
+                if (in.p < in.end && *in.p == ',') {
+                    ++in.p;
+                    in.ws();
+                    if (in.p == in.end) {            // the piece ends behind a comma: fine unless it is the last one
+                        ok[k] = !last;
+                        return;
+                    }
+                    continue;
+                }
+                if (last && in.p < in.end && *in.p == '}') {
+                    ++in.p;
+                    in.ws();
+                    ok[k] = in.p == in.end;
+                }
+                return;
+            }
+        });
+    for (auto &t : pool) t.join();
+    for (size_t k = 0; k < n; ++k)
+        if (!ok[k]) return false;
+    KeySink sink{keys, {}, true};
+    for (auto &v : part)
+        for (auto &rk : v) sink.add(std::move(rk));
+    return true;
+}
+
 static bool parse_edges(const char *text, size_t len, std::vector<RawKey> &keys, std::string &err) {
+    if (parse_edges_pieces(text, len, keys)) return true;
+    keys.clear();
     JsonIn in{text, text + len, {}};
     // json.load() accepts a UTF-8 BOM-less document; skip leading whitespace
     in.ws();
@@ -315,8 +499,7 @@ static bool parse_edges(const char *text, size_t len, std::vector<RawKey> &keys,
         return false;
     }
     ++in.p;
-    std::unordered_map<std::string, size_t> seen;  // duplicate keys: the last one wins (dict)
-    bool ascending = true;
+    KeySink sink{keys, {}, true};
     in.ws();
     if (in.p < in.end && *in.p == '}') {
         ++in.p;
@@ -324,110 +507,8 @@ static bool parse_edges(const char *text, size_t len, std::vector<RawKey> &keys,
         for (;;) {
             in.ws();
             RawKey rk;
-            if (!in.string(rk.key)) break;
-            in.ws();
-            if (in.p >= in.end || *in.p != ':') {
-                in.fail("expected ':'");
-                break;
-            }
-            ++in.p;
-            in.ws();
-            if (in.p < in.end && *in.p == '[') {
-                ++in.p;
-                in.ws();
-                if (in.p < in.end && *in.p == ']') {
-                    ++in.p;
-                } else {
-                    for (;;) {
-                        in.ws();
-                        // one entry: [ "sv id", allele ]
-                        if (in.p < in.end && *in.p == '[') {
-                            ++in.p;
-                            int n_el = 0;
-                            std::string sv;
-                            bool sv_is_str = false;
-                            int allele = -1;
-                            in.ws();
-                            if (in.p < in.end && *in.p == ']') {
-                                ++in.p;
-                            } else {
-                                for (;;) {
-                                    JsonIn::Kind kind;
-                                    long long iv = 0;
-                                    std::string sval;
-                                    if (!in.skip_value(kind, &iv, &sval)) break;
-                                    if (n_el == 0 && kind == JsonIn::K_STRING) {
-                                        sv_is_str = true;
-                                        sv.swap(sval);
-                                    }
-                                    if (n_el == 1) {
-                                        // list index semantics of Python: 0,1,-1,-2 and bools are valid
-                                        if (kind == JsonIn::K_INT) {
-                                            if (iv == 0 || iv == -2) allele = 0;
-                                            else if (iv == 1 || iv == -1) allele = 1;
-                                        } else if (kind == JsonIn::K_TRUE) allele = 1;
-                                        else if (kind == JsonIn::K_FALSE) allele = 0;
-                                    }
-                                    ++n_el;
-                                    in.ws();
-                                    if (in.p < in.end && *in.p == ',') {
-                                        ++in.p;
-                                        continue;
-                                    }
-                                    if (in.p < in.end && *in.p == ']') {
-                                        ++in.p;
-                                        break;
-                                    }
-                                    in.fail("expected ',' or ']'");
-                                    break;
-                                }
-                            }
-                            if (!in.err.empty()) break;
-                            if (n_el != 2) rk.poison_key = true;  // tuple unpack raises as soon as the key is found
-                            else if (!sv_is_str || sv.find(':') == std::string::npos) rk.ents.push_back({std::string(), -1});
-                            else rk.ents.push_back({sv, allele});
-                        } else {
-                            JsonIn::Kind kind;
-                            if (!in.skip_value(kind)) break;
-                            // a 2-character string would unpack; everything else raises
-                            rk.poison_key = true;
-                        }
-                        in.ws();
-                        if (in.p < in.end && *in.p == ',') {
-                            ++in.p;
-                            continue;
-                        }
-                        if (in.p < in.end && *in.p == ']') {
-                            ++in.p;
-                            break;
-                        }
-                        in.fail("expected ',' or ']'");
-                        break;
-                    }
-                }
-            } else {
-                JsonIn::Kind kind;
-                if (!in.skip_value(kind)) break;
-                rk.poison_key = true;
-            }
-            if (!in.err.empty()) break;
-            // json.dumps(sort_keys=True) wrote the keys in ascending order: no key can repeat while that holds,
-            // and the dictionary of seen keys is only built once it stops holding
-            if (ascending && (keys.empty() || keys.back().key < rk.key)) {
-                keys.push_back(std::move(rk));
-            } else {
-                if (ascending) {
-                    ascending = false;
-                    for (size_t i = 0; i < keys.size(); ++i) seen.emplace(keys[i].key, i);
-                }
-                auto it = seen.find(rk.key);
-                if (it == seen.end()) {
-                    seen.emplace(rk.key, keys.size());
-                    keys.push_back(std::move(rk));
-                } else {
-                    keys[it->second] = std::move(rk);
-                }
-            }
+            if (!parse_member(in, rk)) break;
+            sink.add(std::move(rk));
             in.ws();
             if (in.p < in.end && *in.p == ',') {
                 ++in.p;

@@ -161,3 +161,44 @@ def test_table_images_are_reproducible(quirks):
     a = alnfilter.Tables.from_memory('{"a:1-2@+@a:3-4@+": [["a:X", 0]], "b:1-2@+@b:3-4@+": [["b:Y", 1]], "a:1-2@+@a:3-4@+": [["a:Z", 1]]}', "")
     b = alnfilter.Tables.from_memory('{"a:1-2@+@a:3-4@+": [["a:Z", 1]], "b:1-2@+@b:3-4@+": [["b:Y", 1]]}', "")
     assert a.image_hash == b.image_hash and a.sv_ids == ["a:Z", "b:Y"]
+
+
+def test_large_link_table_parsed_in_pieces_equals_the_sequential_parse():
+    """A svs_edges.json beyond 32 MiB in the layout construct-graph.py:554 writes (json.dumps(indent=4)) is cut at
+    top-level members and parsed side by side (csrc/tables.cpp: parse_edges_pieces); the same dictionary in any
+    other layout goes through the sequential parser.  Same tables either way; a misleading line in the layout, a
+    duplicate key across the cut and a damaged file fall back to the sequential parser and its verdict."""
+    import os
+    from svjg import alnfilter, capi
+    if (os.cpu_count() or 1) < 2 or len(os.sched_getaffinity(0)) < 2:
+        pytest.skip("one CPU: every file is parsed sequentially")
+    n = 230_000
+    d = {}
+    for i in range(n):
+        a, b = f"chr{i % 22 + 1}:{i * 100 + 1}-{i * 100 + 100}", f"chr{i % 22 + 1}:{i * 100 + 101}-{i * 100 + 200}"
+        d[f"{a}@+@{b}@+"] = [[f"chr{i % 22 + 1}:DEL-{i * 100 + 100}-{i * 100 + 190}", i & 1]]
+        if i % 7 == 0:
+            d[f"{a}@+@{b}@+"].append([f"chr{i % 22 + 1}:INS-{i * 100 + 100}-1", 1])
+    pretty = json.dumps(d, sort_keys=True, indent=4)
+    compact = json.dumps(d, sort_keys=True)
+    assert len(pretty) > (33 << 20) and "\n    \"" in pretty and "\n    \"" not in compact
+    want = alnfilter.Tables.from_memory(compact, "")
+    got = alnfilter.Tables.from_memory(pretty, "")
+    assert got.image_hash == want.image_hash and got.num_links == want.num_links == n and got.sv_ids == want.sv_ids
+    # a nested line dressed up as a top-level member start: valid JSON, same dictionary
+    k = pretty.index("\n            \"chr", len(pretty) // 2)
+    trap = pretty[:k] + "\n    \"" + pretty[k + len("\n            \""):]
+    assert json.loads(trap) == d
+    assert alnfilter.Tables.from_memory(trap, "").image_hash == want.image_hash
+    # the first key once more at the very end (the last one wins, as in a dict): across the pieces
+    first_key = min(d)
+    dup = pretty[:pretty.rindex("\n}")] + ",\n    " + json.dumps(first_key) + ": [\n        [\n            \"chr1:DEL-7-77\",\n            1\n        ]\n    ]\n}"
+    d2 = json.loads(dup)
+    assert d2[first_key] == [["chr1:DEL-7-77", 1]]
+    assert alnfilter.Tables.from_memory(dup, "").image_hash == alnfilter.Tables.from_memory(json.dumps(d2, sort_keys=True), "").image_hash
+    # damaged in the second half: the sequential parser's error
+    cut = pretty[: (len(pretty) * 3) // 4]
+    with pytest.raises(capi.SvjgError):
+        alnfilter.Tables.from_memory(cut, "")
+    with pytest.raises(capi.SvjgError):
+        alnfilter.Tables.from_memory(pretty + " x", "")
